@@ -1,0 +1,125 @@
+/* troy_b200 — C ABI of the B200-native RNS polynomial engine behind the troy (troyn::) API.
+ *
+ * The reference (lightbulb128/troy) has no FFI: its boundary is the troyn:: C++ classes and, underneath, the free
+ * functions of namespace troy::kernel_util plus RNSToolCuda / GaloisToolCuda methods. This header cuts
+ * the boundary exactly at that seam. Every entry point names the reference interface it replaces (file:line under
+ * /root/reference). Plain pointers and sizes only; all `d_` pointers are device pointers on the context's GPU;
+ * `stream` is a cudaStream_t passed as void* (NULL = default stream). Every function returns 0 on success or a
+ * TROYB_E_* code; troyb_last_error() gives the message (the C++ shim maps codes to the reference's exception types).
+ *
+ * Layouts (identical to the reference):
+ *   ciphertext      [poly][limb][coeff] uint64, limb count = level's coeff_modulus size   src/ciphertext_cuda.cuh:62-67
+ *   batch           `batch` ciphertexts `*_stride` words apart (stride >= size*L*N); batch = 1 is the reference call
+ *   key-switch key  [digit j][component k<2][key limb][coeff], NTT form at the key level   src/kswitchkeys_cuda.cuh:43-56,366
+ * Levels: level 0 = first (data) level = all coeff primes but the special one; level l drops l more primes
+ * (src/context.cpp:470-524). Key level = level 0 primes + special prime.
+ */
+#ifndef TROY_B200_H
+#define TROY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TROYB_OK 0
+#define TROYB_E_INVALID_ARGUMENT 1 /* std::invalid_argument in the reference */
+#define TROYB_E_LOGIC 2            /* std::logic_error */
+#define TROYB_E_OUT_OF_RANGE 3     /* std::out_of_range */
+#define TROYB_E_CUDA 4             /* std::runtime_error("CUDA error.")  src/kernelprovider.cuh:6-14 */
+#define TROYB_E_NOT_INITIALIZED 5  /* std::invalid_argument("KernelProvider not initialized.")  src/kernelprovider.cuh:24-27 */
+
+#define TROYB_SCHEME_BFV 1
+#define TROYB_SCHEME_CKKS 2
+#define TROYB_SCHEME_BGV 3
+
+typedef struct troyb_context troyb_context;
+
+const char *troyb_last_error(void);
+
+/* KernelProvider::initialize()  src/kernelprovider.cuh:29-33  (device index added; the reference hard-codes 0) */
+int troyb_initialize(int device);
+int troyb_initialized(void);
+
+/* KernelProvider::malloc / free / copy / retrieve / memset  src/kernelprovider.cuh:35-83 (stream-ordered) */
+int troyb_malloc(void **d_ptr, size_t bytes, void *stream);
+int troyb_free(void *d_ptr, void *stream);
+int troyb_copy_to_device(void *d_dst, const void *h_src, size_t bytes, void *stream);
+int troyb_copy_to_host(void *h_dst, const void *d_src, size_t bytes, void *stream);
+int troyb_copy_on_device(void *d_dst, const void *d_src, size_t bytes, void *stream);
+int troyb_memset_zero(void *d_ptr, size_t bytes, void *stream);
+int troyb_stream_synchronize(void *stream);
+
+/* SEALContextCuda(EncryptionParameters, expand_mod_chain, SecurityLevel)  src/context_cuda.cuh:146-156, src/context_cuda.cu:5-62
+ * Builds every NTT table / RNS constant on the host and uploads it once. Security level is not enforced (none). */
+int troyb_context_create(int scheme, uint64_t poly_modulus_degree, const uint64_t *coeff_moduli, int n_moduli,
+                         uint64_t plain_modulus, int expand_mod_chain, troyb_context **out);
+void troyb_context_destroy(troyb_context *ctx);
+int troyb_context_scheme(const troyb_context *ctx);
+uint64_t troyb_context_poly_degree(const troyb_context *ctx);
+int troyb_context_num_levels(const troyb_context *ctx);           /* data levels in the chain */
+int troyb_context_level_limbs(const troyb_context *ctx, int level); /* level = -1: key level */
+int troyb_context_level_moduli(const troyb_context *ctx, int level, uint64_t *out);
+int troyb_context_using_keyswitching(const troyb_context *ctx);   /* SEALContext::using_keyswitching */
+int troyb_context_total_coeff_bits(const troyb_context *ctx, int level); /* ContextData::totalCoeffModulusBitCount */
+uint64_t troyb_context_plain_modulus(const troyb_context *ctx);
+/* BEHZ auxiliary base of a BFV level (RNSTool::baseBsk, src/utils/rns.h:246): returns |Bsk|, writes the primes */
+int troyb_context_bsk(const troyb_context *ctx, int level, uint64_t *out);
+/* NTTTablesCuda root powers of one key-level modulus, N pairs {operand, quotient}  src/utils/ntt_cuda.cuh:15-102 */
+int troyb_context_root_powers(const troyb_context *ctx, int key_limb, uint64_t *h_out);
+
+/* kernel_util::kNttNegacyclicHarvey / kInverseNttNegacyclicHarvey  src/kernelutils.cuh:578-632
+ * In-place transform of n_polys polynomials of the level's L limbs each, [n_polys][L][N]; canonical output. */
+int troyb_ntt_forward(troyb_context *ctx, int level, uint64_t *d_data, size_t n_polys, void *stream);
+int troyb_ntt_inverse(troyb_context *ctx, int level, uint64_t *d_data, size_t n_polys, void *stream);
+/* Same over the key-level base (level limbs + special prime): used for key material and tests. */
+int troyb_ntt_forward_key(troyb_context *ctx, uint64_t *d_data, size_t n_polys, void *stream);
+int troyb_ntt_inverse_key(troyb_context *ctx, uint64_t *d_data, size_t n_polys, void *stream);
+
+/* kAddPolyCoeffmod / kSubPolyCoeffmod / kNegatePolyCoeffmod  src/kernelutils.cu:48,524,318
+ * (EvaluatorCuda::addInplace / subInplace / negateInplace, src/evaluator_cuda.cu:143-260). n_polys = batch*size. */
+int troyb_add(troyb_context *ctx, int level, const uint64_t *d_a, const uint64_t *d_b, uint64_t *d_out, size_t n_polys, void *stream);
+int troyb_sub(troyb_context *ctx, int level, const uint64_t *d_a, const uint64_t *d_b, uint64_t *d_out, size_t n_polys, void *stream);
+int troyb_negate(troyb_context *ctx, int level, const uint64_t *d_a, uint64_t *d_out, size_t n_polys, void *stream);
+
+/* EvaluatorCuda::multiplyInplace → ckksMultiply / bgvMultiply / bfvMultiply  src/evaluator_cuda.cu:262-523
+ * (squareInplace :525-701 is the same call with d_b = d_a). Inputs a: a_size polys, b: b_size polys; output
+ * a_size+b_size-1 polys. d_out may alias d_a (in-place, as the reference does after resize).
+ * CKKS operands are NTT form; BFV/BGV operands are coefficient form. */
+int troyb_multiply(troyb_context *ctx, int level, const uint64_t *d_a, size_t a_size, size_t a_stride,
+                   const uint64_t *d_b, size_t b_size, size_t b_stride, uint64_t *d_out, size_t out_stride,
+                   size_t batch, void *stream);
+
+/* EvaluatorCuda::switchKeyInplace  src/evaluator_cuda.cu:1163-1378 (+ gSwitchKeyInplaceUtilA–G :1012-1161)
+ * ct: [2][L][N] updated in place (the switched polynomial is ADDED into c0, c1); target: [L][N];
+ * d_key: one key-switching key [Ltop digits][2][Ltop+1][N] (keys[key_index] of RelinKeys/GaloisKeys).
+ * d_target must not alias d_ct. */
+int troyb_switch_key(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_stride, const uint64_t *d_target,
+                     size_t target_stride, const uint64_t *d_key, size_t batch, void *stream);
+
+/* EvaluatorCuda::relinearizeInternal, size 3 → 2  src/evaluator_cuda.cu:703-747: key-switch of poly 2 into polys 0,1 */
+int troyb_relinearize(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_stride, const uint64_t *d_relin_key,
+                      size_t batch, void *stream);
+
+/* GaloisToolCuda::applyGalois / applyGaloisNtt  src/utils/galois_cuda.cu:166-215 — permutation only, n_polys polys */
+int troyb_galois_permute(troyb_context *ctx, int level, const uint64_t *d_in, uint64_t *d_out, size_t n_polys,
+                         uint32_t galois_elt, int ntt_form, void *stream);
+/* GaloisToolCuda::getEltFromStep  src/utils/galois_cuda.cu:44-62 (steps = 0 → column rotation / conjugation element) */
+int troyb_galois_elt_from_step(const troyb_context *ctx, int step, uint32_t *out);
+
+/* EvaluatorCuda::applyGaloisInplace  src/evaluator_cuda.cu:2024-2117: permute c0, c1 by X→X^elt, then key-switch c1.
+ * d_key = GaloisKeys key for this element (index (elt-1)/2). */
+int troyb_apply_galois(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_stride, uint32_t galois_elt,
+                       const uint64_t *d_key, size_t batch, void *stream);
+
+/* EvaluatorCuda::modSwitchScaleToNext  src/evaluator_cuda.cu:749-825 (rescaleToNext :1380 for CKKS, modSwitchToNext for
+ * BFV/BGV): drops the level's last prime with rounding. in: [size][L][N] at `level`, out: [size][L-1][N] at level+1. */
+int troyb_mod_switch_scale_to_next(troyb_context *ctx, int level, const uint64_t *d_in, size_t in_stride, uint64_t *d_out,
+                                   size_t out_stride, size_t size, size_t batch, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TROY_B200_H */

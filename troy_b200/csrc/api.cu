@@ -1,0 +1,710 @@
+// C ABI of troy_b200 (include/troy_b200.h): argument checks, scratch management and kernel orchestration.
+// The host control flow restates the reference's evaluator methods (cited per function); the kernels do not.
+#include "../../include/troy_b200.h"
+#include "context.h"
+#include "kernels_elt.cuh"
+#include "kernels_ntt.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+using namespace troyb;
+
+struct troyb_context {
+    Context *impl;
+};
+
+namespace {
+
+thread_local std::string g_error;
+bool g_initialized = false;
+int g_device = 0;
+
+struct CudaError : std::runtime_error {
+    explicit CudaError(cudaError_t e) : std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e)) {}
+};
+
+inline void ck(cudaError_t e) {
+    if (e != cudaSuccess) throw CudaError(e);
+}
+
+int fail(int code, const std::string &msg) {
+    g_error = msg;
+    return code;
+}
+
+#define API_BEGIN try {
+#define API_END                                                                                       \
+    return TROYB_OK;                                                                                  \
+    }                                                                                                 \
+    catch (const CudaError &e) { return fail(TROYB_E_CUDA, e.what()); }                               \
+    catch (const std::invalid_argument &e) { return fail(TROYB_E_INVALID_ARGUMENT, e.what()); }       \
+    catch (const std::out_of_range &e) { return fail(TROYB_E_OUT_OF_RANGE, e.what()); }               \
+    catch (const std::logic_error &e) { return fail(TROYB_E_LOGIC, e.what()); }                       \
+    catch (const std::exception &e) { return fail(TROYB_E_CUDA, e.what()); }
+
+void need_init() {
+    if (!g_initialized) throw std::invalid_argument("KernelProvider not initialized.");
+}
+
+inline cudaStream_t S(void *s) { return static_cast<cudaStream_t>(s); }
+
+// Stream-ordered scratch buffer (RAII).
+struct Scratch {
+    u64 *p = nullptr;
+    cudaStream_t s;
+    Scratch(size_t words, cudaStream_t stream) : s(stream) {
+        if (words) ck(cudaMallocAsync(reinterpret_cast<void **>(&p), words * sizeof(u64), s));
+    }
+    ~Scratch() {
+        if (p) cudaFreeAsync(p, s);
+    }
+    Scratch(const Scratch &) = delete;
+    Scratch &operator=(const Scratch &) = delete;
+};
+
+Context *C(troyb_context *c) {
+    if (!c || !c->impl) throw std::invalid_argument("context is null");
+    return c->impl;
+}
+const Context *C(const troyb_context *c) {
+    if (!c || !c->impl) throw std::invalid_argument("context is null");
+    return c->impl;
+}
+
+int level_limbs(const Context *ctx, int level) {
+    if (level == -1) return ctx->Ltop + (ctx->has_special ? 1 : 0);
+    if (level < 0 || level >= (int)ctx->levels.size()) throw std::invalid_argument("level is not valid for encryption parameters");
+    return ctx->levels[level].L;
+}
+
+u32 grid_for(u64 total, int threads) { return (u32)((total + threads - 1) / threads); }
+
+// ---- NTT dispatch --------------------------------------------------------------------------------------------------
+size_t tile_smem(int logt) { return (size_t)padded_words(1u << logt) * sizeof(u64); }
+
+void run_fwd(const Context *ctx, NttArgs a, u32 units, cudaStream_t s) {
+    a.logN = ctx->logN;
+    a.mods = ctx->d_mods;
+    a.row_pass = 0;
+    const int logN = ctx->logN;
+    if (logN < 12) {
+        ck(launch_cta(NttFwd<0>{a}, units, (size_t)ctx->N * sizeof(u64), s));
+    } else if (logN == 12) {
+        ck(launch_cta(NttFwd<12>{a}, units, tile_smem(12), s));
+    } else if (logN == 13) {
+        ck(launch_cta(NttFwd<13>{a}, units, tile_smem(13), s));
+    } else if (logN == 14) {
+        ck(launch_cta(NttFwd<14>{a}, units, tile_smem(14), s));
+    } else {
+        // four-step: strided column pass (layers 0..logN-13), then 4096-coefficient rows
+        Scratch stage(a.mode == FWD_MODDOWN ? (size_t)units * ctx->N : 0, s);
+        a.scratch = stage.p;
+        if (logN == 15) ck(launch_cta(NttFwdCols<15>{a}, units * ((1u << 15) / 16 / 256), 0, s));
+        else if (logN == 16) ck(launch_cta(NttFwdCols<16>{a}, units * ((1u << 16) / 16 / 256), 0, s));
+        else throw std::invalid_argument("poly_modulus_degree above 65536 is not supported");
+        a.row_pass = 1;
+        ck(launch_cta(NttFwd<12>{a}, units << (logN - 12), tile_smem(12), s));
+    }
+}
+
+void run_inv(const Context *ctx, NttArgs a, u32 units, cudaStream_t s) {
+    a.logN = ctx->logN;
+    a.mods = ctx->d_mods;
+    a.row_pass = 0;
+    const int logN = ctx->logN;
+    if (logN < 12) {
+        ck(launch_cta(NttInv<0>{a}, units, (size_t)ctx->N * sizeof(u64), s));
+    } else if (logN == 12) {
+        ck(launch_cta(NttInv<12>{a}, units, tile_smem(12), s));
+    } else if (logN == 13) {
+        ck(launch_cta(NttInv<13>{a}, units, tile_smem(13), s));
+    } else if (logN == 14) {
+        ck(launch_cta(NttInv<14>{a}, units, tile_smem(14), s));
+    } else {
+        Scratch stage(a.mode == INV_COMBINE ? (size_t)units * ctx->N : 0, s);
+        a.scratch = stage.p;
+        ck(launch_cta(NttInv<12>{a}, units << (logN - 12), tile_smem(12), s));
+        if (logN == 15) ck(launch_cta(NttInvCols<15>{a}, units * ((1u << 15) / 16 / 256), 0, s));
+        else if (logN == 16) ck(launch_cta(NttInvCols<16>{a}, units * ((1u << 16) / 16 / 256), 0, s));
+        else throw std::invalid_argument("poly_modulus_degree above 65536 is not supported");
+    }
+}
+
+// Plain batched transform: `batch` elements of `limbs_per_elem` limbs (polys x L), moduli map[l % L].
+void ntt_plain(const Context *ctx, bool inverse, const LimbMap &map, u32 L, const u64 *src, u64 src_stride, u64 *dst,
+               u64 dst_stride, u32 limbs_per_elem, u32 batch, bool canon, cudaStream_t s) {
+    NttArgs a{};
+    a.mode = inverse ? INV_PLAIN : FWD_PLAIN;
+    a.map = map;
+    a.n_limbs = limbs_per_elem;
+    a.L = L;
+    a.src = src;
+    a.dst = dst;
+    a.src_unit_stride = src_stride;
+    a.dst_batch_stride = dst_stride;
+    a.canon = canon ? 1 : 0;
+    a.scheme = ctx->scheme;
+    if (inverse) run_inv(ctx, a, batch * limbs_per_elem, s);
+    else run_fwd(ctx, a, batch * limbs_per_elem, s);
+}
+
+// ---- key switching ---------------------------------------------------------------------------------------------------
+// Host control flow of EvaluatorCuda::switchKeyInplace (src/evaluator_cuda.cu:1163-1378) over a batch:
+//   (CKKS) INTT the target  →  mod-up NTTs for all (output modulus i, digit j)  →  inner product with the key
+//   →  INTT the special-prime rows (+ half)  →  mod-down tail fused into the last transform of every data limb.
+void switch_key_impl(Context *ctx, int level, u64 *ct, u64 ct_stride, const u64 *target, u64 target_stride, const u64 *key,
+                     u32 batch, cudaStream_t s) {
+    if (!ctx->has_special) throw std::logic_error("keyswitching is not supported by the context");
+    const u32 L = (u32)ctx->levels[level].L;
+    const u64 N = ctx->N;
+    const u32 Lp = L + 1;
+    const u32 key_limbs = (u32)ctx->Ltop + 1;
+    const bool ckks = ctx->scheme == SCHEME_CKKS;
+    LimbMap kmap = ctx->map_prefix(L);
+    kmap.idx[L] = (uint8_t)ctx->pool_special;
+
+    // keep the mod-up scratch of one chunk inside the L2 (126 MB on B200)
+    const u64 per_ct_words = (u64)Lp * L * N;
+    u32 chunk = (u32)std::max<u64>(1, (48ull << 20) / (per_ct_words * 8));
+    chunk = std::min(chunk, batch);
+
+    Scratch t_target(ckks ? (size_t)chunk * L * N : 0, s);
+    Scratch D((size_t)chunk * per_ct_words, s);
+    Scratch prod((size_t)chunk * 2 * Lp * N, s);
+    Scratch sp((size_t)chunk * 2 * N, s);
+
+    for (u32 b0 = 0; b0 < batch; b0 += chunk) {
+        const u32 nb = std::min(chunk, batch - b0);
+        const u64 *tgt = target + (u64)b0 * target_stride;
+        u64 *cts = ct + (u64)b0 * ct_stride;
+        if (ckks) ntt_plain(ctx, true, kmap, L, tgt, target_stride, t_target.p, (u64)L * N, L, nb, true, s);
+        {
+            NttArgs a{};
+            a.mode = FWD_MODUP;
+            a.map = kmap;
+            a.L = L;
+            a.src = ckks ? t_target.p : tgt;
+            a.src_unit_stride = ckks ? (u64)L * N : target_stride;
+            a.aux0 = ckks ? tgt : nullptr;
+            a.aux0_batch_stride = target_stride;
+            a.dst = D.p;
+            a.scheme = ctx->scheme;
+            run_fwd(ctx, a, nb * Lp * L, s);
+        }
+        {
+            KsInnerProduct k{};
+            k.logN = ctx->logN;
+            k.mods = ctx->d_mods;
+            k.map = kmap;
+            k.L = L;
+            k.key_limbs = key_limbs;
+            k.special_key_limb = key_limbs - 1;
+            k.total = (u64)nb * Lp * N;
+            k.D = D.p;
+            k.key = key;
+            k.prod = prod.p;
+            ck(launch_cta(k, grid_for(k.total, KsInnerProduct::kThreads), 0, s));
+        }
+        {
+            NttArgs a{};
+            a.mode = INV_ADD_HALF;
+            a.map = kmap;
+            a.L = L;
+            a.K = 2;
+            a.src = prod.p;
+            a.src_offset = (u64)L * N;
+            a.src_unit_stride = 2ull * Lp * N;
+            a.src_poly_stride = (u64)Lp * N;
+            a.dst = sp.p;
+            a.drop = ctx->key_drop;
+            a.add_half = ctx->scheme != SCHEME_BGV;
+            a.scheme = ctx->scheme;
+            run_inv(ctx, a, nb * 2, s);
+        }
+        {
+            NttArgs a{};
+            a.mode = ckks ? FWD_MODDOWN : INV_COMBINE;
+            a.map = kmap;
+            a.L = L;
+            a.K = 2;
+            a.aux0 = prod.p;
+            a.acc_batch_stride = 2ull * Lp * N;
+            a.acc_poly_stride = (u64)Lp * N;
+            a.aux1 = sp.p;
+            a.ct = cts;
+            a.ct_batch_stride = ct_stride;
+            a.ct_poly_stride = (u64)L * N;
+            a.drop = ctx->key_drop;
+            a.scheme = ctx->scheme;
+            if (ckks) run_fwd(ctx, a, nb * 2 * L, s);
+            else run_inv(ctx, a, nb * 2 * L, s);
+        }
+    }
+}
+
+void check_batch_stride(size_t stride, size_t min_words, const char *what) {
+    if (stride < min_words) throw std::invalid_argument(std::string(what) + " stride is smaller than one ciphertext");
+}
+
+} // namespace
+
+extern "C" {
+
+const char *troyb_last_error(void) { return g_error.c_str(); }
+
+int troyb_initialize(int device) {
+    API_BEGIN
+    ck(cudaSetDevice(device));
+    ck(cudaFree(0));
+    g_device = device;
+    g_initialized = true;
+    API_END
+}
+
+int troyb_initialized(void) { return g_initialized ? 1 : 0; }
+
+int troyb_malloc(void **d_ptr, size_t bytes, void *stream) {
+    API_BEGIN
+    need_init();
+    ck(cudaMallocAsync(d_ptr, bytes ? bytes : 8, S(stream)));
+    API_END
+}
+int troyb_free(void *d_ptr, void *stream) {
+    API_BEGIN
+    if (d_ptr) ck(cudaFreeAsync(d_ptr, S(stream)));
+    API_END
+}
+int troyb_copy_to_device(void *d_dst, const void *h_src, size_t bytes, void *stream) {
+    API_BEGIN
+    need_init();
+    ck(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, S(stream)));
+    API_END
+}
+int troyb_copy_to_host(void *h_dst, const void *d_src, size_t bytes, void *stream) {
+    API_BEGIN
+    need_init();
+    ck(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, S(stream)));
+    ck(cudaStreamSynchronize(S(stream)));
+    API_END
+}
+int troyb_copy_on_device(void *d_dst, const void *d_src, size_t bytes, void *stream) {
+    API_BEGIN
+    need_init();
+    ck(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, S(stream)));
+    API_END
+}
+int troyb_memset_zero(void *d_ptr, size_t bytes, void *stream) {
+    API_BEGIN
+    need_init();
+    ck(cudaMemsetAsync(d_ptr, 0, bytes, S(stream)));
+    API_END
+}
+int troyb_stream_synchronize(void *stream) {
+    API_BEGIN
+    ck(cudaStreamSynchronize(S(stream)));
+    API_END
+}
+
+int troyb_context_create(int scheme, uint64_t n, const uint64_t *moduli, int n_moduli, uint64_t plain_modulus,
+                         int expand_mod_chain, troyb_context **out) {
+    API_BEGIN
+    need_init();
+    if (!out || !moduli) throw std::invalid_argument("null argument");
+    Context *impl = context_create(g_device, scheme, n, moduli, n_moduli, plain_modulus, expand_mod_chain != 0);
+    *out = new troyb_context{impl};
+    API_END
+}
+
+void troyb_context_destroy(troyb_context *ctx) {
+    if (!ctx) return;
+    delete ctx->impl;
+    delete ctx;
+}
+
+int troyb_context_scheme(const troyb_context *ctx) { return ctx && ctx->impl ? ctx->impl->scheme : 0; }
+uint64_t troyb_context_poly_degree(const troyb_context *ctx) { return ctx && ctx->impl ? ctx->impl->N : 0; }
+int troyb_context_num_levels(const troyb_context *ctx) { return ctx && ctx->impl ? (int)ctx->impl->levels.size() : 0; }
+int troyb_context_level_limbs(const troyb_context *ctx, int level) {
+    try {
+        return level_limbs(C(ctx), level);
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+int troyb_context_level_moduli(const troyb_context *ctx, int level, uint64_t *out) {
+    API_BEGIN
+    const Context *c = C(ctx);
+    int L = level_limbs(c, level);
+    if (level == -1) {
+        for (int i = 0; i < c->Ltop; i++) out[i] = c->pool[i];
+        if (c->has_special) out[c->Ltop] = c->pool[c->pool_special];
+    } else {
+        for (int i = 0; i < L; i++) out[i] = c->pool[i];
+    }
+    API_END
+}
+int troyb_context_using_keyswitching(const troyb_context *ctx) { return ctx && ctx->impl && ctx->impl->has_special ? 1 : 0; }
+int troyb_context_total_coeff_bits(const troyb_context *ctx, int level) {
+    try {
+        const Context *c = C(ctx);
+        level_limbs(c, level);
+        return c->level_total_bits(level);
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+uint64_t troyb_context_plain_modulus(const troyb_context *ctx) { return ctx && ctx->impl ? ctx->impl->plain : 0; }
+
+int troyb_context_bsk(const troyb_context *ctx, int level, uint64_t *out) {
+    try {
+        const Context *c = C(ctx);
+        level_limbs(c, level);
+        const LevelData &lv = c->levels[level];
+        if (!lv.has_behz) return 0;
+        if (out) {
+            for (int b = 0; b < lv.behz.nB; b++) out[b] = c->pool[c->pool_B0 + b];
+            out[lv.behz.nB] = c->pool[c->pool_msk];
+        }
+        return lv.behz.nBsk;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
+int troyb_context_root_powers(const troyb_context *ctx, int key_limb, uint64_t *h_out) {
+    API_BEGIN
+    const Context *c = C(ctx);
+    int n = c->Ltop + (c->has_special ? 1 : 0);
+    if (key_limb < 0 || key_limb >= n) throw std::out_of_range("key_limb");
+    int pool = key_limb < c->Ltop ? key_limb : c->pool_special;
+    ck(cudaMemcpy(h_out, c->h_mods[pool].fwd, 2 * c->N * sizeof(u64), cudaMemcpyDeviceToHost));
+    API_END
+}
+
+int troyb_ntt_forward(troyb_context *ctx, int level, uint64_t *d_data, size_t n_polys, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    u32 L = (u32)level_limbs(c, level);
+    ntt_plain(c, false, c->map_prefix(L), L, d_data, (u64)L * c->N, d_data, (u64)L * c->N, L, (u32)n_polys, true, S(stream));
+    API_END
+}
+int troyb_ntt_inverse(troyb_context *ctx, int level, uint64_t *d_data, size_t n_polys, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    u32 L = (u32)level_limbs(c, level);
+    ntt_plain(c, true, c->map_prefix(L), L, d_data, (u64)L * c->N, d_data, (u64)L * c->N, L, (u32)n_polys, true, S(stream));
+    API_END
+}
+int troyb_ntt_forward_key(troyb_context *ctx, uint64_t *d_data, size_t n_polys, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    u32 L = (u32)level_limbs(c, -1);
+    LimbMap m = c->has_special ? c->map_prefix_special(c->Ltop) : c->map_prefix(c->Ltop);
+    ntt_plain(c, false, m, L, d_data, (u64)L * c->N, d_data, (u64)L * c->N, L, (u32)n_polys, true, S(stream));
+    API_END
+}
+int troyb_ntt_inverse_key(troyb_context *ctx, uint64_t *d_data, size_t n_polys, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    u32 L = (u32)level_limbs(c, -1);
+    LimbMap m = c->has_special ? c->map_prefix_special(c->Ltop) : c->map_prefix(c->Ltop);
+    ntt_plain(c, true, m, L, d_data, (u64)L * c->N, d_data, (u64)L * c->N, L, (u32)n_polys, true, S(stream));
+    API_END
+}
+
+static int addsub(troyb_context *ctx, int level, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n_polys,
+                  void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    u32 L = (u32)level_limbs(c, level);
+    EltAddSub k{};
+    k.op = op;
+    k.logN = c->logN;
+    k.mods = c->d_mods;
+    k.map = c->map_prefix(L);
+    k.n_limbs = L;
+    k.total = (u64)n_polys * L * c->N;
+    k.a = a;
+    k.b = b;
+    k.out = out;
+    ck(launch_cta(k, grid_for(k.total, EltAddSub::kThreads), 0, S(stream)));
+    API_END
+}
+int troyb_add(troyb_context *ctx, int level, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n, void *st) {
+    return addsub(ctx, level, 0, a, b, out, n, st);
+}
+int troyb_sub(troyb_context *ctx, int level, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n, void *st) {
+    return addsub(ctx, level, 1, a, b, out, n, st);
+}
+int troyb_negate(troyb_context *ctx, int level, const uint64_t *a, uint64_t *out, size_t n, void *st) {
+    return addsub(ctx, level, 2, a, a, out, n, st);
+}
+
+int troyb_multiply(troyb_context *ctx, int level, const uint64_t *d_a, size_t a_size, size_t a_stride, const uint64_t *d_b,
+                   size_t b_size, size_t b_stride, uint64_t *d_out, size_t out_stride, size_t batch, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const u32 L = (u32)level_limbs(c, level);
+    const u64 N = c->N;
+    cudaStream_t s = S(stream);
+    if (a_size < 1 || b_size < 1 || a_size > 8 || b_size > 8) throw std::invalid_argument("invalid ciphertext size");
+    const size_t out_size = a_size + b_size - 1;
+    check_batch_stride(a_stride, a_size * L * N, "a");
+    check_batch_stride(b_stride, b_size * L * N, "b");
+    check_batch_stride(out_stride, out_size * L * N, "out");
+
+    auto tensor = [&](const LimbMap &map, u32 limbs, const u64 *a, u64 as, const u64 *b, u64 bs, u64 *o, u64 os) {
+        EltTensor k{};
+        k.logN = c->logN;
+        k.mods = c->d_mods;
+        k.map = map;
+        k.n_limbs = limbs;
+        k.a_size = (u32)a_size;
+        k.b_size = (u32)b_size;
+        k.per_batch = (u64)limbs * N;
+        k.total = (u64)batch * limbs * N;
+        k.a = a; k.b = b; k.out = o;
+        k.a_batch_stride = as; k.b_batch_stride = bs; k.out_batch_stride = os;
+        ck(launch_cta(k, grid_for(k.total, EltTensor::kThreads), 0, s));
+    };
+
+    if (c->scheme == SCHEME_CKKS) {
+        // ckksMultiply  src/evaluator_cuda.cu:384-433
+        tensor(c->map_prefix(L), L, d_a, a_stride, d_b, b_stride, d_out, out_stride);
+    } else if (c->scheme == SCHEME_BGV) {
+        // bgvMultiply  src/evaluator_cuda.cu:435-523: NTT both operands, tensor, INTT
+        const bool square = (d_a == d_b && a_size == b_size && a_stride == b_stride);
+        LimbMap map = c->map_prefix(L);
+        Scratch ta((size_t)batch * a_size * L * N, s);
+        Scratch tb(square ? 0 : (size_t)batch * b_size * L * N, s);
+        ntt_plain(c, false, map, L, d_a, a_stride, ta.p, (u64)a_size * L * N, (u32)a_size * L, (u32)batch, true, s);
+        if (!square) ntt_plain(c, false, map, L, d_b, b_stride, tb.p, (u64)b_size * L * N, (u32)b_size * L, (u32)batch, true, s);
+        tensor(map, L, ta.p, (u64)a_size * L * N, square ? ta.p : tb.p, (u64)b_size * L * N, d_out, out_stride);
+        ntt_plain(c, true, map, L, d_out, out_stride, d_out, out_stride, (u32)out_size * L, (u32)batch, true, s);
+    } else {
+        // bfvMultiply (BEHZ)  src/evaluator_cuda.cu:283-382
+        const LevelData &lv = c->levels[level];
+        if (!lv.has_behz) throw std::logic_error("BEHZ tables missing");
+        const u32 E = L + (u32)lv.behz.nBsk;
+        if (E > (u32)kBehzMax) throw std::invalid_argument("too many limbs for BFV multiply");
+        LimbMap map = c->map_q_bsk(level);
+        const bool square = (d_a == d_b && a_size == b_size && a_stride == b_stride);
+        Scratch ea((size_t)batch * a_size * E * N, s);
+        Scratch eb(square ? 0 : (size_t)batch * b_size * E * N, s);
+        Scratch prod((size_t)batch * out_size * E * N, s);
+        auto extend = [&](const u64 *in, size_t size, u64 stride, u64 *out) {
+            BehzExtend k{};
+            k.logN = c->logN;
+            k.mods = c->d_mods;
+            k.map = map;
+            k.z = lv.behz;
+            k.total = (u64)batch * size * N;
+            k.polys_per_batch = (u32)size;
+            k.in_batch_stride = stride;
+            k.in = in;
+            k.out = out;
+            ck(launch_cta(k, grid_for(k.total, BehzExtend::kThreads), 0, s));
+            ntt_plain(c, false, map, E, out, (u64)size * E * N, out, (u64)size * E * N, (u32)size * E, (u32)batch, true, s);
+        };
+        extend(d_a, a_size, a_stride, ea.p);
+        if (!square) extend(d_b, b_size, b_stride, eb.p);
+        tensor(map, E, ea.p, (u64)a_size * E * N, square ? ea.p : eb.p, (u64)b_size * E * N, prod.p, (u64)out_size * E * N);
+        ntt_plain(c, true, map, E, prod.p, (u64)out_size * E * N, prod.p, (u64)out_size * E * N, (u32)out_size * E, (u32)batch,
+                  true, s);
+        BehzFloorSk k{};
+        k.logN = c->logN;
+        k.mods = c->d_mods;
+        k.map = map;
+        k.z = lv.behz;
+        k.total = (u64)batch * out_size * N;
+        k.in = prod.p;
+        k.out = d_out;
+        k.polys_per_batch = (u32)out_size;
+        k.out_batch_stride = out_stride;
+        ck(launch_cta(k, grid_for(k.total, BehzFloorSk::kThreads), 0, s));
+    }
+    API_END
+}
+
+int troyb_switch_key(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_stride, const uint64_t *d_target,
+                     size_t target_stride, const uint64_t *d_key, size_t batch, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const u32 L = (u32)level_limbs(c, level);
+    if (level < 0) throw std::invalid_argument("level");
+    if (!d_ct || !d_target || !d_key) throw std::invalid_argument("target_iter");
+    check_batch_stride(ct_stride, 2ull * L * c->N, "ct");
+    check_batch_stride(target_stride, (u64)L * c->N, "target");
+    switch_key_impl(c, level, d_ct, ct_stride, d_target, target_stride, d_key, (u32)batch, S(stream));
+    API_END
+}
+
+int troyb_relinearize(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_stride, const uint64_t *d_relin_key,
+                      size_t batch, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const u32 L = (u32)level_limbs(c, level);
+    if (level < 0) throw std::invalid_argument("level");
+    if (!d_ct || !d_relin_key) throw std::invalid_argument("null argument");
+    check_batch_stride(ct_stride, 3ull * L * c->N, "ct");
+    switch_key_impl(c, level, d_ct, ct_stride, d_ct + 2ull * L * c->N, ct_stride, d_relin_key, (u32)batch, S(stream));
+    API_END
+}
+
+int troyb_galois_permute(troyb_context *ctx, int level, const uint64_t *d_in, uint64_t *d_out, size_t n_polys,
+                         uint32_t galois_elt, int ntt_form, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const u32 L = (u32)level_limbs(c, level);
+    if (!(galois_elt & 1) || galois_elt >= 2 * c->N) throw std::invalid_argument("Galois element is not valid");
+    if (d_in == d_out) throw std::invalid_argument("operand cannot point to the same value as result");
+    EltGalois k{};
+    k.logN = c->logN;
+    k.ntt_form = ntt_form;
+    k.mods = c->d_mods;
+    k.map = c->map_prefix(L);
+    k.n_limbs = L;
+    k.L = L;
+    k.elt = galois_elt;
+    k.total = (u64)n_polys * L * c->N;
+    k.in = d_in;
+    k.out = d_out;
+    k.in_batch_stride = (u64)L * c->N;
+    k.out_batch_stride = (u64)L * c->N;
+    ck(launch_cta(k, grid_for(k.total, EltGalois::kThreads), 0, S(stream)));
+    API_END
+}
+
+int troyb_galois_elt_from_step(const troyb_context *ctx, int step, uint32_t *out) {
+    API_BEGIN
+    // GaloisTool::getEltFromStep  src/utils/galois.cpp:58-92 (generator 3, row size N/2)
+    const Context *c = C(ctx);
+    const u32 n = (u32)c->N, m = 2 * n;
+    if (step == 0) {
+        *out = m - 1;
+    } else {
+        bool sign = step < 0;
+        u32 pos = (u32)(sign ? -(int64_t)step : step);
+        if (pos >= (n >> 1)) throw std::invalid_argument("step count too large");
+        pos = sign ? (n >> 1) - pos : pos;
+        u64 g = 1;
+        for (u32 i = 0; i < pos; i++) g = (g * 3) & (m - 1);
+        *out = (u32)g;
+    }
+    API_END
+}
+
+int troyb_apply_galois(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_stride, uint32_t galois_elt,
+                       const uint64_t *d_key, size_t batch, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const u32 L = (u32)level_limbs(c, level);
+    const u64 N = c->N;
+    cudaStream_t s = S(stream);
+    if (level < 0) throw std::invalid_argument("level");
+    if (!(galois_elt & 1) || galois_elt >= 2 * N) throw std::invalid_argument("Galois element is not valid");
+    if (!d_ct || !d_key) throw std::invalid_argument("Galois key not present");
+    check_batch_stride(ct_stride, 2ull * L * N, "ct");
+    Scratch tmp((size_t)batch * 2 * L * N, s);
+    EltGalois k{};
+    k.logN = c->logN;
+    k.ntt_form = c->scheme == SCHEME_CKKS;
+    k.mods = c->d_mods;
+    k.map = c->map_prefix(L);
+    k.n_limbs = 2 * L;
+    k.L = L;
+    k.elt = galois_elt;
+    k.total = (u64)batch * 2 * L * N;
+    k.in = d_ct;
+    k.out = tmp.p;
+    k.in_batch_stride = ct_stride;
+    k.out_batch_stride = 2ull * L * N;
+    ck(launch_cta(k, grid_for(k.total, EltGalois::kThreads), 0, s));
+    // c0 <- permuted c0 ; c1 <- 0 ; then key-switch the permuted c1 into (c0, c1)   src/evaluator_cuda.cu:2104-2116
+    ck(cudaMemcpy2DAsync(d_ct, ct_stride * 8, tmp.p, 2ull * L * N * 8, (size_t)L * N * 8, batch, cudaMemcpyDeviceToDevice, s));
+    ck(cudaMemset2DAsync(d_ct + (u64)L * N, ct_stride * 8, 0, (size_t)L * N * 8, batch, s));
+    switch_key_impl(c, level, d_ct, ct_stride, tmp.p + (u64)L * N, 2ull * L * N, d_key, (u32)batch, s);
+    API_END
+}
+
+int troyb_mod_switch_scale_to_next(troyb_context *ctx, int level, const uint64_t *d_in, size_t in_stride, uint64_t *d_out,
+                                   size_t out_stride, size_t size, size_t batch, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const u32 L = (u32)level_limbs(c, level);
+    const u64 N = c->N;
+    cudaStream_t s = S(stream);
+    if (level < 0 || level + 1 >= (int)c->levels.size()) throw std::invalid_argument("end of modulus switching chain reached");
+    if (d_in == d_out) throw std::invalid_argument("in-place call must go through a temporary (as the reference does)");
+    check_batch_stride(in_stride, size * L * N, "in");
+    check_batch_stride(out_stride, size * (L - 1) * N, "out");
+    const LevelData &lv = c->levels[level];
+    if (c->scheme == SCHEME_CKKS) {
+        // divideAndRoundqLastNttInplace  src/utils/rns_cuda.cu:348-363
+        Scratch sp((size_t)batch * size * N, s);
+        NttArgs a{};
+        a.mode = INV_ADD_HALF;
+        a.map = c->map_prefix(L);
+        a.L = L;
+        a.K = (u32)size;
+        a.src = d_in;
+        a.src_offset = (u64)(L - 1) * N;
+        a.src_unit_stride = in_stride;
+        a.src_poly_stride = (u64)L * N;
+        a.dst = sp.p;
+        a.drop = lv.drop;
+        a.add_half = 1;
+        a.scheme = c->scheme;
+        run_inv(c, a, (u32)(batch * size), s);
+        NttArgs f{};
+        f.mode = FWD_MODDOWN;
+        f.map = c->map_prefix(L - 1);
+        f.L = L - 1;
+        f.K = (u32)size;
+        f.aux0 = d_in;
+        f.acc_batch_stride = in_stride;
+        f.acc_poly_stride = (u64)L * N;
+        f.aux1 = sp.p;
+        f.ct = nullptr;
+        f.dst = d_out;
+        f.dst_batch_stride = out_stride;
+        f.dst_poly_stride = (u64)(L - 1) * N;
+        f.drop = lv.drop;
+        f.scheme = c->scheme;
+        run_fwd(c, f, (u32)(batch * size * (L - 1)), s);
+    } else {
+        EltDropLast k{};
+        k.logN = c->logN;
+        k.scheme = c->scheme;
+        k.mods = c->d_mods;
+        k.drop = lv.drop;
+        k.L = L;
+        k.size = (u32)size;
+        k.total = (u64)batch * size * (L - 1) * N;
+        k.in_batch_stride = in_stride;
+        k.out_batch_stride = out_stride;
+        k.in = d_in;
+        k.out = d_out;
+        ck(launch_cta(k, grid_for(k.total, EltDropLast::kThreads), 0, s));
+    }
+    API_END
+}
+
+} // extern "C"

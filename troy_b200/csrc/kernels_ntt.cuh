@@ -1,0 +1,344 @@
+// NTT kernels (functors for launch_cta) with fused prologues / epilogues.
+//
+// One forward family and one inverse family cover every transform on the hot path; a runtime `mode`
+// (uniform per launch) selects how a CTA maps to (source, destination, modulus) and which element-wise
+// work is fused into the load and the store:
+//
+//   FWD_PLAIN     transformToNttInplace / kNttNegacyclicHarvey[Lazy]      src/kernelutils.cuh:578-603
+//   FWD_MODUP     key-switch mod-up: digit j reduced mod q_i, then NTT_i   src/evaluator_cuda.cu:1231-1247
+//   FWD_MODDOWN   CKKS mod-down / rescale tail: (s' mod q_j) - half, NTT_j, subtract, x q_last^-1, (+ ct)
+//                                                                          src/evaluator_cuda.cu:1118-1161 (UtilF/G),
+//                                                                          src/utils/rns_cuda.cu:307-363
+//   INV_PLAIN     transformFromNttInplace / kInverseNttNegacyclicHarvey   src/kernelutils.cuh:607-632
+//   INV_ADD_HALF  INTT of the limb being dropped, + floor(q_last/2) mod q_last   src/evaluator_cuda.cu:1327-1331
+//   INV_COMBINE   BFV/BGV mod-down tail in coefficient form               src/evaluator_cuda.cu:1087-1161 (UtilE/F/G)
+#pragma once
+#include "ntt.cuh"
+
+namespace troyb {
+
+enum NttMode {
+    FWD_PLAIN = 0, FWD_MODUP = 1, FWD_MODDOWN = 2,
+    INV_PLAIN = 10, INV_ADD_HALF = 11, INV_COMBINE = 12,
+};
+
+struct NttArgs {
+    int mode;
+    int logN;
+    const ModDev *mods;
+    LimbMap map;        // launch limb -> pool index
+    u32 n_limbs;        // limbs per poly in the launch's unit order
+    u64 *dst;
+    const u64 *src;
+    int canon;          // store canonical residues (else lazy)
+    // --- key-switch / drop-last extras
+    const u64 *aux0;    // MODUP: original NTT-form target (CKKS) or null; MODDOWN/COMBINE: accumulators (t_poly_prod)
+    const u64 *aux1;    // MODDOWN/COMBINE: s' (rounded special limb, coefficient form)
+    u64 *ct;            // MODDOWN/COMBINE: ciphertext updated in place (null for rescale -> write dst)
+    DropDev drop;       // constants for the prime being dropped
+    u32 L;              // data limbs in play
+    u32 K;              // polys per batch element handled (2 for key-switch, ct size for rescale)
+    u64 src_unit_stride;  // words between batch elements of src
+    u64 src_poly_stride;  // words between polys of one batch element in src (INV_ADD_HALF)
+    u64 src_offset;       // word offset of the first source unit
+    u64 aux0_batch_stride;
+    u64 acc_poly_stride;  // words between polys in aux0
+    u64 acc_batch_stride;
+    u64 ct_poly_stride;
+    u64 ct_batch_stride;
+    u64 dst_poly_stride;
+    u64 dst_batch_stride;
+    int scheme;
+    int add_half;       // INV_ADD_HALF: add half (BFV/CKKS) or plain canonical INTT (BGV)
+    int row_pass;       // forward four-step: this launch is the row pass that follows a column pass
+    u64 *scratch;       // four-step intermediate rows [unit][N] for modes that cannot stage in dst
+};
+
+// Generic small transform (N < 4096; only the reference's toy-parameter tests use it): radix-2 in shared memory.
+template <class Ld, class St>
+TB_D void small_ntt_fwd(u64 *sm, u32 logn, Ld ld, St st, const u64 *__restrict__ tw, u64 p) {
+    const u32 n = 1u << logn;
+    const u64 p2 = p << 1;
+    TB_PHASE(256, t, for (u32 i = t; i < n; i += 256) sm[i] = ld(i);)
+    for (u32 s = 0; s < logn; s++) {
+        const u32 lg = logn - 1 - s;
+        TB_PHASE(256, t, for (u32 b = t; b < n / 2; b += 256) {
+            u32 r = b >> lg, pos = b & ((1u << lg) - 1);
+            u32 i = (r << (lg + 1)) | pos;
+            ulonglong2 w = ld_tw(tw, (1u << s) + r);
+            u64 X = sm[i], Y = sm[i + (1u << lg)];
+            ct_bfly(X, Y, w.x, w.y, p, p2);
+            sm[i] = X;
+            sm[i + (1u << lg)] = Y;
+        })
+    }
+    TB_PHASE(256, t, for (u32 i = t; i < n; i += 256) st(i, sm[i]);)
+}
+
+template <class Ld, class St>
+TB_D void small_ntt_inv(u64 *sm, u32 logn, Ld ld, St st, const u64 *__restrict__ tw, u64 p, const ModDev *md) {
+    const u32 n = 1u << logn;
+    const u64 p2 = p << 1;
+    TB_PHASE(256, t, for (u32 i = t; i < n; i += 256) sm[i] = ld(i);)
+    for (int s = (int)logn - 1; s >= 0; s--) {
+        const u32 lg = logn - 1 - s;
+        TB_PHASE(256, t, for (u32 b = t; b < n / 2; b += 256) {
+            u32 r = b >> lg, pos = b & ((1u << lg) - 1);
+            u32 i = (r << (lg + 1)) | pos;
+            u64 X = sm[i], Y = sm[i + (1u << lg)];
+            if (s == 0) {
+                gs_bfly_last(X, Y, md->ninv, md->ninv_shoup, md->inv1n, md->inv1n_shoup, p, p2);
+            } else {
+                ulonglong2 w = ld_tw(tw, (1u << s) + r);
+                gs_bfly(X, Y, w.x, w.y, p, p2);
+            }
+            sm[i] = X;
+            sm[i + (1u << lg)] = Y;
+        })
+    }
+    TB_PHASE(256, t, for (u32 i = t; i < n; i += 256) st(i, sm[i]);)
+}
+
+TB_D u64 canon4(u64 v, u64 p) {
+    u64 p2 = p << 1;
+    v -= (v >= p2 ? p2 : 0);
+    v -= (v >= p ? p : 0);
+    return v;
+}
+TB_D u64 canon2(u64 v, u64 p) { return v - (v >= p ? p : 0); }
+
+// Per-CTA resolved job: where to read / write and with which modulus.
+struct NttUnit {
+    const ModDev *md;
+    const u64 *src;
+    u64 *dst;
+    const u64 *acc;   // accumulators row
+    const u64 *sp;    // s' row
+    u64 *ct;          // ciphertext row (read-modify-write)
+    DropLimb dl;
+    bool passthrough; // MODUP with i == j in CKKS: copy the NTT-form limb
+    u32 row;          // four-step row
+    u32 rows_log;
+    u32 unit;
+};
+
+// LOGT == 0 selects the generic small-N path (whole limb, runtime logN).
+template <int LOGT> TB_D NttUnit resolve_unit(const NttArgs &a, u32 bid) {
+    NttUnit u{};
+    const u32 rows_log = LOGT == 0 ? 0 : (u32)(a.logN - LOGT);
+    const u32 row = bid & ((1u << rows_log) - 1);
+    const u32 unit = bid >> rows_log;
+    const u64 N = u64(1) << a.logN;
+    u.row = row;
+    u.rows_log = rows_log;
+    u.unit = unit;
+    u.passthrough = false;
+    switch (a.mode) {
+    case FWD_PLAIN:
+    case INV_PLAIN: {
+        // unit = b * n_limbs + l ; n_limbs counts every limb of one batch element (polys x limbs)
+        u32 l = unit % a.n_limbs, b = unit / a.n_limbs;
+        u.md = a.mods + a.map.idx[l % a.L];
+        u.src = a.src + (u64)b * a.src_unit_stride + (u64)l * N;
+        u.dst = a.dst + (u64)b * a.dst_batch_stride + (u64)l * N;
+        break;
+    }
+    case FWD_MODUP: {
+        // unit = (b * (L+1) + i) * L + j
+        u32 j = unit % a.L, bi = unit / a.L, i = bi % (a.L + 1), b = bi / (a.L + 1);
+        u.md = a.mods + a.map.idx[i];
+        u.src = a.src + (u64)b * a.src_unit_stride + (u64)j * N;
+        u.dst = a.dst + (u64)unit * N;
+        if (a.aux0 != nullptr && i == j) {
+            u.passthrough = true;
+            u.src = a.aux0 + (u64)b * a.aux0_batch_stride + (u64)j * N;
+        }
+        break;
+    }
+    case INV_ADD_HALF: {
+        // unit = b * K + k
+        u.md = a.mods + a.drop.last_pool;
+        u.src = a.src + a.src_offset + (u64)(unit / a.K) * a.src_unit_stride + (u64)(unit % a.K) * a.src_poly_stride;
+        u.dst = a.dst + (u64)unit * N;
+        break;
+    }
+    case FWD_MODDOWN:
+    case INV_COMBINE: {
+        // unit = (b * K + k) * L + j
+        u32 j = unit % a.L, bk = unit / a.L, k = bk % a.K, b = bk / a.K;
+        u.md = a.mods + a.map.idx[j];
+        u.sp = a.aux1 + (u64)bk * N;
+        u.acc = a.aux0 + (u64)b * a.acc_batch_stride + (u64)k * a.acc_poly_stride + (u64)j * N;
+        u.ct = a.ct ? a.ct + (u64)b * a.ct_batch_stride + (u64)k * a.ct_poly_stride + (u64)j * N : nullptr;
+        u.dst = a.dst ? a.dst + (u64)b * a.dst_batch_stride + (u64)k * a.dst_poly_stride + (u64)j * N : nullptr;
+        u.dl = a.drop.limbs[j];
+        u.src = (a.mode == FWD_MODDOWN) ? u.sp : u.acc;
+        break;
+    }
+    }
+    return u;
+}
+
+template <int LOGT> struct NttFwd {
+    static constexpr int kThreads = LOGT == 0 ? 256 : (1 << (LOGT == 0 ? 4 : LOGT)) / 16;
+    NttArgs a;
+    TB_D void operator()(u32 bid, u64 *sm) const {
+        const NttUnit u = resolve_unit<LOGT>(a, bid);
+        const ModDev *md = u.md;
+        const u64 p = md->p;
+        const u32 tile = LOGT == 0 ? (1u << a.logN) : (1u << LOGT);
+        const u64 off = (u64)u.row * tile;
+        const int mode = a.mode;
+        const bool row_pass = a.row_pass != 0;
+        if (u.passthrough) {
+            if (row_pass) return; // the column pass already copied the limb
+            TB_PHASE(kThreads, t, for (u32 i = t; i < tile; i += kThreads) u.dst[off + i] = u.src[off + i];)
+            return;
+        }
+        const u64 ratio1 = md->ratio1;
+        const u64 fix = (mode == FWD_MODDOWN) ? p - u.dl.half_mod : 0;
+        const u64 *in = !row_pass ? u.src : (mode == FWD_MODDOWN ? a.scratch + ((u64)u.unit << a.logN) : u.dst);
+        auto ld = [&](u32 i) -> u64 {
+            u64 x = in[off + i];
+            if (row_pass) return x;
+            if (mode == FWD_MODUP) x = barrett64(x, p, ratio1);
+            else if (mode == FWD_MODDOWN) x = barrett64(x, p, ratio1) + fix;
+            return x;
+        };
+        const int canon = a.canon;
+        auto st = [&](u32 i, u64 v) {
+            if (mode == FWD_MODDOWN) {
+                // v in [0,4p): d = acc + 4p - v in (0,5p); r = d * q_last^-1 mod p
+                u64 d = u.acc[off + i] + (p << 2) - v;
+                u64 r = shoup(d, u.dl.inv_last, u.dl.inv_last_shoup, p);
+                if (u.ct) u.ct[off + i] = addmod(u.ct[off + i], r, p);
+                else u.dst[off + i] = r;
+            } else {
+                u.dst[off + i] = canon ? canon4(v, p) : v;
+            }
+        };
+        if constexpr (LOGT == 0) {
+            small_ntt_fwd(sm, (u32)a.logN, ld, st, md->fwd, p);
+        } else {
+            tile_ntt_fwd<LOGT>(sm, ld, st, md->fwd, (1u << u.rows_log) + u.row, p);
+        }
+    }
+};
+
+template <int LOGT> struct NttInv {
+    static constexpr int kThreads = LOGT == 0 ? 256 : (1 << (LOGT == 0 ? 4 : LOGT)) / 16;
+    NttArgs a;
+    TB_D void operator()(u32 bid, u64 *sm) const {
+        const NttUnit u = resolve_unit<LOGT>(a, bid);
+        const ModDev *md = u.md;
+        const u64 p = md->p;
+        const u32 tile = LOGT == 0 ? (1u << a.logN) : (1u << LOGT);
+        const u64 off = (u64)u.row * tile;
+        const int mode = a.mode;
+        const bool whole = (u.rows_log == 0);
+        auto ld = [&](u32 i) -> u64 { return u.src[off + i]; };
+        const int canon = a.canon;
+        u64 *stage = (mode == INV_COMBINE) ? a.scratch + ((u64)u.unit << a.logN) : u.dst;
+        auto st = [&](u32 i, u64 v) {
+            // v in [0,2p)
+            if (!whole) { stage[off + i] = v; return; } // four-step: the column pass finishes the job
+            store_final(a, u, p, off + i, v);
+        };
+        if constexpr (LOGT == 0) {
+            small_ntt_inv(sm, (u32)a.logN, ld, st, md->inv, p, md);
+        } else {
+            if (whole) tile_ntt_inv<LOGT, true>(sm, ld, st, md->inv, 1u, p, md);
+            else tile_ntt_inv<LOGT, false>(sm, ld, st, md->inv, (1u << u.rows_log) + u.row, p, md);
+        }
+    }
+
+    // Epilogue of a completed inverse transform; shared with the four-step column pass.
+    static TB_D void store_final(const NttArgs &a, const NttUnit &u, u64 p, u64 idx, u64 v) {
+        const int mode = a.mode, canon = a.canon;
+        const DropDev &dr = a.drop;
+        if (mode == INV_PLAIN) {
+            u.dst[idx] = canon ? canon2(v, p) : v;
+        } else if (mode == INV_ADD_HALF) {
+            u64 c = canon2(v, p);
+            if (a.add_half) c = addmod(c, dr.half, p);
+            u.dst[idx] = c;
+        } else { // INV_COMBINE
+            u64 s = u.sp[idx];
+            u64 sub;
+            const u64 ratio1 = u.md->ratio1;
+            if (a.scheme == SCHEME_BGV) {
+                // BGV (UtilE): k = -(s mod t) * q_last^-1 mod t ; delta = (k mod q_j) * q_last mod q_j ; c = s mod q_j
+                u64 kk = negmod(barrett64(s, dr.t, dr.t_ratio1), dr.t);
+                kk = shoup(kk, dr.inv_last_mod_t, dr.inv_last_mod_t_shoup, dr.t);
+                u64 delta = shoup(barrett64(kk, p, ratio1), u.dl.last_mod, u.dl.last_mod_shoup, p);
+                sub = delta + barrett64(s, p, ratio1);
+            } else {
+                // BFV (UtilF/G): (s' mod q_j) + q_j - half mod q_j
+                sub = barrett64(s, p, ratio1) + (p - u.dl.half_mod);
+            }
+            u64 d = v + (p << 1) - sub; // v < 2p, sub <= 2p  ->  d in [0,4p)
+            u64 r = shoup(d, u.dl.inv_last, u.dl.inv_last_shoup, p);
+            if (u.ct) u.ct[idx] = addmod(u.ct[idx], r, p);
+            else u.dst[idx] = r;
+        }
+    }
+};
+
+// ---- four-step column passes (N = 32768 / 65536): layers 0..LOGN-13 over elements N/16 apart -------------
+template <int LOGN> struct NttFwdCols {
+    static constexpr int kThreads = 256;
+    NttArgs a;
+    TB_D void operator()(u32 bid, u64 *) const {
+        constexpr u32 NTV = (1u << LOGN) / 16, CPB = NTV / kThreads;
+        const u32 chunk = bid % CPB;
+        NttArgs b = a;
+        b.logN = LOGN; // resolve with rows_log = 0: unit = bid / CPB
+        const NttUnit u = resolve_unit<LOGN>(b, bid / CPB);
+        const ModDev *md = u.md;
+        const u64 p = md->p, p2 = p << 1;
+        if (u.passthrough) {
+            TB_PHASE(kThreads, t, {
+                u32 v = chunk * kThreads + t;
+                for (u32 k = 0; k < 16; k++) u.dst[v + k * NTV] = u.src[v + k * NTV];
+            })
+            return;
+        }
+        const int mode = a.mode;
+        const u64 ratio1 = md->ratio1;
+        const u64 fix = (mode == FWD_MODDOWN) ? p - u.dl.half_mod : 0;
+        // The column pass writes its lazy result where the row pass will read it: the destination buffer
+        // for PLAIN / MODUP, a scratch row (dst) for MODDOWN.
+        auto ld = [&](u32 i) -> u64 {
+            u64 x = u.src[i];
+            if (mode == FWD_MODUP) x = barrett64(x, p, ratio1);
+            else if (mode == FWD_MODDOWN) x = barrett64(x, p, ratio1) + fix;
+            return x;
+        };
+        u64 *out = (mode == FWD_MODDOWN) ? a.scratch + ((u64)u.unit << LOGN) : u.dst;
+        auto st = [&](u32 i, u64 v) { out[i] = v; };
+        TB_PHASE(kThreads, t, (fwd_round<LOGN, 0, LOGN - 12, (int)NTV>(chunk * kThreads + t, ld, st, md->fwd, 1u, p, p2));)
+    }
+};
+
+template <int LOGN> struct NttInvCols {
+    static constexpr int kThreads = 256;
+    NttArgs a;
+    TB_D void operator()(u32 bid, u64 *) const {
+        constexpr u32 NTV = (1u << LOGN) / 16, CPB = NTV / kThreads;
+        const u32 chunk = bid % CPB;
+        NttArgs b = a;
+        b.logN = LOGN;
+        const NttUnit u = resolve_unit<LOGN>(b, bid / CPB);
+        const ModDev *md = u.md;
+        const u64 p = md->p, p2 = p << 1;
+        const int mode = a.mode;
+        // The row pass left its lazy output in the destination row (PLAIN / ADD_HALF) or in a scratch row (COMBINE).
+        const u64 *in = (mode == INV_COMBINE) ? a.scratch + ((u64)u.unit << LOGN) : u.dst;
+        auto ld = [&](u32 i) -> u64 { return in[i]; };
+        auto st = [&](u32 i, u64 v) { NttInv<12>::store_final(a, u, p, i, v); };
+        TB_PHASE(kThreads, t,
+                 (inv_round<LOGN, 0, LOGN - 12, (int)NTV, true>(chunk * kThreads + t, ld, st, md->inv, 1u, p, p2, md));)
+    }
+};
+
+} // namespace troyb

@@ -1,0 +1,605 @@
+"""Host-side mirror of the reference's ``troyn::`` classes for the RNS polynomial path.
+
+Names, argument meaning and error behaviour follow the reference (file:line cited per class); the arithmetic is all in
+the CUDA library behind the C ABI. Differences that are deliberate and documented in DESIGN.md:
+
+* a ``ParmsID`` is the chain index (``int``; ``-1`` is the key level) instead of a Blake2 hash of the parameters;
+* every ciphertext object may carry a leading ``batch`` dimension (``[batch][poly][limb][coeff]``); ``batch == 1`` is
+  exactly the reference object, larger batches are how one GPU is kept busy with independent ciphertexts;
+* key generation / encryption / encoding stay on the host in the reference (``KeyGeneratorCuda`` wraps the host
+  ``KeyGenerator``, src/keygenerator_cuda.cuh:36-60), so keys and ciphertexts enter through ``from_host`` uploads.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import lib as _lib
+from .lib import TroyInvalidArgument, TroyLogicError, TroyOutOfRange
+
+BFV, CKKS, BGV = 1, 2, 3
+
+
+class SchemeType:
+    """src/encryptionparams.h SchemeType."""
+    none, bfv, ckks, bgv = 0, 1, 2, 3
+
+
+def _L():
+    return _lib.library()
+
+
+def _vp(x):
+    return C.c_void_p(x)
+
+
+class KernelProvider:
+    """src/kernelprovider.cuh:18-85."""
+
+    @staticmethod
+    def initialize(device=0):
+        _L().call("troyb_initialize", device)
+
+    @staticmethod
+    def initialized():
+        return bool(_L().cdll.troyb_initialized())
+
+
+class DeviceArray:
+    """Owning device buffer of uint64 words (DeviceArray<uint64_t>, src/utils/devicearray.cuh:90-200)."""
+
+    def __init__(self, words, stream=None):
+        self.words = int(words)
+        self.stream = stream
+        p = C.c_void_p()
+        _L().call("troyb_malloc", C.byref(p), self.words * 8, _vp(stream))
+        self.ptr = p.value
+
+    def __del__(self):
+        try:
+            if getattr(self, "ptr", None):
+                _L().cdll.troyb_free(_vp(self.ptr), _vp(self.stream))
+                self.ptr = None
+        except Exception:
+            pass
+
+    def at(self, word_offset):
+        return self.ptr + 8 * int(word_offset)
+
+    def upload(self, arr, word_offset=0):
+        a = np.ascontiguousarray(arr, dtype=np.uint64)
+        if a.size + word_offset > self.words:
+            raise TroyInvalidArgument("upload larger than buffer")
+        _L().call("troyb_copy_to_device", _vp(self.at(word_offset)), a.ctypes.data_as(C.c_void_p), a.size * 8,
+                  _vp(self.stream))
+        _L().call("troyb_stream_synchronize", _vp(self.stream))
+
+    def download(self, words=None, word_offset=0):
+        n = self.words - word_offset if words is None else int(words)
+        out = np.empty(n, dtype=np.uint64)
+        _L().call("troyb_copy_to_host", out.ctypes.data_as(C.c_void_p), _vp(self.at(word_offset)), n * 8, _vp(self.stream))
+        return out
+
+
+class ExternalArray:
+    """Non-owning view of device memory owned by someone else (DevicePointer<uint64_t>, src/utils/devicearray.cuh:16-55);
+    used to run the evaluator directly on torch tensors."""
+
+    def __init__(self, ptr, words):
+        self.ptr, self.words, self.stream = int(ptr), int(words), None
+
+    def at(self, word_offset):
+        return self.ptr + 8 * int(word_offset)
+
+
+class EncryptionParameters:
+    """src/encryptionparams.h:90-260 (only what the path needs: scheme, N, coeff_modulus, plain_modulus)."""
+
+    def __init__(self, scheme=SchemeType.none):
+        self.scheme = int(scheme)
+        self.poly_modulus_degree = 0
+        self.coeff_modulus = []
+        self.plain_modulus = 0
+
+    def set_poly_modulus_degree(self, n):
+        self.poly_modulus_degree = int(n)
+
+    def set_coeff_modulus(self, moduli):
+        self.coeff_modulus = [int(m) for m in moduli]
+
+    def set_plain_modulus(self, t):
+        if self.scheme == SchemeType.ckks and int(t) != 0:
+            raise TroyLogicError("unsupported scheme")
+        self.plain_modulus = int(t)
+
+    setPolyModulusDegree, setCoeffModulus, setPlainModulus = set_poly_modulus_degree, set_coeff_modulus, set_plain_modulus
+
+
+class SEALContextCuda:
+    """src/context_cuda.cuh:146-186 + src/context_cuda.cu:5-62. ``parms_id`` values are chain indices."""
+
+    KEY_LEVEL = -1
+
+    def __init__(self, parms, expand_mod_chain=True):
+        self.parms = parms
+        q = np.array(parms.coeff_modulus, dtype=np.uint64)
+        h = C.c_void_p()
+        _L().call("troyb_context_create", parms.scheme, parms.poly_modulus_degree,
+                  q.ctypes.data_as(C.POINTER(C.c_uint64)), len(parms.coeff_modulus), parms.plain_modulus,
+                  int(bool(expand_mod_chain)), C.byref(h))
+        self.h = h.value
+        self.scheme = parms.scheme
+        self.n = parms.poly_modulus_degree
+        self.num_levels = _L().cdll.troyb_context_num_levels(_vp(self.h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                _L().cdll.troyb_context_destroy(_vp(self.h))
+                self.h = None
+        except Exception:
+            pass
+
+    def level_limbs(self, level):
+        r = _L().cdll.troyb_context_level_limbs(_vp(self.h), level)
+        if r < 0:
+            raise TroyInvalidArgument(_L().last_error())
+        return r
+
+    def level_moduli(self, level):
+        n = self.level_limbs(level)
+        out = np.zeros(n, dtype=np.uint64)
+        _L().call("troyb_context_level_moduli", _vp(self.h), level, out.ctypes.data_as(C.POINTER(C.c_uint64)))
+        return [int(x) for x in out]
+
+    def total_coeff_modulus_bit_count(self, level):
+        return _L().cdll.troyb_context_total_coeff_bits(_vp(self.h), level)
+
+    def using_keyswitching(self):
+        return bool(_L().cdll.troyb_context_using_keyswitching(_vp(self.h)))
+
+    def first_parms_id(self):
+        return 0
+
+    def last_parms_id(self):
+        return self.num_levels - 1
+
+    def key_parms_id(self):
+        return self.KEY_LEVEL if self.using_keyswitching() else 0
+
+    def bsk(self, level):
+        out = np.zeros(80, dtype=np.uint64)
+        n = _L().cdll.troyb_context_bsk(_vp(self.h), level, out.ctypes.data_as(C.POINTER(C.c_uint64)))
+        return [int(x) for x in out[:max(n, 0)]]
+
+    def root_powers(self, key_limb):
+        out = np.zeros((self.n, 2), dtype=np.uint64)
+        _L().call("troyb_context_root_powers", _vp(self.h), key_limb, out.ctypes.data_as(C.POINTER(C.c_uint64)))
+        return out
+
+    def galois_elt_from_step(self, step):
+        e = C.c_uint32()
+        _L().call("troyb_galois_elt_from_step", _vp(self.h), int(step), C.byref(e))
+        return e.value
+
+
+class CiphertextCuda:
+    """src/ciphertext_cuda.cuh:12-268: metadata + device words ``[batch][poly][limb][coeff]``."""
+
+    def __init__(self, context, level=0, size=2, is_ntt_form=False, scale=1.0, correction_factor=1, batch=1,
+                 capacity=None, data=None):
+        self.context = context
+        self.parms_id = int(level)
+        self.size = int(size)
+        self.is_ntt_form = bool(is_ntt_form)
+        self.scale = float(scale)
+        self.correction_factor = int(correction_factor)
+        self.batch = int(batch)
+        self.limbs = context.level_limbs(level)
+        self.capacity = max(int(capacity or 0), self.size)
+        self.data = data if data is not None else DeviceArray(self.batch * self.capacity * self.limbs * context.n)
+
+    # -- layout
+    @property
+    def poly_words(self):
+        return self.limbs * self.context.n
+
+    @property
+    def stride(self):
+        """words between consecutive batch elements"""
+        return self.capacity * self.poly_words
+
+    def poly_modulus_degree(self):
+        return self.context.n
+
+    def coeff_modulus_size(self):
+        return self.limbs
+
+    def ptr(self, poly=0, batch_index=0):
+        return self.data.at(batch_index * self.stride + poly * self.poly_words)
+
+    # -- host <-> device (CiphertextCuda(const Ciphertext&) / toHost, src/ciphertext_cuda.cuh:20-51)
+    @classmethod
+    def from_host(cls, context, words, level=0, is_ntt_form=False, scale=1.0, correction_factor=1, capacity=None):
+        w = np.ascontiguousarray(words, dtype=np.uint64)
+        if w.ndim == 3:
+            w = w[None]
+        if w.ndim != 4 or w.shape[2] != context.level_limbs(level) or w.shape[3] != context.n:
+            raise TroyInvalidArgument("encrypted is not valid for encryption parameters")
+        ct = cls(context, level, w.shape[1], is_ntt_form, scale, correction_factor, batch=w.shape[0], capacity=capacity)
+        for b in range(ct.batch):
+            ct.data.upload(w[b], b * ct.stride)
+        return ct
+
+    @classmethod
+    def from_device(cls, context, ptr, batch, size, level=0, is_ntt_form=False, scale=1.0, correction_factor=1,
+                    capacity=None):
+        cap = max(int(capacity or 0), size)
+        words = batch * cap * context.level_limbs(level) * context.n
+        return cls(context, level, size, is_ntt_form, scale, correction_factor, batch=batch, capacity=cap,
+                   data=ExternalArray(ptr, words))
+
+    def to_host(self):
+        out = np.empty((self.batch, self.size, self.limbs, self.context.n), dtype=np.uint64)
+        for b in range(self.batch):
+            buf = np.empty(self.size * self.poly_words, dtype=np.uint64)
+            _L().call("troyb_copy_to_host", buf.ctypes.data_as(C.c_void_p), _vp(self.ptr(0, b)), buf.size * 8, _vp(None))
+            out[b] = buf.reshape(self.size, self.limbs, self.context.n)
+        return out
+
+    def clone(self):
+        c = CiphertextCuda(self.context, self.parms_id, self.size, self.is_ntt_form, self.scale, self.correction_factor,
+                           self.batch, self.capacity)
+        _L().call("troyb_copy_on_device", _vp(c.data.ptr), _vp(self.data.ptr), self.batch * self.stride * 8, _vp(None))
+        return c
+
+    def reserve(self, capacity):
+        """src/ciphertext_cuda.cuh:68-152: grow the per-ciphertext capacity, preserving contents."""
+        if capacity <= self.capacity:
+            return
+        new = DeviceArray(self.batch * capacity * self.poly_words)
+        for b in range(self.batch):
+            _L().call("troyb_copy_on_device", _vp(new.at(b * capacity * self.poly_words)), _vp(self.ptr(0, b)),
+                      self.size * self.poly_words * 8, _vp(None))
+        self.data, self.capacity = new, capacity
+
+    def resize(self, size):
+        if size < 2 and size != 0:
+            raise TroyInvalidArgument("invalid size")
+        self.reserve(size)
+        self.size = size
+
+
+class KSwitchKeysCuda:
+    """src/kswitchkeys_cuda.cuh:31-366: ``keys[index]`` = one key-switching key, device words
+    ``[digit][2][key_limbs][N]`` in NTT form at the key level."""
+
+    def __init__(self, context):
+        self.context = context
+        self.parms_id = context.key_parms_id()
+        self.keys = []
+
+    @classmethod
+    def from_host(cls, context, words_by_index):
+        """words_by_index: {index: ndarray [digits][2][key_limbs][N]} (RelinKeysCuda(const RelinKeys&) upload)."""
+        k = cls(context)
+        n_key_limbs = context.level_limbs(SEALContextCuda.KEY_LEVEL)
+        digits = context.level_limbs(0)
+        size = max(words_by_index) + 1 if words_by_index else 0
+        k.keys = [None] * size
+        for idx, w in words_by_index.items():
+            a = np.ascontiguousarray(w, dtype=np.uint64)
+            if a.shape != (digits, 2, n_key_limbs, context.n):
+                raise TroyInvalidArgument("kswitch_keys is not valid for encryption parameters")
+            buf = DeviceArray(a.size)
+            buf.upload(a)
+            k.keys[idx] = buf
+        return k
+
+    def data(self, index):
+        if index >= len(self.keys) or self.keys[index] is None:
+            raise TroyOutOfRange("kswitch_keys_index")
+        return self.keys[index]
+
+
+class RelinKeysCuda(KSwitchKeysCuda):
+    """src/relinkeys_cuda.cuh."""
+
+    @staticmethod
+    def get_index(key_power):
+        if key_power < 2:
+            raise TroyInvalidArgument("key_power cannot be less than 2")
+        return key_power - 2
+
+    def has_key(self, key_power):
+        i = self.get_index(key_power)
+        return i < len(self.keys) and self.keys[i] is not None
+
+    def key(self, key_power):
+        return self.data(self.get_index(key_power))
+
+
+class GaloisKeysCuda(KSwitchKeysCuda):
+    """src/galoiskeys_cuda.cuh."""
+
+    @staticmethod
+    def get_index(galois_elt):
+        if not (galois_elt & 1) or galois_elt < 3:
+            raise TroyInvalidArgument("galois_elt is not valid")
+        return (galois_elt - 1) >> 1
+
+    def has_key(self, galois_elt):
+        i = self.get_index(galois_elt)
+        return i < len(self.keys) and self.keys[i] is not None
+
+    def key(self, galois_elt):
+        return self.data(self.get_index(galois_elt))
+
+
+def _naf(value):
+    """src/utils/numth.h:16-36."""
+    res = []
+    sign = value < 0
+    value = abs(value)
+    i = 0
+    while value:
+        zi = (2 - (value & 3)) if (value & 1) else 0
+        value = (value - zi) >> 1
+        if zi:
+            res.append((-zi if sign else zi) * (1 << i))
+        i += 1
+    return res
+
+
+class EvaluatorCuda:
+    """src/evaluator_cuda.cuh:17-440 — the methods on the RNS polynomial hot path. ``stream`` is a raw cudaStream_t
+    handle (e.g. ``torch.cuda.current_stream().cuda_stream``); ``None`` is the default stream like the reference."""
+
+    def __init__(self, context, stream=None):
+        self.context = context
+        self.stream = stream
+
+    # -- helpers
+    def _h(self):
+        return _vp(self.context.h)
+
+    def _s(self):
+        return _vp(self.stream)
+
+    def _check_scale(self, scale, level):
+        """isScaleWithinBounds, src/evaluator_cuda.cu:32-51."""
+        if self.context.scheme == CKKS:
+            bound = self.context.total_coeff_modulus_bit_count(level)
+        else:
+            bound = int(self.context.parms.plain_modulus).bit_length()
+        return not (scale <= 0 or int(math.log2(scale)) >= bound)
+
+    def _same_parms(self, a, b):
+        if a.parms_id != b.parms_id or a.batch != b.batch:
+            raise TroyInvalidArgument("encrypted1 and encrypted2 parameter mismatch")
+        if a.is_ntt_form != b.is_ntt_form:
+            raise TroyInvalidArgument("NTT form mismatch")
+
+    # -- add / sub / negate (src/evaluator_cuda.cu:143-260)
+    def negate_inplace(self, ct):
+        for b in range(ct.batch):
+            _L().call("troyb_negate", self._h(), ct.parms_id, _vp(ct.ptr(0, b)), _vp(ct.ptr(0, b)), ct.size, self._s())
+
+    def _addsub(self, name, a, b):
+        self._same_parms(a, b)
+        if a.correction_factor != b.correction_factor:
+            raise TroyLogicError("BGV correction-factor balancing is outside the ported path (SURVEY.md §8f)")
+        if self.context.scheme == CKKS and not math.isclose(a.scale, b.scale, rel_tol=1e-15):
+            raise TroyInvalidArgument("scale mismatch")
+        mn, mx = min(a.size, b.size), max(a.size, b.size)
+        a_old = a.size
+        a.resize(mx)
+        for i in range(a.batch):
+            _L().call(name, self._h(), a.parms_id, _vp(a.ptr(0, i)), _vp(b.ptr(0, i)), _vp(a.ptr(0, i)), mn, self._s())
+            if a_old < b.size:
+                words = (b.size - a_old) * a.poly_words
+                if name == "troyb_add":
+                    _L().call("troyb_copy_on_device", _vp(a.ptr(a_old, i)), _vp(b.ptr(a_old, i)), words * 8, self._s())
+                else:
+                    _L().call("troyb_negate", self._h(), a.parms_id, _vp(b.ptr(a_old, i)), _vp(a.ptr(a_old, i)),
+                              b.size - a_old, self._s())
+
+    def add_inplace(self, a, b):
+        self._addsub("troyb_add", a, b)
+
+    def sub_inplace(self, a, b):
+        self._addsub("troyb_sub", a, b)
+
+    # -- multiply / square (src/evaluator_cuda.cu:262-701)
+    def multiply_inplace(self, a, b):
+        self._same_parms(a, b)
+        scheme = self.context.scheme
+        if scheme == CKKS and not (a.is_ntt_form and b.is_ntt_form):
+            raise TroyInvalidArgument("encrypted1 or encrypted2 must be in NTT form")
+        if scheme != CKKS and (a.is_ntt_form or b.is_ntt_form):
+            raise TroyInvalidArgument("encrypted1 or encrypted2 cannot be in NTT form")
+        out_size = a.size + b.size - 1
+        new_scale = a.scale * b.scale
+        if scheme == CKKS and not self._check_scale(new_scale, a.parms_id):
+            raise TroyInvalidArgument("scale out of bounds")
+        a_size = a.size
+        b_ptr, b_stride = b.ptr(), b.stride  # taken before a possible reallocation when b is a
+        a.reserve(out_size)
+        if b is a:
+            b_ptr, b_stride = a.ptr(), a.stride
+        _L().call("troyb_multiply", self._h(), a.parms_id, _vp(a.ptr()), a_size, a.stride, _vp(b_ptr), b.size, b_stride,
+                  _vp(a.ptr()), a.stride, a.batch, self._s())
+        a.size = out_size
+        if scheme == CKKS:
+            a.scale = new_scale
+        if scheme == BGV:
+            a.correction_factor = (a.correction_factor * b.correction_factor) % self.context.parms.plain_modulus
+
+    def multiply(self, a, b, destination=None):
+        d = a.clone()
+        self.multiply_inplace(d, b)
+        return d
+
+    def square_inplace(self, a):
+        self.multiply_inplace(a, a)
+
+    # -- key switching (src/evaluator_cuda.cu:703-747, 1163-1378)
+    def _check_keyswitch(self, ct, keys):
+        scheme = self.context.scheme
+        if not self.context.using_keyswitching():
+            raise TroyLogicError("keyswitching is not supported by the context")
+        if keys.parms_id != self.context.key_parms_id():
+            raise TroyInvalidArgument("parameter mismatch")
+        if scheme == BFV and ct.is_ntt_form:
+            raise TroyInvalidArgument("BFV encrypted cannot be in NTT form")
+        if scheme == CKKS and not ct.is_ntt_form:
+            raise TroyInvalidArgument("CKKS encrypted must be in NTT form")
+        if scheme == BGV and ct.is_ntt_form:
+            raise TroyInvalidArgument("BGV encrypted cannot be in NTT form")
+
+    def relinearize_inplace(self, ct, relin_keys):
+        """relinearizeInternal(ct, keys, 2); only 3 -> 2 is on the ported path (§A.9)."""
+        if ct.size == 2:
+            return
+        if ct.size != 3:
+            raise TroyLogicError("relinearization of size > 3 is outside the ported path (SURVEY.md §A.9)")
+        self._check_keyswitch(ct, relin_keys)
+        if not relin_keys.has_key(2):
+            raise TroyInvalidArgument("not enough relinearization keys")
+        _L().call("troyb_relinearize", self._h(), ct.parms_id, _vp(ct.ptr()), ct.stride, _vp(relin_keys.key(2).ptr), ct.batch,
+                  self._s())
+        ct.size = 2
+
+    def switch_key_inplace(self, ct, target, keys, index):
+        """switchKeyInplace(ct, target, keys, index): target is a DeviceArray/[batch][L][N] buffer."""
+        self._check_keyswitch(ct, keys)
+        _L().call("troyb_switch_key", self._h(), ct.parms_id, _vp(ct.ptr()), ct.stride, _vp(target.ptr), ct.poly_words,
+                  _vp(keys.data(index).ptr), ct.batch, self._s())
+
+    # -- Galois / rotations (src/evaluator_cuda.cu:2024-2176)
+    def apply_galois_inplace(self, ct, galois_elt, galois_keys):
+        if galois_keys.parms_id != self.context.key_parms_id():
+            raise TroyInvalidArgument("galois_keys is not valid for encryption parameters")
+        if not (galois_elt & 1) or galois_elt >= 2 * self.context.n:
+            raise TroyInvalidArgument("Galois element is not valid")
+        if not galois_keys.has_key(galois_elt):
+            raise TroyInvalidArgument("Galois key not present")
+        if ct.size > 2:
+            raise TroyInvalidArgument("encrypted size must be 2")
+        self._check_keyswitch(ct, galois_keys)
+        _L().call("troyb_apply_galois", self._h(), ct.parms_id, _vp(ct.ptr()), ct.stride, galois_elt,
+                  _vp(galois_keys.key(galois_elt).ptr), ct.batch, self._s())
+
+    def _rotate_internal(self, ct, steps, galois_keys):
+        if galois_keys.parms_id != self.context.key_parms_id():
+            raise TroyInvalidArgument("galois_keys is not valid for encryption parameters")
+        if steps == 0:
+            return
+        elt = self.context.galois_elt_from_step(steps)
+        if galois_keys.has_key(elt):
+            self.apply_galois_inplace(ct, elt, galois_keys)
+            return
+        naf_steps = _naf(steps)
+        if len(naf_steps) == 1:
+            raise TroyInvalidArgument("Galois key not present")
+        for s in naf_steps:
+            if abs(s) != (self.context.n >> 1):
+                self._rotate_internal(ct, s, galois_keys)
+
+    def rotate_rows_inplace(self, ct, steps, galois_keys):
+        if self.context.scheme not in (BFV, BGV):
+            raise TroyLogicError("unsupported scheme")
+        self._rotate_internal(ct, steps, galois_keys)
+
+    def rotate_columns_inplace(self, ct, galois_keys):
+        if self.context.scheme not in (BFV, BGV):
+            raise TroyLogicError("unsupported scheme")
+        self.apply_galois_inplace(ct, self.context.galois_elt_from_step(0), galois_keys)
+
+    def rotate_vector_inplace(self, ct, steps, galois_keys):
+        if self.context.scheme != CKKS:
+            raise TroyLogicError("unsupported scheme")
+        self._rotate_internal(ct, steps, galois_keys)
+
+    def complex_conjugate_inplace(self, ct, galois_keys):
+        if self.context.scheme != CKKS:
+            raise TroyLogicError("unsupported scheme")
+        self.apply_galois_inplace(ct, self.context.galois_elt_from_step(0), galois_keys)
+
+    # -- rescale / mod switch (src/evaluator_cuda.cu:749-1010, 1380)
+    def _scale_to_next(self, ct):
+        scheme = self.context.scheme
+        if ct.parms_id + 1 >= self.context.num_levels:
+            raise TroyInvalidArgument("end of modulus switching chain reached")
+        if scheme == CKKS and not ct.is_ntt_form:
+            raise TroyInvalidArgument("CKKS encrypted must be in NTT form")
+        if scheme != CKKS and ct.is_ntt_form:
+            raise TroyInvalidArgument("BFV encrypted cannot be in NTT form" if scheme == BFV
+                                      else "BGV encrypted cannot be in NTT form")
+        q_last = self.context.level_moduli(ct.parms_id)[-1]
+        out = CiphertextCuda(self.context, ct.parms_id + 1, ct.size, ct.is_ntt_form, ct.scale, ct.correction_factor, ct.batch)
+        _L().call("troyb_mod_switch_scale_to_next", self._h(), ct.parms_id, _vp(ct.ptr()), ct.stride, _vp(out.ptr()),
+                  out.stride, ct.size, ct.batch, self._s())
+        if scheme == CKKS:
+            out.scale = ct.scale / float(q_last)
+        elif scheme == BGV:
+            t = self.context.parms.plain_modulus
+            out.correction_factor = (ct.correction_factor * pow(q_last % t, -1, t)) % t
+        return out
+
+    def _assign(self, dst, src):
+        dst.parms_id, dst.size, dst.is_ntt_form, dst.scale = src.parms_id, src.size, src.is_ntt_form, src.scale
+        dst.correction_factor, dst.batch, dst.limbs, dst.capacity, dst.data = \
+            src.correction_factor, src.batch, src.limbs, src.capacity, src.data
+
+    def rescale_to_next(self, ct):
+        if self.context.scheme != CKKS:
+            raise TroyInvalidArgument("unsupported operation for scheme type")
+        return self._scale_to_next(ct)
+
+    def rescale_to_next_inplace(self, ct):
+        self._assign(ct, self.rescale_to_next(ct))
+
+    def mod_switch_to_next(self, ct):
+        """modSwitchToNext: BFV/BGV scale-and-round; CKKS just drops the last limb (modSwitchDropToNext,
+        src/evaluator_cuda.cu:826-880)."""
+        if self.context.scheme != CKKS:
+            return self._scale_to_next(ct)
+        if ct.parms_id + 1 >= self.context.num_levels:
+            raise TroyInvalidArgument("end of modulus switching chain reached")
+        out = CiphertextCuda(self.context, ct.parms_id + 1, ct.size, ct.is_ntt_form, ct.scale, ct.correction_factor, ct.batch)
+        n = self.context.n
+        for b in range(ct.batch):
+            for p in range(ct.size):
+                _L().call("troyb_copy_on_device", _vp(out.ptr(p, b)), _vp(ct.ptr(p, b)), out.limbs * n * 8, self._s())
+        return out
+
+    def mod_switch_to_next_inplace(self, ct):
+        self._assign(ct, self.mod_switch_to_next(ct))
+
+    # -- NTT transforms (src/evaluator_cuda.cu:1950-2022)
+    def transform_to_ntt_inplace(self, ct):
+        if ct.is_ntt_form:
+            raise TroyInvalidArgument("encrypted is already in NTT form")
+        for b in range(ct.batch):
+            _L().call("troyb_ntt_forward", self._h(), ct.parms_id, _vp(ct.ptr(0, b)), ct.size, self._s())
+        ct.is_ntt_form = True
+
+    def transform_from_ntt_inplace(self, ct):
+        if not ct.is_ntt_form:
+            raise TroyInvalidArgument("encrypted_ntt is not in NTT form")
+        for b in range(ct.batch):
+            _L().call("troyb_ntt_inverse", self._h(), ct.parms_id, _vp(ct.ptr(0, b)), ct.size, self._s())
+        ct.is_ntt_form = False
+
+    def synchronize(self):
+        _L().call("troyb_stream_synchronize", self._s())
+
+    # camelCase aliases matching the reference's spelling
+    negateInplace, addInplace, subInplace = negate_inplace, add_inplace, sub_inplace
+    multiplyInplace, squareInplace, relinearizeInplace = multiply_inplace, square_inplace, relinearize_inplace
+    applyGaloisInplace, rotateRowsInplace, rotateColumnsInplace = apply_galois_inplace, rotate_rows_inplace, rotate_columns_inplace
+    rotateVectorInplace, complexConjugateInplace = rotate_vector_inplace, complex_conjugate_inplace
+    rescaleToNext, rescaleToNextInplace = rescale_to_next, rescale_to_next_inplace
+    modSwitchToNext, modSwitchToNextInplace = mod_switch_to_next, mod_switch_to_next_inplace
+    transformToNttInplace, transformFromNttInplace = transform_to_ntt_inplace, transform_from_ntt_inplace
