@@ -1,0 +1,17 @@
+"""`-m "not gpu"`: the library's own kernel sources, compiled for sequential CPU execution (tests/emul), against the
+reference CPU library. This checks host orchestration, table generation and kernel index arithmetic without a GPU;
+it is a debugging aid, not the product path (the GPU parity tests in test_parity_gpu.py are the parity tests proper)."""
+import numpy as np
+import pytest
+
+from common import run_evaluator_flow
+
+
+@pytest.mark.parametrize("scheme", [1, 2, 3])
+@pytest.mark.parametrize("n,bits", [(64, [40, 30, 30, 40]), (4096, [60, 40, 40, 60])])
+def test_evaluator_flow_emulated(ref, emul_lib, scheme, n, bits):
+    run_evaluator_flow(ref, emul_lib, scheme, n, bits, np.random.default_rng(100 + scheme))
+
+
+def test_batch_emulated(ref, emul_lib):
+    run_evaluator_flow(ref, emul_lib, ref.CKKS, 256, [40, 30, 30, 30, 40], np.random.default_rng(5), batch=3)

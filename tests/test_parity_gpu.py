@@ -1,0 +1,169 @@
+"""`-m gpu`: the parity tests proper. Every call goes through the C ABI of the CUDA library; every output word and the
+metadata are compared with the reference troy:: CPU library (oracle/_ref) on identical seeded keys and inputs."""
+import numpy as np
+import pytest
+
+from common import run_evaluator_flow
+
+pytestmark = pytest.mark.gpu
+
+FLOWS = [
+    # (scheme, N, coeff_modulus bits)            config in BASELINE.json
+    (1, 8192, [60, 40, 40, 60]),                  # config 1: BFV N=8192 {60,40,40,60}
+    (2, 16384, [60, 40, 40, 40, 40, 40, 40, 40, 60]),  # config 3: CKKS N=16384 L=8
+    (1, 32768, [60, 50, 50, 50, 60]),             # config 4: BFV N=32768, 4 data primes
+    (3, 32768, [60, 50, 50, 50, 60]),             # config 4: BGV
+    (2, 65536, [60, 50, 50, 50, 60]),             # config 5 shape at reduced limb count
+    (2, 4096, [60, 40, 40, 60]),
+    (3, 8192, [60, 40, 40, 60]),
+    (2, 64, [40, 30, 30, 40]),                    # the reference's toy sizes
+    (1, 128, [40, 30, 30, 40]),
+    (3, 32, [40, 30, 40]),
+]
+
+
+@pytest.mark.parametrize("scheme,n,bits", FLOWS)
+def test_evaluator_flow(ref, cuda_lib, scheme, n, bits):
+    run_evaluator_flow(ref, cuda_lib, scheme, n, bits, np.random.default_rng(1000 + n + scheme))
+
+
+def test_batched_flow(ref, cuda_lib):
+    run_evaluator_flow(ref, cuda_lib, ref.CKKS, 16384, [60, 40, 40, 40, 60], np.random.default_rng(77), batch=5)
+    run_evaluator_flow(ref, cuda_lib, ref.BFV, 8192, [60, 40, 40, 60], np.random.default_rng(78), batch=3)
+
+
+# ---- committed golden fixtures (generated from the reference by tests/golden/make_golden.py) ----------------------
+import os  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", ["ckks_n256", "bfv_n256", "bgv_n256", "ckks_n1024"])
+def test_golden_fixture(cuda_lib, name):
+    tb = cuda_lib
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    scheme, n, t = int(g["scheme"]), int(g["n"]), int(g["t"])
+    p = tb.EncryptionParameters(scheme)
+    p.set_poly_modulus_degree(n)
+    p.set_coeff_modulus([int(x) for x in g["q"]])
+    if t:
+        p.set_plain_modulus(t)
+    ctx = tb.SEALContextCuda(p)
+    ev = tb.EvaluatorCuda(ctx)
+    e1, ec = int(g["elt_step1"]), int(g["elt_conj"])
+    rlk = tb.RelinKeysCuda.from_host(ctx, {0: g["relin_key"]})
+    gk = tb.GaloisKeysCuda.from_host(ctx, {(e1 - 1) >> 1: g["galois_key_step1"], (ec - 1) >> 1: g["galois_key_conj"]})
+    assert np.array_equal(ctx.root_powers(0)[:, 0], g["root_powers_q0"])
+    ntt = scheme == 2
+    sc = float(g["scale"])
+    a = tb.CiphertextCuda.from_host(ctx, g["in_a"], 0, ntt, sc)
+    b = tb.CiphertextCuda.from_host(ctx, g["in_b"], 0, ntt, sc)
+    ev.multiply_inplace(a, b)
+    assert np.array_equal(a.to_host()[0], g["multiply"])
+    ev.relinearize_inplace(a, rlk)
+    assert np.array_equal(a.to_host()[0], g["relinearize"])
+    if ntt:
+        ev.rescale_to_next_inplace(a)
+        assert np.array_equal(a.to_host()[0], g["rescale"])
+        ev.rotate_vector_inplace(a, 1, gk)
+        assert np.array_equal(a.to_host()[0], g["rotate"])
+        ev.complex_conjugate_inplace(a, gk)
+        assert np.array_equal(a.to_host()[0], g["conjugate"])
+    else:
+        ev.rotate_rows_inplace(a, 1, gk)
+        assert np.array_equal(a.to_host()[0], g["rotate"])
+        ev.mod_switch_to_next_inplace(a)
+        assert np.array_equal(a.to_host()[0], g["mod_switch"])
+        ev.rotate_columns_inplace(a, gk)
+        assert np.array_equal(a.to_host()[0], g["rotate_columns"])
+        if scheme == 1:
+            assert ctx.bsk(0) == [int(x) for x in g["bsk"]]
+    assert a.scale == float(g["final_scale"]) and a.correction_factor == int(g["final_correction_factor"])
+
+
+# ---- full-size, size-independent properties (BASELINE.json config 2 and 5 shapes) --------------------------------------
+def _ckks_ctx(tb, n, n_data_limbs, bits=60):
+    from oracle import oracle as orc
+    q = orc.coeff_modulus_create(n, [bits] * (n_data_limbs + 1))
+    p = tb.EncryptionParameters(tb.SchemeType.ckks)
+    p.set_poly_modulus_degree(n)
+    p.set_coeff_modulus(q)
+    return tb.SEALContextCuda(p, expand_mod_chain=False), q
+
+
+@pytest.mark.parametrize("n,limbs", [(4096, 1), (8192, 3), (16384, 32), (32768, 8), (65536, 16), (65536, 32)])
+def test_ntt_sweep_round_trip_and_spot_check(cuda_lib, n, limbs):
+    """NTT sweep of config 2 (60-bit primes): inverse(forward(x)) == x on every word, forward is linear, and one limb
+    is checked word-for-word against the oracle."""
+    from oracle import oracle as orc
+    tb = cuda_lib
+    ctx, q = _ckks_ctx(tb, n, limbs)
+    ev = tb.EvaluatorCuda(ctx)
+    rng = np.random.default_rng(n + limbs)
+    polys = 3
+    x = np.stack([np.stack([rng.integers(0, m, n, dtype=np.uint64) for m in q[:limbs]]) for _ in range(polys)])
+    ct = tb.CiphertextCuda.from_host(ctx, x, 0, False)
+    ev.transform_to_ntt_inplace(ct)
+    f = ct.to_host()[0]
+    assert all((f[:, l, :] < q[l]).all() for l in range(limbs)), "outputs must be canonical residues"
+    l = limbs - 1
+    assert np.array_equal(f[1, l], orc.ntt_forward(q[l], x[1, l]))
+    # linearity: NTT(x0) + NTT(x1) == NTT(x0 + x1) (mod q)
+    s = np.stack([(x[0, k].astype(object) + x[1, k].astype(object)) % q[k] for k in range(limbs)]).astype(np.uint64)
+    cs = tb.CiphertextCuda.from_host(ctx, np.stack([s, s]), 0, False)
+    ev.transform_to_ntt_inplace(cs)
+    want = np.stack([(f[0, k].astype(object) + f[1, k].astype(object)) % q[k] for k in range(limbs)]).astype(np.uint64)
+    assert np.array_equal(cs.to_host()[0, 0], want)
+    ev.transform_from_ntt_inplace(ct)
+    assert np.array_equal(ct.to_host()[0], x)
+
+
+def test_large_keyswitch_against_oracle(cuda_lib):
+    """Config 5 shape (CKKS N=65536) at a limb count the C oracle finishes in seconds: relinearize word-for-word."""
+    from oracle import oracle as orc
+    tb = cuda_lib
+    n, L = 65536, 3
+    ctx, q = _ckks_ctx(tb, n, L, bits=55)
+    ev = tb.EvaluatorCuda(ctx)
+    rng = np.random.default_rng(9)
+    key = np.stack([np.stack([np.stack([rng.integers(0, m, n, dtype=np.uint64) for m in q]) for _ in range(2)]) for _ in range(L)])
+    ct3 = np.stack([np.stack([rng.integers(0, m, n, dtype=np.uint64) for m in q[:L]]) for _ in range(3)])
+    rlk = tb.RelinKeysCuda.from_host(ctx, {0: key})
+    a = tb.CiphertextCuda.from_host(ctx, ct3, 0, True, 2.0 ** 40)
+    ev.relinearize_inplace(a, rlk)
+    want = orc.switch_key(orc.CKKS, q, 0, ct3[:2], ct3[2], key)
+    assert np.array_equal(a.to_host()[0], want)
+
+
+def test_error_behaviour(cuda_lib):
+    """Argument errors surface as the reference's exception kinds before any launch."""
+    tb = cuda_lib
+    from troy_b200.lib import TroyInvalidArgument, TroyLogicError
+    ctx, q = _ckks_ctx(tb, 4096, 2)
+    ev = tb.EvaluatorCuda(ctx)
+    x = np.zeros((2, 2, 4096), dtype=np.uint64)
+    ct = tb.CiphertextCuda.from_host(ctx, x, 0, False, 2.0 ** 20)
+    with pytest.raises(TroyInvalidArgument):
+        ev.multiply_inplace(ct, ct)  # CKKS operands must be in NTT form
+    with pytest.raises(TroyInvalidArgument):
+        ev.transform_from_ntt_inplace(ct)
+    gk = tb.GaloisKeysCuda(ctx)
+    ct.is_ntt_form = True
+    with pytest.raises(TroyInvalidArgument, match="Galois key not present"):
+        ev.rotate_vector_inplace(ct, 1, gk)
+    with pytest.raises(TroyInvalidArgument):
+        ev.rescale_to_next(tb.CiphertextCuda.from_host(ctx, x, 0, False))
+    p = tb.EncryptionParameters(tb.SchemeType.bfv)
+    p.set_poly_modulus_degree(4096)
+    p.set_coeff_modulus(q[:1])
+    p.set_plain_modulus(65537)
+    one = tb.SEALContextCuda(p)
+    assert not one.using_keyswitching()
+    with pytest.raises(TroyLogicError, match="keyswitching is not supported"):
+        c3 = tb.CiphertextCuda.from_host(one, np.zeros((3, 1, 4096), dtype=np.uint64), 0, False)
+        tb.EvaluatorCuda(one).relinearize_inplace(c3, tb.RelinKeysCuda(one))
+    with pytest.raises(TroyInvalidArgument):
+        bad = tb.EncryptionParameters(tb.SchemeType.ckks)
+        bad.set_poly_modulus_degree(4096)
+        bad.set_coeff_modulus([q[0], q[0]])
+        tb.SEALContextCuda(bad)

@@ -166,27 +166,36 @@ void switch_key_impl(Context *ctx, int level, u64 *ct, u64 ct_stride, const u64 
     LimbMap kmap = ctx->map_prefix(L);
     kmap.idx[L] = (uint8_t)ctx->pool_special;
 
-    // keep the mod-up scratch of one chunk inside the L2 (126 MB on B200)
+    // Only the mod-up output D ([L+1][L] limbs per ciphertext) is large; it is produced and consumed chunk by chunk so
+    // that it stays inside the 126 MB L2, with the chunk sized to fill whole waves of CTAs on the 148 SMs. Everything
+    // else runs once over the whole batch.
     const u64 per_ct_words = (u64)Lp * L * N;
-    u32 chunk = (u32)std::max<u64>(1, (48ull << 20) / (per_ct_words * 8));
-    chunk = std::min(chunk, batch);
+    const u32 wave = 148u * (ctx->logN >= 14 ? 1u : (ctx->logN == 13 ? 2u : 4u)); // CTAs resident per wave
+    const u32 ctas_per_ct = Lp * L * (ctx->logN > 14 ? (1u << (ctx->logN - 12)) : 1u);
+    const u32 max_chunk = (u32)std::max<u64>(1, (64ull << 20) / (per_ct_words * 8));
+    u32 chunk = 1;
+    double best = 0;
+    for (u32 c = 1; c <= std::min(max_chunk, batch); c++) {
+        u64 ctas = (u64)c * ctas_per_ct;
+        double util = (double)ctas / (double)(((ctas + wave - 1) / wave) * wave);
+        if (util >= best - 1e-9) { best = util; chunk = c; }
+    }
 
-    Scratch t_target(ckks ? (size_t)chunk * L * N : 0, s);
+    Scratch t_target(ckks ? (size_t)batch * L * N : 0, s);
     Scratch D((size_t)chunk * per_ct_words, s);
-    Scratch prod((size_t)chunk * 2 * Lp * N, s);
-    Scratch sp((size_t)chunk * 2 * N, s);
+    Scratch prod((size_t)batch * 2 * Lp * N, s);
+    Scratch sp((size_t)batch * 2 * N, s);
 
+    if (ckks) ntt_plain(ctx, true, kmap, L, target, target_stride, t_target.p, (u64)L * N, L, batch, true, s);
     for (u32 b0 = 0; b0 < batch; b0 += chunk) {
         const u32 nb = std::min(chunk, batch - b0);
         const u64 *tgt = target + (u64)b0 * target_stride;
-        u64 *cts = ct + (u64)b0 * ct_stride;
-        if (ckks) ntt_plain(ctx, true, kmap, L, tgt, target_stride, t_target.p, (u64)L * N, L, nb, true, s);
         {
             NttArgs a{};
             a.mode = FWD_MODUP;
             a.map = kmap;
             a.L = L;
-            a.src = ckks ? t_target.p : tgt;
+            a.src = ckks ? t_target.p + (u64)b0 * L * N : tgt;
             a.src_unit_stride = ckks ? (u64)L * N : target_stride;
             a.aux0 = ckks ? tgt : nullptr;
             a.aux0_batch_stride = target_stride;
@@ -205,43 +214,43 @@ void switch_key_impl(Context *ctx, int level, u64 *ct, u64 ct_stride, const u64 
             k.total = (u64)nb * Lp * N;
             k.D = D.p;
             k.key = key;
-            k.prod = prod.p;
+            k.prod = prod.p + (u64)b0 * 2 * Lp * N;
             ck(launch_cta(k, grid_for(k.total, KsInnerProduct::kThreads), 0, s));
         }
-        {
-            NttArgs a{};
-            a.mode = INV_ADD_HALF;
-            a.map = kmap;
-            a.L = L;
-            a.K = 2;
-            a.src = prod.p;
-            a.src_offset = (u64)L * N;
-            a.src_unit_stride = 2ull * Lp * N;
-            a.src_poly_stride = (u64)Lp * N;
-            a.dst = sp.p;
-            a.drop = ctx->key_drop;
-            a.add_half = ctx->scheme != SCHEME_BGV;
-            a.scheme = ctx->scheme;
-            run_inv(ctx, a, nb * 2, s);
-        }
-        {
-            NttArgs a{};
-            a.mode = ckks ? FWD_MODDOWN : INV_COMBINE;
-            a.map = kmap;
-            a.L = L;
-            a.K = 2;
-            a.aux0 = prod.p;
-            a.acc_batch_stride = 2ull * Lp * N;
-            a.acc_poly_stride = (u64)Lp * N;
-            a.aux1 = sp.p;
-            a.ct = cts;
-            a.ct_batch_stride = ct_stride;
-            a.ct_poly_stride = (u64)L * N;
-            a.drop = ctx->key_drop;
-            a.scheme = ctx->scheme;
-            if (ckks) run_fwd(ctx, a, nb * 2 * L, s);
-            else run_inv(ctx, a, nb * 2 * L, s);
-        }
+    }
+    {
+        NttArgs a{};
+        a.mode = INV_ADD_HALF;
+        a.map = kmap;
+        a.L = L;
+        a.K = 2;
+        a.src = prod.p;
+        a.src_offset = (u64)L * N;
+        a.src_unit_stride = 2ull * Lp * N;
+        a.src_poly_stride = (u64)Lp * N;
+        a.dst = sp.p;
+        a.drop = ctx->key_drop;
+        a.add_half = ctx->scheme != SCHEME_BGV;
+        a.scheme = ctx->scheme;
+        run_inv(ctx, a, batch * 2, s);
+    }
+    {
+        NttArgs a{};
+        a.mode = ckks ? FWD_MODDOWN : INV_COMBINE;
+        a.map = kmap;
+        a.L = L;
+        a.K = 2;
+        a.aux0 = prod.p;
+        a.acc_batch_stride = 2ull * Lp * N;
+        a.acc_poly_stride = (u64)Lp * N;
+        a.aux1 = sp.p;
+        a.ct = ct;
+        a.ct_batch_stride = ct_stride;
+        a.ct_poly_stride = (u64)L * N;
+        a.drop = ctx->key_drop;
+        a.scheme = ctx->scheme;
+        if (ckks) run_fwd(ctx, a, batch * 2 * L, s);
+        else run_inv(ctx, a, batch * 2 * L, s);
     }
 }
 
