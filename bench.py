@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py — the driver's measurement contract for troy_b200.
+
+Workload (BASELINE.json configs[2], the configuration its metric is quoted on): CKKS, N = 16384, L = 8 data primes +
+1 special prime {60, 40x7, 60}, scale 2^40; synthetic random ciphertexts and key-switching keys (uniform residues).
+One "step" = Evaluator::multiply followed by Evaluator::relinearize_inplace on a batch of independent ciphertext pairs.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path on the host cores
+
+One JSON line on stdout (rank 0). Extra keys `rotate`, `rescale`, `ntt` report the other quantities BASELINE.json's
+metric names (rotate ops/s, limb-NTT/s and fraction of the HBM roofline).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N, L, BITS = 16384, 8, [60] + [40] * 7 + [60]
+SCALE = 2.0 ** 40
+METRIC, UNIT = "ckks_n16384_mult_relin_ops_per_s", "ops/s"
+WORKLOAD = "CKKS N=16384 L=8 {60,40x7,60} scale 2^40: multiply+relinearize on a batch of synthetic ciphertext pairs"
+
+
+def algo_bytes():
+    """SURVEY.md §8(d) per-unit algorithmic HBM bytes."""
+    return dict(limb_ntt=16 * N, multiply=56 * L * N, keyswitch=8 * N * (2 * L * L + 7 * L),
+                rotate=8 * N * (2 * L * L + 11 * L), rescale=8 * N * (4 * L - 2))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc = device, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference arm: the reference's own troy:: CPU implementation (oracle/_ref, compiled from /root/reference) on
+    every host core, same config, metric and unit; each step is a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import ref
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libtroyref.so was not built"}))
+        return
+    cores = os.cpu_count() or 1
+    q = ref.coeff_modulus_create(N, BITS)
+    rc = ref.RefContext(ref.CKKS, N, q)
+    rng = np.random.default_rng(0)
+    kq = rc.level_moduli(-1)
+    key = np.stack([np.stack([np.stack([rng.integers(0, m, N, dtype=np.uint64) for m in kq]) for _ in range(2)]) for _ in range(L)])
+    rlk = rc.synthetic_keys(False, 1)
+    rlk.set_words(0, key)
+    w = np.stack([np.stack([rng.integers(0, m, N, dtype=np.uint64) for m in q[:L]]) for _ in range(2)])
+    a, b = rc.ciphertext(w, 0, True, SCALE), rc.ciphertext(w, 0, True, SCALE)
+    reps = args.ref_reps
+    for _ in range(args.warmup):
+        rc.time_ops(0, a, b, rlk, None, 0, 1, cores)
+    t = 0.0
+    for _ in range(args.steps):
+        t += rc.time_ops(0, a, b, rlk, None, 0, reps, cores)
+    ops = args.steps * reps * cores
+    value = ops / t
+    sample = f"{reps} multiply+relinearize per thread x {cores} threads per step (one independent Evaluator per thread)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_step": reps * cores, "l2": "n/a (host)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import troy_b200 as tb
+    from troy_b200.lib import library
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    tb.KernelProvider.initialize(local)
+    lib = library()
+    B = args.batch
+    bytes_ = algo_bytes()
+    hbm_peak, peak_kind = measured_peaks()
+
+    q = tb.CoeffModulus.Create(N, BITS)
+    parms = tb.EncryptionParameters(tb.SchemeType.ckks)
+    parms.set_poly_modulus_degree(N)
+    parms.set_coeff_modulus(q)
+    ctx = tb.SEALContextCuda(parms)
+    stream = torch.cuda.current_stream().cuda_stream
+    ev = tb.EvaluatorCuda(ctx, stream=stream)
+
+    # synthetic keys and ciphertexts: uniform residues (values do not change the work)
+    g = torch.Generator(device=dev)
+    g.manual_seed(0x5EED0000 + rank)
+
+    def uniform(shape_prefix, moduli):
+        out = torch.empty(*shape_prefix, len(moduli), N, dtype=torch.int64, device=dev)
+        for i, m in enumerate(moduli):
+            out[..., i, :] = torch.randint(0, m, (*shape_prefix, N), generator=g, device=dev, dtype=torch.int64)
+        return out
+
+    kq = ctx.level_moduli(-1)
+    key_t = uniform((L, 2), kq)
+    gkey_t = uniform((L, 2), kq)
+    rlk = tb.RelinKeysCuda(ctx)
+    rlk.keys = [tb.host.ExternalArray(key_t.data_ptr(), key_t.numel())]
+    elt = ctx.galois_elt_from_step(1)
+    gk = tb.GaloisKeysCuda(ctx)
+    gk.keys = [None] * (((elt - 1) >> 1) + 1)
+    gk.keys[(elt - 1) >> 1] = tb.host.ExternalArray(gkey_t.data_ptr(), gkey_t.numel())
+
+    a_in = uniform((B, 2), q[:L])           # pristine inputs
+    b_in = uniform((B, 2), q[:L])
+    a_work = torch.empty(B, 3, L, N, dtype=torch.int64, device=dev)  # capacity 3: multiply writes the third polynomial
+    a_ct = tb.CiphertextCuda.from_device(ctx, a_work.data_ptr(), B, 2, 0, True, SCALE, capacity=3)
+    b_ct = tb.CiphertextCuda.from_device(ctx, b_in.data_ptr(), B, 2, 0, True, SCALE)
+
+    def reset_a():
+        a_work[:, :2].copy_(a_in)
+        a_ct.size, a_ct.scale = 2, SCALE
+
+    def step():
+        reset_a()
+        ev.multiply_inplace(a_ct, b_ct)
+        ev.relinearize_inplace(a_ct, rlk)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """K steps between barriers, CUDA events on the launching stream, max over ranks (seconds)."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.cdll.troyb_launch_count()
+    t_main = timed(step, args.steps)
+    launches = lib.cdll.troyb_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / t_main
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
+    a_host = torch.empty(B, 2, L, N, dtype=torch.int64).pin_memory()
+    b_host = torch.empty(B, 2, L, N, dtype=torch.int64).pin_memory()
+    out_host = torch.empty(B, 2, L, N, dtype=torch.int64).pin_memory()
+    a_host.copy_(a_in)
+    b_host.copy_(b_in)
+    b_dev = torch.empty(B, 2, L, N, dtype=torch.int64, device=dev)
+    b2_ct = tb.CiphertextCuda.from_device(ctx, b_dev.data_ptr(), B, 2, 0, True, SCALE)
+
+    def step_e2e():
+        a_work[:, :2].copy_(a_host, non_blocking=True)
+        b_dev.copy_(b_host, non_blocking=True)
+        a_ct.size, a_ct.scale = 2, SCALE
+        ev.multiply_inplace(a_ct, b2_ct)
+        ev.relinearize_inplace(a_ct, rlk)
+        out_host.copy_(a_work[:, :2], non_blocking=True)
+
+    for _ in range(2):
+        step_e2e()
+    e2e_steps = max(2, min(args.steps, 5))
+    t_e2e = timed(step_e2e, e2e_steps)
+    e2e = {"value": world * B * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * a_host.numel() * 8,
+           "d2h_bytes_per_step": out_host.numel() * 8}
+
+    # ---- the other quantities the metric names: rotate, rescale, standalone NTT
+    def rot():
+        reset_a()
+        ev.rotate_vector_inplace(a_ct, 1, gk)
+
+    def resc():
+        reset_a()
+        ev.rescale_to_next(a_ct)
+
+    extra_steps = max(2, min(args.steps, 5))
+    t_rot = timed(rot, extra_steps)
+    t_resc = timed(resc, extra_steps)
+    ntt_polys = 512  # 512 polys x 8 limbs x 128 KiB = 512 MiB > L2
+    ntt_buf = uniform((ntt_polys,), q[:L])
+
+    def ntt_f():
+        lib.call("troyb_ntt_forward", C.c_void_p(ctx.h), 0, C.c_void_p(ntt_buf.data_ptr()), ntt_polys, C.c_void_p(stream))
+
+    def ntt_i():
+        lib.call("troyb_ntt_inverse", C.c_void_p(ctx.h), 0, C.c_void_p(ntt_buf.data_ptr()), ntt_polys, C.c_void_p(stream))
+
+    ntt_f()
+    ntt_i()
+    t_nf = timed(ntt_f, extra_steps)
+    t_ni = timed(ntt_i, extra_steps)
+    limbs = ntt_polys * L
+
+    # ---- per-kernel device time of one step (CUDA events around every launch) for the roofline of the dominant kernel
+    lib.call("troyb_profile_enable", 1)
+    step()
+    buf = C.create_string_buffer(1 << 16)
+    lib.call("troyb_profile_report", buf, len(buf))
+    lib.call("troyb_profile_enable", 0)
+    kernels = [json.loads(x) for x in buf.value.decode().strip().splitlines() if x]
+    total_ms = sum(k["ms"] for k in kernels) or 1.0
+    for k in kernels:
+        k["share"] = k["ms"] / total_ms
+    dom = max(kernels, key=lambda k: k["ms"])
+    # algorithmic bytes of one launch of the dominant kernel: every NTT-family CTA (unit) reads and writes one limb
+    if dom["kernel"].startswith("ntt_"):
+        dom_bytes = dom["grid"] / dom["launches"] * bytes_["limb_ntt"]
+    elif dom["kernel"] == "ks_inner_product":
+        dom_bytes = B * (L + 1) * N * 8 * (L + 2 * L + 2) / dom["launches"]
+    else:
+        dom_bytes = B * bytes_["multiply"] / dom["launches"]
+    dom_s = dom["ms"] * 1e-3 / dom["launches"]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get(dom["kernel"])
+    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom_bytes / dom_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": dom_bytes / dom_s / 1e9 / hbm_peak, "traffic": traffic, "peak_source": peak_kind,
+                "share_of_step": dom["share"],
+                "note": "NTT butterflies are bound by the integer-multiply pipe, not HBM (DESIGN.md §roofline)"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    # ---- CPU baseline: the reference's own CPU path on this box's host cores, bounded sample
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import ref
+            if ref.available():
+                cores = os.cpu_count() or 1
+                rc = ref.RefContext(ref.CKKS, N, q)
+                key_np = key_t.cpu().numpy().astype(np.uint64)
+                r_rlk = rc.synthetic_keys(False, 1)
+                r_rlk.set_words(0, key_np)
+                w = a_in[0].cpu().numpy().astype(np.uint64)
+                ra, rb = rc.ciphertext(w, 0, True, SCALE), rc.ciphertext(w, 0, True, SCALE)
+                rc.time_ops(0, ra, rb, r_rlk, None, 0, 1, cores)
+                reps = 6
+                t0 = time.time()
+                tt = rc.time_ops(0, ra, rb, r_rlk, None, 0, reps, cores)
+                cpu = {"value": reps * cores / tt, "unit": UNIT, "cores": cores, "kind": "reference",
+                       "sample": f"{reps} multiply+relinearize per thread x {cores} threads, troy:: CPU Evaluator per thread "
+                                 f"({time.time() - t0:.1f} s wall)"}
+        except Exception as e:  # the baseline is reporting only; never fail the bench for it
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": t_main / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "parallelism": f"{world} independent ciphertext shards, no collective",
+                   "l2": f"inputs {B * 5 * L * N * 8 >> 20} MiB per step > 126 MiB L2 (no explicit flush)"},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "mult_relin_frac_of_hbm_roofline": value / world * (bytes_["multiply"] + bytes_["keyswitch"]) / 1e9 / hbm_peak,
+        "rotate": {"value": world * B * extra_steps / t_rot, "unit": "ops/s",
+                   "frac_of_hbm_roofline": B * extra_steps / t_rot * bytes_["rotate"] / 1e9 / hbm_peak},
+        "rescale": {"value": world * B * extra_steps / t_resc, "unit": "ops/s",
+                    "frac_of_hbm_roofline": B * extra_steps / t_resc * bytes_["rescale"] / 1e9 / hbm_peak},
+        "ntt": {"forward_limb_ntt_per_s": world * limbs * extra_steps / t_nf, "inverse_limb_ntt_per_s": world * limbs * extra_steps / t_ni,
+                "forward_gbs": limbs * extra_steps / t_nf * bytes_["limb_ntt"] / 1e9,
+                "forward_frac_of_hbm_roofline": limbs * extra_steps / t_nf * bytes_["limb_ntt"] / 1e9 / hbm_peak,
+                "inverse_frac_of_hbm_roofline": limbs * extra_steps / t_ni * bytes_["limb_ntt"] / 1e9 / hbm_peak,
+                "shape": f"{ntt_polys} polys x {L} limbs, N={N}"},
+        "kernels": kernels,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=128, help="ciphertext pairs per GPU per step")
+    ap.add_argument("--ref-reps", type=int, default=4, help="reference arm: ops per thread per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -43,6 +43,17 @@ const char *troyb_last_error(void);
 int troyb_initialize(int device);
 int troyb_initialized(void);
 
+/* Number of kernels this library has launched so far in this process (diagnostic used by bench.py). */
+uint64_t troyb_launch_count(void);
+
+/* Per-kernel device timing for bench.py's roofline (CUDA events around every launch while enabled; off by default).
+ * troyb_profile_report writes JSON lines {"kernel","launches","grid","ms"} aggregated by kernel name and clears the log. */
+int troyb_profile_enable(int on);
+int troyb_profile_report(char *buf, size_t buf_bytes);
+
+/* CoeffModulus::Create(poly_modulus_degree, bit_sizes)  src/modulus.cpp:80-122 (PlainModulus::Batching is the 1-element case) */
+int troyb_coeff_modulus_create(uint64_t poly_modulus_degree, const int *bit_sizes, int count, uint64_t *out);
+
 /* KernelProvider::malloc / free / copy / retrieve / memset  src/kernelprovider.cuh:35-83 (stream-ordered) */
 int troyb_malloc(void **d_ptr, size_t bytes, void *stream);
 int troyb_free(void *d_ptr, void *stream);

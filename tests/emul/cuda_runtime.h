@@ -51,3 +51,7 @@ inline unsigned __brev(unsigned x) {
     for (int i = 0; i < 32; i++) r |= ((x >> i) & 1u) << (31 - i);
     return r;
 }
+typedef void *cudaEvent_t;
+inline cudaError_t cudaDeviceSynchronize() { return 0; }
+inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0; return 0; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }

@@ -4,9 +4,11 @@
 #include "context.h"
 #include "kernels_elt.cuh"
 #include "kernels_ntt.cuh"
+#include "hostmath.h"
 
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 
@@ -274,6 +276,65 @@ int troyb_initialize(int device) {
 }
 
 int troyb_initialized(void) { return g_initialized ? 1 : 0; }
+
+uint64_t troyb_launch_count(void) { return launch_counter(); }
+
+int troyb_profile_enable(int on) {
+    profiler().enabled = on != 0;
+    return TROYB_OK;
+}
+
+int troyb_profile_report(char *buf, size_t buf_bytes) {
+    API_BEGIN
+    Profiler &p = profiler();
+    ck(cudaDeviceSynchronize());
+    struct Agg { std::string name; unsigned long long launches = 0, grid = 0; double ms = 0; };
+    std::vector<Agg> aggs;
+    for (auto &r : p.records) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+        Agg *a = nullptr;
+        for (auto &x : aggs) if (x.name == r.name) a = &x;
+        if (!a) { aggs.push_back(Agg{}); a = &aggs.back(); a->name = r.name; }
+        a->launches++; a->grid += r.grid; a->ms += ms;
+    }
+    p.records.clear();
+    std::string out;
+    for (auto &a : aggs) {
+        char line[256];
+        snprintf(line, sizeof line, "{\"kernel\": \"%s\", \"launches\": %llu, \"grid\": %llu, \"ms\": %.6f}\n", a.name.c_str(), a.launches, a.grid, a.ms);
+        out += line;
+    }
+    if (buf && buf_bytes) {
+        size_t n = std::min(out.size(), buf_bytes - 1);
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    API_END
+}
+
+int troyb_coeff_modulus_create(uint64_t n, const int *bit_sizes, int count, uint64_t *out) {
+    API_BEGIN
+    if (!bit_sizes || !out || count < 0 || count > 64) throw std::invalid_argument("bit_sizes is invalid");
+    if (n < 2 || n > 131072 || (n & (n - 1))) throw std::invalid_argument("poly_modulus_degree is invalid");
+    std::vector<std::vector<u64>> lists(64);
+    for (int i = 0; i < count; i++) {
+        int b = bit_sizes[i];
+        if (b < 2 || b > 60) throw std::invalid_argument("bit_sizes is invalid");
+        if (lists[b].empty()) {
+            size_t need = 0;
+            for (int j = 0; j < count; j++) need += bit_sizes[j] == b;
+            lists[b] = host::get_primes(2 * n, b, need);
+        }
+    }
+    for (int i = 0; i < count; i++) {
+        out[i] = lists[bit_sizes[i]].back();
+        lists[bit_sizes[i]].pop_back();
+    }
+    API_END
+}
 
 int troyb_malloc(void **d_ptr, size_t bytes, void *stream) {
     API_BEGIN

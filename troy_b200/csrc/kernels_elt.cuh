@@ -19,6 +19,7 @@ TB_D void mac128(u64 &lo, u64 &hi, u64 a, u64 b) {
 // kAddPolyCoeffmod / kSubPolyCoeffmod / kNegatePolyCoeffmod   src/kernelutils.cu:30-58, 505-535, 300-328
 struct EltAddSub {
     static constexpr int kThreads = kEltThreads;
+    const char *name() const { return "elt_add_sub_negate"; }
     int op; // 0 add, 1 sub, 2 negate
     int logN;
     const ModDev *mods;
@@ -50,6 +51,7 @@ struct EltAddSub {
 // a, b, out may alias (in-place multiply): a thread reads every input word it needs before it writes.
 struct EltTensor {
     static constexpr int kThreads = kEltThreads;
+    const char *name() const { return "ct_tensor_product"; }
     int logN;
     const ModDev *mods;
     LimbMap map;
@@ -109,6 +111,7 @@ struct EltTensor {
 //   prod : [batch][2][L+1][N]  (t_poly_prod layout, §A.8)
 struct KsInnerProduct {
     static constexpr int kThreads = kEltThreads;
+    const char *name() const { return "ks_inner_product"; }
     int logN;
     const ModDev *mods;
     LimbMap map; // output modulus i -> pool index (i == L -> special)
@@ -154,6 +157,7 @@ struct KsInnerProduct {
 // gApplyGaloisNtt (NTT form, gather)        src/utils/galois_cuda.cu:181-196 ; table rule src/utils/galois_cuda.cu:26-42
 struct EltGalois {
     static constexpr int kThreads = kEltThreads;
+    const char *name() const { return "galois_permute"; }
     int logN;
     int ntt_form;
     const ModDev *mods;
@@ -198,6 +202,7 @@ struct EltGalois {
 //   in  : [batch*polys][L][N]   out : [batch*polys][L-1][N]
 struct EltDropLast {
     static constexpr int kThreads = kEltThreads;
+    const char *name() const { return "drop_last_coeff"; }
     int logN;
     int scheme;
     const ModDev *mods;
@@ -249,6 +254,7 @@ constexpr int kBehzMax = 40;
 
 struct BehzExtend {
     static constexpr int kThreads = kEltThreads;
+    const char *name() const { return "behz_extend"; }
     int logN;
     const ModDev *mods;
     LimbMap map; // q_0..q_{L-1}, B.., m_sk
@@ -301,6 +307,7 @@ struct BehzExtend {
 //   in  : [polys][L+nBsk][N]  (coefficient form, canonical, after INTT)     out : [polys][L][N]
 struct BehzFloorSk {
     static constexpr int kThreads = kEltThreads;
+    const char *name() const { return "behz_floor_sk"; }
     int logN;
     const ModDev *mods;
     LimbMap map;

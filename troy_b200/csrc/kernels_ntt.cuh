@@ -99,6 +99,20 @@ TB_D void small_ntt_inv(u64 *sm, u32 logn, Ld ld, St st, const u64 *__restrict__
     TB_PHASE(256, t, for (u32 i = t; i < n; i += 256) st(i, sm[i]);)
 }
 
+inline const char *ntt_kernel_name(int mode, int pass) {
+    // pass: 0 whole tile / row pass of the inverse, 1 four-step column pass, 2 four-step row pass of the forward
+    static const char *names[6][3] = {
+        {"ntt_fwd", "ntt_fwd_cols", "ntt_fwd_rows"},
+        {"ntt_fwd_modup", "ntt_fwd_modup_cols", "ntt_fwd_modup_rows"},
+        {"ntt_fwd_moddown", "ntt_fwd_moddown_cols", "ntt_fwd_moddown_rows"},
+        {"ntt_inv", "ntt_inv_cols", "ntt_inv"},
+        {"ntt_inv_add_half", "ntt_inv_add_half_cols", "ntt_inv_add_half"},
+        {"ntt_inv_combine", "ntt_inv_combine_cols", "ntt_inv_combine"},
+    };
+    int row = mode >= 10 ? 3 + (mode - 10) : mode;
+    return names[row][pass];
+}
+
 TB_D u64 canon4(u64 v, u64 p) {
     u64 p2 = p << 1;
     v -= (v >= p2 ? p2 : 0);
@@ -182,6 +196,7 @@ template <int LOGT> TB_D NttUnit resolve_unit(const NttArgs &a, u32 bid) {
 template <int LOGT> struct NttFwd {
     static constexpr int kThreads = LOGT == 0 ? 256 : (1 << (LOGT == 0 ? 4 : LOGT)) / 16;
     NttArgs a;
+    const char *name() const { return ntt_kernel_name(a.mode, a.row_pass ? 2 : 0); }
     TB_D void operator()(u32 bid, u64 *sm) const {
         const NttUnit u = resolve_unit<LOGT>(a, bid);
         const ModDev *md = u.md;
@@ -228,6 +243,7 @@ template <int LOGT> struct NttFwd {
 template <int LOGT> struct NttInv {
     static constexpr int kThreads = LOGT == 0 ? 256 : (1 << (LOGT == 0 ? 4 : LOGT)) / 16;
     NttArgs a;
+    const char *name() const { return ntt_kernel_name(a.mode, 0); }
     TB_D void operator()(u32 bid, u64 *sm) const {
         const NttUnit u = resolve_unit<LOGT>(a, bid);
         const ModDev *md = u.md;
@@ -288,6 +304,7 @@ template <int LOGT> struct NttInv {
 template <int LOGN> struct NttFwdCols {
     static constexpr int kThreads = 256;
     NttArgs a;
+    const char *name() const { return ntt_kernel_name(a.mode, 1); }
     TB_D void operator()(u32 bid, u64 *) const {
         constexpr u32 NTV = (1u << LOGN) / 16, CPB = NTV / kThreads;
         const u32 chunk = bid % CPB;
@@ -323,6 +340,7 @@ template <int LOGN> struct NttFwdCols {
 template <int LOGN> struct NttInvCols {
     static constexpr int kThreads = 256;
     NttArgs a;
+    const char *name() const { return ntt_kernel_name(a.mode, 1); }
     TB_D void operator()(u32 bid, u64 *) const {
         constexpr u32 NTV = (1u << LOGN) / 16, CPB = NTV / kThreads;
         const u32 chunk = bid % CPB;

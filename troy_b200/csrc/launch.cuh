@@ -15,6 +15,25 @@
 
 namespace troyb {
 
+inline unsigned long long &launch_counter() {
+    static unsigned long long n = 0;
+    return n;
+}
+
+struct ProfRecord {
+    const char *name;
+    u32 grid;
+    cudaEvent_t e0, e1;
+};
+struct Profiler {
+    bool enabled = false;
+    std::vector<ProfRecord> records;
+};
+inline Profiler &profiler() {
+    static Profiler p;
+    return p;
+}
+
 #if defined(TROYB_HOST_EMUL)
 
 #define TB_PHASE(NT, t, ...)                       \
@@ -52,7 +71,22 @@ template <class F> inline cudaError_t launch_cta(const F &f, u32 grid, size_t sm
             configured = true;
         }
     }
-    k_cta<F><<<grid, F::kThreads, smem_bytes, stream>>>(f);
+    Profiler &prof = profiler();
+    if (prof.enabled) {
+        // bench.py's per-kernel timing pass: CUDA events on the launching stream around this one launch
+        ProfRecord r;
+        r.name = f.name();
+        r.grid = grid;
+        cudaEventCreate(&r.e0);
+        cudaEventCreate(&r.e1);
+        cudaEventRecord(r.e0, stream);
+        k_cta<F><<<grid, F::kThreads, smem_bytes, stream>>>(f);
+        cudaEventRecord(r.e1, stream);
+        prof.records.push_back(r);
+    } else {
+        k_cta<F><<<grid, F::kThreads, smem_bytes, stream>>>(f);
+    }
+    launch_counter()++;
     return cudaGetLastError();
 }
 

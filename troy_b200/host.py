@@ -45,6 +45,29 @@ class KernelProvider:
         return bool(_L().cdll.troyb_initialized())
 
 
+class CoeffModulus:
+    """src/modulus.h:412-505."""
+
+    @staticmethod
+    def Create(poly_modulus_degree, bit_sizes):
+        b = (C.c_int * len(bit_sizes))(*bit_sizes)
+        out = np.zeros(len(bit_sizes), dtype=np.uint64)
+        _L().call("troyb_coeff_modulus_create", int(poly_modulus_degree), b, len(bit_sizes), out.ctypes.data_as(C.POINTER(C.c_uint64)))
+        return [int(x) for x in out]
+
+    create = Create
+
+
+class PlainModulus:
+    """src/modulus.h:511-552."""
+
+    @staticmethod
+    def Batching(poly_modulus_degree, bit_size):
+        return CoeffModulus.Create(poly_modulus_degree, [bit_size])[0]
+
+    batching = Batching
+
+
 class DeviceArray:
     """Owning device buffer of uint64 words (DeviceArray<uint64_t>, src/utils/devicearray.cuh:90-200)."""
 

@@ -36,6 +36,10 @@ _SIGNATURES = {
     "troyb_last_error": (C.c_char_p, []),
     "troyb_initialize": (C.c_int, [C.c_int]),
     "troyb_initialized": (C.c_int, []),
+    "troyb_launch_count": (C.c_uint64, []),
+    "troyb_profile_enable": (C.c_int, [C.c_int]),
+    "troyb_profile_report": (C.c_int, [C.c_char_p, _sz]),
+    "troyb_coeff_modulus_create": (C.c_int, [C.c_uint64, C.POINTER(C.c_int), C.c_int, _u64p]),
     "troyb_malloc": (C.c_int, [C.POINTER(_vp), _sz, _vp]),
     "troyb_free": (C.c_int, [_vp, _vp]),
     "troyb_copy_to_device": (C.c_int, [_vp, _vp, _sz, _vp]),
