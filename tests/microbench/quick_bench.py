@@ -75,9 +75,9 @@ def main():
     torch.cuda.init()
     tb.KernelProvider.initialize(0)
     hbm = 6532.5e9
-    for n, nl, polys in [(4096, 8, 2048), (8192, 8, 1024), (16384, 8, 512), (32768, 8, 256), (65536, 8, 128), (16384, 1, 4096),
-                         (16384, 32, 128)]:
-        q = primes_for(n, [60] * nl + [60])
+    for n, nl, polys, bits in [(4096, 8, 2048, 60), (8192, 8, 1024, 60), (16384, 8, 512, 60), (32768, 8, 256, 60), (65536, 8, 128, 60),
+                               (4096, 8, 2048, 40), (8192, 8, 1024, 40), (16384, 8, 512, 40), (32768, 8, 256, 40), (65536, 8, 128, 40)]:
+        q = primes_for(n, [bits] * nl + [60])
         p = tb.EncryptionParameters(tb.SchemeType.ckks)
         p.set_poly_modulus_degree(n)
         p.set_coeff_modulus(q)
@@ -87,7 +87,7 @@ def main():
         tf = timeit(lambda: _L().call("troyb_ntt_forward", _vp(ctx.h), 0, _vp(buf.ptr), polys, _vp(None)))
         ti = timeit(lambda: _L().call("troyb_ntt_inverse", _vp(ctx.h), 0, _vp(buf.ptr), polys, _vp(None)))
         limbs = polys * nl
-        print(json.dumps(dict(kind="ntt", n=n, limbs_per_poly=nl, polys=polys, fwd_limb_ntt_per_s=limbs / tf,
+        print(json.dumps(dict(kind="ntt", n=n, prime_bits=bits, limbs_per_poly=nl, polys=polys, fwd_limb_ntt_per_s=limbs / tf,
                               inv_limb_ntt_per_s=limbs / ti, fwd_gbs=limbs * 16 * n / tf / 1e9, inv_gbs=limbs * 16 * n / ti / 1e9,
                               fwd_frac=limbs * 16 * n / tf / hbm, inv_frac=limbs * 16 * n / ti / hbm)), flush=True)
         del buf, ctx

@@ -104,8 +104,8 @@ void run_fwd(const Context *ctx, NttArgs a, u32 units, cudaStream_t s) {
         // four-step: strided column pass (layers 0..logN-13), then 4096-coefficient rows
         Scratch stage(a.mode == FWD_MODDOWN ? (size_t)units * ctx->N : 0, s);
         a.scratch = stage.p;
-        if (logN == 15) ck(launch_cta(NttFwdCols<15>{a}, units * ((1u << 15) / 16 / 256), 0, s));
-        else if (logN == 16) ck(launch_cta(NttFwdCols<16>{a}, units * ((1u << 16) / 16 / 256), 0, s));
+        if (logN == 15) ck(launch_cta(NttFwdCols<15>{a}, units * (4096 / 256), 0, s));
+        else if (logN == 16) ck(launch_cta(NttFwdCols<16>{a}, units * (4096 / 256), 0, s));
         else throw std::invalid_argument("poly_modulus_degree above 65536 is not supported");
         a.row_pass = 1;
         ck(launch_cta(NttFwd<12>{a}, units << (logN - 12), tile_smem(12), s));
@@ -129,8 +129,8 @@ void run_inv(const Context *ctx, NttArgs a, u32 units, cudaStream_t s) {
         Scratch stage(a.mode == INV_COMBINE ? (size_t)units * ctx->N : 0, s);
         a.scratch = stage.p;
         ck(launch_cta(NttInv<12>{a}, units << (logN - 12), tile_smem(12), s));
-        if (logN == 15) ck(launch_cta(NttInvCols<15>{a}, units * ((1u << 15) / 16 / 256), 0, s));
-        else if (logN == 16) ck(launch_cta(NttInvCols<16>{a}, units * ((1u << 16) / 16 / 256), 0, s));
+        if (logN == 15) ck(launch_cta(NttInvCols<15>{a}, units * (4096 / 256), 0, s));
+        else if (logN == 16) ck(launch_cta(NttInvCols<16>{a}, units * (4096 / 256), 0, s));
         else throw std::invalid_argument("poly_modulus_degree above 65536 is not supported");
     }
 }

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <memory>
 #include <cstring>
+#include <cstdlib>
 #include <stdexcept>
 
 namespace troyb {
@@ -288,6 +289,30 @@ Context *context_create(int device, int scheme, u64 N, const u64 *moduli, int n_
         md.inv1n_shoup = shoup_quotient(md.inv1n, p);
         md.fwd = upload(ctx->owned, fwd);
         md.inv = upload(ctx->owned, inv);
+        // butterfly policy (ntt.cuh). TROYB_NTT_POLICY=exact|fast forces the integer paths (A/B measurements).
+        const char *force = getenv("TROYB_NTT_POLICY");
+        const bool force_exact = force && std::string(force) == "exact";
+        const bool force_fast = force && std::string(force) == "fast";
+        md.policy = (p >> 60) || force_exact ? POLICY_U64_EXACT : POLICY_U64_FAST;
+        md.fwd_d = md.inv_d = nullptr;
+        md.pd = (double)p;
+        md.pinv_d = 1.0 / (double)p;
+        md.ninv_d = (double)md.ninv;
+        md.ninv_dp = (double)md.ninv / (double)p;
+        md.inv1n_d = (double)md.inv1n;
+        md.inv1n_dp = (double)md.inv1n / (double)p;
+        if (!(p >> 46) && !force_exact && !force_fast) {
+            std::vector<double> fd(2 * N), id(2 * N);
+            for (u64 k = 0; k < N; k++) {
+                fd[2 * k] = (double)fwd[2 * k];
+                fd[2 * k + 1] = (double)fwd[2 * k] / (double)p;
+                id[2 * k] = (double)inv[2 * k];
+                id[2 * k + 1] = (double)inv[2 * k] / (double)p;
+            }
+            md.fwd_d = upload(ctx->owned, fd);
+            md.inv_d = upload(ctx->owned, id);
+            md.policy = POLICY_F64;
+        }
     }
     ctx->d_mods = upload(ctx->owned, ctx->h_mods);
 

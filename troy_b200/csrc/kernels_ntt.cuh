@@ -54,6 +54,14 @@ struct NttArgs {
     u64 *scratch;       // four-step intermediate rows [unit][N] for modes that cannot stage in dst
 };
 
+TB_D u64 canon4(u64 v, u64 p) {
+    u64 p2 = p << 1;
+    v -= (v >= p2 ? p2 : 0);
+    v -= (v >= p ? p : 0);
+    return v;
+}
+TB_D u64 canon2(u64 v, u64 p) { return v - (v >= p ? p : 0); }
+
 // Generic small transform (N < 4096; only the reference's toy-parameter tests use it): radix-2 in shared memory.
 template <class Ld, class St>
 TB_D void small_ntt_fwd(u64 *sm, u32 logn, Ld ld, St st, const u64 *__restrict__ tw, u64 p) {
@@ -65,14 +73,14 @@ TB_D void small_ntt_fwd(u64 *sm, u32 logn, Ld ld, St st, const u64 *__restrict__
         TB_PHASE(256, t, for (u32 b = t; b < n / 2; b += 256) {
             u32 r = b >> lg, pos = b & ((1u << lg) - 1);
             u32 i = (r << (lg + 1)) | pos;
-            ulonglong2 w = ld_tw(tw, (1u << s) + r);
+            ulonglong2 w = __ldg(reinterpret_cast<const ulonglong2 *>(tw) + ((1u << s) + r));
             u64 X = sm[i], Y = sm[i + (1u << lg)];
-            ct_bfly(X, Y, w.x, w.y, p, p2);
+            { u64 x_ = X - (X >= p2 ? p2 : 0); u64 t_ = shoup_lazy(Y, w.x, w.y, p); X = x_ + t_; Y = x_ - t_ + p2; }
             sm[i] = X;
             sm[i + (1u << lg)] = Y;
         })
     }
-    TB_PHASE(256, t, for (u32 i = t; i < n; i += 256) st(i, sm[i]);)
+    TB_PHASE(256, t, for (u32 i = t; i < n; i += 256) st(i, canon4(sm[i], p));)
 }
 
 template <class Ld, class St>
@@ -87,16 +95,16 @@ TB_D void small_ntt_inv(u64 *sm, u32 logn, Ld ld, St st, const u64 *__restrict__
             u32 i = (r << (lg + 1)) | pos;
             u64 X = sm[i], Y = sm[i + (1u << lg)];
             if (s == 0) {
-                gs_bfly_last(X, Y, md->ninv, md->ninv_shoup, md->inv1n, md->inv1n_shoup, p, p2);
+                { u64 s_ = X + Y, d_ = X + p2 - Y; X = shoup_lazy(s_, md->ninv, md->ninv_shoup, p); Y = shoup_lazy(d_, md->inv1n, md->inv1n_shoup, p); }
             } else {
-                ulonglong2 w = ld_tw(tw, (1u << s) + r);
-                gs_bfly(X, Y, w.x, w.y, p, p2);
+                ulonglong2 w = __ldg(reinterpret_cast<const ulonglong2 *>(tw) + ((1u << s) + r));
+                { u64 s_ = X + Y, d_ = X + p2 - Y; X = s_ - (s_ >= p2 ? p2 : 0); Y = shoup_lazy(d_, w.x, w.y, p); }
             }
             sm[i] = X;
             sm[i + (1u << lg)] = Y;
         })
     }
-    TB_PHASE(256, t, for (u32 i = t; i < n; i += 256) st(i, sm[i]);)
+    TB_PHASE(256, t, for (u32 i = t; i < n; i += 256) st(i, canon2(sm[i], p));)
 }
 
 inline const char *ntt_kernel_name(int mode, int pass) {
@@ -112,14 +120,6 @@ inline const char *ntt_kernel_name(int mode, int pass) {
     int row = mode >= 10 ? 3 + (mode - 10) : mode;
     return names[row][pass];
 }
-
-TB_D u64 canon4(u64 v, u64 p) {
-    u64 p2 = p << 1;
-    v -= (v >= p2 ? p2 : 0);
-    v -= (v >= p ? p : 0);
-    return v;
-}
-TB_D u64 canon2(u64 v, u64 p) { return v - (v >= p ? p : 0); }
 
 // Per-CTA resolved job: where to read / write and with which modulus.
 struct NttUnit {
@@ -193,8 +193,21 @@ template <int LOGT> TB_D NttUnit resolve_unit(const NttArgs &a, u32 bid) {
     return u;
 }
 
+// Runs `body` with the butterfly policy of this modulus (warp-uniform branch).
+#define TB_WITH_POLICY(md, ...)                                                     \
+    switch ((md)->policy) {                                                         \
+    case POLICY_F64: { typedef ArithF64 A; __VA_ARGS__ } break;                     \
+    case POLICY_U64_FAST: { typedef ArithU64Fast A; __VA_ARGS__ } break;            \
+    default: { typedef ArithU64Exact A; __VA_ARGS__ } break;                        \
+    }
+
+template <int LOGT> __host__ __device__ constexpr int ntt_cta_threads() {
+    if constexpr (LOGT == 0) return 256;
+    else return tile_threads<LOGT>();
+}
+
 template <int LOGT> struct NttFwd {
-    static constexpr int kThreads = LOGT == 0 ? 256 : (1 << (LOGT == 0 ? 4 : LOGT)) / 16;
+    static constexpr int kThreads = ntt_cta_threads<LOGT>();
     NttArgs a;
     const char *name() const { return ntt_kernel_name(a.mode, a.row_pass ? 2 : 0); }
     TB_D void operator()(u32 bid, u64 *sm) const {
@@ -215,33 +228,35 @@ template <int LOGT> struct NttFwd {
         const u64 *in = !row_pass ? u.src : (mode == FWD_MODDOWN ? a.scratch + ((u64)u.unit << a.logN) : u.dst);
         auto ld = [&](u32 i) -> u64 {
             u64 x = in[off + i];
-            if (row_pass) return x;
+            if (row_pass) return x; // raw element bits left by the column pass
             if (mode == FWD_MODUP) x = barrett64(x, p, ratio1);
             else if (mode == FWD_MODDOWN) x = barrett64(x, p, ratio1) + fix;
             return x;
         };
-        const int canon = a.canon;
-        auto st = [&](u32 i, u64 v) {
+        auto st = [&](u32 i, u64 v) { // v is the canonical residue
             if (mode == FWD_MODDOWN) {
-                // v in [0,4p): d = acc + 4p - v in (0,5p); r = d * q_last^-1 mod p
-                u64 d = u.acc[off + i] + (p << 2) - v;
-                u64 r = shoup(d, u.dl.inv_last, u.dl.inv_last_shoup, p);
+                u64 r = shoup(submod(u.acc[off + i], v, p), u.dl.inv_last, u.dl.inv_last_shoup, p);
                 if (u.ct) u.ct[off + i] = addmod(u.ct[off + i], r, p);
                 else u.dst[off + i] = r;
             } else {
-                u.dst[off + i] = canon ? canon4(v, p) : v;
+                u.dst[off + i] = v;
             }
         };
         if constexpr (LOGT == 0) {
             small_ntt_fwd(sm, (u32)a.logN, ld, st, md->fwd, p);
         } else {
-            tile_ntt_fwd<LOGT>(sm, ld, st, md->fwd, (1u << u.rows_log) + u.row, p);
+            const u32 R = (1u << u.rows_log) + u.row;
+            if (row_pass) {
+                TB_WITH_POLICY(md, (tile_ntt_fwd<A, LOGT, true>(sm, ld, st, md, R));)
+            } else {
+                TB_WITH_POLICY(md, (tile_ntt_fwd<A, LOGT, false>(sm, ld, st, md, R));)
+            }
         }
     }
 };
 
 template <int LOGT> struct NttInv {
-    static constexpr int kThreads = LOGT == 0 ? 256 : (1 << (LOGT == 0 ? 4 : LOGT)) / 16;
+    static constexpr int kThreads = ntt_cta_threads<LOGT>();
     NttArgs a;
     const char *name() const { return ntt_kernel_name(a.mode, 0); }
     TB_D void operator()(u32 bid, u64 *sm) const {
@@ -250,34 +265,32 @@ template <int LOGT> struct NttInv {
         const u64 p = md->p;
         const u32 tile = LOGT == 0 ? (1u << a.logN) : (1u << LOGT);
         const u64 off = (u64)u.row * tile;
-        const int mode = a.mode;
         const bool whole = (u.rows_log == 0);
         auto ld = [&](u32 i) -> u64 { return u.src[off + i]; };
-        const int canon = a.canon;
-        u64 *stage = (mode == INV_COMBINE) ? a.scratch + ((u64)u.unit << a.logN) : u.dst;
+        u64 *stage = (a.mode == INV_COMBINE) ? a.scratch + ((u64)u.unit << a.logN) : u.dst;
         auto st = [&](u32 i, u64 v) {
-            // v in [0,2p)
-            if (!whole) { stage[off + i] = v; return; } // four-step: the column pass finishes the job
+            if (!whole) { stage[off + i] = v; return; } // four-step: raw bits; the column pass finishes the job
             store_final(a, u, p, off + i, v);
         };
         if constexpr (LOGT == 0) {
             small_ntt_inv(sm, (u32)a.logN, ld, st, md->inv, p, md);
         } else {
-            if (whole) tile_ntt_inv<LOGT, true>(sm, ld, st, md->inv, 1u, p, md);
-            else tile_ntt_inv<LOGT, false>(sm, ld, st, md->inv, (1u << u.rows_log) + u.row, p, md);
+            if (whole) {
+                TB_WITH_POLICY(md, (tile_ntt_inv<A, LOGT, true>(sm, ld, st, md, 1u));)
+            } else {
+                TB_WITH_POLICY(md, (tile_ntt_inv<A, LOGT, false>(sm, ld, st, md, (1u << u.rows_log) + u.row));)
+            }
         }
     }
 
-    // Epilogue of a completed inverse transform; shared with the four-step column pass.
+    // Epilogue of a completed inverse transform (v = canonical residue); shared with the four-step column pass.
     static TB_D void store_final(const NttArgs &a, const NttUnit &u, u64 p, u64 idx, u64 v) {
-        const int mode = a.mode, canon = a.canon;
+        const int mode = a.mode;
         const DropDev &dr = a.drop;
         if (mode == INV_PLAIN) {
-            u.dst[idx] = canon ? canon2(v, p) : v;
+            u.dst[idx] = v;
         } else if (mode == INV_ADD_HALF) {
-            u64 c = canon2(v, p);
-            if (a.add_half) c = addmod(c, dr.half, p);
-            u.dst[idx] = c;
+            u.dst[idx] = a.add_half ? addmod(v, dr.half, p) : v;
         } else { // INV_COMBINE
             u64 s = u.sp[idx];
             u64 sub;
@@ -292,7 +305,7 @@ template <int LOGT> struct NttInv {
                 // BFV (UtilF/G): (s' mod q_j) + q_j - half mod q_j
                 sub = barrett64(s, p, ratio1) + (p - u.dl.half_mod);
             }
-            u64 d = v + (p << 1) - sub; // v < 2p, sub <= 2p  ->  d in [0,4p)
+            u64 d = v + (p << 1) - sub; // v < p, sub <= 2p  ->  d in (0,3p)
             u64 r = shoup(d, u.dl.inv_last, u.dl.inv_last_shoup, p);
             if (u.ct) u.ct[idx] = addmod(u.ct[idx], r, p);
             else u.dst[idx] = r;
@@ -306,34 +319,37 @@ template <int LOGN> struct NttFwdCols {
     NttArgs a;
     const char *name() const { return ntt_kernel_name(a.mode, 1); }
     TB_D void operator()(u32 bid, u64 *) const {
-        constexpr u32 NTV = (1u << LOGN) / 16, CPB = NTV / kThreads;
+        constexpr u32 NTV = (1u << LOGN) >> (LOGN - 12), CPB = NTV / kThreads;
         const u32 chunk = bid % CPB;
         NttArgs b = a;
         b.logN = LOGN; // resolve with rows_log = 0: unit = bid / CPB
         const NttUnit u = resolve_unit<LOGN>(b, bid / CPB);
         const ModDev *md = u.md;
-        const u64 p = md->p, p2 = p << 1;
+        const u64 p = md->p;
         if (u.passthrough) {
             TB_PHASE(kThreads, t, {
                 u32 v = chunk * kThreads + t;
-                for (u32 k = 0; k < 16; k++) u.dst[v + k * NTV] = u.src[v + k * NTV];
+                for (u32 k = 0; k < (1u << (LOGN - 12)); k++) u.dst[v + k * NTV] = u.src[v + k * NTV];
             })
             return;
         }
         const int mode = a.mode;
         const u64 ratio1 = md->ratio1;
         const u64 fix = (mode == FWD_MODDOWN) ? p - u.dl.half_mod : 0;
-        // The column pass writes its lazy result where the row pass will read it: the destination buffer
-        // for PLAIN / MODUP, a scratch row (dst) for MODDOWN.
-        auto ld = [&](u32 i) -> u64 {
-            u64 x = u.src[i];
-            if (mode == FWD_MODUP) x = barrett64(x, p, ratio1);
-            else if (mode == FWD_MODDOWN) x = barrett64(x, p, ratio1) + fix;
-            return x;
-        };
+        // The column pass leaves raw element bits where the row pass will read them: the destination buffer for
+        // PLAIN / MODUP, a scratch row for MODDOWN.
         u64 *out = (mode == FWD_MODDOWN) ? a.scratch + ((u64)u.unit << LOGN) : u.dst;
-        auto st = [&](u32 i, u64 v) { out[i] = v; };
-        TB_PHASE(kThreads, t, (fwd_round<LOGN, 0, LOGN - 12, (int)NTV>(chunk * kThreads + t, ld, st, md->fwd, 1u, p, p2));)
+        TB_WITH_POLICY(md, {
+            const typename A::Mod m = A::make(md);
+            auto ld = [&](u32 i) -> typename A::elem {
+                u64 x = u.src[i];
+                if (mode == FWD_MODUP) x = barrett64(x, p, ratio1);
+                else if (mode == FWD_MODDOWN) x = barrett64(x, p, ratio1) + fix;
+                return A::from_u64(x, m);
+            };
+            auto st = [&](u32 i, typename A::elem v) { out[i] = A::to_bits(v); };
+            TB_PHASE(kThreads, t, (fwd_round<A, LOGN, (int)NTV, 0, LOGN - 12, false, false>(chunk * kThreads + t, ld, st, A::fwd_table(md), 1u, m));)
+        })
     }
 };
 
@@ -342,20 +358,22 @@ template <int LOGN> struct NttInvCols {
     NttArgs a;
     const char *name() const { return ntt_kernel_name(a.mode, 1); }
     TB_D void operator()(u32 bid, u64 *) const {
-        constexpr u32 NTV = (1u << LOGN) / 16, CPB = NTV / kThreads;
+        constexpr u32 NTV = (1u << LOGN) >> (LOGN - 12), CPB = NTV / kThreads;
         const u32 chunk = bid % CPB;
         NttArgs b = a;
         b.logN = LOGN;
         const NttUnit u = resolve_unit<LOGN>(b, bid / CPB);
         const ModDev *md = u.md;
-        const u64 p = md->p, p2 = p << 1;
-        const int mode = a.mode;
-        // The row pass left its lazy output in the destination row (PLAIN / ADD_HALF) or in a scratch row (COMBINE).
-        const u64 *in = (mode == INV_COMBINE) ? a.scratch + ((u64)u.unit << LOGN) : u.dst;
-        auto ld = [&](u32 i) -> u64 { return in[i]; };
-        auto st = [&](u32 i, u64 v) { NttInv<12>::store_final(a, u, p, i, v); };
-        TB_PHASE(kThreads, t,
-                 (inv_round<LOGN, 0, LOGN - 12, (int)NTV, true>(chunk * kThreads + t, ld, st, md->inv, 1u, p, p2, md));)
+        const u64 p = md->p;
+        // The row pass left raw element bits in the destination row (PLAIN / ADD_HALF) or in a scratch row (COMBINE).
+        const u64 *in = (a.mode == INV_COMBINE) ? a.scratch + ((u64)u.unit << LOGN) : u.dst;
+        TB_WITH_POLICY(md, {
+            const typename A::Mod m = A::make(md);
+            auto ld = [&](u32 i) -> typename A::elem { return A::from_bits(in[i]); };
+            auto st = [&](u32 i, typename A::elem v) { NttInv<12>::store_final(a, u, p, i, A::canon(v, m)); };
+            TB_PHASE(kThreads, t,
+                     (inv_round<A, LOGN, (int)NTV, 0, LOGN - 12, true, false, false>(chunk * kThreads + t, ld, st, A::inv_table(md), 1u, m));)
+        })
     }
 };
 

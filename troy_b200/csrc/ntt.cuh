@@ -5,217 +5,401 @@
 //             DWTHandler::transformToRev src/utils/dwthandler.h:88-204   (natural in, bit-reversed out)
 //   inverse : kInverseNttNegacyclicHarvey src/kernelutils.cuh:607-632, CPU src/utils/ntt.cpp:189-213,
 //             DWTHandler::transformFromRev src/utils/dwthandler.h:215-372 (bit-reversed in, natural out, x N^-1)
-// How it is computed is new: instead of one kernel launch per butterfly layer with one thread per
-// coefficient, a CTA keeps a tile of 2^LOGT coefficients in (padded) shared memory and every thread runs
-// radix-16 register butterflies (4 layers per shared-memory round trip). A tile is either a whole limb
-// (N <= 16384: one HBM read + one HBM write per transform) or a 4096-coefficient row of the four-step
-// split used for N = 32768 / 65536 (a strided "column" pass does the first log2(N/4096) layers).
+// How it is computed is new. Instead of one kernel launch per butterfly layer with one thread per coefficient, a CTA
+// keeps a tile of 2^LOGT coefficients in padded shared memory and every thread runs radix-32 (or radix-16) register
+// butterflies: 5 (4) layers per shared-memory round trip. A tile is either a whole limb (N <= 16384: one HBM read and
+// one HBM write per transform) or a 4096-coefficient row of the four-step split used for N = 32768 / 65536 (a strided
+// "column" pass does the first log2(N/4096) layers).
 //
-// Twiddle index rule (same table order as the reference's root_powers_): for a tile whose sub-transform
-// has root base R (R = 1 for a whole limb, R = N/T + row for row `row` of the four-step split), layer s of
-// the tile (0-based) and lower butterfly element i use table entry (R << s) + (i >> (LOGT - s)).
+// The butterfly arithmetic is a policy (measured in tests/microbench):
+//   ArithF64      primes below 2^46 (CKKS 40-bit primes): exact FP64-FMA modular multiply on the otherwise idle FP64
+//                 pipe, balanced residues, no range corrections in the forward transform
+//   ArithU64Fast  primes below 2^60: Shoup multiply with a 3-product quotient estimate, fused accumulate chains
+//   ArithU64Exact primes up to 61 bits (BEHZ auxiliary base): textbook Harvey lazy butterfly
+// Every policy returns canonical residues at the tile boundary, so results do not depend on the policy.
+//
+// Twiddle index rule (same table order as the reference's root_powers_): for a tile whose sub-transform has root base R
+// (R = 1 for a whole limb, R = N/T + row for row `row` of the four-step split), layer s of the tile (0-based) and lower
+// butterfly element i use table entry (R << s) + (i >> (LOGT - s)).
 #pragma once
 #include "launch.cuh"
 
+#if defined(TROYB_HOST_EMUL)
+#include <cmath>
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
+inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
+inline long long __double_as_longlong(double d) { long long v; memcpy(&v, &d, 8); return v; }
+#endif
+
 namespace troyb {
 
-// Shared-memory padding: one extra word per 16 keeps every radix round and the linear copy phases
-// bank-conflict free for 64-bit accesses.
+// Shared-memory padding: one extra word per 16 keeps every radix round used below and the linear copy phases
+// bank-conflict free for 64-bit accesses (checked exhaustively by tools/banksim.py).
 __host__ __device__ constexpr u32 pad_idx(u32 i) { return i + (i >> 4); }
 __host__ __device__ constexpr u32 padded_words(u32 n) { return n + (n >> 4); }
 
-// Cooley-Tukey (forward) Harvey butterfly. X in [0,4p), Y in [0,4p) -> both in [0,4p).
-TB_D void ct_bfly(u64 &X, u64 &Y, u64 w, u64 wq, u64 p, u64 p2) {
-    u64 x = X - (X >= p2 ? p2 : 0);
-    u64 t = shoup_lazy(Y, w, wq, p);
-    X = x + t;
-    Y = x - t + p2;
-}
+// ---- 32-bit multiply helpers (the integer pipe's native width) ---------------------------------------------------------
+TB_D u32 lo32(u64 x) { return (u32)x; }
+TB_D u32 hi32(u64 x) { return (u32)(x >> 32); }
+TB_D u64 mk64(u32 lo, u32 hi) { return ((u64)hi << 32) | lo; }
+TB_D u64 mulw(u32 a, u32 b) { return (u64)a * b; }
+TB_D u64 madw(u32 a, u32 b, u64 c) { return (u64)a * b + c; }
+TB_D u32 madlo(u32 a, u32 b, u32 c) { return a * b + c; }
 
-// Gentleman-Sande (inverse) Harvey butterfly. X, Y in [0,2p) -> both in [0,2p).
-TB_D void gs_bfly(u64 &X, u64 &Y, u64 w, u64 wq, u64 p, u64 p2) {
-    u64 s = X + Y;
-    u64 d = X + p2 - Y;
-    X = s - (s >= p2 ? p2 : 0);
-    Y = shoup_lazy(d, w, wq, p);
-}
+// ---- arithmetic policies --------------------------------------------------------------------------------------------------
+struct TwU64 { u64 w, wq; };
 
-// Last inverse layer with the N^-1 scaling folded in (like the reference CPU path, dwthandler.h:289-330).
-TB_D void gs_bfly_last(u64 &X, u64 &Y, u64 ninv, u64 ninvq, u64 w, u64 wq, u64 p, u64 p2) {
-    u64 s = X + Y;
-    u64 d = X + p2 - Y;
-    X = shoup_lazy(s, ninv, ninvq, p); // s < 4p < 2^64
-    Y = shoup_lazy(d, w, wq, p);
-}
-
-TB_D ulonglong2 ld_tw(const u64 *tw, u32 k) { return __ldg(reinterpret_cast<const ulonglong2 *>(tw) + k); }
-
-// One radix-2^RR round of the forward transform on a tile of 2^LOGT coefficients, layers S0..S0+RR-1.
-// `vt` is this thread's index among NT cooperating threads (NT * 16 == 2^LOGT); each thread owns
-// G = 16 >> RR groups of 2^RR coefficients spaced 2^BLO apart.
-template <int LOGT, int S0, int RR, int NT, class Ld, class St>
-TB_D void fwd_round(u32 vt, Ld ld, St st, const u64 *__restrict__ tw, u32 R, u64 p, u64 p2) {
-    constexpr int E = 16, G = E >> RR, K = 1 << RR, BLO = LOGT - S0 - RR;
-    static_assert(NT * E == (1 << LOGT), "tile/threads mismatch");
-    static_assert(BLO >= 0, "bad round");
-    u64 x[E];
-#pragma unroll
-    for (int g = 0; g < G; g++) {
-        u32 v = vt + g * NT;
-        u32 lo = v & ((1u << BLO) - 1), hi = v >> BLO;
-        u32 base = (hi << (BLO + RR)) | lo;
-#pragma unroll
-        for (int k = 0; k < K; k++) x[g * K + k] = ld(base + (k << BLO));
+// Textbook Harvey lazy butterflies (forward values in [0,4p), inverse in [0,2p)); p up to 61 bits.
+struct ArithU64Exact {
+    typedef u64 elem;
+    typedef TwU64 tw_t;
+    static constexpr bool kReduceEachInvRound = false;
+    struct Mod {
+        u64 p, p2, ratio1;
+        TwU64 ninv, inv1n;
+    };
+    static TB_D Mod make(const ModDev *md) {
+        Mod m;
+        m.p = md->p; m.p2 = md->p << 1; m.ratio1 = md->ratio1;
+        m.ninv = TwU64{md->ninv, md->ninv_shoup};
+        m.inv1n = TwU64{md->inv1n, md->inv1n_shoup};
+        return m;
     }
+    static TB_D const void *fwd_table(const ModDev *md) { return md->fwd; }
+    static TB_D const void *inv_table(const ModDev *md) { return md->inv; }
+    static TB_D tw_t ld_tw(const void *tab, u32 k) {
+        ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(tab) + k);
+        return TwU64{v.x, v.y};
+    }
+    static TB_D elem from_u64(u64 v, const Mod &) { return v; }         // forward accepts [0,4p), inverse [0,2p)
+    static TB_D elem from_bits(u64 v) { return v; }
+    static TB_D u64 to_bits(elem x) { return x; }
+    static TB_D u64 canon(elem x, const Mod &m) { return barrett64(x, m.p, m.ratio1); }
+    static TB_D void reduce(elem &, const Mod &) {}
+    static TB_D void ct(elem &X, elem &Y, tw_t w, const Mod &m) {
+        u64 x = X - (X >= m.p2 ? m.p2 : 0);
+        u64 t = shoup_lazy(Y, w.w, w.wq, m.p);
+        X = x + t;
+        Y = x - t + m.p2;
+    }
+    static TB_D void gs(elem &X, elem &Y, tw_t w, const Mod &m) {
+        u64 s = X + Y;
+        u64 d = X + m.p2 - Y;
+        X = s - (s >= m.p2 ? m.p2 : 0);
+        Y = shoup_lazy(d, w.w, w.wq, m.p);
+    }
+    static TB_D void gs_last(elem &X, elem &Y, const Mod &m) {
+        u64 s = X + Y;
+        u64 d = X + m.p2 - Y;
+        X = shoup_lazy(s, m.ninv.w, m.ninv.wq, m.p);
+        Y = shoup_lazy(d, m.inv1n.w, m.inv1n.wq, m.p);
+    }
+};
+
+// Fast integer path for p < 2^60. The quotient of the Shoup multiply is estimated from three 32x32->64 products
+// (error <= 2, so the lazy product lies in [0,4p)); the remainder is one fused multiply-accumulate chain modulo 2^64.
+// Invariants: forward values < 8p + 2^32 (range correction compares only the high word), inverse values < 4p.
+struct ArithU64Fast {
+    typedef u64 elem;
+    typedef TwU64 tw_t;
+    static constexpr bool kReduceEachInvRound = false;
+    struct Mod {
+        u64 p, p4, ratio1;
+        u32 np0, np1, H;
+        TwU64 ninv, inv1n;
+    };
+    static TB_D Mod make(const ModDev *md) {
+        Mod m;
+        m.p = md->p; m.p4 = md->p << 2; m.ratio1 = md->ratio1;
+        u64 np = 0 - md->p;
+        m.np0 = lo32(np); m.np1 = hi32(np);
+        m.H = hi32(m.p4) + 1;
+        m.ninv = TwU64{md->ninv, md->ninv_shoup};
+        m.inv1n = TwU64{md->inv1n, md->inv1n_shoup};
+        return m;
+    }
+    static TB_D const void *fwd_table(const ModDev *md) { return md->fwd; }
+    static TB_D const void *inv_table(const ModDev *md) { return md->inv; }
+    static TB_D tw_t ld_tw(const void *tab, u32 k) { return ArithU64Exact::ld_tw(tab, k); }
+    static TB_D elem from_u64(u64 v, const Mod &) { return v; }         // needs v < 4p
+    static TB_D elem from_bits(u64 v) { return v; }
+    static TB_D u64 to_bits(elem x) { return x; }
+    static TB_D u64 canon(elem x, const Mod &m) { return barrett64(x, m.p, m.ratio1); }
+    static TB_D void reduce(elem &, const Mod &) {}
+    // add + Y*w - q*p (mod 2^64) with q in [Q-2, Q], Q = floor(Y*wq / 2^64); equals add + (Y*w mod p) + {0,1,2}*p
+    static TB_D u64 mul_acc(u64 add, u64 Y, tw_t t, const Mod &m) {
+        u32 y0 = lo32(Y), y1 = hi32(Y), w0 = lo32(t.w), w1 = hi32(t.w), v0 = lo32(t.wq), v1 = hi32(t.wq);
+        u64 A = mulw(y1, v0), B = mulw(y0, v1);
+        u64 q = madw(y1, v1, (u64)hi32(A) + (u64)hi32(B));
+        u32 q0 = lo32(q), q1 = hi32(q);
+        u64 r = madw(y0, w0, add);
+        r = madw(q0, m.np0, r);
+        u32 rh = hi32(r);
+        rh = madlo(y1, w0, rh);
+        rh = madlo(y0, w1, rh);
+        rh = madlo(q1, m.np0, rh);
+        rh = madlo(q0, m.np1, rh);
+        return mk64(lo32(r), rh);
+    }
+    static TB_D void ct(elem &X, elem &Y, tw_t w, const Mod &m) {
+        u64 x = X;
+        if (hi32(x) >= m.H) x -= m.p4;          // x < 4p + 2^32
+        u64 xn = mul_acc(x, Y, w, m);           // x + T, T in [0,4p)
+        X = xn;
+        Y = (x + m.p4) + (x - xn);              // x + 4p - T
+    }
+    static TB_D void gs(elem &X, elem &Y, tw_t w, const Mod &m) {
+        u64 s = X + Y;
+        u64 d = X + m.p4 - Y;
+        u64 t = s - m.p4;
+        X = s >= m.p4 ? t : s;
+        Y = mul_acc(0, d, w, m);
+    }
+    static TB_D void gs_last(elem &X, elem &Y, const Mod &m) {
+        u64 s = X + Y;
+        u64 d = X + m.p4 - Y;
+        X = mul_acc(0, s, m.ninv, m);
+        Y = mul_acc(0, d, m.inv1n, m);
+    }
+};
+
+// FP64 path for p < 2^46: residues are integers held exactly in doubles (|x| < 2^51 throughout). The product y*w is
+// formed exactly as h + l with one multiply and one FMA, the quotient comes from y * (w/p) rounded to nearest with the
+// 1.5*2^52 trick, and h - q*p + l is exact, so the result is the balanced residue up to a tiny excess:
+// |mulmod| <= (1/2 + 2^-6) p. Forward butterflies therefore need no range correction at all (growth <= 0.52 p per layer,
+// 16 layers from a start below 4p stay under 2^51); the inverse doubles the sum path each layer, so every inverse round
+// first re-centres its inputs.
+struct TwF64 { double w, wp; };
+struct ArithF64 {
+    typedef double elem;
+    typedef TwF64 tw_t;
+    static constexpr bool kReduceEachInvRound = true;
+    struct Mod {
+        double p, pinv;
+        TwF64 ninv, inv1n;
+    };
+    static TB_D Mod make(const ModDev *md) {
+        Mod m;
+        m.p = md->pd; m.pinv = md->pinv_d;
+        m.ninv = TwF64{md->ninv_d, md->ninv_dp};
+        m.inv1n = TwF64{md->inv1n_d, md->inv1n_dp};
+        return m;
+    }
+    static TB_D const void *fwd_table(const ModDev *md) { return md->fwd_d; }
+    static TB_D const void *inv_table(const ModDev *md) { return md->inv_d; }
+    static TB_D tw_t ld_tw(const void *tab, u32 k) {
+        ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(tab) + k);
+        return TwF64{__longlong_as_double((long long)v.x), __longlong_as_double((long long)v.y)};
+    }
+    static constexpr double kMagic = 6755399441055744.0; // 1.5 * 2^52
+    static constexpr double kTwo52 = 4503599627370496.0;
+    static TB_D elem from_u64(u64 v, const Mod &) { // exact for v < 2^52
+        return __dadd_rn(__longlong_as_double((long long)(v | 0x4330000000000000ull)), -kTwo52);
+    }
+    static TB_D elem from_bits(u64 v) { return __longlong_as_double((long long)v); }
+    static TB_D u64 to_bits(elem x) { return (u64)__double_as_longlong(x); }
+    static TB_D void reduce(elem &x, const Mod &m) {
+        double q = __dadd_rn(__fma_rn(x, m.pinv, kMagic), -kMagic);
+        x = __fma_rn(-q, m.p, x);
+    }
+    static TB_D u64 canon(elem x, const Mod &m) {
+        reduce(x, m);
+        if (x < 0.0) x = __dadd_rn(x, m.p);
+        return (u64)__double_as_longlong(__dadd_rn(x, kTwo52)) & 0x000FFFFFFFFFFFFFull;
+    }
+    static TB_D double mulmod(double y, tw_t t, const Mod &m) {
+        double h = __dmul_rn(y, t.w);
+        double l = __fma_rn(y, t.w, -h);
+        double q = __dadd_rn(__fma_rn(y, t.wp, kMagic), -kMagic);
+        double r = __fma_rn(-q, m.p, h);
+        return __dadd_rn(r, l);
+    }
+    static TB_D void ct(elem &X, elem &Y, tw_t w, const Mod &m) {
+        double t = mulmod(Y, w, m);
+        double x = X;
+        X = __dadd_rn(x, t);
+        Y = __dadd_rn(x, -t);
+    }
+    static TB_D void gs(elem &X, elem &Y, tw_t w, const Mod &m) {
+        double s = __dadd_rn(X, Y);
+        double d = __dadd_rn(X, -Y);
+        X = s;
+        Y = mulmod(d, w, m);
+    }
+    static TB_D void gs_last(elem &X, elem &Y, const Mod &m) {
+        double s = __dadd_rn(X, Y);
+        double d = __dadd_rn(X, -Y);
+        X = mulmod(s, m.ninv, m);
+        Y = mulmod(d, m.inv1n, m);
+    }
+};
+
+// One radix-2^RR round of the forward transform on a tile of 2^LOGT coefficients, layers S0..S0+RR-1, run by NT
+// cooperating threads. The tile splits into 2^(LOGT-RR) independent groups of 2^RR coefficients spaced 2^BLO apart; a
+// thread takes groups vt, vt+NT, ... one after the other, holding one group (and all of its 2^RR-1 twiddles, fetched
+// up front so that their latency overlaps the data loads) in registers at a time.
+//   PIN / POUT: the source / destination is the padded shared-memory tile (index = pad_idx(i)); the padded offset of
+//   coefficient k of a group is a compile-time constant because the group base and k << BLO occupy disjoint bits.
+template <class A, int LOGT, int NT, int S0, int RR, bool PIN, bool POUT, class Ld, class St>
+TB_D void fwd_round(u32 vt, Ld ld, St st, const void *__restrict__ tw, u32 R, const typename A::Mod &m) {
+    constexpr int K = 1 << RR, BLO = LOGT - S0 - RR, NV = (1 << LOGT) / K, G = NV / NT;
+    static_assert(BLO >= 0 && G >= 1 && NV % NT == 0, "bad round");
+#pragma unroll 1
+    for (int g = 0; g < G; g++) {
+        const u32 v = vt + g * NT;
+        const u32 lo = v & ((1u << BLO) - 1), hi = v >> BLO;
+        const u32 base = (hi << (BLO + RR)) | lo;
+        const u32 ib = PIN ? pad_idx(base) : base, ob = POUT ? pad_idx(base) : base;
+        typename A::tw_t w[K - 1];
 #pragma unroll
-    for (int u = 0; u < RR; u++) {
-        const int half = 1 << (RR - 1 - u);
+        for (int u = 0; u < RR; u++) {
+            const u32 tbase = (R << (S0 + u)) + (hi << u);
 #pragma unroll
-        for (int g = 0; g < G; g++) {
-            u32 hi = (vt + g * NT) >> BLO;
-            u32 tbase = (R << (S0 + u)) + (hi << u);
+            for (int j = 0; j < (1 << u); j++) w[(1 << u) - 1 + j] = A::ld_tw(tw, tbase + j);
+        }
+        typename A::elem x[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) x[k] = ld(ib + (PIN ? pad_idx((u32)k << BLO) : ((u32)k << BLO)));
+#pragma unroll
+        for (int u = 0; u < RR; u++) {
+            const int half = 1 << (RR - 1 - u);
 #pragma unroll
             for (int j = 0; j < (1 << u); j++) {
-                ulonglong2 w = ld_tw(tw, tbase + j);
 #pragma unroll
                 for (int r = 0; r < half; r++) {
-                    int k = (j << (RR - u)) | r;
-                    ct_bfly(x[g * K + k], x[g * K + k + half], w.x, w.y, p, p2);
+                    const int k = (j << (RR - u)) | r;
+                    A::ct(x[k], x[k + half], w[(1 << u) - 1 + j], m);
                 }
             }
         }
-    }
 #pragma unroll
-    for (int g = 0; g < G; g++) {
-        u32 v = vt + g * NT;
-        u32 lo = v & ((1u << BLO) - 1), hi = v >> BLO;
-        u32 base = (hi << (BLO + RR)) | lo;
-#pragma unroll
-        for (int k = 0; k < K; k++) st(base + (k << BLO), x[g * K + k]);
+        for (int k = 0; k < K; k++) st(ob + (POUT ? pad_idx((u32)k << BLO) : ((u32)k << BLO)), x[k]);
     }
 }
 
 // One radix-2^RR round of the inverse transform: layers S0+RR-1 down to S0 of the tile.
 // FINAL: layer 0 of the whole transform is in this round and carries the N^-1 scaling.
-template <int LOGT, int S0, int RR, int NT, bool FINAL, class Ld, class St>
-TB_D void inv_round(u32 vt, Ld ld, St st, const u64 *__restrict__ tw, u32 R, u64 p, u64 p2, const ModDev *md) {
-    constexpr int E = 16, G = E >> RR, K = 1 << RR, BLO = LOGT - S0 - RR;
-    static_assert(NT * E == (1 << LOGT), "tile/threads mismatch");
-    static_assert(BLO >= 0, "bad round");
-    u64 x[E];
-#pragma unroll
+template <class A, int LOGT, int NT, int S0, int RR, bool FINAL, bool PIN, bool POUT, class Ld, class St>
+TB_D void inv_round(u32 vt, Ld ld, St st, const void *__restrict__ tw, u32 R, const typename A::Mod &m) {
+    constexpr int K = 1 << RR, BLO = LOGT - S0 - RR, NV = (1 << LOGT) / K, G = NV / NT;
+    static_assert(BLO >= 0 && G >= 1 && NV % NT == 0, "bad round");
+#pragma unroll 1
     for (int g = 0; g < G; g++) {
-        u32 v = vt + g * NT;
-        u32 lo = v & ((1u << BLO) - 1), hi = v >> BLO;
-        u32 base = (hi << (BLO + RR)) | lo;
+        const u32 v = vt + g * NT;
+        const u32 lo = v & ((1u << BLO) - 1), hi = v >> BLO;
+        const u32 base = (hi << (BLO + RR)) | lo;
+        const u32 ib = PIN ? pad_idx(base) : base, ob = POUT ? pad_idx(base) : base;
+        typename A::tw_t w[K - 1];
 #pragma unroll
-        for (int k = 0; k < K; k++) x[g * K + k] = ld(base + (k << BLO));
-    }
+        for (int u = 0; u < RR; u++) {
+            const u32 tbase = (R << (S0 + u)) + (hi << u);
+            if (!(FINAL && S0 == 0 && u == 0)) {
 #pragma unroll
-    for (int u = RR - 1; u >= 0; u--) {
-        const int half = 1 << (RR - 1 - u);
+                for (int j = 0; j < (1 << u); j++) w[(1 << u) - 1 + j] = A::ld_tw(tw, tbase + j);
+            }
+        }
+        typename A::elem x[K];
 #pragma unroll
-        for (int g = 0; g < G; g++) {
-            u32 hi = (vt + g * NT) >> BLO;
-            u32 tbase = (R << (S0 + u)) + (hi << u);
+        for (int k = 0; k < K; k++) {
+            x[k] = ld(ib + (PIN ? pad_idx((u32)k << BLO) : ((u32)k << BLO)));
+            if (A::kReduceEachInvRound) A::reduce(x[k], m);
+        }
+#pragma unroll
+        for (int u = RR - 1; u >= 0; u--) {
+            const int half = 1 << (RR - 1 - u);
             if (FINAL && S0 == 0 && u == 0) {
-                u64 ninv = md->ninv, ninvq = md->ninv_shoup, w1 = md->inv1n, w1q = md->inv1n_shoup;
 #pragma unroll
-                for (int r = 0; r < half; r++) gs_bfly_last(x[g * K + r], x[g * K + r + half], ninv, ninvq, w1, w1q, p, p2);
+                for (int r = 0; r < half; r++) A::gs_last(x[r], x[r + half], m);
             } else {
 #pragma unroll
                 for (int j = 0; j < (1 << u); j++) {
-                    ulonglong2 w = ld_tw(tw, tbase + j);
 #pragma unroll
                     for (int r = 0; r < half; r++) {
-                        int k = (j << (RR - u)) | r;
-                        gs_bfly(x[g * K + k], x[g * K + k + half], w.x, w.y, p, p2);
+                        const int k = (j << (RR - u)) | r;
+                        A::gs(x[k], x[k + half], w[(1 << u) - 1 + j], m);
                     }
                 }
             }
         }
-    }
 #pragma unroll
-    for (int g = 0; g < G; g++) {
-        u32 v = vt + g * NT;
-        u32 lo = v & ((1u << BLO) - 1), hi = v >> BLO;
-        u32 base = (hi << (BLO + RR)) | lo;
-#pragma unroll
-        for (int k = 0; k < K; k++) st(base + (k << BLO), x[g * K + k]);
+        for (int k = 0; k < K; k++) st(ob + (POUT ? pad_idx((u32)k << BLO) : ((u32)k << BLO)), x[k]);
     }
 }
 
-// ---- shared-memory accessors ---------------------------------------------------------------------
-struct SmLd {
+// ---- tile plans ------------------------------------------------------------------------------------------------------------
+// Threads per CTA and layers per round for a tile of 2^LOGT coefficients. Radix-16 rounds keep one group plus its 15
+// twiddles in registers without spilling under the CTA's register cap; every listed round is bank-conflict free with
+// pad_idx (tools/banksim.py).
+template <int LOGT> struct TilePlan;
+template <> struct TilePlan<12> { static constexpr int NT = 256, R0 = 4, R1 = 4, R2 = 4, R3 = 0; };
+template <> struct TilePlan<13> { static constexpr int NT = 512, R0 = 4, R1 = 4, R2 = 4, R3 = 1; };
+template <> struct TilePlan<14> { static constexpr int NT = 512, R0 = 4, R1 = 4, R2 = 4, R3 = 2; };
+template <int LOGT> __host__ __device__ constexpr int tile_threads() { return TilePlan<LOGT>::NT; }
+
+template <class A> struct SmLd { // index is already padded
     const u64 *sm;
-    TB_D u64 operator()(u32 i) const { return sm[pad_idx(i)]; }
+    TB_D typename A::elem operator()(u32 i) const { return A::from_bits(sm[i]); }
 };
-struct SmSt {
+template <class A> struct SmSt {
     u64 *sm;
-    TB_D void operator()(u32 i, u64 v) const { sm[pad_idx(i)] = v; }
+    TB_D void operator()(u32 i, typename A::elem v) const { sm[i] = A::to_bits(v); }
 };
 
-// ---- whole-tile transforms --------------------------------------------------------------------------
-// Forward transform of a tile held by one CTA of NT = 2^LOGT/16 threads.
-//   ld(i)    : coefficient i of the tile, value in [0,4p)  (prologue fused here)
-//   st(i, v) : receives output i, v in [0,4p)              (epilogue fused here; called in linear, coalesced order)
+// Forward transform of a tile held by one CTA.
+//   ld(i)    : coefficient i of the tile as u64 (prologue fused here); RAW_IN: raw element bits of an earlier pass
+//   st(i, v) : receives the canonical residue of output i (epilogue fused here; linear, coalesced order)
 // The last round's results pass through shared memory once more so that global stores are coalesced.
-template <int LOGT, class Ld, class St>
-TB_D void tile_ntt_fwd(u64 *sm, Ld ld, St st, const u64 *__restrict__ tw, u32 R, u64 p) {
-    constexpr int NT = (1 << LOGT) / 16;
-    constexpr int NR = (LOGT + 3) / 4;      // rounds
-    constexpr int RL = LOGT - 4 * (NR - 1); // layers in the last round
-    const u64 p2 = p << 1;
-    SmLd sl{sm};
-    SmSt ss{sm};
-    if constexpr (NR == 1) {
-        TB_PHASE(NT, t, fwd_round<LOGT, 0, RL, NT>(t, ld, ss, tw, R, p, p2);)
-    } else {
-        TB_PHASE(NT, t, fwd_round<LOGT, 0, 4, NT>(t, ld, ss, tw, R, p, p2);)
-        if constexpr (NR >= 3) {
-            TB_PHASE(NT, t, fwd_round<LOGT, 4, 4, NT>(t, sl, ss, tw, R, p, p2);)
-        }
-        if constexpr (NR >= 4) {
-            TB_PHASE(NT, t, fwd_round<LOGT, 8, 4, NT>(t, sl, ss, tw, R, p, p2);)
-        }
-        TB_PHASE(NT, t, fwd_round<LOGT, 4 * (NR - 1), RL, NT>(t, sl, ss, tw, R, p, p2);)
+template <class A, int LOGT, bool RAW_IN, class Ld, class St>
+TB_D void tile_ntt_fwd(u64 *sm, Ld ld, St st, const ModDev *md, u32 R) {
+    typedef TilePlan<LOGT> P;
+    constexpr int NT = P::NT, T = 1 << LOGT;
+    const typename A::Mod m = A::make(md);
+    const void *tw = A::fwd_table(md);
+    SmLd<A> sl{sm};
+    SmSt<A> ss{sm};
+    auto gl = [&](u32 i) -> typename A::elem { return RAW_IN ? A::from_bits(ld(i)) : A::from_u64(ld(i), m); };
+    TB_PHASE(NT, t, (fwd_round<A, LOGT, NT, 0, P::R0, false, true>(t, gl, ss, tw, R, m));)
+    TB_PHASE(NT, t, (fwd_round<A, LOGT, NT, P::R0, P::R1, true, true>(t, sl, ss, tw, R, m));)
+    TB_PHASE(NT, t, (fwd_round<A, LOGT, NT, P::R0 + P::R1, P::R2, true, true>(t, sl, ss, tw, R, m));)
+    if constexpr (P::R3 > 0) {
+        TB_PHASE(NT, t, (fwd_round<A, LOGT, NT, P::R0 + P::R1 + P::R2, P::R3, true, true>(t, sl, ss, tw, R, m));)
     }
     TB_PHASE(NT, t, {
-        _Pragma("unroll") for (int k = 0; k < 16; k++) {
+        _Pragma("unroll 4") for (int k = 0; k < T / NT; k++) {
             u32 i = t + k * NT;
-            st(i, sm[pad_idx(i)]);
+            st(i, A::canon(A::from_bits(sm[pad_idx(i)]), m));
         }
     })
 }
 
-// Inverse transform of a tile. ld(i) must return values in [0,2p); st(i, v) gets v in [0,2p).
-// FINAL = the tile contains layer 0 of the whole transform (N^-1 folded into that layer).
-template <int LOGT, bool FINAL, class Ld, class St>
-TB_D void tile_ntt_inv(u64 *sm, Ld ld, St st, const u64 *__restrict__ tw, u32 R, u64 p, const ModDev *md) {
-    constexpr int NT = (1 << LOGT) / 16;
-    constexpr int NR = (LOGT + 3) / 4;
-    constexpr int RL = LOGT - 4 * (NR - 1); // layers in the FIRST inverse round (deepest layers)
-    const u64 p2 = p << 1;
-    SmLd sl{sm};
-    SmSt ss{sm};
+// Inverse transform of a tile. ld(i): canonical residues as u64. FINAL (the tile contains layer 0, N^-1 folded in):
+// st(i, v) receives canonical residues; otherwise (four-step row pass) st(i, bits) receives raw element bits.
+template <class A, int LOGT, bool FINAL, class Ld, class St>
+TB_D void tile_ntt_inv(u64 *sm, Ld ld, St st, const ModDev *md, u32 R) {
+    typedef TilePlan<LOGT> P;
+    constexpr int NT = P::NT, T = 1 << LOGT;
+    const typename A::Mod m = A::make(md);
+    const void *tw = A::inv_table(md);
+    SmLd<A> sl{sm};
+    SmSt<A> ss{sm};
+    auto gs_ = [&](u32 i, typename A::elem x) {
+        if (FINAL) st(i, A::canon(x, m));
+        else st(i, A::to_bits(x));
+    };
     TB_PHASE(NT, t, {
-        _Pragma("unroll") for (int k = 0; k < 16; k++) {
+        _Pragma("unroll 4") for (int k = 0; k < T / NT; k++) {
             u32 i = t + k * NT;
-            sm[pad_idx(i)] = ld(i);
+            sm[pad_idx(i)] = A::to_bits(A::from_u64(ld(i), m));
         }
     })
-    if constexpr (NR == 1) {
-        TB_PHASE(NT, t, (inv_round<LOGT, 0, RL, NT, FINAL>(t, sl, st, tw, R, p, p2, md));)
-    } else {
-        TB_PHASE(NT, t, (inv_round<LOGT, 4 * (NR - 1), RL, NT, false>(t, sl, ss, tw, R, p, p2, md));)
-        if constexpr (NR >= 4) {
-            TB_PHASE(NT, t, (inv_round<LOGT, 8, 4, NT, false>(t, sl, ss, tw, R, p, p2, md));)
-        }
-        if constexpr (NR >= 3) {
-            TB_PHASE(NT, t, (inv_round<LOGT, 4, 4, NT, false>(t, sl, ss, tw, R, p, p2, md));)
-        }
-        TB_PHASE(NT, t, (inv_round<LOGT, 0, 4, NT, FINAL>(t, sl, st, tw, R, p, p2, md));)
+    if constexpr (P::R3 > 0) {
+        TB_PHASE(NT, t, (inv_round<A, LOGT, NT, P::R0 + P::R1 + P::R2, P::R3, false, true, true>(t, sl, ss, tw, R, m));)
     }
+    TB_PHASE(NT, t, (inv_round<A, LOGT, NT, P::R0 + P::R1, P::R2, false, true, true>(t, sl, ss, tw, R, m));)
+    TB_PHASE(NT, t, (inv_round<A, LOGT, NT, P::R0, P::R1, false, true, true>(t, sl, ss, tw, R, m));)
+    TB_PHASE(NT, t, (inv_round<A, LOGT, NT, 0, P::R0, FINAL, true, false>(t, sl, gs_, tw, R, m));)
 }
 
 } // namespace troyb
