@@ -52,7 +52,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -81,7 +81,8 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return None
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        load = [x for x in sm if x >= 0.5 * max(sm)]  # drop idle samples taken before / after the timed region
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(load)}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -211,11 +212,12 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(max(args.warmup, 3)):
-        step()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)  # let nvidia-smi come up so that it samples during the timed region
+    for _ in range(max(args.warmup, 3)):
+        step()
     launches0 = lib.cdll.troyb_launch_count()
     t_main = timed(step, args.steps)
     launches = lib.cdll.troyb_launch_count() - launches0
@@ -356,8 +358,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="ciphertext pairs per GPU per step")
     ap.add_argument("--ref-reps", type=int, default=4, help="reference arm: ops per thread per step")

@@ -36,7 +36,7 @@ def pad_default(i):
     return i + (i >> 4)
 
 
-PLANS = {12: (256, [4, 4, 4]), 13: (512, [4, 4, 4, 1]), 14: (512, [4, 4, 4, 2])}
+PLANS = {12: (256, [4, 4, 4]), 13: (256, [3, 3, 4, 3]), 14: (512, [3, 4, 4, 3])}
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "search":

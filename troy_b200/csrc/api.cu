@@ -87,6 +87,18 @@ u32 grid_for(u64 total, int threads) { return (u32)((total + threads - 1) / thre
 // ---- NTT dispatch --------------------------------------------------------------------------------------------------
 size_t tile_smem(int logt) { return (size_t)padded_words(1u << logt) * sizeof(u64); }
 
+// Launch order of the limbs of a launch: most expensive butterfly policy first, so that the slow CTAs do not end up
+// alone in the last wave (the CTA scheduler dispatches in blockIdx order).
+void set_order(const Context *ctx, NttArgs &a, u32 n_limbs_in_map, u32 n_outer) {
+    std::vector<int> idx(n_limbs_in_map);
+    for (u32 i = 0; i < n_limbs_in_map; i++) idx[i] = (int)i;
+    std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) {
+        return ctx->h_mods[a.map.idx[x]].policy > ctx->h_mods[a.map.idx[y]].policy;
+    });
+    for (u32 i = 0; i < n_limbs_in_map; i++) a.order[i] = (uint8_t)idx[i];
+    a.n_outer = n_outer;
+}
+
 void run_fwd(const Context *ctx, NttArgs a, u32 units, cudaStream_t s) {
     a.logN = ctx->logN;
     a.mods = ctx->d_mods;
@@ -149,6 +161,7 @@ void ntt_plain(const Context *ctx, bool inverse, const LimbMap &map, u32 L, cons
     a.dst_batch_stride = dst_stride;
     a.canon = canon ? 1 : 0;
     a.scheme = ctx->scheme;
+    set_order(ctx, a, L, batch * (limbs_per_elem / L));
     if (inverse) run_inv(ctx, a, batch * limbs_per_elem, s);
     else run_fwd(ctx, a, batch * limbs_per_elem, s);
 }
@@ -203,6 +216,7 @@ void switch_key_impl(Context *ctx, int level, u64 *ct, u64 ct_stride, const u64 
             a.aux0_batch_stride = target_stride;
             a.dst = D.p;
             a.scheme = ctx->scheme;
+            set_order(ctx, a, Lp, nb);
             run_fwd(ctx, a, nb * Lp * L, s);
         }
         {
@@ -213,7 +227,7 @@ void switch_key_impl(Context *ctx, int level, u64 *ct, u64 ct_stride, const u64 
             k.L = L;
             k.key_limbs = key_limbs;
             k.special_key_limb = key_limbs - 1;
-            k.total = (u64)nb * Lp * N;
+            k.total = (u64)nb * Lp * (N / 2);
             k.D = D.p;
             k.key = key;
             k.prod = prod.p + (u64)b0 * 2 * Lp * N;
@@ -251,6 +265,7 @@ void switch_key_impl(Context *ctx, int level, u64 *ct, u64 ct_stride, const u64 
         a.ct_poly_stride = (u64)L * N;
         a.drop = ctx->key_drop;
         a.scheme = ctx->scheme;
+        set_order(ctx, a, L, batch * 2);
         if (ckks) run_fwd(ctx, a, batch * 2 * L, s);
         else run_inv(ctx, a, batch * 2 * L, s);
     }
@@ -758,6 +773,7 @@ int troyb_mod_switch_scale_to_next(troyb_context *ctx, int level, const uint64_t
         f.dst_poly_stride = (u64)(L - 1) * N;
         f.drop = lv.drop;
         f.scheme = c->scheme;
+        set_order(c, f, L - 1, (u32)(batch * size));
         run_fwd(c, f, (u32)(batch * size * (L - 1)), s);
     } else {
         EltDropLast k{};

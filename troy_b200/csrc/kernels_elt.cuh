@@ -118,7 +118,7 @@ struct KsInnerProduct {
     u32 L;
     u32 key_limbs;
     u32 special_key_limb; // key_limbs - 1
-    u64 total;            // batch * (L+1) * N
+    u64 total;            // batch * (L+1) * N/2 threads (two adjacent coefficients per thread, 128-bit accesses)
     const u64 *D;
     const u64 *key;
     u64 *prod;
@@ -127,26 +127,33 @@ struct KsInnerProduct {
             u64 idx = (u64)bid * kThreads + t;
             if (idx < total) {
                 const u64 N = u64(1) << logN;
-                u64 c = idx & (N - 1);
-                u64 bi = idx >> logN;
-                u32 i = (u32)(bi % (L + 1));
-                u64 b = bi / (L + 1);
+                const u64 c = (idx & (N / 2 - 1)) * 2;
+                const u64 bi = idx >> (logN - 1);
+                const u32 i = (u32)(bi % (L + 1));
+                const u64 b = bi / (L + 1);
                 const ModDev &m = mods[map.idx[i]];
-                u32 key_limb = (i == L) ? special_key_limb : i;
+                const u32 key_limb = (i == L) ? special_key_limb : i;
                 const u64 *d = D + (bi * L) * N + c;
                 const u64 *kp = key + (u64)key_limb * N + c;
                 const u64 key_digit_stride = 2ull * key_limbs * N, key_comp_stride = (u64)key_limbs * N;
-                u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+                u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0, lo2 = 0, hi2 = 0, lo3 = 0, hi3 = 0;
                 for (u32 j = 0; j < L; j++) {
-                    u64 x = d[(u64)j * N];
-                    u64 k0 = __ldg(kp + j * key_digit_stride);
-                    u64 k1 = __ldg(kp + j * key_digit_stride + key_comp_stride);
-                    mac128(lo0, hi0, x, k0);
-                    mac128(lo1, hi1, x, k1);
+                    const ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(d + (u64)j * N);
+                    const ulonglong2 k0 = __ldg(reinterpret_cast<const ulonglong2 *>(kp + j * key_digit_stride));
+                    const ulonglong2 k1 = __ldg(reinterpret_cast<const ulonglong2 *>(kp + j * key_digit_stride + key_comp_stride));
+                    mac128(lo0, hi0, x.x, k0.x);
+                    mac128(lo1, hi1, x.y, k0.y);
+                    mac128(lo2, hi2, x.x, k1.x);
+                    mac128(lo3, hi3, x.y, k1.y);
                 }
                 u64 *po = prod + (b * 2 * (L + 1) + i) * N + c;
-                po[0] = barrett128(lo0, hi0, m.p, m.ratio0, m.ratio1);
-                po[(u64)(L + 1) * N] = barrett128(lo1, hi1, m.p, m.ratio0, m.ratio1);
+                ulonglong2 r0, r1;
+                r0.x = barrett128(lo0, hi0, m.p, m.ratio0, m.ratio1);
+                r0.y = barrett128(lo1, hi1, m.p, m.ratio0, m.ratio1);
+                r1.x = barrett128(lo2, hi2, m.p, m.ratio0, m.ratio1);
+                r1.y = barrett128(lo3, hi3, m.p, m.ratio0, m.ratio1);
+                *reinterpret_cast<ulonglong2 *>(po) = r0;
+                *reinterpret_cast<ulonglong2 *>(po + (u64)(L + 1) * N) = r1;
             }
         })
     }

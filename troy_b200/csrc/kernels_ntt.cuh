@@ -50,6 +50,8 @@ struct NttArgs {
     u64 dst_batch_stride;
     int scheme;
     int add_half;       // INV_ADD_HALF: add half (BFV/CKKS) or plain canonical INTT (BGV)
+    uint8_t order[kMaxLimbs]; // launch rank -> limb index, most expensive butterfly policy first (evens out the waves)
+    u32 n_outer;        // units per limb rank (batch x polys, or batch for MODUP)
     int row_pass;       // forward four-step: this launch is the row pass that follows a column pass
     u64 *scratch;       // four-step intermediate rows [unit][N] for modes that cannot stage in dst
 };
@@ -150,19 +152,23 @@ template <int LOGT> TB_D NttUnit resolve_unit(const NttArgs &a, u32 bid) {
     switch (a.mode) {
     case FWD_PLAIN:
     case INV_PLAIN: {
-        // unit = b * n_limbs + l ; n_limbs counts every limb of one batch element (polys x limbs)
-        u32 l = unit % a.n_limbs, b = unit / a.n_limbs;
+        // storage: unit = b * n_limbs + l, l = poly * L + limb (n_limbs = polys x L); launch order: limb rank slowest
+        const u32 polys = a.n_limbs / a.L;
+        const u32 limb = a.order[unit / a.n_outer], bp = unit % a.n_outer;
+        const u32 l = (bp % polys) * a.L + limb, b = bp / polys;
+        u.unit = b * a.n_limbs + l;
         u.md = a.mods + a.map.idx[l % a.L];
         u.src = a.src + (u64)b * a.src_unit_stride + (u64)l * N;
         u.dst = a.dst + (u64)b * a.dst_batch_stride + (u64)l * N;
         break;
     }
     case FWD_MODUP: {
-        // unit = (b * (L+1) + i) * L + j
-        u32 j = unit % a.L, bi = unit / a.L, i = bi % (a.L + 1), b = bi / (a.L + 1);
+        // storage: unit = (b * (L+1) + i) * L + j; launch order: (rank of i, b, j)
+        const u32 j = unit % a.L, ib = unit / a.L, b = ib % a.n_outer, i = a.order[ib / a.n_outer];
+        u.unit = (b * (a.L + 1) + i) * a.L + j;
         u.md = a.mods + a.map.idx[i];
         u.src = a.src + (u64)b * a.src_unit_stride + (u64)j * N;
-        u.dst = a.dst + (u64)unit * N;
+        u.dst = a.dst + (u64)u.unit * N;
         if (a.aux0 != nullptr && i == j) {
             u.passthrough = true;
             u.src = a.aux0 + (u64)b * a.aux0_batch_stride + (u64)j * N;
@@ -178,8 +184,9 @@ template <int LOGT> TB_D NttUnit resolve_unit(const NttArgs &a, u32 bid) {
     }
     case FWD_MODDOWN:
     case INV_COMBINE: {
-        // unit = (b * K + k) * L + j
-        u32 j = unit % a.L, bk = unit / a.L, k = bk % a.K, b = bk / a.K;
+        // storage: unit = (b * K + k) * L + j; launch order: (rank of j, b * K + k)
+        const u32 j = a.order[unit / a.n_outer], bk = unit % a.n_outer, k = bk % a.K, b = bk / a.K;
+        u.unit = bk * a.L + j;
         u.md = a.mods + a.map.idx[j];
         u.sp = a.aux1 + (u64)bk * N;
         u.acc = a.aux0 + (u64)b * a.acc_batch_stride + (u64)k * a.acc_poly_stride + (u64)j * N;

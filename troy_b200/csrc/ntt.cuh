@@ -334,8 +334,8 @@ TB_D void inv_round(u32 vt, Ld ld, St st, const void *__restrict__ tw, u32 R, co
 // pad_idx (tools/banksim.py).
 template <int LOGT> struct TilePlan;
 template <> struct TilePlan<12> { static constexpr int NT = 256, R0 = 4, R1 = 4, R2 = 4, R3 = 0; };
-template <> struct TilePlan<13> { static constexpr int NT = 512, R0 = 4, R1 = 4, R2 = 4, R3 = 1; };
-template <> struct TilePlan<14> { static constexpr int NT = 512, R0 = 4, R1 = 4, R2 = 4, R3 = 2; };
+template <> struct TilePlan<13> { static constexpr int NT = 256, R0 = 3, R1 = 3, R2 = 4, R3 = 3; };
+template <> struct TilePlan<14> { static constexpr int NT = 512, R0 = 3, R1 = 4, R2 = 4, R3 = 3; };
 template <int LOGT> __host__ __device__ constexpr int tile_threads() { return TilePlan<LOGT>::NT; }
 
 template <class A> struct SmLd { // index is already padded
