@@ -13,5 +13,11 @@ def test_evaluator_flow_emulated(ref, emul_lib, scheme, n, bits):
     run_evaluator_flow(ref, emul_lib, scheme, n, bits, np.random.default_rng(100 + scheme))
 
 
+@pytest.mark.parametrize("scheme,n,bits", [(2, 16384, [60, 40, 60]), (1, 32768, [50, 40, 60]), (3, 65536, [50, 40, 60])])
+def test_cluster_transforms_emulated(ref, emul_lib, scheme, n, bits):
+    """N >= 16384: a limb is a cluster of 2 / 4 / 8 tiles exchanging data through distributed shared memory."""
+    run_evaluator_flow(ref, emul_lib, scheme, n, bits, np.random.default_rng(200 + scheme))
+
+
 def test_batch_emulated(ref, emul_lib):
     run_evaluator_flow(ref, emul_lib, ref.CKKS, 256, [40, 30, 30, 30, 40], np.random.default_rng(5), batch=3)

@@ -99,51 +99,37 @@ void set_order(const Context *ctx, NttArgs &a, u32 n_limbs_in_map, u32 n_outer) 
     a.n_outer = n_outer;
 }
 
+// Tiles per limb and the tile size used for a transform of 2^logN coefficients (see ntt.cuh TilePlan).
+int tile_log(int logN) { return logN == 12 ? 12 : 13; }
+u32 tiles_per_limb(int logN) { return logN <= 13 ? 1u : (1u << (logN - 13)); }
+
 void run_fwd(const Context *ctx, NttArgs a, u32 units, cudaStream_t s) {
     a.logN = ctx->logN;
     a.mods = ctx->d_mods;
-    a.row_pass = 0;
     const int logN = ctx->logN;
+    if (logN > 16) throw std::invalid_argument("poly_modulus_degree above 65536 is not supported");
     if (logN < 12) {
-        ck(launch_cta(NttFwd<0>{a}, units, (size_t)ctx->N * sizeof(u64), s));
+        ck(launch_cta(NttFwdSmall{a}, units, (size_t)ctx->N * sizeof(u64), s));
     } else if (logN == 12) {
-        ck(launch_cta(NttFwd<12>{a}, units, tile_smem(12), s));
-    } else if (logN == 13) {
-        ck(launch_cta(NttFwd<13>{a}, units, tile_smem(13), s));
-    } else if (logN == 14) {
-        ck(launch_cta(NttFwd<14>{a}, units, tile_smem(14), s));
+        ck(launch_cluster(NttFwdTile<12>{a}, units, 1, tile_smem(12), s));
     } else {
-        // four-step: strided column pass (layers 0..logN-13), then 4096-coefficient rows
-        Scratch stage(a.mode == FWD_MODDOWN ? (size_t)units * ctx->N : 0, s);
-        a.scratch = stage.p;
-        if (logN == 15) ck(launch_cta(NttFwdCols<15>{a}, units * (4096 / 256), 0, s));
-        else if (logN == 16) ck(launch_cta(NttFwdCols<16>{a}, units * (4096 / 256), 0, s));
-        else throw std::invalid_argument("poly_modulus_degree above 65536 is not supported");
-        a.row_pass = 1;
-        ck(launch_cta(NttFwd<12>{a}, units << (logN - 12), tile_smem(12), s));
+        const u32 c = tiles_per_limb(logN);
+        ck(launch_cluster(NttFwdTile<13>{a}, units * c, c, tile_smem(13), s));
     }
 }
 
 void run_inv(const Context *ctx, NttArgs a, u32 units, cudaStream_t s) {
     a.logN = ctx->logN;
     a.mods = ctx->d_mods;
-    a.row_pass = 0;
     const int logN = ctx->logN;
+    if (logN > 16) throw std::invalid_argument("poly_modulus_degree above 65536 is not supported");
     if (logN < 12) {
-        ck(launch_cta(NttInv<0>{a}, units, (size_t)ctx->N * sizeof(u64), s));
+        ck(launch_cta(NttInvSmall{a}, units, (size_t)ctx->N * sizeof(u64), s));
     } else if (logN == 12) {
-        ck(launch_cta(NttInv<12>{a}, units, tile_smem(12), s));
-    } else if (logN == 13) {
-        ck(launch_cta(NttInv<13>{a}, units, tile_smem(13), s));
-    } else if (logN == 14) {
-        ck(launch_cta(NttInv<14>{a}, units, tile_smem(14), s));
+        ck(launch_cluster(NttInvTile<12>{a}, units, 1, tile_smem(12), s));
     } else {
-        Scratch stage(a.mode == INV_COMBINE ? (size_t)units * ctx->N : 0, s);
-        a.scratch = stage.p;
-        ck(launch_cta(NttInv<12>{a}, units << (logN - 12), tile_smem(12), s));
-        if (logN == 15) ck(launch_cta(NttInvCols<15>{a}, units * (4096 / 256), 0, s));
-        else if (logN == 16) ck(launch_cta(NttInvCols<16>{a}, units * (4096 / 256), 0, s));
-        else throw std::invalid_argument("poly_modulus_degree above 65536 is not supported");
+        const u32 c = tiles_per_limb(logN);
+        ck(launch_cluster(NttInvTile<13>{a}, units * c, c, tile_smem(13), s));
     }
 }
 
@@ -185,8 +171,8 @@ void switch_key_impl(Context *ctx, int level, u64 *ct, u64 ct_stride, const u64 
     // that it stays inside the 126 MB L2, with the chunk sized to fill whole waves of CTAs on the 148 SMs. Everything
     // else runs once over the whole batch.
     const u64 per_ct_words = (u64)Lp * L * N;
-    const u32 wave = 148u * (ctx->logN >= 14 ? 1u : (ctx->logN == 13 ? 2u : 4u)); // CTAs resident per wave
-    const u32 ctas_per_ct = Lp * L * (ctx->logN > 14 ? (1u << (ctx->logN - 12)) : 1u);
+    const u32 wave = 148u * (ctx->logN >= 13 ? 3u : 6u); // CTAs resident per wave (ntt.cuh TilePlan)
+    const u32 ctas_per_ct = Lp * L * tiles_per_limb(ctx->logN);
     const u32 max_chunk = (u32)std::max<u64>(1, (64ull << 20) / (per_ct_words * 8));
     u32 chunk = 1;
     double best = 0;

@@ -52,8 +52,6 @@ struct NttArgs {
     int add_half;       // INV_ADD_HALF: add half (BFV/CKKS) or plain canonical INTT (BGV)
     uint8_t order[kMaxLimbs]; // launch rank -> limb index, most expensive butterfly policy first (evens out the waves)
     u32 n_outer;        // units per limb rank (batch x polys, or batch for MODUP)
-    int row_pass;       // forward four-step: this launch is the row pass that follows a column pass
-    u64 *scratch;       // four-step intermediate rows [unit][N] for modes that cannot stage in dst
 };
 
 TB_D u64 canon4(u64 v, u64 p) {
@@ -109,18 +107,15 @@ TB_D void small_ntt_inv(u64 *sm, u32 logn, Ld ld, St st, const u64 *__restrict__
     TB_PHASE(256, t, for (u32 i = t; i < n; i += 256) st(i, canon2(sm[i], p));)
 }
 
-inline const char *ntt_kernel_name(int mode, int pass) {
-    // pass: 0 whole tile / row pass of the inverse, 1 four-step column pass, 2 four-step row pass of the forward
-    static const char *names[6][3] = {
-        {"ntt_fwd", "ntt_fwd_cols", "ntt_fwd_rows"},
-        {"ntt_fwd_modup", "ntt_fwd_modup_cols", "ntt_fwd_modup_rows"},
-        {"ntt_fwd_moddown", "ntt_fwd_moddown_cols", "ntt_fwd_moddown_rows"},
-        {"ntt_inv", "ntt_inv_cols", "ntt_inv"},
-        {"ntt_inv_add_half", "ntt_inv_add_half_cols", "ntt_inv_add_half"},
-        {"ntt_inv_combine", "ntt_inv_combine_cols", "ntt_inv_combine"},
-    };
-    int row = mode >= 10 ? 3 + (mode - 10) : mode;
-    return names[row][pass];
+inline const char *ntt_kernel_name(int mode) {
+    switch (mode) {
+    case FWD_PLAIN: return "ntt_fwd";
+    case FWD_MODUP: return "ntt_fwd_modup";
+    case FWD_MODDOWN: return "ntt_fwd_moddown";
+    case INV_PLAIN: return "ntt_inv";
+    case INV_ADD_HALF: return "ntt_inv_add_half";
+    default: return "ntt_inv_combine";
+    }
 }
 
 // Per-CTA resolved job: where to read / write and with which modulus.
@@ -208,179 +203,178 @@ template <int LOGT> TB_D NttUnit resolve_unit(const NttArgs &a, u32 bid) {
     default: { typedef ArithU64Exact A; __VA_ARGS__ } break;                        \
     }
 
-template <int LOGT> __host__ __device__ constexpr int ntt_cta_threads() {
-    if constexpr (LOGT == 0) return 256;
-    else return tile_threads<LOGT>();
+// Prologue of a forward transform: coefficient i of the limb as the transform's input.
+struct FwdLoad {
+    const u64 *in;
+    u64 p, ratio1, fix;
+    int mode;
+    TB_D u64 operator()(u32 i) const {
+        u64 x = in[i];
+        if (mode == FWD_MODUP) x = barrett64(x, p, ratio1);
+        else if (mode == FWD_MODDOWN) x = barrett64(x, p, ratio1) + fix;
+        return x;
+    }
+};
+
+// Epilogue of a forward transform: v is the canonical residue of output i of the limb.
+struct FwdStore {
+    NttUnit u;
+    u64 p;
+    int mode;
+    TB_D void operator()(u32 i, u64 v) const {
+        if (mode == FWD_MODDOWN) {
+            u64 r = shoup(submod(u.acc[i], v, p), u.dl.inv_last, u.dl.inv_last_shoup, p);
+            if (u.ct) u.ct[i] = addmod(u.ct[i], r, p);
+            else u.dst[i] = r;
+        } else {
+            u.dst[i] = v;
+        }
+    }
+};
+
+// Epilogue of a completed inverse transform (v = canonical residue of coefficient idx of the limb).
+TB_D void inv_store_final(const NttArgs &a, const NttUnit &u, u64 p, u64 idx, u64 v) {
+    const int mode = a.mode;
+    const DropDev &dr = a.drop;
+    if (mode == INV_PLAIN) {
+        u.dst[idx] = v;
+    } else if (mode == INV_ADD_HALF) {
+        u.dst[idx] = a.add_half ? addmod(v, dr.half, p) : v;
+    } else { // INV_COMBINE
+        u64 s = u.sp[idx];
+        u64 sub;
+        const u64 ratio1 = u.md->ratio1;
+        if (a.scheme == SCHEME_BGV) {
+            // BGV (UtilE): k = -(s mod t) * q_last^-1 mod t ; delta = (k mod q_j) * q_last mod q_j ; c = s mod q_j
+            u64 kk = negmod(barrett64(s, dr.t, dr.t_ratio1), dr.t);
+            kk = shoup(kk, dr.inv_last_mod_t, dr.inv_last_mod_t_shoup, dr.t);
+            u64 delta = shoup(barrett64(kk, p, ratio1), u.dl.last_mod, u.dl.last_mod_shoup, p);
+            sub = delta + barrett64(s, p, ratio1);
+        } else {
+            // BFV (UtilF/G): (s' mod q_j) + q_j - half mod q_j
+            sub = barrett64(s, p, ratio1) + (p - u.dl.half_mod);
+        }
+        u64 d = v + (p << 1) - sub; // v < p, sub <= 2p  ->  d in (0,3p)
+        u64 r = shoup(d, u.dl.inv_last, u.dl.inv_last_shoup, p);
+        if (u.ct) u.ct[idx] = addmod(u.ct[idx], r, p);
+        else u.dst[idx] = r;
+    }
 }
 
-template <int LOGT> struct NttFwd {
-    static constexpr int kThreads = ntt_cta_threads<LOGT>();
+// ---- small N (< 4096; only the reference's toy-parameter tests use it): one CTA per limb, radix-2 -------------------------
+struct NttFwdSmall {
+    static constexpr int kThreads = 256;
     NttArgs a;
-    const char *name() const { return ntt_kernel_name(a.mode, a.row_pass ? 2 : 0); }
+    const char *name() const { return ntt_kernel_name(a.mode); }
     TB_D void operator()(u32 bid, u64 *sm) const {
+        const NttUnit u = resolve_unit<0>(a, bid);
+        const ModDev *md = u.md;
+        const u32 n = 1u << a.logN;
+        if (u.passthrough) {
+            TB_PHASE(kThreads, t, for (u32 i = t; i < n; i += kThreads) u.dst[i] = u.src[i];)
+            return;
+        }
+        const FwdLoad ld{u.src, md->p, md->ratio1, a.mode == FWD_MODDOWN ? md->p - u.dl.half_mod : 0, a.mode};
+        const FwdStore st{u, md->p, a.mode};
+        small_ntt_fwd(sm, (u32)a.logN, ld, st, md->fwd, md->p);
+    }
+};
+
+struct NttInvSmall {
+    static constexpr int kThreads = 256;
+    NttArgs a;
+    const char *name() const { return ntt_kernel_name(a.mode); }
+    TB_D void operator()(u32 bid, u64 *sm) const {
+        const NttUnit u = resolve_unit<0>(a, bid);
+        const ModDev *md = u.md;
+        const u64 p = md->p;
+        auto ld = [&](u32 i) -> u64 { return u.src[i]; };
+        auto st = [&](u32 i, u64 v) { inv_store_final(a, u, p, i, v); };
+        small_ntt_inv(sm, (u32)a.logN, ld, st, md->inv, p, md);
+    }
+};
+
+// ---- tile / cluster transforms (N >= 4096) ---------------------------------------------------------------------------
+// One CTA per tile of 2^LOGT coefficients; a limb of N = 2^LOGC tiles is one thread-block cluster (launch_cluster).
+// Forward: stage_a = the LOGC layers that couple the tiles (results scattered into the peers' shared memory),
+//          stage_b = the tile's own 2^LOGT-point transform, canonical store with the fused epilogue.
+// Inverse: stage_a = the tile's own inverse transform, stage_b = the last LOGC layers gathered from the peers.
+#define TB_WITH_LOGC(logc, ...)                                  \
+    switch (logc) {                                              \
+    case 1: { constexpr int LOGC = 1; __VA_ARGS__ } break;       \
+    case 2: { constexpr int LOGC = 2; __VA_ARGS__ } break;       \
+    default: { constexpr int LOGC = 3; __VA_ARGS__ } break;      \
+    }
+
+template <int LOGT> struct NttFwdTile {
+    static constexpr int kThreads = TilePlan<LOGT>::NT;
+    static constexpr int kMinCtas = TilePlan<LOGT>::CTAS;
+    static constexpr bool kTrailingBarrier = false; // peers only write into this CTA's tile, and only before the barrier
+    NttArgs a;
+    const char *name() const { return ntt_kernel_name(a.mode); }
+
+    TB_D void stage_a(u32 bid, u32 rank, u32 nranks, u64 *, const Peers &peers) const {
+        if (nranks == 1) return;
+        const NttUnit u = resolve_unit<LOGT>(a, bid);
+        if (u.passthrough) return;
+        const ModDev *md = u.md;
+        const FwdLoad ld{u.src, md->p, md->ratio1, a.mode == FWD_MODDOWN ? md->p - u.dl.half_mod : 0, a.mode};
+        auto st_peer = [&](u32 k, u32 pi, u64 bits) { peers.st(k, pi, bits); };
+        TB_WITH_POLICY(md, TB_WITH_LOGC(u.rows_log, TB_PHASE(kThreads, t, (cluster_fwd_stage<A, LOGC, LOGT, kThreads>(t, rank, ld, st_peer, md));)))
+    }
+
+    TB_D void stage_b(u32 bid, u32 rank, u32 nranks, u64 *sm, const Peers &) const {
+        NttUnit u = resolve_unit<LOGT>(a, bid);
+        const ModDev *md = u.md;
+        const u64 off = (u64)rank << LOGT;
+        if (u.passthrough) {
+            TB_PHASE(kThreads, t, for (u32 i = t; i < (1u << LOGT); i += kThreads) u.dst[off + i] = u.src[off + i];)
+            return;
+        }
+        const u32 R = nranks + rank;
+        // this tile's outputs are coefficients [off, off + T) of the limb's (bit-reversed) output
+        if (u.dst) u.dst += off;
+        if (u.ct) u.ct += off;
+        if (u.acc) u.acc += off;
+        const FwdStore st{u, md->p, a.mode};
+        if (nranks == 1) {
+            const FwdLoad ld{u.src, md->p, md->ratio1, a.mode == FWD_MODDOWN ? md->p - u.dl.half_mod : 0, a.mode};
+            TB_WITH_POLICY(md, (tile_ntt_fwd<A, LOGT, false>(sm, ld, st, md, R));)
+        } else {
+            TB_WITH_POLICY(md, (tile_ntt_fwd<A, LOGT, true>(sm, 0, st, md, R));)
+        }
+    }
+};
+
+template <int LOGT> struct NttInvTile {
+    static constexpr int kThreads = TilePlan<LOGT>::NT;
+    static constexpr int kMinCtas = TilePlan<LOGT>::CTAS;
+    static constexpr bool kTrailingBarrier = true; // peers read this CTA's tile in stage_b
+    NttArgs a;
+    const char *name() const { return ntt_kernel_name(a.mode); }
+
+    TB_D void stage_a(u32 bid, u32 rank, u32 nranks, u64 *sm, const Peers &) const {
         const NttUnit u = resolve_unit<LOGT>(a, bid);
         const ModDev *md = u.md;
         const u64 p = md->p;
-        const u32 tile = LOGT == 0 ? (1u << a.logN) : (1u << LOGT);
-        const u64 off = (u64)u.row * tile;
-        const int mode = a.mode;
-        const bool row_pass = a.row_pass != 0;
-        if (u.passthrough) {
-            if (row_pass) return; // the column pass already copied the limb
-            TB_PHASE(kThreads, t, for (u32 i = t; i < tile; i += kThreads) u.dst[off + i] = u.src[off + i];)
-            return;
-        }
-        const u64 ratio1 = md->ratio1;
-        const u64 fix = (mode == FWD_MODDOWN) ? p - u.dl.half_mod : 0;
-        const u64 *in = !row_pass ? u.src : (mode == FWD_MODDOWN ? a.scratch + ((u64)u.unit << a.logN) : u.dst);
-        auto ld = [&](u32 i) -> u64 {
-            u64 x = in[off + i];
-            if (row_pass) return x; // raw element bits left by the column pass
-            if (mode == FWD_MODUP) x = barrett64(x, p, ratio1);
-            else if (mode == FWD_MODDOWN) x = barrett64(x, p, ratio1) + fix;
-            return x;
-        };
-        auto st = [&](u32 i, u64 v) { // v is the canonical residue
-            if (mode == FWD_MODDOWN) {
-                u64 r = shoup(submod(u.acc[off + i], v, p), u.dl.inv_last, u.dl.inv_last_shoup, p);
-                if (u.ct) u.ct[off + i] = addmod(u.ct[off + i], r, p);
-                else u.dst[off + i] = r;
-            } else {
-                u.dst[off + i] = v;
-            }
-        };
-        if constexpr (LOGT == 0) {
-            small_ntt_fwd(sm, (u32)a.logN, ld, st, md->fwd, p);
+        const u64 *in = u.src + ((u64)rank << LOGT);
+        auto ld = [&](u32 i) -> u64 { return in[i]; };
+        if (nranks == 1) {
+            auto st = [&](u32 i, u64 v) { inv_store_final(a, u, p, i, v); };
+            TB_WITH_POLICY(md, (tile_ntt_inv<A, LOGT, true>(sm, ld, st, md, 1u));)
         } else {
-            const u32 R = (1u << u.rows_log) + u.row;
-            if (row_pass) {
-                TB_WITH_POLICY(md, (tile_ntt_fwd<A, LOGT, true>(sm, ld, st, md, R));)
-            } else {
-                TB_WITH_POLICY(md, (tile_ntt_fwd<A, LOGT, false>(sm, ld, st, md, R));)
-            }
+            TB_WITH_POLICY(md, (tile_ntt_inv<A, LOGT, false>(sm, ld, 0, md, nranks + rank));)
         }
     }
-};
 
-template <int LOGT> struct NttInv {
-    static constexpr int kThreads = ntt_cta_threads<LOGT>();
-    NttArgs a;
-    const char *name() const { return ntt_kernel_name(a.mode, 0); }
-    TB_D void operator()(u32 bid, u64 *sm) const {
+    TB_D void stage_b(u32 bid, u32 rank, u32 nranks, u64 *, const Peers &peers) const {
+        if (nranks == 1) return;
         const NttUnit u = resolve_unit<LOGT>(a, bid);
         const ModDev *md = u.md;
         const u64 p = md->p;
-        const u32 tile = LOGT == 0 ? (1u << a.logN) : (1u << LOGT);
-        const u64 off = (u64)u.row * tile;
-        const bool whole = (u.rows_log == 0);
-        auto ld = [&](u32 i) -> u64 { return u.src[off + i]; };
-        u64 *stage = (a.mode == INV_COMBINE) ? a.scratch + ((u64)u.unit << a.logN) : u.dst;
-        auto st = [&](u32 i, u64 v) {
-            if (!whole) { stage[off + i] = v; return; } // four-step: raw bits; the column pass finishes the job
-            store_final(a, u, p, off + i, v);
-        };
-        if constexpr (LOGT == 0) {
-            small_ntt_inv(sm, (u32)a.logN, ld, st, md->inv, p, md);
-        } else {
-            if (whole) {
-                TB_WITH_POLICY(md, (tile_ntt_inv<A, LOGT, true>(sm, ld, st, md, 1u));)
-            } else {
-                TB_WITH_POLICY(md, (tile_ntt_inv<A, LOGT, false>(sm, ld, st, md, (1u << u.rows_log) + u.row));)
-            }
-        }
-    }
-
-    // Epilogue of a completed inverse transform (v = canonical residue); shared with the four-step column pass.
-    static TB_D void store_final(const NttArgs &a, const NttUnit &u, u64 p, u64 idx, u64 v) {
-        const int mode = a.mode;
-        const DropDev &dr = a.drop;
-        if (mode == INV_PLAIN) {
-            u.dst[idx] = v;
-        } else if (mode == INV_ADD_HALF) {
-            u.dst[idx] = a.add_half ? addmod(v, dr.half, p) : v;
-        } else { // INV_COMBINE
-            u64 s = u.sp[idx];
-            u64 sub;
-            const u64 ratio1 = u.md->ratio1;
-            if (a.scheme == SCHEME_BGV) {
-                // BGV (UtilE): k = -(s mod t) * q_last^-1 mod t ; delta = (k mod q_j) * q_last mod q_j ; c = s mod q_j
-                u64 kk = negmod(barrett64(s, dr.t, dr.t_ratio1), dr.t);
-                kk = shoup(kk, dr.inv_last_mod_t, dr.inv_last_mod_t_shoup, dr.t);
-                u64 delta = shoup(barrett64(kk, p, ratio1), u.dl.last_mod, u.dl.last_mod_shoup, p);
-                sub = delta + barrett64(s, p, ratio1);
-            } else {
-                // BFV (UtilF/G): (s' mod q_j) + q_j - half mod q_j
-                sub = barrett64(s, p, ratio1) + (p - u.dl.half_mod);
-            }
-            u64 d = v + (p << 1) - sub; // v < p, sub <= 2p  ->  d in (0,3p)
-            u64 r = shoup(d, u.dl.inv_last, u.dl.inv_last_shoup, p);
-            if (u.ct) u.ct[idx] = addmod(u.ct[idx], r, p);
-            else u.dst[idx] = r;
-        }
-    }
-};
-
-// ---- four-step column passes (N = 32768 / 65536): layers 0..LOGN-13 over elements N/16 apart -------------
-template <int LOGN> struct NttFwdCols {
-    static constexpr int kThreads = 256;
-    NttArgs a;
-    const char *name() const { return ntt_kernel_name(a.mode, 1); }
-    TB_D void operator()(u32 bid, u64 *) const {
-        constexpr u32 NTV = (1u << LOGN) >> (LOGN - 12), CPB = NTV / kThreads;
-        const u32 chunk = bid % CPB;
-        NttArgs b = a;
-        b.logN = LOGN; // resolve with rows_log = 0: unit = bid / CPB
-        const NttUnit u = resolve_unit<LOGN>(b, bid / CPB);
-        const ModDev *md = u.md;
-        const u64 p = md->p;
-        if (u.passthrough) {
-            TB_PHASE(kThreads, t, {
-                u32 v = chunk * kThreads + t;
-                for (u32 k = 0; k < (1u << (LOGN - 12)); k++) u.dst[v + k * NTV] = u.src[v + k * NTV];
-            })
-            return;
-        }
-        const int mode = a.mode;
-        const u64 ratio1 = md->ratio1;
-        const u64 fix = (mode == FWD_MODDOWN) ? p - u.dl.half_mod : 0;
-        // The column pass leaves raw element bits where the row pass will read them: the destination buffer for
-        // PLAIN / MODUP, a scratch row for MODDOWN.
-        u64 *out = (mode == FWD_MODDOWN) ? a.scratch + ((u64)u.unit << LOGN) : u.dst;
-        TB_WITH_POLICY(md, {
-            const typename A::Mod m = A::make(md);
-            auto ld = [&](u32 i) -> typename A::elem {
-                u64 x = u.src[i];
-                if (mode == FWD_MODUP) x = barrett64(x, p, ratio1);
-                else if (mode == FWD_MODDOWN) x = barrett64(x, p, ratio1) + fix;
-                return A::from_u64(x, m);
-            };
-            auto st = [&](u32 i, typename A::elem v) { out[i] = A::to_bits(v); };
-            TB_PHASE(kThreads, t, (fwd_round<A, LOGN, (int)NTV, 0, LOGN - 12, false, false>(chunk * kThreads + t, ld, st, A::fwd_table(md), 1u, m));)
-        })
-    }
-};
-
-template <int LOGN> struct NttInvCols {
-    static constexpr int kThreads = 256;
-    NttArgs a;
-    const char *name() const { return ntt_kernel_name(a.mode, 1); }
-    TB_D void operator()(u32 bid, u64 *) const {
-        constexpr u32 NTV = (1u << LOGN) >> (LOGN - 12), CPB = NTV / kThreads;
-        const u32 chunk = bid % CPB;
-        NttArgs b = a;
-        b.logN = LOGN;
-        const NttUnit u = resolve_unit<LOGN>(b, bid / CPB);
-        const ModDev *md = u.md;
-        const u64 p = md->p;
-        // The row pass left raw element bits in the destination row (PLAIN / ADD_HALF) or in a scratch row (COMBINE).
-        const u64 *in = (a.mode == INV_COMBINE) ? a.scratch + ((u64)u.unit << LOGN) : u.dst;
-        TB_WITH_POLICY(md, {
-            const typename A::Mod m = A::make(md);
-            auto ld = [&](u32 i) -> typename A::elem { return A::from_bits(in[i]); };
-            auto st = [&](u32 i, typename A::elem v) { NttInv<12>::store_final(a, u, p, i, A::canon(v, m)); };
-            TB_PHASE(kThreads, t,
-                     (inv_round<A, LOGN, (int)NTV, 0, LOGN - 12, true, false, false>(chunk * kThreads + t, ld, st, A::inv_table(md), 1u, m));)
-        })
+        auto ld_peer = [&](u32 k, u32 pi) -> u64 { return peers.ld(k, pi); };
+        auto st = [&](u32 i, u64 v) { inv_store_final(a, u, p, i, v); };
+        TB_WITH_POLICY(md, TB_WITH_LOGC(u.rows_log, TB_PHASE(kThreads, t, (cluster_inv_stage<A, LOGC, LOGT, kThreads>(t, rank, ld_peer, st, md));)))
     }
 };
 

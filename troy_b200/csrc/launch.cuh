@@ -7,6 +7,12 @@
 // where `t` is the thread index. On the GPU a phase is the body followed by __syncthreads(); nothing is
 // carried in registers across phases.
 //
+// Cluster kernels (launch_cluster) are functors with two stages separated by a cluster-wide barrier:
+//     __device__ void stage_a(u32 bid, u32 rank, u32 nranks, u64 *smem, const Peers &peers) const
+//     __device__ void stage_b(u32 bid, u32 rank, u32 nranks, u64 *smem, const Peers &peers) const
+// `peers` reads / writes 64-bit words of the shared memory of any CTA of the cluster (distributed shared memory).
+// A second barrier after stage_b keeps every CTA's shared memory alive until its peers have finished reading it.
+//
 // TROYB_HOST_EMUL (tests/emul only, never part of the product library) re-targets the same functors to a
 // sequential CPU loop over CTAs and threads so that index arithmetic can be debugged without a GPU.
 #pragma once
@@ -44,6 +50,26 @@ inline Profiler &profiler() {
 template <class F> inline cudaError_t launch_cta(const F &f, u32 grid, size_t smem_bytes, cudaStream_t) {
     std::vector<u64> sm(smem_bytes / 8 + 1);
     for (u32 b = 0; b < grid; b++) f(b, sm.data());
+    launch_counter()++;
+    return cudaSuccess;
+}
+
+struct Peers {
+    u64 *const *tiles;
+    u64 ld(u32 rank, u32 word) const { return tiles[rank][word]; }
+    void st(u32 rank, u32 word, u64 v) const { tiles[rank][word] = v; }
+};
+
+template <class F> inline cudaError_t launch_cluster(const F &f, u32 grid, u32 nranks, size_t smem_bytes, cudaStream_t) {
+    std::vector<std::vector<u64>> sm(nranks, std::vector<u64>(smem_bytes / 8 + 1));
+    std::vector<u64 *> ptr(nranks);
+    for (u32 r = 0; r < nranks; r++) ptr[r] = sm[r].data();
+    Peers peers{ptr.data()};
+    for (u32 b0 = 0; b0 < grid; b0 += nranks) {
+        for (u32 r = 0; r < nranks; r++) f.stage_a(b0 + r, r, nranks, ptr[r], peers);
+        for (u32 r = 0; r < nranks; r++) f.stage_b(b0 + r, r, nranks, ptr[r], peers);
+    }
+    launch_counter()++;
     return cudaSuccess;
 }
 
@@ -88,6 +114,80 @@ template <class F> inline cudaError_t launch_cta(const F &f, u32 grid, size_t sm
     }
     launch_counter()++;
     return cudaGetLastError();
+}
+
+// ---- thread-block clusters + distributed shared memory ---------------------------------------------------------------
+struct Peers {
+    u32 base; // shared::cta address of this CTA's dynamic shared memory (same offset in every CTA of the cluster)
+    TB_D u32 addr(u32 rank, u32 word) const {
+        u32 r;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(base + word * 8u), "r"(rank));
+        return r;
+    }
+    TB_D u64 ld(u32 rank, u32 word) const {
+        u64 v;
+        asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(addr(rank, word)) : "memory");
+        return v;
+    }
+    TB_D void st(u32 rank, u32 word, u64 v) const {
+        asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(addr(rank, word)), "l"(v) : "memory");
+    }
+};
+
+TB_D void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <class F> __global__ void __launch_bounds__(F::kThreads, F::kMinCtas) k_cluster(const F f) {
+    extern __shared__ __align__(16) u64 tb_smem[];
+    u32 rank, nranks;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(nranks));
+    const Peers peers{(u32)__cvta_generic_to_shared(tb_smem)};
+    f.stage_a(blockIdx.x, rank, nranks, tb_smem, peers);
+    if (nranks > 1) cluster_barrier();
+    f.stage_b(blockIdx.x, rank, nranks, tb_smem, peers);
+    if (nranks > 1 && F::kTrailingBarrier) cluster_barrier();
+}
+
+template <class F> inline cudaError_t launch_cluster(const F &f, u32 grid, u32 nranks, size_t smem_bytes, cudaStream_t stream) {
+    if (grid == 0) return cudaSuccess;
+    if (grid % nranks) return cudaErrorInvalidValue;
+    static bool configured = false; // per functor type
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_cluster<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(F::kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = nranks;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    Profiler &prof = profiler();
+    cudaError_t e;
+    if (prof.enabled) {
+        ProfRecord r;
+        r.name = f.name();
+        r.grid = grid;
+        cudaEventCreate(&r.e0);
+        cudaEventCreate(&r.e1);
+        cudaEventRecord(r.e0, stream);
+        e = cudaLaunchKernelEx(&cfg, k_cluster<F>, f);
+        cudaEventRecord(r.e1, stream);
+        prof.records.push_back(r);
+    } else {
+        e = cudaLaunchKernelEx(&cfg, k_cluster<F>, f);
+    }
+    launch_counter()++;
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 #endif

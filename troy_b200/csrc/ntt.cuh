@@ -236,46 +236,146 @@ struct ArithF64 {
     }
 };
 
-// One radix-2^RR round of the forward transform on a tile of 2^LOGT coefficients, layers S0..S0+RR-1, run by NT
-// cooperating threads. The tile splits into 2^(LOGT-RR) independent groups of 2^RR coefficients spaced 2^BLO apart; a
-// thread takes groups vt, vt+NT, ... one after the other, holding one group (and all of its 2^RR-1 twiddles, fetched
-// up front so that their latency overlaps the data loads) in registers at a time.
-//   PIN / POUT: the source / destination is the padded shared-memory tile (index = pad_idx(i)); the padded offset of
-//   coefficient k of a group is a compile-time constant because the group base and k << BLO occupy disjoint bits.
-template <class A, int LOGT, int NT, int S0, int RR, bool PIN, bool POUT, class Ld, class St>
-TB_D void fwd_round(u32 vt, Ld ld, St st, const void *__restrict__ tw, u32 R, const typename A::Mod &m) {
-    constexpr int K = 1 << RR, BLO = LOGT - S0 - RR, NV = (1 << LOGT) / K, G = NV / NT;
-    static_assert(BLO >= 0 && G >= 1 && NV % NT == 0, "bad round");
-#pragma unroll 1
-    for (int g = 0; g < G; g++) {
-        const u32 v = vt + g * NT;
-        const u32 lo = v & ((1u << BLO) - 1), hi = v >> BLO;
-        const u32 base = (hi << (BLO + RR)) | lo;
-        const u32 ib = PIN ? pad_idx(base) : base, ob = POUT ? pad_idx(base) : base;
-        typename A::tw_t w[K - 1];
+// ---- register butterfly networks --------------------------------------------------------------------------------------------
+// 2^RR coefficients held by one thread; w[(1 << u) - 1 + j] is the twiddle of block j of layer u of the network.
+template <class A, int RR> TB_D void radix_fwd(typename A::elem (&x)[1 << RR], const typename A::tw_t (&w)[(1 << RR) - 1 + (RR == 0)],
+                                               const typename A::Mod &m) {
 #pragma unroll
-        for (int u = 0; u < RR; u++) {
-            const u32 tbase = (R << (S0 + u)) + (hi << u);
+    for (int u = 0; u < RR; u++) {
+        const int half = 1 << (RR - 1 - u);
 #pragma unroll
-            for (int j = 0; j < (1 << u); j++) w[(1 << u) - 1 + j] = A::ld_tw(tw, tbase + j);
+        for (int j = 0; j < (1 << u); j++) {
+#pragma unroll
+            for (int r = 0; r < half; r++) {
+                const int k = (j << (RR - u)) | r;
+                A::ct(x[k], x[k + half], w[(1 << u) - 1 + j], m);
+            }
         }
-        typename A::elem x[K];
+    }
+}
+
+// LAST: layer 0 of the whole transform is layer 0 of this network and carries the N^-1 scaling (its twiddle is unused).
+template <class A, int RR, bool LAST> TB_D void radix_inv(typename A::elem (&x)[1 << RR],
+                                                          const typename A::tw_t (&w)[(1 << RR) - 1 + (RR == 0)],
+                                                          const typename A::Mod &m) {
 #pragma unroll
-        for (int k = 0; k < K; k++) x[k] = ld(ib + (PIN ? pad_idx((u32)k << BLO) : ((u32)k << BLO)));
+    for (int u = RR - 1; u >= 0; u--) {
+        const int half = 1 << (RR - 1 - u);
+        if (LAST && u == 0) {
 #pragma unroll
-        for (int u = 0; u < RR; u++) {
-            const int half = 1 << (RR - 1 - u);
+            for (int r = 0; r < half; r++) A::gs_last(x[r], x[r + half], m);
+        } else {
 #pragma unroll
             for (int j = 0; j < (1 << u); j++) {
 #pragma unroll
                 for (int r = 0; r < half; r++) {
                     const int k = (j << (RR - u)) | r;
-                    A::ct(x[k], x[k + half], w[(1 << u) - 1 + j], m);
+                    A::gs(x[k], x[k + half], w[(1 << u) - 1 + j], m);
                 }
             }
         }
+    }
+}
+
+// Which group a thread slot handles. Slots are consecutive across lanes; for rounds whose groups are less than 16
+// coefficients apart (0 < BLO < 4) consecutive groups would collide in shared-memory banks, so the lane bits [BLO,4) are
+// exchanged with the group bits that the padding maps to the missing banks (tools/banksim.py checks every plan).
+template <int BLO, int RR> TB_D u32 group_of_slot(u32 w) {
+    if constexpr (BLO > 0 && BLO < 4) {
+        static_assert(BLO >= RR, "round plan needs a lane rotation that is not implemented");
+        constexpr u32 W = 4 - BLO, A0 = BLO, B0 = BLO + 4 - RR;
+        constexpr u32 MA = ((1u << W) - 1) << A0, MB = ((1u << W) - 1) << B0;
+        return (w & ~(MA | MB)) | ((w & MA) << (B0 - A0)) | ((w & MB) >> (B0 - A0));
+    } else {
+        return w;
+    }
+}
+
+__host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x >> 1); }
+
+// Geometry of one radix-2^RR round on a tile of 2^LOGT coefficients, layers S0..S0+RR-1, run by NT cooperating
+// threads. The tile splits into NV = 2^(LOGT-RR) independent groups of K = 2^RR coefficients spaced 2^BLO apart;
+// group v = (hi, lo) has base index (hi << (BLO+RR)) | lo and uses the twiddles of block hi. A thread takes G groups.
+//   SHARED : the G groups of a thread lie in the same block hi (possible when a block has at least 16 G groups), so
+//            the thread fetches its 2^RR-1 twiddles once per round;
+//   else   : thread slots are consecutive groups; U groups are in flight at a time (twiddles and data fetched up front
+//            so that their latencies overlap).
+template <int LOGT, int NT, int S0, int RR> struct RoundGeom {
+    static constexpr int K = 1 << RR, BLO = LOGT - S0 - RR, NV = (1 << LOGT) / K, G = NV / NT, LOGG = ilog2(G);
+    static_assert(BLO >= 0 && G >= 1 && NV % NT == 0 && (1 << LOGG) == G, "bad round");
+    static constexpr bool SHARED = BLO >= LOGG + 4;
+    static constexpr int TL = SHARED ? BLO - LOGG : 0;
+    static constexpr int U = SHARED ? 1 : ((RR <= 2 && G % 2 == 0) ? 2 : 1);
+    // group handled by thread vt in its g-th turn
+    static TB_D void locate(u32 vt, int g, u32 &hi, u32 &base) {
+        if constexpr (SHARED) {
+            hi = vt >> TL;
+            base = (hi << (BLO + RR)) | ((u32)g << TL) | (vt & ((1u << TL) - 1));
+        } else {
+            const u32 v = group_of_slot<BLO, RR>(vt + (u32)g * NT);
+            hi = v >> BLO;
+            base = (hi << (BLO + RR)) | (v & ((1u << BLO) - 1));
+        }
+    }
+};
+
+template <class A, int RR, int S0> TB_D void load_twiddles(typename A::tw_t (&w)[(1 << RR) - 1], const void *__restrict__ tw, u32 R, u32 hi) {
 #pragma unroll
-        for (int k = 0; k < K; k++) st(ob + (POUT ? pad_idx((u32)k << BLO) : ((u32)k << BLO)), x[k]);
+    for (int u = 0; u < RR; u++) {
+        const u32 tbase = (R << (S0 + u)) + (hi << u);
+#pragma unroll
+        for (int j = 0; j < (1 << u); j++) w[(1 << u) - 1 + j] = A::ld_tw(tw, tbase + j);
+    }
+}
+
+//   PIN / POUT: the source / destination is the padded shared-memory tile (index = pad_idx(i)); the padded offset of
+//   coefficient k of a group is a compile-time constant because the group base and k << BLO occupy disjoint bits.
+template <class A, int LOGT, int NT, int S0, int RR, bool PIN, bool POUT, class Ld, class St>
+TB_D void fwd_round(u32 vt, Ld ld, St st, const void *__restrict__ tw, u32 R, const typename A::Mod &m) {
+    typedef RoundGeom<LOGT, NT, S0, RR> Q;
+    constexpr int K = Q::K, BLO = Q::BLO, G = Q::G, U = Q::U;
+    if constexpr (Q::SHARED) {
+        u32 hi, base0;
+        Q::locate(vt, 0, hi, base0);
+        typename A::tw_t w[K - 1];
+        load_twiddles<A, RR, S0>(w, tw, R, hi);
+#pragma unroll 2
+        for (int g = 0; g < G; g++) {
+            const u32 base = base0 | ((u32)g << Q::TL);
+            const u32 ib = PIN ? pad_idx(base) : base, ob = POUT ? pad_idx(base) : base;
+            typename A::elem x[K];
+#pragma unroll
+            for (int k = 0; k < K; k++) x[k] = ld(ib + (PIN ? pad_idx((u32)k << BLO) : ((u32)k << BLO)));
+            radix_fwd<A, RR>(x, w, m);
+#pragma unroll
+            for (int k = 0; k < K; k++) st(ob + (POUT ? pad_idx((u32)k << BLO) : ((u32)k << BLO)), x[k]);
+        }
+    } else {
+#pragma unroll 1
+        for (int g = 0; g < G; g += U) {
+            u32 ib[U], ob[U];
+            typename A::tw_t w[U][K - 1];
+            typename A::elem x[U][K];
+#pragma unroll
+            for (int q = 0; q < U; q++) {
+                u32 hi, base;
+                Q::locate(vt, g + q, hi, base);
+                ib[q] = PIN ? pad_idx(base) : base;
+                ob[q] = POUT ? pad_idx(base) : base;
+                load_twiddles<A, RR, S0>(w[q], tw, R, hi);
+            }
+#pragma unroll
+            for (int q = 0; q < U; q++) {
+#pragma unroll
+                for (int k = 0; k < K; k++) x[q][k] = ld(ib[q] + (PIN ? pad_idx((u32)k << BLO) : ((u32)k << BLO)));
+            }
+#pragma unroll
+            for (int q = 0; q < U; q++) {
+                radix_fwd<A, RR>(x[q], w[q], m);
+#pragma unroll
+                for (int k = 0; k < K; k++) st(ob[q] + (POUT ? pad_idx((u32)k << BLO) : ((u32)k << BLO)), x[q][k]);
+            }
+        }
     }
 }
 
@@ -283,59 +383,68 @@ TB_D void fwd_round(u32 vt, Ld ld, St st, const void *__restrict__ tw, u32 R, co
 // FINAL: layer 0 of the whole transform is in this round and carries the N^-1 scaling.
 template <class A, int LOGT, int NT, int S0, int RR, bool FINAL, bool PIN, bool POUT, class Ld, class St>
 TB_D void inv_round(u32 vt, Ld ld, St st, const void *__restrict__ tw, u32 R, const typename A::Mod &m) {
-    constexpr int K = 1 << RR, BLO = LOGT - S0 - RR, NV = (1 << LOGT) / K, G = NV / NT;
-    static_assert(BLO >= 0 && G >= 1 && NV % NT == 0, "bad round");
-#pragma unroll 1
-    for (int g = 0; g < G; g++) {
-        const u32 v = vt + g * NT;
-        const u32 lo = v & ((1u << BLO) - 1), hi = v >> BLO;
-        const u32 base = (hi << (BLO + RR)) | lo;
-        const u32 ib = PIN ? pad_idx(base) : base, ob = POUT ? pad_idx(base) : base;
+    typedef RoundGeom<LOGT, NT, S0, RR> Q;
+    constexpr int K = Q::K, BLO = Q::BLO, G = Q::G, U = Q::U;
+    constexpr bool LAST = FINAL && S0 == 0;
+    if constexpr (Q::SHARED) {
+        u32 hi, base0;
+        Q::locate(vt, 0, hi, base0);
         typename A::tw_t w[K - 1];
+        load_twiddles<A, RR, S0>(w, tw, R, hi);
+#pragma unroll 2
+        for (int g = 0; g < G; g++) {
+            const u32 base = base0 | ((u32)g << Q::TL);
+            const u32 ib = PIN ? pad_idx(base) : base, ob = POUT ? pad_idx(base) : base;
+            typename A::elem x[K];
 #pragma unroll
-        for (int u = 0; u < RR; u++) {
-            const u32 tbase = (R << (S0 + u)) + (hi << u);
-            if (!(FINAL && S0 == 0 && u == 0)) {
-#pragma unroll
-                for (int j = 0; j < (1 << u); j++) w[(1 << u) - 1 + j] = A::ld_tw(tw, tbase + j);
+            for (int k = 0; k < K; k++) {
+                x[k] = ld(ib + (PIN ? pad_idx((u32)k << BLO) : ((u32)k << BLO)));
+                if (A::kReduceEachInvRound) A::reduce(x[k], m);
             }
+            radix_inv<A, RR, LAST>(x, w, m);
+#pragma unroll
+            for (int k = 0; k < K; k++) st(ob + (POUT ? pad_idx((u32)k << BLO) : ((u32)k << BLO)), x[k]);
         }
-        typename A::elem x[K];
+    } else {
+#pragma unroll 1
+        for (int g = 0; g < G; g += U) {
+            u32 ib[U], ob[U];
+            typename A::tw_t w[U][K - 1];
+            typename A::elem x[U][K];
 #pragma unroll
-        for (int k = 0; k < K; k++) {
-            x[k] = ld(ib + (PIN ? pad_idx((u32)k << BLO) : ((u32)k << BLO)));
-            if (A::kReduceEachInvRound) A::reduce(x[k], m);
-        }
+            for (int q = 0; q < U; q++) {
+                u32 hi, base;
+                Q::locate(vt, g + q, hi, base);
+                ib[q] = PIN ? pad_idx(base) : base;
+                ob[q] = POUT ? pad_idx(base) : base;
+                load_twiddles<A, RR, S0>(w[q], tw, R, hi);
+            }
 #pragma unroll
-        for (int u = RR - 1; u >= 0; u--) {
-            const int half = 1 << (RR - 1 - u);
-            if (FINAL && S0 == 0 && u == 0) {
+            for (int q = 0; q < U; q++) {
 #pragma unroll
-                for (int r = 0; r < half; r++) A::gs_last(x[r], x[r + half], m);
-            } else {
-#pragma unroll
-                for (int j = 0; j < (1 << u); j++) {
-#pragma unroll
-                    for (int r = 0; r < half; r++) {
-                        const int k = (j << (RR - u)) | r;
-                        A::gs(x[k], x[k + half], w[(1 << u) - 1 + j], m);
-                    }
+                for (int k = 0; k < K; k++) {
+                    x[q][k] = ld(ib[q] + (PIN ? pad_idx((u32)k << BLO) : ((u32)k << BLO)));
+                    if (A::kReduceEachInvRound) A::reduce(x[q][k], m);
                 }
             }
-        }
 #pragma unroll
-        for (int k = 0; k < K; k++) st(ob + (POUT ? pad_idx((u32)k << BLO) : ((u32)k << BLO)), x[k]);
+            for (int q = 0; q < U; q++) {
+                radix_inv<A, RR, LAST>(x[q], w[q], m);
+#pragma unroll
+                for (int k = 0; k < K; k++) st(ob[q] + (POUT ? pad_idx((u32)k << BLO) : ((u32)k << BLO)), x[q][k]);
+            }
+        }
     }
 }
 
 // ---- tile plans ------------------------------------------------------------------------------------------------------------
-// Threads per CTA and layers per round for a tile of 2^LOGT coefficients. Radix-16 rounds keep one group plus its 15
-// twiddles in registers without spilling under the CTA's register cap; every listed round is bank-conflict free with
-// pad_idx (tools/banksim.py).
+// A tile is 2^LOGT coefficients owned by one CTA: 4096 (N = 4096) or 8192 (N = 8192, and N = 16384 / 32768 / 65536 as a
+// thread-block cluster of 2 / 4 / 8 CTAs, see kernels_ntt.cuh). Radix-8 / radix-4 rounds keep a group plus its twiddles
+// under 80 registers, so three 8192-tiles (or six 4096-tiles) are resident per SM and their load, butterfly and store
+// phases overlap. Every listed round is bank-conflict free with pad_idx and group_of_slot (tools/banksim.py).
 template <int LOGT> struct TilePlan;
-template <> struct TilePlan<12> { static constexpr int NT = 256, R0 = 4, R1 = 4, R2 = 4, R3 = 0; };
-template <> struct TilePlan<13> { static constexpr int NT = 256, R0 = 3, R1 = 3, R2 = 4, R3 = 3; };
-template <> struct TilePlan<14> { static constexpr int NT = 512, R0 = 3, R1 = 4, R2 = 4, R3 = 3; };
+template <> struct TilePlan<12> { static constexpr int NT = 128, CTAS = 6, R0 = 3, R1 = 3, R2 = 3, R3 = 3, R4 = 0; };
+template <> struct TilePlan<13> { static constexpr int NT = 256, CTAS = 3, R0 = 3, R1 = 3, R2 = 3, R3 = 2, R4 = 2; };
 template <int LOGT> __host__ __device__ constexpr int tile_threads() { return TilePlan<LOGT>::NT; }
 
 template <class A> struct SmLd { // index is already padded
@@ -348,10 +457,11 @@ template <class A> struct SmSt {
 };
 
 // Forward transform of a tile held by one CTA.
-//   ld(i)    : coefficient i of the tile as u64 (prologue fused here); RAW_IN: raw element bits of an earlier pass
+//   SMEM_IN  : the tile already sits in shared memory as raw element bits (a cluster's first stage put it there);
+//              otherwise ld(i) returns coefficient i of the tile as u64 (prologue fused there)
 //   st(i, v) : receives the canonical residue of output i (epilogue fused here; linear, coalesced order)
 // The last round's results pass through shared memory once more so that global stores are coalesced.
-template <class A, int LOGT, bool RAW_IN, class Ld, class St>
+template <class A, int LOGT, bool SMEM_IN, class Ld, class St>
 TB_D void tile_ntt_fwd(u64 *sm, Ld ld, St st, const ModDev *md, u32 R) {
     typedef TilePlan<LOGT> P;
     constexpr int NT = P::NT, T = 1 << LOGT;
@@ -359,12 +469,19 @@ TB_D void tile_ntt_fwd(u64 *sm, Ld ld, St st, const ModDev *md, u32 R) {
     const void *tw = A::fwd_table(md);
     SmLd<A> sl{sm};
     SmSt<A> ss{sm};
-    auto gl = [&](u32 i) -> typename A::elem { return RAW_IN ? A::from_bits(ld(i)) : A::from_u64(ld(i), m); };
-    TB_PHASE(NT, t, (fwd_round<A, LOGT, NT, 0, P::R0, false, true>(t, gl, ss, tw, R, m));)
+    if constexpr (SMEM_IN) {
+        TB_PHASE(NT, t, (fwd_round<A, LOGT, NT, 0, P::R0, true, true>(t, sl, ss, tw, R, m));)
+    } else {
+        auto gl = [&](u32 i) -> typename A::elem { return A::from_u64(ld(i), m); };
+        TB_PHASE(NT, t, (fwd_round<A, LOGT, NT, 0, P::R0, false, true>(t, gl, ss, tw, R, m));)
+    }
     TB_PHASE(NT, t, (fwd_round<A, LOGT, NT, P::R0, P::R1, true, true>(t, sl, ss, tw, R, m));)
     TB_PHASE(NT, t, (fwd_round<A, LOGT, NT, P::R0 + P::R1, P::R2, true, true>(t, sl, ss, tw, R, m));)
     if constexpr (P::R3 > 0) {
         TB_PHASE(NT, t, (fwd_round<A, LOGT, NT, P::R0 + P::R1 + P::R2, P::R3, true, true>(t, sl, ss, tw, R, m));)
+    }
+    if constexpr (P::R4 > 0) {
+        TB_PHASE(NT, t, (fwd_round<A, LOGT, NT, P::R0 + P::R1 + P::R2 + P::R3, P::R4, true, true>(t, sl, ss, tw, R, m));)
     }
     TB_PHASE(NT, t, {
         _Pragma("unroll 4") for (int k = 0; k < T / NT; k++) {
@@ -374,8 +491,9 @@ TB_D void tile_ntt_fwd(u64 *sm, Ld ld, St st, const ModDev *md, u32 R) {
     })
 }
 
-// Inverse transform of a tile. ld(i): canonical residues as u64. FINAL (the tile contains layer 0, N^-1 folded in):
-// st(i, v) receives canonical residues; otherwise (four-step row pass) st(i, bits) receives raw element bits.
+// Inverse transform of a tile. ld(i): canonical residues as u64.
+//   FINAL    : the tile contains layer 0 (N^-1 folded in) and st(i, v) receives canonical residues; otherwise the raw
+//              element bits stay in shared memory for the cluster's last stage and st is not called.
 template <class A, int LOGT, bool FINAL, class Ld, class St>
 TB_D void tile_ntt_inv(u64 *sm, Ld ld, St st, const ModDev *md, u32 R) {
     typedef TilePlan<LOGT> P;
@@ -384,22 +502,85 @@ TB_D void tile_ntt_inv(u64 *sm, Ld ld, St st, const ModDev *md, u32 R) {
     const void *tw = A::inv_table(md);
     SmLd<A> sl{sm};
     SmSt<A> ss{sm};
-    auto gs_ = [&](u32 i, typename A::elem x) {
-        if (FINAL) st(i, A::canon(x, m));
-        else st(i, A::to_bits(x));
-    };
     TB_PHASE(NT, t, {
-        _Pragma("unroll 4") for (int k = 0; k < T / NT; k++) {
+        _Pragma("unroll 8") for (int k = 0; k < T / NT; k++) {
             u32 i = t + k * NT;
             sm[pad_idx(i)] = A::to_bits(A::from_u64(ld(i), m));
         }
     })
+    if constexpr (P::R4 > 0) {
+        TB_PHASE(NT, t, (inv_round<A, LOGT, NT, P::R0 + P::R1 + P::R2 + P::R3, P::R4, false, true, true>(t, sl, ss, tw, R, m));)
+    }
     if constexpr (P::R3 > 0) {
         TB_PHASE(NT, t, (inv_round<A, LOGT, NT, P::R0 + P::R1 + P::R2, P::R3, false, true, true>(t, sl, ss, tw, R, m));)
     }
     TB_PHASE(NT, t, (inv_round<A, LOGT, NT, P::R0 + P::R1, P::R2, false, true, true>(t, sl, ss, tw, R, m));)
     TB_PHASE(NT, t, (inv_round<A, LOGT, NT, P::R0, P::R1, false, true, true>(t, sl, ss, tw, R, m));)
-    TB_PHASE(NT, t, (inv_round<A, LOGT, NT, 0, P::R0, FINAL, true, false>(t, sl, gs_, tw, R, m));)
+    if constexpr (FINAL) {
+        auto gs_ = [&](u32 i, typename A::elem x) { st(i, A::canon(x, m)); };
+        TB_PHASE(NT, t, (inv_round<A, LOGT, NT, 0, P::R0, true, true, false>(t, sl, gs_, tw, R, m));)
+    } else {
+        TB_PHASE(NT, t, (inv_round<A, LOGT, NT, 0, P::R0, false, true, true>(t, sl, ss, tw, R, m));)
+    }
+}
+
+// ---- cluster stages (N = 2^LOGC tiles) -----------------------------------------------------------------------------------------
+// The first LOGC layers of the forward transform couple coefficients one tile apart. CTA `rank` of the cluster loads the
+// 2^LOGC coefficients {v + k T} for its share of v, runs the radix-2^LOGC network in registers and hands output k to
+// tile k (a store into that CTA's shared memory through the cluster's distributed shared memory). After the cluster
+// barrier every CTA owns an independent 2^LOGT-point transform with root base 2^LOGC + rank.
+//   ld(i)            : coefficient i of the limb as u64 (prologue fused there)
+//   st_peer(k, i, b) : store raw element bits b at padded index i of tile k
+template <class A, int LOGC, int LOGT, int NT, class Ld, class StPeer>
+TB_D void cluster_fwd_stage(u32 vt, u32 rank, Ld ld, StPeer st_peer, const ModDev *md) {
+    constexpr int C = 1 << LOGC, T = 1 << LOGT, G = T / C / NT;
+    static_assert(G >= 1, "bad cluster stage");
+    const typename A::Mod m = A::make(md);
+    const void *tw = A::fwd_table(md);
+    typename A::tw_t w[C - 1];
+#pragma unroll
+    for (int k = 1; k < C; k++) w[k - 1] = A::ld_tw(tw, k); // layer u, block j: table entry 2^u + j
+#pragma unroll(8 / C)
+    for (int g = 0; g < G; g++) {
+        const u32 v = rank * (T / C) + vt + g * NT;
+        typename A::elem x[C];
+#pragma unroll
+        for (int k = 0; k < C; k++) x[k] = A::from_u64(ld(v + (u32)k * T), m);
+        radix_fwd<A, LOGC>(x, w, m);
+        const u32 pv = pad_idx(v);
+#pragma unroll
+        for (int k = 0; k < C; k++) st_peer((u32)k, pv, A::to_bits(x[k]));
+    }
+}
+
+// Mirror image for the inverse: after every tile has run its 2^LOGT-point inverse (raw bits left in shared memory) and
+// the cluster barrier, CTA `rank` gathers {tile k, position v} for its share of v, runs the last LOGC layers (layer 0
+// carries N^-1) and stores the canonical results.
+//   ld_peer(k, i) : raw element bits at padded index i of tile k
+//   st(i, v)      : canonical residue of coefficient i of the limb (epilogue fused there)
+template <class A, int LOGC, int LOGT, int NT, class LdPeer, class St>
+TB_D void cluster_inv_stage(u32 vt, u32 rank, LdPeer ld_peer, St st, const ModDev *md) {
+    constexpr int C = 1 << LOGC, T = 1 << LOGT, G = T / C / NT;
+    static_assert(G >= 1, "bad cluster stage");
+    const typename A::Mod m = A::make(md);
+    const void *tw = A::inv_table(md);
+    typename A::tw_t w[C - 1];
+#pragma unroll
+    for (int k = 2; k < C; k++) w[k - 1] = A::ld_tw(tw, k); // entry 1 (layer 0) is folded into gs_last
+#pragma unroll(8 / C)
+    for (int g = 0; g < G; g++) {
+        const u32 v = rank * (T / C) + vt + g * NT;
+        const u32 pv = pad_idx(v);
+        typename A::elem x[C];
+#pragma unroll
+        for (int k = 0; k < C; k++) {
+            x[k] = A::from_bits(ld_peer((u32)k, pv));
+            if (A::kReduceEachInvRound) A::reduce(x[k], m);
+        }
+        radix_inv<A, LOGC, true>(x, w, m);
+#pragma unroll
+        for (int k = 0; k < C; k++) st(v + (u32)k * T, A::canon(x[k], m));
+    }
 }
 
 } // namespace troyb
