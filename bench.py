@@ -258,6 +258,9 @@ def run_ours(args):
         ev.rescale_to_next(a_ct)
 
     extra_steps = max(2, min(args.steps, 5))
+    for fn in (rot, resc):  # warm-up: first calls grow the stream-ordered scratch pool
+        for _ in range(3):
+            fn()
     t_rot = timed(rot, extra_steps)
     t_resc = timed(resc, extra_steps)
     ntt_polys = 512  # 512 polys x 8 limbs x 128 KiB = 512 MiB > L2
@@ -269,8 +272,9 @@ def run_ours(args):
     def ntt_i():
         lib.call("troyb_ntt_inverse", C.c_void_p(ctx.h), 0, C.c_void_p(ntt_buf.data_ptr()), ntt_polys, C.c_void_p(stream))
 
-    ntt_f()
-    ntt_i()
+    for _ in range(3):
+        ntt_f()
+        ntt_i()
     t_nf = timed(ntt_f, extra_steps)
     t_ni = timed(ntt_i, extra_steps)
     limbs = ntt_polys * L
@@ -288,7 +292,8 @@ def run_ours(args):
     dom = max(kernels, key=lambda k: k["ms"])
     # algorithmic bytes of one launch of the dominant kernel: every NTT-family CTA (unit) reads and writes one limb
     if dom["kernel"].startswith("ntt_"):
-        dom_bytes = dom["grid"] / dom["launches"] * bytes_["limb_ntt"]
+        tiles_per_limb = max(1, N // 8192)  # a limb is a cluster of 8192-coefficient tiles, one CTA each
+        dom_bytes = dom["grid"] / tiles_per_limb / dom["launches"] * bytes_["limb_ntt"]
     elif dom["kernel"] == "ks_inner_product":
         dom_bytes = B * (L + 1) * N * 8 * (L + 2 * L + 2) / dom["launches"]
     else:

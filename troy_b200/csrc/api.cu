@@ -87,16 +87,22 @@ u32 grid_for(u64 total, int threads) { return (u32)((total + threads - 1) / thre
 // ---- NTT dispatch --------------------------------------------------------------------------------------------------
 size_t tile_smem(int logt) { return (size_t)padded_words(1u << logt) * sizeof(u64); }
 
-// Launch order of the limbs of a launch: most expensive butterfly policy first, so that the slow CTAs do not end up
-// alone in the last wave (the CTA scheduler dispatches in blockIdx order).
-void set_order(const Context *ctx, NttArgs &a, u32 n_limbs_in_map, u32 n_outer) {
-    std::vector<int> idx(n_limbs_in_map);
-    for (u32 i = 0; i < n_limbs_in_map; i++) idx[i] = (int)i;
-    std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) {
-        return ctx->h_mods[a.map.idx[x]].policy > ctx->h_mods[a.map.idx[y]].policy;
-    });
-    for (u32 i = 0; i < n_limbs_in_map; i++) a.order[i] = (uint8_t)idx[i];
-    a.n_outer = n_outer;
+// Launch order of the limbs of a launch. Consecutive CTAs cycle through the limbs; limbs whose butterflies run on the
+// integer pipe (60-bit primes) are spread evenly between those on the FP64 pipe (primes below 2^46), so that the CTAs
+// resident on one SM at any time keep both pipes busy.
+void set_order(const Context *ctx, NttArgs &a, u32 n_limbs_in_map) {
+    std::vector<int> heavy, light;
+    for (u32 i = 0; i < n_limbs_in_map; i++) {
+        const int pol = ctx->h_mods[a.map.idx[i]].policy;
+        (pol == POLICY_U64_FAST || pol == POLICY_U64_EXACT ? heavy : light).push_back((int)i);
+    }
+    size_t ih = 0, il = 0;
+    for (u32 r = 0; r < n_limbs_in_map; r++) {
+        // Bresenham merge: heavy limb whenever its share of the ranks so far falls behind
+        const bool take_heavy = il >= light.size() || (ih < heavy.size() && ih * n_limbs_in_map <= r * heavy.size());
+        a.order[r] = (uint8_t)(take_heavy ? heavy[ih++] : light[il++]);
+    }
+    a.n_rank = n_limbs_in_map;
 }
 
 // Tiles per limb and the tile size used for a transform of 2^logN coefficients (see ntt.cuh TilePlan).
@@ -147,7 +153,7 @@ void ntt_plain(const Context *ctx, bool inverse, const LimbMap &map, u32 L, cons
     a.dst_batch_stride = dst_stride;
     a.canon = canon ? 1 : 0;
     a.scheme = ctx->scheme;
-    set_order(ctx, a, L, batch * (limbs_per_elem / L));
+    set_order(ctx, a, L);
     if (inverse) run_inv(ctx, a, batch * limbs_per_elem, s);
     else run_fwd(ctx, a, batch * limbs_per_elem, s);
 }
@@ -167,20 +173,15 @@ void switch_key_impl(Context *ctx, int level, u64 *ct, u64 ct_stride, const u64 
     LimbMap kmap = ctx->map_prefix(L);
     kmap.idx[L] = (uint8_t)ctx->pool_special;
 
-    // Only the mod-up output D ([L+1][L] limbs per ciphertext) is large; it is produced and consumed chunk by chunk so
-    // that it stays inside the 126 MB L2, with the chunk sized to fill whole waves of CTAs on the 148 SMs. Everything
-    // else runs once over the whole batch.
+    // Only the mod-up output D ([L+1][L] limbs per ciphertext) is large. It is produced and consumed in chunks of at
+    // most 4 GiB (TROYB_KS_CHUNK_MB overrides): measured on B200, few large launches beat L2-sized chunks (the kernels are
+    // bound by the FP64 / integer pipes, not by the HBM round trip of D, and small launches lose to partial waves).
     const u64 per_ct_words = (u64)Lp * L * N;
-    const u32 wave = 148u * (ctx->logN >= 13 ? 3u : 6u); // CTAs resident per wave (ntt.cuh TilePlan)
-    const u32 ctas_per_ct = Lp * L * tiles_per_limb(ctx->logN);
-    const u32 max_chunk = (u32)std::max<u64>(1, (64ull << 20) / (per_ct_words * 8));
-    u32 chunk = 1;
-    double best = 0;
-    for (u32 c = 1; c <= std::min(max_chunk, batch); c++) {
-        u64 ctas = (u64)c * ctas_per_ct;
-        double util = (double)ctas / (double)(((ctas + wave - 1) / wave) * wave);
-        if (util >= best - 1e-9) { best = util; chunk = c; }
-    }
+    const char *chunk_env = getenv("TROYB_KS_CHUNK_MB");
+    const u64 chunk_bytes = (chunk_env ? (u64)atoi(chunk_env) : 4096ull) << 20;
+    const u32 max_chunk = (u32)std::max<u64>(1, chunk_bytes / (per_ct_words * 8));
+    const u32 n_chunks = (batch + max_chunk - 1) / max_chunk;
+    const u32 chunk = (batch + n_chunks - 1) / n_chunks; // equal chunks
 
     Scratch t_target(ckks ? (size_t)batch * L * N : 0, s);
     Scratch D((size_t)chunk * per_ct_words, s);
@@ -202,7 +203,7 @@ void switch_key_impl(Context *ctx, int level, u64 *ct, u64 ct_stride, const u64 
             a.aux0_batch_stride = target_stride;
             a.dst = D.p;
             a.scheme = ctx->scheme;
-            set_order(ctx, a, Lp, nb);
+            set_order(ctx, a, Lp);
             run_fwd(ctx, a, nb * Lp * L, s);
         }
         {
@@ -217,6 +218,8 @@ void switch_key_impl(Context *ctx, int level, u64 *ct, u64 ct_stride, const u64 
             k.D = D.p;
             k.key = key;
             k.prod = prod.p + (u64)b0 * 2 * Lp * N;
+            k.pass = ckks ? tgt : nullptr;
+            k.pass_stride = target_stride;
             ck(launch_cta(k, grid_for(k.total, KsInnerProduct::kThreads), 0, s));
         }
     }
@@ -251,7 +254,7 @@ void switch_key_impl(Context *ctx, int level, u64 *ct, u64 ct_stride, const u64 
         a.ct_poly_stride = (u64)L * N;
         a.drop = ctx->key_drop;
         a.scheme = ctx->scheme;
-        set_order(ctx, a, L, batch * 2);
+        set_order(ctx, a, L);
         if (ckks) run_fwd(ctx, a, batch * 2 * L, s);
         else run_inv(ctx, a, batch * 2 * L, s);
     }
@@ -259,6 +262,12 @@ void switch_key_impl(Context *ctx, int level, u64 *ct, u64 ct_stride, const u64 
 
 void check_batch_stride(size_t stride, size_t min_words, const char *what) {
     if (stride < min_words) throw std::invalid_argument(std::string(what) + " stride is smaller than one ciphertext");
+    if (stride & 1) throw std::invalid_argument(std::string(what) + " stride must be even (128-bit accesses)");
+}
+
+// The kernels use 128-bit accesses: every buffer must be 16-byte aligned (anything from cudaMalloc / troyb_malloc is).
+void check_aligned(const void *p, const char *what) {
+    if (reinterpret_cast<uintptr_t>(p) & 15) throw std::invalid_argument(std::string(what) + " must be 16-byte aligned");
 }
 
 } // namespace
@@ -463,6 +472,7 @@ int troyb_ntt_forward(troyb_context *ctx, int level, uint64_t *d_data, size_t n_
     need_init();
     Context *c = C(ctx);
     u32 L = (u32)level_limbs(c, level);
+    check_aligned(d_data, "data");
     ntt_plain(c, false, c->map_prefix(L), L, d_data, (u64)L * c->N, d_data, (u64)L * c->N, L, (u32)n_polys, true, S(stream));
     API_END
 }
@@ -471,6 +481,7 @@ int troyb_ntt_inverse(troyb_context *ctx, int level, uint64_t *d_data, size_t n_
     need_init();
     Context *c = C(ctx);
     u32 L = (u32)level_limbs(c, level);
+    check_aligned(d_data, "data");
     ntt_plain(c, true, c->map_prefix(L), L, d_data, (u64)L * c->N, d_data, (u64)L * c->N, L, (u32)n_polys, true, S(stream));
     API_END
 }
@@ -480,6 +491,7 @@ int troyb_ntt_forward_key(troyb_context *ctx, uint64_t *d_data, size_t n_polys, 
     Context *c = C(ctx);
     u32 L = (u32)level_limbs(c, -1);
     LimbMap m = c->has_special ? c->map_prefix_special(c->Ltop) : c->map_prefix(c->Ltop);
+    check_aligned(d_data, "data");
     ntt_plain(c, false, m, L, d_data, (u64)L * c->N, d_data, (u64)L * c->N, L, (u32)n_polys, true, S(stream));
     API_END
 }
@@ -489,6 +501,7 @@ int troyb_ntt_inverse_key(troyb_context *ctx, uint64_t *d_data, size_t n_polys, 
     Context *c = C(ctx);
     u32 L = (u32)level_limbs(c, -1);
     LimbMap m = c->has_special ? c->map_prefix_special(c->Ltop) : c->map_prefix(c->Ltop);
+    check_aligned(d_data, "data");
     ntt_plain(c, true, m, L, d_data, (u64)L * c->N, d_data, (u64)L * c->N, L, (u32)n_polys, true, S(stream));
     API_END
 }
@@ -535,6 +548,9 @@ int troyb_multiply(troyb_context *ctx, int level, const uint64_t *d_a, size_t a_
     check_batch_stride(a_stride, a_size * L * N, "a");
     check_batch_stride(b_stride, b_size * L * N, "b");
     check_batch_stride(out_stride, out_size * L * N, "out");
+    check_aligned(d_a, "a");
+    check_aligned(d_b, "b");
+    check_aligned(d_out, "out");
 
     auto tensor = [&](const LimbMap &map, u32 limbs, const u64 *a, u64 as, const u64 *b, u64 bs, u64 *o, u64 os) {
         EltTensor k{};
@@ -619,6 +635,9 @@ int troyb_switch_key(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_st
     if (!d_ct || !d_target || !d_key) throw std::invalid_argument("target_iter");
     check_batch_stride(ct_stride, 2ull * L * c->N, "ct");
     check_batch_stride(target_stride, (u64)L * c->N, "target");
+    check_aligned(d_ct, "ct");
+    check_aligned(d_target, "target");
+    check_aligned(d_key, "key");
     switch_key_impl(c, level, d_ct, ct_stride, d_target, target_stride, d_key, (u32)batch, S(stream));
     API_END
 }
@@ -632,6 +651,8 @@ int troyb_relinearize(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_s
     if (level < 0) throw std::invalid_argument("level");
     if (!d_ct || !d_relin_key) throw std::invalid_argument("null argument");
     check_batch_stride(ct_stride, 3ull * L * c->N, "ct");
+    check_aligned(d_ct, "ct");
+    check_aligned(d_relin_key, "key");
     switch_key_impl(c, level, d_ct, ct_stride, d_ct + 2ull * L * c->N, ct_stride, d_relin_key, (u32)batch, S(stream));
     API_END
 }
@@ -692,6 +713,8 @@ int troyb_apply_galois(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_
     if (!(galois_elt & 1) || galois_elt >= 2 * N) throw std::invalid_argument("Galois element is not valid");
     if (!d_ct || !d_key) throw std::invalid_argument("Galois key not present");
     check_batch_stride(ct_stride, 2ull * L * N, "ct");
+    check_aligned(d_ct, "ct");
+    check_aligned(d_key, "key");
     Scratch tmp((size_t)batch * 2 * L * N, s);
     EltGalois k{};
     k.logN = c->logN;
@@ -726,6 +749,8 @@ int troyb_mod_switch_scale_to_next(troyb_context *ctx, int level, const uint64_t
     if (d_in == d_out) throw std::invalid_argument("in-place call must go through a temporary (as the reference does)");
     check_batch_stride(in_stride, size * L * N, "in");
     check_batch_stride(out_stride, size * (L - 1) * N, "out");
+    check_aligned(d_in, "in");
+    check_aligned(d_out, "out");
     const LevelData &lv = c->levels[level];
     if (c->scheme == SCHEME_CKKS) {
         // divideAndRoundqLastNttInplace  src/utils/rns_cuda.cu:348-363
@@ -759,7 +784,7 @@ int troyb_mod_switch_scale_to_next(troyb_context *ctx, int level, const uint64_t
         f.dst_poly_stride = (u64)(L - 1) * N;
         f.drop = lv.drop;
         f.scheme = c->scheme;
-        set_order(c, f, L - 1, (u32)(batch * size));
+        set_order(c, f, L - 1);
         run_fwd(c, f, (u32)(batch * size * (L - 1)), s);
     } else {
         EltDropLast k{};

@@ -311,7 +311,7 @@ Context *context_create(int device, int scheme, u64 N, const u64 *moduli, int n_
             }
             md.fwd_d = upload(ctx->owned, fd);
             md.inv_d = upload(ctx->owned, id);
-            md.policy = POLICY_F64;
+            md.policy = (p >> 41) ? POLICY_F64 : POLICY_F64_SMALL;
         }
     }
     ctx->d_mods = upload(ctx->owned, ctx->h_mods);

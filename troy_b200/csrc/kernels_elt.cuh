@@ -122,6 +122,8 @@ struct KsInnerProduct {
     const u64 *D;
     const u64 *key;
     u64 *prod;
+    const u64 *pass;      // CKKS: the NTT-form target [batch][L][N]; its limb i IS digit i under modulus i (no transform)
+    u64 pass_stride;
     TB_D void operator()(u32 bid, u64 *) const {
         TB_PHASE(kThreads, t, {
             u64 idx = (u64)bid * kThreads + t;
@@ -137,14 +139,26 @@ struct KsInnerProduct {
                 const u64 *kp = key + (u64)key_limb * N + c;
                 const u64 key_digit_stride = 2ull * key_limbs * N, key_comp_stride = (u64)key_limbs * N;
                 u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0, lo2 = 0, hi2 = 0, lo3 = 0, hi3 = 0;
-                for (u32 j = 0; j < L; j++) {
-                    const ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(d + (u64)j * N);
-                    const ulonglong2 k0 = __ldg(reinterpret_cast<const ulonglong2 *>(kp + j * key_digit_stride));
-                    const ulonglong2 k1 = __ldg(reinterpret_cast<const ulonglong2 *>(kp + j * key_digit_stride + key_comp_stride));
-                    mac128(lo0, hi0, x.x, k0.x);
-                    mac128(lo1, hi1, x.y, k0.y);
-                    mac128(lo2, hi2, x.x, k1.x);
-                    mac128(lo3, hi3, x.y, k1.y);
+                const u64 *ps = (pass != nullptr && i < L) ? pass + b * pass_stride + (u64)i * N + c : nullptr;
+                for (u32 j0 = 0; j0 < L; j0 += 4) { // four digits' loads in flight
+                    ulonglong2 x[4], k0[4], k1[4];
+                    _Pragma("unroll") for (u32 q = 0; q < 4; q++) {
+                        const u32 j = j0 + q;
+                        if (j < L) {
+                            const u64 *src = (ps != nullptr && j == i) ? ps : d + (u64)j * N;
+                            x[q] = *reinterpret_cast<const ulonglong2 *>(src);
+                            k0[q] = __ldg(reinterpret_cast<const ulonglong2 *>(kp + j * key_digit_stride));
+                            k1[q] = __ldg(reinterpret_cast<const ulonglong2 *>(kp + j * key_digit_stride + key_comp_stride));
+                        }
+                    }
+                    _Pragma("unroll") for (u32 q = 0; q < 4; q++) {
+                        if (j0 + q < L) {
+                            mac128(lo0, hi0, x[q].x, k0[q].x);
+                            mac128(lo1, hi1, x[q].y, k0[q].y);
+                            mac128(lo2, hi2, x[q].x, k1[q].x);
+                            mac128(lo3, hi3, x[q].y, k1[q].y);
+                        }
+                    }
                 }
                 u64 *po = prod + (b * 2 * (L + 1) + i) * N + c;
                 ulonglong2 r0, r1;

@@ -50,8 +50,8 @@ struct NttArgs {
     u64 dst_batch_stride;
     int scheme;
     int add_half;       // INV_ADD_HALF: add half (BFV/CKKS) or plain canonical INTT (BGV)
-    uint8_t order[kMaxLimbs]; // launch rank -> limb index, most expensive butterfly policy first (evens out the waves)
-    u32 n_outer;        // units per limb rank (batch x polys, or batch for MODUP)
+    uint8_t order[kMaxLimbs]; // launch rank -> limb index: integer-pipe and FP64-pipe limbs interleaved (see set_order)
+    u32 n_rank;         // limb ranks in the launch; consecutive units cycle through them
 };
 
 TB_D u64 canon4(u64 v, u64 p) {
@@ -147,9 +147,9 @@ template <int LOGT> TB_D NttUnit resolve_unit(const NttArgs &a, u32 bid) {
     switch (a.mode) {
     case FWD_PLAIN:
     case INV_PLAIN: {
-        // storage: unit = b * n_limbs + l, l = poly * L + limb (n_limbs = polys x L); launch order: limb rank slowest
+        // storage: unit = b * n_limbs + l, l = poly * L + limb (n_limbs = polys x L); launch order: limb rank fastest
         const u32 polys = a.n_limbs / a.L;
-        const u32 limb = a.order[unit / a.n_outer], bp = unit % a.n_outer;
+        const u32 limb = a.order[unit % a.n_rank], bp = unit / a.n_rank;
         const u32 l = (bp % polys) * a.L + limb, b = bp / polys;
         u.unit = b * a.n_limbs + l;
         u.md = a.mods + a.map.idx[l % a.L];
@@ -158,8 +158,9 @@ template <int LOGT> TB_D NttUnit resolve_unit(const NttArgs &a, u32 bid) {
         break;
     }
     case FWD_MODUP: {
-        // storage: unit = (b * (L+1) + i) * L + j; launch order: (rank of i, b, j)
-        const u32 j = unit % a.L, ib = unit / a.L, b = ib % a.n_outer, i = a.order[ib / a.n_outer];
+        // storage: unit = (b * (L+1) + i) * L + j; launch order: (b, j, rank of i): the L+1 transforms of one digit are
+        // neighbours, so the digit is read from HBM once
+        const u32 i = a.order[unit % a.n_rank], bj = unit / a.n_rank, j = bj % a.L, b = bj / a.L;
         u.unit = (b * (a.L + 1) + i) * a.L + j;
         u.md = a.mods + a.map.idx[i];
         u.src = a.src + (u64)b * a.src_unit_stride + (u64)j * N;
@@ -179,8 +180,8 @@ template <int LOGT> TB_D NttUnit resolve_unit(const NttArgs &a, u32 bid) {
     }
     case FWD_MODDOWN:
     case INV_COMBINE: {
-        // storage: unit = (b * K + k) * L + j; launch order: (rank of j, b * K + k)
-        const u32 j = a.order[unit / a.n_outer], bk = unit % a.n_outer, k = bk % a.K, b = bk / a.K;
+        // storage: unit = (b * K + k) * L + j; launch order: (b * K + k, rank of j)
+        const u32 j = a.order[unit % a.n_rank], bk = unit / a.n_rank, k = bk % a.K, b = bk / a.K;
         u.unit = bk * a.L + j;
         u.md = a.mods + a.map.idx[j];
         u.sp = a.aux1 + (u64)bk * N;
@@ -195,21 +196,18 @@ template <int LOGT> TB_D NttUnit resolve_unit(const NttArgs &a, u32 bid) {
     return u;
 }
 
-// Runs `body` with the butterfly policy of this modulus (warp-uniform branch).
-#define TB_WITH_POLICY(md, ...)                                                     \
-    switch ((md)->policy) {                                                         \
-    case POLICY_F64: { typedef ArithF64 A; __VA_ARGS__ } break;                     \
-    case POLICY_U64_FAST: { typedef ArithU64Fast A; __VA_ARGS__ } break;            \
-    default: { typedef ArithU64Exact A; __VA_ARGS__ } break;                        \
+#define TB_WITH_LOGC(logc, ...)                                  \
+    switch (logc) {                                              \
+    case 1: { constexpr int LOGC = 1; __VA_ARGS__ } break;       \
+    case 2: { constexpr int LOGC = 2; __VA_ARGS__ } break;       \
+    default: { constexpr int LOGC = 3; __VA_ARGS__ } break;      \
     }
 
-// Prologue of a forward transform: coefficient i of the limb as the transform's input.
-struct FwdLoad {
-    const u64 *in;
+// Prologue of a forward transform applied to the raw coefficient x.
+struct FwdPrologue {
     u64 p, ratio1, fix;
     int mode;
-    TB_D u64 operator()(u32 i) const {
-        u64 x = in[i];
+    TB_D u64 operator()(u64 x) const {
         if (mode == FWD_MODUP) x = barrett64(x, p, ratio1);
         else if (mode == FWD_MODDOWN) x = barrett64(x, p, ratio1) + fix;
         return x;
@@ -221,9 +219,10 @@ struct FwdStore {
     NttUnit u;
     u64 p;
     int mode;
+    TB_D u64 finish(u64 acc, u64 v) const { return shoup(submod(acc, v, p), u.dl.inv_last, u.dl.inv_last_shoup, p); }
     TB_D void operator()(u32 i, u64 v) const {
         if (mode == FWD_MODDOWN) {
-            u64 r = shoup(submod(u.acc[i], v, p), u.dl.inv_last, u.dl.inv_last_shoup, p);
+            u64 r = finish(u.acc[i], v);
             if (u.ct) u.ct[i] = addmod(u.ct[i], r, p);
             else u.dst[i] = r;
         } else {
@@ -270,11 +269,9 @@ struct NttFwdSmall {
         const NttUnit u = resolve_unit<0>(a, bid);
         const ModDev *md = u.md;
         const u32 n = 1u << a.logN;
-        if (u.passthrough) {
-            TB_PHASE(kThreads, t, for (u32 i = t; i < n; i += kThreads) u.dst[i] = u.src[i];)
-            return;
-        }
-        const FwdLoad ld{u.src, md->p, md->ratio1, a.mode == FWD_MODDOWN ? md->p - u.dl.half_mod : 0, a.mode};
+        if (u.passthrough) return; // digit already in NTT form under this modulus: the inner product reads it in place
+        const FwdPrologue pro{md->p, md->ratio1, a.mode == FWD_MODDOWN ? md->p - u.dl.half_mod : 0, a.mode};
+        auto ld = [&](u32 i) -> u64 { return pro(u.src[i]); };
         const FwdStore st{u, md->p, a.mode};
         small_ntt_fwd(sm, (u32)a.logN, ld, st, md->fwd, md->p);
     }
@@ -295,53 +292,55 @@ struct NttInvSmall {
 };
 
 // ---- tile / cluster transforms (N >= 4096) ---------------------------------------------------------------------------
-// One CTA per tile of 2^LOGT coefficients; a limb of N = 2^LOGC tiles is one thread-block cluster (launch_cluster).
-// Forward: stage_a = the LOGC layers that couple the tiles (results scattered into the peers' shared memory),
-//          stage_b = the tile's own 2^LOGT-point transform, canonical store with the fused epilogue.
-// Inverse: stage_a = the tile's own inverse transform, stage_b = the last LOGC layers gathered from the peers.
-#define TB_WITH_LOGC(logc, ...)                                  \
-    switch (logc) {                                              \
-    case 1: { constexpr int LOGC = 1; __VA_ARGS__ } break;       \
-    case 2: { constexpr int LOGC = 2; __VA_ARGS__ } break;       \
-    default: { constexpr int LOGC = 3; __VA_ARGS__ } break;      \
+// One CTA per tile of 2^LOGT coefficients; a limb of N = C tiles is one thread-block cluster (launch_cluster). See
+// ntt.cuh "cluster stages" for how the layers are split between the tiles' own transforms and the exchange stages.
+// Runs `body` with the butterfly policy `pol` (warp-uniform branch).
+#define TB_WITH_POLICY(pol, ...)                                                    \
+    switch (pol) {                                                         \
+    case POLICY_F64: { typedef ArithF64 A; __VA_ARGS__ } break;                     \
+    case POLICY_F64_SMALL: { typedef ArithF64S A; __VA_ARGS__ } break;              \
+    case POLICY_U64_FAST: { typedef ArithU64Fast A; __VA_ARGS__ } break;            \
+    default: { typedef ArithU64Exact A; __VA_ARGS__ } break;                        \
     }
 
 template <int LOGT> struct NttFwdTile {
     static constexpr int kThreads = TilePlan<LOGT>::NT;
     static constexpr int kMinCtas = TilePlan<LOGT>::CTAS;
-    static constexpr bool kTrailingBarrier = false; // peers only write into this CTA's tile, and only before the barrier
+    static constexpr int kStages = 2;
+    static constexpr bool kTrailingBarrier = false; // peers only write into this CTA's tile, and only in stage 0
+    static constexpr u32 T = 1u << LOGT;
     NttArgs a;
     const char *name() const { return ntt_kernel_name(a.mode); }
 
-    TB_D void stage_a(u32 bid, u32 rank, u32 nranks, u64 *, const Peers &peers) const {
-        if (nranks == 1) return;
-        const NttUnit u = resolve_unit<LOGT>(a, bid);
-        if (u.passthrough) return;
-        const ModDev *md = u.md;
-        const FwdLoad ld{u.src, md->p, md->ratio1, a.mode == FWD_MODDOWN ? md->p - u.dl.half_mod : 0, a.mode};
-        auto st_peer = [&](u32 k, u32 pi, u64 bits) { peers.st(k, pi, bits); };
-        TB_WITH_POLICY(md, TB_WITH_LOGC(u.rows_log, TB_PHASE(kThreads, t, (cluster_fwd_stage<A, LOGC, LOGT, kThreads>(t, rank, ld, st_peer, md));)))
-    }
-
-    TB_D void stage_b(u32 bid, u32 rank, u32 nranks, u64 *sm, const Peers &) const {
+    template <int S> TB_D void stage(u32 bid, u32 rank, u32 nranks, u64 *sm, const Peers &peers) const {
         NttUnit u = resolve_unit<LOGT>(a, bid);
         const ModDev *md = u.md;
-        const u64 off = (u64)rank << LOGT;
-        if (u.passthrough) {
-            TB_PHASE(kThreads, t, for (u32 i = t; i < (1u << LOGT); i += kThreads) u.dst[off + i] = u.src[off + i];)
-            return;
-        }
-        const u32 R = nranks + rank;
-        // this tile's outputs are coefficients [off, off + T) of the limb's (bit-reversed) output
-        if (u.dst) u.dst += off;
-        if (u.ct) u.ct += off;
-        if (u.acc) u.acc += off;
-        const FwdStore st{u, md->p, a.mode};
-        if (nranks == 1) {
-            const FwdLoad ld{u.src, md->p, md->ratio1, a.mode == FWD_MODDOWN ? md->p - u.dl.half_mod : 0, a.mode};
-            TB_WITH_POLICY(md, (tile_ntt_fwd<A, LOGT, false>(sm, ld, st, md, R));)
+        const int pol = md->policy;
+        const FwdPrologue pro{md->p, md->ratio1, a.mode == FWD_MODDOWN ? md->p - u.dl.half_mod : 0, a.mode};
+        if constexpr (S == 0) {
+            // scatter stage: the layers that couple the tiles, results into the peers' shared memory
+            if (nranks == 1 || u.passthrough) return;
+            auto ld = [&](u32 i) -> u64 { return pro(u.src[i]); };
+            u32 handle[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) handle[k] = peers.map((u32)k < nranks ? (u32)k : 0u);
+            auto st_peer = [&](u32 k, u32 pi, u64 bits) { peers.st(handle[k], pi, bits); };
+            TB_WITH_POLICY(pol, TB_WITH_LOGC(u.rows_log, TB_PHASE(kThreads, t, (cluster_fwd_scatter<A, LOGC, LOGT, kThreads>(t, rank, ld, st_peer, md));)))
         } else {
-            TB_WITH_POLICY(md, (tile_ntt_fwd<A, LOGT, true>(sm, 0, st, md, R));)
+            const u64 off = (u64)rank << LOGT;
+            if (u.passthrough) return; // digit already in NTT form under this modulus: the inner product reads it in place
+            if (nranks == 1) {
+                auto gld = [&](u32 i) -> u64 { return pro(u.src[i]); };
+                TB_WITH_POLICY(pol, (tile_ntt_fwd<A, LOGT, true>(sm, gld, md, 1u));)
+            } else {
+                TB_WITH_POLICY(pol, (tile_ntt_fwd<A, LOGT, false>(sm, 0, md, nranks + rank));)
+            }
+            // this tile's outputs are coefficients [off, off + T) of the limb's (bit-reversed) output
+            if (u.dst) u.dst += off;
+            if (u.ct) u.ct += off;
+            if (u.acc) u.acc += off;
+            const FwdStore st{u, md->p, a.mode};
+            TB_WITH_POLICY(pol, (tile_store_canon<A, LOGT>(sm, st, md));)
         }
     }
 };
@@ -349,32 +348,33 @@ template <int LOGT> struct NttFwdTile {
 template <int LOGT> struct NttInvTile {
     static constexpr int kThreads = TilePlan<LOGT>::NT;
     static constexpr int kMinCtas = TilePlan<LOGT>::CTAS;
-    static constexpr bool kTrailingBarrier = true; // peers read this CTA's tile in stage_b
+    static constexpr int kStages = 2;
+    static constexpr bool kTrailingBarrier = true; // peers read this CTA's tile in the gather stage
     NttArgs a;
     const char *name() const { return ntt_kernel_name(a.mode); }
 
-    TB_D void stage_a(u32 bid, u32 rank, u32 nranks, u64 *sm, const Peers &) const {
+    template <int S> TB_D void stage(u32 bid, u32 rank, u32 nranks, u64 *sm, const Peers &peers) const {
         const NttUnit u = resolve_unit<LOGT>(a, bid);
         const ModDev *md = u.md;
         const u64 p = md->p;
-        const u64 *in = u.src + ((u64)rank << LOGT);
-        auto ld = [&](u32 i) -> u64 { return in[i]; };
-        if (nranks == 1) {
-            auto st = [&](u32 i, u64 v) { inv_store_final(a, u, p, i, v); };
-            TB_WITH_POLICY(md, (tile_ntt_inv<A, LOGT, true>(sm, ld, st, md, 1u));)
-        } else {
-            TB_WITH_POLICY(md, (tile_ntt_inv<A, LOGT, false>(sm, ld, 0, md, nranks + rank));)
-        }
-    }
-
-    TB_D void stage_b(u32 bid, u32 rank, u32 nranks, u64 *, const Peers &peers) const {
-        if (nranks == 1) return;
-        const NttUnit u = resolve_unit<LOGT>(a, bid);
-        const ModDev *md = u.md;
-        const u64 p = md->p;
-        auto ld_peer = [&](u32 k, u32 pi) -> u64 { return peers.ld(k, pi); };
+        const int pol = md->policy;
         auto st = [&](u32 i, u64 v) { inv_store_final(a, u, p, i, v); };
-        TB_WITH_POLICY(md, TB_WITH_LOGC(u.rows_log, TB_PHASE(kThreads, t, (cluster_inv_stage<A, LOGC, LOGT, kThreads>(t, rank, ld_peer, st, md));)))
+        if constexpr (S == 0) {
+            const u64 *in = u.src + ((u64)rank << LOGT);
+            auto gld = [&](u32 i) -> u64 { return in[i]; };
+            if (nranks == 1) {
+                TB_WITH_POLICY(pol, (tile_ntt_inv<A, LOGT, true>(sm, gld, st, md, 1u));)
+            } else {
+                TB_WITH_POLICY(pol, (tile_ntt_inv<A, LOGT, false>(sm, gld, 0, md, nranks + rank));)
+            }
+        } else {
+            if (nranks == 1) return;
+            u32 handle[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) handle[k] = peers.map((u32)k < nranks ? (u32)k : 0u);
+            auto ld_peer = [&](u32 k, u32 pi) -> u64 { return peers.ld(handle[k], pi); };
+            TB_WITH_POLICY(pol, TB_WITH_LOGC(u.rows_log, TB_PHASE(kThreads, t, (cluster_inv_gather<A, LOGC, LOGT, kThreads>(t, rank, ld_peer, st, md));)))
+        }
     }
 };
 

@@ -7,11 +7,10 @@
 // where `t` is the thread index. On the GPU a phase is the body followed by __syncthreads(); nothing is
 // carried in registers across phases.
 //
-// Cluster kernels (launch_cluster) are functors with two stages separated by a cluster-wide barrier:
-//     __device__ void stage_a(u32 bid, u32 rank, u32 nranks, u64 *smem, const Peers &peers) const
-//     __device__ void stage_b(u32 bid, u32 rank, u32 nranks, u64 *smem, const Peers &peers) const
+// Cluster kernels (launch_cluster) are functors with F::kStages stages separated by cluster-wide barriers:
+//     template <int S> __device__ void stage(u32 bid, u32 rank, u32 nranks, u64 *smem, const Peers &peers) const
 // `peers` reads / writes 64-bit words of the shared memory of any CTA of the cluster (distributed shared memory).
-// A second barrier after stage_b keeps every CTA's shared memory alive until its peers have finished reading it.
+// A last barrier after the final stage keeps every CTA's shared memory alive until its peers have finished reading it.
 //
 // TROYB_HOST_EMUL (tests/emul only, never part of the product library) re-targets the same functors to a
 // sequential CPU loop over CTAs and threads so that index arithmetic can be debugged without a GPU.
@@ -56,19 +55,24 @@ template <class F> inline cudaError_t launch_cta(const F &f, u32 grid, size_t sm
 
 struct Peers {
     u64 *const *tiles;
-    u64 ld(u32 rank, u32 word) const { return tiles[rank][word]; }
-    void st(u32 rank, u32 word, u64 v) const { tiles[rank][word] = v; }
+    u32 map(u32 rank) const { return rank; } // handle of a peer's tile
+    u64 ld(u32 handle, u32 word) const { return tiles[handle][word]; }
+    void st(u32 handle, u32 word, u64 v) const { tiles[handle][word] = v; }
 };
+
+template <class F, int S> inline void emul_stages(const F &f, u32 b0, u32 nranks, std::vector<u64 *> &ptr, const Peers &peers) {
+    if constexpr (S < F::kStages) {
+        for (u32 r = 0; r < nranks; r++) f.template stage<S>(b0 + r, r, nranks, ptr[r], peers);
+        emul_stages<F, S + 1>(f, b0, nranks, ptr, peers);
+    }
+}
 
 template <class F> inline cudaError_t launch_cluster(const F &f, u32 grid, u32 nranks, size_t smem_bytes, cudaStream_t) {
     std::vector<std::vector<u64>> sm(nranks, std::vector<u64>(smem_bytes / 8 + 1));
     std::vector<u64 *> ptr(nranks);
     for (u32 r = 0; r < nranks; r++) ptr[r] = sm[r].data();
     Peers peers{ptr.data()};
-    for (u32 b0 = 0; b0 < grid; b0 += nranks) {
-        for (u32 r = 0; r < nranks; r++) f.stage_a(b0 + r, r, nranks, ptr[r], peers);
-        for (u32 r = 0; r < nranks; r++) f.stage_b(b0 + r, r, nranks, ptr[r], peers);
-    }
+    for (u32 b0 = 0; b0 < grid; b0 += nranks) emul_stages<F, 0>(f, b0, nranks, ptr, peers);
     launch_counter()++;
     return cudaSuccess;
 }
@@ -119,23 +123,32 @@ template <class F> inline cudaError_t launch_cta(const F &f, u32 grid, size_t sm
 // ---- thread-block clusters + distributed shared memory ---------------------------------------------------------------
 struct Peers {
     u32 base; // shared::cta address of this CTA's dynamic shared memory (same offset in every CTA of the cluster)
-    TB_D u32 addr(u32 rank, u32 word) const {
+    // shared::cluster address of the start of CTA `rank`'s tile
+    TB_D u32 map(u32 rank) const {
         u32 r;
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(base + word * 8u), "r"(rank));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(base), "r"(rank));
         return r;
     }
-    TB_D u64 ld(u32 rank, u32 word) const {
+    TB_D u64 ld(u32 handle, u32 word) const {
         u64 v;
-        asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(addr(rank, word)) : "memory");
+        asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(handle + word * 8u) : "memory");
         return v;
     }
-    TB_D void st(u32 rank, u32 word, u64 v) const {
-        asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(addr(rank, word)), "l"(v) : "memory");
+    TB_D void st(u32 handle, u32 word, u64 v) const {
+        asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(handle + word * 8u), "l"(v) : "memory");
     }
 };
 
 TB_D void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <class F, int S> TB_D void run_stages(const F &f, u32 rank, u32 nranks, u64 *smem, const Peers &peers) {
+    if constexpr (S < F::kStages) {
+        f.template stage<S>(blockIdx.x, rank, nranks, smem, peers);
+        if (nranks > 1 && (S + 1 < F::kStages || F::kTrailingBarrier)) cluster_barrier();
+        run_stages<F, S + 1>(f, rank, nranks, smem, peers);
+    }
 }
 
 template <class F> __global__ void __launch_bounds__(F::kThreads, F::kMinCtas) k_cluster(const F f) {
@@ -144,10 +157,7 @@ template <class F> __global__ void __launch_bounds__(F::kThreads, F::kMinCtas) k
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(nranks));
     const Peers peers{(u32)__cvta_generic_to_shared(tb_smem)};
-    f.stage_a(blockIdx.x, rank, nranks, tb_smem, peers);
-    if (nranks > 1) cluster_barrier();
-    f.stage_b(blockIdx.x, rank, nranks, tb_smem, peers);
-    if (nranks > 1 && F::kTrailingBarrier) cluster_barrier();
+    run_stages<F, 0>(f, rank, nranks, tb_smem, peers);
 }
 
 template <class F> inline cudaError_t launch_cluster(const F &f, u32 grid, u32 nranks, size_t smem_bytes, cudaStream_t stream) {

@@ -56,6 +56,7 @@ struct ArithU64Exact {
     typedef u64 elem;
     typedef TwU64 tw_t;
     static constexpr bool kReduceEachInvRound = false;
+    static constexpr bool kReduceInvMidway = false;
     struct Mod {
         u64 p, p2, ratio1;
         TwU64 ninv, inv1n;
@@ -77,6 +78,7 @@ struct ArithU64Exact {
     static TB_D elem from_bits(u64 v) { return v; }
     static TB_D u64 to_bits(elem x) { return x; }
     static TB_D u64 canon(elem x, const Mod &m) { return barrett64(x, m.p, m.ratio1); }
+    static TB_D u64 canon_reduced(elem x, const Mod &m) { return x - (x >= m.p ? m.p : 0); } // after gs_last: [0,2p)
     static TB_D void reduce(elem &, const Mod &) {}
     static TB_D void ct(elem &X, elem &Y, tw_t w, const Mod &m) {
         u64 x = X - (X >= m.p2 ? m.p2 : 0);
@@ -105,6 +107,7 @@ struct ArithU64Fast {
     typedef u64 elem;
     typedef TwU64 tw_t;
     static constexpr bool kReduceEachInvRound = false;
+    static constexpr bool kReduceInvMidway = false;
     struct Mod {
         u64 p, p4, ratio1;
         u32 np0, np1, H;
@@ -127,6 +130,11 @@ struct ArithU64Fast {
     static TB_D elem from_bits(u64 v) { return v; }
     static TB_D u64 to_bits(elem x) { return x; }
     static TB_D u64 canon(elem x, const Mod &m) { return barrett64(x, m.p, m.ratio1); }
+    static TB_D u64 canon_reduced(elem x, const Mod &m) { // after gs_last: [0,3p)
+        const u64 p2 = m.p << 1;
+        x -= (x >= p2 ? p2 : 0);
+        return x - (x >= m.p ? m.p : 0);
+    }
     static TB_D void reduce(elem &, const Mod &) {}
     // add + Y*w - q*p (mod 2^64) with q in [Q-2, Q], Q = floor(Y*wq / 2^64); equals add + (Y*w mod p) + {0,1,2}*p
     static TB_D u64 mul_acc(u64 add, u64 Y, tw_t t, const Mod &m) {
@@ -176,6 +184,7 @@ struct ArithF64 {
     typedef double elem;
     typedef TwF64 tw_t;
     static constexpr bool kReduceEachInvRound = true;
+    static constexpr bool kReduceInvMidway = false;
     struct Mod {
         double p, pinv;
         TwF64 ninv, inv1n;
@@ -204,10 +213,13 @@ struct ArithF64 {
         double q = __dadd_rn(__fma_rn(x, m.pinv, kMagic), -kMagic);
         x = __fma_rn(-q, m.p, x);
     }
-    static TB_D u64 canon(elem x, const Mod &m) {
-        reduce(x, m);
+    static TB_D u64 canon_reduced(elem x, const Mod &m) { // |x| < p (a mulmod result)
         if (x < 0.0) x = __dadd_rn(x, m.p);
         return (u64)__double_as_longlong(__dadd_rn(x, kTwo52)) & 0x000FFFFFFFFFFFFFull;
+    }
+    static TB_D u64 canon(elem x, const Mod &m) {
+        reduce(x, m);
+        return canon_reduced(x, m);
     }
     static TB_D double mulmod(double y, tw_t t, const Mod &m) {
         double h = __dmul_rn(y, t.w);
@@ -234,6 +246,14 @@ struct ArithF64 {
         X = mulmod(s, m.ninv, m);
         Y = mulmod(d, m.inv1n, m);
     }
+};
+
+// The same arithmetic for p < 2^41 (the usual 40-bit CKKS scale primes). A mulmod accepts |y| < 2^51 and returns
+// |r| <= p, and an unreduced sum path doubles per layer, so values stay below 2^50 for 9 layers after a reduction: the
+// inverse transform re-centres only once, at the start of its second-to-last tile round, instead of in every round.
+struct ArithF64S : ArithF64 {
+    static constexpr bool kReduceEachInvRound = false;
+    static constexpr bool kReduceInvMidway = true;
 };
 
 // ---- register butterfly networks --------------------------------------------------------------------------------------------
@@ -295,24 +315,32 @@ __host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x
 
 // Geometry of one radix-2^RR round on a tile of 2^LOGT coefficients, layers S0..S0+RR-1, run by NT cooperating
 // threads. The tile splits into NV = 2^(LOGT-RR) independent groups of K = 2^RR coefficients spaced 2^BLO apart;
-// group v = (hi, lo) has base index (hi << (BLO+RR)) | lo and uses the twiddles of block hi. A thread takes G groups.
-//   SHARED : the G groups of a thread lie in the same block hi (possible when a block has at least 16 G groups), so
-//            the thread fetches its 2^RR-1 twiddles once per round;
-//   else   : thread slots are consecutive groups; U groups are in flight at a time (twiddles and data fetched up front
-//            so that their latencies overlap).
+// group v = (hi, lo) has base index (hi << (BLO+RR)) | lo and uses the twiddles of block hi. A thread takes G groups,
+// SH of them at a time from the same block so that one set of 2^RR-1 twiddles serves SH groups:
+//   SHARED (SH = G) : a block holds at least 16 G groups;
+//   PAIRED (SH = 2) : BLO = 4 and RR = 3: lanes take lo bits 0-2 and hi bit 0 (the padding maps index bit 7 to the bank
+//                     bit that lo bit 3 would have supplied), the two groups of a turn differ in lo bit 3;
+//   else   (SH = 1) : thread slots are consecutive groups (with the lane rotation of group_of_slot when 0 < BLO < 4);
+//                     U groups are in flight at a time.
 template <int LOGT, int NT, int S0, int RR> struct RoundGeom {
     static constexpr int K = 1 << RR, BLO = LOGT - S0 - RR, NV = (1 << LOGT) / K, G = NV / NT, LOGG = ilog2(G);
     static_assert(BLO >= 0 && G >= 1 && NV % NT == 0 && (1 << LOGG) == G, "bad round");
     static constexpr bool SHARED = BLO >= LOGG + 4;
+    static constexpr bool PAIRED = !SHARED && BLO == 4 && RR == 3 && G % 2 == 0;
+    static constexpr int SH = SHARED ? G : (PAIRED ? 2 : 1);
     static constexpr int TL = SHARED ? BLO - LOGG : 0;
-    static constexpr int U = SHARED ? 1 : ((RR <= 2 && G % 2 == 0) ? 2 : 1);
-    // group handled by thread vt in its g-th turn
-    static TB_D void locate(u32 vt, int g, u32 &hi, u32 &base) {
+    static constexpr int U = (SH == 1 && RR <= 2 && G % 2 == 0) ? 2 : 1; // independent groups in flight (SH == 1)
+    static constexpr int TURNS = G / (SH * U);
+    // group handled by thread vt: turn `turn`, in-flight slot q (< U), shared-twiddle member e (< SH)
+    static TB_D void locate(u32 vt, int turn, int q, int e, u32 &hi, u32 &base) {
         if constexpr (SHARED) {
             hi = vt >> TL;
-            base = (hi << (BLO + RR)) | ((u32)g << TL) | (vt & ((1u << TL) - 1));
+            base = (hi << (BLO + RR)) | ((u32)e << TL) | (vt & ((1u << TL) - 1));
+        } else if constexpr (PAIRED) {
+            hi = ((vt >> 3) & ((NT >> 3) - 1)) | ((u32)turn * (NT >> 3));
+            base = (hi << (BLO + RR)) | ((u32)e << 3) | (vt & 7);
         } else {
-            const u32 v = group_of_slot<BLO, RR>(vt + (u32)g * NT);
+            const u32 v = group_of_slot<BLO, RR>(vt + (u32)(turn * U + q) * NT);
             hi = v >> BLO;
             base = (hi << (BLO + RR)) | (v & ((1u << BLO) - 1));
         }
@@ -328,110 +356,70 @@ template <class A, int RR, int S0> TB_D void load_twiddles(typename A::tw_t (&w)
     }
 }
 
+// One round of the forward (INVERSE = false) or inverse transform over the tile.
 //   PIN / POUT: the source / destination is the padded shared-memory tile (index = pad_idx(i)); the padded offset of
 //   coefficient k of a group is a compile-time constant because the group base and k << BLO occupy disjoint bits.
-template <class A, int LOGT, int NT, int S0, int RR, bool PIN, bool POUT, class Ld, class St>
-TB_D void fwd_round(u32 vt, Ld ld, St st, const void *__restrict__ tw, u32 R, const typename A::Mod &m) {
+//   LAST   : (inverse) layer 0 of the whole transform is layer S0 = 0 of this round and carries the N^-1 scaling
+//   REDUCE : (inverse) re-centre the inputs first (FP64 policies)
+template <class A, int LOGT, int NT, int S0, int RR, bool INVERSE, bool LAST, bool REDUCE, bool PIN, bool POUT, class Ld, class St>
+TB_D void tile_round(u32 vt, Ld ld, St st, const void *__restrict__ tw, u32 R, const typename A::Mod &m) {
     typedef RoundGeom<LOGT, NT, S0, RR> Q;
-    constexpr int K = Q::K, BLO = Q::BLO, G = Q::G, U = Q::U;
+    constexpr int K = Q::K, BLO = Q::BLO, U = Q::U, SH = Q::SH;
     if constexpr (Q::SHARED) {
+        // all G groups of the thread share one twiddle set; two groups in flight at a time
         u32 hi, base0;
-        Q::locate(vt, 0, hi, base0);
+        Q::locate(vt, 0, 0, 0, hi, base0);
         typename A::tw_t w[K - 1];
         load_twiddles<A, RR, S0>(w, tw, R, hi);
 #pragma unroll 2
-        for (int g = 0; g < G; g++) {
-            const u32 base = base0 | ((u32)g << Q::TL);
-            const u32 ib = PIN ? pad_idx(base) : base, ob = POUT ? pad_idx(base) : base;
-            typename A::elem x[K];
-#pragma unroll
-            for (int k = 0; k < K; k++) x[k] = ld(ib + (PIN ? pad_idx((u32)k << BLO) : ((u32)k << BLO)));
-            radix_fwd<A, RR>(x, w, m);
-#pragma unroll
-            for (int k = 0; k < K; k++) st(ob + (POUT ? pad_idx((u32)k << BLO) : ((u32)k << BLO)), x[k]);
-        }
-    } else {
-#pragma unroll 1
-        for (int g = 0; g < G; g += U) {
-            u32 ib[U], ob[U];
-            typename A::tw_t w[U][K - 1];
-            typename A::elem x[U][K];
-#pragma unroll
-            for (int q = 0; q < U; q++) {
-                u32 hi, base;
-                Q::locate(vt, g + q, hi, base);
-                ib[q] = PIN ? pad_idx(base) : base;
-                ob[q] = POUT ? pad_idx(base) : base;
-                load_twiddles<A, RR, S0>(w[q], tw, R, hi);
-            }
-#pragma unroll
-            for (int q = 0; q < U; q++) {
-#pragma unroll
-                for (int k = 0; k < K; k++) x[q][k] = ld(ib[q] + (PIN ? pad_idx((u32)k << BLO) : ((u32)k << BLO)));
-            }
-#pragma unroll
-            for (int q = 0; q < U; q++) {
-                radix_fwd<A, RR>(x[q], w[q], m);
-#pragma unroll
-                for (int k = 0; k < K; k++) st(ob[q] + (POUT ? pad_idx((u32)k << BLO) : ((u32)k << BLO)), x[q][k]);
-            }
-        }
-    }
-}
-
-// One radix-2^RR round of the inverse transform: layers S0+RR-1 down to S0 of the tile.
-// FINAL: layer 0 of the whole transform is in this round and carries the N^-1 scaling.
-template <class A, int LOGT, int NT, int S0, int RR, bool FINAL, bool PIN, bool POUT, class Ld, class St>
-TB_D void inv_round(u32 vt, Ld ld, St st, const void *__restrict__ tw, u32 R, const typename A::Mod &m) {
-    typedef RoundGeom<LOGT, NT, S0, RR> Q;
-    constexpr int K = Q::K, BLO = Q::BLO, G = Q::G, U = Q::U;
-    constexpr bool LAST = FINAL && S0 == 0;
-    if constexpr (Q::SHARED) {
-        u32 hi, base0;
-        Q::locate(vt, 0, hi, base0);
-        typename A::tw_t w[K - 1];
-        load_twiddles<A, RR, S0>(w, tw, R, hi);
-#pragma unroll 2
-        for (int g = 0; g < G; g++) {
-            const u32 base = base0 | ((u32)g << Q::TL);
+        for (int e = 0; e < SH; e++) {
+            const u32 base = base0 | ((u32)e << Q::TL);
             const u32 ib = PIN ? pad_idx(base) : base, ob = POUT ? pad_idx(base) : base;
             typename A::elem x[K];
 #pragma unroll
             for (int k = 0; k < K; k++) {
                 x[k] = ld(ib + (PIN ? pad_idx((u32)k << BLO) : ((u32)k << BLO)));
-                if (A::kReduceEachInvRound) A::reduce(x[k], m);
+                if (REDUCE) A::reduce(x[k], m);
             }
-            radix_inv<A, RR, LAST>(x, w, m);
+            if constexpr (INVERSE) radix_inv<A, RR, LAST>(x, w, m);
+            else radix_fwd<A, RR>(x, w, m);
 #pragma unroll
             for (int k = 0; k < K; k++) st(ob + (POUT ? pad_idx((u32)k << BLO) : ((u32)k << BLO)), x[k]);
         }
     } else {
+        constexpr int F = U * SH; // groups in flight
 #pragma unroll 1
-        for (int g = 0; g < G; g += U) {
-            u32 ib[U], ob[U];
+        for (int turn = 0; turn < Q::TURNS; turn++) {
+            u32 ib[F], ob[F];
             typename A::tw_t w[U][K - 1];
-            typename A::elem x[U][K];
+            typename A::elem x[F][K];
 #pragma unroll
             for (int q = 0; q < U; q++) {
-                u32 hi, base;
-                Q::locate(vt, g + q, hi, base);
-                ib[q] = PIN ? pad_idx(base) : base;
-                ob[q] = POUT ? pad_idx(base) : base;
+                u32 hi = 0;
+#pragma unroll
+                for (int e = 0; e < SH; e++) {
+                    u32 base;
+                    Q::locate(vt, turn, q, e, hi, base);
+                    ib[q * SH + e] = PIN ? pad_idx(base) : base;
+                    ob[q * SH + e] = POUT ? pad_idx(base) : base;
+                }
                 load_twiddles<A, RR, S0>(w[q], tw, R, hi);
             }
 #pragma unroll
-            for (int q = 0; q < U; q++) {
+            for (int f = 0; f < F; f++) {
 #pragma unroll
-                for (int k = 0; k < K; k++) {
-                    x[q][k] = ld(ib[q] + (PIN ? pad_idx((u32)k << BLO) : ((u32)k << BLO)));
-                    if (A::kReduceEachInvRound) A::reduce(x[q][k], m);
-                }
+                for (int k = 0; k < K; k++) x[f][k] = ld(ib[f] + (PIN ? pad_idx((u32)k << BLO) : ((u32)k << BLO)));
             }
 #pragma unroll
-            for (int q = 0; q < U; q++) {
-                radix_inv<A, RR, LAST>(x[q], w[q], m);
+            for (int f = 0; f < F; f++) {
+                if (REDUCE) {
 #pragma unroll
-                for (int k = 0; k < K; k++) st(ob[q] + (POUT ? pad_idx((u32)k << BLO) : ((u32)k << BLO)), x[q][k]);
+                    for (int k = 0; k < K; k++) A::reduce(x[f][k], m);
+                }
+                if constexpr (INVERSE) radix_inv<A, RR, LAST>(x[f], w[f / SH], m);
+                else radix_fwd<A, RR>(x[f], w[f / SH], m);
+#pragma unroll
+                for (int k = 0; k < K; k++) st(ob[f] + (POUT ? pad_idx((u32)k << BLO) : ((u32)k << BLO)), x[f][k]);
             }
         }
     }
@@ -439,9 +427,10 @@ TB_D void inv_round(u32 vt, Ld ld, St st, const void *__restrict__ tw, u32 R, co
 
 // ---- tile plans ------------------------------------------------------------------------------------------------------------
 // A tile is 2^LOGT coefficients owned by one CTA: 4096 (N = 4096) or 8192 (N = 8192, and N = 16384 / 32768 / 65536 as a
-// thread-block cluster of 2 / 4 / 8 CTAs, see kernels_ntt.cuh). Radix-8 / radix-4 rounds keep a group plus its twiddles
-// under 80 registers, so three 8192-tiles (or six 4096-tiles) are resident per SM and their load, butterfly and store
-// phases overlap. Every listed round is bank-conflict free with pad_idx and group_of_slot (tools/banksim.py).
+// thread-block cluster of 2 / 4 / 8 CTAs, see kernels_ntt.cuh). Radix-8 / radix-4 rounds keep the groups in flight plus
+// their twiddles under 80 registers, so three 8192-tiles (or six 4096-tiles) are resident per SM and their load,
+// butterfly and store phases overlap. Every listed round is bank-conflict free with pad_idx and RoundGeom::locate
+// (tools/banksim.py).
 template <int LOGT> struct TilePlan;
 template <> struct TilePlan<12> { static constexpr int NT = 128, CTAS = 6, R0 = 3, R1 = 3, R2 = 3, R3 = 3, R4 = 0; };
 template <> struct TilePlan<13> { static constexpr int NT = 256, CTAS = 3, R0 = 3, R1 = 3, R2 = 3, R3 = 2, R4 = 2; };
@@ -456,83 +445,90 @@ template <class A> struct SmSt {
     TB_D void operator()(u32 i, typename A::elem v) const { sm[i] = A::to_bits(v); }
 };
 
-// Forward transform of a tile held by one CTA.
-//   SMEM_IN  : the tile already sits in shared memory as raw element bits (a cluster's first stage put it there);
-//              otherwise ld(i) returns coefficient i of the tile as u64 (prologue fused there)
-//   st(i, v) : receives the canonical residue of output i (epilogue fused here; linear, coalesced order)
-// The last round's results pass through shared memory once more so that global stores are coalesced.
-template <class A, int LOGT, bool SMEM_IN, class Ld, class St>
-TB_D void tile_ntt_fwd(u64 *sm, Ld ld, St st, const ModDev *md, u32 R) {
+// The tile's own 2^LOGT-point forward transform, in place in shared memory (layers 0..LOGT-1 with root base R).
+//   GLOBAL_IN : the first round reads coefficient i of the tile as gld(i) (global memory, prologue fused there).
+//               Otherwise the tile holds element bits left by the cluster's scatter stage.
+// The results stay in shared memory as element bits.
+template <class A, int LOGT, bool GLOBAL_IN, class Gld>
+TB_D void tile_ntt_fwd(u64 *sm, Gld gld, const ModDev *md, u32 R) {
     typedef TilePlan<LOGT> P;
-    constexpr int NT = P::NT, T = 1 << LOGT;
+    constexpr int NT = P::NT;
     const typename A::Mod m = A::make(md);
     const void *tw = A::fwd_table(md);
     SmLd<A> sl{sm};
     SmSt<A> ss{sm};
-    if constexpr (SMEM_IN) {
-        TB_PHASE(NT, t, (fwd_round<A, LOGT, NT, 0, P::R0, true, true>(t, sl, ss, tw, R, m));)
+    if constexpr (GLOBAL_IN) {
+        auto rl = [&](u32 i) -> typename A::elem { return A::from_u64(gld(i), m); };
+        TB_PHASE(NT, t, (tile_round<A, LOGT, NT, 0, P::R0, false, false, false, false, true>(t, rl, ss, tw, R, m));)
     } else {
-        auto gl = [&](u32 i) -> typename A::elem { return A::from_u64(ld(i), m); };
-        TB_PHASE(NT, t, (fwd_round<A, LOGT, NT, 0, P::R0, false, true>(t, gl, ss, tw, R, m));)
+        TB_PHASE(NT, t, (tile_round<A, LOGT, NT, 0, P::R0, false, false, false, true, true>(t, sl, ss, tw, R, m));)
     }
-    TB_PHASE(NT, t, (fwd_round<A, LOGT, NT, P::R0, P::R1, true, true>(t, sl, ss, tw, R, m));)
-    TB_PHASE(NT, t, (fwd_round<A, LOGT, NT, P::R0 + P::R1, P::R2, true, true>(t, sl, ss, tw, R, m));)
+    TB_PHASE(NT, t, (tile_round<A, LOGT, NT, P::R0, P::R1, false, false, false, true, true>(t, sl, ss, tw, R, m));)
+    TB_PHASE(NT, t, (tile_round<A, LOGT, NT, P::R0 + P::R1, P::R2, false, false, false, true, true>(t, sl, ss, tw, R, m));)
     if constexpr (P::R3 > 0) {
-        TB_PHASE(NT, t, (fwd_round<A, LOGT, NT, P::R0 + P::R1 + P::R2, P::R3, true, true>(t, sl, ss, tw, R, m));)
+        TB_PHASE(NT, t, (tile_round<A, LOGT, NT, P::R0 + P::R1 + P::R2, P::R3, false, false, false, true, true>(t, sl, ss, tw, R, m));)
     }
     if constexpr (P::R4 > 0) {
-        TB_PHASE(NT, t, (fwd_round<A, LOGT, NT, P::R0 + P::R1 + P::R2 + P::R3, P::R4, true, true>(t, sl, ss, tw, R, m));)
+        TB_PHASE(NT, t, (tile_round<A, LOGT, NT, P::R0 + P::R1 + P::R2 + P::R3, P::R4, false, false, false, true, true>(t, sl, ss, tw, R, m));)
     }
+}
+
+// Canonical store of a finished tile: st(i, v) receives the canonical residue of output i (linear, coalesced order).
+template <class A, int LOGT, class St> TB_D void tile_store_canon(const u64 *sm, St st, const ModDev *md) {
+    typedef TilePlan<LOGT> P;
+    constexpr int NT = P::NT, T = 1 << LOGT;
+    const typename A::Mod m = A::make(md);
     TB_PHASE(NT, t, {
         _Pragma("unroll 4") for (int k = 0; k < T / NT; k++) {
-            u32 i = t + k * NT;
+            const u32 i = t + k * NT;
             st(i, A::canon(A::from_bits(sm[pad_idx(i)]), m));
         }
     })
 }
 
-// Inverse transform of a tile. ld(i): canonical residues as u64.
-//   FINAL    : the tile contains layer 0 (N^-1 folded in) and st(i, v) receives canonical residues; otherwise the raw
-//              element bits stay in shared memory for the cluster's last stage and st is not called.
-template <class A, int LOGT, bool FINAL, class Ld, class St>
-TB_D void tile_ntt_inv(u64 *sm, Ld ld, St st, const ModDev *md, u32 R) {
+// The tile's own inverse transform (layers LOGT-1..0 with root base R); the first round reads the canonical
+// coefficient i of the tile as gld(i) straight from global memory.
+//   FINAL : the tile is the whole limb: layer 0 carries N^-1 and st(i, v) receives canonical residues; otherwise the
+//           element bits stay in shared memory for the cluster's gather stage and st is not called.
+template <class A, int LOGT, bool FINAL, class Gld, class St>
+TB_D void tile_ntt_inv(u64 *sm, Gld gld, St st, const ModDev *md, u32 R) {
     typedef TilePlan<LOGT> P;
-    constexpr int NT = P::NT, T = 1 << LOGT;
+    constexpr int NT = P::NT;
+    constexpr bool RE = A::kReduceEachInvRound, RM = A::kReduceInvMidway;
     const typename A::Mod m = A::make(md);
     const void *tw = A::inv_table(md);
     SmLd<A> sl{sm};
     SmSt<A> ss{sm};
-    TB_PHASE(NT, t, {
-        _Pragma("unroll 8") for (int k = 0; k < T / NT; k++) {
-            u32 i = t + k * NT;
-            sm[pad_idx(i)] = A::to_bits(A::from_u64(ld(i), m));
-        }
-    })
+    auto rl = [&](u32 i) -> typename A::elem { return A::from_u64(gld(i), m); }; // canonical input: no re-centring needed
+    constexpr int S1 = P::R0, S2 = S1 + P::R1, S3 = S2 + P::R2, S4 = S3 + P::R3;
     if constexpr (P::R4 > 0) {
-        TB_PHASE(NT, t, (inv_round<A, LOGT, NT, P::R0 + P::R1 + P::R2 + P::R3, P::R4, false, true, true>(t, sl, ss, tw, R, m));)
-    }
-    if constexpr (P::R3 > 0) {
-        TB_PHASE(NT, t, (inv_round<A, LOGT, NT, P::R0 + P::R1 + P::R2, P::R3, false, true, true>(t, sl, ss, tw, R, m));)
-    }
-    TB_PHASE(NT, t, (inv_round<A, LOGT, NT, P::R0 + P::R1, P::R2, false, true, true>(t, sl, ss, tw, R, m));)
-    TB_PHASE(NT, t, (inv_round<A, LOGT, NT, P::R0, P::R1, false, true, true>(t, sl, ss, tw, R, m));)
-    if constexpr (FINAL) {
-        auto gs_ = [&](u32 i, typename A::elem x) { st(i, A::canon(x, m)); };
-        TB_PHASE(NT, t, (inv_round<A, LOGT, NT, 0, P::R0, true, true, false>(t, sl, gs_, tw, R, m));)
+        TB_PHASE(NT, t, (tile_round<A, LOGT, NT, S4, P::R4, true, false, false, false, true>(t, rl, ss, tw, R, m));)
+        TB_PHASE(NT, t, (tile_round<A, LOGT, NT, S3, P::R3, true, false, RE, true, true>(t, sl, ss, tw, R, m));)
     } else {
-        TB_PHASE(NT, t, (inv_round<A, LOGT, NT, 0, P::R0, false, true, true>(t, sl, ss, tw, R, m));)
+        TB_PHASE(NT, t, (tile_round<A, LOGT, NT, S3, P::R3, true, false, false, false, true>(t, rl, ss, tw, R, m));)
+    }
+    TB_PHASE(NT, t, (tile_round<A, LOGT, NT, S2, P::R2, true, false, RE, true, true>(t, sl, ss, tw, R, m));)
+    TB_PHASE(NT, t, (tile_round<A, LOGT, NT, S1, P::R1, true, false, RE || RM, true, true>(t, sl, ss, tw, R, m));)
+    if constexpr (FINAL) {
+        auto gs_ = [&](u32 i, typename A::elem x) { st(i, A::canon_reduced(x, m)); };
+        TB_PHASE(NT, t, (tile_round<A, LOGT, NT, 0, P::R0, true, true, RE, true, false>(t, sl, gs_, tw, R, m));)
+    } else {
+        TB_PHASE(NT, t, (tile_round<A, LOGT, NT, 0, P::R0, true, false, RE, true, true>(t, sl, ss, tw, R, m));)
     }
 }
 
-// ---- cluster stages (N = 2^LOGC tiles) -----------------------------------------------------------------------------------------
-// The first LOGC layers of the forward transform couple coefficients one tile apart. CTA `rank` of the cluster loads the
-// 2^LOGC coefficients {v + k T} for its share of v, runs the radix-2^LOGC network in registers and hands output k to
-// tile k (a store into that CTA's shared memory through the cluster's distributed shared memory). After the cluster
-// barrier every CTA owns an independent 2^LOGT-point transform with root base 2^LOGC + rank.
+// ---- cluster stages ------------------------------------------------------------------------------------------------------------
+// A limb of N = C tiles is one cluster of C CTAs (C = 2, 4, 8). Tile r owns the contiguous block [r T, (r+1) T) of the
+// transform's bit-reversed side.
+//
+// Forward. The first log C layers couple coefficients one tile apart. CTA `rank` loads the C coefficients {v + k T}
+// for its share of v, runs the radix-C network in registers and hands output k to tile k (a store into that CTA's
+// shared memory through the cluster's distributed shared memory). After the cluster barrier every CTA owns an
+// independent 2^LOGT-point transform with root base C + rank.
 //   ld(i)            : coefficient i of the limb as u64 (prologue fused there)
 //   st_peer(k, i, b) : store raw element bits b at padded index i of tile k
 template <class A, int LOGC, int LOGT, int NT, class Ld, class StPeer>
-TB_D void cluster_fwd_stage(u32 vt, u32 rank, Ld ld, StPeer st_peer, const ModDev *md) {
+TB_D void cluster_fwd_scatter(u32 vt, u32 rank, Ld ld, StPeer st_peer, const ModDev *md) {
     constexpr int C = 1 << LOGC, T = 1 << LOGT, G = T / C / NT;
     static_assert(G >= 1, "bad cluster stage");
     const typename A::Mod m = A::make(md);
@@ -540,7 +536,7 @@ TB_D void cluster_fwd_stage(u32 vt, u32 rank, Ld ld, StPeer st_peer, const ModDe
     typename A::tw_t w[C - 1];
 #pragma unroll
     for (int k = 1; k < C; k++) w[k - 1] = A::ld_tw(tw, k); // layer u, block j: table entry 2^u + j
-#pragma unroll(8 / C)
+#pragma unroll(16 / C)
     for (int g = 0; g < G; g++) {
         const u32 v = rank * (T / C) + vt + g * NT;
         typename A::elem x[C];
@@ -553,15 +549,16 @@ TB_D void cluster_fwd_stage(u32 vt, u32 rank, Ld ld, StPeer st_peer, const ModDe
     }
 }
 
-// Mirror image for the inverse: after every tile has run its 2^LOGT-point inverse (raw bits left in shared memory) and
-// the cluster barrier, CTA `rank` gathers {tile k, position v} for its share of v, runs the last LOGC layers (layer 0
-// carries N^-1) and stores the canonical results.
+// Inverse. Each tile's own inverse transform covers layers log N-1..log C; the last log C layers (layer 0 carries N^-1) couple the tiles: CTA `rank` gathers
+// {tile k, position v} for its share of v and stores the canonical results (natural order, coalesced).
 //   ld_peer(k, i) : raw element bits at padded index i of tile k
 //   st(i, v)      : canonical residue of coefficient i of the limb (epilogue fused there)
 template <class A, int LOGC, int LOGT, int NT, class LdPeer, class St>
-TB_D void cluster_inv_stage(u32 vt, u32 rank, LdPeer ld_peer, St st, const ModDev *md) {
+TB_D void cluster_inv_gather(u32 vt, u32 rank, LdPeer ld_peer, St st, const ModDev *md) {
     constexpr int C = 1 << LOGC, T = 1 << LOGT, G = T / C / NT;
     static_assert(G >= 1, "bad cluster stage");
+    // the tile's last round leaves at most 2^3 x the re-centred magnitude: one more layer needs no re-centring
+    constexpr bool RE = A::kReduceEachInvRound && LOGC > 1;
     const typename A::Mod m = A::make(md);
     const void *tw = A::inv_table(md);
     typename A::tw_t w[C - 1];
@@ -575,11 +572,14 @@ TB_D void cluster_inv_stage(u32 vt, u32 rank, LdPeer ld_peer, St st, const ModDe
 #pragma unroll
         for (int k = 0; k < C; k++) {
             x[k] = A::from_bits(ld_peer((u32)k, pv));
-            if (A::kReduceEachInvRound) A::reduce(x[k], m);
+            if (RE) A::reduce(x[k], m);
         }
         radix_inv<A, LOGC, true>(x, w, m);
 #pragma unroll
-        for (int k = 0; k < C; k++) st(v + (u32)k * T, A::canon(x[k], m));
+        for (int k = 0; k < C; k++) {
+            // outputs of layer 0 are mulmod results; for C > 2 the others passed through it too
+            st(v + (u32)k * T, A::canon_reduced(x[k], m));
+        }
     }
 }
 
