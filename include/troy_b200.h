@@ -94,6 +94,10 @@ int troyb_ntt_inverse_key(troyb_context *ctx, uint64_t *d_data, size_t n_polys, 
 int troyb_add(troyb_context *ctx, int level, const uint64_t *d_a, const uint64_t *d_b, uint64_t *d_out, size_t n_polys, void *stream);
 int troyb_sub(troyb_context *ctx, int level, const uint64_t *d_a, const uint64_t *d_b, uint64_t *d_out, size_t n_polys, void *stream);
 int troyb_negate(troyb_context *ctx, int level, const uint64_t *d_a, uint64_t *d_out, size_t n_polys, void *stream);
+/* kMultiplyPolyScalarCoeffmod  src/kernelutils.cu:272-298: out = a * (scalar mod q_l) mod q_l on every limb
+ * (BGV correction-factor balancing before add / sub, src/evaluator_cuda.cu:171-190) */
+int troyb_multiply_scalar(troyb_context *ctx, int level, const uint64_t *d_a, uint64_t scalar, uint64_t *d_out, size_t n_polys,
+                          void *stream);
 
 /* EvaluatorCuda::multiplyInplace → ckksMultiply / bgvMultiply / bfvMultiply  src/evaluator_cuda.cu:262-523
  * (squareInplace :525-701 is the same call with d_b = d_a). Inputs a: a_size polys, b: b_size polys; output

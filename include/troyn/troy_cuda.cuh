@@ -1,0 +1,661 @@
+// troyn drop-in host layer: the reference's `troyn::` / `troy::*Cuda` C++ surface for the RNS polynomial hot path,
+// implemented over the C ABI of libtroy_b200.so (include/troy_b200.h).
+//
+// A user of lightbulb128/troy includes this header INSTEAD of the reference's src/troy_cuda.cuh (same class names in
+// the same namespaces, same method names, argument meaning and exception types) and links libtroy_b200.so plus the
+// reference's own host (CPU) classes, which this header reuses exactly where the reference's CUDA classes do:
+//   * KeyGeneratorCuda wraps the host KeyGenerator          (reference: src/keygenerator_cuda.cuh:36-60)
+//   * encoders, encryption, decryption and plaintexts are host work that is out of the hot path:
+//     they delegate to the host classes and move words over the C ABI's copy calls.
+// Everything arithmetic on ciphertexts (Evaluator) runs in the CUDA library; nothing here computes on the CPU.
+//
+// Needs the reference's host headers on the include path (-I<troy>/src). Header-only; C++17; no CUDA headers needed.
+//
+// Reference interfaces mirrored (file:line under the reference tree):
+//   KernelProvider            src/kernelprovider.cuh:18-85
+//   EncryptionParametersCuda  src/encryptionparams_cuda.cuh
+//   SEALContextCuda           src/context_cuda.cuh:146-186
+//   CiphertextCuda            src/ciphertext_cuda.cuh:12-268
+//   KSwitchKeysCuda / RelinKeysCuda / GaloisKeysCuda   src/kswitchkeys_cuda.cuh:31-366, relinkeys_cuda.cuh, galoiskeys_cuda.cuh
+//   EvaluatorCuda             src/evaluator_cuda.cuh:17-440
+//   KeyGeneratorCuda / EncryptorCuda / DecryptorCuda    src/keygenerator_cuda.cuh, encryptor_cuda.cuh, decryptor_cuda.cuh
+#pragma once
+
+#include "troy_cpu.h" // the reference's host classes (troy::)
+
+#include "../troy_b200.h"
+
+#include <cmath>
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace troy {
+
+namespace b200 {
+
+// C ABI status -> the reference's exception types (SURVEY.md §8b "Errors")
+inline void check(int rc) {
+    if (rc == TROYB_OK) return;
+    const std::string msg = troyb_last_error();
+    switch (rc) {
+    case TROYB_E_INVALID_ARGUMENT:
+    case TROYB_E_NOT_INITIALIZED: throw std::invalid_argument(msg);
+    case TROYB_E_LOGIC: throw std::logic_error(msg);
+    case TROYB_E_OUT_OF_RANGE: throw std::out_of_range(msg);
+    default: throw std::runtime_error("CUDA error.");
+    }
+}
+
+// Owning device buffer of 64-bit words (util::DeviceArray<uint64_t>, src/utils/devicearray.cuh:90-200)
+class DeviceWords {
+public:
+    DeviceWords() = default;
+    explicit DeviceWords(std::size_t words) { allocate(words); }
+    DeviceWords(const DeviceWords &o) { *this = o; }
+    DeviceWords(DeviceWords &&o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+    DeviceWords &operator=(const DeviceWords &o) {
+        if (this == &o) return *this;
+        allocate(o.n_);
+        if (n_) check(troyb_copy_on_device(p_, o.p_, n_ * 8, nullptr));
+        return *this;
+    }
+    DeviceWords &operator=(DeviceWords &&o) noexcept {
+        if (this != &o) { release(); p_ = o.p_; n_ = o.n_; o.p_ = nullptr; o.n_ = 0; }
+        return *this;
+    }
+    ~DeviceWords() { release(); }
+    void allocate(std::size_t words) {
+        if (words == n_ && p_) return;
+        release();
+        if (words) { void *p = nullptr; check(troyb_malloc(&p, words * 8, nullptr)); p_ = static_cast<std::uint64_t *>(p); n_ = words; }
+    }
+    void upload(const std::uint64_t *h, std::size_t words, std::size_t at = 0) {
+        if (words) { check(troyb_copy_to_device(p_ + at, h, words * 8, nullptr)); check(troyb_stream_synchronize(nullptr)); }
+    }
+    void download(std::uint64_t *h, std::size_t words, std::size_t at = 0) const {
+        if (words) check(troyb_copy_to_host(h, p_ + at, words * 8, nullptr));
+    }
+    std::uint64_t *get() const { return p_; }
+    std::size_t size() const { return n_; }
+
+private:
+    void release() { if (p_) troyb_free(p_, nullptr); p_ = nullptr; n_ = 0; }
+    std::uint64_t *p_ = nullptr;
+    std::size_t n_ = 0;
+};
+
+} // namespace b200
+
+class KernelProvider {
+public:
+    static void initialize(int device = 0) { b200::check(troyb_initialize(device)); }
+    static bool initialized() { return troyb_initialized() != 0; }
+};
+
+class EncryptionParametersCuda {
+public:
+    EncryptionParametersCuda(SchemeType scheme = SchemeType::none) : host_(scheme) {}
+    EncryptionParametersCuda(const EncryptionParameters &host) : host_(host) {}
+    void setPolyModulusDegree(std::size_t n) { host_.setPolyModulusDegree(n); }
+    void setCoeffModulus(const std::vector<Modulus> &q) { host_.setCoeffModulus(q); }
+    void setPlainModulus(const Modulus &t) { host_.setPlainModulus(t); }
+    void setPlainModulus(std::uint64_t t) { host_.setPlainModulus(t); }
+    void setRandomGenerator(std::shared_ptr<UniformRandomGeneratorFactory> f) { host_.setRandomGenerator(std::move(f)); }
+    SchemeType scheme() const { return host_.scheme(); }
+    std::size_t polyModulusDegree() const { return host_.polyModulusDegree(); }
+    const std::vector<Modulus> &coeffModulus() const { return host_.coeffModulus(); }
+    const Modulus &plainModulus() const { return host_.plainModulus(); }
+    const ParmsID &parmsID() const { return host_.parmsID(); }
+    const EncryptionParameters &host() const { return host_; }
+    operator const EncryptionParameters &() const { return host_; }
+
+private:
+    EncryptionParameters host_;
+};
+
+class SEALContextCuda {
+public:
+    SEALContextCuda(const EncryptionParametersCuda &parms, bool expand_mod_chain = true, SecurityLevel sec = SecurityLevel::tc128)
+        : host_(std::make_shared<SEALContext>(parms.host(), expand_mod_chain, sec)) {
+        if (!host_->parametersSet()) throw std::invalid_argument("encryption parameters are not set correctly");
+        const auto &p = host_->keyContextData()->parms();
+        std::vector<std::uint64_t> q;
+        for (const auto &m : p.coeffModulus()) q.push_back(m.value());
+        const int scheme = p.scheme() == SchemeType::bfv ? TROYB_SCHEME_BFV : p.scheme() == SchemeType::ckks ? TROYB_SCHEME_CKKS : TROYB_SCHEME_BGV;
+        troyb_context *h = nullptr;
+        b200::check(troyb_context_create(scheme, p.polyModulusDegree(), q.data(), (int)q.size(),
+                                         p.scheme() == SchemeType::ckks ? 0 : p.plainModulus().value(), expand_mod_chain ? 1 : 0, &h));
+        handle_ = std::shared_ptr<troyb_context>(h, troyb_context_destroy);
+        for (auto cd = host_->firstContextData(); cd; cd = cd->nextContextData()) levels_.push_back(cd->parmsID());
+    }
+    // chain index of a parms_id (the C ABI's `level`); throws like the reference when the id is not in the chain
+    int levelOf(const ParmsID &id) const {
+        for (std::size_t i = 0; i < levels_.size(); i++) if (levels_[i] == id) return (int)i;
+        throw std::invalid_argument("encrypted is not valid for encryption parameters");
+    }
+    const ParmsID &parmsIDOf(int level) const { return levels_.at((std::size_t)level); }
+    std::size_t chainLength() const { return levels_.size(); }
+    auto getContextData(const ParmsID &id) const { return host_->getContextData(id); }
+    auto keyContextData() const { return host_->keyContextData(); }
+    auto firstContextData() const { return host_->firstContextData(); }
+    auto lastContextData() const { return host_->lastContextData(); }
+    const ParmsID &keyParmsID() const { return host_->keyParmsID(); }
+    const ParmsID &firstParmsID() const { return host_->firstParmsID(); }
+    const ParmsID &lastParmsID() const { return host_->lastParmsID(); }
+    bool parametersSet() const { return host_->parametersSet(); }
+    bool using_keyswitching() const { return host_->using_keyswitching(); }
+    const SEALContext &host() const { return *host_; }
+    operator const SEALContext &() const { return *host_; } // host encoders / key generator take the host context
+    troyb_context *handle() const { return handle_.get(); }
+
+private:
+    std::shared_ptr<SEALContext> host_;
+    std::shared_ptr<troyb_context> handle_;
+    std::vector<ParmsID> levels_;
+};
+
+// Host-side objects that never enter the hot path keep their host representation (the reference's PlaintextCuda /
+// PublicKeyCuda / SecretKeyCuda are device mirrors of data that only encode / encrypt / decrypt touch).
+class PlaintextCuda : public Plaintext {
+public:
+    using Plaintext::Plaintext;
+    PlaintextCuda() = default;
+    PlaintextCuda(const Plaintext &p) : Plaintext(p) {}
+    PlaintextCuda &operator=(const std::string &hex_poly) { Plaintext::operator=(hex_poly); return *this; }
+    PlaintextCuda &operator=(std::uint64_t c) { Plaintext::operator=(c); return *this; }
+    const Plaintext &cpu() const { return *this; }
+};
+class PublicKeyCuda : public PublicKey {
+public:
+    PublicKeyCuda() = default;
+    PublicKeyCuda(const PublicKey &k) : PublicKey(k) {}
+};
+class SecretKeyCuda : public SecretKey {
+public:
+    SecretKeyCuda() = default;
+    SecretKeyCuda(const SecretKey &k) : SecretKey(k) {}
+};
+// Encoders are host work in this build: the host classes, constructed from the device context.
+class CKKSEncoderCuda : public CKKSEncoder {
+public:
+    CKKSEncoderCuda(const SEALContextCuda &context) : CKKSEncoder(context.host()) {}
+};
+class BatchEncoderCuda : public BatchEncoder {
+public:
+    BatchEncoderCuda(const SEALContextCuda &context) : BatchEncoder(context.host()) {}
+};
+
+class CiphertextCuda {
+public:
+    CiphertextCuda() = default;
+    // upload (CiphertextCuda(const Ciphertext&), src/ciphertext_cuda.cuh:20-36)
+    CiphertextCuda(const Ciphertext &h)
+        : size_(h.size()), n_(h.polyModulusDegree()), limbs_(h.coeffModulusSize()), parms_id_(h.parmsID()), is_ntt_(h.isNttForm()),
+          scale_(h.scale()), correction_(h.correctionFactor()), data_(h.size() * h.polyModulusDegree() * h.coeffModulusSize()) {
+        data_.upload(h.data(), data_.size());
+    }
+    // capacity-only constructors (src/ciphertext_cuda.cuh:102-123): parameters are recorded, size stays 0
+    explicit CiphertextCuda(const SEALContextCuda &context) : CiphertextCuda(context, context.firstParmsID()) {}
+    explicit CiphertextCuda(const SEALContextCuda &context, const ParmsID &parms_id, std::size_t = 2) {
+        auto cd = context.getContextData(parms_id);
+        if (!cd) throw std::invalid_argument("parms_id is not valid for encryption parameters");
+        parms_id_ = parms_id;
+        n_ = cd->parms().polyModulusDegree();
+        limbs_ = cd->parms().coeffModulus().size();
+    }
+    // download (cpu / toHost, src/ciphertext_cuda.cuh:38-51); Ciphertext befriends CiphertextCuda (src/ciphertext.h:55)
+    Ciphertext cpu() const {
+        Ciphertext h;
+        h.parms_id_ = parms_id_;
+        h.is_ntt_form_ = is_ntt_;
+        h.size_ = size_;
+        h.poly_modulus_degree_ = n_;
+        h.coeff_modulus_size_ = limbs_;
+        h.scale_ = scale_;
+        h.correction_factor_ = correction_;
+        h.data_ = util::HostDynamicArray<std::uint64_t>(size_ * n_ * limbs_);
+        data_.download(h.data(), size_ * n_ * limbs_);
+        return h;
+    }
+    Ciphertext toHost() const { return cpu(); }
+    bool isTransparent() const { return cpu().isTransparent(); }
+
+    std::size_t size() const { return size_; }
+    std::size_t polyModulusDegree() const { return n_; }
+    std::size_t coeffModulusSize() const { return limbs_; }
+    std::size_t polyCoeffSize() const { return n_ * limbs_; }
+    ParmsID &parmsID() { return parms_id_; }
+    const ParmsID &parmsID() const { return parms_id_; }
+    bool &isNttForm() { return is_ntt_; }
+    bool isNttForm() const { return is_ntt_; }
+    double &scale() { return scale_; }
+    const double &scale() const { return scale_; }
+    std::uint64_t &correctionFactor() { return correction_; }
+    const std::uint64_t &correctionFactor() const { return correction_; }
+    std::uint64_t *data() { return data_.get(); }
+    const std::uint64_t *data() const { return data_.get(); }
+    std::uint64_t *data(std::size_t poly) { return data_.get() + poly * polyCoeffSize(); }
+    const std::uint64_t *data(std::size_t poly) const { return data_.get() + poly * polyCoeffSize(); }
+
+    // resize / reserve keep the first min(old, new) polynomials (src/ciphertext_cuda.cuh:68-152)
+    void resize(const SEALContextCuda &context, const ParmsID &parms_id, std::size_t size) {
+        auto cd = context.getContextData(parms_id);
+        if (!cd) throw std::invalid_argument("parms_id is not valid for encryption parameters");
+        const auto &p = cd->parms();
+        parms_id_ = parms_id;
+        resizeInternal(size, p.polyModulusDegree(), p.coeffModulus().size());
+    }
+    void resize(std::size_t size) { resizeInternal(size, n_, limbs_); }
+    void release() { *this = CiphertextCuda(); }
+
+    // used by the evaluator when an operation changes the limb count
+    void adopt(b200::DeviceWords &&data, std::size_t size, std::size_t n, std::size_t limbs) {
+        data_ = std::move(data); size_ = size; n_ = n; limbs_ = limbs;
+    }
+
+private:
+    void resizeInternal(std::size_t size, std::size_t n, std::size_t limbs) {
+        if ((size < 2 && size != 0) || size > 6) throw std::invalid_argument("invalid size");
+        if (n == n_ && limbs == limbs_ && size * n * limbs <= data_.size()) { size_ = size; return; }
+        b200::DeviceWords fresh(size * n * limbs);
+        if (n == n_ && limbs == limbs_) {
+            const std::size_t keep = std::min(size_, size) * n * limbs;
+            if (keep) b200::check(troyb_copy_on_device(fresh.get(), data_.get(), keep * 8, nullptr));
+        }
+        data_ = std::move(fresh);
+        size_ = size; n_ = n; limbs_ = limbs;
+    }
+    std::size_t size_ = 0, n_ = 0, limbs_ = 0;
+    ParmsID parms_id_ = parmsIDZero;
+    bool is_ntt_ = false;
+    double scale_ = 1.0;
+    std::uint64_t correction_ = 1;
+    b200::DeviceWords data_;
+};
+
+// keys()[index] = one key-switching key as device words [digit][2][key limbs][N]   (src/kswitchkeys_cuda.cuh:43-56,366)
+class KSwitchKeysCuda {
+public:
+    KSwitchKeysCuda() = default;
+    KSwitchKeysCuda(const KSwitchKeys &h) { assign(h); }
+    void assign(const KSwitchKeys &h) {
+        parms_id_ = h.parmsID();
+        keys_.clear();
+        keys_.resize(h.data().size());
+        for (std::size_t idx = 0; idx < h.data().size(); idx++) {
+            const auto &digits = h.data()[idx];
+            if (digits.empty()) continue;
+            const Ciphertext &first = digits[0].data();
+            const std::size_t per = first.size() * first.polyModulusDegree() * first.coeffModulusSize();
+            keys_[idx].allocate(per * digits.size());
+            for (std::size_t j = 0; j < digits.size(); j++) keys_[idx].upload(digits[j].data().data(), per, j * per);
+        }
+    }
+    std::size_t size() const { std::size_t c = 0; for (auto &k : keys_) c += k.size() ? 1 : 0; return c; }
+    const ParmsID &parmsID() const { return parms_id_; }
+    const std::uint64_t *key(std::size_t index) const {
+        if (index >= keys_.size() || !keys_[index].size()) throw std::invalid_argument("keyswitching key does not exist");
+        return keys_[index].get();
+    }
+    bool hasIndex(std::size_t index) const { return index < keys_.size() && keys_[index].size() != 0; }
+
+protected:
+    ParmsID parms_id_ = parmsIDZero;
+    std::vector<b200::DeviceWords> keys_;
+};
+
+class RelinKeysCuda : public KSwitchKeysCuda {
+public:
+    RelinKeysCuda() = default;
+    RelinKeysCuda(const RelinKeys &h) : KSwitchKeysCuda(h) {}
+    static std::size_t getIndex(std::size_t key_power) {
+        if (key_power < 2) throw std::invalid_argument("key_power cannot be less than 2");
+        return key_power - 2;
+    }
+    bool hasKey(std::size_t key_power) const { return hasIndex(getIndex(key_power)); }
+};
+
+class GaloisKeysCuda : public KSwitchKeysCuda {
+public:
+    GaloisKeysCuda() = default;
+    GaloisKeysCuda(const GaloisKeys &h) : KSwitchKeysCuda(h) {}
+    static std::size_t getIndex(std::uint32_t galois_elt) { return util::GaloisTool::GetIndexFromElt(galois_elt); }
+    bool hasKey(std::uint32_t galois_elt) const { return hasIndex(getIndex(galois_elt)); }
+};
+
+// Key generation runs on the host in the reference as well (src/keygenerator_cuda.cuh:36-60); results are uploaded.
+class KeyGeneratorCuda {
+public:
+    KeyGeneratorCuda(const SEALContextCuda &context) : gen_(context.host()) {}
+    KeyGeneratorCuda(const SEALContextCuda &context, const SecretKey &sk) : gen_(context.host(), sk) {}
+    SecretKeyCuda secretKey() const { return SecretKeyCuda(gen_.secretKey()); }
+    void createPublicKey(PublicKeyCuda &dst) const { PublicKey pk; gen_.createPublicKey(pk); dst = PublicKeyCuda(pk); }
+    void createRelinKeys(RelinKeysCuda &dst) { RelinKeys k; gen_.createRelinKeys(k); dst = RelinKeysCuda(k); }
+    void createGaloisKeys(const std::vector<std::uint32_t> &elts, GaloisKeysCuda &dst) { GaloisKeys k; gen_.createGaloisKeys(elts, k); dst = GaloisKeysCuda(k); }
+    void createGaloisKeys(const std::vector<int> &steps, GaloisKeysCuda &dst) { GaloisKeys k; gen_.createGaloisKeys(steps, k); dst = GaloisKeysCuda(k); }
+    void createGaloisKeys(GaloisKeysCuda &dst) { GaloisKeys k; gen_.createGaloisKeys(k); dst = GaloisKeysCuda(k); }
+    KeyGenerator &host() { return gen_; }
+
+private:
+    KeyGenerator gen_;
+};
+
+// Encryption / decryption are host work outside the hot path: host class + copy.
+class EncryptorCuda {
+public:
+    EncryptorCuda(const SEALContextCuda &context, const PublicKey &pk) : enc_(context.host(), pk) {}
+    EncryptorCuda(const SEALContextCuda &context, const SecretKey &sk) : enc_(context.host(), sk) {}
+    EncryptorCuda(const SEALContextCuda &context, const PublicKey &pk, const SecretKey &sk) : enc_(context.host(), pk, sk) {}
+    void encrypt(const Plaintext &plain, CiphertextCuda &dst) const { Ciphertext c; enc_.encrypt(plain, c); dst = CiphertextCuda(c); }
+    void encryptSymmetric(const Plaintext &plain, CiphertextCuda &dst) const { Ciphertext c; enc_.encryptSymmetric(plain, c); dst = CiphertextCuda(c); }
+    void encryptZero(CiphertextCuda &dst) const { Ciphertext c; enc_.encryptZero(c); dst = CiphertextCuda(c); }
+    void encryptZero(ParmsID id, CiphertextCuda &dst) const { Ciphertext c; enc_.encryptZero(id, c); dst = CiphertextCuda(c); }
+
+private:
+    Encryptor enc_;
+};
+
+class DecryptorCuda {
+public:
+    DecryptorCuda(const SEALContextCuda &context, const SecretKey &sk) : dec_(context.host(), sk) {}
+    void decrypt(const CiphertextCuda &ct, Plaintext &dst) { dec_.decrypt(ct.cpu(), dst); }
+    int invariantNoiseBudget(const CiphertextCuda &ct) { return dec_.invariantNoiseBudget(ct.cpu()); }
+
+private:
+    Decryptor dec_;
+};
+
+class EvaluatorCuda {
+public:
+    EvaluatorCuda(const SEALContextCuda &context) : context_(context) {}
+
+    // ---- add / sub / negate (src/evaluator_cuda.cu:143-260)
+    void negateInplace(CiphertextCuda &ct) const {
+        b200::check(troyb_negate(h(), level(ct), ct.data(), ct.data(), ct.size(), nullptr));
+    }
+    void negate(const CiphertextCuda &a, CiphertextCuda &dst) const { dst = a; negateInplace(dst); }
+    void addInplace(CiphertextCuda &a, const CiphertextCuda &b) const { addSub(a, b, false); }
+    void subInplace(CiphertextCuda &a, const CiphertextCuda &b) const { addSub(a, b, true); }
+    void add(const CiphertextCuda &a, const CiphertextCuda &b, CiphertextCuda &dst) const {
+        if (&b == &dst) addInplace(dst, a);
+        else { dst = a; addInplace(dst, b); }
+    }
+    void sub(const CiphertextCuda &a, const CiphertextCuda &b, CiphertextCuda &dst) const {
+        if (&b == &dst) { subInplace(dst, a); negateInplace(dst); }
+        else { dst = a; subInplace(dst, b); }
+    }
+    void addMany(const std::vector<CiphertextCuda> &cts, CiphertextCuda &dst) const {
+        if (cts.empty()) throw std::invalid_argument("encrypteds cannot be empty");
+        for (auto &c : cts) if (&c == &dst) throw std::invalid_argument("encrypteds must be different from destination");
+        dst = cts[0];
+        for (std::size_t i = 1; i < cts.size(); i++) addInplace(dst, cts[i]);
+    }
+
+    // ---- multiply / square (src/evaluator_cuda.cu:262-701)
+    void multiplyInplace(CiphertextCuda &a, const CiphertextCuda &b) const {
+        if (a.parmsID() != b.parmsID()) throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
+        const SchemeType s = scheme();
+        if (s == SchemeType::ckks && !(a.isNttForm() && b.isNttForm())) throw std::invalid_argument("encrypted1 or encrypted2 must be in NTT form");
+        if (s != SchemeType::ckks && (a.isNttForm() || b.isNttForm())) throw std::invalid_argument("encrypted1 or encrypted2 cannot be in NTT form");
+        const int lv = level(a);
+        const std::size_t a_size = a.size(), b_size = b.size(), out = a_size + b_size - 1;
+        double new_scale = a.scale() * b.scale();
+        if (s == SchemeType::ckks && !scaleWithinBounds(new_scale, a.parmsID())) throw std::invalid_argument("scale out of bounds");
+        const bool square = &a == &b;
+        const std::size_t stride = out * a.polyCoeffSize();
+        a.resize(out); // keeps the first a_size polynomials
+        const std::uint64_t *pb = square ? a.data() : b.data();
+        b200::check(troyb_multiply(h(), lv, a.data(), a_size, stride, pb, b_size, square ? stride : b_size * b.polyCoeffSize(), a.data(),
+                                   stride, 1, nullptr));
+        if (s == SchemeType::ckks) a.scale() = new_scale;
+        if (s == SchemeType::bgv) {
+            const std::uint64_t t = context_.firstContextData()->parms().plainModulus().value();
+            a.correctionFactor() = (std::uint64_t)((unsigned __int128)a.correctionFactor() * b.correctionFactor() % t);
+        }
+    }
+    void multiply(const CiphertextCuda &a, const CiphertextCuda &b, CiphertextCuda &dst) const {
+        if (&b == &dst) multiplyInplace(dst, a);
+        else { dst = a; multiplyInplace(dst, b); }
+    }
+    void squareInplace(CiphertextCuda &a) const { multiplyInplace(a, a); }
+    void square(const CiphertextCuda &a, CiphertextCuda &dst) const { dst = a; squareInplace(dst); }
+
+    // ---- key switching (src/evaluator_cuda.cu:703-747, 1163-1378)
+    void relinearizeInplace(CiphertextCuda &ct, const RelinKeysCuda &rlk) const {
+        if (ct.size() == 2) return;
+        if (ct.size() != 3) throw std::logic_error("relinearization of size > 3 is outside the ported path");
+        checkKeySwitch(ct, rlk);
+        if (!rlk.hasKey(2)) throw std::invalid_argument("not enough relinearization keys");
+        b200::check(troyb_relinearize(h(), level(ct), ct.data(), 3 * ct.polyCoeffSize(), rlk.key(RelinKeysCuda::getIndex(2)), 1, nullptr));
+        ct.resize(2);
+    }
+    void relinearize(const CiphertextCuda &ct, const RelinKeysCuda &rlk, CiphertextCuda &dst) const { dst = ct; relinearizeInplace(dst, rlk); }
+
+    // ---- Galois / rotations (src/evaluator_cuda.cu:2024-2176)
+    void applyGaloisInplace(CiphertextCuda &ct, std::uint32_t elt, const GaloisKeysCuda &gk) const {
+        if (gk.parmsID() != context_.keyParmsID()) throw std::invalid_argument("galois_keys is not valid for encryption parameters");
+        const std::size_t n = ct.polyModulusDegree();
+        if (!(elt & 1) || elt >= 2 * n) throw std::invalid_argument("Galois element is not valid");
+        if (ct.size() > 2) throw std::invalid_argument("encrypted size must be 2");
+        if (!gk.hasKey(elt)) throw std::invalid_argument("Galois key not present");
+        checkKeySwitch(ct, gk);
+        b200::check(troyb_apply_galois(h(), level(ct), ct.data(), 2 * ct.polyCoeffSize(), elt, gk.key(GaloisKeysCuda::getIndex(elt)), 1, nullptr));
+    }
+    void applyGalois(const CiphertextCuda &ct, std::uint32_t elt, const GaloisKeysCuda &gk, CiphertextCuda &dst) const { dst = ct; applyGaloisInplace(dst, elt, gk); }
+    void rotateRowsInplace(CiphertextCuda &ct, int steps, const GaloisKeysCuda &gk) const {
+        if (scheme() != SchemeType::bfv && scheme() != SchemeType::bgv) throw std::logic_error("unsupported scheme");
+        rotateInternal(ct, steps, gk);
+    }
+    void rotateRows(const CiphertextCuda &ct, int steps, const GaloisKeysCuda &gk, CiphertextCuda &dst) const { dst = ct; rotateRowsInplace(dst, steps, gk); }
+    void rotateColumnsInplace(CiphertextCuda &ct, const GaloisKeysCuda &gk) const {
+        if (scheme() != SchemeType::bfv && scheme() != SchemeType::bgv) throw std::logic_error("unsupported scheme");
+        applyGaloisInplace(ct, eltFromStep(0), gk);
+    }
+    void rotateColumns(const CiphertextCuda &ct, const GaloisKeysCuda &gk, CiphertextCuda &dst) const { dst = ct; rotateColumnsInplace(dst, gk); }
+    void rotateVectorInplace(CiphertextCuda &ct, int steps, const GaloisKeysCuda &gk) const {
+        if (scheme() != SchemeType::ckks) throw std::logic_error("unsupported scheme");
+        rotateInternal(ct, steps, gk);
+    }
+    void rotateVector(const CiphertextCuda &ct, int steps, const GaloisKeysCuda &gk, CiphertextCuda &dst) const { dst = ct; rotateVectorInplace(dst, steps, gk); }
+    void complexConjugateInplace(CiphertextCuda &ct, const GaloisKeysCuda &gk) const {
+        if (scheme() != SchemeType::ckks) throw std::logic_error("unsupported scheme");
+        applyGaloisInplace(ct, eltFromStep(0), gk);
+    }
+    void complexConjugate(const CiphertextCuda &ct, const GaloisKeysCuda &gk, CiphertextCuda &dst) const { dst = ct; complexConjugateInplace(dst, gk); }
+
+    // ---- rescale / modulus switching (src/evaluator_cuda.cu:749-1010, 1380)
+    void rescaleToNext(const CiphertextCuda &ct, CiphertextCuda &dst) const {
+        if (scheme() != SchemeType::ckks) throw std::invalid_argument("unsupported operation for scheme type");
+        scaleToNext(ct, dst);
+    }
+    void rescaleToNextInplace(CiphertextCuda &ct) const { CiphertextCuda out; rescaleToNext(ct, out); ct = std::move(out); }
+    void rescaleToInplace(CiphertextCuda &ct, const ParmsID &target) const {
+        const int want = context_.levelOf(target);
+        if (level(ct) > want) throw std::invalid_argument("cannot switch to higher level modulus");
+        while (level(ct) < want) rescaleToNextInplace(ct);
+    }
+    void modSwitchToNext(const CiphertextCuda &ct, CiphertextCuda &dst) const {
+        if (scheme() != SchemeType::ckks) { scaleToNext(ct, dst); return; }
+        // CKKS: drop the last limb (modSwitchDropToNext, src/evaluator_cuda.cu:826-880)
+        const int lv = level(ct);
+        if (lv + 1 >= (int)context_.chainLength()) throw std::invalid_argument("end of modulus switching chain reached");
+        const std::size_t n = ct.polyModulusDegree(), L = ct.coeffModulusSize();
+        b200::DeviceWords out(ct.size() * (L - 1) * n);
+        for (std::size_t p = 0; p < ct.size(); p++)
+            b200::check(troyb_copy_on_device(out.get() + p * (L - 1) * n, ct.data(p), (L - 1) * n * 8, nullptr));
+        CiphertextCuda r = metaOf(ct);
+        r.adopt(std::move(out), ct.size(), n, L - 1);
+        r.parmsID() = context_.parmsIDOf(lv + 1);
+        dst = std::move(r);
+    }
+    void modSwitchToNextInplace(CiphertextCuda &ct) const { CiphertextCuda out; modSwitchToNext(ct, out); ct = std::move(out); }
+    void modSwitchToInplace(CiphertextCuda &ct, const ParmsID &target) const {
+        const int want = context_.levelOf(target);
+        if (level(ct) > want) throw std::invalid_argument("cannot switch to higher level modulus");
+        while (level(ct) < want) modSwitchToNextInplace(ct);
+    }
+
+    // ---- NTT transforms (src/evaluator_cuda.cu:1950-2022)
+    void transformToNttInplace(CiphertextCuda &ct) const {
+        if (ct.isNttForm()) throw std::invalid_argument("encrypted is already in NTT form");
+        b200::check(troyb_ntt_forward(h(), level(ct), ct.data(), ct.size(), nullptr));
+        ct.isNttForm() = true;
+    }
+    void transformFromNttInplace(CiphertextCuda &ct) const {
+        if (!ct.isNttForm()) throw std::invalid_argument("encrypted_ntt is not in NTT form");
+        b200::check(troyb_ntt_inverse(h(), level(ct), ct.data(), ct.size(), nullptr));
+        ct.isNttForm() = false;
+    }
+    void transformToNtt(const CiphertextCuda &ct, CiphertextCuda &dst) const { dst = ct; transformToNttInplace(dst); }
+    void transformFromNtt(const CiphertextCuda &ct, CiphertextCuda &dst) const { dst = ct; transformFromNttInplace(dst); }
+
+private:
+    troyb_context *h() const { return context_.handle(); }
+    int level(const CiphertextCuda &ct) const { return context_.levelOf(ct.parmsID()); }
+    SchemeType scheme() const { return context_.firstContextData()->parms().scheme(); }
+    std::uint32_t eltFromStep(int step) const { std::uint32_t e = 0; b200::check(troyb_galois_elt_from_step(h(), step, &e)); return e; }
+    static CiphertextCuda metaOf(const CiphertextCuda &ct) {
+        CiphertextCuda r;
+        r.parmsID() = ct.parmsID(); r.isNttForm() = ct.isNttForm(); r.scale() = ct.scale(); r.correctionFactor() = ct.correctionFactor();
+        return r;
+    }
+    // isScaleWithinBounds, src/evaluator_cuda.cu:32-51
+    bool scaleWithinBounds(double scale, const ParmsID &id) const {
+        auto cd = context_.getContextData(id);
+        int bound = scheme() == SchemeType::ckks ? cd->totalCoeffModulusBitCount() : cd->parms().plainModulus().bitCount();
+        return !(scale <= 0 || (int)std::log2(scale) >= bound);
+    }
+    void checkKeySwitch(const CiphertextCuda &ct, const KSwitchKeysCuda &keys) const {
+        if (!context_.using_keyswitching()) throw std::logic_error("keyswitching is not supported by the context");
+        if (keys.parmsID() != context_.keyParmsID()) throw std::invalid_argument("parameter mismatch");
+        const SchemeType s = scheme();
+        if (s == SchemeType::bfv && ct.isNttForm()) throw std::invalid_argument("BFV encrypted cannot be in NTT form");
+        if (s == SchemeType::ckks && !ct.isNttForm()) throw std::invalid_argument("CKKS encrypted must be in NTT form");
+        if (s == SchemeType::bgv && ct.isNttForm()) throw std::invalid_argument("BGV encrypted cannot be in NTT form");
+    }
+    void addSub(CiphertextCuda &a, const CiphertextCuda &b, bool sub) const {
+        if (a.parmsID() != b.parmsID()) throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
+        if (a.isNttForm() != b.isNttForm()) throw std::invalid_argument("NTT form mismatch");
+        if (scheme() == SchemeType::bgv && a.correctionFactor() != b.correctionFactor()) {
+            // balance the correction factors with scalar multiplications first (src/evaluator_cuda.cu:171-190)
+            const std::uint64_t t = context_.firstContextData()->parms().plainModulus().value();
+            std::uint64_t f, e1, e2;
+            balanceCorrectionFactors(a.correctionFactor(), b.correctionFactor(), t, f, e1, e2);
+            CiphertextCuda b2 = b;
+            b200::check(troyb_multiply_scalar(h(), level(a), a.data(), e1, a.data(), a.size(), nullptr));
+            b200::check(troyb_multiply_scalar(h(), level(b2), b2.data(), e2, b2.data(), b2.size(), nullptr));
+            a.correctionFactor() = f;
+            b2.correctionFactor() = f;
+            addSub(a, b2, sub);
+            return;
+        }
+        if (scheme() == SchemeType::ckks && a.scale() != b.scale() && std::fabs(a.scale() - b.scale()) > 1e-15 * std::fabs(a.scale()))
+            throw std::invalid_argument("scale mismatch");
+        const int lv = level(a);
+        const std::size_t a_old = a.size(), mn = std::min(a.size(), b.size()), mx = std::max(a.size(), b.size());
+        a.resize(mx);
+        b200::check((sub ? troyb_sub : troyb_add)(h(), lv, a.data(), b.data(), a.data(), mn, nullptr));
+        if (a_old < b.size()) {
+            if (!sub) b200::check(troyb_copy_on_device(a.data(a_old), b.data(a_old), (b.size() - a_old) * a.polyCoeffSize() * 8, nullptr));
+            else b200::check(troyb_negate(h(), lv, b.data(a_old), a.data(a_old), b.size() - a_old, nullptr));
+        }
+    }
+    // balanceCorrectionFactors (src/evaluator_cuda.cu:53-114): the pair (e1, e2) with e1 f1 = e2 f2 (mod t) of least
+    // |e1| + |e2| among the remainders of the extended Euclid run on (t, f2 / f1)
+    static void balanceCorrectionFactors(std::uint64_t f1, std::uint64_t f2, std::uint64_t t, std::uint64_t &factor, std::uint64_t &e1,
+                                         std::uint64_t &e2) {
+        typedef unsigned __int128 u128;
+        const std::uint64_t half = t / 2;
+        auto bal = [&](std::uint64_t x) { return x > half ? (std::int64_t)(t - x) : (std::int64_t)x; }; // |balanced x|
+        auto sum_abs = [&](std::uint64_t x, std::uint64_t y) { return bal(x) + bal(y); };
+        auto gcd = [](std::uint64_t x, std::uint64_t y) { while (y) { std::uint64_t r = x % y; x = y; y = r; } return x; };
+        std::uint64_t inv = 0;
+        if (!util::tryInvertUintMod(f1 % t, t, inv)) throw std::logic_error("invalid correction factor1");
+        const std::uint64_t ratio = (std::uint64_t)((u128)inv * f2 % t);
+        e1 = ratio; e2 = 1;
+        std::int64_t best = sum_abs(e1, e2);
+        std::int64_t prev_a = (std::int64_t)t, prev_b = 0, a = (std::int64_t)ratio, b = 1;
+        while (a != 0) {
+            const std::int64_t q = prev_a / a, ra = prev_a % a;
+            prev_a = a; a = ra;
+            const std::int64_t rb = prev_b - b * q;
+            prev_b = b; b = rb;
+            const std::uint64_t a_mod = (std::uint64_t)a % t; // a >= 0 throughout
+            std::uint64_t b_mod = (std::uint64_t)(b < 0 ? -b : b) % t;
+            if (b < 0 && b_mod) b_mod = t - b_mod;
+            if (a_mod != 0 && gcd(a_mod, t) == 1) {
+                const std::int64_t s = sum_abs(a_mod, b_mod);
+                if (s < best) { best = s; e1 = a_mod; e2 = b_mod; }
+            }
+        }
+        factor = (std::uint64_t)((u128)e1 * f1 % t);
+    }
+    // rotateInternal with the NAF fallback for missing keys (src/evaluator_cuda.cu:2119-2176)
+    void rotateInternal(CiphertextCuda &ct, int steps, const GaloisKeysCuda &gk) const {
+        if (gk.parmsID() != context_.keyParmsID()) throw std::invalid_argument("galois_keys is not valid for encryption parameters");
+        if (steps == 0) return;
+        const std::uint32_t elt = eltFromStep(steps);
+        if (gk.hasKey(elt)) { applyGaloisInplace(ct, elt, gk); return; }
+        std::vector<int> naf = util::naf(steps);
+        if (naf.size() == 1) throw std::invalid_argument("Galois key not present");
+        const int half = (int)(ct.polyModulusDegree() >> 1);
+        for (int s : naf) if (std::abs(s) != half) rotateInternal(ct, s, gk);
+    }
+    // modSwitchScaleToNext (src/evaluator_cuda.cu:749-825)
+    void scaleToNext(const CiphertextCuda &ct, CiphertextCuda &dst) const {
+        const SchemeType s = scheme();
+        const int lv = level(ct);
+        if (lv + 1 >= (int)context_.chainLength()) throw std::invalid_argument("end of modulus switching chain reached");
+        if (s == SchemeType::ckks && !ct.isNttForm()) throw std::invalid_argument("CKKS encrypted must be in NTT form");
+        if (s != SchemeType::ckks && ct.isNttForm()) throw std::invalid_argument(s == SchemeType::bfv ? "BFV encrypted cannot be in NTT form" : "BGV encrypted cannot be in NTT form");
+        const std::size_t n = ct.polyModulusDegree(), L = ct.coeffModulusSize();
+        b200::DeviceWords out(ct.size() * (L - 1) * n);
+        b200::check(troyb_mod_switch_scale_to_next(h(), lv, ct.data(), ct.size() * L * n, out.get(), ct.size() * (L - 1) * n, ct.size(), 1, nullptr));
+        const auto &q = context_.getContextData(ct.parmsID())->parms().coeffModulus();
+        const std::uint64_t q_last = q.back().value();
+        CiphertextCuda r = metaOf(ct);
+        r.adopt(std::move(out), ct.size(), n, L - 1);
+        r.parmsID() = context_.parmsIDOf(lv + 1);
+        if (s == SchemeType::ckks) r.scale() = ct.scale() / static_cast<double>(q_last);
+        if (s == SchemeType::bgv) {
+            const std::uint64_t t = context_.firstContextData()->parms().plainModulus().value();
+            std::uint64_t inv = 0;
+            if (!util::tryInvertUintMod(q_last % t, t, inv)) throw std::logic_error("invalid plain modulus");
+            r.correctionFactor() = (std::uint64_t)((unsigned __int128)ct.correctionFactor() * inv % t);
+        }
+        dst = std::move(r);
+    }
+
+    SEALContextCuda context_;
+};
+
+} // namespace troy
+
+namespace troyn {
+using troy::ParmsID;
+using troy::SchemeType;
+using troy::SecurityLevel;
+using troy::Modulus;
+using troy::CoeffModulus;
+using troy::PlainModulus;
+using EncryptionParameters = troy::EncryptionParametersCuda;
+using SEALContext = troy::SEALContextCuda;
+using Plaintext = troy::PlaintextCuda;
+using Ciphertext = troy::CiphertextCuda;
+using Encryptor = troy::EncryptorCuda;
+using Decryptor = troy::DecryptorCuda;
+using Evaluator = troy::EvaluatorCuda;
+using KeyGenerator = troy::KeyGeneratorCuda;
+using PublicKey = troy::PublicKeyCuda;
+using SecretKey = troy::SecretKeyCuda;
+using KSwitchKeys = troy::KSwitchKeysCuda;
+using RelinKeys = troy::RelinKeysCuda;
+using GaloisKeys = troy::GaloisKeysCuda;
+using CKKSEncoder = troy::CKKSEncoderCuda;
+using BatchEncoder = troy::BatchEncoderCuda;
+using KernelProvider = troy::KernelProvider;
+} // namespace troyn

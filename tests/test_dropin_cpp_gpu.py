@@ -1,0 +1,33 @@
+"""`-m gpu`: the C++ drop-in layer (include/troyn/troy_cuda.cuh over libtroy_b200.so).
+
+tests/cpp/_build/troyn_dropin_tests is a gtest binary built by tests/cpp/build_dropin_tests.py from (1) the reference's own
+CUDA tests for the hot path (test/evaluator_cuda.cu, compiled where they lie, only the `troy_cuda.cuh` they include is
+ours) and (2) tests/cpp/dropin_parity.cpp, which compares every output word with the reference's CPU evaluator."""
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "cpp", "_build", "troyn_dropin_tests")
+
+
+def _run(filt):
+    if not os.path.exists(BIN):
+        pytest.skip("tests/cpp/_build/troyn_dropin_tests not built (run __graft_entry__.build() where /root/reference exists)")
+    r = subprocess.run([BIN, f"--gtest_filter={filt}"], capture_output=True, text=True, timeout=1500)
+    tail = "\n".join((r.stdout + r.stderr).splitlines()[-40:])
+    assert r.returncode == 0, tail
+    assert "[  PASSED  ]" in r.stdout, tail
+    return r.stdout
+
+
+def test_word_for_word_parity_through_the_cpp_layer():
+    out = _run("DropInParity.*")
+    assert "3 tests" in out
+
+
+def test_reference_cuda_tests_pass_against_the_drop_in():
+    out = _run("EvaluatorCudaTest.*")
+    assert "[  FAILED  ]" not in out

@@ -167,3 +167,27 @@ def test_error_behaviour(cuda_lib):
         bad.set_poly_modulus_degree(4096)
         bad.set_coeff_modulus([q[0], q[0]])
         tb.SEALContextCuda(bad)
+
+
+def test_bgv_add_sub_with_different_correction_factors(ref, cuda_lib):
+    """BGV add / sub of ciphertexts whose correction factors differ: the factors are balanced with scalar
+    multiplications first (src/evaluator_cuda.cu:53-114, 171-190; kMultiplyPolyScalarCoeffmod)."""
+    from common import assert_same, make_pair, random_ct_words, upload_keys
+    tb = cuda_lib
+    n = 4096
+    rc, ctx = make_pair(ref, tb, ref.BGV, n, [40, 36, 36, 40])
+    rlk, gk, d_rlk, d_gk = upload_keys(tb, ctx, rc, ref)
+    ev = tb.EvaluatorCuda(ctx)
+    rng = np.random.default_rng(31)
+    w = random_ct_words(rc, 0, 2, n, rng)
+    a, ra = tb.CiphertextCuda.from_host(ctx, w, 0, False), rc.ciphertext(w, 0, False, 1.0)
+    ev.mod_switch_to_next_inplace(a); rc.eval(ref.OP_MODSWITCH_NEXT, ra)      # correction factor becomes q_last^-1 mod t
+    sq, rsq = a.clone(), ra.clone()
+    ev.square_inplace(sq); rc.eval(ref.OP_SQUARE, rsq)
+    ev.relinearize_inplace(sq, d_rlk); rc.eval(ref.OP_RELIN, rsq, keys=rlk)  # correction factor squared
+    assert sq.correction_factor != a.correction_factor
+    s2, rs2 = sq.clone(), rsq.clone()
+    ev.add_inplace(sq, a); rc.eval(ref.OP_ADD, rsq, ra)
+    assert_same(sq, rsq, "BGV add with correction-factor balancing")
+    ev.sub_inplace(s2, a); rc.eval(ref.OP_SUB, rs2, ra)
+    assert_same(s2, rs2, "BGV sub with correction-factor balancing")

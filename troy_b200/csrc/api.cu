@@ -507,13 +507,14 @@ int troyb_ntt_inverse_key(troyb_context *ctx, uint64_t *d_data, size_t n_polys, 
 }
 
 static int addsub(troyb_context *ctx, int level, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n_polys,
-                  void *stream) {
+                  void *stream, uint64_t scalar = 0) {
     API_BEGIN
     need_init();
     Context *c = C(ctx);
     u32 L = (u32)level_limbs(c, level);
     EltAddSub k{};
     k.op = op;
+    k.scalar = scalar;
     k.logN = c->logN;
     k.mods = c->d_mods;
     k.map = c->map_prefix(L);
@@ -533,6 +534,9 @@ int troyb_sub(troyb_context *ctx, int level, const uint64_t *a, const uint64_t *
 }
 int troyb_negate(troyb_context *ctx, int level, const uint64_t *a, uint64_t *out, size_t n, void *st) {
     return addsub(ctx, level, 2, a, a, out, n, st);
+}
+int troyb_multiply_scalar(troyb_context *ctx, int level, const uint64_t *a, uint64_t scalar, uint64_t *out, size_t n, void *st) {
+    return addsub(ctx, level, 3, a, a, out, n, st, scalar);
 }
 
 int troyb_multiply(troyb_context *ctx, int level, const uint64_t *d_a, size_t a_size, size_t a_stride, const uint64_t *d_b,

@@ -15,12 +15,14 @@ TB_D void mac128(u64 &lo, u64 &hi, u64 a, u64 b) {
     hi += ph + (lo < pl);
 }
 
-// ---- add / sub / negate -----------------------------------------------------------------------------------
+// ---- add / sub / negate / scalar multiply -------------------------------------------------------------------
 // kAddPolyCoeffmod / kSubPolyCoeffmod / kNegatePolyCoeffmod   src/kernelutils.cu:30-58, 505-535, 300-328
+// kMultiplyPolyScalarCoeffmod                                 src/kernelutils.cu:272-298
 struct EltAddSub {
     static constexpr int kThreads = kEltThreads;
-    const char *name() const { return "elt_add_sub_negate"; }
-    int op; // 0 add, 1 sub, 2 negate
+    const char *name() const { return "elt_add_sub_negate_scale"; }
+    int op; // 0 add, 1 sub, 2 negate, 3 multiply by `scalar`
+    u64 scalar;
     int logN;
     const ModDev *mods;
     LimbMap map;
@@ -33,12 +35,14 @@ struct EltAddSub {
             u64 idx = (u64)bid * kThreads + t;
             if (idx < total) {
                 u32 limb = (u32)((idx >> logN) % n_limbs);
-                u64 p = mods[map.idx[limb]].p;
+                const ModDev &m = mods[map.idx[limb]];
+                u64 p = m.p;
                 u64 x = a[idx];
                 u64 r;
                 if (op == 0) r = addmod(x, b[idx], p);
                 else if (op == 1) r = submod(x, b[idx], p);
-                else r = negmod(x, p);
+                else if (op == 2) r = negmod(x, p);
+                else r = mulmod_barrett(x, barrett64(scalar, p, m.ratio1), p, m.ratio0, m.ratio1);
                 out[idx] = r;
             }
         })

@@ -359,6 +359,29 @@ class GaloisKeysCuda(KSwitchKeysCuda):
         return self.data(self.get_index(galois_elt))
 
 
+def _balance_correction_factors(f1, f2, t):
+    """balanceCorrectionFactors, src/evaluator_cuda.cu:53-114: the pair (e1, e2) with e1 f1 = e2 f2 (mod t) of least
+    |e1| + |e2| among the remainders of the extended Euclid run on (t, f2 / f1). Returns (new factor, e1, e2)."""
+    half = t // 2
+
+    def sum_abs(x, y):
+        return abs(x - t if x > half else x) + abs(y - t if y > half else y)
+
+    ratio = pow(f1, -1, t) * f2 % t
+    e1, e2, best = ratio, 1, sum_abs(ratio, 1)
+    prev_a, prev_b, a, b = t, 0, ratio, 1
+    while a != 0:
+        q = prev_a // a
+        prev_a, a = a, prev_a % a
+        prev_b, b = b, prev_b - b * q
+        a_mod, b_mod = a % t, (abs(b) % t if b >= 0 else (t - abs(b) % t) % t)
+        if a_mod != 0 and math.gcd(a_mod, t) == 1:
+            s = sum_abs(a_mod, b_mod)
+            if s < best:
+                best, e1, e2 = s, a_mod, b_mod
+    return e1 * f1 % t, e1, e2
+
+
 def _naf(value):
     """src/utils/numth.h:16-36."""
     res = []
@@ -410,8 +433,15 @@ class EvaluatorCuda:
 
     def _addsub(self, name, a, b):
         self._same_parms(a, b)
-        if a.correction_factor != b.correction_factor:
-            raise TroyLogicError("BGV correction-factor balancing is outside the ported path (SURVEY.md §8f)")
+        if self.context.scheme == BGV and a.correction_factor != b.correction_factor:
+            # balance the correction factors with scalar multiplications first (src/evaluator_cuda.cu:171-190)
+            f, e1, e2 = _balance_correction_factors(a.correction_factor, b.correction_factor, self.context.parms.plain_modulus)
+            b = b.clone()
+            for ct, e in ((a, e1), (b, e2)):
+                for i in range(ct.batch):
+                    _L().call("troyb_multiply_scalar", self._h(), ct.parms_id, _vp(ct.ptr(0, i)), e, _vp(ct.ptr(0, i)), ct.size,
+                              self._s())
+                ct.correction_factor = f
         if self.context.scheme == CKKS and not math.isclose(a.scale, b.scale, rel_tol=1e-15):
             raise TroyInvalidArgument("scale mismatch")
         mn, mx = min(a.size, b.size), max(a.size, b.size)

@@ -66,6 +66,7 @@ _SIGNATURES = {
     "troyb_add": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _sz, _vp]),
     "troyb_sub": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _sz, _vp]),
     "troyb_negate": (C.c_int, [_vp, C.c_int, _vp, _vp, _sz, _vp]),
+    "troyb_multiply_scalar": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64, _vp, _sz, _vp]),
     "troyb_multiply": (C.c_int, [_vp, C.c_int, _vp, _sz, _sz, _vp, _sz, _sz, _vp, _sz, _sz, _vp]),
     "troyb_switch_key": (C.c_int, [_vp, C.c_int, _vp, _sz, _vp, _sz, _vp, _sz, _vp]),
     "troyb_relinearize": (C.c_int, [_vp, C.c_int, _vp, _sz, _vp, _sz, _vp]),
