@@ -159,36 +159,42 @@ void ntt_plain(const Context *ctx, bool inverse, const LimbMap &map, u32 L, cons
 }
 
 // ---- key switching ---------------------------------------------------------------------------------------------------
-// Host control flow of EvaluatorCuda::switchKeyInplace (src/evaluator_cuda.cu:1163-1378) over a batch:
-//   (CKKS) INTT the target  →  mod-up NTTs for all (output modulus i, digit j)  →  inner product with the key
-//   →  INTT the special-prime rows (+ half)  →  mod-down tail fused into the last transform of every data limb.
-void switch_key_impl(Context *ctx, int level, u64 *ct, u64 ct_stride, const u64 *target, u64 target_stride, const u64 *key,
-                     u32 batch, cudaStream_t s) {
+// Host control flow of EvaluatorCuda::switchKeyInplace (src/evaluator_cuda.cu:1163-1378) over a batch, in two halves:
+//   partial : (CKKS) INTT the target digits  →  mod-up NTTs for all (output modulus i, digit j)  →  inner product with
+//             the key, for the digits [digit0, digit0 + nd) only: prod = sum over those digits        (:1222-1297)
+//   finish  : INTT the special-prime rows (+ half)  →  mod-down tail fused into the last transform of every data limb,
+//             added into the ciphertext                                                                 (:1299-1376)
+// One GPU runs partial over all digits and then finish. With the digits of one key-switch sharded over several GPUs
+// (troy_b200/distributed.py) every GPU runs partial on its digits, the products are summed across GPUs (the only
+// exchange of the path), and finish first reduces the sums modulo each prime.
+void switch_key_partial(Context *ctx, int level, const u64 *target, u64 target_stride, const u64 *key, u32 digit0, u32 nd,
+                        u64 *prod, u32 batch, cudaStream_t s) {
     if (!ctx->has_special) throw std::logic_error("keyswitching is not supported by the context");
     const u32 L = (u32)ctx->levels[level].L;
     const u64 N = ctx->N;
     const u32 Lp = L + 1;
     const u32 key_limbs = (u32)ctx->Ltop + 1;
     const bool ckks = ctx->scheme == SCHEME_CKKS;
+    if (nd == 0 || digit0 + nd > L) throw std::invalid_argument("digit range is not valid");
     LimbMap kmap = ctx->map_prefix(L);
     kmap.idx[L] = (uint8_t)ctx->pool_special;
+    LimbMap dmap{}; // moduli of the digits in play
+    for (u32 j = 0; j < nd; j++) dmap.idx[j] = kmap.idx[digit0 + j];
 
-    // Only the mod-up output D ([L+1][L] limbs per ciphertext) is large. It is produced and consumed in chunks of at
+    // Only the mod-up output D ([L+1][nd] limbs per ciphertext) is large. It is produced and consumed in chunks of at
     // most 4 GiB (TROYB_KS_CHUNK_MB overrides): measured on B200, few large launches beat L2-sized chunks (the kernels are
     // bound by the FP64 / integer pipes, not by the HBM round trip of D, and small launches lose to partial waves).
-    const u64 per_ct_words = (u64)Lp * L * N;
+    const u64 per_ct_words = (u64)Lp * nd * N;
     const char *chunk_env = getenv("TROYB_KS_CHUNK_MB");
     const u64 chunk_bytes = (chunk_env ? (u64)atoi(chunk_env) : 4096ull) << 20;
     const u32 max_chunk = (u32)std::max<u64>(1, chunk_bytes / (per_ct_words * 8));
     const u32 n_chunks = (batch + max_chunk - 1) / max_chunk;
     const u32 chunk = (batch + n_chunks - 1) / n_chunks; // equal chunks
 
-    Scratch t_target(ckks ? (size_t)batch * L * N : 0, s);
+    Scratch t_target(ckks ? (size_t)batch * nd * N : 0, s);
     Scratch D((size_t)chunk * per_ct_words, s);
-    Scratch prod((size_t)batch * 2 * Lp * N, s);
-    Scratch sp((size_t)batch * 2 * N, s);
 
-    if (ckks) ntt_plain(ctx, true, kmap, L, target, target_stride, t_target.p, (u64)L * N, L, batch, true, s);
+    if (ckks) ntt_plain(ctx, true, dmap, nd, target + (u64)digit0 * N, target_stride, t_target.p, (u64)nd * N, nd, batch, true, s);
     for (u32 b0 = 0; b0 < batch; b0 += chunk) {
         const u32 nb = std::min(chunk, batch - b0);
         const u64 *tgt = target + (u64)b0 * target_stride;
@@ -196,15 +202,16 @@ void switch_key_impl(Context *ctx, int level, u64 *ct, u64 ct_stride, const u64 
             NttArgs a{};
             a.mode = FWD_MODUP;
             a.map = kmap;
-            a.L = L;
-            a.src = ckks ? t_target.p + (u64)b0 * L * N : tgt;
-            a.src_unit_stride = ckks ? (u64)L * N : target_stride;
+            a.L = nd;
+            a.digit0 = digit0;
+            a.src = ckks ? t_target.p + (u64)b0 * nd * N : tgt + (u64)digit0 * N;
+            a.src_unit_stride = ckks ? (u64)nd * N : target_stride;
             a.aux0 = ckks ? tgt : nullptr;
             a.aux0_batch_stride = target_stride;
             a.dst = D.p;
             a.scheme = ctx->scheme;
             set_order(ctx, a, Lp);
-            run_fwd(ctx, a, nb * Lp * L, s);
+            run_fwd(ctx, a, nb * Lp * nd, s);
         }
         {
             KsInnerProduct k{};
@@ -212,16 +219,43 @@ void switch_key_impl(Context *ctx, int level, u64 *ct, u64 ct_stride, const u64 
             k.mods = ctx->d_mods;
             k.map = kmap;
             k.L = L;
+            k.nd = nd;
+            k.digit0 = digit0;
             k.key_limbs = key_limbs;
             k.special_key_limb = key_limbs - 1;
             k.total = (u64)nb * Lp * (N / 2);
             k.D = D.p;
             k.key = key;
-            k.prod = prod.p + (u64)b0 * 2 * Lp * N;
+            k.prod = prod + (u64)b0 * 2 * Lp * N;
             k.pass = ckks ? tgt : nullptr;
             k.pass_stride = target_stride;
             ck(launch_cta(k, grid_for(k.total, KsInnerProduct::kThreads), 0, s));
         }
+    }
+}
+
+void switch_key_finish(Context *ctx, int level, u64 *ct, u64 ct_stride, u64 *prod, bool reduce_first, u32 batch, cudaStream_t s) {
+    if (!ctx->has_special) throw std::logic_error("keyswitching is not supported by the context");
+    const u32 L = (u32)ctx->levels[level].L;
+    const u64 N = ctx->N;
+    const u32 Lp = L + 1;
+    const bool ckks = ctx->scheme == SCHEME_CKKS;
+    LimbMap kmap = ctx->map_prefix(L);
+    kmap.idx[L] = (uint8_t)ctx->pool_special;
+    Scratch sp((size_t)batch * 2 * N, s);
+    if (reduce_first) {
+        // sums of several GPUs' canonical partial products: reduce modulo each prime before the tail
+        EltAddSub k{};
+        k.op = 4;
+        k.logN = ctx->logN;
+        k.mods = ctx->d_mods;
+        k.map = kmap;
+        k.n_limbs = Lp;
+        k.total = (u64)batch * 2 * Lp * N;
+        k.a = prod;
+        k.b = prod;
+        k.out = prod;
+        ck(launch_cta(k, grid_for(k.total, EltAddSub::kThreads), 0, s));
     }
     {
         NttArgs a{};
@@ -229,7 +263,7 @@ void switch_key_impl(Context *ctx, int level, u64 *ct, u64 ct_stride, const u64 
         a.map = kmap;
         a.L = L;
         a.K = 2;
-        a.src = prod.p;
+        a.src = prod;
         a.src_offset = (u64)L * N;
         a.src_unit_stride = 2ull * Lp * N;
         a.src_poly_stride = (u64)Lp * N;
@@ -245,7 +279,7 @@ void switch_key_impl(Context *ctx, int level, u64 *ct, u64 ct_stride, const u64 
         a.map = kmap;
         a.L = L;
         a.K = 2;
-        a.aux0 = prod.p;
+        a.aux0 = prod;
         a.acc_batch_stride = 2ull * Lp * N;
         a.acc_poly_stride = (u64)Lp * N;
         a.aux1 = sp.p;
@@ -258,6 +292,15 @@ void switch_key_impl(Context *ctx, int level, u64 *ct, u64 ct_stride, const u64 
         if (ckks) run_fwd(ctx, a, batch * 2 * L, s);
         else run_inv(ctx, a, batch * 2 * L, s);
     }
+}
+
+void switch_key_impl(Context *ctx, int level, u64 *ct, u64 ct_stride, const u64 *target, u64 target_stride, const u64 *key,
+                     u32 batch, cudaStream_t s) {
+    if (!ctx->has_special) throw std::logic_error("keyswitching is not supported by the context");
+    const u32 L = (u32)ctx->levels[level].L;
+    Scratch prod((size_t)batch * 2 * (L + 1) * ctx->N, s);
+    switch_key_partial(ctx, level, target, target_stride, key, 0, L, prod.p, batch, s);
+    switch_key_finish(ctx, level, ct, ct_stride, prod.p, false, batch, s);
 }
 
 void check_batch_stride(size_t stride, size_t min_words, const char *what) {
@@ -643,6 +686,39 @@ int troyb_switch_key(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_st
     check_aligned(d_target, "target");
     check_aligned(d_key, "key");
     switch_key_impl(c, level, d_ct, ct_stride, d_target, target_stride, d_key, (u32)batch, S(stream));
+    API_END
+}
+
+int troyb_switch_key_partial(troyb_context *ctx, int level, const uint64_t *d_target, size_t target_stride, const uint64_t *d_key,
+                             int digit_begin, int digit_end, uint64_t *d_prod, size_t batch, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const u32 L = (u32)level_limbs(c, level);
+    if (level < 0) throw std::invalid_argument("level");
+    if (!d_target || !d_key || !d_prod) throw std::invalid_argument("null argument");
+    if (digit_begin < 0 || digit_end <= digit_begin || (u32)digit_end > L) throw std::invalid_argument("digit range is not valid");
+    check_batch_stride(target_stride, (u64)L * c->N, "target");
+    check_aligned(d_target, "target");
+    check_aligned(d_key, "key");
+    check_aligned(d_prod, "prod");
+    switch_key_partial(c, level, d_target, target_stride, d_key, (u32)digit_begin, (u32)(digit_end - digit_begin), d_prod, (u32)batch,
+                       S(stream));
+    API_END
+}
+
+int troyb_switch_key_finish(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_stride, uint64_t *d_prod, int reduce_first,
+                            size_t batch, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const u32 L = (u32)level_limbs(c, level);
+    if (level < 0) throw std::invalid_argument("level");
+    if (!d_ct || !d_prod) throw std::invalid_argument("null argument");
+    check_batch_stride(ct_stride, 2ull * L * c->N, "ct");
+    check_aligned(d_ct, "ct");
+    check_aligned(d_prod, "prod");
+    switch_key_finish(c, level, d_ct, ct_stride, d_prod, reduce_first != 0, (u32)batch, S(stream));
     API_END
 }
 

@@ -21,7 +21,7 @@ TB_D void mac128(u64 &lo, u64 &hi, u64 a, u64 b) {
 struct EltAddSub {
     static constexpr int kThreads = kEltThreads;
     const char *name() const { return "elt_add_sub_negate_scale"; }
-    int op; // 0 add, 1 sub, 2 negate, 3 multiply by `scalar`
+    int op; // 0 add, 1 sub, 2 negate, 3 multiply by `scalar`, 4 reduce modulo the prime
     u64 scalar;
     int logN;
     const ModDev *mods;
@@ -42,6 +42,7 @@ struct EltAddSub {
                 if (op == 0) r = addmod(x, b[idx], p);
                 else if (op == 1) r = submod(x, b[idx], p);
                 else if (op == 2) r = negmod(x, p);
+                else if (op == 4) r = barrett64(x, p, m.ratio1);
                 else r = mulmod_barrett(x, barrett64(scalar, p, m.ratio1), p, m.ratio0, m.ratio1);
                 out[idx] = r;
             }
@@ -110,7 +111,7 @@ struct EltTensor {
 // ---- key-switch inner product -----------------------------------------------------------------------------
 // gSwitchKeyInplaceUtilB + UtilD  src/evaluator_cuda.cu:1034-1085: acc[k] = sum_j D[i][j] * key[j][k][key_index]
 // with 128-bit lazy accumulators kept in registers, one Barrett-128 at the end.
-//   D    : [batch][L+1][L][N]  mod-up output (lazy, < 4q)
+//   D    : [batch][L+1][nd][N]  mod-up output of digits digit0..digit0+nd-1 (canonical)
 //   key  : [digits][2][key_limbs][N]
 //   prod : [batch][2][L+1][N]  (t_poly_prod layout, §A.8)
 struct KsInnerProduct {
@@ -119,7 +120,8 @@ struct KsInnerProduct {
     int logN;
     const ModDev *mods;
     LimbMap map; // output modulus i -> pool index (i == L -> special)
-    u32 L;
+    u32 L;                // data limbs of the level (output moduli: L + 1)
+    u32 nd, digit0;       // digits summed by this launch
     u32 key_limbs;
     u32 special_key_limb; // key_limbs - 1
     u64 total;            // batch * (L+1) * N/2 threads (two adjacent coefficients per thread, 128-bit accesses)
@@ -139,24 +141,24 @@ struct KsInnerProduct {
                 const u64 b = bi / (L + 1);
                 const ModDev &m = mods[map.idx[i]];
                 const u32 key_limb = (i == L) ? special_key_limb : i;
-                const u64 *d = D + (bi * L) * N + c;
-                const u64 *kp = key + (u64)key_limb * N + c;
+                const u64 *d = D + (bi * nd) * N + c;
+                const u64 *kp = key + (u64)key_limb * N + c + (u64)digit0 * 2 * key_limbs * N;
                 const u64 key_digit_stride = 2ull * key_limbs * N, key_comp_stride = (u64)key_limbs * N;
                 u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0, lo2 = 0, hi2 = 0, lo3 = 0, hi3 = 0;
                 const u64 *ps = (pass != nullptr && i < L) ? pass + b * pass_stride + (u64)i * N + c : nullptr;
-                for (u32 j0 = 0; j0 < L; j0 += 4) { // four digits' loads in flight
+                for (u32 j0 = 0; j0 < nd; j0 += 4) { // four digits' loads in flight
                     ulonglong2 x[4], k0[4], k1[4];
                     _Pragma("unroll") for (u32 q = 0; q < 4; q++) {
                         const u32 j = j0 + q;
-                        if (j < L) {
-                            const u64 *src = (ps != nullptr && j == i) ? ps : d + (u64)j * N;
+                        if (j < nd) {
+                            const u64 *src = (ps != nullptr && j + digit0 == i) ? ps : d + (u64)j * N;
                             x[q] = *reinterpret_cast<const ulonglong2 *>(src);
                             k0[q] = __ldg(reinterpret_cast<const ulonglong2 *>(kp + j * key_digit_stride));
                             k1[q] = __ldg(reinterpret_cast<const ulonglong2 *>(kp + j * key_digit_stride + key_comp_stride));
                         }
                     }
                     _Pragma("unroll") for (u32 q = 0; q < 4; q++) {
-                        if (j0 + q < L) {
+                        if (j0 + q < nd) {
                             mac128(lo0, hi0, x[q].x, k0[q].x);
                             mac128(lo1, hi1, x[q].y, k0[q].y);
                             mac128(lo2, hi2, x[q].x, k1[q].x);

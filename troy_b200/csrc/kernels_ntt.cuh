@@ -36,7 +36,8 @@ struct NttArgs {
     const u64 *aux1;    // MODDOWN/COMBINE: s' (rounded special limb, coefficient form)
     u64 *ct;            // MODDOWN/COMBINE: ciphertext updated in place (null for rescale -> write dst)
     DropDev drop;       // constants for the prime being dropped
-    u32 L;              // data limbs in play
+    u32 L;              // data limbs in play (MODUP: digits in this launch)
+    u32 digit0;         // MODUP: index of the first digit of this launch
     u32 K;              // polys per batch element handled (2 for key-switch, ct size for rescale)
     u64 src_unit_stride;  // words between batch elements of src
     u64 src_poly_stride;  // words between polys of one batch element in src (INV_ADD_HALF)
@@ -158,17 +159,14 @@ template <int LOGT> TB_D NttUnit resolve_unit(const NttArgs &a, u32 bid) {
         break;
     }
     case FWD_MODUP: {
-        // storage: unit = (b * (L+1) + i) * L + j; launch order: (b, j, rank of i): the L+1 transforms of one digit are
+        // storage: unit = (b * (Lfull+1) + i) * L + j; launch order: (b, j, rank of i): the transforms of one digit are
         // neighbours, so the digit is read from HBM once
         const u32 i = a.order[unit % a.n_rank], bj = unit / a.n_rank, j = bj % a.L, b = bj / a.L;
-        u.unit = (b * (a.L + 1) + i) * a.L + j;
+        u.unit = (b * a.n_rank + i) * a.L + j;
         u.md = a.mods + a.map.idx[i];
         u.src = a.src + (u64)b * a.src_unit_stride + (u64)j * N;
         u.dst = a.dst + (u64)u.unit * N;
-        if (a.aux0 != nullptr && i == j) {
-            u.passthrough = true;
-            u.src = a.aux0 + (u64)b * a.aux0_batch_stride + (u64)j * N;
-        }
+        if (a.aux0 != nullptr && i == j + a.digit0) u.passthrough = true; // the inner product reads the NTT-form limb in place
         break;
     }
     case INV_ADD_HALF: {

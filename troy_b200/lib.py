@@ -69,6 +69,8 @@ _SIGNATURES = {
     "troyb_multiply_scalar": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64, _vp, _sz, _vp]),
     "troyb_multiply": (C.c_int, [_vp, C.c_int, _vp, _sz, _sz, _vp, _sz, _sz, _vp, _sz, _sz, _vp]),
     "troyb_switch_key": (C.c_int, [_vp, C.c_int, _vp, _sz, _vp, _sz, _vp, _sz, _vp]),
+    "troyb_switch_key_partial": (C.c_int, [_vp, C.c_int, _vp, _sz, _vp, C.c_int, C.c_int, _vp, _sz, _vp]),
+    "troyb_switch_key_finish": (C.c_int, [_vp, C.c_int, _vp, _sz, _vp, C.c_int, _sz, _vp]),
     "troyb_relinearize": (C.c_int, [_vp, C.c_int, _vp, _sz, _vp, _sz, _vp]),
     "troyb_galois_permute": (C.c_int, [_vp, C.c_int, _vp, _vp, _sz, C.c_uint32, C.c_int, _vp]),
     "troyb_galois_elt_from_step": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_uint32)]),
