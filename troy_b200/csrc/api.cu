@@ -105,12 +105,20 @@ void set_order(const Context *ctx, NttArgs &a, u32 n_limbs_in_map) {
     a.n_rank = n_limbs_in_map;
 }
 
-// Tiles per limb and the tile size used for a transform of 2^logN coefficients (see ntt.cuh TilePlan).
-int tile_log(int logN) { return logN == 12 ? 12 : 13; }
+// Tiles per limb of a transform of 2^logN coefficients (see ntt.cuh TilePlan).
 u32 tiles_per_limb(int logN) { return logN <= 13 ? 1u : (1u << (logN - 13)); }
+
+// L2 prefetch distance of the tile transforms: about one wave of resident CTAs (148 SMs x CTAs per SM, rounded up to
+// whole clusters). TROYB_PF_WAVES_X4 (development knob) scales it in quarter waves; 0 switches the prefetch off.
+u32 prefetch_distance(int logt) {
+    static const int quarters = [] { const char *e = getenv("TROYB_PF_WAVES_X4"); return e ? atoi(e) : 4; }();
+    const u32 wave = logt == 12 ? 888u : 448u;
+    return (wave * (u32)quarters / 4u) & ~7u;
+}
 
 void run_fwd(const Context *ctx, NttArgs a, u32 units, cudaStream_t s) {
     a.logN = ctx->logN;
+    a.pf_ahead = prefetch_distance(ctx->logN == 12 ? 12 : 13);
     a.mods = ctx->d_mods;
     const int logN = ctx->logN;
     if (logN > 16) throw std::invalid_argument("poly_modulus_degree above 65536 is not supported");
@@ -126,6 +134,7 @@ void run_fwd(const Context *ctx, NttArgs a, u32 units, cudaStream_t s) {
 
 void run_inv(const Context *ctx, NttArgs a, u32 units, cudaStream_t s) {
     a.logN = ctx->logN;
+    a.pf_ahead = prefetch_distance(ctx->logN == 12 ? 12 : 13);
     a.mods = ctx->d_mods;
     const int logN = ctx->logN;
     if (logN > 16) throw std::invalid_argument("poly_modulus_degree above 65536 is not supported");

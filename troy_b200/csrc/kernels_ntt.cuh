@@ -53,6 +53,7 @@ struct NttArgs {
     int add_half;       // INV_ADD_HALF: add half (BFV/CKKS) or plain canonical INTT (BGV)
     uint8_t order[kMaxLimbs]; // launch rank -> limb index: integer-pipe and FP64-pipe limbs interleaved (see set_order)
     u32 n_rank;         // limb ranks in the launch; consecutive units cycle through them
+    u32 pf_ahead;       // L2 prefetch distance in CTAs (0 = off): CTA b asks the L2 for the source tile of CTA b + pf_ahead
 };
 
 TB_D u64 canon4(u64 v, u64 p) {
@@ -194,6 +195,30 @@ template <int LOGT> TB_D NttUnit resolve_unit(const NttArgs &a, u32 bid) {
     return u;
 }
 
+// L2 prefetch (GPU only; thread 0 of the CTA). The CTA that will run about one wave later finds its source tile in the
+// L2 instead of HBM, and this CTA's own epilogue operands (accumulator and ciphertext rows, read in the store phase at
+// the very end) are requested now.
+template <int LOGT> TB_D void prefetch_tiles(const NttArgs &a, const NttUnit &u, u32 bid, u32 rank, u32 grid) {
+#if !defined(TROYB_HOST_EMUL)
+    if (a.pf_ahead == 0 || threadIdx.x != 0) return;
+    constexpr u32 bytes = (8u << LOGT);
+    const u64 off = (u64)rank << LOGT;
+    if (a.mode == FWD_MODDOWN || a.mode == INV_COMBINE) {
+        if (a.mode == INV_COMBINE) l2_prefetch(u.sp + off, bytes);
+        else l2_prefetch(u.acc + off, bytes);
+        if (u.ct) l2_prefetch(u.ct + off, bytes);
+    }
+    const u32 ahead = bid + a.pf_ahead;
+    if (ahead < grid) {
+        // sources shared by the n_rank consecutive units of one digit / one poly are requested once
+        const bool shared_src = a.mode == FWD_MODUP || a.mode == FWD_MODDOWN;
+        if (shared_src && ((ahead >> u.rows_log) % a.n_rank) != 0) return;
+        const NttUnit v = resolve_unit<LOGT>(a, ahead);
+        l2_prefetch(v.src + off, bytes);
+    }
+#endif
+}
+
 #define TB_WITH_LOGC(logc, ...)                                  \
     switch (logc) {                                              \
     case 1: { constexpr int LOGC = 1; __VA_ARGS__ } break;       \
@@ -310,12 +335,13 @@ template <int LOGT> struct NttFwdTile {
     NttArgs a;
     const char *name() const { return ntt_kernel_name(a.mode); }
 
-    template <int S> TB_D void stage(u32 bid, u32 rank, u32 nranks, u64 *sm, const Peers &peers) const {
+    template <int S> TB_D void stage(u32 bid, u32 grid, u32 rank, u32 nranks, u64 *sm, const Peers &peers) const {
         NttUnit u = resolve_unit<LOGT>(a, bid);
         const ModDev *md = u.md;
         const int pol = md->policy;
         const FwdPrologue pro{md->p, md->ratio1, a.mode == FWD_MODDOWN ? md->p - u.dl.half_mod : 0, a.mode};
         if constexpr (S == 0) {
+            prefetch_tiles<LOGT>(a, u, bid, rank, grid);
             // scatter stage: the layers that couple the tiles, results into the peers' shared memory
             if (nranks == 1 || u.passthrough) return;
             auto ld = [&](u32 i) -> u64 { return pro(u.src[i]); };
@@ -351,13 +377,14 @@ template <int LOGT> struct NttInvTile {
     NttArgs a;
     const char *name() const { return ntt_kernel_name(a.mode); }
 
-    template <int S> TB_D void stage(u32 bid, u32 rank, u32 nranks, u64 *sm, const Peers &peers) const {
+    template <int S> TB_D void stage(u32 bid, u32 grid, u32 rank, u32 nranks, u64 *sm, const Peers &peers) const {
         const NttUnit u = resolve_unit<LOGT>(a, bid);
         const ModDev *md = u.md;
         const u64 p = md->p;
         const int pol = md->policy;
         auto st = [&](u32 i, u64 v) { inv_store_final(a, u, p, i, v); };
         if constexpr (S == 0) {
+            prefetch_tiles<LOGT>(a, u, bid, rank, grid);
             const u64 *in = u.src + ((u64)rank << LOGT);
             auto gld = [&](u32 i) -> u64 { return in[i]; };
             if (nranks == 1) {

@@ -8,7 +8,7 @@
 // carried in registers across phases.
 //
 // Cluster kernels (launch_cluster) are functors with F::kStages stages separated by cluster-wide barriers:
-//     template <int S> __device__ void stage(u32 bid, u32 rank, u32 nranks, u64 *smem, const Peers &peers) const
+//     template <int S> __device__ void stage(u32 bid, u32 grid, u32 rank, u32 nranks, u64 *smem, const Peers &peers) const
 // `peers` reads / writes 64-bit words of the shared memory of any CTA of the cluster (distributed shared memory).
 // A last barrier after the final stage keeps every CTA's shared memory alive until its peers have finished reading it.
 //
@@ -60,10 +60,12 @@ struct Peers {
     void st(u32 handle, u32 word, u64 v) const { tiles[handle][word] = v; }
 };
 
-template <class F, int S> inline void emul_stages(const F &f, u32 b0, u32 nranks, std::vector<u64 *> &ptr, const Peers &peers) {
+inline void l2_prefetch(const void *, u32) {}
+
+template <class F, int S> inline void emul_stages(const F &f, u32 b0, u32 grid, u32 nranks, std::vector<u64 *> &ptr, const Peers &peers) {
     if constexpr (S < F::kStages) {
-        for (u32 r = 0; r < nranks; r++) f.template stage<S>(b0 + r, r, nranks, ptr[r], peers);
-        emul_stages<F, S + 1>(f, b0, nranks, ptr, peers);
+        for (u32 r = 0; r < nranks; r++) f.template stage<S>(b0 + r, grid, r, nranks, ptr[r], peers);
+        emul_stages<F, S + 1>(f, b0, grid, nranks, ptr, peers);
     }
 }
 
@@ -72,7 +74,7 @@ template <class F> inline cudaError_t launch_cluster(const F &f, u32 grid, u32 n
     std::vector<u64 *> ptr(nranks);
     for (u32 r = 0; r < nranks; r++) ptr[r] = sm[r].data();
     Peers peers{ptr.data()};
-    for (u32 b0 = 0; b0 < grid; b0 += nranks) emul_stages<F, 0>(f, b0, nranks, ptr, peers);
+    for (u32 b0 = 0; b0 < grid; b0 += nranks) emul_stages<F, 0>(f, b0, grid, nranks, ptr, peers);
     launch_counter()++;
     return cudaSuccess;
 }
@@ -121,6 +123,9 @@ template <class F> inline cudaError_t launch_cta(const F &f, u32 grid, size_t sm
 }
 
 // ---- thread-block clusters + distributed shared memory ---------------------------------------------------------------
+// Distributed-shared-memory accesses carry no "memory" clobber: within a stage a CTA's own tile is touched either only
+// through Peers or only through ordinary shared-memory accesses, and stages are separated by cluster_barrier(), which
+// does clobber memory. The compiler is therefore free to batch global loads around them.
 struct Peers {
     u32 base; // shared::cta address of this CTA's dynamic shared memory (same offset in every CTA of the cluster)
     // shared::cluster address of the start of CTA `rank`'s tile
@@ -131,13 +136,18 @@ struct Peers {
     }
     TB_D u64 ld(u32 handle, u32 word) const {
         u64 v;
-        asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(handle + word * 8u) : "memory");
+        asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(handle + word * 8u));
         return v;
     }
     TB_D void st(u32 handle, u32 word, u64 v) const {
-        asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(handle + word * 8u), "l"(v) : "memory");
+        asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(handle + word * 8u), "l"(v));
     }
 };
+
+// Asks the L2 to fetch `bytes` (multiple of 16) at p (16-byte aligned); returns at once.
+TB_D void l2_prefetch(const void *p, u32 bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes));
+}
 
 TB_D void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -145,7 +155,7 @@ TB_D void cluster_barrier() {
 
 template <class F, int S> TB_D void run_stages(const F &f, u32 rank, u32 nranks, u64 *smem, const Peers &peers) {
     if constexpr (S < F::kStages) {
-        f.template stage<S>(blockIdx.x, rank, nranks, smem, peers);
+        f.template stage<S>(blockIdx.x, gridDim.x, rank, nranks, smem, peers);
         if (nranks > 1 && (S + 1 < F::kStages || F::kTrailingBarrier)) cluster_barrier();
         run_stages<F, S + 1>(f, rank, nranks, smem, peers);
     }

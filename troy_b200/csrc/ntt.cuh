@@ -321,7 +321,7 @@ __host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x
 //   PAIRED (SH = 2) : BLO = 4 and RR = 3: lanes take lo bits 0-2 and hi bit 0 (the padding maps index bit 7 to the bank
 //                     bit that lo bit 3 would have supplied), the two groups of a turn differ in lo bit 3;
 //   else   (SH = 1) : thread slots are consecutive groups (with the lane rotation of group_of_slot when 0 < BLO < 4);
-//                     U groups are in flight at a time.
+//                     one group per turn, twiddles requested AHEAD turns early.
 template <int LOGT, int NT, int S0, int RR> struct RoundGeom {
     static constexpr int K = 1 << RR, BLO = LOGT - S0 - RR, NV = (1 << LOGT) / K, G = NV / NT, LOGG = ilog2(G);
     static_assert(BLO >= 0 && G >= 1 && NV % NT == 0 && (1 << LOGG) == G, "bad round");
@@ -329,7 +329,9 @@ template <int LOGT, int NT, int S0, int RR> struct RoundGeom {
     static constexpr bool PAIRED = !SHARED && BLO == 4 && RR == 3 && G % 2 == 0;
     static constexpr int SH = SHARED ? G : (PAIRED ? 2 : 1);
     static constexpr int TL = SHARED ? BLO - LOGG : 0;
-    static constexpr int U = (SH == 1 && RR <= 2 && G % 2 == 0) ? 2 : 1; // independent groups in flight (SH == 1)
+    static constexpr int U = 1;                                          // independent groups in flight (SH == 1)
+    // twiddle sets requested ahead of the turn that uses them (radix-4 turns are short: two turns hide an L2 access)
+    static constexpr int AHEAD = (!SHARED && RR <= 2 && G >= 4) ? 2 : 0;
     static constexpr int TURNS = G / (SH * U);
     // group handled by thread vt: turn `turn`, in-flight slot q (< U), shared-twiddle member e (< SH)
     static TB_D void locate(u32 vt, int turn, int q, int e, u32 &hi, u32 &base) {
@@ -356,21 +358,42 @@ template <class A, int RR, int S0> TB_D void load_twiddles(typename A::tw_t (&w)
     }
 }
 
+// The twiddles of the groups a thread has in flight in one turn of a round. Loading them is split from the round
+// itself so that the loads can be issued before the barrier that precedes the round and, inside a round of several
+// turns, one turn ahead: their L2 latency then overlaps the barrier wait / the previous turn's butterflies.
+template <class A, int LOGT, int NT, int S0, int RR> struct RoundTw {
+    typedef RoundGeom<LOGT, NT, S0, RR> Q;
+    static constexpr int NW = Q::SHARED ? 1 : Q::U;
+    typename A::tw_t w[NW][(1 << RR) - 1];
+    TB_D void load(u32 vt, int turn, const void *__restrict__ tab, u32 R) {
+#pragma unroll
+        for (int q = 0; q < NW; q++) {
+            u32 hi, base;
+            Q::locate(vt, turn, q, 0, hi, base);
+            load_twiddles<A, RR, S0>(w[q], tab, R, hi);
+        }
+    }
+};
+
 // One round of the forward (INVERSE = false) or inverse transform over the tile.
 //   PIN / POUT: the source / destination is the padded shared-memory tile (index = pad_idx(i)); the padded offset of
 //   coefficient k of a group is a compile-time constant because the group base and k << BLO occupy disjoint bits.
 //   LAST   : (inverse) layer 0 of the whole transform is layer S0 = 0 of this round and carries the N^-1 scaling
 //   REDUCE : (inverse) re-centre the inputs first (FP64 policies)
-template <class A, int LOGT, int NT, int S0, int RR, bool INVERSE, bool LAST, bool REDUCE, bool PIN, bool POUT, class Ld, class St>
-TB_D void tile_round(u32 vt, Ld ld, St st, const void *__restrict__ tw, u32 R, const typename A::Mod &m) {
+//   PRE    : the twiddles of turn 0 were loaded by the caller (*pre), see RoundTw
+template <class A, int LOGT, int NT, int S0, int RR, bool INVERSE, bool LAST, bool REDUCE, bool PIN, bool POUT, bool PRE = false, class Ld, class St>
+TB_D void tile_round(u32 vt, Ld ld, St st, const void *__restrict__ tw, u32 R, const typename A::Mod &m,
+                     const RoundTw<A, LOGT, NT, S0, RR> *pre = nullptr) {
     typedef RoundGeom<LOGT, NT, S0, RR> Q;
+    typedef RoundTw<A, LOGT, NT, S0, RR> W;
     constexpr int K = Q::K, BLO = Q::BLO, U = Q::U, SH = Q::SH;
+    W cur;
+    if constexpr (PRE) cur = *pre;
+    else cur.load(vt, 0, tw, R);
     if constexpr (Q::SHARED) {
         // all G groups of the thread share one twiddle set; two groups in flight at a time
         u32 hi, base0;
         Q::locate(vt, 0, 0, 0, hi, base0);
-        typename A::tw_t w[K - 1];
-        load_twiddles<A, RR, S0>(w, tw, R, hi);
 #pragma unroll 2
         for (int e = 0; e < SH; e++) {
             const u32 base = base0 | ((u32)e << Q::TL);
@@ -381,29 +404,39 @@ TB_D void tile_round(u32 vt, Ld ld, St st, const void *__restrict__ tw, u32 R, c
                 x[k] = ld(ib + (PIN ? pad_idx((u32)k << BLO) : ((u32)k << BLO)));
                 if (REDUCE) A::reduce(x[k], m);
             }
-            if constexpr (INVERSE) radix_inv<A, RR, LAST>(x, w, m);
-            else radix_fwd<A, RR>(x, w, m);
+            if constexpr (INVERSE) radix_inv<A, RR, LAST>(x, cur.w[0], m);
+            else radix_fwd<A, RR>(x, cur.w[0], m);
 #pragma unroll
             for (int k = 0; k < K; k++) st(ob + (POUT ? pad_idx((u32)k << BLO) : ((u32)k << BLO)), x[k]);
         }
     } else {
         constexpr int F = U * SH; // groups in flight
-#pragma unroll 1
+        constexpr int D = Q::AHEAD, NR = D + 1;
+        W ring[NR];
+        ring[0] = cur;
+#pragma unroll
+        for (int d = 1; d <= D; d++) {
+            if (d < Q::TURNS) ring[d].load(vt, d, tw, R);
+        }
+#pragma unroll(D > 0 ? Q::TURNS : 1)
         for (int turn = 0; turn < Q::TURNS; turn++) {
+            if constexpr (D > 0) {
+                if (turn + D < Q::TURNS) ring[(turn + D) % NR].load(vt, turn + D, tw, R);
+            } else {
+                if (turn > 0) ring[0].load(vt, turn, tw, R);
+            }
+            const W &wt = ring[D > 0 ? turn % NR : 0];
             u32 ib[F], ob[F];
-            typename A::tw_t w[U][K - 1];
             typename A::elem x[F][K];
 #pragma unroll
             for (int q = 0; q < U; q++) {
-                u32 hi = 0;
 #pragma unroll
                 for (int e = 0; e < SH; e++) {
-                    u32 base;
+                    u32 hi, base;
                     Q::locate(vt, turn, q, e, hi, base);
                     ib[q * SH + e] = PIN ? pad_idx(base) : base;
                     ob[q * SH + e] = POUT ? pad_idx(base) : base;
                 }
-                load_twiddles<A, RR, S0>(w[q], tw, R, hi);
             }
 #pragma unroll
             for (int f = 0; f < F; f++) {
@@ -416,8 +449,8 @@ TB_D void tile_round(u32 vt, Ld ld, St st, const void *__restrict__ tw, u32 R, c
 #pragma unroll
                     for (int k = 0; k < K; k++) A::reduce(x[f][k], m);
                 }
-                if constexpr (INVERSE) radix_inv<A, RR, LAST>(x[f], w[f / SH], m);
-                else radix_fwd<A, RR>(x[f], w[f / SH], m);
+                if constexpr (INVERSE) radix_inv<A, RR, LAST>(x[f], wt.w[f / SH], m);
+                else radix_fwd<A, RR>(x[f], wt.w[f / SH], m);
 #pragma unroll
                 for (int k = 0; k < K; k++) st(ob[f] + (POUT ? pad_idx((u32)k << BLO) : ((u32)k << BLO)), x[f][k]);
             }
@@ -449,6 +482,7 @@ template <class A> struct SmSt {
 //   GLOBAL_IN : the first round reads coefficient i of the tile as gld(i) (global memory, prologue fused there).
 //               Otherwise the tile holds element bits left by the cluster's scatter stage.
 // The results stay in shared memory as element bits.
+// On the GPU the twiddles of round r+1 are requested before the barrier that ends round r (RoundTw).
 template <class A, int LOGT, bool GLOBAL_IN, class Gld>
 TB_D void tile_ntt_fwd(u64 *sm, Gld gld, const ModDev *md, u32 R) {
     typedef TilePlan<LOGT> P;
@@ -457,20 +491,54 @@ TB_D void tile_ntt_fwd(u64 *sm, Gld gld, const ModDev *md, u32 R) {
     const void *tw = A::fwd_table(md);
     SmLd<A> sl{sm};
     SmSt<A> ss{sm};
+    constexpr int S1 = P::R0, S2 = S1 + P::R1, S3 = S2 + P::R2, S4 = S3 + P::R3;
+#if defined(TROYB_HOST_EMUL)
     if constexpr (GLOBAL_IN) {
         auto rl = [&](u32 i) -> typename A::elem { return A::from_u64(gld(i), m); };
         TB_PHASE(NT, t, (tile_round<A, LOGT, NT, 0, P::R0, false, false, false, false, true>(t, rl, ss, tw, R, m));)
     } else {
         TB_PHASE(NT, t, (tile_round<A, LOGT, NT, 0, P::R0, false, false, false, true, true>(t, sl, ss, tw, R, m));)
     }
-    TB_PHASE(NT, t, (tile_round<A, LOGT, NT, P::R0, P::R1, false, false, false, true, true>(t, sl, ss, tw, R, m));)
-    TB_PHASE(NT, t, (tile_round<A, LOGT, NT, P::R0 + P::R1, P::R2, false, false, false, true, true>(t, sl, ss, tw, R, m));)
+    TB_PHASE(NT, t, (tile_round<A, LOGT, NT, S1, P::R1, false, false, false, true, true>(t, sl, ss, tw, R, m));)
+    TB_PHASE(NT, t, (tile_round<A, LOGT, NT, S2, P::R2, false, false, false, true, true>(t, sl, ss, tw, R, m));)
     if constexpr (P::R3 > 0) {
-        TB_PHASE(NT, t, (tile_round<A, LOGT, NT, P::R0 + P::R1 + P::R2, P::R3, false, false, false, true, true>(t, sl, ss, tw, R, m));)
+        TB_PHASE(NT, t, (tile_round<A, LOGT, NT, S3, P::R3, false, false, false, true, true>(t, sl, ss, tw, R, m));)
     }
     if constexpr (P::R4 > 0) {
-        TB_PHASE(NT, t, (tile_round<A, LOGT, NT, P::R0 + P::R1 + P::R2 + P::R3, P::R4, false, false, false, true, true>(t, sl, ss, tw, R, m));)
+        TB_PHASE(NT, t, (tile_round<A, LOGT, NT, S4, P::R4, false, false, false, true, true>(t, sl, ss, tw, R, m));)
     }
+#else
+    const u32 t = threadIdx.x;
+    RoundTw<A, LOGT, NT, 0, P::R0> w0;
+    w0.load(t, 0, tw, R);
+    if constexpr (GLOBAL_IN) {
+        auto rl = [&](u32 i) -> typename A::elem { return A::from_u64(gld(i), m); };
+        tile_round<A, LOGT, NT, 0, P::R0, false, false, false, false, true, true>(t, rl, ss, tw, R, m, &w0);
+    } else {
+        tile_round<A, LOGT, NT, 0, P::R0, false, false, false, true, true, true>(t, sl, ss, tw, R, m, &w0);
+    }
+    RoundTw<A, LOGT, NT, S1, P::R1> w1;
+    w1.load(t, 0, tw, R);
+    __syncthreads();
+    tile_round<A, LOGT, NT, S1, P::R1, false, false, false, true, true, true>(t, sl, ss, tw, R, m, &w1);
+    RoundTw<A, LOGT, NT, S2, P::R2> w2;
+    w2.load(t, 0, tw, R);
+    __syncthreads();
+    tile_round<A, LOGT, NT, S2, P::R2, false, false, false, true, true, true>(t, sl, ss, tw, R, m, &w2);
+    if constexpr (P::R3 > 0) {
+        RoundTw<A, LOGT, NT, S3, P::R3> w3;
+        w3.load(t, 0, tw, R);
+        __syncthreads();
+        tile_round<A, LOGT, NT, S3, P::R3, false, false, false, true, true, true>(t, sl, ss, tw, R, m, &w3);
+    }
+    if constexpr (P::R4 > 0) {
+        RoundTw<A, LOGT, NT, S4, P::R4> w4;
+        w4.load(t, 0, tw, R);
+        __syncthreads();
+        tile_round<A, LOGT, NT, S4, P::R4, false, false, false, true, true, true>(t, sl, ss, tw, R, m, &w4);
+    }
+    __syncthreads();
+#endif
 }
 
 // Canonical store of a finished tile: st(i, v) receives the canonical residue of output i (linear, coalesced order).
@@ -501,6 +569,7 @@ TB_D void tile_ntt_inv(u64 *sm, Gld gld, St st, const ModDev *md, u32 R) {
     SmSt<A> ss{sm};
     auto rl = [&](u32 i) -> typename A::elem { return A::from_u64(gld(i), m); }; // canonical input: no re-centring needed
     constexpr int S1 = P::R0, S2 = S1 + P::R1, S3 = S2 + P::R2, S4 = S3 + P::R3;
+#if defined(TROYB_HOST_EMUL)
     if constexpr (P::R4 > 0) {
         TB_PHASE(NT, t, (tile_round<A, LOGT, NT, S4, P::R4, true, false, false, false, true>(t, rl, ss, tw, R, m));)
         TB_PHASE(NT, t, (tile_round<A, LOGT, NT, S3, P::R3, true, false, RE, true, true>(t, sl, ss, tw, R, m));)
@@ -515,6 +584,40 @@ TB_D void tile_ntt_inv(u64 *sm, Gld gld, St st, const ModDev *md, u32 R) {
     } else {
         TB_PHASE(NT, t, (tile_round<A, LOGT, NT, 0, P::R0, true, false, RE, true, true>(t, sl, ss, tw, R, m));)
     }
+#else
+    const u32 t = threadIdx.x;
+    if constexpr (P::R4 > 0) {
+        RoundTw<A, LOGT, NT, S4, P::R4> w4;
+        w4.load(t, 0, tw, R);
+        tile_round<A, LOGT, NT, S4, P::R4, true, false, false, false, true, true>(t, rl, ss, tw, R, m, &w4);
+        RoundTw<A, LOGT, NT, S3, P::R3> w3;
+        w3.load(t, 0, tw, R);
+        __syncthreads();
+        tile_round<A, LOGT, NT, S3, P::R3, true, false, RE, true, true, true>(t, sl, ss, tw, R, m, &w3);
+    } else {
+        RoundTw<A, LOGT, NT, S3, P::R3> w3;
+        w3.load(t, 0, tw, R);
+        tile_round<A, LOGT, NT, S3, P::R3, true, false, false, false, true, true>(t, rl, ss, tw, R, m, &w3);
+    }
+    RoundTw<A, LOGT, NT, S2, P::R2> w2;
+    w2.load(t, 0, tw, R);
+    __syncthreads();
+    tile_round<A, LOGT, NT, S2, P::R2, true, false, RE, true, true, true>(t, sl, ss, tw, R, m, &w2);
+    RoundTw<A, LOGT, NT, S1, P::R1> w1;
+    w1.load(t, 0, tw, R);
+    __syncthreads();
+    tile_round<A, LOGT, NT, S1, P::R1, true, false, RE || RM, true, true, true>(t, sl, ss, tw, R, m, &w1);
+    RoundTw<A, LOGT, NT, 0, P::R0> w0;
+    w0.load(t, 0, tw, R);
+    __syncthreads();
+    if constexpr (FINAL) {
+        auto gs_ = [&](u32 i, typename A::elem x) { st(i, A::canon_reduced(x, m)); };
+        tile_round<A, LOGT, NT, 0, P::R0, true, true, RE, true, false, true>(t, sl, gs_, tw, R, m, &w0);
+    } else {
+        tile_round<A, LOGT, NT, 0, P::R0, true, false, RE, true, true, true>(t, sl, ss, tw, R, m, &w0);
+    }
+    __syncthreads();
+#endif
 }
 
 // ---- cluster stages ------------------------------------------------------------------------------------------------------------
@@ -531,21 +634,35 @@ template <class A, int LOGC, int LOGT, int NT, class Ld, class StPeer>
 TB_D void cluster_fwd_scatter(u32 vt, u32 rank, Ld ld, StPeer st_peer, const ModDev *md) {
     constexpr int C = 1 << LOGC, T = 1 << LOGT, G = T / C / NT;
     static_assert(G >= 1, "bad cluster stage");
+    // B iterations (16 coefficients) are loaded before any of them is used: one memory latency per batch, not per
+    // iteration
+    constexpr int B = (G * C >= 16) ? (C >= 8 ? 1 : 16 / C) : G; // radix-8 holds 7 twiddles: one iteration at a time
+    static_assert(G % B == 0, "bad scatter batch");
     const typename A::Mod m = A::make(md);
     const void *tw = A::fwd_table(md);
     typename A::tw_t w[C - 1];
 #pragma unroll
     for (int k = 1; k < C; k++) w[k - 1] = A::ld_tw(tw, k); // layer u, block j: table entry 2^u + j
-#pragma unroll(16 / C)
-    for (int g = 0; g < G; g++) {
-        const u32 v = rank * (T / C) + vt + g * NT;
-        typename A::elem x[C];
+#pragma unroll 1
+    for (int g0 = 0; g0 < G; g0 += B) {
+        u64 raw[B][C];
 #pragma unroll
-        for (int k = 0; k < C; k++) x[k] = A::from_u64(ld(v + (u32)k * T), m);
-        radix_fwd<A, LOGC>(x, w, m);
-        const u32 pv = pad_idx(v);
+        for (int b = 0; b < B; b++) {
+            const u32 v = rank * (T / C) + vt + (g0 + b) * NT;
 #pragma unroll
-        for (int k = 0; k < C; k++) st_peer((u32)k, pv, A::to_bits(x[k]));
+            for (int k = 0; k < C; k++) raw[b][k] = ld(v + (u32)k * T);
+        }
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            const u32 v = rank * (T / C) + vt + (g0 + b) * NT;
+            typename A::elem x[C];
+#pragma unroll
+            for (int k = 0; k < C; k++) x[k] = A::from_u64(raw[b][k], m);
+            radix_fwd<A, LOGC>(x, w, m);
+            const u32 pv = pad_idx(v);
+#pragma unroll
+            for (int k = 0; k < C; k++) st_peer((u32)k, pv, A::to_bits(x[k]));
+        }
     }
 }
 
@@ -557,6 +674,8 @@ template <class A, int LOGC, int LOGT, int NT, class LdPeer, class St>
 TB_D void cluster_inv_gather(u32 vt, u32 rank, LdPeer ld_peer, St st, const ModDev *md) {
     constexpr int C = 1 << LOGC, T = 1 << LOGT, G = T / C / NT;
     static_assert(G >= 1, "bad cluster stage");
+    constexpr int B = (G * C >= 8) ? 8 / C : G; // distributed-shared-memory loads in flight: B iterations
+    static_assert(G % B == 0, "bad gather batch");
     // the tile's last round leaves at most 2^3 x the re-centred magnitude: one more layer needs no re-centring
     constexpr bool RE = A::kReduceEachInvRound && LOGC > 1;
     const typename A::Mod m = A::make(md);
@@ -564,21 +683,30 @@ TB_D void cluster_inv_gather(u32 vt, u32 rank, LdPeer ld_peer, St st, const ModD
     typename A::tw_t w[C - 1];
 #pragma unroll
     for (int k = 2; k < C; k++) w[k - 1] = A::ld_tw(tw, k); // entry 1 (layer 0) is folded into gs_last
-#pragma unroll(8 / C)
-    for (int g = 0; g < G; g++) {
-        const u32 v = rank * (T / C) + vt + g * NT;
-        const u32 pv = pad_idx(v);
-        typename A::elem x[C];
+#pragma unroll 1
+    for (int g0 = 0; g0 < G; g0 += B) {
+        u64 raw[B][C];
 #pragma unroll
-        for (int k = 0; k < C; k++) {
-            x[k] = A::from_bits(ld_peer((u32)k, pv));
-            if (RE) A::reduce(x[k], m);
+        for (int b = 0; b < B; b++) {
+            const u32 pv = pad_idx(rank * (T / C) + vt + (g0 + b) * NT);
+#pragma unroll
+            for (int k = 0; k < C; k++) raw[b][k] = ld_peer((u32)k, pv);
         }
-        radix_inv<A, LOGC, true>(x, w, m);
 #pragma unroll
-        for (int k = 0; k < C; k++) {
-            // outputs of layer 0 are mulmod results; for C > 2 the others passed through it too
-            st(v + (u32)k * T, A::canon_reduced(x[k], m));
+        for (int b = 0; b < B; b++) {
+            const u32 v = rank * (T / C) + vt + (g0 + b) * NT;
+            typename A::elem x[C];
+#pragma unroll
+            for (int k = 0; k < C; k++) {
+                x[k] = A::from_bits(raw[b][k]);
+                if (RE) A::reduce(x[k], m);
+            }
+            radix_inv<A, LOGC, true>(x, w, m);
+#pragma unroll
+            for (int k = 0; k < C; k++) {
+                // outputs of layer 0 are mulmod results; for C > 2 the others passed through it too
+                st(v + (u32)k * T, A::canon_reduced(x[k], m));
+            }
         }
     }
 }

@@ -112,7 +112,8 @@ def library():
     """The product library (CUDA). Raises ImportError when it has not been built."""
     global _library
     if _library is None:
-        _library = Library(LIB_PATH)
+        # TROYB_LIB (development knob): another CUDA build of the same sources, e.g. an A/B variant under tests/microbench
+        _library = Library(os.environ.get("TROYB_LIB", LIB_PATH))
     return _library
 
 
