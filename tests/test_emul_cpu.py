@@ -21,3 +21,9 @@ def test_cluster_transforms_emulated(ref, emul_lib, scheme, n, bits):
 
 def test_batch_emulated(ref, emul_lib):
     run_evaluator_flow(ref, emul_lib, ref.CKKS, 256, [40, 30, 30, 30, 40], np.random.default_rng(5), batch=3)
+
+
+def test_many_digits_emulated(ref, emul_lib):
+    """More than 8 digits: the key inner product runs over digit groups that are added up in the product buffer."""
+    run_evaluator_flow(ref, emul_lib, ref.CKKS, 1024, [40] * 10 + [50], np.random.default_rng(11), batch=2)
+    run_evaluator_flow(ref, emul_lib, ref.BFV, 512, [36] * 9 + [40], np.random.default_rng(12))

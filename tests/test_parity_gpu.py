@@ -32,6 +32,13 @@ def test_batched_flow(ref, cuda_lib):
     run_evaluator_flow(ref, cuda_lib, ref.BFV, 8192, [60, 40, 40, 60], np.random.default_rng(78), batch=3)
 
 
+def test_many_digits(ref, cuda_lib):
+    """More than 8 digits: the key inner product runs over digit groups that are added up in the product buffer."""
+    run_evaluator_flow(ref, cuda_lib, ref.CKKS, 1024, [40] * 10 + [50], np.random.default_rng(11), batch=2)
+    run_evaluator_flow(ref, cuda_lib, ref.BFV, 512, [36] * 9 + [40], np.random.default_rng(12))
+    run_evaluator_flow(ref, cuda_lib, ref.CKKS, 8192, [40] * 17 + [50], np.random.default_rng(13))
+
+
 # ---- committed golden fixtures (generated from the reference by tests/golden/make_golden.py) ----------------------
 import os  # noqa: E402
 

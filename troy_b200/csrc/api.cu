@@ -222,7 +222,44 @@ void switch_key_partial(Context *ctx, int level, const u64 *target, u64 target_s
             set_order(ctx, a, Lp);
             run_fwd(ctx, a, nb * Lp * nd, s);
         }
-        {
+        if (N >= kStagedCoeffs) {
+            // key slices staged in shared memory, digits in groups of at most 8, partial sums added up in prod
+            const u64 units = (u64)nb * Lp * (N / kStagedCoeffs);
+            const u32 bc = (u32)std::min<u64>(16, std::max<u64>(1, units / (148 * 3 * 8)));
+            const u32 grid = (u32)(N / kStagedCoeffs) * Lp * ((nb + bc - 1) / bc);
+            for (u32 g0 = 0; g0 < nd; g0 += kStagedMaxDigits) {
+                auto launch = [&](auto k) {
+                    k.logN = ctx->logN;
+                    k.mods = ctx->d_mods;
+                    k.map = kmap;
+                    k.L = L;
+                    k.digit0 = digit0 + g0;
+                    k.key_limbs = key_limbs;
+                    k.special_key_limb = key_limbs - 1;
+                    k.batch = nb;
+                    k.bc = bc;
+                    k.d_rows = nd;
+                    k.d_row0 = g0;
+                    k.accumulate = g0 > 0;
+                    k.D = D.p;
+                    k.key = key;
+                    k.prod = prod + (u64)b0 * 2 * Lp * N;
+                    k.pass = ckks ? tgt : nullptr;
+                    k.pass_stride = target_stride;
+                    ck(launch_cta(k, grid, decltype(k)::smem_bytes(), s));
+                };
+                switch (std::min(kStagedMaxDigits, nd - g0)) {
+                case 1: launch(KsInnerProductStaged<1>{}); break;
+                case 2: launch(KsInnerProductStaged<2>{}); break;
+                case 3: launch(KsInnerProductStaged<3>{}); break;
+                case 4: launch(KsInnerProductStaged<4>{}); break;
+                case 5: launch(KsInnerProductStaged<5>{}); break;
+                case 6: launch(KsInnerProductStaged<6>{}); break;
+                case 7: launch(KsInnerProductStaged<7>{}); break;
+                default: launch(KsInnerProductStaged<8>{}); break;
+                }
+            }
+        } else {
             KsInnerProduct k{};
             k.logN = ctx->logN;
             k.mods = ctx->d_mods;
@@ -617,7 +654,7 @@ int troyb_multiply(troyb_context *ctx, int level, const uint64_t *d_a, size_t a_
         k.a_size = (u32)a_size;
         k.b_size = (u32)b_size;
         k.per_batch = (u64)limbs * N;
-        k.total = (u64)batch * limbs * N;
+        k.total = (u64)batch * limbs * N / 2;
         k.a = a; k.b = b; k.out = o;
         k.a_batch_stride = as; k.b_batch_stride = bs; k.out_batch_stride = os;
         ck(launch_cta(k, grid_for(k.total, EltTensor::kThreads), 0, s));

@@ -269,6 +269,8 @@ Context *context_create(int device, int scheme, u64 N, const u64 *moduli, int n_
         ModDev &md = ctx->h_mods[m];
         md.p = p;
         barrett_ratio(p, md.ratio0, md.ratio1);
+        md.bar_shift = 63u - (u32)__builtin_clzll(p);
+        md.bar_mu = (u64)(((unsigned __int128)1 << (md.bar_shift + 64)) / p);
         u64 psi;
         if (!minimal_primitive_root(2 * N, p, psi)) throw std::invalid_argument("invalid modulus");
         u64 power = 1, ipower = 1;

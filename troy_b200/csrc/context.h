@@ -27,6 +27,8 @@ constexpr int kMaxLimbs = 80; // data limbs + special + BEHZ auxiliary primes
 struct ModDev {
     u64 p;
     u64 ratio0, ratio1;     // floor(2^128/p)
+    u64 bar_mu;             // floor(2^(bar_shift+64)/p): single-word Barrett for short sums of products (modarith.cuh reduce_sum)
+    u32 bar_shift;          // bit length of p, minus 1
     u64 ninv, ninv_shoup;   // N^-1 mod p
     u64 inv1n, inv1n_shoup; // fwd[1]^-1 * N^-1 mod p
     const u64 *fwd;         // 2*N words

@@ -8,6 +8,7 @@
 namespace troyb {
 
 constexpr int kEltThreads = 256;
+constexpr u32 kStagedCoeffs = 2 * kEltThreads, kStagedMaxDigits = 8; // KsInnerProductStaged geometry
 
 TB_D void mac128(u64 &lo, u64 &hi, u64 a, u64 b) {
     u64 pl = a * b, ph = mulhi64(a, b);
@@ -63,45 +64,62 @@ struct EltTensor {
     u32 n_limbs;      // limbs per poly
     u32 a_size, b_size;
     u64 per_batch;    // n_limbs * N
-    u64 total;        // batch * n_limbs * N
+    u64 total;        // batch * n_limbs * N / 2 threads (two adjacent coefficients per thread, 128-bit accesses)
     const u64 *a, *b;
     u64 *out;
     u64 a_batch_stride, b_batch_stride, out_batch_stride; // words
+    static TB_D ulonglong2 ld2(const u64 *p) { return *reinterpret_cast<const ulonglong2 *>(p); }
+    static TB_D void st2(u64 *p, u64 x, u64 y) {
+        ulonglong2 v;
+        v.x = x; v.y = y;
+        *reinterpret_cast<ulonglong2 *>(p) = v;
+    }
     TB_D void operator()(u32 bid, u64 *) const {
         TB_PHASE(kThreads, t, {
             u64 idx = (u64)bid * kThreads + t;
             if (idx < total) {
-                u64 bt = idx / per_batch, rem = idx % per_batch;
+                const u64 half = per_batch >> 1;
+                u64 bt = idx / half, rem = (idx % half) * 2;
                 u32 limb = (u32)(rem >> logN);
                 const ModDev &m = mods[map.idx[limb]];
+                const u64 p = m.p, r0 = m.ratio0, r1 = m.ratio1, mu = m.bar_mu;
+                const u32 sh = m.bar_shift;
                 const u64 *pa = a + bt * a_batch_stride + rem;
                 const u64 *pb = b + bt * b_batch_stride + rem;
                 u64 *po = out + bt * out_batch_stride + rem;
                 if (a_size == 2 && b_size == 2) {
-                    u64 a0 = pa[0], a1 = pa[per_batch], b0 = pb[0], b1 = pb[per_batch];
-                    u64 lo = 0, hi = 0;
-                    mac128(lo, hi, a0, b0);
-                    u64 c0 = barrett128(lo, hi, m.p, m.ratio0, m.ratio1);
+                    const ulonglong2 a0 = ld2(pa), a1 = ld2(pa + per_batch), b0 = ld2(pb), b1 = ld2(pb + per_batch);
+                    // residues below p < 2^61: sums of at most two products are below 2^(n+63) (reduce_sum)
+                    u64 lo, hi;
+                    u64 c0x = reduce_sum(a0.x * b0.x, mulhi64(a0.x, b0.x), p, mu, sh);
+                    u64 c0y = reduce_sum(a0.y * b0.y, mulhi64(a0.y, b0.y), p, mu, sh);
                     lo = 0; hi = 0;
-                    mac128(lo, hi, a0, b1);
-                    mac128(lo, hi, a1, b0);
-                    u64 c1 = barrett128(lo, hi, m.p, m.ratio0, m.ratio1);
+                    mac128(lo, hi, a0.x, b1.x);
+                    mac128(lo, hi, a1.x, b0.x);
+                    u64 c1x = reduce_sum(lo, hi, p, mu, sh);
                     lo = 0; hi = 0;
-                    mac128(lo, hi, a1, b1);
-                    u64 c2 = barrett128(lo, hi, m.p, m.ratio0, m.ratio1);
-                    po[0] = c0; po[per_batch] = c1; po[2 * per_batch] = c2;
+                    mac128(lo, hi, a0.y, b1.y);
+                    mac128(lo, hi, a1.y, b0.y);
+                    u64 c1y = reduce_sum(lo, hi, p, mu, sh);
+                    u64 c2x = reduce_sum(a1.x * b1.x, mulhi64(a1.x, b1.x), p, mu, sh);
+                    u64 c2y = reduce_sum(a1.y * b1.y, mulhi64(a1.y, b1.y), p, mu, sh);
+                    st2(po, c0x, c0y);
+                    st2(po + per_batch, c1x, c1y);
+                    st2(po + 2 * per_batch, c2x, c2y);
                 } else {
-                    u64 av[8], bv[8], cv[15];
-                    for (u32 j = 0; j < a_size; j++) av[j] = pa[j * per_batch];
-                    for (u32 k = 0; k < b_size; k++) bv[k] = pb[k * per_batch];
+                    u64 av[8][2], bv[8][2], cv[15][2];
+                    for (u32 j = 0; j < a_size; j++) { ulonglong2 v = ld2(pa + j * per_batch); av[j][0] = v.x; av[j][1] = v.y; }
+                    for (u32 k = 0; k < b_size; k++) { ulonglong2 v = ld2(pb + k * per_batch); bv[k][0] = v.x; bv[k][1] = v.y; }
                     for (u32 i = 0; i < a_size + b_size - 1; i++) {
-                        u64 lo = 0, hi = 0;
-                        for (u32 j = 0; j < a_size; j++) {
-                            if (i >= j && i - j < b_size) mac128(lo, hi, av[j], bv[i - j]);
+                        for (u32 e = 0; e < 2; e++) {
+                            u64 lo = 0, hi = 0;
+                            for (u32 j = 0; j < a_size; j++) {
+                                if (i >= j && i - j < b_size) mac128(lo, hi, av[j][e], bv[i - j][e]);
+                            }
+                            cv[i][e] = barrett128(lo, hi, p, r0, r1);
                         }
-                        cv[i] = barrett128(lo, hi, m.p, m.ratio0, m.ratio1);
                     }
-                    for (u32 i = 0; i < a_size + b_size - 1; i++) po[i * per_batch] = cv[i];
+                    for (u32 i = 0; i < a_size + b_size - 1; i++) st2(po + i * per_batch, cv[i][0], cv[i][1]);
                 }
             }
         })
@@ -110,10 +128,92 @@ struct EltTensor {
 
 // ---- key-switch inner product -----------------------------------------------------------------------------
 // gSwitchKeyInplaceUtilB + UtilD  src/evaluator_cuda.cu:1034-1085: acc[k] = sum_j D[i][j] * key[j][k][key_index]
-// with 128-bit lazy accumulators kept in registers, one Barrett-128 at the end.
+// with lazy accumulators kept in registers, one Barrett-128 at the end.
 //   D    : [batch][L+1][nd][N]  mod-up output of digits digit0..digit0+nd-1 (canonical)
 //   key  : [digits][2][key_limbs][N]
 //   prod : [batch][2][L+1][N]  (t_poly_prod layout, §A.8)
+//
+// Sum of products of residues below 2^60 (every key-switch modulus is a user prime, at most 60 bits) held as five
+// columns of partial products of 16/32-bit limbs of x with 32-bit limbs of k:
+//   c0l = sum x0l*k0, c0h = sum x0h*k0 (x0 = x0h 2^16 + x0l), c1a = sum x0*k1, c1b = sum x1*k0, c2 = sum x1*k1,
+//   value = c0l + c0h 2^16 + (c1a + c1b) 2^32 + c2 2^64.
+// Every product is below 2^60 (x1, k1 < 2^28), so eight terms accumulate in 64 bits through the multiply-add's own
+// 64-bit addend (IMAD.WIDE): five multiply instructions per term and nothing else, no carries until fold(), which must
+// be called after at most kFoldEvery terms.
+struct ColumnAcc {
+    static constexpr u32 kFoldEvery = 8;
+    u64 c0l, c0h, c1a, c1b, c2;
+    u64 lo, hi; // folded 128-bit sum
+    TB_D void init() { c0l = c0h = c1a = c1b = c2 = 0; lo = hi = 0; }
+    // c += a * b as ONE multiply-add with a 64-bit addend. Written as PTX on the GPU so that the accumulators stay
+    // 64-bit register pairs (the compiler otherwise splits them into halves and adds the zero initial value separately).
+    static TB_D void madw(u64 &c, u32 a, u32 b) {
+#if defined(TROYB_HOST_EMUL)
+        c += (u64)a * b;
+#else
+        asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c) : "r"(a), "r"(b));
+#endif
+    }
+    static TB_D u64 mulw(u32 a, u32 b) {
+#if defined(TROYB_HOST_EMUL)
+        return (u64)a * b;
+#else
+        u64 c;
+        asm("mul.wide.u32 %0, %1, %2;" : "=l"(c) : "r"(a), "r"(b));
+        return c;
+#endif
+    }
+    // first term: plain products, no addend
+    TB_D void mac_first(u32 xl, u32 xh, u32 x0, u32 x1, u64 k) {
+        const u32 k0 = (u32)k, k1 = (u32)(k >> 32);
+        c0l = mulw(xl, k0);
+        c0h = mulw(xh, k0);
+        c1a = mulw(x0, k1);
+        c1b = mulw(x1, k0);
+        c2 = mulw(x1, k1);
+        lo = hi = 0;
+    }
+    // xl, xh, x1: the low 16 bits, bits 16-31 and the high word of x
+    TB_D void mac(u32 xl, u32 xh, u32 x0, u32 x1, u64 k) {
+        const u32 k0 = (u32)k, k1 = (u32)(k >> 32);
+        madw(c0l, xl, k0);
+        madw(c0h, xh, k0);
+        madw(c1a, x0, k1);
+        madw(c1b, x1, k0);
+        madw(c2, x1, k1);
+    }
+    TB_D void fold() {
+        // bits 0..63 and the carries into bit 64
+        u64 l = c0l, h = c2;
+        u64 t = c0h << 16;
+        l += t; h += (l < t);
+        h += c0h >> 48;
+        t = c1a << 32;
+        l += t; h += (l < t);
+        h += c1a >> 32;
+        t = c1b << 32;
+        l += t; h += (l < t);
+        h += c1b >> 32;
+        lo += l;
+        hi += h + (lo < l);
+        c0l = c0h = c1a = c1b = c2 = 0;
+    }
+};
+struct XLimbs {
+    u32 xl, xh, x0, x1;
+    TB_D explicit XLimbs(u64 x) {
+        x0 = (u32)x;
+        x1 = (u32)(x >> 32);
+#if defined(TROYB_HOST_EMUL)
+        xl = x0 & 0xFFFFu;
+        xh = x0 >> 16;
+#else
+        xl = __byte_perm(x0, 0, 0x4410); // one PRMT each
+        xh = __byte_perm(x0, 0, 0x4432);
+#endif
+    }
+};
+
 struct KsInnerProduct {
     static constexpr int kThreads = kEltThreads;
     const char *name() const { return "ks_inner_product"; }
@@ -144,14 +244,17 @@ struct KsInnerProduct {
                 const u64 *d = D + (bi * nd) * N + c;
                 const u64 *kp = key + (u64)key_limb * N + c + (u64)digit0 * 2 * key_limbs * N;
                 const u64 key_digit_stride = 2ull * key_limbs * N, key_comp_stride = (u64)key_limbs * N;
-                u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0, lo2 = 0, hi2 = 0, lo3 = 0, hi3 = 0;
-                const u64 *ps = (pass != nullptr && i < L) ? pass + b * pass_stride + (u64)i * N + c : nullptr;
+                ColumnAcc a0, a1, a2, a3;
+                a0.init(); a1.init(); a2.init(); a3.init();
+                // digit i - digit0 of output modulus i < L is read from the NTT-form target itself
+                const u32 jpass = (pass != nullptr && i < L && i >= digit0) ? i - digit0 : 0xFFFFFFFFu;
+                const u64 *ps = pass + b * pass_stride + (u64)i * N + c;
                 for (u32 j0 = 0; j0 < nd; j0 += 4) { // four digits' loads in flight
                     ulonglong2 x[4], k0[4], k1[4];
                     _Pragma("unroll") for (u32 q = 0; q < 4; q++) {
                         const u32 j = j0 + q;
                         if (j < nd) {
-                            const u64 *src = (ps != nullptr && j + digit0 == i) ? ps : d + (u64)j * N;
+                            const u64 *src = (j == jpass) ? ps : d + (u64)j * N;
                             x[q] = *reinterpret_cast<const ulonglong2 *>(src);
                             k0[q] = __ldg(reinterpret_cast<const ulonglong2 *>(kp + j * key_digit_stride));
                             k1[q] = __ldg(reinterpret_cast<const ulonglong2 *>(kp + j * key_digit_stride + key_comp_stride));
@@ -159,21 +262,140 @@ struct KsInnerProduct {
                     }
                     _Pragma("unroll") for (u32 q = 0; q < 4; q++) {
                         if (j0 + q < nd) {
-                            mac128(lo0, hi0, x[q].x, k0[q].x);
-                            mac128(lo1, hi1, x[q].y, k0[q].y);
-                            mac128(lo2, hi2, x[q].x, k1[q].x);
-                            mac128(lo3, hi3, x[q].y, k1[q].y);
+                            const XLimbs xa(x[q].x), xb(x[q].y);
+                            a0.mac(xa.xl, xa.xh, xa.x0, xa.x1, k0[q].x);
+                            a1.mac(xb.xl, xb.xh, xb.x0, xb.x1, k0[q].y);
+                            a2.mac(xa.xl, xa.xh, xa.x0, xa.x1, k1[q].x);
+                            a3.mac(xb.xl, xb.xh, xb.x0, xb.x1, k1[q].y);
                         }
+                    }
+                    if (((j0 + 4) % ColumnAcc::kFoldEvery) == 0 || j0 + 4 >= nd) {
+                        a0.fold(); a1.fold(); a2.fold(); a3.fold();
                     }
                 }
                 u64 *po = prod + (b * 2 * (L + 1) + i) * N + c;
                 ulonglong2 r0, r1;
-                r0.x = barrett128(lo0, hi0, m.p, m.ratio0, m.ratio1);
-                r0.y = barrett128(lo1, hi1, m.p, m.ratio0, m.ratio1);
-                r1.x = barrett128(lo2, hi2, m.p, m.ratio0, m.ratio1);
-                r1.y = barrett128(lo3, hi3, m.p, m.ratio0, m.ratio1);
+                r0.x = barrett128(a0.lo, a0.hi, m.p, m.ratio0, m.ratio1);
+                r0.y = barrett128(a1.lo, a1.hi, m.p, m.ratio0, m.ratio1);
+                r1.x = barrett128(a2.lo, a2.hi, m.p, m.ratio0, m.ratio1);
+                r1.y = barrett128(a3.lo, a3.hi, m.p, m.ratio0, m.ratio1);
                 *reinterpret_cast<ulonglong2 *>(po) = r0;
                 *reinterpret_cast<ulonglong2 *>(po + (u64)(L + 1) * N) = r1;
+            }
+        })
+    }
+};
+
+// The same inner product with the key slice of the CTA staged in shared memory and reused for `bc` ciphertexts of the
+// batch: a CTA owns (512 coefficients, output modulus i, a group of bc batch elements), copies key[j][k][i][its 512
+// coefficients] for the ND <= 8 digits of the launch once (ND * 8 KiB), then streams the mod-up rows of its
+// batch elements (ND is a template parameter so that the digit loops unroll without guards). The key's L2 -> SM traffic (twice the size of D when every ciphertext fetches it again) drops by bc,
+// and for keys larger than the L2 (N = 65536, 40 limbs) so does its HBM traffic.
+//   accumulate : add the previous contents of prod (launches over successive digit groups of one key switch)
+template <int ND> struct KsInnerProductStaged {
+    static constexpr int kThreads = kEltThreads;
+    static constexpr int kMinCtas = 2; // up to 128 registers: two batch elements' rows plus twenty 64-bit columns
+    static constexpr u32 kCoeffs = 2 * kEltThreads; // per CTA
+    static_assert(ND >= 1 && ND <= (int)ColumnAcc::kFoldEvery, "one fold per launch");
+    const char *name() const { return "ks_inner_product"; }
+    int logN;
+    const ModDev *mods;
+    LimbMap map;
+    u32 L, digit0, key_limbs, special_key_limb; // ND digits from digit0
+    u32 batch, bc;        // batch elements in the launch / per CTA
+    u32 d_rows, d_row0;   // rows of D per (batch element, output modulus) and the row of this launch's first digit
+    int accumulate;
+    const u64 *D;
+    const u64 *key;
+    u64 *prod;
+    const u64 *pass;
+    u64 pass_stride;
+    static size_t smem_bytes() { return (size_t)ND * 2 * kCoeffs * sizeof(u64); }
+    // grid = (N / kCoeffs) * (L + 1) * ceil(batch / bc), coefficient block fastest
+    TB_D void operator()(u32 bid, u64 *sm) const {
+        const u64 N = u64(1) << logN;
+        const u32 blocks = (u32)(N / kCoeffs);
+        const u32 cb = bid % blocks, i = (bid / blocks) % (L + 1), bg = bid / blocks / (L + 1);
+        const u32 key_limb = (i == L) ? special_key_limb : i;
+        const u64 key_digit_stride = 2ull * key_limbs * N, key_comp_stride = (u64)key_limbs * N;
+        const u64 *kp = key + (u64)key_limb * N + (u64)cb * kCoeffs + (u64)digit0 * key_digit_stride;
+        TB_PHASE(kThreads, t, {
+            _Pragma("unroll") for (u32 r = 0; r < ND * 2; r++) {
+                const u64 *src = kp + (u64)(r >> 1) * key_digit_stride + (u64)(r & 1) * key_comp_stride + 2 * t;
+                *reinterpret_cast<ulonglong2 *>(sm + (u64)r * kCoeffs + 2 * t) = __ldg(reinterpret_cast<const ulonglong2 *>(src));
+            }
+        })
+        TB_PHASE(kThreads, t, {
+            const ModDev &m = mods[map.idx[i]];
+            const u64 p = m.p, mu = m.bar_mu;
+            const u32 sh = m.bar_shift;
+            const u64 c = (u64)cb * kCoeffs + 2 * t;
+            // digit i of output modulus i < L is the NTT-form target itself (pass): its row of D is never written or read
+            const u32 jpass = (pass != nullptr && i < L && i >= digit0 && i - digit0 < ND) ? i - digit0 : 0xFFFFFFFFu;
+            const u32 b_end = (bg + 1) * bc < batch ? (bg + 1) * bc : batch;
+            const u64 d_stride = (u64)(L + 1) * d_rows * N;
+            const u64 *d = D + (((u64)(bg * bc) * (L + 1) + i) * d_rows + d_row0) * N + c;
+            const u64 *ps = pass + (u64)(bg * bc) * pass_stride + (u64)i * N + c;
+            u64 *po = prod + ((u64)(bg * bc) * 2 * (L + 1) + i) * N + c;
+            // The rows of batch element b + 1 are requested before the products of b are formed: eight 16-byte loads per
+            // thread stay in flight for a whole iteration (the kernel is bound by HBM latency x bytes in flight otherwise).
+            ulonglong2 x[ND], xn[ND], xp, xpn;
+            auto load_rows = [&](ulonglong2 (&v)[ND], ulonglong2 &vp, const u64 *dd, const u64 *pp) {
+                _Pragma("unroll") for (u32 j = 0; j < ND; j++) {
+                    v[j].x = 0; v[j].y = 0;
+                    if (j != jpass) v[j] = *reinterpret_cast<const ulonglong2 *>(dd + (u64)j * N);
+                }
+                vp.x = 0; vp.y = 0;
+                if (jpass != 0xFFFFFFFFu) vp = *reinterpret_cast<const ulonglong2 *>(pp);
+            };
+            if (bg * bc < b_end) load_rows(x, xp, d, ps);
+            for (u32 b = bg * bc; b < b_end; b++, d += d_stride, ps += pass_stride, po += 2ull * (L + 1) * N) {
+                if (b + 1 < b_end) load_rows(xn, xpn, d + d_stride, ps + pass_stride);
+                ulonglong2 old0, old1;
+                if (accumulate) {
+                    old0 = *reinterpret_cast<const ulonglong2 *>(po);
+                    old1 = *reinterpret_cast<const ulonglong2 *>(po + (u64)(L + 1) * N);
+                }
+                ColumnAcc a0, a1, a2, a3;
+                _Pragma("unroll") for (u32 j = 0; j < ND; j++) {
+                    const ulonglong2 k0 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * j) * kCoeffs + 2 * t);
+                    const ulonglong2 k1 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * j + 1) * kCoeffs + 2 * t);
+                    const XLimbs xa(x[j].x), xb(x[j].y);
+                    if (j == 0) {
+                        a0.mac_first(xa.xl, xa.xh, xa.x0, xa.x1, k0.x);
+                        a1.mac_first(xb.xl, xb.xh, xb.x0, xb.x1, k0.y);
+                        a2.mac_first(xa.xl, xa.xh, xa.x0, xa.x1, k1.x);
+                        a3.mac_first(xb.xl, xb.xh, xb.x0, xb.x1, k1.y);
+                    } else {
+                        a0.mac(xa.xl, xa.xh, xa.x0, xa.x1, k0.x);
+                        a1.mac(xb.xl, xb.xh, xb.x0, xb.x1, k0.y);
+                        a2.mac(xa.xl, xa.xh, xa.x0, xa.x1, k1.x);
+                        a3.mac(xb.xl, xb.xh, xb.x0, xb.x1, k1.y);
+                    }
+                }
+                if (jpass != 0xFFFFFFFFu) { // CTA-uniform
+                    const ulonglong2 k0 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * jpass) * kCoeffs + 2 * t);
+                    const ulonglong2 k1 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * jpass + 1) * kCoeffs + 2 * t);
+                    const XLimbs xa(xp.x), xb(xp.y);
+                    a0.mac(xa.xl, xa.xh, xa.x0, xa.x1, k0.x);
+                    a1.mac(xb.xl, xb.xh, xb.x0, xb.x1, k0.y);
+                    a2.mac(xa.xl, xa.xh, xa.x0, xa.x1, k1.x);
+                    a3.mac(xb.xl, xb.xh, xb.x0, xb.x1, k1.y);
+                }
+                a0.fold(); a1.fold(); a2.fold(); a3.fold();
+                ulonglong2 q0, q1;
+                q0.x = reduce_sum(a0.lo, a0.hi, p, mu, sh);
+                q0.y = reduce_sum(a1.lo, a1.hi, p, mu, sh);
+                q1.x = reduce_sum(a2.lo, a2.hi, p, mu, sh);
+                q1.y = reduce_sum(a3.lo, a3.hi, p, mu, sh);
+                if (accumulate) {
+                    q0.x = addmod(q0.x, old0.x, p); q0.y = addmod(q0.y, old0.y, p);
+                    q1.x = addmod(q1.x, old1.x, p); q1.y = addmod(q1.y, old1.y, p);
+                }
+                *reinterpret_cast<ulonglong2 *>(po) = q0;
+                *reinterpret_cast<ulonglong2 *>(po + (u64)(L + 1) * N) = q1;
+                _Pragma("unroll") for (u32 j = 0; j < ND; j++) x[j] = xn[j];
+                xp = xpn;
             }
         })
     }

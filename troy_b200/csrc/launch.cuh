@@ -88,7 +88,12 @@ template <class F> inline cudaError_t launch_cluster(const F &f, u32 grid, u32 n
     }                                              \
     __syncthreads();
 
-template <class F> __global__ void __launch_bounds__(F::kThreads) k_cta(const F f) {
+// Resident CTAs per SM the register allocation should allow: F::kMinCtas when the functor declares it (0 = leave the
+// choice to ptxas, which is not the same as asking for 1).
+template <class F, class = void> struct MinCtas { static constexpr int value = 0; };
+template <class F> struct MinCtas<F, decltype((void)F::kMinCtas)> { static constexpr int value = F::kMinCtas; };
+
+template <class F> __global__ void __launch_bounds__(F::kThreads, MinCtas<F>::value) k_cta(const F f) {
     extern __shared__ __align__(16) u64 tb_smem[];
     f(blockIdx.x, tb_smem);
 }

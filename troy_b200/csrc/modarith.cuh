@@ -54,6 +54,18 @@ TB_HD u64 barrett128(u64 lo, u64 hi, u64 q, u64 ratio0, u64 ratio1) {
     return r >= q ? r - q : r;
 }
 
+// (hi:lo) mod q for a value below 2^(n+63), n = bit length of q (e.g. a sum of at most 8 products of residues when
+// n <= 60, or of 2 products when n = 61): one-word Barrett with mu = floor(2^(n-1+64)/q), shift = n - 1. The quotient
+// estimate is at most 2 too small, so the remainder lies in [0, 3q). Our own reduction (the reference reduces such sums
+// with barrettReduce128); the canonical result is the same number.
+TB_HD u64 reduce_sum(u64 lo, u64 hi, u64 q, u64 mu, u32 shift) {
+    const u64 a = (hi << (64 - shift)) | (lo >> shift); // shift in [1, 60]
+    const u64 r0 = lo - mulhi64(a, mu) * q;
+    const u64 q2 = q << 1;
+    const u64 r1 = r0 - (r0 >= q2 ? q2 : 0);
+    return r1 - (r1 >= q ? q : 0);
+}
+
 TB_HD u64 mulmod_barrett(u64 a, u64 b, u64 q, u64 ratio0, u64 ratio1) {
     return barrett128(a * b, mulhi64(a, b), q, ratio0, ratio1);
 }
