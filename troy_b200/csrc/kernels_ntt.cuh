@@ -130,6 +130,7 @@ struct NttUnit {
     u64 *ct;          // ciphertext row (read-modify-write)
     DropLimb dl;
     bool passthrough; // MODUP with i == j in CKKS: copy the NTT-form limb
+    bool reduce_src;  // MODUP: the digit must be reduced mod q_i before the transform
     u32 row;          // four-step row
     u32 rows_log;
     u32 unit;
@@ -168,6 +169,9 @@ template <int LOGT> TB_D NttUnit resolve_unit(const NttArgs &a, u32 bid) {
         u.src = a.src + (u64)b * a.src_unit_stride + (u64)j * N;
         u.dst = a.dst + (u64)u.unit * N;
         if (a.aux0 != nullptr && i == j + a.digit0) u.passthrough = true; // the inner product reads the NTT-form limb in place
+        // a digit whose own modulus is below 4 q_i is already a valid lazy input of the forward transform (every
+        // butterfly policy accepts [0, 4p)): its Barrett reduction mod q_i is skipped (results are canonical either way)
+        u.reduce_src = (a.mods[a.map.idx[j + a.digit0]].p >> 2) >= u.md->p;
         break;
     }
     case INV_ADD_HALF: {
@@ -242,16 +246,26 @@ struct FwdStore {
     NttUnit u;
     u64 p;
     int mode;
-    TB_D u64 finish(u64 acc, u64 v) const { return shoup(submod(acc, v, p), u.dl.inv_last, u.dl.inv_last_shoup, p); }
-    TB_D void operator()(u32 i, u64 v) const {
+    struct Pre { u64 acc, ct; }; // global operands of output i, loaded ahead of the store loop (tile_store_canon)
+    TB_D Pre pre(u32 i) const {
+        Pre r{0, 0};
         if (mode == FWD_MODDOWN) {
-            u64 r = finish(u.acc[i], v);
-            if (u.ct) u.ct[i] = addmod(u.ct[i], r, p);
+            r.acc = u.acc[i];
+            if (u.ct) r.ct = u.ct[i];
+        }
+        return r;
+    }
+    TB_D u64 finish(u64 acc, u64 v) const { return shoup(submod(acc, v, p), u.dl.inv_last, u.dl.inv_last_shoup, p); }
+    TB_D void operator()(u32 i, u64 v, const Pre &q) const {
+        if (mode == FWD_MODDOWN) {
+            u64 r = finish(q.acc, v);
+            if (u.ct) u.ct[i] = addmod(q.ct, r, p);
             else u.dst[i] = r;
         } else {
             u.dst[i] = v;
         }
     }
+    TB_D void operator()(u32 i, u64 v) const { (*this)(i, v, pre(i)); }
 };
 
 // Epilogue of a completed inverse transform (v = canonical residue of coefficient idx of the limb).
@@ -339,7 +353,8 @@ template <int LOGT> struct NttFwdTile {
         NttUnit u = resolve_unit<LOGT>(a, bid);
         const ModDev *md = u.md;
         const int pol = md->policy;
-        const FwdPrologue pro{md->p, md->ratio1, a.mode == FWD_MODDOWN ? md->p - u.dl.half_mod : 0, a.mode};
+        const FwdPrologue pro{md->p, md->ratio1, a.mode == FWD_MODDOWN ? md->p - u.dl.half_mod : 0,
+                              (a.mode == FWD_MODUP && !u.reduce_src) ? (int)FWD_PLAIN : a.mode};
         if constexpr (S == 0) {
             prefetch_tiles<LOGT>(a, u, bid, rank, grid);
             // scatter stage: the layers that couple the tiles, results into the peers' shared memory

@@ -546,10 +546,19 @@ template <class A, int LOGT, class St> TB_D void tile_store_canon(const u64 *sm,
     typedef TilePlan<LOGT> P;
     constexpr int NT = P::NT, T = 1 << LOGT;
     const typename A::Mod m = A::make(md);
+    // The epilogue's own global operands (St::Pre: accumulator and ciphertext words of the mod-down tail) are requested
+    // for UB outputs before any of them is used or stored: one memory latency per UB outputs instead of one per output
+    // (the compiler cannot hoist those loads above the stores, which may alias them).
+    constexpr int UB = 8;
+    static_assert((T / NT) % UB == 0, "bad store batch");
     TB_PHASE(NT, t, {
-        _Pragma("unroll 4") for (int k = 0; k < T / NT; k++) {
-            const u32 i = t + k * NT;
-            st(i, A::canon(A::from_bits(sm[pad_idx(i)]), m));
+        _Pragma("unroll 1") for (int k0 = 0; k0 < T / NT; k0 += UB) {
+            typename St::Pre pre[UB];
+            _Pragma("unroll") for (int k = 0; k < UB; k++) pre[k] = st.pre(t + (k0 + k) * NT);
+            _Pragma("unroll") for (int k = 0; k < UB; k++) {
+                const u32 i = t + (k0 + k) * NT;
+                st(i, A::canon(A::from_bits(sm[pad_idx(i)]), m), pre[k]);
+            }
         }
     })
 }
