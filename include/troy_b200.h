@@ -147,6 +147,39 @@ int troyb_apply_galois(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_
 int troyb_mod_switch_scale_to_next(troyb_context *ctx, int level, const uint64_t *d_in, size_t in_stride, uint64_t *d_out,
                                    size_t out_stride, size_t size, size_t batch, void *stream);
 
+/* ---- ciphertext (x) plaintext: the callers right next to the path ------------------------------ */
+
+/* EvaluatorCuda::multiplyPlainNtt  src/evaluator_cuda.cu:1818-1862 (kDyadicProductCoeffmod per poly, src/kernelutils.cu:151):
+ * out[b][k] = ct[b][k] * plain[b] limb-wise, both in NTT form over the level's L limbs; plain is [L][N].
+ * plain_stride = 0: one plaintext for the whole batch. d_out may alias d_ct. accumulate != 0: out += ct * plain
+ * (the multiplyPlain + addInplace pair of MatmulHelper::matmul, app/LinearHelperCKKS.cuh:225-249, in one pass). */
+int troyb_multiply_plain_ntt(troyb_context *ctx, int level, const uint64_t *d_ct, size_t ct_size, size_t ct_stride,
+                             const uint64_t *d_plain, size_t plain_stride, uint64_t *d_out, size_t out_stride, size_t batch,
+                             int accumulate, void *stream);
+
+/* Plaintext lift of BFV / BGV: `batch` coefficient-form plaintexts of plain_coeff_count words modulo t (plain_stride words
+ * apart) become [batch][L][N] centred residues over the level's limbs; to_ntt != 0 also transforms them.
+ * gMultiplyPlainNormalUtilA/B src/evaluator_cuda.cu:1724-1755; EvaluatorCuda::transformToNttInplace(PlaintextCuda&, ParmsID)
+ * src/evaluator_cuda.cu:1865-1935 (to_ntt = 1). */
+int troyb_plain_lift(troyb_context *ctx, int level, const uint64_t *d_plain, size_t plain_coeff_count, size_t plain_stride,
+                     uint64_t *d_out, size_t batch, int to_ntt, void *stream);
+
+/* EvaluatorCuda::multiplyPlainNormal  src/evaluator_cuda.cu:1757-1816 (CPU src/evaluator.cpp:1790-1935): coefficient-form
+ * ciphertexts [ct_size][L][N] times ONE coefficient-form plaintext, in place; canonical output (the CPU path's fully
+ * reduced inverse transform). The CPU path's monomial shortcut (src/evaluator.cpp:1817-1850) is not reproduced: like the
+ * reference's CUDA path this always takes the generic route. */
+int troyb_multiply_plain_normal(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_size, size_t ct_stride,
+                                const uint64_t *d_plain, size_t plain_coeff_count, size_t batch, void *stream);
+
+/* EvaluatorCuda::addPlainInplace / subPlainInplace for BFV and BGV  src/evaluator_cuda.cu:1555-1700:
+ *   BFV: multiplyAdd/SubPlainWithScalingVariant  src/utils/scalingvariant_cuda.cu:82-175
+ *   BGV: plain * correction_factor mod t, then add/subPlainWithoutScalingVariant  scalingvariant_cuda.cu:21-80
+ * d_c0: the first poly of each ciphertext ([L][N], ct_stride words apart). plain_stride = 0: one plaintext for all.
+ * (CKKS adds an NTT-form plaintext with troyb_add / troyb_sub on poly 0.) */
+int troyb_add_plain(troyb_context *ctx, int level, uint64_t *d_c0, size_t ct_stride, const uint64_t *d_plain,
+                    size_t plain_coeff_count, size_t plain_stride, uint64_t correction_factor, int subtract, size_t batch,
+                    void *stream);
+
 #ifdef __cplusplus
 }
 #endif

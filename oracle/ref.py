@@ -47,6 +47,12 @@ def lib():
             "ref_rns_op": (C.c_int, [vp, C.c_int, C.c_int, u64p, u64p]),
             "ref_galois_elt_from_step": (C.c_uint32, [vp, C.c_int]),
             "ref_apply_galois_poly": (C.c_int, [vp, C.c_int, u64p, C.c_int, C.c_uint32, u64p, C.c_int]),
+            "ref_pt_new": (vp, [vp, u64p, C.c_uint64, C.c_int, C.c_double]),
+            "ref_pt_destroy": (None, [vp]),
+            "ref_pt_count": (C.c_uint64, [vp]),
+            "ref_pt_words": (C.c_int, [vp, u64p]),
+            "ref_pt_to_ntt": (C.c_int, [vp, vp, C.c_int]),
+            "ref_eval_plain": (C.c_int, [vp, C.c_int, vp, vp]),
             "ref_keygen": (C.c_int, [vp]),
             "ref_relin_keys": (vp, [vp]),
             "ref_galois_keys_elts": (vp, [vp, C.POINTER(C.c_uint32), C.c_int]),
@@ -158,6 +164,30 @@ class RefKeys:
             raise RefError(_err())
 
 
+PLAIN_MULTIPLY, PLAIN_ADD, PLAIN_SUB = 1, 2, 3
+
+
+class RefPlaintext:
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_pt_destroy(self.h)
+            self.h = None
+
+    def words(self):
+        out = np.zeros(int(lib().ref_pt_count(self.h)), dtype=np.uint64)
+        lib().ref_pt_words(self.h, _p(out))
+        return out
+
+    def to_ntt(self, level):
+        """Evaluator::transformToNttInplace(Plaintext&, ParmsID)"""
+        if lib().ref_pt_to_ntt(self.ctx.h, self.h, level) != 0:
+            raise RefError(_err())
+        return self
+
+
 class RefContext:
     """The reference SEALContext + Evaluator (+ KeyGenerator/Encryptor/Decryptor/encoders after keygen())."""
 
@@ -251,6 +281,19 @@ class RefContext:
         if not h:
             raise RefError(_err())
         return RefCiphertext(self, h)
+
+    # -- plaintexts (ntt_level None: coefficient form modulo t; else L*N words in NTT form at that level)
+    def plaintext(self, words, ntt_level=None, scale=1.0):
+        w = np.ascontiguousarray(words, dtype=np.uint64).reshape(-1)
+        h = lib().ref_pt_new(self.h, _p(w), w.size, -1 if ntt_level is None else ntt_level, scale)
+        if not h:
+            raise RefError(_err())
+        return RefPlaintext(self, h)
+
+    def eval_plain(self, op, a, pt):
+        if lib().ref_eval_plain(self.h, op, a.h, pt.h) != 0:
+            raise RefError(_err())
+        return a
 
     def eval(self, op, a, b=None, keys=None, arg=0):
         r = lib().ref_eval(self.h, op, a.h, b.h if b is not None else None, keys.h if keys is not None else None, arg)

@@ -419,6 +419,51 @@ int ref_eval(void *h, int op, void *cta, void *ctb, void *keys, int64_t arg) {
     REF_CATCH(-1)
 }
 
+// ---- plaintexts and ciphertext (x) plaintext ops (src/evaluator.cpp:1603-1985, 1987-2060) ------------------
+// ntt_level < 0: coefficient-form plaintext modulo t (parms_id zero); otherwise `count` = L*N words in NTT form at that level.
+void *ref_pt_new(void *h, const uint64_t *words, uint64_t count, int ntt_level, double scale) {
+    REF_TRY
+    auto c = static_cast<RefCtx *>(h);
+    auto pt = std::make_unique<Plaintext>();
+    pt->resize(count);
+    std::memcpy(pt->data(), words, count * sizeof(uint64_t));
+    if (ntt_level >= 0) pt->parmsID() = c->chain.at(ntt_level);
+    pt->scale() = scale;
+    return pt.release();
+    REF_CATCH(nullptr)
+}
+void ref_pt_destroy(void *pth) { delete static_cast<Plaintext *>(pth); }
+uint64_t ref_pt_count(void *pth) { return static_cast<Plaintext *>(pth)->coeffCount(); }
+int ref_pt_words(void *pth, uint64_t *out) {
+    auto pt = static_cast<Plaintext *>(pth);
+    std::memcpy(out, pt->data(), pt->coeffCount() * sizeof(uint64_t));
+    return 0;
+}
+// Evaluator::transformToNttInplace(Plaintext &, ParmsID)
+int ref_pt_to_ntt(void *h, void *pth, int level) {
+    REF_TRY
+    auto c = static_cast<RefCtx *>(h);
+    c->evaluator->transformToNttInplace(*static_cast<Plaintext *>(pth), c->chain.at(level));
+    return 0;
+    REF_CATCH(-1)
+}
+// op: 1 multiplyPlainInplace, 2 addPlainInplace, 3 subPlainInplace
+int ref_eval_plain(void *h, int op, void *cta, void *pth) {
+    REF_TRY
+    auto c = static_cast<RefCtx *>(h);
+    auto &ev = *c->evaluator;
+    auto a = static_cast<Ciphertext *>(cta);
+    auto p = static_cast<Plaintext *>(pth);
+    switch (op) {
+    case 1: ev.multiplyPlainInplace(*a, *p); break;
+    case 2: ev.addPlainInplace(*a, *p); break;
+    case 3: ev.subPlainInplace(*a, *p); break;
+    default: g_last_error = "bad op"; return -1;
+    }
+    return 0;
+    REF_CATCH(-1)
+}
+
 // ---- encode / encrypt / decrypt (functional round trips; host-side, seeded PRNG) -------------
 void *ref_encrypt_batch(void *h, const uint64_t *values, int count) {
     REF_TRY

@@ -104,3 +104,84 @@ def run_evaluator_flow(ref, tb, scheme, n, bits, rng, batch=1):
         assert_same(c, rc0, "transform_to_ntt")
         ev.transform_from_ntt_inplace(c); rc.eval(ref.OP_FROM_NTT, rc0)
     assert_same(c, rc0, "transform round trip")
+
+
+def run_plain_flow(ref, tb, scheme, n, bits, rng, batch=2, level=0):
+    """The ciphertext (x) plaintext callers next to the path, every word against the reference:
+    CKKS: multiply_plain (NTT form), add_plain, sub_plain, fused multiply-accumulate (matmul step);
+    BFV / BGV: multiply_plain (coefficient form), add_plain, sub_plain, plaintext transform_to_ntt + multiply_plain (NTT)."""
+    rc, ctx = make_pair(ref, tb, scheme, n, bits)
+    ev = tb.EvaluatorCuda(ctx)
+    ckks = scheme == ref.CKKS
+    sc = 2.0 ** 30 if ckks else 1.0
+    mods = rc.level_moduli(level)
+    w = random_ct_words(rc, level, 2, n, rng, batch)
+    cf = 1 if scheme != ref.BGV else 3  # a non-trivial BGV correction factor
+    a = tb.CiphertextCuda.from_host(ctx, w, level, ckks, sc, cf)
+    ras = [rc.ciphertext(w[i], level, ckks, sc, cf) for i in range(batch)]
+
+    def check(name):
+        for i in range(batch):
+            assert_same(a, ras[i], f"{name} [scheme {scheme}, N {n}, level {level}, batch elt {i}]", i)
+
+    if ckks:
+        pw = np.stack([rng.integers(0, m, n, dtype=np.uint64) for m in mods])
+        pt = tb.PlaintextCuda.from_host(ctx, pw, level, sc)
+        rpt = rc.plaintext(pw, level, sc)
+        ev.add_plain_inplace(a, pt)
+        [rc.eval_plain(ref.PLAIN_ADD, r, rpt) for r in ras]
+        check("add_plain")
+        ev.sub_plain_inplace(a, pt)
+        ev.sub_plain_inplace(a, pt)
+        [rc.eval_plain(ref.PLAIN_SUB, rc.eval_plain(ref.PLAIN_SUB, r, rpt), rpt) for r in ras]
+        check("sub_plain")
+        # matmul step: acc = x * w0, acc += x * w1 in one pass vs multiplyPlain + addInplace
+        pw1 = np.stack([rng.integers(0, m, n, dtype=np.uint64) for m in mods])
+        pt1, rpt1 = tb.PlaintextCuda.from_host(ctx, pw1, level, sc), rc.plaintext(pw1, level, sc)
+        x = a.clone()
+        rxs = [r.clone() for r in ras]
+        ev.multiply_plain_inplace(a, pt)
+        [rc.eval_plain(ref.PLAIN_MULTIPLY, r, rpt) for r in ras]
+        check("multiply_plain")
+        ev.multiply_plain_accumulate(x, pt1, a)
+        for r, rx in zip(ras, rxs):
+            rc.eval_plain(ref.PLAIN_MULTIPLY, rx, rpt1)
+            rc.eval(ref.OP_ADD, r, rx)
+        check("multiply_plain_accumulate")
+        # one plaintext per batch element
+        pwb = np.stack([np.stack([rng.integers(0, m, n, dtype=np.uint64) for m in mods]) for _ in range(batch)])
+        ptb = tb.PlaintextCuda.from_host(ctx, pwb, level, 1.0)
+        ev.multiply_plain_inplace(a, ptb)
+        for i in range(batch):
+            rc.eval_plain(ref.PLAIN_MULTIPLY, ras[i], rc.plaintext(pwb[i], level, 1.0))
+        check("multiply_plain (batched plaintexts)")
+        return
+    t = rc.plain_modulus
+    for count in (n, n // 2 + 2):  # full and short plaintexts (coeff_count < N)
+        pw = rng.integers(0, t, count, dtype=np.uint64)
+        pt, rpt = tb.PlaintextCuda.from_host(ctx, pw), rc.plaintext(pw)
+        ev.add_plain_inplace(a, pt)
+        [rc.eval_plain(ref.PLAIN_ADD, r, rpt) for r in ras]
+        check(f"add_plain ({count} coefficients)")
+        ev.multiply_plain_inplace(a, pt)
+        [rc.eval_plain(ref.PLAIN_MULTIPLY, r, rpt) for r in ras]
+        check(f"multiply_plain ({count} coefficients)")
+        pw2 = rng.integers(0, t, count, dtype=np.uint64)
+        pt2, rpt2 = tb.PlaintextCuda.from_host(ctx, pw2), rc.plaintext(pw2)
+        ev.sub_plain_inplace(a, pt2)
+        [rc.eval_plain(ref.PLAIN_SUB, r, rpt2) for r in ras]
+        check(f"sub_plain ({count} coefficients)")
+    # NTT-form route: transformToNttInplace on both operands, multiplyPlainNtt, back
+    pw = rng.integers(0, t, n, dtype=np.uint64)
+    pt, rpt = tb.PlaintextCuda.from_host(ctx, pw), rc.plaintext(pw)
+    ev.transform_plain_to_ntt_inplace(pt, level)
+    rpt.to_ntt(level)
+    assert np.array_equal(pt.to_host()[0], rpt.words()), "plaintext transform_to_ntt"
+    ev.transform_to_ntt_inplace(a)
+    ev.multiply_plain_inplace(a, pt)
+    ev.transform_from_ntt_inplace(a)
+    for r in ras:
+        rc.eval(ref.OP_TO_NTT, r)
+        rc.eval_plain(ref.PLAIN_MULTIPLY, r, rpt)
+        rc.eval(ref.OP_FROM_NTT, r)
+    check("multiply_plain (NTT form)")

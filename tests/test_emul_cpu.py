@@ -4,7 +4,7 @@ it is a debugging aid, not the product path (the GPU parity tests in test_parity
 import numpy as np
 import pytest
 
-from common import run_evaluator_flow
+from common import run_evaluator_flow, run_plain_flow
 
 
 @pytest.mark.parametrize("scheme", [1, 2, 3])
@@ -27,3 +27,10 @@ def test_many_digits_emulated(ref, emul_lib):
     """More than 8 digits: the key inner product runs over digit groups that are added up in the product buffer."""
     run_evaluator_flow(ref, emul_lib, ref.CKKS, 1024, [40] * 10 + [50], np.random.default_rng(11), batch=2)
     run_evaluator_flow(ref, emul_lib, ref.BFV, 512, [36] * 9 + [40], np.random.default_rng(12))
+
+
+@pytest.mark.parametrize("scheme,n,bits", [(2, 64, [40, 30, 30, 40]), (1, 128, [40, 30, 30, 40]), (3, 4096, [60, 40, 40, 60]),
+                                           (2, 16384, [60, 40, 60]), (1, 4096, [60, 40, 40, 60])])
+def test_plain_ops_emulated(ref, emul_lib, scheme, n, bits):
+    """multiplyPlain / addPlain / subPlain and the fused multiply-accumulate."""
+    run_plain_flow(ref, emul_lib, scheme, n, bits, np.random.default_rng(300 + scheme + n))

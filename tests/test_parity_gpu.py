@@ -3,7 +3,7 @@ metadata are compared with the reference troy:: CPU library (oracle/_ref) on ide
 import numpy as np
 import pytest
 
-from common import run_evaluator_flow
+from common import run_evaluator_flow, run_plain_flow
 
 pytestmark = pytest.mark.gpu
 
@@ -37,6 +37,14 @@ def test_many_digits(ref, cuda_lib):
     run_evaluator_flow(ref, cuda_lib, ref.CKKS, 1024, [40] * 10 + [50], np.random.default_rng(11), batch=2)
     run_evaluator_flow(ref, cuda_lib, ref.BFV, 512, [36] * 9 + [40], np.random.default_rng(12))
     run_evaluator_flow(ref, cuda_lib, ref.CKKS, 8192, [40] * 17 + [50], np.random.default_rng(13))
+
+
+@pytest.mark.parametrize("scheme,n,bits", FLOWS)
+def test_plain_ops(ref, cuda_lib, scheme, n, bits):
+    """multiplyPlain / addPlain / subPlain and the fused multiply-accumulate."""
+    run_plain_flow(ref, cuda_lib, scheme, n, bits, np.random.default_rng(3000 + n + scheme))
+    if len(bits) > 3:
+        run_plain_flow(ref, cuda_lib, scheme, n, bits, np.random.default_rng(4000 + n + scheme), batch=1, level=1)
 
 
 # ---- committed golden fixtures (generated from the reference by tests/golden/make_golden.py) ----------------------

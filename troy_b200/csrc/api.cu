@@ -718,6 +718,124 @@ int troyb_multiply(troyb_context *ctx, int level, const uint64_t *d_a, size_t a_
     API_END
 }
 
+// ---- ciphertext (x) plaintext -------------------------------------------------------------------------------------------
+namespace {
+void mul_plain(Context *c, u32 L, const u64 *ct, size_t ct_size, u64 ct_stride, const u64 *plain, u64 plain_stride, u64 *out,
+               u64 out_stride, size_t batch, int accumulate, cudaStream_t s) {
+    EltMulPlain k{};
+    k.logN = c->logN;
+    k.mods = c->d_mods;
+    k.map = c->map_prefix(L);
+    k.n_limbs = L;
+    k.per_ct = (u64)ct_size * L * c->N;
+    k.total = (u64)batch * k.per_ct / 2;
+    k.ct = ct; k.plain = plain; k.out = out;
+    k.ct_stride = ct_stride; k.plain_stride = plain_stride; k.out_stride = out_stride;
+    k.accumulate = accumulate;
+    ck(launch_cta(k, grid_for(k.total, EltMulPlain::kThreads), 0, s));
+}
+
+void plain_lift(Context *c, int level, u32 L, const u64 *plain, size_t coeff_count, u64 plain_stride, u64 *out, size_t batch,
+                bool to_ntt, cudaStream_t s) {
+    const LevelData &lv = c->levels[level];
+    if (!lv.has_plain) throw std::invalid_argument("unsupported scheme");
+    if (coeff_count > c->N) throw std::invalid_argument("plain is not valid for encryption parameters");
+    EltPlainLift k{};
+    k.logN = c->logN;
+    k.mods = c->d_mods;
+    k.map = c->map_prefix(L);
+    k.n_limbs = L;
+    k.coeff_count = coeff_count;
+    k.total = (u64)batch * L * c->N;
+    k.plain = plain; k.out = out;
+    k.plain_stride = plain_stride;
+    k.pc = lv.plain;
+    ck(launch_cta(k, grid_for(k.total, EltPlainLift::kThreads), 0, s));
+    if (to_ntt) ntt_plain(c, false, k.map, L, out, (u64)L * c->N, out, (u64)L * c->N, L, (u32)batch, true, s);
+}
+} // namespace
+
+int troyb_multiply_plain_ntt(troyb_context *ctx, int level, const uint64_t *d_ct, size_t ct_size, size_t ct_stride,
+                             const uint64_t *d_plain, size_t plain_stride, uint64_t *d_out, size_t out_stride, size_t batch,
+                             int accumulate, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const u32 L = (u32)level_limbs(c, level);
+    if (ct_size < 1) throw std::invalid_argument("invalid ciphertext size");
+    check_batch_stride(ct_stride, ct_size * L * c->N, "ct");
+    check_batch_stride(out_stride, ct_size * L * c->N, "out");
+    if (plain_stride != 0) check_batch_stride(plain_stride, (size_t)L * c->N, "plain");
+    check_aligned(d_ct, "ct");
+    check_aligned(d_plain, "plain");
+    check_aligned(d_out, "out");
+    mul_plain(c, L, d_ct, ct_size, ct_stride, d_plain, plain_stride, d_out, out_stride, batch, accumulate, S(stream));
+    API_END
+}
+
+int troyb_plain_lift(troyb_context *ctx, int level, const uint64_t *d_plain, size_t plain_coeff_count, size_t plain_stride,
+                     uint64_t *d_out, size_t batch, int to_ntt, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const u32 L = (u32)level_limbs(c, level);
+    if (level < 0) throw std::invalid_argument("level is not valid for encryption parameters");
+    check_aligned(d_out, "out");
+    plain_lift(c, level, L, d_plain, plain_coeff_count, plain_stride, d_out, batch, to_ntt != 0, S(stream));
+    API_END
+}
+
+int troyb_multiply_plain_normal(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_size, size_t ct_stride,
+                                const uint64_t *d_plain, size_t plain_coeff_count, size_t batch, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const u32 L = (u32)level_limbs(c, level);
+    if (level < 0) throw std::invalid_argument("level is not valid for encryption parameters");
+    if (ct_size < 1) throw std::invalid_argument("invalid ciphertext size");
+    check_batch_stride(ct_stride, ct_size * L * c->N, "ct");
+    check_aligned(d_ct, "ct");
+    cudaStream_t s = S(stream);
+    // lift + NTT of the plaintext once, then NTT -> dyadic product -> INTT over all polys of the batch (3 launches)
+    Scratch temp((size_t)L * c->N, s);
+    plain_lift(c, level, L, d_plain, plain_coeff_count, 0, temp.p, 1, true, s);
+    const LimbMap map = c->map_prefix(L);
+    ntt_plain(c, false, map, L, d_ct, ct_stride, d_ct, ct_stride, (u32)ct_size * L, (u32)batch, true, s);
+    mul_plain(c, L, d_ct, ct_size, ct_stride, temp.p, 0, d_ct, ct_stride, batch, 0, s);
+    ntt_plain(c, true, map, L, d_ct, ct_stride, d_ct, ct_stride, (u32)ct_size * L, (u32)batch, true, s);
+    API_END
+}
+
+int troyb_add_plain(troyb_context *ctx, int level, uint64_t *d_c0, size_t ct_stride, const uint64_t *d_plain,
+                    size_t plain_coeff_count, size_t plain_stride, uint64_t correction_factor, int subtract, size_t batch,
+                    void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const u32 L = (u32)level_limbs(c, level);
+    if (level < 0) throw std::invalid_argument("level is not valid for encryption parameters");
+    const LevelData &lv = c->levels[level];
+    if (!lv.has_plain) throw std::invalid_argument("unsupported scheme");
+    if (plain_coeff_count > c->N) throw std::invalid_argument("plain is not valid for encryption parameters");
+    check_batch_stride(ct_stride, (size_t)L * c->N, "ct");
+    if (plain_coeff_count == 0 || batch == 0) return 0;
+    EltAddPlain k{};
+    k.logN = c->logN;
+    k.mods = c->d_mods;
+    k.map = c->map_prefix(L);
+    k.n_limbs = L;
+    k.coeff_count = plain_coeff_count;
+    k.total = (u64)batch * plain_coeff_count;
+    k.plain = d_plain; k.c0 = d_c0;
+    k.plain_stride = plain_stride; k.ct_stride = ct_stride;
+    k.scaled = c->scheme == SCHEME_BFV ? 1 : 0;
+    k.subtract = subtract;
+    k.factor = correction_factor;
+    k.pc = lv.plain;
+    ck(launch_cta(k, grid_for(k.total, EltAddPlain::kThreads), 0, S(stream)));
+    API_END
+}
+
 int troyb_switch_key(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_stride, const uint64_t *d_target,
                      size_t target_stride, const uint64_t *d_key, size_t batch, void *stream) {
     API_BEGIN

@@ -56,6 +56,41 @@ void barrett_ratio(u64 q, u64 &r0, u64 &r1) {
     (void)ratio_hi;
 }
 
+// Plaintext-space constants of one level (src/context.cpp:296-352): floor(Q / t) and Q mod t need the full product
+// Q = q_0 ... q_{L-1}, formed here as a little-endian multi-word integer.
+void build_plain(const Context &ctx, LevelData &lv) {
+    const u64 t = ctx.plain;
+    std::vector<u64> Q{1};
+    for (int i = 0; i < lv.L; i++) {
+        u64 carry = 0;
+        for (size_t k = 0; k < Q.size(); k++) {
+            u128 v = (u128)Q[k] * ctx.pool[i] + carry;
+            Q[k] = (u64)v;
+            carry = (u64)(v >> 64);
+        }
+        if (carry) Q.push_back(carry);
+    }
+    std::vector<u64> quo(Q.size());
+    u64 rem = 0;
+    for (size_t k = Q.size(); k-- > 0;) {
+        u128 v = ((u128)rem << 64) | Q[k];
+        quo[k] = (u64)(v / t);
+        rem = (u64)(v % t);
+    }
+    PlainConsts &pc = lv.plain;
+    pc.t = t;
+    pc.threshold = (t + 1) >> 1;
+    pc.q_mod_t = rem;
+    for (int i = 0; i < lv.L; i++) {
+        const u64 qi = ctx.pool[i];
+        u64 d = 0;
+        for (size_t k = quo.size(); k-- > 0;) d = (u64)((((u128)d << 64) | quo[k]) % qi);
+        pc.delta[i] = d;
+        pc.inc[i] = (qi - t % qi) % qi;
+    }
+    lv.has_plain = true;
+}
+
 void build_drop(Context &ctx, const std::vector<u64> &base, std::vector<void *> &owned, DropDev &out, DropLimb *&d_limbs,
                 int last_pool) {
     int m = (int)base.size() - 1;
@@ -348,6 +383,7 @@ Context *context_create(int device, int scheme, u64 N, const u64 *moduli, int n_
             lv.last_prime_as_double = (double)base.back();
         }
         if (scheme == SCHEME_BFV) build_behz(*ctx, lv);
+        if (scheme != SCHEME_CKKS && plain_modulus > 1) build_plain(*ctx, lv);
     }
     if (ctx->has_special) {
         std::vector<u64> base(ctx->pool.begin(), ctx->pool.begin() + ctx->Ltop);

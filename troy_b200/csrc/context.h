@@ -83,6 +83,14 @@ struct BehzDev {
     const u64 *t_mod;              // [L+nBsk][2] Shoup pair of plain modulus t in each of q ∪ Bsk
 };
 
+// Per-level constants of the plaintext space of BFV / BGV (src/context.cpp:296-352), passed by value with a launch.
+struct PlainConsts {
+    u64 t, threshold;        // plain modulus, plain_upper_half_threshold = (t + 1) / 2
+    u64 q_mod_t;             // coeff_modulus_mod_plain_modulus
+    u64 inc[kMaxLimbs];      // plain_upper_half_increment: (Q - t) mod q_i
+    u64 delta[kMaxLimbs];    // coeff_div_plain_modulus: floor(Q / t) mod q_i
+};
+
 struct LimbMap {
     uint8_t idx[kMaxLimbs]; // pool index of launch limb l
 };
@@ -95,6 +103,8 @@ struct LevelData {
     BehzDev behz{};
     std::vector<void *> owned;       // device allocations
     double last_prime_as_double = 0; // for scale bookkeeping
+    bool has_plain = false;          // BFV / BGV
+    PlainConsts plain{};
 };
 
 struct Context {

@@ -401,6 +401,134 @@ template <int ND> struct KsInnerProductStaged {
     }
 };
 
+// ---- ciphertext x plaintext, ciphertext +- plaintext -----------------------------------------------
+// multiplyPlainNtt: kDyadicProductCoeffmod on every poly   src/evaluator_cuda.cu:1818-1862, src/kernelutils.cu:151-186
+// (CPU src/evaluator.cpp:1937-1985). One launch for a whole batch; `accumulate` adds the product to what `out` holds,
+// which turns the multiplyPlain + addInplace pairs of MatmulHelper::matmul (app/LinearHelperCKKS.cuh:225-249) into one
+// pass over the output.
+struct EltMulPlain {
+    static constexpr int kThreads = kEltThreads;
+    const char *name() const { return "ct_times_plain"; }
+    int logN;
+    const ModDev *mods;
+    LimbMap map;
+    u32 n_limbs;      // limbs per poly
+    u64 per_ct;       // ct_size * n_limbs * N
+    u64 total;        // batch * per_ct / 2 threads (two adjacent coefficients per thread, 128-bit accesses)
+    const u64 *ct, *plain;
+    u64 *out;
+    u64 ct_stride, plain_stride, out_stride; // words between batch elements (plain_stride 0: one plaintext for all)
+    int accumulate;
+    TB_D void operator()(u32 bid, u64 *) const {
+        TB_PHASE(kThreads, t, {
+            const u64 idx = (u64)bid * kThreads + t;
+            if (idx < total) {
+                const u64 half = per_ct >> 1;
+                const u64 b = idx / half, rem = (idx % half) * 2;
+                const u64 per_poly = (u64)n_limbs << logN;
+                const u64 in_poly = rem % per_poly;
+                const ModDev &m = mods[map.idx[(u32)(in_poly >> logN)]];
+                const u64 p = m.p, mu = m.bar_mu;
+                const u32 sh = m.bar_shift;
+                const ulonglong2 x = EltTensor::ld2(ct + b * ct_stride + rem);
+                const ulonglong2 w = EltTensor::ld2(plain + b * plain_stride + in_poly);
+                u64 r0 = reduce_sum(x.x * w.x, mulhi64(x.x, w.x), p, mu, sh);
+                u64 r1 = reduce_sum(x.y * w.y, mulhi64(x.y, w.y), p, mu, sh);
+                u64 *po = out + b * out_stride + rem;
+                if (accumulate) {
+                    const ulonglong2 o = EltTensor::ld2(po);
+                    r0 = addmod(r0, o.x, p);
+                    r1 = addmod(r1, o.y, p);
+                }
+                EltTensor::st2(po, r0, r1);
+            }
+        })
+    }
+};
+
+// Plaintext lift: coefficient x of a plaintext modulo t becomes its centred representative modulo every q_i
+// (x >= threshold: x + (Q - t)); coefficients past coeff_count are zero. gMultiplyPlainNormalUtilA/B + decomposeArray
+// src/evaluator_cuda.cu:1724-1755,1783-1797; gTransformToNttInplace :1865-1935; CPU src/evaluator.cpp:1866-1895. In RNS
+// both branches of the reference (using_fast_plain_lift or not) are the same function: (x mod q_i + inc_i) mod q_i.
+struct EltPlainLift {
+    static constexpr int kThreads = kEltThreads;
+    const char *name() const { return "plain_lift"; }
+    int logN;
+    const ModDev *mods;
+    LimbMap map;
+    u32 n_limbs;
+    u64 coeff_count;
+    u64 total; // batch * n_limbs * N
+    const u64 *plain;
+    u64 *out;
+    u64 plain_stride; // words between the plaintexts of a batch; out is [batch][n_limbs][N]
+    PlainConsts pc;
+    TB_D void operator()(u32 bid, u64 *) const {
+        TB_PHASE(kThreads, t, {
+            const u64 idx = (u64)bid * kThreads + t;
+            if (idx < total) {
+                const u64 c = idx & ((u64(1) << logN) - 1);
+                const u32 limb = (u32)((idx >> logN) % n_limbs);
+                const u64 b = (idx >> logN) / n_limbs;
+                u64 r = 0;
+                if (c < coeff_count) {
+                    const ModDev &m = mods[map.idx[limb]];
+                    const u64 x = plain[b * plain_stride + c];
+                    r = barrett64(x, m.p, m.ratio1);
+                    if (x >= pc.threshold) r = addmod(r, pc.inc[limb], m.p);
+                }
+                out[idx] = r;
+            }
+        })
+    }
+};
+
+// addPlain / subPlain on the first poly of a coefficient-form ciphertext, one thread per coefficient, all limbs:
+//   BFV (scaled = 1): multiplyAdd/SubPlainWithScalingVariant  src/utils/scalingvariant_cuda.cu:82-175
+//        c0[j][i] +-= (x * floor(Q/t) + floor((x * (Q mod t) + threshold) / t)) mod q_j
+//   BGV (scaled = 0): x * correction_factor mod t, then add/subPlainWithoutScalingVariant
+//        src/evaluator_cuda.cu:1617-1622,1690-1694, src/utils/scalingvariant_cuda.cu:21-80
+struct EltAddPlain {
+    static constexpr int kThreads = kEltThreads;
+    const char *name() const { return "ct_plus_plain"; }
+    int logN;
+    const ModDev *mods;
+    LimbMap map;
+    u32 n_limbs;
+    u64 coeff_count;
+    u64 total; // batch * coeff_count
+    const u64 *plain;
+    u64 *c0;
+    u64 plain_stride, ct_stride;
+    int scaled, subtract;
+    u64 factor; // BGV: the ciphertext's correction factor
+    PlainConsts pc;
+    TB_D void operator()(u32 bid, u64 *) const {
+        TB_PHASE(kThreads, t, {
+            const u64 idx = (u64)bid * kThreads + t;
+            if (idx < total) {
+                const u64 b = idx / coeff_count, c = idx % coeff_count;
+                u64 x = plain[b * plain_stride + c];
+                u64 fix = 0;
+                if (scaled) {
+                    const unsigned __int128 num = (unsigned __int128)x * pc.q_mod_t + pc.threshold;
+                    fix = (u64)(num / pc.t);
+                } else {
+                    x = (u64)(((unsigned __int128)x * factor) % pc.t);
+                }
+                u64 *dst = c0 + b * ct_stride + c;
+                for (u32 j = 0; j < n_limbs; j++) {
+                    const ModDev &m = mods[map.idx[j]];
+                    u64 v = barrett64(x, m.p, m.ratio1);
+                    if (scaled) v = addmod(mulmod_barrett(v, pc.delta[j], m.p, m.ratio0, m.ratio1), barrett64(fix, m.p, m.ratio1), m.p);
+                    u64 *w = dst + ((u64)j << logN);
+                    *w = subtract ? submod(*w, v, m.p) : addmod(*w, v, m.p);
+                }
+            }
+        })
+    }
+};
+
 // ---- Galois automorphisms ---------------------------------------------------------------------------------
 // gApplyGalois (coefficient form, scatter)  src/utils/galois_cuda.cu:139-164 ; CPU src/utils/galois.cpp:141-175
 // gApplyGaloisNtt (NTT form, gather)        src/utils/galois_cuda.cu:181-196 ; table rule src/utils/galois_cuda.cu:26-42

@@ -293,6 +293,52 @@ class CiphertextCuda:
         self.size = size
 
 
+class PlaintextCuda:
+    """src/plaintext_cuda.cuh: device plaintext. Coefficient form (``parms_id is None``, the reference's parmsIDZero):
+    ``coeff_count`` words modulo t. NTT form: ``[L][N]`` words over the limbs of level ``parms_id`` (CKKS encodings, or a
+    BFV / BGV plaintext after ``EvaluatorCuda.transform_plain_to_ntt_inplace``). ``batch`` > 1 holds that many plaintexts
+    back to back (one per ciphertext of a batched call); batch = 1 is shared by every ciphertext of a batch."""
+
+    def __init__(self, context, coeff_count, parms_id=None, scale=1.0, batch=1, data=None):
+        self.context, self.coeff_count, self.parms_id, self.scale, self.batch = context, int(coeff_count), parms_id, scale, batch
+        self.data = data if data is not None else DeviceArray(batch * self.coeff_count)
+
+    @property
+    def is_ntt_form(self):
+        return self.parms_id is not None
+
+    @property
+    def stride(self):
+        """words between the plaintexts of a batch as the C ABI wants it (0: one plaintext for all)"""
+        return self.coeff_count if self.batch > 1 else 0
+
+    @classmethod
+    def from_host(cls, context, words, parms_id=None, scale=1.0):
+        """words: [coeff_count] / [batch][coeff_count] (coefficient form) or [L][N] / [batch][L][N] (NTT form)."""
+        w = np.ascontiguousarray(words, dtype=np.uint64)
+        unit_dims = 1 if parms_id is None else 2
+        batch = w.shape[0] if w.ndim == unit_dims + 1 else 1
+        count = w.size // batch
+        if parms_id is not None and count != context.level_limbs(parms_id) * context.n:
+            raise TroyInvalidArgument("plain is not valid for encryption parameters")
+        if parms_id is None and count > context.n:
+            raise TroyInvalidArgument("plain is not valid for encryption parameters")
+        if count & 1 and batch > 1:
+            raise TroyInvalidArgument("batched plaintexts need an even coefficient count")
+        pt = cls(context, count, parms_id, scale, batch)
+        pt.data.upload(w.reshape(-1))
+        return pt
+
+    @classmethod
+    def from_device(cls, context, ptr, coeff_count, parms_id=None, scale=1.0, batch=1):
+        return cls(context, coeff_count, parms_id, scale, batch, data=ExternalArray(ptr, batch * coeff_count))
+
+    def to_host(self):
+        return self.data.download(self.batch * self.coeff_count).reshape(self.batch, -1)
+
+    isNttForm = is_ntt_form
+
+
 class KSwitchKeysCuda:
     """src/kswitchkeys_cuda.cuh:31-366: ``keys[index]`` = one key-switching key, device words
     ``[digit][2][key_limbs][N]`` in NTT form at the key level."""
@@ -630,6 +676,97 @@ class EvaluatorCuda:
     def mod_switch_to_next_inplace(self, ct):
         self._assign(ct, self.mod_switch_to_next(ct))
 
+    # -- ciphertext (x) plaintext (src/evaluator_cuda.cu:1555-1935)
+    def _check_plain_batch(self, ct, plain):
+        if plain.batch not in (1, ct.batch):
+            raise TroyInvalidArgument("plain batch does not match the ciphertext batch")
+
+    def _addsub_plain(self, ct, plain, subtract):
+        scheme = self.context.scheme
+        if scheme == BFV and ct.is_ntt_form:
+            raise TroyInvalidArgument("BFV encrypted cannot be in NTT form")
+        if scheme == CKKS and not ct.is_ntt_form:
+            raise TroyInvalidArgument("CKKS encrypted must be in NTT form")
+        if scheme == BGV and ct.is_ntt_form:
+            raise TroyInvalidArgument("BGV encrypted cannot be in NTT form")
+        if plain.is_ntt_form != ct.is_ntt_form:
+            raise TroyInvalidArgument("NTT form mismatch")
+        if ct.is_ntt_form and ct.parms_id != plain.parms_id:
+            raise TroyInvalidArgument("encrypted and plain parameter mismatch")
+        if scheme == CKKS and not math.isclose(ct.scale, plain.scale, rel_tol=1e-15):
+            raise TroyInvalidArgument("scale mismatch")
+        self._check_plain_batch(ct, plain)
+        if scheme == CKKS:
+            # kAddPolyCoeffmod / kSubPolyCoeffmod on poly 0 (src/evaluator_cuda.cu:1607-1612)
+            name = "troyb_sub" if subtract else "troyb_add"
+            for b in range(ct.batch):
+                pp = plain.data.at((b if plain.batch > 1 else 0) * plain.coeff_count)
+                _L().call(name, self._h(), ct.parms_id, _vp(ct.ptr(0, b)), _vp(pp), _vp(ct.ptr(0, b)), 1, self._s())
+        else:
+            _L().call("troyb_add_plain", self._h(), ct.parms_id, _vp(ct.ptr()), ct.stride, _vp(plain.data.ptr),
+                      plain.coeff_count, plain.stride, C.c_uint64(ct.correction_factor), int(subtract), ct.batch, self._s())
+
+    def add_plain_inplace(self, ct, plain):
+        self._addsub_plain(ct, plain, False)
+
+    def sub_plain_inplace(self, ct, plain):
+        self._addsub_plain(ct, plain, True)
+
+    def multiply_plain_inplace(self, ct, plain):
+        """multiplyPlainInplace → multiplyPlainNtt / multiplyPlainNormal (src/evaluator_cuda.cu:1704-1862)."""
+        if ct.is_ntt_form != plain.is_ntt_form:
+            raise TroyInvalidArgument("NTT form mismatch")
+        self._check_plain_batch(ct, plain)
+        new_scale = ct.scale * plain.scale
+        if ct.is_ntt_form:
+            if ct.parms_id != plain.parms_id:
+                raise TroyInvalidArgument("encrypted_ntt and plain_ntt parameter mismatch")
+            _L().call("troyb_multiply_plain_ntt", self._h(), ct.parms_id, _vp(ct.ptr()), ct.size, ct.stride,
+                      _vp(plain.data.ptr), plain.stride, _vp(ct.ptr()), ct.stride, ct.batch, 0, self._s())
+            ct.scale = new_scale
+            if not self._check_scale(ct.scale, ct.parms_id):
+                raise TroyInvalidArgument("scale out of bounds")
+        else:
+            if plain.batch != 1:
+                raise TroyInvalidArgument("multiply_plain in coefficient form takes one plaintext per call")
+            _L().call("troyb_multiply_plain_normal", self._h(), ct.parms_id, _vp(ct.ptr()), ct.size, ct.stride,
+                      _vp(plain.data.ptr), plain.coeff_count, ct.batch, self._s())
+            if self.context.scheme == CKKS:
+                ct.scale = new_scale
+                if not self._check_scale(ct.scale, ct.parms_id):
+                    raise TroyInvalidArgument("scale out of bounds")
+
+    def multiply_plain(self, ct, plain):
+        d = ct.clone()
+        self.multiply_plain_inplace(d, plain)
+        return d
+
+    def multiply_plain_accumulate(self, ct, plain, destination):
+        """destination += ct * plain (NTT form) in one pass: the multiplyPlain + addInplace pair of
+        MatmulHelper::matmul (app/LinearHelperCKKS.cuh:225-249). The scales must agree like in addInplace."""
+        if not (ct.is_ntt_form and plain.is_ntt_form and destination.is_ntt_form):
+            raise TroyInvalidArgument("NTT form mismatch")
+        if ct.parms_id != plain.parms_id or ct.parms_id != destination.parms_id or ct.size != destination.size \
+                or ct.batch != destination.batch:
+            raise TroyInvalidArgument("encrypted_ntt and plain_ntt parameter mismatch")
+        self._check_plain_batch(ct, plain)
+        if self.context.scheme == CKKS and not math.isclose(ct.scale * plain.scale, destination.scale, rel_tol=1e-15):
+            raise TroyInvalidArgument("scale mismatch")
+        _L().call("troyb_multiply_plain_ntt", self._h(), ct.parms_id, _vp(ct.ptr()), ct.size, ct.stride, _vp(plain.data.ptr),
+                  plain.stride, _vp(destination.ptr()), destination.stride, ct.batch, 1, self._s())
+
+    def transform_plain_to_ntt_inplace(self, plain, parms_id):
+        """transformToNttInplace(PlaintextCuda&, ParmsID) (src/evaluator_cuda.cu:1865-1935): lift + forward NTT."""
+        if plain.is_ntt_form:
+            raise TroyInvalidArgument("plain is already in NTT form")
+        if not (0 <= parms_id < self.context.num_levels):
+            raise TroyInvalidArgument("parms_id is not valid for the current context")
+        words = self.context.level_limbs(parms_id) * self.context.n
+        out = DeviceArray(plain.batch * words)
+        _L().call("troyb_plain_lift", self._h(), parms_id, _vp(plain.data.ptr), plain.coeff_count, plain.coeff_count,
+                  _vp(out.ptr), plain.batch, 1, self._s())
+        plain.data, plain.coeff_count, plain.parms_id = out, words, parms_id
+
     # -- NTT transforms (src/evaluator_cuda.cu:1950-2022)
     def transform_to_ntt_inplace(self, ct):
         if ct.is_ntt_form:
@@ -656,3 +793,5 @@ class EvaluatorCuda:
     rescaleToNext, rescaleToNextInplace = rescale_to_next, rescale_to_next_inplace
     modSwitchToNext, modSwitchToNextInplace = mod_switch_to_next, mod_switch_to_next_inplace
     transformToNttInplace, transformFromNttInplace = transform_to_ntt_inplace, transform_from_ntt_inplace
+    addPlainInplace, subPlainInplace, multiplyPlainInplace = add_plain_inplace, sub_plain_inplace, multiply_plain_inplace
+    multiplyPlain = multiply_plain
