@@ -317,6 +317,28 @@ def run_ours(args):
     t_ni = timed(ntt_i, extra_steps)
     limbs = ntt_polys * L
 
+    # ---- the HE matmul of BASELINE config 5 (MatmulHelper::matmul, app/LinearHelperCKKS.cuh:225-249) at this config's
+    # shape: y[b][j] = sum_i x[b][i] * W[i][j], 16 x 8 ciphertexts times 8 x 8 plaintexts, as ONE launch, and the same
+    # product as the reference issues it (one multiplyPlain per term + one addInplace per term, fused here into one
+    # multiply-accumulate launch per (i, j) over the batch).
+    MB_, MI_, MJ_ = 16, 8, 8
+    mm_x_buf = uniform((MB_ * MI_, 2), q[:L])
+    mm_x = tb.Cipher2d(MB_, MI_, tb.CiphertextCuda.from_device(ctx, mm_x_buf.data_ptr(), MB_ * MI_, 2, 0, True, 2.0 ** 20))
+    mm_w_buf = uniform((MI_ * MJ_,), q[:L])
+    mm_w = tb.Plain2d(MI_, MJ_, tb.PlaintextCuda.from_device(ctx, mm_w_buf.data_ptr(), L * N, 0, 2.0 ** 20, batch=MI_ * MJ_))
+    mm = tb.MatmulHelper(MB_, 1, 1, N // 2)
+    mm.grid = (MI_, MJ_)
+    mm_keep = []
+
+    def matmul_fused():
+        mm_keep[:] = [mm.matmul(ev, mm_x, mm_w)]
+
+    for _ in range(3):
+        matmul_fused()
+    t_mm = timed(matmul_fused, extra_steps)
+    mm_terms = MB_ * MI_ * MJ_
+    mm_bytes = (MB_ * MI_ * 2 + MI_ * MJ_ + MB_ * MJ_ * 2) * L * N * 8  # every operand word once
+
     # ---- per-kernel device time of one step (CUDA events around every launch) for the roofline of the dominant kernel
     lib.call("troyb_profile_enable", 1)
     step()
@@ -331,7 +353,10 @@ def run_ours(args):
     # algorithmic bytes of one launch of the dominant kernel: every NTT-family CTA (unit) reads and writes one limb
     if dom["kernel"].startswith("ntt_"):
         tiles_per_limb = max(1, N // 8192)  # a limb is a cluster of 8192-coefficient tiles, one CTA each
-        dom_bytes = dom["grid"] / tiles_per_limb / dom["launches"] * bytes_["limb_ntt"]
+        units = dom["grid"] / tiles_per_limb / dom["launches"]
+        if dom["kernel"] == "ntt_fwd_modup":
+            units *= L / (L + 1)  # CKKS: digit i under modulus i is read in place by the inner product, its CTA exits at once
+        dom_bytes = units * bytes_["limb_ntt"]
     elif dom["kernel"] == "ks_inner_product":
         dom_bytes = B * (L + 1) * N * 8 * (L + 2 * L + 2) / dom["launches"]
     else:
@@ -391,6 +416,9 @@ def run_ours(args):
                 "forward_frac_of_hbm_roofline": limbs * extra_steps / t_nf * bytes_["limb_ntt"] / 1e9 / hbm_peak,
                 "inverse_frac_of_hbm_roofline": limbs * extra_steps / t_ni * bytes_["limb_ntt"] / 1e9 / hbm_peak,
                 "shape": f"{ntt_polys} polys x {L} limbs, N={N}"},
+        "matmul": {"multiply_plain_accumulate_per_s": world * mm_terms * extra_steps / t_mm, "ms": t_mm / extra_steps * 1e3,
+                   "shape": f"{MB_}x{MI_} ciphertexts times {MI_}x{MJ_} plaintexts, one launch",
+                   "gbs": mm_bytes * extra_steps / t_mm / 1e9, "frac_of_hbm_roofline": mm_bytes * extra_steps / t_mm / 1e9 / hbm_peak},
         "kernels": kernels,
     }
     print(json.dumps(line))

@@ -157,6 +157,14 @@ int troyb_multiply_plain_ntt(troyb_context *ctx, int level, const uint64_t *d_ct
                              const uint64_t *d_plain, size_t plain_stride, uint64_t *d_out, size_t out_stride, size_t batch,
                              int accumulate, void *stream);
 
+/* MatmulHelper::matmul  app/LinearHelperCKKS.cuh:225-249: out[b][j] = sum_i ct[b][i] * plain[i][j] over NTT-form operands
+ * (the reference: batch*inputs*outputs multiplyPlain + batch*(inputs-1)*outputs addInplace calls), one launch.
+ * d_ct: [batch][inputs] ciphertexts of ct_size polys, ct_stride words apart; d_plain: [inputs][outputs][L][N];
+ * d_out: [batch][outputs] ciphertexts, out_stride words apart (must not alias d_ct). */
+int troyb_matmul_plain_ntt(troyb_context *ctx, int level, const uint64_t *d_ct, size_t ct_size, size_t ct_stride,
+                           const uint64_t *d_plain, uint64_t *d_out, size_t out_stride, size_t batch, size_t inputs, size_t outputs,
+                           void *stream);
+
 /* Plaintext lift of BFV / BGV: `batch` coefficient-form plaintexts of plain_coeff_count words modulo t (plain_stride words
  * apart) become [batch][L][N] centred residues over the level's limbs; to_ntt != 0 also transforms them.
  * gMultiplyPlainNormalUtilA/B src/evaluator_cuda.cu:1724-1755; EvaluatorCuda::transformToNttInplace(PlaintextCuda&, ParmsID)

@@ -510,6 +510,52 @@ public:
         b200::check(troyb_ntt_inverse(h(), level(ct), ct.data(), ct.size(), nullptr));
         ct.isNttForm() = false;
     }
+    // ---- ciphertext (x) plaintext (src/evaluator_cuda.cu:1555-1935). Plaintexts keep their host representation in this
+    // layer (see PlaintextCuda above); each call uploads the plaintext words it needs.
+    void addPlainInplace(CiphertextCuda &ct, const PlaintextCuda &plain) const { addSubPlain(ct, plain, false); }
+    void subPlainInplace(CiphertextCuda &ct, const PlaintextCuda &plain) const { addSubPlain(ct, plain, true); }
+    void addPlain(const CiphertextCuda &ct, const PlaintextCuda &plain, CiphertextCuda &dst) const { dst = ct; addPlainInplace(dst, plain); }
+    void subPlain(const CiphertextCuda &ct, const PlaintextCuda &plain, CiphertextCuda &dst) const { dst = ct; subPlainInplace(dst, plain); }
+    void multiplyPlainInplace(CiphertextCuda &ct, const PlaintextCuda &plain) const {
+        if (ct.isNttForm() != plain.isNttForm()) throw std::invalid_argument("NTT form mismatch");
+        const int lv = level(ct);
+        const std::size_t stride = ct.size() * ct.polyCoeffSize();
+        b200::DeviceWords d(plain.coeffCount());
+        d.upload(plain.data(), plain.coeffCount());
+        if (ct.isNttForm()) {
+            // multiplyPlainNtt  src/evaluator_cuda.cu:1818-1862
+            if (ct.parmsID() != plain.parmsID()) throw std::invalid_argument("encrypted_ntt and plain_ntt parameter mismatch");
+            b200::check(troyb_multiply_plain_ntt(h(), lv, ct.data(), ct.size(), stride, d.get(), 0, ct.data(), stride, 1, 0, nullptr));
+            ct.scale() *= plain.scale();
+            if (!scaleWithinBounds(ct.scale(), ct.parmsID())) throw std::invalid_argument("scale out of bounds");
+        } else {
+            // multiplyPlainNormal  src/evaluator_cuda.cu:1757-1816
+            b200::check(troyb_multiply_plain_normal(h(), lv, ct.data(), ct.size(), stride, d.get(), plain.coeffCount(), 1, nullptr));
+            if (scheme() == SchemeType::ckks) {
+                ct.scale() *= plain.scale();
+                if (!scaleWithinBounds(ct.scale(), ct.parmsID())) throw std::invalid_argument("scale out of bounds");
+            }
+        }
+    }
+    void multiplyPlain(const CiphertextCuda &ct, const PlaintextCuda &plain, CiphertextCuda &dst) const { dst = ct; multiplyPlainInplace(dst, plain); }
+    // transformToNttInplace(PlaintextCuda &, ParmsID)  src/evaluator_cuda.cu:1865-1935
+    void transformToNttInplace(PlaintextCuda &plain, const ParmsID &parms_id) const {
+        auto cd = context_.getContextData(parms_id);
+        if (!cd) throw std::invalid_argument("parms_id is not valid for the current context");
+        if (plain.isNttForm()) throw std::invalid_argument("plain is already in NTT form");
+        const std::size_t n = cd->parms().polyModulusDegree(), L = cd->parms().coeffModulus().size(), count = plain.coeffCount();
+        b200::DeviceWords in(count), out(L * n);
+        in.upload(plain.data(), count);
+        b200::check(troyb_plain_lift(h(), context_.levelOf(parms_id), in.get(), count, count, out.get(), 1, 1, nullptr));
+        plain.resize(L * n);
+        out.download(plain.data(), L * n);
+        plain.parmsID() = parms_id;
+    }
+    void transformToNtt(const PlaintextCuda &plain, const ParmsID &parms_id, PlaintextCuda &dst) const {
+        dst = plain;
+        transformToNttInplace(dst, parms_id);
+    }
+
     void transformToNtt(const CiphertextCuda &ct, CiphertextCuda &dst) const { dst = ct; transformToNttInplace(dst); }
     void transformFromNtt(const CiphertextCuda &ct, CiphertextCuda &dst) const { dst = ct; transformFromNttInplace(dst); }
 
@@ -528,6 +574,27 @@ private:
         auto cd = context_.getContextData(id);
         int bound = scheme() == SchemeType::ckks ? cd->totalCoeffModulusBitCount() : cd->parms().plainModulus().bitCount();
         return !(scale <= 0 || (int)std::log2(scale) >= bound);
+    }
+    void addSubPlain(CiphertextCuda &ct, const PlaintextCuda &plain, bool sub) const {
+        const SchemeType s = scheme();
+        if (s == SchemeType::bfv && ct.isNttForm()) throw std::invalid_argument("BFV encrypted cannot be in NTT form");
+        if (s == SchemeType::ckks && !ct.isNttForm()) throw std::invalid_argument("CKKS encrypted must be in NTT form");
+        if (s == SchemeType::bgv && ct.isNttForm()) throw std::invalid_argument("BGV encrypted cannot be in NTT form");
+        if (plain.isNttForm() != ct.isNttForm()) throw std::invalid_argument("NTT form mismatch");
+        if (ct.isNttForm() && ct.parmsID() != plain.parmsID()) throw std::invalid_argument("encrypted and plain parameter mismatch");
+        if (s == SchemeType::ckks && ct.scale() != plain.scale() && std::fabs(ct.scale() - plain.scale()) > 1e-15 * std::fabs(ct.scale()))
+            throw std::invalid_argument("scale mismatch");
+        const int lv = level(ct);
+        b200::DeviceWords d(plain.coeffCount());
+        d.upload(plain.data(), plain.coeffCount());
+        if (s == SchemeType::ckks) {
+            // kAddPolyCoeffmod / kSubPolyCoeffmod on poly 0  src/evaluator_cuda.cu:1607-1612,1680-1685
+            if (plain.coeffCount() != ct.polyCoeffSize()) throw std::invalid_argument("plain is not valid for encryption parameters");
+            b200::check((sub ? troyb_sub : troyb_add)(h(), lv, ct.data(), d.get(), ct.data(), 1, nullptr));
+        } else {
+            b200::check(troyb_add_plain(h(), lv, ct.data(), ct.size() * ct.polyCoeffSize(), d.get(), plain.coeffCount(), 0,
+                                        ct.correctionFactor(), sub ? 1 : 0, 1, nullptr));
+        }
     }
     void checkKeySwitch(const CiphertextCuda &ct, const KSwitchKeysCuda &keys) const {
         if (!context_.using_keyswitching()) throw std::logic_error("keyswitching is not supported by the context");

@@ -185,3 +185,30 @@ def run_plain_flow(ref, tb, scheme, n, bits, rng, batch=2, level=0):
         rc.eval_plain(ref.PLAIN_MULTIPLY, r, rpt)
         rc.eval(ref.OP_FROM_NTT, r)
     check("multiply_plain (NTT form)")
+
+
+def run_matmul_flow(ref, tb, n, bits, rng, B=3, I=3, J=3, level=0):
+    """MatmulHelper::matmul (app/LinearHelperCKKS.cuh:225-249) on random NTT-form operands: the one-launch product against
+    the reference's own loop of multiplyPlain + addInplace, every word."""
+    rc, ctx = make_pair(ref, tb, ref.CKKS, n, bits)
+    ev = tb.EvaluatorCuda(ctx)
+    sc = 2.0 ** 20
+    mods = rc.level_moduli(level)
+    x = random_ct_words(rc, level, 2, n, rng, B * I)
+    w = np.stack([np.stack([rng.integers(0, m, n, dtype=np.uint64) for m in mods]) for _ in range(I * J)])
+    helper = tb.MatmulHelper(B, 1, 1, n // 2)
+    helper.grid = (I, J)  # operands are synthetic: only the grid shape matters here
+    a = tb.Cipher2d(B, I, tb.CiphertextCuda.from_host(ctx, x, level, True, sc))
+    wp = tb.Plain2d(I, J, tb.PlaintextCuda.from_host(ctx, w, level, sc))
+    y = helper.matmul(ev, a, wp)
+    got = y.ct.to_host()
+    assert y.ct.scale == sc * sc and y.rows == B and y.cols == J
+    for b in range(B):
+        for j in range(J):
+            acc = None
+            for i in range(I):
+                prod = rc.ciphertext(x[b * I + i], level, True, sc)
+                rc.eval_plain(ref.PLAIN_MULTIPLY, prod, rc.plaintext(w[i * J + j], level, sc))
+                acc = prod if acc is None else rc.eval(ref.OP_ADD, acc, prod)
+            want = acc.words()
+            assert np.array_equal(got[b * J + j], want), f"matmul [{b}][{j}]: {int((got[b * J + j] != want).sum())} words differ"

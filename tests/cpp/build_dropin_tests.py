@@ -30,6 +30,10 @@ REFERENCE_TESTS = [
     "CKKSEncryptRotateDecrypt", "CKKSEncryptRescaleRotateDecrypt", "BFVEncryptSquareDecrypt", "BGVEncryptSquareDecrypt",
     "TransformEncryptedToFromNTT", "BFVEncryptApplyGaloisDecrypt", "BFVEncryptRotateMatrixDecrypt",
     "BGVEncryptApplyGaloisDecrypt", "BGVEncryptRotateMatrixDecrypt", "BFVEncryptModSwitchToNextDecrypt", "BGVEncryptModSwitchToNextDecrypt",
+    # ciphertext (x) plaintext
+    "CKKSEncryptAddPlainDecrypt", "CKKSEncryptSubPlainDecrypt", "BFVEncryptAddPlainDecrypt", "BFVEncryptSubPlainDecrypt",
+    "BFVEncryptMultiplyPlainDecrypt", "BGVEncryptAddPlainDecrypt", "BGVEncryptSubPlainDecrypt", "BGVEncryptMultiplyPlainDecrypt",
+    "CKKSEncryptMultiplyByNumberDecrypt", "TransformPlainToNTT", "BFVEncryptMultiplyPlainNTTDecrypt", "BGVEncryptMultiplyPlainNTTDecrypt",
 ]
 
 

@@ -4,7 +4,7 @@ it is a debugging aid, not the product path (the GPU parity tests in test_parity
 import numpy as np
 import pytest
 
-from common import run_evaluator_flow, run_plain_flow
+from common import run_evaluator_flow, run_matmul_flow, run_plain_flow
 
 
 @pytest.mark.parametrize("scheme", [1, 2, 3])
@@ -34,3 +34,30 @@ def test_many_digits_emulated(ref, emul_lib):
 def test_plain_ops_emulated(ref, emul_lib, scheme, n, bits):
     """multiplyPlain / addPlain / subPlain and the fused multiply-accumulate."""
     run_plain_flow(ref, emul_lib, scheme, n, bits, np.random.default_rng(300 + scheme + n))
+
+
+def test_matmul_emulated(ref, emul_lib):
+    """The one-launch HE matmul against the reference's multiplyPlain + addInplace loop; odd grids hit the edge tiles."""
+    run_matmul_flow(ref, emul_lib, 256, [40, 30, 30, 40], np.random.default_rng(41), B=3, I=3, J=3)
+    run_matmul_flow(ref, emul_lib, 4096, [60, 40, 60], np.random.default_rng(42), B=2, I=40, J=1, level=1)
+
+
+def test_matmul_block_layout():
+    """determineBlock and the slot layout of MatmulHelper (app/LinearHelperCKKS.cuh:113-167,291-311): multiplying the
+    coefficient vectors as polynomials modulo X^N + 1 and reading the outputs back gives x @ W."""
+    from troy_b200.linear import MatmulHelper
+    rng = np.random.default_rng(3)
+    for (bs, din, dout, slots) in [(2, 5, 7, 16), (3, 40, 9, 32), (1, 64, 64, 64)]:
+        h = MatmulHelper(bs, din, dout, slots)
+        n = 2 * slots
+        x = rng.integers(-5, 6, (bs, din)).astype(np.float64)
+        w = rng.integers(-5, 6, (din, dout)).astype(np.float64)
+        xv, wv = h.input_vectors(x), h.weight_vectors(w)
+        I, J = h.grid
+        out = np.zeros((bs, J, n))
+        for b in range(bs):
+            for j in range(J):
+                for i in range(I):
+                    full = np.convolve(xv[b, i], wv[i, j])
+                    out[b, j] += full[:n] - np.concatenate([full[n:], np.zeros(2 * n - len(full))])[:n]
+        assert np.array_equal(h.read_outputs(out), x @ w)

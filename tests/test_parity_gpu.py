@@ -3,7 +3,7 @@ metadata are compared with the reference troy:: CPU library (oracle/_ref) on ide
 import numpy as np
 import pytest
 
-from common import run_evaluator_flow, run_plain_flow
+from common import run_evaluator_flow, run_matmul_flow, run_plain_flow
 
 pytestmark = pytest.mark.gpu
 
@@ -45,6 +45,13 @@ def test_plain_ops(ref, cuda_lib, scheme, n, bits):
     run_plain_flow(ref, cuda_lib, scheme, n, bits, np.random.default_rng(3000 + n + scheme))
     if len(bits) > 3:
         run_plain_flow(ref, cuda_lib, scheme, n, bits, np.random.default_rng(4000 + n + scheme), batch=1, level=1)
+
+
+def test_matmul(ref, cuda_lib):
+    """The one-launch HE matmul (MatmulHelper::matmul) against the reference's multiplyPlain + addInplace loop."""
+    run_matmul_flow(ref, cuda_lib, 16384, [60, 40, 40, 40, 60], np.random.default_rng(51), B=3, I=5, J=3)
+    run_matmul_flow(ref, cuda_lib, 65536, [60, 50, 60], np.random.default_rng(52), B=2, I=2, J=4, level=1)
+    run_matmul_flow(ref, cuda_lib, 4096, [60, 40, 60], np.random.default_rng(53), B=1, I=70, J=1)
 
 
 # ---- committed golden fixtures (generated from the reference by tests/golden/make_golden.py) ----------------------

@@ -11,3 +11,4 @@ from .host import (  # noqa: F401
     PlainModulus, PlaintextCuda, RelinKeysCuda, SEALContextCuda, SchemeType,
 )
 from .lib import TroyError, library  # noqa: F401
+from .linear import Cipher2d, MatmulHelper, Plain2d  # noqa: F401

@@ -773,6 +773,35 @@ int troyb_multiply_plain_ntt(troyb_context *ctx, int level, const uint64_t *d_ct
     API_END
 }
 
+int troyb_matmul_plain_ntt(troyb_context *ctx, int level, const uint64_t *d_ct, size_t ct_size, size_t ct_stride,
+                           const uint64_t *d_plain, uint64_t *d_out, size_t out_stride, size_t batch, size_t inputs, size_t outputs,
+                           void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const u32 L = (u32)level_limbs(c, level);
+    if (ct_size < 1) throw std::invalid_argument("invalid ciphertext size");
+    if (inputs < 1) throw std::invalid_argument("inner dimension cannot be zero");
+    check_batch_stride(ct_stride, ct_size * L * c->N, "ct");
+    check_batch_stride(out_stride, ct_size * L * c->N, "out");
+    check_aligned(d_ct, "ct");
+    check_aligned(d_plain, "plain");
+    check_aligned(d_out, "out");
+    if (batch == 0 || outputs == 0) return 0;
+    EltMatmulPlain k{};
+    k.logN = c->logN;
+    k.mods = c->d_mods;
+    k.map = c->map_prefix(L);
+    k.n_limbs = L;
+    k.ct_size = (u32)ct_size;
+    k.B = (u32)batch; k.I = (u32)inputs; k.J = (u32)outputs;
+    k.total = (u64)((batch + 1) / 2) * ((outputs + 1) / 2) * ct_size * L * (c->N / 2);
+    k.a = d_ct; k.w = d_plain; k.out = d_out;
+    k.a_ct_stride = ct_stride; k.out_ct_stride = out_stride;
+    ck(launch_cta(k, grid_for(k.total, EltMatmulPlain::kThreads), 0, S(stream)));
+    API_END
+}
+
 int troyb_plain_lift(troyb_context *ctx, int level, const uint64_t *d_plain, size_t plain_coeff_count, size_t plain_stride,
                      uint64_t *d_out, size_t batch, int to_ntt, void *stream) {
     API_BEGIN

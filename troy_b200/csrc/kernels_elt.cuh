@@ -446,6 +446,75 @@ struct EltMulPlain {
     }
 };
 
+// MatmulHelper::matmul (app/LinearHelperCKKS.cuh:225-249): out[b][j] = sum_i a[b][i] * w[i][j] over a grid of NTT-form
+// ciphertexts and plaintexts, which the reference runs as B*I*J multiplyPlain calls plus B*(I-1)*J addInplace calls, each
+// a pass over global memory. Here a thread owns two adjacent coefficients of one limb of one poly for a 2 x 2 tile of
+// (b, j): it streams i once, so every a[b][i] word is read ceil(J/2) times instead of J times, every w[i][j] word
+// ceil(B/2) times instead of B, and the partial sums never leave registers (128-bit lazy sums, folded every 32 terms so
+// that any inner dimension is safe for 61-bit primes). Canonical output = what the reference's chain of canonical
+// products and modular additions yields.
+struct EltMatmulPlain {
+    static constexpr int kThreads = kEltThreads;
+    static constexpr int kMinCtas = 3;
+    const char *name() const { return "ct_matmul_plain"; }
+    int logN;
+    const ModDev *mods;
+    LimbMap map;
+    u32 n_limbs, ct_size;
+    u32 B, I, J;
+    u64 total; // ceil(B/2) * ceil(J/2) * ct_size * n_limbs * N/2 threads
+    const u64 *a;   // [B][I] ciphertexts, a_ct_stride words apart
+    const u64 *w;   // [I][J][n_limbs][N]
+    u64 *out;       // [B][J] ciphertexts, out_ct_stride words apart
+    u64 a_ct_stride, out_ct_stride;
+    TB_D void operator()(u32 bid, u64 *) const {
+        TB_PHASE(kThreads, t, {
+            const u64 idx = (u64)bid * kThreads + t;
+            if (idx < total) {
+                const u64 c = (idx & ((u64(1) << (logN - 1)) - 1)) * 2;
+                u64 r = idx >> (logN - 1);
+                const u32 limb = (u32)(r % n_limbs); r /= n_limbs;
+                const u32 k = (u32)(r % ct_size); r /= ct_size;
+                const u32 JT = (J + 1) / 2;
+                const u32 j0 = (u32)(r % JT) * 2, b0 = (u32)(r / JT) * 2;
+                const u32 j1 = j0 + 1 < J ? j0 + 1 : j0, b1 = b0 + 1 < B ? b0 + 1 : b0; // clamped: edge tiles recompute
+                const ModDev &m = mods[map.idx[limb]];
+                const u64 p = m.p, r0 = m.ratio0, r1 = m.ratio1;
+                const u64 off = (((u64)k * n_limbs + limb) << logN) + c, woff = ((u64)limb << logN) + c;
+                const u64 wplain = (u64)n_limbs << logN;
+                const u64 *pa0 = a + (u64)b0 * I * a_ct_stride + off, *pa1 = a + (u64)b1 * I * a_ct_stride + off;
+                const u64 *pw0 = w + (u64)j0 * wplain + woff, *pw1 = w + (u64)j1 * wplain + woff;
+                u64 lo[2][2][2], hi[2][2][2]; // [b][j][coefficient]
+                _Pragma("unroll") for (int q = 0; q < 8; q++) { (&lo[0][0][0])[q] = 0; (&hi[0][0][0])[q] = 0; }
+                _Pragma("unroll 2") for (u32 i = 0; i < I; i++) {
+                    const ulonglong2 x0 = EltTensor::ld2(pa0 + (u64)i * a_ct_stride), x1 = EltTensor::ld2(pa1 + (u64)i * a_ct_stride);
+                    const ulonglong2 w0 = EltTensor::ld2(pw0 + (u64)i * J * wplain), w1 = EltTensor::ld2(pw1 + (u64)i * J * wplain);
+                    mac128(lo[0][0][0], hi[0][0][0], x0.x, w0.x); mac128(lo[0][0][1], hi[0][0][1], x0.y, w0.y);
+                    mac128(lo[0][1][0], hi[0][1][0], x0.x, w1.x); mac128(lo[0][1][1], hi[0][1][1], x0.y, w1.y);
+                    mac128(lo[1][0][0], hi[1][0][0], x1.x, w0.x); mac128(lo[1][0][1], hi[1][0][1], x1.y, w0.y);
+                    mac128(lo[1][1][0], hi[1][1][0], x1.x, w1.x); mac128(lo[1][1][1], hi[1][1][1], x1.y, w1.y);
+                    if ((i & 31) == 31) {
+                        _Pragma("unroll") for (int q = 0; q < 8; q++) {
+                            (&lo[0][0][0])[q] = barrett128((&lo[0][0][0])[q], (&hi[0][0][0])[q], p, r0, r1);
+                            (&hi[0][0][0])[q] = 0;
+                        }
+                    }
+                }
+                _Pragma("unroll") for (int bb = 0; bb < 2; bb++) {
+                    _Pragma("unroll") for (int jj = 0; jj < 2; jj++) {
+                        const u32 b = bb ? b0 + 1 : b0, j = jj ? j0 + 1 : j0;
+                        if (b < B && j < J) {
+                            EltTensor::st2(out + ((u64)b * J + j) * out_ct_stride + off,
+                                           barrett128(lo[bb][jj][0], hi[bb][jj][0], p, r0, r1),
+                                           barrett128(lo[bb][jj][1], hi[bb][jj][1], p, r0, r1));
+                        }
+                    }
+                }
+            }
+        })
+    }
+};
+
 // Plaintext lift: coefficient x of a plaintext modulo t becomes its centred representative modulo every q_i
 // (x >= threshold: x + (Q - t)); coefficients past coeff_count are zero. gMultiplyPlainNormalUtilA/B + decomposeArray
 // src/evaluator_cuda.cu:1724-1755,1783-1797; gTransformToNttInplace :1865-1935; CPU src/evaluator.cpp:1866-1895. In RNS

@@ -77,6 +77,7 @@ _SIGNATURES = {
     "troyb_apply_galois": (C.c_int, [_vp, C.c_int, _vp, _sz, C.c_uint32, _vp, _sz, _vp]),
     "troyb_mod_switch_scale_to_next": (C.c_int, [_vp, C.c_int, _vp, _sz, _vp, _sz, _sz, _sz, _vp]),
     "troyb_multiply_plain_ntt": (C.c_int, [_vp, C.c_int, _vp, _sz, _sz, _vp, _sz, _vp, _sz, _sz, C.c_int, _vp]),
+    "troyb_matmul_plain_ntt": (C.c_int, [_vp, C.c_int, _vp, _sz, _sz, _vp, _vp, _sz, _sz, _sz, _sz, _vp]),
     "troyb_plain_lift": (C.c_int, [_vp, C.c_int, _vp, _sz, _sz, _vp, _sz, C.c_int, _vp]),
     "troyb_multiply_plain_normal": (C.c_int, [_vp, C.c_int, _vp, _sz, _sz, _vp, _sz, _sz, _vp]),
     "troyb_add_plain": (C.c_int, [_vp, C.c_int, _vp, _sz, _vp, _sz, _sz, C.c_uint64, C.c_int, _sz, _vp]),
