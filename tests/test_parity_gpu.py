@@ -3,7 +3,7 @@ metadata are compared with the reference troy:: CPU library (oracle/_ref) on ide
 import numpy as np
 import pytest
 
-from common import run_evaluator_flow, run_matmul_flow, run_plain_flow
+from common import assert_same, make_pair, random_ct_words, run_evaluator_flow, run_matmul_flow, run_plain_flow
 
 pytestmark = pytest.mark.gpu
 
@@ -45,6 +45,43 @@ def test_plain_ops(ref, cuda_lib, scheme, n, bits):
     run_plain_flow(ref, cuda_lib, scheme, n, bits, np.random.default_rng(3000 + n + scheme))
     if len(bits) > 3:
         run_plain_flow(ref, cuda_lib, scheme, n, bits, np.random.default_rng(4000 + n + scheme), batch=1, level=1)
+
+
+def test_config5_full_size_key_switch(ref, cuda_lib):
+    """BASELINE config 5 at its full size: CKKS N=65536, 40 data primes + special prime. One relinearisation (40 digits,
+    1640 mod-up transforms, a 1.7 GB key) word for word against the reference CPU library, on a synthetic key
+    (uniform residues: key VALUES are irrelevant to the arithmetic being compared)."""
+    tb = cuda_lib
+    n, bits = 65536, [60] + [50] * 39 + [60]
+    rng = np.random.default_rng(65536)
+    rc, ctx = make_pair(ref, tb, ref.CKKS, n, bits)
+    kq = rc.level_moduli(-1)
+    L = len(kq) - 1
+    assert L == 40 and ctx.level_limbs(0) == 40
+    key = np.empty((L, 2, L + 1, n), dtype=np.uint64)
+    for i, m in enumerate(kq):
+        key[:, :, i, :] = rng.integers(0, m, (L, 2, n), dtype=np.uint64)
+    rks = rc.synthetic_keys(False, 1)
+    rks.set_words(0, key)
+    d_rlk = tb.RelinKeysCuda.from_host(ctx, {0: key})
+    del key
+    ev = tb.EvaluatorCuda(ctx)
+    w = random_ct_words(rc, 0, 3, n, rng)
+    a = tb.CiphertextCuda.from_host(ctx, w, 0, True, 2.0 ** 50)
+    ra = rc.ciphertext(w, 0, True, 2.0 ** 50)
+    ev.relinearize_inplace(a, d_rlk)
+    rc.eval(ref.OP_RELIN, ra, keys=rks)
+    assert_same(a, ra, "config 5 relinearize (N=65536, 40 digits)")
+    # two levels down (38 limbs): only digits < 38 and key limbs {0..37, special} are touched
+    for _ in range(2):
+        ev.rescale_to_next_inplace(a)
+        rc.eval(ref.OP_RESCALE_NEXT, ra)
+    assert_same(a, ra, "config 5 rescale x2")
+    ev.multiply_inplace(a, a.clone())
+    rc.eval(ref.OP_MULTIPLY, ra, ra.clone())
+    ev.relinearize_inplace(a, d_rlk)
+    rc.eval(ref.OP_RELIN, ra, keys=rks)
+    assert_same(a, ra, "config 5 multiply + relinearize at level 2")
 
 
 def test_matmul(ref, cuda_lib):
