@@ -106,7 +106,14 @@ void set_order(const Context *ctx, NttArgs &a, u32 n_limbs_in_map) {
 }
 
 // Tiles per limb of a transform of 2^logN coefficients (see ntt.cuh TilePlan).
-u32 tiles_per_limb(int logN) { return logN <= 13 ? 1u : (1u << (logN - 13)); }
+// Tile size of a transform of 2^logN coefficients: 4096-coefficient tiles (four radix-8 rounds, six CTAs per SM) for
+// N = 4096 and, as clusters of 4 / 8 tiles, for N up to 2^TROYB_TILE12_MAXLOGN (development knob for A/B runs);
+// 8192-coefficient tiles otherwise.
+int tile_log(int logN) {
+    static const int max12 = [] { const char *e = getenv("TROYB_TILE12_MAXLOGN"); return e ? atoi(e) : 12; }();
+    return (logN == 12 || (logN > 13 && logN <= max12 && logN <= 15)) ? 12 : 13;
+}
+u32 tiles_per_limb(int logN) { const int lt = tile_log(logN); return logN <= lt ? 1u : (1u << (logN - lt)); }
 
 // L2 prefetch distance of the tile transforms: about one wave of resident CTAs (148 SMs x CTAs per SM, rounded up to
 // whole clusters). TROYB_PF_WAVES_X4 (development knob) scales it in quarter waves; 0 switches the prefetch off.
@@ -118,14 +125,15 @@ u32 prefetch_distance(int logt) {
 
 void run_fwd(const Context *ctx, NttArgs a, u32 units, cudaStream_t s) {
     a.logN = ctx->logN;
-    a.pf_ahead = prefetch_distance(ctx->logN == 12 ? 12 : 13);
+    a.pf_ahead = prefetch_distance(tile_log(ctx->logN));
     a.mods = ctx->d_mods;
     const int logN = ctx->logN;
     if (logN > 16) throw std::invalid_argument("poly_modulus_degree above 65536 is not supported");
     if (logN < 12) {
         ck(launch_cta(NttFwdSmall{a}, units, (size_t)ctx->N * sizeof(u64), s));
-    } else if (logN == 12) {
-        ck(launch_cluster(NttFwdTile<12>{a}, units, 1, tile_smem(12), s));
+    } else if (tile_log(logN) == 12) {
+        const u32 c = tiles_per_limb(logN);
+        ck(launch_cluster(NttFwdTile<12>{a}, units * c, c, tile_smem(12), s));
     } else {
         const u32 c = tiles_per_limb(logN);
         ck(launch_cluster(NttFwdTile<13>{a}, units * c, c, tile_smem(13), s));
@@ -134,14 +142,15 @@ void run_fwd(const Context *ctx, NttArgs a, u32 units, cudaStream_t s) {
 
 void run_inv(const Context *ctx, NttArgs a, u32 units, cudaStream_t s) {
     a.logN = ctx->logN;
-    a.pf_ahead = prefetch_distance(ctx->logN == 12 ? 12 : 13);
+    a.pf_ahead = prefetch_distance(tile_log(ctx->logN));
     a.mods = ctx->d_mods;
     const int logN = ctx->logN;
     if (logN > 16) throw std::invalid_argument("poly_modulus_degree above 65536 is not supported");
     if (logN < 12) {
         ck(launch_cta(NttInvSmall{a}, units, (size_t)ctx->N * sizeof(u64), s));
-    } else if (logN == 12) {
-        ck(launch_cluster(NttInvTile<12>{a}, units, 1, tile_smem(12), s));
+    } else if (tile_log(logN) == 12) {
+        const u32 c = tiles_per_limb(logN);
+        ck(launch_cluster(NttInvTile<12>{a}, units * c, c, tile_smem(12), s));
     } else {
         const u32 c = tiles_per_limb(logN);
         ck(launch_cluster(NttInvTile<13>{a}, units * c, c, tile_smem(13), s));
