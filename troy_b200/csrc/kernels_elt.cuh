@@ -337,20 +337,20 @@ template <int ND> struct KsInnerProductStaged {
             const u64 *d = D + (((u64)(bg * bc) * (L + 1) + i) * d_rows + d_row0) * N + c;
             const u64 *ps = pass + (u64)(bg * bc) * pass_stride + (u64)i * N + c;
             u64 *po = prod + ((u64)(bg * bc) * 2 * (L + 1) + i) * N + c;
-            // The rows of batch element b + 1 are requested before the products of b are formed: eight 16-byte loads per
-            // thread stay in flight for a whole iteration (the kernel is bound by HBM latency x bytes in flight otherwise).
-            ulonglong2 x[ND], xn[ND], xp, xpn;
-            auto load_rows = [&](ulonglong2 (&v)[ND], ulonglong2 &vp, const u64 *dd, const u64 *pp) {
-                _Pragma("unroll") for (u32 j = 0; j < ND; j++) {
-                    v[j].x = 0; v[j].y = 0;
-                    if (j != jpass) v[j] = *reinterpret_cast<const ulonglong2 *>(dd + (u64)j * N);
-                }
-                vp.x = 0; vp.y = 0;
-                if (jpass != 0xFFFFFFFFu) vp = *reinterpret_cast<const ulonglong2 *>(pp);
-            };
-            if (bg * bc < b_end) load_rows(x, xp, d, ps);
+            // Register-rotating pipeline over the batch elements of the CTA: row j of element b + 1 is requested as soon
+            // as row j of element b has been copied out of its registers, so ND 16-byte loads per thread stay in flight
+            // for a whole iteration (the kernel is bound by HBM latency x bytes in flight otherwise) with ONE set of row
+            // registers (a second set for the next element spilled to local memory, and the spill stores waited for the
+            // loads: profiles/r1_s6 notes).
+            ulonglong2 x[ND], xp;
+            _Pragma("unroll") for (u32 j = 0; j < ND; j++) {
+                x[j].x = 0; x[j].y = 0;
+                if (bg * bc < b_end && j != jpass) x[j] = *reinterpret_cast<const ulonglong2 *>(d + (u64)j * N);
+            }
+            xp.x = 0; xp.y = 0;
+            if (bg * bc < b_end && jpass != 0xFFFFFFFFu) xp = *reinterpret_cast<const ulonglong2 *>(ps);
             for (u32 b = bg * bc; b < b_end; b++, d += d_stride, ps += pass_stride, po += 2ull * (L + 1) * N) {
-                if (b + 1 < b_end) load_rows(xn, xpn, d + d_stride, ps + pass_stride);
+                const bool more = b + 1 < b_end;
                 ulonglong2 old0, old1;
                 if (accumulate) {
                     old0 = *reinterpret_cast<const ulonglong2 *>(po);
@@ -358,9 +358,11 @@ template <int ND> struct KsInnerProductStaged {
                 }
                 ColumnAcc a0, a1, a2, a3;
                 _Pragma("unroll") for (u32 j = 0; j < ND; j++) {
+                    const ulonglong2 cur = x[j];
+                    if (more && j != jpass) x[j] = *reinterpret_cast<const ulonglong2 *>(d + d_stride + (u64)j * N);
                     const ulonglong2 k0 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * j) * kCoeffs + 2 * t);
                     const ulonglong2 k1 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * j + 1) * kCoeffs + 2 * t);
-                    const XLimbs xa(x[j].x), xb(x[j].y);
+                    const XLimbs xa(cur.x), xb(cur.y);
                     if (j == 0) {
                         a0.mac_first(xa.xl, xa.xh, xa.x0, xa.x1, k0.x);
                         a1.mac_first(xb.xl, xb.xh, xb.x0, xb.x1, k0.y);
@@ -374,9 +376,11 @@ template <int ND> struct KsInnerProductStaged {
                     }
                 }
                 if (jpass != 0xFFFFFFFFu) { // CTA-uniform
+                    const ulonglong2 cur = xp;
+                    if (more) xp = *reinterpret_cast<const ulonglong2 *>(ps + pass_stride);
                     const ulonglong2 k0 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * jpass) * kCoeffs + 2 * t);
                     const ulonglong2 k1 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * jpass + 1) * kCoeffs + 2 * t);
-                    const XLimbs xa(xp.x), xb(xp.y);
+                    const XLimbs xa(cur.x), xb(cur.y);
                     a0.mac(xa.xl, xa.xh, xa.x0, xa.x1, k0.x);
                     a1.mac(xb.xl, xb.xh, xb.x0, xb.x1, k0.y);
                     a2.mac(xa.xl, xa.xh, xa.x0, xa.x1, k1.x);
@@ -394,8 +398,6 @@ template <int ND> struct KsInnerProductStaged {
                 }
                 *reinterpret_cast<ulonglong2 *>(po) = q0;
                 *reinterpret_cast<ulonglong2 *>(po + (u64)(L + 1) * N) = q1;
-                _Pragma("unroll") for (u32 j = 0; j < ND; j++) x[j] = xn[j];
-                xp = xpn;
             }
         })
     }
