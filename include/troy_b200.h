@@ -188,6 +188,30 @@ int troyb_add_plain(troyb_context *ctx, int level, uint64_t *d_c0, size_t ct_str
                     size_t plain_coeff_count, size_t plain_stride, uint64_t correction_factor, int subtract, size_t batch,
                     void *stream);
 
+/* ---- decryption: the step right after the path ------------------------------------------------- */
+
+/* DecryptorCuda::computeSecretKeyArray  src/decryptor_cuda.cu:188-235: d_out[i] = s^(i+1), i < max_power, each
+ * [key_limbs][N] in NTT form at the key level (d_secret = the secret key as KeyGenerator stores it). d_out may start at
+ * d_secret. */
+int troyb_secret_key_powers(troyb_context *ctx, const uint64_t *d_secret, size_t max_power, uint64_t *d_out, void *stream);
+
+/* DecryptorCuda::dotProductCtSkArray  src/decryptor_cuda.cu:237-300: d_phase[b] = c_0 + c_1 s + ... + c_{size-1} s^{size-1}
+ * over the level's limbs, [batch][L][N], in the form of the ciphertext (is_ntt_form = 0: coefficient form, BFV / BGV).
+ * For CKKS this IS the decrypted plaintext (ckksDecrypt :118-141). d_secret_powers: at least ct_size-1 powers. */
+int troyb_decrypt_dot_product(troyb_context *ctx, int level, const uint64_t *d_ct, size_t ct_size, size_t ct_stride, int is_ntt_form,
+                              const uint64_t *d_secret_powers, uint64_t *d_phase, size_t batch, void *stream);
+
+/* RNSToolCuda::decryptScaleAndRound  src/utils/rns_cuda.cu:499-577 (BFV, bfvDecrypt src/decryptor_cuda.cu:92-116):
+ * phase [batch][L][N] -> plaintext coefficients modulo t, [batch][N]. */
+int troyb_decrypt_scale_and_round(troyb_context *ctx, int level, const uint64_t *d_phase, uint64_t *d_plain, size_t batch,
+                                  void *stream);
+
+/* RNSToolCuda::decryptModt  src/utils/rns_cuda.cu:617-620 (exact base conversion q -> t, CPU src/utils/rns.cpp:462-538) and
+ * the correction-factor fix of bgvDecrypt  src/decryptor_cuda.cu:143-186: phase [batch][L][N] -> plaintext coefficients
+ * modulo t, [batch][N]. inv_correction_factor = correction_factor^-1 mod t (1 when the factor is 1). */
+int troyb_decrypt_mod_t(troyb_context *ctx, int level, const uint64_t *d_phase, uint64_t *d_plain, uint64_t inv_correction_factor,
+                        size_t batch, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

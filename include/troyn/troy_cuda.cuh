@@ -359,14 +359,66 @@ private:
     Encryptor enc_;
 };
 
+// DecryptorCuda (src/decryptor_cuda.cuh / .cu): the secret key powers live on the device; decrypt() is the dot product
+// c_0 + c_1 s + ... on the device followed by decryptScaleAndRound (BFV) / decryptModt (BGV) on the device; the plaintext
+// comes back to its host representation. invariantNoiseBudget stays host work (multi-precision arithmetic).
 class DecryptorCuda {
 public:
-    DecryptorCuda(const SEALContextCuda &context, const SecretKey &sk) : dec_(context.host(), sk) {}
-    void decrypt(const CiphertextCuda &ct, Plaintext &dst) { dec_.decrypt(ct.cpu(), dst); }
+    DecryptorCuda(const SEALContextCuda &context, const SecretKey &sk) : context_(context), dec_(context.host(), sk) {
+        key_words_ = sk.data().coeffCount();
+        powers_.allocate(key_words_);
+        powers_.upload(sk.data().data(), key_words_);
+        n_powers_ = 1;
+    }
+    void decrypt(const CiphertextCuda &ct, Plaintext &dst) {
+        if (ct.size() < 2) throw std::invalid_argument("encrypted is empty");
+        const SchemeType s = context_.firstContextData()->parms().scheme();
+        if (s == SchemeType::ckks && !ct.isNttForm()) throw std::invalid_argument("encrypted must be in NTT form");
+        if (s != SchemeType::ckks && ct.isNttForm()) throw std::invalid_argument("encrypted cannot be in NTT form");
+        const std::size_t need = ct.size() - 1;
+        if (need > n_powers_) { // computeSecretKeyArray  src/decryptor_cuda.cu:188-235
+            b200::DeviceWords p(need * key_words_);
+            b200::check(troyb_secret_key_powers(context_.handle(), powers_.get(), need, p.get(), nullptr));
+            powers_ = std::move(p);
+            n_powers_ = need;
+        }
+        const int lv = context_.levelOf(ct.parmsID());
+        const std::size_t n = ct.polyModulusDegree(), words = ct.polyCoeffSize();
+        b200::DeviceWords phase(words);
+        b200::check(troyb_decrypt_dot_product(context_.handle(), lv, ct.data(), ct.size(), ct.size() * words, ct.isNttForm() ? 1 : 0,
+                                              powers_.get(), phase.get(), 1, nullptr));
+        dst.parmsID() = parmsIDZero;
+        if (s == SchemeType::ckks) { // ckksDecrypt  src/decryptor_cuda.cu:118-141
+            dst.resize(words);
+            phase.download(dst.data(), words);
+            dst.parmsID() = ct.parmsID();
+            dst.scale() = ct.scale();
+            return;
+        }
+        b200::DeviceWords out(n);
+        if (s == SchemeType::bfv) {
+            b200::check(troyb_decrypt_scale_and_round(context_.handle(), lv, phase.get(), out.get(), 1, nullptr));
+        } else {
+            std::uint64_t fix = 1;
+            const auto &t = context_.firstContextData()->parms().plainModulus();
+            if (ct.correctionFactor() != 1 && !util::tryInvertUintMod(ct.correctionFactor(), t, fix))
+                throw std::logic_error("invalid correction factor");
+            b200::check(troyb_decrypt_mod_t(context_.handle(), lv, phase.get(), out.get(), fix, 1, nullptr));
+        }
+        dst.resize(n);
+        out.download(dst.data(), n);
+        // the CPU decryptor trims the plaintext to its significant coefficients (src/decryptor.cpp bfvDecrypt / bgvDecrypt)
+        std::size_t count = n;
+        while (count > 1 && dst.data()[count - 1] == 0) count--;
+        dst.resize(count);
+    }
     int invariantNoiseBudget(const CiphertextCuda &ct) { return dec_.invariantNoiseBudget(ct.cpu()); }
 
 private:
+    SEALContextCuda context_;
     Decryptor dec_;
+    b200::DeviceWords powers_;
+    std::size_t key_words_ = 0, n_powers_ = 0;
 };
 
 class EvaluatorCuda {

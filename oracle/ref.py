@@ -53,6 +53,8 @@ def lib():
             "ref_pt_words": (C.c_int, [vp, u64p]),
             "ref_pt_to_ntt": (C.c_int, [vp, vp, C.c_int]),
             "ref_eval_plain": (C.c_int, [vp, C.c_int, vp, vp]),
+            "ref_secret_key_words": (C.c_int, [vp, u64p]),
+            "ref_decrypt_plain": (vp, [vp, vp]),
             "ref_keygen": (C.c_int, [vp]),
             "ref_relin_keys": (vp, [vp]),
             "ref_galois_keys_elts": (vp, [vp, C.POINTER(C.c_uint32), C.c_int]),
@@ -294,6 +296,21 @@ class RefContext:
         if lib().ref_eval_plain(self.h, op, a.h, pt.h) != 0:
             raise RefError(_err())
         return a
+
+    def secret_key_words(self):
+        """[key_limbs][N] NTT-form words of the secret key (after keygen())."""
+        kl = len(self.level_moduli(-1))
+        out = np.zeros((kl, self.n), dtype=np.uint64)
+        if lib().ref_secret_key_words(self.h, _p(out)) != kl * self.n:
+            raise RefError(_err())
+        return out
+
+    def decrypt_plain(self, ct):
+        """Decryptor::decrypt -> RefPlaintext (coefficient form modulo t for BFV / BGV, NTT form for CKKS)."""
+        h = lib().ref_decrypt_plain(self.h, ct.h)
+        if not h:
+            raise RefError(_err())
+        return RefPlaintext(self, h)
 
     def eval(self, op, a, b=None, keys=None, arg=0):
         r = lib().ref_eval(self.h, op, a.h, b.h if b is not None else None, keys.h if keys is not None else None, arg)

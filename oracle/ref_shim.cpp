@@ -464,6 +464,25 @@ int ref_eval_plain(void *h, int op, void *cta, void *pth) {
     REF_CATCH(-1)
 }
 
+// The secret key as KeyGenerator stores it: [key_limbs][N] words, NTT form at the key level.
+int ref_secret_key_words(void *h, uint64_t *out) {
+    REF_TRY
+    auto c = static_cast<RefCtx *>(h);
+    const SecretKey &sk = c->keygen->secretKey();
+    std::memcpy(out, sk.data().data(), sk.data().coeffCount() * sizeof(uint64_t));
+    return (int)sk.data().coeffCount();
+    REF_CATCH(-1)
+}
+// Decryptor::decrypt (src/decryptor.cpp): returns a new plaintext handle (ref_pt_*)
+void *ref_decrypt_plain(void *h, void *cth) {
+    REF_TRY
+    auto c = static_cast<RefCtx *>(h);
+    auto pt = std::make_unique<Plaintext>();
+    c->decryptor->decrypt(*static_cast<Ciphertext *>(cth), *pt);
+    return pt.release();
+    REF_CATCH(nullptr)
+}
+
 // ---- encode / encrypt / decrypt (functional round trips; host-side, seeded PRNG) -------------
 void *ref_encrypt_batch(void *h, const uint64_t *values, int count) {
     REF_TRY

@@ -212,3 +212,29 @@ def run_matmul_flow(ref, tb, n, bits, rng, B=3, I=3, J=3, level=0):
                 acc = prod if acc is None else rc.eval(ref.OP_ADD, acc, prod)
             want = acc.words()
             assert np.array_equal(got[b * J + j], want), f"matmul [{b}][{j}]: {int((got[b * J + j] != want).sum())} words differ"
+
+
+def run_decrypt_flow(ref, tb, scheme, n, bits, rng, batch=2):
+    """Decryptor::decrypt (SURVEY.md §8f row 2) on synthetic ciphertexts of size 2 and 3 at levels 0 and 1, and on a real
+    encryption: every plaintext word against the reference CPU decryptor holding the same secret key."""
+    rc, ctx = make_pair(ref, tb, scheme, n, bits)
+    rc.keygen()
+    dec = tb.DecryptorCuda(ctx, rc.secret_key_words())
+    ckks = scheme == ref.CKKS
+    sc = 2.0 ** 30 if ckks else 1.0
+    for level in ([0, 1] if ctx.num_levels > 1 else [0]):
+        for size in (2, 3):
+            w = random_ct_words(rc, level, size, n, rng, batch)
+            cf = 1 if scheme != ref.BGV or size == 2 else 5  # BGV: also a non-trivial correction factor
+            got = dec.decrypt(tb.CiphertextCuda.from_host(ctx, w, level, ckks, sc, cf)).to_host()
+            for i in range(batch):
+                want = rc.decrypt_plain(rc.ciphertext(w[i], level, ckks, sc, cf)).words()
+                full = np.zeros(got.shape[1], dtype=np.uint64)
+                full[: want.size] = want  # the CPU decryptor trims leading zero coefficients of BFV plaintexts
+                assert np.array_equal(got[i], full), f"decrypt [scheme {scheme}, N {n}, level {level}, size {size}, elt {i}]"
+    if not ckks:
+        vals = rng.integers(0, rc.plain_modulus, n, dtype=np.uint64)
+        rct = rc.encrypt_batch(vals)
+        got = dec.decrypt(tb.CiphertextCuda.from_host(ctx, rct.words(), 0, False, 1.0)).to_host()[0]
+        want = rc.decrypt_plain(rct).words()
+        assert np.array_equal(got[: want.size], want) and not got[want.size:].any(), "decrypt of a real encryption"

@@ -4,7 +4,7 @@ it is a debugging aid, not the product path (the GPU parity tests in test_parity
 import numpy as np
 import pytest
 
-from common import run_evaluator_flow, run_matmul_flow, run_plain_flow
+from common import run_decrypt_flow, run_evaluator_flow, run_matmul_flow, run_plain_flow
 
 
 @pytest.mark.parametrize("scheme", [1, 2, 3])
@@ -61,3 +61,10 @@ def test_matmul_block_layout():
                     full = np.convolve(xv[b, i], wv[i, j])
                     out[b, j] += full[:n] - np.concatenate([full[n:], np.zeros(2 * n - len(full))])[:n]
         assert np.array_equal(h.read_outputs(out), x @ w)
+
+
+@pytest.mark.parametrize("scheme,n,bits", [(2, 64, [40, 30, 30, 40]), (1, 128, [40, 30, 30, 40]), (1, 4096, [60, 40, 40, 60]),
+                                           (2, 16384, [60, 40, 60]), (3, 256, [40, 30, 30, 40]), (3, 4096, [60, 40, 40, 60])])
+def test_decrypt_emulated(ref, emul_lib, scheme, n, bits):
+    """CKKS / BFV / BGV decryption on the device against the reference CPU decryptor."""
+    run_decrypt_flow(ref, emul_lib, scheme, n, bits, np.random.default_rng(500 + scheme + n))

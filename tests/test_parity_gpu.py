@@ -3,7 +3,8 @@ metadata are compared with the reference troy:: CPU library (oracle/_ref) on ide
 import numpy as np
 import pytest
 
-from common import assert_same, make_pair, random_ct_words, run_evaluator_flow, run_matmul_flow, run_plain_flow
+from common import (assert_same, make_pair, random_ct_words, run_decrypt_flow, run_evaluator_flow, run_matmul_flow,
+                    run_plain_flow)
 
 pytestmark = pytest.mark.gpu
 
@@ -82,6 +83,12 @@ def test_config5_full_size_key_switch(ref, cuda_lib):
     ev.relinearize_inplace(a, d_rlk)
     rc.eval(ref.OP_RELIN, ra, keys=rks)
     assert_same(a, ra, "config 5 multiply + relinearize at level 2")
+
+
+@pytest.mark.parametrize("scheme,n,bits", FLOWS)
+def test_decrypt(ref, cuda_lib, scheme, n, bits):
+    """CKKS / BFV / BGV decryption on the device against the reference CPU decryptor."""
+    run_decrypt_flow(ref, cuda_lib, scheme, n, bits, np.random.default_rng(5000 + n + scheme))
 
 
 def test_matmul(ref, cuda_lib):

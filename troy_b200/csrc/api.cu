@@ -874,6 +874,119 @@ int troyb_add_plain(troyb_context *ctx, int level, uint64_t *d_c0, size_t ct_str
     API_END
 }
 
+// ---- decryption ------------------------------------------------------------------------------------------------------------
+int troyb_secret_key_powers(troyb_context *ctx, const uint64_t *d_secret, size_t max_power, uint64_t *d_out, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const u32 KL = (u32)level_limbs(c, -1);
+    if (max_power < 1) throw std::invalid_argument("max_power cannot be zero");
+    check_aligned(d_secret, "secret");
+    check_aligned(d_out, "out");
+    cudaStream_t s = S(stream);
+    const u64 words = (u64)KL * c->N;
+    if (d_out != d_secret) ck(cudaMemcpyAsync(d_out, d_secret, words * 8, cudaMemcpyDeviceToDevice, s));
+    for (size_t i = 1; i < max_power; i++) {
+        // computeSecretKeyArray  src/decryptor_cuda.cu:188-235: s^(i+1) = s^i * s, limb-wise over the key-level base
+        EltMulPlain k{};
+        k.logN = c->logN;
+        k.mods = c->d_mods;
+        k.map = c->has_special ? c->map_prefix_special(c->Ltop) : c->map_prefix(c->Ltop);
+        k.n_limbs = KL;
+        k.per_ct = words;
+        k.total = words / 2;
+        k.ct = d_out + (i - 1) * words; k.plain = d_out; k.out = d_out + i * words;
+        ck(launch_cta(k, grid_for(k.total, EltMulPlain::kThreads), 0, s));
+    }
+    API_END
+}
+
+int troyb_decrypt_dot_product(troyb_context *ctx, int level, const uint64_t *d_ct, size_t ct_size, size_t ct_stride, int is_ntt_form,
+                              const uint64_t *d_secret_powers, uint64_t *d_phase, size_t batch, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const u32 L = (u32)level_limbs(c, level);
+    if (level < 0) throw std::invalid_argument("level is not valid for encryption parameters");
+    if (ct_size < 2 || ct_size > 8) throw std::invalid_argument("encrypted is empty");
+    check_batch_stride(ct_stride, ct_size * L * c->N, "ct");
+    check_aligned(d_ct, "ct");
+    check_aligned(d_secret_powers, "secret");
+    check_aligned(d_phase, "phase");
+    if (batch == 0) return 0;
+    cudaStream_t s = S(stream);
+    const LimbMap map = c->map_prefix(L);
+    const u64 per_ct = (u64)ct_size * L * c->N;
+    // coefficient form (BFV / BGV): the transform is linear, so NTT every poly (c_0 included), take the dot product in the
+    // NTT domain and transform back: the canonical phase c_0 + INTT(sum NTT(c_i) s^i) of src/decryptor_cuda.cu:262-268
+    Scratch tmp(is_ntt_form ? 0 : (size_t)batch * per_ct, s);
+    const u64 *src = d_ct;
+    u64 src_stride = ct_stride;
+    if (!is_ntt_form) {
+        ntt_plain(c, false, map, L, d_ct, ct_stride, tmp.p, per_ct, (u32)ct_size * L, (u32)batch, true, s);
+        src = tmp.p;
+        src_stride = per_ct;
+    }
+    EltDecryptDot k{};
+    k.logN = c->logN;
+    k.mods = c->d_mods;
+    k.map = map;
+    k.n_limbs = L;
+    k.ct_size = (u32)ct_size;
+    k.key_limbs = (u32)level_limbs(c, -1);
+    k.total = (u64)batch * L * c->N / 2;
+    k.ct = src; k.sk = d_secret_powers; k.out = d_phase;
+    k.ct_stride = src_stride;
+    ck(launch_cta(k, grid_for(k.total, EltDecryptDot::kThreads), 0, s));
+    if (!is_ntt_form) ntt_plain(c, true, map, L, d_phase, (u64)L * c->N, d_phase, (u64)L * c->N, L, (u32)batch, true, s);
+    API_END
+}
+
+int troyb_decrypt_scale_and_round(troyb_context *ctx, int level, const uint64_t *d_phase, uint64_t *d_plain, size_t batch, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const u32 L = (u32)level_limbs(c, level);
+    if (level < 0) throw std::invalid_argument("level is not valid for encryption parameters");
+    const LevelData &lv = c->levels[level];
+    if (!lv.has_decrypt || c->scheme != SCHEME_BFV) throw std::invalid_argument("unsupported scheme");
+    if (batch == 0) return 0;
+    EltDecryptScaleRound k{};
+    k.logN = c->logN;
+    k.mods = c->d_mods;
+    k.map = c->map_prefix(L);
+    k.n_limbs = L;
+    k.gamma_pool = (u32)c->pool_gamma;
+    k.total = (u64)batch * c->N;
+    k.phase = d_phase; k.out = d_plain;
+    k.dc = lv.decrypt;
+    ck(launch_cta(k, grid_for(k.total, EltDecryptScaleRound::kThreads), 0, S(stream)));
+    API_END
+}
+
+int troyb_decrypt_mod_t(troyb_context *ctx, int level, const uint64_t *d_phase, uint64_t *d_plain, uint64_t inv_correction_factor,
+                        size_t batch, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const u32 L = (u32)level_limbs(c, level);
+    if (level < 0) throw std::invalid_argument("level is not valid for encryption parameters");
+    const LevelData &lv = c->levels[level];
+    if (!lv.has_decrypt) throw std::invalid_argument("unsupported scheme");
+    if (batch == 0) return 0;
+    EltDecryptModT k{};
+    k.logN = c->logN;
+    k.mods = c->d_mods;
+    k.map = c->map_prefix(L);
+    k.n_limbs = L;
+    k.total = (u64)batch * c->N;
+    k.phase = d_phase; k.out = d_plain;
+    k.inv_factor = inv_correction_factor;
+    k.dc = lv.decrypt;
+    ck(launch_cta(k, grid_for(k.total, EltDecryptModT::kThreads), 0, S(stream)));
+    API_END
+}
+
 int troyb_switch_key(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_stride, const uint64_t *d_target,
                      size_t target_stride, const uint64_t *d_key, size_t batch, void *stream) {
     API_BEGIN

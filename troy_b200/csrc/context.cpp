@@ -91,6 +91,36 @@ void build_plain(const Context &ctx, LevelData &lv) {
     lv.has_plain = true;
 }
 
+// RNSTool's constants for BFV decryption ({t, gamma} base, src/utils/rns.cpp:748-775) and BGV decryption (exact conversion
+// q -> t, src/utils/rns.cpp:462-538)
+void build_decrypt(const Context &ctx, LevelData &lv) {
+    const u64 t = ctx.plain;
+    std::vector<u64> q(ctx.pool.begin(), ctx.pool.begin() + lv.L);
+    DecryptConsts &d = lv.decrypt;
+    d.t = t;
+    d.q_mod_t = punctured_prod_mod(q, -1, t);
+    u64 inv;
+    for (int i = 0; i < lv.L; i++) {
+        d.punct_mod_t[i] = punctured_prod_mod(q, i, t);
+        d.inv_punct_q[i] = invert(punctured_prod_mod(q, i, q[i]), q[i]);
+    }
+    if (ctx.pool_gamma >= 0) {
+        const u64 g = ctx.pool[ctx.pool_gamma];
+        d.gamma = g;
+        if (!try_invert(g % t, t, inv)) throw std::logic_error("invalid rns bases");
+        d.inv_gamma_mod_t = inv;
+        if (!try_invert(d.q_mod_t, t, inv)) throw std::logic_error("invalid rns bases");
+        d.neg_inv_q_mod_t = (t - inv) % t;
+        if (!try_invert(punctured_prod_mod(q, -1, g), g, inv)) throw std::logic_error("invalid rns bases");
+        d.neg_inv_q_mod_gamma = (g - inv) % g;
+        for (int i = 0; i < lv.L; i++) {
+            d.tg_mod_q[i] = mulmod(t % q[i], g % q[i], q[i]);
+            d.punct_mod_gamma[i] = punctured_prod_mod(q, i, g);
+        }
+    }
+    lv.has_decrypt = true;
+}
+
 void build_drop(Context &ctx, const std::vector<u64> &base, std::vector<void *> &owned, DropDev &out, DropLimb *&d_limbs,
                 int last_pool) {
     int m = (int)base.size() - 1;
@@ -383,6 +413,7 @@ Context *context_create(int device, int scheme, u64 N, const u64 *moduli, int n_
             lv.last_prime_as_double = (double)base.back();
         }
         if (scheme == SCHEME_BFV) build_behz(*ctx, lv);
+        if (scheme != SCHEME_CKKS && plain_modulus > 1) build_decrypt(*ctx, lv);
         if (scheme != SCHEME_CKKS && plain_modulus > 1) build_plain(*ctx, lv);
     }
     if (ctx->has_special) {

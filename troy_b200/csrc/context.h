@@ -91,6 +91,19 @@ struct PlainConsts {
     u64 delta[kMaxLimbs];    // coeff_div_plain_modulus: floor(Q / t) mod q_i
 };
 
+// Constants of RNSToolCuda::decryptScaleAndRound (BFV; gamma = 0 otherwise) and decryptModt (BGV) for one level
+// (src/utils/rns.cpp:748-775, 462-538), passed by value with the launch.
+struct DecryptConsts {
+    u64 t, gamma;
+    u64 neg_inv_q_mod_t, neg_inv_q_mod_gamma; // -(Q^-1) mod t, mod gamma
+    u64 inv_gamma_mod_t;
+    u64 tg_mod_q[kMaxLimbs];        // t * gamma mod q_i
+    u64 punct_mod_t[kMaxLimbs];     // (Q / q_i) mod t
+    u64 punct_mod_gamma[kMaxLimbs]; // (Q / q_i) mod gamma
+    u64 inv_punct_q[kMaxLimbs];     // (Q / q_i)^-1 mod q_i
+    u64 q_mod_t;                    // Q mod t (BGV decryptModt)
+};
+
 struct LimbMap {
     uint8_t idx[kMaxLimbs]; // pool index of launch limb l
 };
@@ -103,6 +116,8 @@ struct LevelData {
     BehzDev behz{};
     std::vector<void *> owned;       // device allocations
     double last_prime_as_double = 0; // for scale bookkeeping
+    bool has_decrypt = false;        // BFV / BGV
+    DecryptConsts decrypt{};
     bool has_plain = false;          // BFV / BGV
     PlainConsts plain{};
 };

@@ -600,6 +600,144 @@ struct EltAddPlain {
     }
 };
 
+// ---- decryption --------------------------------------------------------------------------------------
+// DecryptorCuda::dotProductCtSkArray  src/decryptor_cuda.cu:237-300 on NTT-form operands: phase = c_0 + sum_{i>=1} c_i s^i,
+// one pass with a 128-bit lazy sum (the reference: one product and one addition launch per term through global memory).
+struct EltDecryptDot {
+    static constexpr int kThreads = kEltThreads;
+    const char *name() const { return "decrypt_dot_product"; }
+    int logN;
+    const ModDev *mods;
+    LimbMap map;
+    u32 n_limbs, ct_size, key_limbs;
+    u64 total; // batch * n_limbs * N / 2 threads
+    const u64 *ct;
+    const u64 *sk; // [power][key_limbs][N], NTT form at the key level: power i holds s^(i+1)
+    u64 *out;      // [batch][n_limbs][N]
+    u64 ct_stride;
+    TB_D void operator()(u32 bid, u64 *) const {
+        TB_PHASE(kThreads, t, {
+            const u64 idx = (u64)bid * kThreads + t;
+            if (idx < total) {
+                const u64 per = ((u64)n_limbs << logN) >> 1;
+                const u64 b = idx / per, rem = (idx % per) * 2;
+                const ModDev &m = mods[map.idx[(u32)(rem >> logN)]];
+                const u64 *pc = ct + b * ct_stride + rem;
+                const ulonglong2 c0 = EltTensor::ld2(pc);
+                u64 lo0 = c0.x, hi0 = 0, lo1 = c0.y, hi1 = 0;
+                for (u32 i = 1; i < ct_size; i++) {
+                    const ulonglong2 c = EltTensor::ld2(pc + (u64)i * (per * 2));
+                    const ulonglong2 s = EltTensor::ld2(sk + (((u64)(i - 1) * key_limbs) << logN) + rem);
+                    mac128(lo0, hi0, c.x, s.x);
+                    mac128(lo1, hi1, c.y, s.y);
+                }
+                EltTensor::st2(out + b * (per * 2) + rem, barrett128(lo0, hi0, m.p, m.ratio0, m.ratio1),
+                               barrett128(lo1, hi1, m.p, m.ratio0, m.ratio1));
+            }
+        })
+    }
+};
+
+// RNSToolCuda::decryptScaleAndRound  src/utils/rns_cuda.cu:499-577 (CPU src/utils/rns.cpp:1040-1075): the phase modulo q
+// becomes the plaintext modulo t. One thread per coefficient does the reference's four launches: x t gamma, fast base
+// conversion q -> {t, gamma}, x -(Q^-1), and the gamma-correction with the final x gamma^-1 mod t. Integer only.
+struct EltDecryptScaleRound {
+    static constexpr int kThreads = kEltThreads;
+    const char *name() const { return "decrypt_scale_round"; }
+    int logN;
+    const ModDev *mods;
+    LimbMap map;          // q_0 .. q_{L-1}
+    u32 n_limbs;
+    u32 gamma_pool;       // pool index of gamma
+    u64 total;            // batch * N
+    const u64 *phase;     // [batch][L][N]
+    u64 *out;             // [batch][N]
+    DecryptConsts dc;
+    TB_D void operator()(u32 bid, u64 *) const {
+        TB_PHASE(kThreads, t, {
+            const u64 idx = (u64)bid * kThreads + t;
+            if (idx < total) {
+                const u64 N = u64(1) << logN;
+                const u64 b = idx >> logN, c = idx & (N - 1);
+                const u64 *ph = phase + ((b * n_limbs) << logN) + c;
+                const ModDev &mg = mods[gamma_pool];
+                unsigned __int128 st = 0, sg = 0;
+                for (u32 i = 0; i < n_limbs; i++) {
+                    const ModDev &m = mods[map.idx[i]];
+                    u64 y = mulmod_barrett(ph[(u64)i << logN], dc.tg_mod_q[i], m.p, m.ratio0, m.ratio1);
+                    y = mulmod_barrett(y, dc.inv_punct_q[i], m.p, m.ratio0, m.ratio1);
+                    st += (unsigned __int128)y * dc.punct_mod_t[i];
+                    sg += (unsigned __int128)y * dc.punct_mod_gamma[i];
+                    if ((i & 31) == 31) {
+                        st %= dc.t;
+                        sg = barrett128((u64)sg, (u64)(sg >> 64), mg.p, mg.ratio0, mg.ratio1);
+                    }
+                }
+                u64 vt = (u64)(st % dc.t);
+                u64 vg = barrett128((u64)sg, (u64)(sg >> 64), mg.p, mg.ratio0, mg.ratio1);
+                vt = (u64)(((unsigned __int128)vt * dc.neg_inv_q_mod_t) % dc.t);
+                vg = mulmod_barrett(vg, dc.neg_inv_q_mod_gamma, mg.p, mg.ratio0, mg.ratio1);
+                u64 d;
+                if (vg > (dc.gamma >> 1)) d = addmod(vt, (dc.gamma - vg) % dc.t, dc.t);
+                else d = submod(vt, vg % dc.t, dc.t);
+                if (d != 0) d = (u64)(((unsigned __int128)d * dc.inv_gamma_mod_t) % dc.t);
+                out[idx] = d;
+            }
+        })
+    }
+};
+
+// RNSToolCuda::decryptModt  src/utils/rns_cuda.cu:617-620 = BaseConverter::exactConvertArray q -> t (CPU
+// src/utils/rns.cpp:462-538), then x correction_factor^-1 (bgvDecrypt src/decryptor_cuda.cu:143-186). The rounding term
+// v = floor(sum_i y_i / q_i + 0.5) is formed in double precision exactly as the CPU path does it (IEEE division, the sum
+// taken in limb order, truncating conversion), so the result is the same word.
+struct EltDecryptModT {
+    static constexpr int kThreads = kEltThreads;
+    const char *name() const { return "decrypt_mod_t"; }
+    int logN;
+    const ModDev *mods;
+    LimbMap map;
+    u32 n_limbs;
+    u64 total;        // batch * N
+    const u64 *phase; // [batch][L][N]
+    u64 *out;         // [batch][N]
+    u64 inv_factor;   // correction_factor^-1 mod t (1: none)
+    DecryptConsts dc;
+    TB_D void operator()(u32 bid, u64 *) const {
+        TB_PHASE(kThreads, t, {
+            const u64 idx = (u64)bid * kThreads + t;
+            if (idx < total) {
+                const u64 N = u64(1) << logN;
+                const u64 b = idx >> logN, c = idx & (N - 1);
+                const u64 *ph = phase + ((b * n_limbs) << logN) + c;
+                unsigned __int128 st = 0;
+                double v = 0.0;
+                for (u32 i = 0; i < n_limbs; i++) {
+                    const ModDev &m = mods[map.idx[i]];
+                    const u64 y = mulmod_barrett(ph[(u64)i << logN], dc.inv_punct_q[i], m.p, m.ratio0, m.ratio1);
+#if defined(TROYB_HOST_EMUL)
+                    v = v + (double)y / (double)m.p;
+#else
+                    v = __dadd_rn(v, __ddiv_rn(__ull2double_rn(y), __ull2double_rn(m.p)));
+#endif
+                    st += (unsigned __int128)y * dc.punct_mod_t[i];
+                    if ((i & 31) == 31) st %= dc.t;
+                }
+#if defined(TROYB_HOST_EMUL)
+                const u64 rounded = (u64)(v + 0.5);
+#else
+                const u64 rounded = __double2ull_rz(__dadd_rn(v, 0.5));
+#endif
+                const u64 sum = (u64)(st % dc.t);
+                const u64 vq = (u64)(((unsigned __int128)rounded * dc.q_mod_t) % dc.t);
+                u64 d = submod(sum, vq, dc.t);
+                if (inv_factor != 1) d = (u64)(((unsigned __int128)d * inv_factor) % dc.t);
+                out[idx] = d;
+            }
+        })
+    }
+};
+
 // ---- Galois automorphisms ---------------------------------------------------------------------------------
 // gApplyGalois (coefficient form, scatter)  src/utils/galois_cuda.cu:139-164 ; CPU src/utils/galois.cpp:141-175
 // gApplyGaloisNtt (NTT form, gather)        src/utils/galois_cuda.cu:181-196 ; table rule src/utils/galois_cuda.cu:26-42

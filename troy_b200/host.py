@@ -405,6 +405,58 @@ class GaloisKeysCuda(KSwitchKeysCuda):
         return self.data(self.get_index(galois_elt))
 
 
+class DecryptorCuda:
+    """src/decryptor_cuda.cuh / .cu: decryption on the device for the three schemes. ``secret_key_words``: ``[key_limbs][N]`` NTT-form words of the secret key at the key
+    level, as ``KeyGenerator`` stores it. A batched ciphertext decrypts to a batched plaintext."""
+
+    def __init__(self, context, secret_key_words, stream=None):
+        self.context, self.stream = context, stream
+        w = np.ascontiguousarray(secret_key_words, dtype=np.uint64)
+        self.key_words = context.level_limbs(SEALContextCuda.KEY_LEVEL) * context.n
+        if w.size != self.key_words:
+            raise TroyInvalidArgument("secret key is not valid for encryption parameters")
+        self.powers = DeviceArray(self.key_words)
+        self.powers.upload(w.reshape(-1))
+        self.n_powers = 1
+
+    def _ensure_powers(self, max_power):
+        """computeSecretKeyArray (src/decryptor_cuda.cu:188-235)"""
+        if max_power <= self.n_powers:
+            return
+        new = DeviceArray(max_power * self.key_words)
+        _L().call("troyb_secret_key_powers", _vp(self.context.h), _vp(self.powers.ptr), max_power, _vp(new.ptr), _vp(self.stream))
+        self.powers, self.n_powers = new, max_power
+
+    def decrypt(self, ct):
+        scheme = self.context.scheme
+        if ct.size < 2:
+            raise TroyInvalidArgument("encrypted is empty")
+        if scheme == CKKS and not ct.is_ntt_form:
+            raise TroyInvalidArgument("encrypted must be in NTT form")
+        if scheme != CKKS and ct.is_ntt_form:
+            raise TroyInvalidArgument("encrypted cannot be in NTT form")
+        self._ensure_powers(ct.size - 1)
+        words = ct.limbs * self.context.n
+        phase = DeviceArray(ct.batch * words)
+        _L().call("troyb_decrypt_dot_product", _vp(self.context.h), ct.parms_id, _vp(ct.ptr()), ct.size, ct.stride,
+                  int(ct.is_ntt_form), _vp(self.powers.ptr), _vp(phase.ptr), ct.batch, _vp(self.stream))
+        if scheme == CKKS:
+            return PlaintextCuda(self.context, words, ct.parms_id, ct.scale, ct.batch, data=phase)
+        out = PlaintextCuda(self.context, self.context.n, None, 1.0, ct.batch)
+        if scheme == BGV:
+            t = self.context.parms.plain_modulus
+            try:
+                fix = pow(ct.correction_factor, -1, t) if ct.correction_factor != 1 else 1
+            except ValueError:
+                raise TroyLogicError("invalid correction factor")
+            _L().call("troyb_decrypt_mod_t", _vp(self.context.h), ct.parms_id, _vp(phase.ptr), _vp(out.data.ptr), C.c_uint64(fix),
+                      ct.batch, _vp(self.stream))
+            return out
+        _L().call("troyb_decrypt_scale_and_round", _vp(self.context.h), ct.parms_id, _vp(phase.ptr), _vp(out.data.ptr), ct.batch,
+                  _vp(self.stream))
+        return out
+
+
 def _balance_correction_factors(f1, f2, t):
     """balanceCorrectionFactors, src/evaluator_cuda.cu:53-114: the pair (e1, e2) with e1 f1 = e2 f2 (mod t) of least
     |e1| + |e2| among the remainders of the extended Euclid run on (t, f2 / f1). Returns (new factor, e1, e2)."""

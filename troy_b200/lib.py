@@ -80,6 +80,10 @@ _SIGNATURES = {
     "troyb_matmul_plain_ntt": (C.c_int, [_vp, C.c_int, _vp, _sz, _sz, _vp, _vp, _sz, _sz, _sz, _sz, _vp]),
     "troyb_plain_lift": (C.c_int, [_vp, C.c_int, _vp, _sz, _sz, _vp, _sz, C.c_int, _vp]),
     "troyb_multiply_plain_normal": (C.c_int, [_vp, C.c_int, _vp, _sz, _sz, _vp, _sz, _sz, _vp]),
+    "troyb_secret_key_powers": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
+    "troyb_decrypt_dot_product": (C.c_int, [_vp, C.c_int, _vp, _sz, _sz, C.c_int, _vp, _vp, _sz, _vp]),
+    "troyb_decrypt_scale_and_round": (C.c_int, [_vp, C.c_int, _vp, _vp, _sz, _vp]),
+    "troyb_decrypt_mod_t": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_uint64, _sz, _vp]),
     "troyb_add_plain": (C.c_int, [_vp, C.c_int, _vp, _sz, _vp, _sz, _sz, C.c_uint64, C.c_int, _sz, _vp]),
 }
 
