@@ -94,7 +94,7 @@ void set_order(const Context *ctx, NttArgs &a, u32 n_limbs_in_map) {
     std::vector<int> heavy, light;
     for (u32 i = 0; i < n_limbs_in_map; i++) {
         const int pol = ctx->h_mods[a.map.idx[i]].policy;
-        (pol == POLICY_U64_FAST || pol == POLICY_U64_EXACT ? heavy : light).push_back((int)i);
+        (pol == POLICY_U64_FAST || pol == POLICY_U64_EXACT || pol == POLICY_U64_LAZY ? heavy : light).push_back((int)i);
     }
     size_t ih = 0, il = 0;
     for (u32 r = 0; r < n_limbs_in_map; r++) {

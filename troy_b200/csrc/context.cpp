@@ -360,7 +360,7 @@ Context *context_create(int device, int scheme, u64 N, const u64 *moduli, int n_
         const char *force = getenv("TROYB_NTT_POLICY");
         const bool force_exact = force && std::string(force) == "exact";
         const bool force_fast = force && std::string(force) == "fast";
-        md.policy = (p >> 60) || force_exact ? POLICY_U64_EXACT : POLICY_U64_FAST;
+        md.policy = (p >> 60) || force_exact ? POLICY_U64_EXACT : ((p >> 57) || force_fast ? POLICY_U64_FAST : POLICY_U64_LAZY);
         md.fwd_d = md.inv_d = nullptr;
         md.pd = (double)p;
         md.pinv_d = 1.0 / (double)p;

@@ -173,6 +173,19 @@ struct ArithU64Fast {
     }
 };
 
+// The fast integer path for p < 2^57 (e.g. the 50-bit primes of the N = 32768 / 65536 parameter sets): a forward
+// butterfly adds less than 4p to the magnitude of its inputs, so log2 N <= 16 layers from a start below 4p stay below
+// 68p < 2^64 and the forward transform needs NO range correction (5 of its 27 instructions per butterfly); the store's
+// Barrett reduction accepts any 64-bit value. The inverse transform is ArithU64Fast's.
+struct ArithU64Lazy : ArithU64Fast {
+    static TB_D void ct(elem &X, elem &Y, tw_t w, const Mod &m) {
+        const u64 x = X;
+        const u64 xn = mul_acc(x, Y, w, m);     // x + T, T in [0,4p)
+        X = xn;
+        Y = (x + m.p4) + (x - xn);              // x + 4p - T
+    }
+};
+
 // FP64 path for p < 2^46: residues are integers held exactly in doubles (|x| < 2^51 throughout). The product y*w is
 // formed exactly as h + l with one multiply and one FMA, the quotient comes from y * (w/p) rounded to nearest with the
 // 1.5*2^52 trick, and h - q*p + l is exact, so the result is the balanced residue up to a tiny excess:
