@@ -399,6 +399,21 @@ def run_ours(args):
         except Exception as e:  # the baseline is reporting only; never fail the bench for it
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
 
+    # ---- the reference's OWN CUDA path (troyn::, unmodified sources compiled for sm_100a: oracle/_ref/troyn_ref_bench) on this
+    # GPU, same configuration, one reference call per ciphertext (it has no batch API). A reported baseline like the CPU one.
+    ref_cuda = None
+    tool = os.path.join(ROOT, "oracle", "_ref", "troyn_ref_bench")
+    if world == 1 and not args.no_cpu_baseline and os.path.exists(tool):
+        try:
+            import subprocess
+            torch.cuda.synchronize()
+            r = subprocess.run([tool, "bench", "64", "3"], capture_output=True, text=True, timeout=600)
+            for ln in r.stdout.splitlines():
+                if ln.startswith("{"):
+                    ref_cuda = json.loads(ln)
+        except Exception as e:  # the baseline is optional; the bench line must still print
+            ref_cuda = {"unavailable": str(e)[:200]}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": t_main / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -419,6 +434,7 @@ def run_ours(args):
         "matmul": {"multiply_plain_accumulate_per_s": world * mm_terms * extra_steps / t_mm, "ms": t_mm / extra_steps * 1e3,
                    "shape": f"{MB_}x{MI_} ciphertexts times {MI_}x{MJ_} plaintexts, one launch",
                    "gbs": mm_bytes * extra_steps / t_mm / 1e9, "frac_of_hbm_roofline": mm_bytes * extra_steps / t_mm / 1e9 / hbm_peak},
+        "reference_cuda_path": ref_cuda,
         "kernels": kernels,
     }
     print(json.dumps(line))

@@ -1,0 +1,60 @@
+"""`-m gpu`: parity with the reference's OWN CUDA path (troyn::), the second target north_star names. oracle/_ref/troyn_ref_bench
+is the unmodified reference CUDA library compiled for sm_100a (oracle/Makefile `refcuda`) plus a small driver
+(oracle/ref_cuda_bench.cu). Both sides get the same synthetic ciphertexts and the same seeded keys; every ciphertext word
+after multiply, relinearize, rescale / rotate_rows and rotate_vector / mod_switch must agree."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from common import make_pair, random_ct_words, upload_keys
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOOL = os.path.join(ROOT, "oracle", "_ref", "troyn_ref_bench")
+
+
+@pytest.mark.parametrize("scheme,n,bits", [(2, 16384, [60, 40, 40, 40, 40, 40, 40, 40, 60]), (1, 8192, [60, 40, 40, 60]),
+                                           (3, 8192, [60, 40, 40, 60]), (2, 4096, [60, 40, 40, 60])])
+def test_same_words_as_the_reference_cuda_path(ref, cuda_lib, tmp_path, scheme, n, bits):
+    if not os.path.exists(TOOL):
+        pytest.skip("oracle/_ref/troyn_ref_bench not built (make -C oracle refcuda where /root/reference exists)")
+    tb = cuda_lib
+    rng = np.random.default_rng(9000 + n + scheme)
+    rc, ctx = make_pair(ref, tb, scheme, n, bits)
+    q = rc.level_moduli(-1)
+    w1, w2 = random_ct_words(rc, 0, 2, n, rng), random_ct_words(rc, 0, 2, n, rng)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(fin, "wb") as f:
+        np.array([scheme, n, len(q), rc.plain_modulus], dtype=np.uint64).tofile(f)
+        np.array(q, dtype=np.uint64).tofile(f)
+        w1.tofile(f)
+        w2.tofile(f)
+    r = subprocess.run([TOOL, "dump", fin, fout], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    raw = np.fromfile(fout, dtype=np.uint64)
+    steps, pos = [], 0
+    while pos < raw.size:
+        cnt = int(raw[pos])
+        steps.append(raw[pos + 1: pos + 1 + cnt])
+        pos += 1 + cnt
+    assert len(steps) == 4
+    # our side: the same keys (the CPU key generator with the same seed and call order) and the same inputs
+    rlk, gk, d_rlk, d_gk = upload_keys(tb, ctx, rc, ref)
+    ev = tb.EvaluatorCuda(ctx)
+    ckks = scheme == ref.CKKS
+    sc = 2.0 ** 40 if ckks else 1.0
+    a = tb.CiphertextCuda.from_host(ctx, w1, 0, ckks, sc)
+    b = tb.CiphertextCuda.from_host(ctx, w2, 0, ckks, sc)
+    names = ["multiply", "relinearize"] + (["rescale", "rotate_vector"] if ckks else ["rotate_rows", "mod_switch"])
+    ops = [lambda: ev.multiply_inplace(a, b), lambda: ev.relinearize_inplace(a, d_rlk)]
+    if ckks:
+        ops += [lambda: ev.rescale_to_next_inplace(a), lambda: ev.rotate_vector_inplace(a, 1, d_gk)]
+    else:
+        ops += [lambda: ev.rotate_rows_inplace(a, 1, d_gk), lambda: ev.mod_switch_to_next_inplace(a)]
+    for name, op, want in zip(names, ops, steps):
+        op()
+        got = a.to_host()[0].reshape(-1)
+        assert got.size == want.size, name
+        assert np.array_equal(got, want), f"{name}: {int((got != want).sum())} of {got.size} words differ from the reference CUDA path"

@@ -525,7 +525,15 @@ class EvaluatorCuda:
             raise TroyInvalidArgument("NTT form mismatch")
 
     # -- add / sub / negate (src/evaluator_cuda.cu:143-260)
+    @staticmethod
+    def _dense(ct):
+        """the batch is one contiguous run of polys (no spare capacity between ciphertexts): one launch covers it"""
+        return ct.capacity == ct.size
+
     def negate_inplace(self, ct):
+        if self._dense(ct):
+            _L().call("troyb_negate", self._h(), ct.parms_id, _vp(ct.ptr()), _vp(ct.ptr()), ct.batch * ct.size, self._s())
+            return
         for b in range(ct.batch):
             _L().call("troyb_negate", self._h(), ct.parms_id, _vp(ct.ptr(0, b)), _vp(ct.ptr(0, b)), ct.size, self._s())
 
@@ -544,6 +552,9 @@ class EvaluatorCuda:
             raise TroyInvalidArgument("scale mismatch")
         mn, mx = min(a.size, b.size), max(a.size, b.size)
         a_old = a.size
+        if a.size == b.size and self._dense(a) and self._dense(b):
+            _L().call(name, self._h(), a.parms_id, _vp(a.ptr()), _vp(b.ptr()), _vp(a.ptr()), a.batch * a.size, self._s())
+            return
         a.resize(mx)
         for i in range(a.batch):
             _L().call(name, self._h(), a.parms_id, _vp(a.ptr(0, i)), _vp(b.ptr(0, i)), _vp(a.ptr(0, i)), mn, self._s())
@@ -823,15 +834,21 @@ class EvaluatorCuda:
     def transform_to_ntt_inplace(self, ct):
         if ct.is_ntt_form:
             raise TroyInvalidArgument("encrypted is already in NTT form")
-        for b in range(ct.batch):
-            _L().call("troyb_ntt_forward", self._h(), ct.parms_id, _vp(ct.ptr(0, b)), ct.size, self._s())
+        if self._dense(ct):
+            _L().call("troyb_ntt_forward", self._h(), ct.parms_id, _vp(ct.ptr()), ct.batch * ct.size, self._s())
+        else:
+            for b in range(ct.batch):
+                _L().call("troyb_ntt_forward", self._h(), ct.parms_id, _vp(ct.ptr(0, b)), ct.size, self._s())
         ct.is_ntt_form = True
 
     def transform_from_ntt_inplace(self, ct):
         if not ct.is_ntt_form:
             raise TroyInvalidArgument("encrypted_ntt is not in NTT form")
-        for b in range(ct.batch):
-            _L().call("troyb_ntt_inverse", self._h(), ct.parms_id, _vp(ct.ptr(0, b)), ct.size, self._s())
+        if self._dense(ct):
+            _L().call("troyb_ntt_inverse", self._h(), ct.parms_id, _vp(ct.ptr()), ct.batch * ct.size, self._s())
+        else:
+            for b in range(ct.batch):
+                _L().call("troyb_ntt_inverse", self._h(), ct.parms_id, _vp(ct.ptr(0, b)), ct.size, self._s())
         ct.is_ntt_form = False
 
     def synchronize(self):
