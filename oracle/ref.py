@@ -55,6 +55,7 @@ def lib():
             "ref_eval_plain": (C.c_int, [vp, C.c_int, vp, vp]),
             "ref_secret_key_words": (C.c_int, [vp, u64p]),
             "ref_decrypt_plain": (vp, [vp, vp]),
+            "ref_parms_id": (C.c_int, [vp, C.c_int, u64p]),
             "ref_keygen": (C.c_int, [vp]),
             "ref_relin_keys": (vp, [vp]),
             "ref_galois_keys_elts": (vp, [vp, C.POINTER(C.c_uint32), C.c_int]),
@@ -296,6 +297,13 @@ class RefContext:
         if lib().ref_eval_plain(self.h, op, a.h, pt.h) != 0:
             raise RefError(_err())
         return a
+
+    def parms_id(self, level):
+        """The reference's ParmsID of a level (-1: key level) as 32 bytes."""
+        out = np.zeros(4, dtype=np.uint64)
+        if lib().ref_parms_id(self.h, level, _p(out)) != 0:
+            raise RefError(_err())
+        return out.tobytes()
 
     def secret_key_words(self):
         """[key_limbs][N] NTT-form words of the secret key (after keygen())."""

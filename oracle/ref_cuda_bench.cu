@@ -20,6 +20,7 @@
 #include <cstring>
 #include <fstream>
 #include <random>
+#include <string>
 #include <vector>
 
 using namespace troyn;
@@ -109,6 +110,49 @@ static int dump(const char *in_path, const char *out_path) {
     return 0;
 }
 
+// Wire-format parity: the reference saves a ciphertext and its relinearisation keys (<dir>/ct.bin, <dir>/rlk.bin), and
+// loads <dir>/ours_ct.bin + <dir>/ours_rlk.bin (written by troy_b200/serialize.py), squares and relinearises with them and
+// writes the result words to <dir>/ours_result.bin.
+static int serialize(const char *in_path, const char *dir) {
+    std::ifstream in(in_path, std::ios::binary);
+    uint64_t hdr[4];
+    in.read(reinterpret_cast<char *>(hdr), sizeof(hdr));
+    const int scheme = (int)hdr[0];
+    const size_t n = hdr[1], nmod = hdr[2];
+    std::vector<uint64_t> moduli(nmod);
+    in.read(reinterpret_cast<char *>(moduli.data()), nmod * 8);
+    const size_t L = nmod - 1, ct_words = 2 * L * n;
+    std::vector<uint64_t> a(ct_words);
+    in.read(reinterpret_cast<char *>(a.data()), ct_words * 8);
+    KernelProvider::initialize();
+    HostContext hc(make_parms(scheme, n, moduli, hdr[3]), true, troy::SecurityLevel::none);
+    SEALContext context(hc);
+    KeyGenerator keygen(context);
+    PublicKey pk;
+    keygen.createPublicKey(pk);
+    RelinKeys rlk;
+    keygen.createRelinKeys(rlk);
+    const bool ckks = scheme == 2;
+    const double sc = ckks ? 1048576.0 : 1.0;
+    Ciphertext ca = upload(hc, a.data(), 2, ckks, sc);
+    const std::string d(dir);
+    { std::ofstream f(d + "/ct.bin", std::ios::binary); ca.save(f); }
+    { std::ofstream f(d + "/rlk.bin", std::ios::binary); rlk.save(f); }
+    Ciphertext c2;
+    RelinKeys r2;
+    { std::ifstream f(d + "/ours_ct.bin", std::ios::binary); c2.load(f); }
+    { std::ifstream f(d + "/ours_rlk.bin", std::ios::binary); r2.load(f); }
+    Evaluator ev(context);
+    ev.squareInplace(c2);
+    ev.relinearizeInplace(c2, r2);
+    std::vector<uint64_t> out;
+    append(out, c2);
+    std::ofstream o(d + "/ours_result.bin", std::ios::binary);
+    o.write(reinterpret_cast<const char *>(out.data()), out.size() * 8);
+    std::printf("serialize ok\n");
+    return 0;
+}
+
 template <class F> static double timed(F f, int iters) {
     f();
     cudaDeviceSynchronize();
@@ -181,6 +225,7 @@ static int bench(int batch, int iters) {
 int main(int argc, char **argv) {
     try {
         if (argc >= 4 && !std::strcmp(argv[1], "dump")) return dump(argv[2], argv[3]);
+        if (argc >= 4 && !std::strcmp(argv[1], "serialize")) return serialize(argv[2], argv[3]);
         if (argc >= 4 && !std::strcmp(argv[1], "bench")) return bench(std::atoi(argv[2]), std::atoi(argv[3]));
         std::fprintf(stderr, "usage: troyn_ref_bench bench <batch> <iters> | dump <in> <out>\n");
         return 2;

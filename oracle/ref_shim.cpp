@@ -464,6 +464,16 @@ int ref_eval_plain(void *h, int op, void *cta, void *pth) {
     REF_CATCH(-1)
 }
 
+// ParmsID (4 words) of a level of the chain (-1: key level)
+int ref_parms_id(void *h, int level, uint64_t *out) {
+    REF_TRY
+    auto c = static_cast<RefCtx *>(h);
+    const ParmsID &id = level < 0 ? c->context->keyParmsID() : c->chain.at(level);
+    for (int i = 0; i < 4; i++) out[i] = id[i];
+    return 0;
+    REF_CATCH(-1)
+}
+
 // The secret key as KeyGenerator stores it: [key_limbs][N] words, NTT form at the key level.
 int ref_secret_key_words(void *h, uint64_t *out) {
     REF_TRY

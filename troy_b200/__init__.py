@@ -12,3 +12,4 @@ from .host import (  # noqa: F401
 )
 from .lib import TroyError, library  # noqa: F401
 from .linear import Cipher2d, MatmulHelper, Plain2d  # noqa: F401
+from . import serialize  # noqa: F401
