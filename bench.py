@@ -448,7 +448,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=128, help="ciphertext pairs per GPU per step")
+    ap.add_argument("--batch", type=int, default=256, help="ciphertext pairs per GPU per step")
     ap.add_argument("--ref-reps", type=int, default=4, help="reference arm: ops per thread per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=16, help="end-to-end arm: ciphertext pairs per chunk")

@@ -27,7 +27,10 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstring>
+#include <istream>
 #include <memory>
+#include <ostream>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -168,6 +171,31 @@ public:
     PlaintextCuda &operator=(const std::string &hex_poly) { Plaintext::operator=(hex_poly); return *this; }
     PlaintextCuda &operator=(std::uint64_t c) { Plaintext::operator=(c); return *this; }
     const Plaintext &cpu() const { return *this; }
+    // PlaintextCuda::save / load  src/plaintext_cuda.cu:7-27: parms_id, coeff_count, scale, data_size, data
+    void save(std::ostream &stream) const {
+        const std::size_t count = coeffCount();
+        stream.write(reinterpret_cast<const char *>(&parmsID()), sizeof(ParmsID));
+        stream.write(reinterpret_cast<const char *>(&count), sizeof(count));
+        stream.write(reinterpret_cast<const char *>(&scale()), sizeof(double));
+        stream.write(reinterpret_cast<const char *>(&count), sizeof(count));
+        stream.write(reinterpret_cast<const char *>(data()), count * sizeof(std::uint64_t));
+    }
+    void load(std::istream &stream) {
+        ParmsID id;
+        std::size_t count = 0, data_size = 0;
+        double sc = 1.0;
+        stream.read(reinterpret_cast<char *>(&id), sizeof(ParmsID));
+        stream.read(reinterpret_cast<char *>(&count), sizeof(count));
+        stream.read(reinterpret_cast<char *>(&sc), sizeof(double));
+        stream.read(reinterpret_cast<char *>(&data_size), sizeof(data_size));
+        std::vector<std::uint64_t> w(data_size);
+        stream.read(reinterpret_cast<char *>(w.data()), data_size * sizeof(std::uint64_t));
+        parmsID() = parmsIDZero;
+        resize(count);
+        std::memcpy(data(), w.data(), std::min(count, data_size) * sizeof(std::uint64_t));
+        parmsID() = id;
+        scale() = sc;
+    }
 };
 class PublicKeyCuda : public PublicKey {
 public:
@@ -182,12 +210,76 @@ public:
 // Encoders are host work in this build: the host classes, constructed from the device context.
 class CKKSEncoderCuda : public CKKSEncoder {
 public:
-    CKKSEncoderCuda(const SEALContextCuda &context) : CKKSEncoder(context.host()) {}
+    CKKSEncoderCuda(const SEALContextCuda &context) : CKKSEncoder(context.host()), host_context_(context.host()) {}
+
+    // encodePolynomial / decodePolynomial exist only in the reference's CUDA encoder (src/ckks_cuda.cu:455-571, 983-1055):
+    // coefficient i of the plaintext polynomial is round(values[i] * scale). Host work here, like the rest of the encoder.
+    void encodePolynomial(const std::vector<double> &values, ParmsID parms_id, double scale, PlaintextCuda &destination) {
+        auto cd = host_context_.getContextData(parms_id);
+        if (!cd) throw std::invalid_argument("parms_id is not valid for encryption parameters");
+        const auto &q = cd->parms().coeffModulus();
+        const std::size_t n = cd->parms().polyModulusDegree(), L = q.size();
+        if (values.size() > n) throw std::invalid_argument("values_size is too large");
+        if (scale <= 0 || (int)std::log2(scale) + 1 >= cd->totalCoeffModulusBitCount()) throw std::invalid_argument("scale out of bounds");
+        double max_coeff = 0;
+        for (double v : values) max_coeff = std::max(max_coeff, std::fabs(v * scale));
+        const int bits = (int)std::ceil(std::log2(std::max(max_coeff, 1.0))) + 1;
+        if (bits >= cd->totalCoeffModulusBitCount()) throw std::invalid_argument("encoded values are too large");
+        if (bits > 64) throw std::logic_error("encodePolynomial: coefficients above 64 bits are outside the ported path");
+        destination.parmsID() = parmsIDZero;
+        destination.resize(n * L);
+        for (std::size_t i = 0; i < n; i++) {
+            const double c = i < values.size() ? std::round(values[i] * scale) : 0.0;
+            const bool neg = c < 0;
+            const std::uint64_t u = (std::uint64_t)std::fabs(c);
+            for (std::size_t j = 0; j < L; j++) {
+                const std::uint64_t r = util::barrettReduce64(u, q[j]);
+                destination.data()[j * n + i] = neg ? util::negateUintMod(r, q[j]) : r;
+            }
+        }
+        util::nttNegacyclicHarvey(util::HostPointer<std::uint64_t>(destination.data()), L, cd->smallNTTTables());
+        destination.parmsID() = parms_id;
+        destination.scale() = scale;
+    }
+    void encodePolynomial(const std::vector<double> &values, double scale, PlaintextCuda &destination) {
+        encodePolynomial(values, host_context_.firstParmsID(), scale, destination);
+    }
+    void decodePolynomial(const PlaintextCuda &plain, std::vector<double> &destination) {
+        if (!plain.isNttForm()) throw std::invalid_argument("plain is not in NTT form");
+        auto cd = host_context_.getContextData(plain.parmsID());
+        if (!cd) throw std::invalid_argument("plain is not valid for encryption parameters");
+        const std::size_t n = cd->parms().polyModulusDegree(), L = cd->parms().coeffModulus().size();
+        if (plain.scale() <= 0 || (int)std::log2(plain.scale()) >= cd->totalCoeffModulusBitCount()) throw std::invalid_argument("scale out of bounds");
+        std::vector<std::uint64_t> w(plain.data(), plain.data() + n * L);
+        util::inverseNttNegacyclicHarvey(util::HostPointer<std::uint64_t>(w.data()), L, cd->smallNTTTables());
+        cd->rnsTool()->baseq()->composeArray(w.data(), n);
+        const std::uint64_t *Q = cd->totalCoeffModulus(), *half = cd->upperHalfThreshold();
+        const double inv_scale = 1.0 / plain.scale(), two64 = std::pow(2.0, 64);
+        destination.assign(n, 0.0);
+        for (std::size_t i = 0; i < n; i++) { // gDecodeInternal, src/ckks_cuda.cu:793-831
+            const std::uint64_t *x = w.data() + i * L;
+            double r = 0, f = inv_scale;
+            if (util::isGreaterThanOrEqualUint(x, half, L)) {
+                for (std::size_t j = 0; j < L; j++, f *= two64) {
+                    if (x[j] > Q[j]) r += (double)(x[j] - Q[j]) * f;
+                    else r -= (double)(Q[j] - x[j]) * f;
+                }
+            } else {
+                for (std::size_t j = 0; j < L; j++, f *= two64) r += (double)x[j] * f;
+            }
+            destination[i] = r;
+        }
+    }
+
+private:
+    SEALContext host_context_;
 };
 class BatchEncoderCuda : public BatchEncoder {
 public:
     BatchEncoderCuda(const SEALContextCuda &context) : BatchEncoder(context.host()) {}
 };
+
+class EvaluatorCuda;
 
 class CiphertextCuda {
 public:
@@ -252,12 +344,65 @@ public:
     void resize(std::size_t size) { resizeInternal(size, n_, limbs_); }
     void release() { *this = CiphertextCuda(); }
 
+    // Wire format of the reference (src/ciphertext_cuda.cu:16-194): parms_id, is_ntt_form, size, N, limbs, scale,
+    // correction_factor, seed, terms, data_size, data. Seeded ciphertexts (the transport form of fresh symmetric
+    // encryptions, expanded with the reference's cuRAND sampler) are never produced here and are rejected on load.
+    void save(std::ostream &stream) const {
+        std::vector<std::uint64_t> w(size_ * n_ * limbs_);
+        data_.download(w.data(), w.size());
+        saveHeader(stream, false);
+        const std::size_t count = w.size();
+        stream.write(reinterpret_cast<const char *>(&count), sizeof(count));
+        stream.write(reinterpret_cast<const char *>(w.data()), count * 8);
+    }
+    void load(std::istream &stream) {
+        if (loadHeader(stream)) throw std::invalid_argument("Trying to load a termed ciphertext, but indices is not specified");
+        std::size_t count = 0;
+        stream.read(reinterpret_cast<char *>(&count), sizeof(count));
+        std::vector<std::uint64_t> w(count);
+        stream.read(reinterpret_cast<char *>(w.data()), count * 8);
+        if (count < size_ * n_ * limbs_) throw std::invalid_argument("ciphertext data is too short");
+        data_ = b200::DeviceWords(size_ * n_ * limbs_);
+        data_.upload(w.data(), size_ * n_ * limbs_);
+    }
+    void load(std::istream &stream, const SEALContextCuda &) { load(stream); }
+    // saveTerms / loadTerms (:45-77, :101-140): only the listed coefficients of poly 0 travel (coefficient form), poly 1.. whole
+    inline void saveTerms(std::ostream &stream, EvaluatorCuda &evaluator, const std::vector<std::size_t> &term_ids) const;
+    inline void loadTerms(std::istream &stream, EvaluatorCuda &evaluator, const std::vector<std::size_t> &term_ids);
+
     // used by the evaluator when an operation changes the limb count
     void adopt(b200::DeviceWords &&data, std::size_t size, std::size_t n, std::size_t limbs) {
         data_ = std::move(data); size_ = size; n_ = n; limbs_ = limbs;
     }
 
 private:
+    void saveHeader(std::ostream &stream, bool terms) const {
+        const std::uint64_t seed = 0;
+        stream.write(reinterpret_cast<const char *>(&parms_id_), sizeof(ParmsID));
+        stream.write(reinterpret_cast<const char *>(&is_ntt_), sizeof(bool));
+        stream.write(reinterpret_cast<const char *>(&size_), sizeof(std::size_t));
+        stream.write(reinterpret_cast<const char *>(&n_), sizeof(std::size_t));
+        stream.write(reinterpret_cast<const char *>(&limbs_), sizeof(std::size_t));
+        stream.write(reinterpret_cast<const char *>(&scale_), sizeof(double));
+        stream.write(reinterpret_cast<const char *>(&correction_), sizeof(std::uint64_t));
+        stream.write(reinterpret_cast<const char *>(&seed), sizeof(std::uint64_t));
+        stream.write(reinterpret_cast<const char *>(&terms), sizeof(bool));
+    }
+    bool loadHeader(std::istream &stream) { // returns the `terms` flag
+        std::uint64_t seed = 0;
+        bool terms = false;
+        stream.read(reinterpret_cast<char *>(&parms_id_), sizeof(ParmsID));
+        stream.read(reinterpret_cast<char *>(&is_ntt_), sizeof(bool));
+        stream.read(reinterpret_cast<char *>(&size_), sizeof(std::size_t));
+        stream.read(reinterpret_cast<char *>(&n_), sizeof(std::size_t));
+        stream.read(reinterpret_cast<char *>(&limbs_), sizeof(std::size_t));
+        stream.read(reinterpret_cast<char *>(&scale_), sizeof(double));
+        stream.read(reinterpret_cast<char *>(&correction_), sizeof(std::uint64_t));
+        stream.read(reinterpret_cast<char *>(&seed), sizeof(std::uint64_t));
+        stream.read(reinterpret_cast<char *>(&terms), sizeof(bool));
+        if (seed != 0) throw std::invalid_argument("seed is not zero.");
+        return terms;
+    }
     void resizeInternal(std::size_t size, std::size_t n, std::size_t limbs) {
         if ((size < 2 && size != 0) || size > 6) throw std::invalid_argument("invalid size");
         if (n == n_ && limbs == limbs_ && size * n * limbs <= data_.size()) { size_ = size; return; }
@@ -352,6 +497,10 @@ public:
     EncryptorCuda(const SEALContextCuda &context, const PublicKey &pk, const SecretKey &sk) : enc_(context.host(), pk, sk) {}
     void encrypt(const Plaintext &plain, CiphertextCuda &dst) const { Ciphertext c; enc_.encrypt(plain, c); dst = CiphertextCuda(c); }
     void encryptSymmetric(const Plaintext &plain, CiphertextCuda &dst) const { Ciphertext c; enc_.encryptSymmetric(plain, c); dst = CiphertextCuda(c); }
+    CiphertextCuda encrypt(const Plaintext &plain) const { CiphertextCuda d; encrypt(plain, d); return d; }
+    CiphertextCuda encryptSymmetric(const Plaintext &plain) const { CiphertextCuda d; encryptSymmetric(plain, d); return d; }
+    void setPublicKey(const PublicKey &pk) { enc_.setPublicKey(pk); }
+    void setSecretKey(const SecretKey &sk) { enc_.setSecretKey(sk); }
     void encryptZero(CiphertextCuda &dst) const { Ciphertext c; enc_.encryptZero(c); dst = CiphertextCuda(c); }
     void encryptZero(ParmsID id, CiphertextCuda &dst) const { Ciphertext c; enc_.encryptZero(id, c); dst = CiphertextCuda(c); }
 
@@ -751,6 +900,37 @@ private:
 
     SEALContextCuda context_;
 };
+
+inline void CiphertextCuda::saveTerms(std::ostream &stream, EvaluatorCuda &evaluator, const std::vector<std::size_t> &term_ids) const {
+    CiphertextCuda copy = *this;
+    if (is_ntt_) evaluator.transformFromNttInplace(copy);
+    std::vector<std::uint64_t> w(size_ * n_ * limbs_);
+    copy.data_.download(w.data(), w.size());
+    // the header records the form of the ORIGINAL ciphertext (src/ciphertext_cuda.cu:46-47)
+    saveHeader(stream, true);
+    for (std::size_t id : term_ids)
+        for (std::size_t j = 0; j < limbs_; j++) stream.write(reinterpret_cast<const char *>(&w[j * n_ + id]), 8);
+    const std::size_t offset = n_ * limbs_, count = w.size() - offset;
+    stream.write(reinterpret_cast<const char *>(&count), sizeof(count));
+    stream.write(reinterpret_cast<const char *>(w.data() + offset), count * 8);
+}
+inline void CiphertextCuda::loadTerms(std::istream &stream, EvaluatorCuda &evaluator, const std::vector<std::size_t> &term_ids) {
+    if (!loadHeader(stream)) throw std::invalid_argument("Trying to load a normal ciphertext, but term indices is specified");
+    std::vector<std::uint64_t> w(size_ * n_ * limbs_, 0);
+    for (std::size_t id : term_ids)
+        for (std::size_t j = 0; j < limbs_; j++) stream.read(reinterpret_cast<char *>(&w[j * n_ + id]), 8);
+    std::size_t count = 0;
+    stream.read(reinterpret_cast<char *>(&count), sizeof(count));
+    const std::size_t offset = n_ * limbs_;
+    if (offset + count > w.size()) throw std::invalid_argument("ciphertext data is too long");
+    stream.read(reinterpret_cast<char *>(w.data() + offset), count * 8);
+    data_ = b200::DeviceWords(w.size());
+    data_.upload(w.data(), w.size());
+    if (is_ntt_) {
+        is_ntt_ = false;
+        evaluator.transformToNttInplace(*this);
+    }
+}
 
 } // namespace troy
 

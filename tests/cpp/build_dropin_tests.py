@@ -69,10 +69,15 @@ def main():
         with open(gen, "w") as f:
             f.write('#include "troy_cuda.cuh"\n#include <cstddef>\n#include <cstdint>\n#include <ctime>\n#include <string>\n'
                     '#include "gtest/gtest.h"\n' + aliases + "\nnamespace troytest\n{\n" + bodies + "}\n")
-        inc = ["-I" + os.path.join(ROOT, "include", "troyn"), "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(REF, "src"),
+        # the reference's application header for the HE matmul, minus the line that includes the reference's own CUDA API
+        app = open(os.path.join(REF, "app", "LinearHelperCKKS.cuh")).read()
+        with open(os.path.join(tmp, "LinearHelperCKKS.cuh"), "w") as f:
+            f.write("\n".join(l for l in app.splitlines() if "troy_cuda.cuh" not in l) + "\n")
+        inc = ["-I" + tmp, "-I" + os.path.join(ROOT, "include", "troyn"), "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(REF, "src"),
                "-I" + os.path.join(gt, "include"), "-I" + gt]
         objs = []
         jobs = [(gen, "ref_tests.o"), (os.path.join(ROOT, "tests", "cpp", "dropin_parity.cpp"), "parity.o"),
+                (os.path.join(ROOT, "tests", "cpp", "dropin_linear.cpp"), "linear.o"),
                 (os.path.join(gt, "src", "gtest-all.cc"), "gtest-all.o"), (os.path.join(gt, "src", "gtest_main.cc"), "gtest_main.o")]
         procs = []
         for s, o in jobs:
@@ -86,7 +91,7 @@ def main():
         print("+", " ".join(cmd), flush=True)
         if subprocess.call(cmd):
             return 1
-    print(f"built {OUT}: {len(found)} reference CUDA tests + DropInParity")
+    print(f"built {OUT}: {len(found)} reference CUDA tests + DropInParity + DropInLinear")
     return 0
 
 

@@ -31,3 +31,10 @@ def test_word_for_word_parity_through_the_cpp_layer():
 def test_reference_cuda_tests_pass_against_the_drop_in():
     out = _run("EvaluatorCudaTest.*")
     assert "[  FAILED  ]" not in out
+
+
+def test_reference_app_header_matmul_runs_on_the_drop_in():
+    """app/LinearHelperCKKS.cuh (MatmulHelper) compiled unchanged against the drop-in header: encode, encrypt, matmul,
+    serialise by terms, decrypt on the device; the decoded product equals x @ W."""
+    out = _run("DropInLinear.*")
+    assert "2 tests" in out

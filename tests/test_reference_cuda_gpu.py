@@ -16,7 +16,9 @@ TOOL = os.path.join(ROOT, "oracle", "_ref", "troyn_ref_bench")
 
 
 @pytest.mark.parametrize("scheme,n,bits", [(2, 16384, [60, 40, 40, 40, 40, 40, 40, 40, 60]), (1, 8192, [60, 40, 40, 60]),
-                                           (3, 8192, [60, 40, 40, 60]), (2, 4096, [60, 40, 40, 60])])
+                                           (3, 8192, [60, 40, 40, 60]), (2, 4096, [60, 40, 40, 60]),
+                                           (1, 32768, [60, 50, 50, 50, 60]), (3, 32768, [60, 50, 50, 50, 60]),
+                                           (2, 65536, [60, 50, 50, 50, 60]), (1, 128, [40, 30, 30, 40])])
 def test_same_words_as_the_reference_cuda_path(ref, cuda_lib, tmp_path, scheme, n, bits):
     if not os.path.exists(TOOL):
         pytest.skip("oracle/_ref/troyn_ref_bench not built (make -C oracle refcuda where /root/reference exists)")

@@ -3,22 +3,25 @@ per launch and metric) into a per-kernel table (launches, average time, average 
 time of this library's kernels) and profiles/traffic.json (profile name of the kernel -> DRAM bytes per launch at the
 bench batch), which bench.py reports as roofline.traffic.
 
-  python tools/launch_traffic.py gpurun_out/<tag>/launches.csv profiles/r1_s6_launches_summary.txt profiles/traffic.json
+  python tools/launch_traffic.py gpurun_out/<tag>/launches.csv profiles/r1_s6_launches_summary.txt profiles/traffic.json [batch]
 """
 import collections
 import csv
 import json
 import sys
 
-# (kernel functor, grid of the bench step's launch at batch 128) -> bench.py profile name
-BENCH_STEP = {
-    ("EltTensor", 32768): "ct_tensor_product", ("NttInvTile<13>", 2048): "ntt_inv", ("NttFwdTile<13>", 18432): "ntt_fwd_modup",
-    ("KsInnerProductStaged<8>", 3744): "ks_inner_product", ("NttInvTile<13>", 512): "ntt_inv_add_half",
-    ("NttFwdTile<13>", 4096): "ntt_fwd_moddown",
-}
+# (kernel functor, grid of the bench step's launch at batch B: CKKS N=16384 L=8) -> bench.py profile name. The key inner
+# product's grid depends on how many ciphertexts share a staged key slice: it is the slowest launch of its functor.
+def bench_step(batch):
+    return {
+        ("EltTensor", 256 * batch): "ct_tensor_product", ("NttInvTile<13>", 16 * batch): "ntt_inv",
+        ("NttFwdTile<13>", 144 * batch): "ntt_fwd_modup", ("NttInvTile<13>", 4 * batch): "ntt_inv_add_half",
+        ("NttFwdTile<13>", 32 * batch): "ntt_fwd_moddown",
+    }
 
 
-def main(src, out_txt, out_json):
+def main(src, out_txt, out_json, batch=256):
+    BENCH_STEP = bench_step(int(batch))
     rows = [r for r in csv.reader(open(src)) if len(r) > 10]
     ix = {h: i for i, h in enumerate(rows[0])}
     launches = collections.OrderedDict()
@@ -35,6 +38,9 @@ def main(src, out_txt, out_json):
         short = d["name"].split("troyb::")[-1].split(">(")[0].rstrip(">") if "<troyb::" in d["name"] else d["name"]
         short = d["name"][d["name"].index("<troyb::") + 8:].split(">(")[0]
         groups.setdefault((short, d["grid"]), []).append(d)
+    ip = [k for k in groups if k[0].startswith("KsInnerProductStaged")]
+    if ip:
+        BENCH_STEP[max(ip, key=lambda k: sum(x["gpu__time_duration.sum"] for x in groups[k]) / len(groups[k]))] = "ks_inner_product"
     step_total = sum(sum(x["gpu__time_duration.sum"] for x in v) / len(v) for k, v in groups.items() if k in BENCH_STEP)
     lines = [f"{'kernel':<28}{'grid':>8}{'launches':>9}{'avg_us':>10}{'dram_rd_MB':>12}{'dram_wr_MB':>12}  bench-step kernel (share of step)"]
     traffic = {}
@@ -49,10 +55,10 @@ def main(src, out_txt, out_json):
             traffic[name] = int(rd + wr)
         lines.append(f"{short:<28}{grid:>8}{len(v):>9}{t:>10.1f}{rd / 1e6:>12.1f}{wr / 1e6:>12.1f}  {tag}")
     open(out_txt, "w").write("\n".join(lines) + "\n")
-    traffic["_source"] = f"{src}: ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, bench batch 128 (python bench.py --steps 2 --warmup 1)"
+    traffic["_source"] = f"{src}: ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, bench batch {batch} (python bench.py --steps 2 --warmup 1)"
     json.dump(traffic, open(out_json, "w"), indent=1)
     print("\n".join(lines))
 
 
 if __name__ == "__main__":
-    main(*sys.argv[1:4])
+    main(*sys.argv[1:5])
