@@ -19,7 +19,9 @@ timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
   --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
 echo "launch list rc=$? lines=$(wc -l < $OUT/launches.csv)"
 # full capture of the mod-up NTT at the bench batch (profile_target launch order: standalone forward NTT, then mod-up)
-PROFILE_BATCH=128 timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:NttFwdTile -s 1 -c 1 \
+PROFILE_BATCH=256 timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:NttFwdTile -s 1 -c 1 \
   -o $OUT/modup -f python tests/microbench/profile_target.py > $OUT/ncu_full.log 2>&1
 echo "full capture rc=$?"
 ncu -i $OUT/modup.ncu-rep --page raw --csv > $OUT/modup_raw.csv 2>/dev/null
+# one tiny hot-path call checked against the oracle, as the driver runs it
+timeout 600 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $OUT/smoke.log
