@@ -38,6 +38,14 @@ def main(src, out_txt, out_json, batch=256):
         short = d["name"].split("troyb::")[-1].split(">(")[0].rstrip(">") if "<troyb::" in d["name"] else d["name"]
         short = d["name"][d["name"].index("<troyb::") + 8:].split(">(")[0]
         groups.setdefault((short, d["grid"]), []).append(d)
+    # launches of one functor with one grid can still differ in work (the inner product's grid is the same for 256
+    # ciphertexts sharing staged key slices and for the 16-ciphertext chunks of the end-to-end arm): keep the long ones
+    for k in list(groups):
+        longest = max(x["gpu__time_duration.sum"] for x in groups[k])
+        short = [x for x in groups[k] if x["gpu__time_duration.sum"] < 0.5 * longest]
+        if short and k[0].startswith("KsInnerProductStaged"):
+            groups[k] = [x for x in groups[k] if x["gpu__time_duration.sum"] >= 0.5 * longest]
+            groups[(k[0] + " (small batch)", k[1])] = short
     ip = [k for k in groups if k[0].startswith("KsInnerProductStaged")]
     if ip:
         BENCH_STEP[max(ip, key=lambda k: sum(x["gpu__time_duration.sum"] for x in groups[k]) / len(groups[k]))] = "ks_inner_product"
