@@ -360,12 +360,14 @@ template <int LOGT> struct NttFwdTile {
             prefetch_tiles<LOGT>(a, u, bid, rank, grid);
             // scatter stage: the layers that couple the tiles, results into the peers' shared memory
             if (nranks == 1 || u.passthrough) return;
+            cluster_arrive_started();
+            auto started = [] { cluster_wait_started(); };
             auto ld = [&](u32 i) -> u64 { return pro(u.src[i]); };
             u32 handle[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) handle[k] = peers.map((u32)k < nranks ? (u32)k : 0u);
             auto st_peer = [&](u32 k, u32 pi, u64 bits) { peers.st(handle[k], pi, bits); };
-            TB_WITH_POLICY(pol, TB_WITH_LOGC(u.rows_log, TB_PHASE(kThreads, t, (cluster_fwd_scatter<A, LOGC, LOGT, kThreads>(t, rank, ld, st_peer, md));)))
+            TB_WITH_POLICY(pol, TB_WITH_LOGC(u.rows_log, TB_PHASE(kThreads, t, (cluster_fwd_scatter<A, LOGC, LOGT, kThreads>(t, rank, ld, st_peer, started, md));)))
         } else {
             const u64 off = (u64)rank << LOGT;
             if (u.passthrough) return; // digit already in NTT form under this modulus: the inner product reads it in place

@@ -61,6 +61,8 @@ struct Peers {
 };
 
 inline void l2_prefetch(const void *, u32) {}
+inline void cluster_arrive_started() {}
+inline void cluster_wait_started() {}
 
 template <class F, int S> inline void emul_stages(const F &f, u32 b0, u32 grid, u32 nranks, std::vector<u64 *> &ptr, const Peers &peers) {
     if constexpr (S < F::kStages) {
@@ -153,6 +155,12 @@ struct Peers {
 TB_D void l2_prefetch(const void *p, u32 bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes));
 }
+
+// Split cluster barrier without memory ordering: "every CTA of the cluster has started". A CTA's shared memory exists only
+// once it runs, so a peer may store into it (distributed shared memory) only after this handshake; the arrive is issued
+// first thing and the wait just before the first remote store, with the CTA's own global loads in between.
+TB_D void cluster_arrive_started() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+TB_D void cluster_wait_started() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
 
 TB_D void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");

@@ -652,8 +652,9 @@ TB_D void tile_ntt_inv(u64 *sm, Gld gld, St st, const ModDev *md, u32 R) {
 // independent 2^LOGT-point transform with root base C + rank.
 //   ld(i)            : coefficient i of the limb as u64 (prologue fused there)
 //   st_peer(k, i, b) : store raw element bits b at padded index i of tile k
-template <class A, int LOGC, int LOGT, int NT, class Ld, class StPeer>
-TB_D void cluster_fwd_scatter(u32 vt, u32 rank, Ld ld, StPeer st_peer, const ModDev *md) {
+//   peers_started()  : called once by every thread before the first remote store (the peers' shared memory must exist)
+template <class A, int LOGC, int LOGT, int NT, class Ld, class StPeer, class Started>
+TB_D void cluster_fwd_scatter(u32 vt, u32 rank, Ld ld, StPeer st_peer, Started peers_started, const ModDev *md) {
     constexpr int C = 1 << LOGC, T = 1 << LOGT, G = T / C / NT;
     static_assert(G >= 1, "bad cluster stage");
     // B iterations (16 coefficients) are loaded before any of them is used: one memory latency per batch, not per
@@ -674,6 +675,7 @@ TB_D void cluster_fwd_scatter(u32 vt, u32 rank, Ld ld, StPeer st_peer, const Mod
 #pragma unroll
             for (int k = 0; k < C; k++) raw[b][k] = ld(v + (u32)k * T);
         }
+        if (g0 == 0) peers_started();
 #pragma unroll
         for (int b = 0; b < B; b++) {
             const u32 v = rank * (T / C) + vt + (g0 + b) * NT;
