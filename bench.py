@@ -390,7 +390,7 @@ def run_ours(args):
                 w = a_in[0].cpu().numpy().astype(np.uint64)
                 ra, rb = rc.ciphertext(w, 0, True, SCALE), rc.ciphertext(w, 0, True, SCALE)
                 rc.time_ops(0, ra, rb, r_rlk, None, 0, 1, cores)
-                reps = 6
+                reps = 32  # about 1 s of wall time on 16 threads: a bounded sample of ~15 CPU-seconds
                 t0 = time.time()
                 tt = rc.time_ops(0, ra, rb, r_rlk, None, 0, reps, cores)
                 cpu = {"value": reps * cores / tt, "unit": UNIT, "cores": cores, "kind": "reference",
