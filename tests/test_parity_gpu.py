@@ -48,6 +48,44 @@ def test_plain_ops(ref, cuda_lib, scheme, n, bits):
         run_plain_flow(ref, cuda_lib, scheme, n, bits, np.random.default_rng(4000 + n + scheme), batch=1, level=1)
 
 
+@pytest.mark.parametrize("n", [4096, 8192, 16384, 32768, 65536])
+def test_ntt_sweep(ref, cuda_lib, n):
+    """BASELINE config 2: the standalone batched NTT / INTT sweep, N = 4096 .. 65536 x 1 .. 32 limbs of 60-bit primes.
+    Size-independent properties on a batch of 3 polys (round trip = identity, linearity) and direct parity of the first and
+    the last limb with the reference's transform."""
+    import ctypes as C
+    tb = cuda_lib
+    from troy_b200.host import DeviceArray, _L, _vp
+    rng = np.random.default_rng(n)
+    for L in (1, 8, 32):
+        q = ref.coeff_modulus_create(n, [60] * (L + 1))
+        p = tb.EncryptionParameters(tb.SchemeType.ckks)
+        p.set_poly_modulus_degree(n)
+        p.set_coeff_modulus(q)
+        ctx = tb.SEALContextCuda(p, expand_mod_chain=False)
+        assert ctx.level_limbs(0) == L
+        a = np.stack([np.stack([rng.integers(0, m, n, dtype=np.uint64) for m in q[:L]]) for _ in range(3)])
+        b = np.stack([np.stack([rng.integers(0, m, n, dtype=np.uint64) for m in q[:L]]) for _ in range(3)])
+        qv = np.array(q[:L], dtype=np.uint64)[None, :, None]
+        s = a + b
+        s = np.where(s >= qv, s - qv, s)
+
+        def transform(x, inverse=False):
+            d = DeviceArray(x.size)
+            d.upload(x.reshape(-1))
+            _L().call("troyb_ntt_inverse" if inverse else "troyb_ntt_forward", _vp(ctx.h), 0, _vp(d.ptr), 3, _vp(None))
+            return d.download().reshape(x.shape)
+
+        fa, fb, fs = transform(a), transform(b), transform(s)
+        assert np.array_equal(transform(fa, inverse=True), a), f"round trip N={n} L={L}"
+        lin = fa + fb
+        lin = np.where(lin >= qv, lin - qv, lin)
+        assert np.array_equal(fs, lin), f"linearity N={n} L={L}"
+        for limb in {0, L - 1}:
+            assert np.array_equal(fa[1, limb], ref.ntt_prime(n, q[limb], a[1, limb])), f"forward N={n} L={L} limb {limb}"
+            assert np.array_equal(a[2, limb], ref.ntt_prime(n, q[limb], fa[2, limb], inverse=True)), f"inverse N={n} limb {limb}"
+
+
 def test_config5_full_size_key_switch(ref, cuda_lib):
     """BASELINE config 5 at its full size: CKKS N=65536, 40 data primes + special prime. One relinearisation (40 digits,
     1640 mod-up transforms, a 1.7 GB key) word for word against the reference CPU library, on a synthetic key
