@@ -289,7 +289,10 @@ void switch_key_partial(Context *ctx, int level, const u64 *target, u64 target_s
     }
 }
 
-void switch_key_finish(Context *ctx, int level, u64 *ct, u64 ct_stride, u64 *prod, bool reduce_first, u32 batch, cudaStream_t s) {
+// ct_src (optional): the tail writes ct = ct_src + result for the first ct_src_polys polys and ct = result for the rest,
+// instead of ct += result (applyGalois: permuted c0 in scratch, c1 from zero; saves a copy and a memset pass over ct).
+void switch_key_finish(Context *ctx, int level, u64 *ct, u64 ct_stride, u64 *prod, bool reduce_first, u32 batch, cudaStream_t s,
+                       const u64 *ct_src = nullptr, u64 ct_src_stride = 0, u32 ct_src_polys = 0) {
     if (!ctx->has_special) throw std::logic_error("keyswitching is not supported by the context");
     const u32 L = (u32)ctx->levels[level].L;
     const u64 N = ctx->N;
@@ -341,6 +344,9 @@ void switch_key_finish(Context *ctx, int level, u64 *ct, u64 ct_stride, u64 *pro
         a.ct = ct;
         a.ct_batch_stride = ct_stride;
         a.ct_poly_stride = (u64)L * N;
+        a.ct_src = ct_src;
+        a.ct_src_batch_stride = ct_src_stride;
+        a.ct_src_polys = ct_src_polys;
         a.drop = ctx->key_drop;
         a.scheme = ctx->scheme;
         set_order(ctx, a, L);
@@ -350,12 +356,12 @@ void switch_key_finish(Context *ctx, int level, u64 *ct, u64 ct_stride, u64 *pro
 }
 
 void switch_key_impl(Context *ctx, int level, u64 *ct, u64 ct_stride, const u64 *target, u64 target_stride, const u64 *key,
-                     u32 batch, cudaStream_t s) {
+                     u32 batch, cudaStream_t s, const u64 *ct_src = nullptr, u64 ct_src_stride = 0, u32 ct_src_polys = 0) {
     if (!ctx->has_special) throw std::logic_error("keyswitching is not supported by the context");
     const u32 L = (u32)ctx->levels[level].L;
     Scratch prod((size_t)batch * 2 * (L + 1) * ctx->N, s);
     switch_key_partial(ctx, level, target, target_stride, key, 0, L, prod.p, batch, s);
-    switch_key_finish(ctx, level, ct, ct_stride, prod.p, false, batch, s);
+    switch_key_finish(ctx, level, ct, ct_stride, prod.p, false, batch, s, ct_src, ct_src_stride, ct_src_polys);
 }
 
 void check_batch_stride(size_t stride, size_t min_words, const char *what) {
@@ -1125,10 +1131,9 @@ int troyb_apply_galois(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_
     k.in_batch_stride = ct_stride;
     k.out_batch_stride = 2ull * L * N;
     ck(launch_cta(k, grid_for(k.total, EltGalois::kThreads), 0, s));
-    // c0 <- permuted c0 ; c1 <- 0 ; then key-switch the permuted c1 into (c0, c1)   src/evaluator_cuda.cu:2104-2116
-    ck(cudaMemcpy2DAsync(d_ct, ct_stride * 8, tmp.p, 2ull * L * N * 8, (size_t)L * N * 8, batch, cudaMemcpyDeviceToDevice, s));
-    ck(cudaMemset2DAsync(d_ct + (u64)L * N, ct_stride * 8, 0, (size_t)L * N * 8, batch, s));
-    switch_key_impl(c, level, d_ct, ct_stride, tmp.p + (u64)L * N, 2ull * L * N, d_key, (u32)batch, s);
+    // c0 <- permuted c0 ; c1 <- 0 ; then key-switch the permuted c1 into (c0, c1)   src/evaluator_cuda.cu:2104-2116.
+    // The copy and the memset are folded into the key switch's tail: it writes ct = (permuted c0, 0) + result.
+    switch_key_impl(c, level, d_ct, ct_stride, tmp.p + (u64)L * N, 2ull * L * N, d_key, (u32)batch, s, tmp.p, 2ull * L * N, 1);
     API_END
 }
 

@@ -35,6 +35,10 @@ struct NttArgs {
     const u64 *aux0;    // MODUP: original NTT-form target (CKKS) or null; MODDOWN/COMBINE: accumulators (t_poly_prod)
     const u64 *aux1;    // MODDOWN/COMBINE: s' (rounded special limb, coefficient form)
     u64 *ct;            // MODDOWN/COMBINE: ciphertext updated in place (null for rescale -> write dst)
+    const u64 *ct_src;  // MODDOWN/COMBINE: when set, ct = ct_src + result for polys k < ct_src_polys and ct = result for the
+                        // others (applyGalois: the permuted c0 lives in scratch, c1 starts from zero), instead of ct += result
+    u64 ct_src_batch_stride;
+    u32 ct_src_polys;
     DropDev drop;       // constants for the prime being dropped
     u32 L;              // data limbs in play (MODUP: digits in this launch)
     u32 digit0;         // MODUP: index of the first digit of this launch
@@ -127,7 +131,8 @@ struct NttUnit {
     u64 *dst;
     const u64 *acc;   // accumulators row
     const u64 *sp;    // s' row
-    u64 *ct;          // ciphertext row (read-modify-write)
+    u64 *ct;          // ciphertext row (written)
+    const u64 *ct_in; // the row added to the result (ct itself, a row of NttArgs::ct_src, or null for zero)
     DropLimb dl;
     bool passthrough; // MODUP with i == j in CKKS: copy the NTT-form limb
     bool reduce_src;  // MODUP: the digit must be reduced mod q_i before the transform
@@ -190,6 +195,8 @@ template <int LOGT> TB_D NttUnit resolve_unit(const NttArgs &a, u32 bid) {
         u.sp = a.aux1 + (u64)bk * N;
         u.acc = a.aux0 + (u64)b * a.acc_batch_stride + (u64)k * a.acc_poly_stride + (u64)j * N;
         u.ct = a.ct ? a.ct + (u64)b * a.ct_batch_stride + (u64)k * a.ct_poly_stride + (u64)j * N : nullptr;
+        if (a.ct_src == nullptr) u.ct_in = u.ct;
+        else u.ct_in = k < a.ct_src_polys ? a.ct_src + (u64)b * a.ct_src_batch_stride + (u64)k * a.ct_poly_stride + (u64)j * N : nullptr;
         u.dst = a.dst ? a.dst + (u64)b * a.dst_batch_stride + (u64)k * a.dst_poly_stride + (u64)j * N : nullptr;
         u.dl = a.drop.limbs[j];
         u.src = (a.mode == FWD_MODDOWN) ? u.sp : u.acc;
@@ -210,7 +217,7 @@ template <int LOGT> TB_D void prefetch_tiles(const NttArgs &a, const NttUnit &u,
     if (a.mode == FWD_MODDOWN || a.mode == INV_COMBINE) {
         if (a.mode == INV_COMBINE) l2_prefetch(u.sp + off, bytes);
         else l2_prefetch(u.acc + off, bytes);
-        if (u.ct) l2_prefetch(u.ct + off, bytes);
+        if (u.ct_in) l2_prefetch(u.ct_in + off, bytes);
     }
     const u32 ahead = bid + a.pf_ahead;
     if (ahead < grid) {
@@ -251,7 +258,7 @@ struct FwdStore {
         Pre r{0, 0};
         if (mode == FWD_MODDOWN) {
             r.acc = u.acc[i];
-            if (u.ct) r.ct = u.ct[i];
+            if (u.ct_in) r.ct = u.ct_in[i];
         }
         return r;
     }
@@ -292,7 +299,7 @@ TB_D void inv_store_final(const NttArgs &a, const NttUnit &u, u64 p, u64 idx, u6
         }
         u64 d = v + (p << 1) - sub; // v < p, sub <= 2p  ->  d in (0,3p)
         u64 r = shoup(d, u.dl.inv_last, u.dl.inv_last_shoup, p);
-        if (u.ct) u.ct[idx] = addmod(u.ct[idx], r, p);
+        if (u.ct) u.ct[idx] = addmod(u.ct_in ? u.ct_in[idx] : 0, r, p);
         else u.dst[idx] = r;
     }
 }
@@ -380,6 +387,7 @@ template <int LOGT> struct NttFwdTile {
             // this tile's outputs are coefficients [off, off + T) of the limb's (bit-reversed) output
             if (u.dst) u.dst += off;
             if (u.ct) u.ct += off;
+            if (u.ct_in) u.ct_in += off;
             if (u.acc) u.acc += off;
             const FwdStore st{u, md->p, a.mode};
             TB_WITH_POLICY(pol, (tile_store_canon<A, LOGT>(sm, st, md));)
