@@ -142,6 +142,11 @@ int troyb_galois_elt_from_step(const troyb_context *ctx, int step, uint32_t *out
 int troyb_apply_galois(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_stride, uint32_t galois_elt,
                        const uint64_t *d_key, size_t batch, void *stream);
 
+/* EvaluatorCuda::applyGalois(encrypted, elt, keys, destination)  src/evaluator_cuda.cuh:275: the same, reading d_in and writing
+ * d_out (which may be d_in); the input is not modified otherwise. */
+int troyb_apply_galois_to(troyb_context *ctx, int level, const uint64_t *d_in, size_t in_stride, uint64_t *d_out, size_t out_stride,
+                          uint32_t galois_elt, const uint64_t *d_key, size_t batch, void *stream);
+
 /* EvaluatorCuda::modSwitchScaleToNext  src/evaluator_cuda.cu:749-825 (rescaleToNext :1380 for CKKS, modSwitchToNext for
  * BFV/BGV): drops the level's last prime with rounding. in: [size][L][N] at `level`, out: [size][L-1][N] at level+1. */
 int troyb_mod_switch_scale_to_next(troyb_context *ctx, int level, const uint64_t *d_in, size_t in_stride, uint64_t *d_out,

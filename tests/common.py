@@ -73,14 +73,26 @@ def run_evaluator_flow(ref, tb, scheme, n, bits, rng, batch=1):
             rc.eval(op, ras[i], kw.get("b", [None] * batch)[i], keys=kw.get("keys"), arg=kw.get("arg", 0))
             assert_same(a, ras[i], f"{name} [scheme {scheme}, N {n}, batch elt {i}]", i)
 
+    # out-of-place forms write straight into a destination and leave their inputs alone
+    dst = tb.CiphertextCuda(ctx, 0, 3, ntt, sc, batch=batch)
+    before = a.to_host().copy()
+    ev.multiply(a, b, dst)
+    assert np.array_equal(a.to_host(), before), "multiply(a, b, dst) modified its input"
     both("multiply", lambda: ev.multiply_inplace(a, b), ref.OP_MULTIPLY, b=rbs)
+    assert np.array_equal(dst.to_host(), a.to_host()) and dst.size == a.size and dst.scale == a.scale, "multiply(a, b, dst)"
     both("relinearize", lambda: ev.relinearize_inplace(a, d_rlk), ref.OP_RELIN, keys=rlk)
     if ntt:
         both("rescale", lambda: ev.rescale_to_next_inplace(a), ref.OP_RESCALE_NEXT)
+        dst2 = tb.CiphertextCuda(ctx, a.parms_id, 2, ntt, a.scale, batch=batch)
+        ev.rotate_vector(a, 1, d_gk, dst2)
         both("rotate_vector", lambda: ev.rotate_vector_inplace(a, 1, d_gk), ref.OP_ROTATE_VECTOR, keys=gk, arg=1)
+        assert np.array_equal(dst2.to_host(), a.to_host()), "rotate_vector(a, steps, keys, dst)"
         both("conjugate", lambda: ev.complex_conjugate_inplace(a, d_gk), ref.OP_CONJUGATE, keys=gk)
     else:
+        dst2 = tb.CiphertextCuda(ctx, a.parms_id, 2, ntt, a.scale, a.correction_factor, batch=batch)
+        ev.rotate_rows(a, 1, d_gk, dst2)
         both("rotate_rows", lambda: ev.rotate_rows_inplace(a, 1, d_gk), ref.OP_ROTATE_ROWS, keys=gk, arg=1)
+        assert np.array_equal(dst2.to_host(), a.to_host()), "rotate_rows(a, steps, keys, dst)"
         both("mod_switch", lambda: ev.mod_switch_to_next_inplace(a), ref.OP_MODSWITCH_NEXT)
         both("rotate_columns", lambda: ev.rotate_columns_inplace(a, d_gk), ref.OP_ROTATE_COLUMNS, keys=gk)
     both("add", lambda: ev.add_inplace(a, a.clone()), ref.OP_ADD, b=[r.clone() for r in ras])

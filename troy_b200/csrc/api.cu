@@ -1104,6 +1104,11 @@ int troyb_galois_elt_from_step(const troyb_context *ctx, int step, uint32_t *out
 
 int troyb_apply_galois(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_stride, uint32_t galois_elt,
                        const uint64_t *d_key, size_t batch, void *stream) {
+    return troyb_apply_galois_to(ctx, level, d_ct, ct_stride, d_ct, ct_stride, galois_elt, d_key, batch, stream);
+}
+
+int troyb_apply_galois_to(troyb_context *ctx, int level, const uint64_t *d_in, size_t in_stride, uint64_t *d_ct, size_t ct_stride,
+                          uint32_t galois_elt, const uint64_t *d_key, size_t batch, void *stream) {
     API_BEGIN
     need_init();
     Context *c = C(ctx);
@@ -1112,9 +1117,11 @@ int troyb_apply_galois(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_
     cudaStream_t s = S(stream);
     if (level < 0) throw std::invalid_argument("level");
     if (!(galois_elt & 1) || galois_elt >= 2 * N) throw std::invalid_argument("Galois element is not valid");
-    if (!d_ct || !d_key) throw std::invalid_argument("Galois key not present");
+    if (!d_ct || !d_in || !d_key) throw std::invalid_argument("Galois key not present");
     check_batch_stride(ct_stride, 2ull * L * N, "ct");
+    check_batch_stride(in_stride, 2ull * L * N, "in");
     check_aligned(d_ct, "ct");
+    check_aligned(d_in, "in");
     check_aligned(d_key, "key");
     Scratch tmp((size_t)batch * 2 * L * N, s);
     EltGalois k{};
@@ -1126,9 +1133,9 @@ int troyb_apply_galois(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_
     k.L = L;
     k.elt = galois_elt;
     k.total = (u64)batch * 2 * L * N;
-    k.in = d_ct;
+    k.in = d_in;
     k.out = tmp.p;
-    k.in_batch_stride = ct_stride;
+    k.in_batch_stride = in_stride;
     k.out_batch_stride = 2ull * L * N;
     ck(launch_cta(k, grid_for(k.total, EltGalois::kThreads), 0, s));
     // c0 <- permuted c0 ; c1 <- 0 ; then key-switch the permuted c1 into (c0, c1)   src/evaluator_cuda.cu:2104-2116.

@@ -598,8 +598,34 @@ class EvaluatorCuda:
             a.correction_factor = (a.correction_factor * b.correction_factor) % self.context.parms.plain_modulus
 
     def multiply(self, a, b, destination=None):
-        d = a.clone()
-        self.multiply_inplace(d, b)
+        """multiply(encrypted1, encrypted2, destination) (src/evaluator_cuda.cuh:85-97). With a ``destination`` of the same
+        batch and level and capacity for the product, the product is written there directly (the reference copies first)."""
+        out_size = a.size + b.size - 1
+        if destination is None or destination is a or destination is b or destination.batch != a.batch \
+                or destination.limbs != a.limbs or destination.capacity < out_size:
+            d = a.clone()
+            self.multiply_inplace(d, b)
+            if destination is not None:
+                self._assign(destination, d)
+                return destination
+            return d
+        self._same_parms(a, b)
+        scheme = self.context.scheme
+        if scheme == CKKS and not (a.is_ntt_form and b.is_ntt_form):
+            raise TroyInvalidArgument("encrypted1 or encrypted2 must be in NTT form")
+        if scheme != CKKS and (a.is_ntt_form or b.is_ntt_form):
+            raise TroyInvalidArgument("encrypted1 or encrypted2 cannot be in NTT form")
+        new_scale = a.scale * b.scale
+        if scheme == CKKS and not self._check_scale(new_scale, a.parms_id):
+            raise TroyInvalidArgument("scale out of bounds")
+        d = destination
+        _L().call("troyb_multiply", self._h(), a.parms_id, _vp(a.ptr()), a.size, a.stride, _vp(b.ptr()), b.size, b.stride,
+                  _vp(d.ptr()), d.stride, a.batch, self._s())
+        d.parms_id, d.size, d.is_ntt_form = a.parms_id, out_size, a.is_ntt_form
+        d.scale = new_scale if scheme == CKKS else a.scale
+        d.correction_factor = a.correction_factor
+        if scheme == BGV:
+            d.correction_factor = (a.correction_factor * b.correction_factor) % self.context.parms.plain_modulus
         return d
 
     def square_inplace(self, a):
@@ -651,6 +677,47 @@ class EvaluatorCuda:
         self._check_keyswitch(ct, galois_keys)
         _L().call("troyb_apply_galois", self._h(), ct.parms_id, _vp(ct.ptr()), ct.stride, galois_elt,
                   _vp(galois_keys.key(galois_elt).ptr), ct.batch, self._s())
+
+    def apply_galois(self, ct, galois_elt, galois_keys, destination):
+        """applyGalois(encrypted, elt, keys, destination) (src/evaluator_cuda.cuh:275): ``destination`` (same batch, level and
+        size-2 capacity) receives the result; ``ct`` is only read."""
+        if destination is ct:
+            return self.apply_galois_inplace(ct, galois_elt, galois_keys)
+        if galois_keys.parms_id != self.context.key_parms_id():
+            raise TroyInvalidArgument("galois_keys is not valid for encryption parameters")
+        if not (galois_elt & 1) or galois_elt >= 2 * self.context.n:
+            raise TroyInvalidArgument("Galois element is not valid")
+        if not galois_keys.has_key(galois_elt):
+            raise TroyInvalidArgument("Galois key not present")
+        if ct.size > 2:
+            raise TroyInvalidArgument("encrypted size must be 2")
+        if destination.batch != ct.batch or destination.limbs != ct.limbs or destination.capacity < 2:
+            raise TroyInvalidArgument("destination is not valid for encryption parameters")
+        self._check_keyswitch(ct, galois_keys)
+        d = destination
+        _L().call("troyb_apply_galois_to", self._h(), ct.parms_id, _vp(ct.ptr()), ct.stride, _vp(d.ptr()), d.stride, galois_elt,
+                  _vp(galois_keys.key(galois_elt).ptr), ct.batch, self._s())
+        d.parms_id, d.size, d.is_ntt_form, d.scale, d.correction_factor = ct.parms_id, 2, ct.is_ntt_form, ct.scale, ct.correction_factor
+        return d
+
+    def rotate_vector(self, ct, steps, galois_keys, destination):
+        """rotateVector(encrypted, steps, keys, destination): one key switch when the key for ``steps`` exists."""
+        if self.context.scheme != CKKS:
+            raise TroyLogicError("unsupported scheme")
+        return self._rotate_to(ct, steps, galois_keys, destination)
+
+    def rotate_rows(self, ct, steps, galois_keys, destination):
+        if self.context.scheme not in (BFV, BGV):
+            raise TroyLogicError("unsupported scheme")
+        return self._rotate_to(ct, steps, galois_keys, destination)
+
+    def _rotate_to(self, ct, steps, galois_keys, destination):
+        elt = self.context.galois_elt_from_step(steps) if steps != 0 else None
+        if elt is not None and galois_keys.has_key(elt):
+            return self.apply_galois(ct, elt, galois_keys, destination)
+        self._assign(destination, ct.clone())
+        self._rotate_internal(destination, steps, galois_keys)
+        return destination
 
     def _rotate_internal(self, ct, steps, galois_keys):
         if galois_keys.parms_id != self.context.key_parms_id():
@@ -864,3 +931,4 @@ class EvaluatorCuda:
     transformToNttInplace, transformFromNttInplace = transform_to_ntt_inplace, transform_from_ntt_inplace
     addPlainInplace, subPlainInplace, multiplyPlainInplace = add_plain_inplace, sub_plain_inplace, multiply_plain_inplace
     multiplyPlain = multiply_plain
+    applyGalois, rotateVector, rotateRows = apply_galois, rotate_vector, rotate_rows

@@ -75,6 +75,7 @@ _SIGNATURES = {
     "troyb_galois_permute": (C.c_int, [_vp, C.c_int, _vp, _vp, _sz, C.c_uint32, C.c_int, _vp]),
     "troyb_galois_elt_from_step": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_uint32)]),
     "troyb_apply_galois": (C.c_int, [_vp, C.c_int, _vp, _sz, C.c_uint32, _vp, _sz, _vp]),
+    "troyb_apply_galois_to": (C.c_int, [_vp, C.c_int, _vp, _sz, _vp, _sz, C.c_uint32, _vp, _sz, _vp]),
     "troyb_mod_switch_scale_to_next": (C.c_int, [_vp, C.c_int, _vp, _sz, _vp, _sz, _sz, _sz, _vp]),
     "troyb_multiply_plain_ntt": (C.c_int, [_vp, C.c_int, _vp, _sz, _sz, _vp, _sz, _vp, _sz, _sz, C.c_int, _vp]),
     "troyb_matmul_plain_ntt": (C.c_int, [_vp, C.c_int, _vp, _sz, _sz, _vp, _vp, _sz, _sz, _sz, _sz, _vp]),
