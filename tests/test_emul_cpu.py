@@ -68,3 +68,11 @@ def test_matmul_block_layout():
 def test_decrypt_emulated(ref, emul_lib, scheme, n, bits):
     """CKKS / BFV / BGV decryption on the device against the reference CPU decryptor."""
     run_decrypt_flow(ref, emul_lib, scheme, n, bits, np.random.default_rng(500 + scheme + n))
+
+
+@pytest.mark.parametrize("scheme,n,bits", [(2, 4096, [50, 50, 49, 48, 47, 50]), (1, 8192, [50, 50, 50, 50]), (3, 16384, [50, 49, 50]),
+                                           (2, 65536, [50, 50, 50])])
+def test_fp64_butterflies_for_50_bit_primes_emulated(ref, emul_lib, scheme, n, bits):
+    """46..50-bit primes run the FP64 butterflies with per-butterfly re-centring (ArithF64L): no head-room to spare, so this
+    is checked on parameter sets made only of such primes, at every transform size class."""
+    run_evaluator_flow(ref, emul_lib, scheme, n, bits, np.random.default_rng(600 + scheme + n), batch=2)

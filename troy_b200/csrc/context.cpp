@@ -356,7 +356,7 @@ Context *context_create(int device, int scheme, u64 N, const u64 *moduli, int n_
         md.inv1n_shoup = shoup_quotient(md.inv1n, p);
         md.fwd = upload(ctx->owned, fwd);
         md.inv = upload(ctx->owned, inv);
-        // butterfly policy (ntt.cuh). TROYB_NTT_POLICY=exact|fast forces the integer paths (A/B measurements).
+        // butterfly policy (ntt.cuh). TROYB_NTT_POLICY=exact|fast forces the integer paths, nof64l only for 46..50-bit primes (A/B measurements).
         const char *force = getenv("TROYB_NTT_POLICY");
         const bool force_exact = force && std::string(force) == "exact";
         const bool force_fast = force && std::string(force) == "fast";
@@ -368,7 +368,8 @@ Context *context_create(int device, int scheme, u64 N, const u64 *moduli, int n_
         md.ninv_dp = (double)md.ninv / (double)p;
         md.inv1n_d = (double)md.inv1n;
         md.inv1n_dp = (double)md.inv1n / (double)p;
-        if (!(p >> 46) && !force_exact && !force_fast) {
+        const bool no_f64l = force && std::string(force) == "nof64l"; // A/B: 46..50-bit primes on the integer path
+        if (!(p >> 50) && !force_exact && !force_fast && !(no_f64l && (p >> 46))) {
             std::vector<double> fd(2 * N), id(2 * N);
             for (u64 k = 0; k < N; k++) {
                 fd[2 * k] = (double)fwd[2 * k];
@@ -378,7 +379,7 @@ Context *context_create(int device, int scheme, u64 N, const u64 *moduli, int n_
             }
             md.fwd_d = upload(ctx->owned, fd);
             md.inv_d = upload(ctx->owned, id);
-            md.policy = (p >> 41) ? POLICY_F64 : POLICY_F64_SMALL;
+            md.policy = (p >> 46) ? POLICY_F64_LARGE : ((p >> 41) ? POLICY_F64 : POLICY_F64_SMALL);
         }
     }
     ctx->d_mods = upload(ctx->owned, ctx->h_mods);

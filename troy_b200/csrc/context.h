@@ -33,16 +33,16 @@ struct ModDev {
     u64 inv1n, inv1n_shoup; // fwd[1]^-1 * N^-1 mod p
     const u64 *fwd;         // 2*N words
     const u64 *inv;         // 2*N words
-    // FP64 butterfly path (primes below 2^46, see ntt.cuh ArithF64): the same tables as doubles {w, w/p}; null otherwise
+    // FP64 butterfly path (primes below 2^50, see ntt.cuh ArithF64 / ArithF64L): the same tables as doubles {w, w/p}; null otherwise
     const double *fwd_d;
     const double *inv_d;
     double pd, pinv_d;            // p and 1/p
     double ninv_d, ninv_dp;       // N^-1 and N^-1 / p
     double inv1n_d, inv1n_dp;     // fwd[1]^-1 * N^-1 and that / p
     int policy;                   // 0 FP64 (p < 2^46), 1 fast integer (p < 2^60), 2 exact integer (p up to 61 bits), 3 FP64 (p < 2^41),
-                                  // 4 fast integer without forward range corrections (p < 2^57)
+                                  // 4 fast integer without forward range corrections (p < 2^57), 5 FP64 with per-butterfly re-centring (p < 2^50)
 };
-enum { POLICY_F64 = 0, POLICY_U64_FAST = 1, POLICY_U64_EXACT = 2, POLICY_F64_SMALL = 3, POLICY_U64_LAZY = 4 };
+enum { POLICY_F64 = 0, POLICY_U64_FAST = 1, POLICY_U64_EXACT = 2, POLICY_F64_SMALL = 3, POLICY_U64_LAZY = 4, POLICY_F64_LARGE = 5 };
 
 // Constants for dividing by the last prime of a base {q_0..q_{m-1}, q_last} (rescale, mod-switch, key-switch mod-down)
 //   src/utils/rns.cpp:784-803 (inv_q_last_mod_q_, inv_q_last_mod_t_, q_last_mod_t_)

@@ -343,6 +343,7 @@ struct NttInvSmall {
     switch (pol) {                                                         \
     case POLICY_F64: { typedef ArithF64 A; __VA_ARGS__ } break;                     \
     case POLICY_F64_SMALL: { typedef ArithF64S A; __VA_ARGS__ } break;              \
+    case POLICY_F64_LARGE: { typedef ArithF64L A; __VA_ARGS__ } break;              \
     case POLICY_U64_FAST: { typedef ArithU64Fast A; __VA_ARGS__ } break;            \
     case POLICY_U64_LAZY: { typedef ArithU64Lazy A; __VA_ARGS__ } break;            \
     default: { typedef ArithU64Exact A; __VA_ARGS__ } break;                        \
