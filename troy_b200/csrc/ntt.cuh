@@ -80,7 +80,7 @@ struct ArithU64Exact {
     static TB_D u64 canon(elem x, const Mod &m) { return barrett64(x, m.p, m.ratio1); }
     static TB_D u64 canon_reduced(elem x, const Mod &m) { return x - (x >= m.p ? m.p : 0); } // after gs_last: [0,2p)
     static TB_D void reduce(elem &, const Mod &) {}
-    static TB_D void ct(elem &X, elem &Y, tw_t w, const Mod &m) {
+    static TB_D void ct(elem &X, elem &Y, tw_t w, const Mod &m, bool = false) {
         u64 x = X - (X >= m.p2 ? m.p2 : 0);
         u64 t = shoup_lazy(Y, w.w, w.wq, m.p);
         X = x + t;
@@ -151,7 +151,7 @@ struct ArithU64Fast {
         rh = madlo(q0, m.np1, rh);
         return mk64(lo32(r), rh);
     }
-    static TB_D void ct(elem &X, elem &Y, tw_t w, const Mod &m) {
+    static TB_D void ct(elem &X, elem &Y, tw_t w, const Mod &m, bool = false) {
         u64 x = X;
         if (hi32(x) >= m.H) x -= m.p4;          // x < 4p + 2^32
         u64 xn = mul_acc(x, Y, w, m);           // x + T, T in [0,4p)
@@ -178,7 +178,7 @@ struct ArithU64Fast {
 // 68p < 2^64 and the forward transform needs NO range correction (5 of its 27 instructions per butterfly); the store's
 // Barrett reduction accepts any 64-bit value. The inverse transform is ArithU64Fast's.
 struct ArithU64Lazy : ArithU64Fast {
-    static TB_D void ct(elem &X, elem &Y, tw_t w, const Mod &m) {
+    static TB_D void ct(elem &X, elem &Y, tw_t w, const Mod &m, bool = false) {
         const u64 x = X;
         const u64 xn = mul_acc(x, Y, w, m);     // x + T, T in [0,4p)
         X = xn;
@@ -241,7 +241,7 @@ struct ArithF64 {
         double r = __fma_rn(-q, m.p, h);
         return __dadd_rn(r, l);
     }
-    static TB_D void ct(elem &X, elem &Y, tw_t w, const Mod &m) {
+    static TB_D void ct(elem &X, elem &Y, tw_t w, const Mod &m, bool = false) {
         double t = mulmod(Y, w, m);
         double x = X;
         X = __dadd_rn(x, t);
@@ -273,8 +273,8 @@ struct ArithF64S : ArithF64 {
 // exact for |y| <= 2^51 (y w < 2^101: h and l = y w - h are exact, |l| <= 2^47; the quotient estimate is off by at most
 // 0.75, so h - q p is an integer below 2^50 and the FMA returns it exactly) and returns |r| <= 0.75 p. There is no head-room
 // for unreduced growth, so every butterfly re-centres the operand that is not multiplied (|x| <= p/2 after `reduce`):
-// forward outputs are |x +- t| <= 1.25 p < 2^51, inverse inputs stay below p (sum re-centred, difference multiplied), 11
-// instead of 8 FP64 instructions per butterfly - still fewer issue cycles than the 23-27 instructions of the integer paths.
+// forward outputs are |x +- t| <= 1.25 p < 2^51 (2 p after the one layer per register network that skips it), inverse inputs
+// stay below p (sum re-centred, difference multiplied), 10-11 instead of 8 FP64 instructions per butterfly - still fewer issue cycles than the 23-27 instructions of the integer paths.
 struct ArithF64L : ArithF64 {
     static constexpr bool kReduceEachInvRound = false;
     static constexpr bool kReduceInvMidway = false;
@@ -283,10 +283,13 @@ struct ArithF64L : ArithF64 {
         reduce(x, m);
         return x;
     }
-    static TB_D void ct(elem &X, elem &Y, tw_t w, const Mod &m) {
+    // odd_layer: the second layer of a register network. Its inputs come from a re-centring layer (|.| <= 1.25 p), so it may
+    // skip its own: |x +- t| <= 1.25 p + 0.75 p = 2 p < 2^51, which the next layer (always a re-centring one: the third of
+    // the network or the first of the next round) accepts both as x and as y.
+    static TB_D void ct(elem &X, elem &Y, tw_t w, const Mod &m, bool odd_layer = false) {
         double t = mulmod(Y, w, m);
         double x = X;
-        reduce(x, m);
+        if (!odd_layer) reduce(x, m);
         X = __dadd_rn(x, t);
         Y = __dadd_rn(x, -t);
     }
@@ -311,7 +314,7 @@ template <class A, int RR> TB_D void radix_fwd(typename A::elem (&x)[1 << RR], c
 #pragma unroll
             for (int r = 0; r < half; r++) {
                 const int k = (j << (RR - u)) | r;
-                A::ct(x[k], x[k + half], w[(1 << u) - 1 + j], m);
+                A::ct(x[k], x[k + half], w[(1 << u) - 1 + j], m, (u & 1) != 0);
             }
         }
     }
