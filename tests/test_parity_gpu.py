@@ -53,7 +53,6 @@ def test_ntt_sweep(ref, cuda_lib, n):
     """BASELINE config 2: the standalone batched NTT / INTT sweep, N = 4096 .. 65536 x 1 .. 32 limbs of 60-bit primes.
     Size-independent properties on a batch of 3 polys (round trip = identity, linearity) and direct parity of the first and
     the last limb with the reference's transform."""
-    import ctypes as C
     tb = cuda_lib
     from troy_b200.host import DeviceArray, _L, _vp
     rng = np.random.default_rng(n)

@@ -8,7 +8,7 @@ polynomial holds which matrix entry), so any CKKS polynomial encoder can produce
 """
 import numpy as np
 
-from .host import CiphertextCuda, PlaintextCuda, _L, _vp
+from .host import CiphertextCuda, _L, _vp
 from .lib import TroyInvalidArgument
 
 
