@@ -412,6 +412,20 @@ def run_ours(args):
         except Exception as e:  # the baseline is optional; the bench line must still print
             ref_cuda = {"unavailable": str(e)[:200]}
 
+    # ---- SEAL 4.0 (the copy the reference vendors, oracle/_ref/seal_bench: plain g++ build, no HEXL) on the host cores, same
+    # configuration on real encryptions, one Evaluator loop per thread. Reported next to the troy:: CPU baseline; optional.
+    seal = None
+    tool = os.path.join(ROOT, "oracle", "_ref", "seal_bench")
+    if world == 1 and not args.no_cpu_baseline and os.path.exists(tool):
+        try:
+            import subprocess
+            r = subprocess.run([tool, str(os.cpu_count() or 1), "16"], capture_output=True, text=True, timeout=300)
+            for ln in r.stdout.splitlines():
+                if ln.startswith("{"):
+                    seal = json.loads(ln)
+        except Exception as e:
+            seal = {"unavailable": str(e)[:200]}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": t_main / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -433,6 +447,7 @@ def run_ours(args):
                    "shape": f"{MB_}x{MI_} ciphertexts times {MI_}x{MJ_} plaintexts, one launch",
                    "gbs": mm_bytes * extra_steps / t_mm / 1e9, "frac_of_hbm_roofline": mm_bytes * extra_steps / t_mm / 1e9 / hbm_peak},
         "reference_cuda_path": ref_cuda,
+        "seal_cpu_baseline": seal,
         "kernels": kernels,
     }
     print(json.dumps(line))
