@@ -139,7 +139,13 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist = None
+    out_fd = None
     if world > 1:
+        # NCCL writes its version banner to stdout when the communicator is created: keep stdout to the ONE JSON line by
+        # pointing fd 1 at stderr for the run and printing the line on the saved descriptor.
+        sys.stdout.flush()
+        out_fd = os.dup(1)
+        os.dup2(2, 1)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -450,7 +456,11 @@ def run_ours(args):
         "seal_cpu_baseline": seal,
         "kernels": kernels,
     }
-    print(json.dumps(line))
+    if out_fd is None:
+        print(json.dumps(line))
+    else:
+        sys.stdout.flush()
+        os.write(out_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
 
