@@ -370,12 +370,12 @@ template <int LOGT> struct NttFwdTile {
             if (nranks == 1 || u.passthrough) return;
             cluster_arrive_started();
             auto started = [] { cluster_wait_started(); };
-            auto ld = [&](u32 i) -> u64 { return pro(u.src[i]); };
+            auto ld = [&](u32 i) -> u64 { return u.src[i]; };
             u32 handle[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) handle[k] = peers.map((u32)k < nranks ? (u32)k : 0u);
             auto st_peer = [&](u32 k, u32 pi, u64 bits) { peers.st(handle[k], pi, bits); };
-            TB_WITH_POLICY(pol, TB_WITH_LOGC(u.rows_log, TB_PHASE(kThreads, t, (cluster_fwd_scatter<A, LOGC, LOGT, kThreads>(t, rank, ld, st_peer, started, md));)))
+            TB_WITH_POLICY(pol, TB_WITH_LOGC(u.rows_log, TB_PHASE(kThreads, t, (cluster_fwd_scatter<A, LOGC, LOGT, kThreads>(t, rank, ld, pro, st_peer, started, md));)))
         } else {
             const u64 off = (u64)rank << LOGT;
             if (u.passthrough) return; // digit already in NTT form under this modulus: the inner product reads it in place

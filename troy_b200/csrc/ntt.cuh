@@ -683,11 +683,13 @@ TB_D void tile_ntt_inv(u64 *sm, Gld gld, St st, const ModDev *md, u32 R) {
 // for its share of v, runs the radix-C network in registers and hands output k to tile k (a store into that CTA's
 // shared memory through the cluster's distributed shared memory). After the cluster barrier every CTA owns an
 // independent 2^LOGT-point transform with root base C + rank.
-//   ld(i)            : coefficient i of the limb as u64 (prologue fused there)
+//   ld(i)            : coefficient i of the limb as u64, a bare global load
+//   pro(x)           : prologue applied to a loaded coefficient (kept out of ld: its mode branches between the loads made
+//                      ptxas issue one load, wait, reduce, next load - a memory latency per coefficient instead of per batch)
 //   st_peer(k, i, b) : store raw element bits b at padded index i of tile k
 //   peers_started()  : called once by every thread before the first remote store (the peers' shared memory must exist)
-template <class A, int LOGC, int LOGT, int NT, class Ld, class StPeer, class Started>
-TB_D void cluster_fwd_scatter(u32 vt, u32 rank, Ld ld, StPeer st_peer, Started peers_started, const ModDev *md) {
+template <class A, int LOGC, int LOGT, int NT, class Ld, class Pro, class StPeer, class Started>
+TB_D void cluster_fwd_scatter(u32 vt, u32 rank, Ld ld, Pro pro, StPeer st_peer, Started peers_started, const ModDev *md) {
     constexpr int C = 1 << LOGC, T = 1 << LOGT, G = T / C / NT;
     static_assert(G >= 1, "bad cluster stage");
     // B iterations (16 coefficients) are loaded before any of them is used: one memory latency per batch, not per
@@ -714,7 +716,7 @@ TB_D void cluster_fwd_scatter(u32 vt, u32 rank, Ld ld, StPeer st_peer, Started p
             const u32 v = rank * (T / C) + vt + (g0 + b) * NT;
             typename A::elem x[C];
 #pragma unroll
-            for (int k = 0; k < C; k++) x[k] = A::from_u64(raw[b][k], m);
+            for (int k = 0; k < C; k++) x[k] = A::from_u64(pro(raw[b][k]), m);
             radix_fwd<A, LOGC>(x, w, m);
             const u32 pv = pad_idx(v);
 #pragma unroll
