@@ -42,6 +42,12 @@ const char *troyb_last_error(void);
 /* KernelProvider::initialize()  src/kernelprovider.cuh:29-33  (device index added; the reference hard-codes 0) */
 int troyb_initialize(int device);
 int troyb_initialized(void);
+/* More than one GPU in a process (the reference pins device 0, src/kernelprovider.cuh:30): the CUDA current device is a
+ * per-host-thread setting. Calls that take a context make the context's device current for the calling thread; the
+ * context-free calls (troyb_malloc, the copies, troyb_context_create) act on the thread's current device, chosen by
+ * troyb_initialize / troyb_set_device. */
+int troyb_set_device(int device);
+int troyb_context_device(const troyb_context *ctx);
 
 /* Number of kernels this library has launched so far in this process (diagnostic used by bench.py). */
 uint64_t troyb_launch_count(void);

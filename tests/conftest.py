@@ -36,7 +36,8 @@ def emul_lib():
     g.build_emul()
     import troy_b200 as tb
     from troy_b200 import lib as tlib
-    prev = tlib._set_library_for_tests(tlib.Library(os.path.join(ROOT, "tests", "emul", "libtroy_b200_emul.so")))
+    # the package itself only ever loads troy_b200/libtroy_b200.so; the swap is done from here, by the test harness
+    prev, tlib._library = tlib._library, tlib.Library(os.path.join(ROOT, "tests", "emul", "libtroy_b200_emul.so"))
     tb.KernelProvider.initialize(0)
     yield tb
-    tlib._set_library_for_tests(prev)
+    tlib._library = prev

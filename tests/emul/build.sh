@@ -4,5 +4,5 @@
 set -e
 HERE=$(cd "$(dirname "$0")" && pwd)
 SRC=$HERE/../../troy_b200/csrc
-g++ -std=c++17 -O2 -ffp-contract=off -fPIC -shared -DTROYB_HOST_EMUL -D__CUDACC__ -I"$HERE" -x c++ "$SRC/api.cu" -x c++ "$SRC/context.cpp" \
+g++ -std=c++17 -O2 -ffp-contract=off -fPIC -shared -DTROYB_HOST_EMUL -D__CUDACC__ -I"$HERE" -x c++ "$SRC/api.cu" -x c++ "$SRC/ntt_fwd.cu" -x c++ "$SRC/ntt_inv.cu" -x c++ "$SRC/context.cpp" \
     -o "$HERE/libtroy_b200_emul.so"

@@ -26,6 +26,9 @@ enum { cudaMemPoolAttrReleaseThreshold = 0 };
 
 inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
 inline cudaError_t cudaSetDevice(int) { return 0; }
+inline cudaError_t cudaGetDevice(int *d) { *d = 0; return 0; }
+enum { cudaDevAttrMultiProcessorCount = 16 };
+inline cudaError_t cudaDeviceGetAttribute(int *v, int, int) { *v = 148; return 0; }
 inline cudaError_t cudaFree(void *p) { free(p); return 0; }
 inline cudaError_t cudaMalloc(void **p, size_t n) { *p = malloc(n ? n : 8); return 0; }
 inline cudaError_t cudaMallocAsync(void **p, size_t n, cudaStream_t) { *p = malloc(n ? n : 8); return 0; }

@@ -39,7 +39,7 @@ def _worker(rank, world, port, scheme, n, bits, out):
         from troy_b200.distributed import DigitShardedKeySwitch, shard_range
         from oracle import ref
         from common import make_pair, random_ct_words
-        tlib._set_library_for_tests(tlib.Library(os.path.join(ROOT, "tests", "emul", "libtroy_b200_emul.so")))
+        tlib._library = tlib.Library(os.path.join(ROOT, "tests", "emul", "libtroy_b200_emul.so"))
         tb.KernelProvider.initialize(0)
         rc, ctx = make_pair(ref, tb, scheme, n, bits)
         rc.keygen()                      # seeded: identical keys in every rank

@@ -4,9 +4,11 @@
 #include "context.h"
 #include "kernels_elt.cuh"
 #include "kernels_ntt.cuh"
+#include "ntt_launch.h"
 #include "hostmath.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
@@ -21,8 +23,18 @@ struct troyb_context {
 namespace {
 
 thread_local std::string g_error;
-bool g_initialized = false;
-int g_device = 0;
+std::atomic<bool> g_initialized{false};
+// The CUDA "current device" is a per-host-thread setting. One process may drive several GPUs (one context per device,
+// typically one host thread per device): every entry point that takes a context makes the context's device current for the
+// calling thread first, and the context-free calls (troyb_malloc, copies) act on the thread's current device, which
+// troyb_initialize / troyb_set_device choose.
+thread_local int t_device = -1;
+void use_device(int device) {
+    if (t_device == device) return;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e));
+    t_device = device;
+}
 
 struct CudaError : std::runtime_error {
     explicit CudaError(cudaError_t e) : std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e)) {}
@@ -69,10 +81,12 @@ struct Scratch {
 
 Context *C(troyb_context *c) {
     if (!c || !c->impl) throw std::invalid_argument("context is null");
+    use_device(c->impl->device);
     return c->impl;
 }
 const Context *C(const troyb_context *c) {
     if (!c || !c->impl) throw std::invalid_argument("context is null");
+    use_device(c->impl->device);
     return c->impl;
 }
 
@@ -84,9 +98,7 @@ int level_limbs(const Context *ctx, int level) {
 
 u32 grid_for(u64 total, int threads) { return (u32)((total + threads - 1) / threads); }
 
-// ---- NTT dispatch --------------------------------------------------------------------------------------------------
-size_t tile_smem(int logt) { return (size_t)padded_words(1u << logt) * sizeof(u64); }
-
+// ---- NTT dispatch (the transforms are compiled in ntt_fwd.cu / ntt_inv.cu, see ntt_launch.h) -------------------------
 // Launch order of the limbs of a launch. Consecutive CTAs cycle through the limbs; limbs whose butterflies run on the
 // integer pipe (60-bit primes) are spread evenly between those on the FP64 pipe (primes below 2^46), so that the CTAs
 // resident on one SM at any time keep both pipes busy.
@@ -105,56 +117,13 @@ void set_order(const Context *ctx, NttArgs &a, u32 n_limbs_in_map) {
     a.n_rank = n_limbs_in_map;
 }
 
-// Tiles per limb of a transform of 2^logN coefficients (see ntt.cuh TilePlan).
-// Tile size of a transform of 2^logN coefficients: 4096-coefficient tiles (four radix-8 rounds, six CTAs per SM) for
-// N = 4096 and, as clusters of 4 / 8 tiles, for N up to 2^TROYB_TILE12_MAXLOGN (development knob for A/B runs);
-// 8192-coefficient tiles otherwise.
-int tile_log(int logN) {
-    static const int max12 = [] { const char *e = getenv("TROYB_TILE12_MAXLOGN"); return e ? atoi(e) : 12; }();
-    return (logN == 12 || (logN > 13 && logN <= max12 && logN <= 15)) ? 12 : 13;
+void run_fwd(const Context *ctx, const NttArgs &a, u32 units, cudaStream_t s) {
+    if (ctx->logN > 16) throw std::invalid_argument("poly_modulus_degree above 65536 is not supported");
+    ck(launch_ntt_fwd(ctx, a, units, s));
 }
-u32 tiles_per_limb(int logN) { const int lt = tile_log(logN); return logN <= lt ? 1u : (1u << (logN - lt)); }
-
-// L2 prefetch distance of the tile transforms: about one wave of resident CTAs (148 SMs x CTAs per SM, rounded up to
-// whole clusters). TROYB_PF_WAVES_X4 (development knob) scales it in quarter waves; 0 switches the prefetch off.
-u32 prefetch_distance(int logt) {
-    static const int quarters = [] { const char *e = getenv("TROYB_PF_WAVES_X4"); return e ? atoi(e) : 4; }();
-    const u32 wave = logt == 12 ? 888u : 448u;
-    return (wave * (u32)quarters / 4u) & ~7u;
-}
-
-void run_fwd(const Context *ctx, NttArgs a, u32 units, cudaStream_t s) {
-    a.logN = ctx->logN;
-    a.pf_ahead = prefetch_distance(tile_log(ctx->logN));
-    a.mods = ctx->d_mods;
-    const int logN = ctx->logN;
-    if (logN > 16) throw std::invalid_argument("poly_modulus_degree above 65536 is not supported");
-    if (logN < 12) {
-        ck(launch_cta(NttFwdSmall{a}, units, (size_t)ctx->N * sizeof(u64), s));
-    } else if (tile_log(logN) == 12) {
-        const u32 c = tiles_per_limb(logN);
-        ck(launch_cluster(NttFwdTile<12>{a}, units * c, c, tile_smem(12), s));
-    } else {
-        const u32 c = tiles_per_limb(logN);
-        ck(launch_cluster(NttFwdTile<13>{a}, units * c, c, tile_smem(13), s));
-    }
-}
-
-void run_inv(const Context *ctx, NttArgs a, u32 units, cudaStream_t s) {
-    a.logN = ctx->logN;
-    a.pf_ahead = prefetch_distance(tile_log(ctx->logN));
-    a.mods = ctx->d_mods;
-    const int logN = ctx->logN;
-    if (logN > 16) throw std::invalid_argument("poly_modulus_degree above 65536 is not supported");
-    if (logN < 12) {
-        ck(launch_cta(NttInvSmall{a}, units, (size_t)ctx->N * sizeof(u64), s));
-    } else if (tile_log(logN) == 12) {
-        const u32 c = tiles_per_limb(logN);
-        ck(launch_cluster(NttInvTile<12>{a}, units * c, c, tile_smem(12), s));
-    } else {
-        const u32 c = tiles_per_limb(logN);
-        ck(launch_cluster(NttInvTile<13>{a}, units * c, c, tile_smem(13), s));
-    }
+void run_inv(const Context *ctx, const NttArgs &a, u32 units, cudaStream_t s) {
+    if (ctx->logN > 16) throw std::invalid_argument("poly_modulus_degree above 65536 is not supported");
+    ck(launch_ntt_inv(ctx, a, units, s));
 }
 
 // Plain batched transform: `batch` elements of `limbs_per_elem` limbs (polys x L), moduli map[l % L].
@@ -234,7 +203,7 @@ void switch_key_partial(Context *ctx, int level, const u64 *target, u64 target_s
         if (N >= kStagedCoeffs) {
             // key slices staged in shared memory, digits in groups of at most 8, partial sums added up in prod
             const u64 units = (u64)nb * Lp * (N / kStagedCoeffs);
-            const u32 bc = (u32)std::min<u64>(16, std::max<u64>(1, units / (148 * 3 * 8)));
+            const u32 bc = (u32)std::min<u64>(16, std::max<u64>(1, units / ((u64)ctx->sm_count * 3 * 8)));
             const u32 grid = (u32)(N / kStagedCoeffs) * Lp * ((nb + bc - 1) / bc);
             for (u32 g0 = 0; g0 < nd; g0 += kStagedMaxDigits) {
                 auto launch = [&](auto k) {
@@ -384,10 +353,20 @@ int troyb_initialize(int device) {
     API_BEGIN
     ck(cudaSetDevice(device));
     ck(cudaFree(0));
-    g_device = device;
+    t_device = device;
     g_initialized = true;
     API_END
 }
+
+int troyb_set_device(int device) {
+    API_BEGIN
+    need_init();
+    t_device = -1;
+    use_device(device);
+    API_END
+}
+
+int troyb_context_device(const troyb_context *ctx) { return ctx && ctx->impl ? ctx->impl->device : -1; }
 
 int troyb_initialized(void) { return g_initialized ? 1 : 0; }
 
@@ -497,7 +476,10 @@ int troyb_context_create(int scheme, uint64_t n, const uint64_t *moduli, int n_m
     API_BEGIN
     need_init();
     if (!out || !moduli) throw std::invalid_argument("null argument");
-    Context *impl = context_create(g_device, scheme, n, moduli, n_moduli, plain_modulus, expand_mod_chain != 0);
+    int device = t_device;
+    if (device < 0) ck(cudaGetDevice(&device));
+    Context *impl = context_create(device, scheme, n, moduli, n_moduli, plain_modulus, expand_mod_chain != 0);
+    t_device = device;
     *out = new troyb_context{impl};
     API_END
 }
@@ -536,6 +518,7 @@ int troyb_context_total_coeff_bits(const troyb_context *ctx, int level) {
     try {
         const Context *c = C(ctx);
         level_limbs(c, level);
+        // the key level (-1) is not an entry of levels[]: its modulus is every prime of the pool's chain
         return c->level_total_bits(level);
     } catch (const std::exception &e) {
         g_error = e.what();
@@ -548,6 +531,7 @@ int troyb_context_bsk(const troyb_context *ctx, int level, uint64_t *out) {
     try {
         const Context *c = C(ctx);
         level_limbs(c, level);
+        if (level < 0) return 0; // the key level has no BEHZ base
         const LevelData &lv = c->levels[level];
         if (!lv.has_behz) return 0;
         if (out) {

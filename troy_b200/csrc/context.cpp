@@ -267,13 +267,24 @@ LimbMap Context::map_q_bsk(int level) const {
 }
 
 int Context::level_total_bits(int level) const {
-    // bit count of prod(q_0..q_{L-1}) computed exactly with a small big-integer
-    int L = levels[level].L;
+    // bit count of prod(q_0..q_{L-1}) computed exactly with a small big-integer; level -1 is the key level: the data
+    // primes of the first level and the special prime
+    const bool key_level = level < 0;
+    int L = key_level ? Ltop : levels[level].L;
     std::vector<u64> acc{1};
     for (int i = 0; i < L; i++) {
         u64 carry = 0;
         for (auto &w : acc) {
             u128 t = (u128)w * pool[i] + carry;
+            w = (u64)t;
+            carry = (u64)(t >> 64);
+        }
+        if (carry) acc.push_back(carry);
+    }
+    if (key_level && has_special) {
+        u64 carry = 0;
+        for (auto &w : acc) {
+            u128 t = (u128)w * pool[pool_special] + carry;
             w = (u64)t;
             carry = (u64)(t >> 64);
         }
@@ -288,6 +299,8 @@ Context *context_create(int device, int scheme, u64 N, const u64 *moduli, int n_
     int logN = 0;
     while ((u64(1) << logN) < N) logN++;
     if ((u64(1) << logN) != N || N < 2 || N > 131072) throw std::invalid_argument("poly_modulus_degree is invalid");
+    // the transforms are planned for N <= 65536 (a cluster of eight 8192-coefficient tiles); say so now, not at the first NTT
+    if (N > 65536) throw std::invalid_argument("poly_modulus_degree above 65536 is not supported");
     if (n_moduli < 1 || n_moduli > 64) throw std::invalid_argument("invalid coeff modulus size");
     for (int i = 0; i < n_moduli; i++) {
         if ((moduli[i] >> 60) || moduli[i] < 2) throw std::invalid_argument("invalid coeff modulus bit count");
@@ -306,6 +319,11 @@ Context *context_create(int device, int scheme, u64 N, const u64 *moduli, int n_
     CUDA_OK(cudaSetDevice(device));
     std::unique_ptr<Context> ctx(new Context());
     ctx->device = device;
+    {
+        int sms = 0;
+        CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        ctx->sm_count = sms > 0 ? sms : 1;
+    }
     ctx->scheme = scheme;
     ctx->N = N;
     ctx->logN = logN;
@@ -370,16 +388,21 @@ Context *context_create(int device, int scheme, u64 N, const u64 *moduli, int n_
         md.inv1n_dp = (double)md.inv1n / (double)p;
         const bool no_f64l = force && std::string(force) == "nof64l"; // A/B: 46..50-bit primes on the integer path
         if (!(p >> 50) && !force_exact && !force_fast && !(no_f64l && (p >> 46))) {
-            std::vector<double> fd(2 * N), id(2 * N);
+            md.policy = (p >> 46) ? POLICY_F64_LARGE : ((p >> 41) ? POLICY_F64 : POLICY_F64_SMALL);
+            // p < 2^46: one double per twiddle (the quotient is estimated from the product, ntt.cuh ArithF64T<true>);
+            // 46..50 bits: pairs {w, w/p}
+            const u64 per = md.policy == POLICY_F64_LARGE ? 2 : 1;
+            std::vector<double> fd(per * N), id(per * N);
             for (u64 k = 0; k < N; k++) {
-                fd[2 * k] = (double)fwd[2 * k];
-                fd[2 * k + 1] = (double)fwd[2 * k] / (double)p;
-                id[2 * k] = (double)inv[2 * k];
-                id[2 * k + 1] = (double)inv[2 * k] / (double)p;
+                fd[per * k] = (double)fwd[2 * k];
+                id[per * k] = (double)inv[2 * k];
+                if (per == 2) {
+                    fd[2 * k + 1] = (double)fwd[2 * k] / (double)p;
+                    id[2 * k + 1] = (double)inv[2 * k] / (double)p;
+                }
             }
             md.fwd_d = upload(ctx->owned, fd);
             md.inv_d = upload(ctx->owned, id);
-            md.policy = (p >> 46) ? POLICY_F64_LARGE : ((p >> 41) ? POLICY_F64 : POLICY_F64_SMALL);
         }
     }
     ctx->d_mods = upload(ctx->owned, ctx->h_mods);

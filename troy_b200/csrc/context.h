@@ -125,6 +125,7 @@ struct LevelData {
 
 struct Context {
     int device = 0;
+    int sm_count = 148;           // multiprocessors of `device` (grid and prefetch sizing)
     int scheme = 0;
     u64 N = 0;
     int logN = 0;

@@ -58,6 +58,9 @@ struct NttArgs {
     uint8_t order[kMaxLimbs]; // launch rank -> limb index: integer-pipe and FP64-pipe limbs interleaved (see set_order)
     u32 n_rank;         // limb ranks in the launch; consecutive units cycle through them
     u32 pf_ahead;       // L2 prefetch distance in CTAs (0 = off): CTA b asks the L2 for the source tile of CTA b + pf_ahead
+    int solo;           // forward, limb = 2 tiles: independent CTAs that both recompute layer 0 (FwdSoloLd). Launched without a
+                        // cluster when the transform is out of place; in place, as a cluster of two whose only exchange is one
+                        // split barrier "my loads are done" before anybody stores (run_fwd)
 };
 
 TB_D u64 canon4(u64 v, u64 p) {
@@ -248,6 +251,48 @@ struct FwdPrologue {
     }
 };
 
+// Staged loaders (ntt.cuh IsStagedLd) of a forward tile transform's first round.
+// The tile is the whole limb: input i is coefficient i.
+template <class A> struct FwdTileLd {
+    typedef u64 Raw;
+    const u64 *src;
+    FwdPrologue pro;
+    typename A::Mod m;
+    TB_D Raw raw(u32 i) const { return src[i]; }
+    template <int K> TB_D void cook(const Raw (&r)[K], typename A::elem (&x)[K]) const {
+        if (pro.mode != FWD_PLAIN) {
+#pragma unroll
+            for (int k = 0; k < K; k++) x[k] = A::from_u64(pro(r[k]), m);
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; k++) x[k] = A::from_u64(r[k], m);
+        }
+    }
+};
+// Solo tiles (limb = 2 tiles, no cluster): the CTA of tile `upper` recomputes layer 0 of the limb's transform, which couples
+// coefficient i with i + T, from both inputs and keeps its own side: one extra modular multiply per coefficient instead of a
+// scatter stage through distributed shared memory, a cluster barrier and co-scheduling of the two CTAs.
+template <class A, int LOGT> struct FwdSoloLd {
+    struct Raw { u64 a, b; };
+    const u64 *src; // coefficient 0 of the limb
+    FwdPrologue pro;
+    typename A::Mod m;
+    typename A::tw_t w1;
+    bool upper;
+    TB_D Raw raw(u32 i) const { return Raw{src[i], src[i + (1u << LOGT)]}; }
+    template <int K> TB_D void cook(const Raw (&r)[K], typename A::elem (&x)[K]) const {
+        u64 a[K], b[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) { a[k] = r[k].a; b[k] = r[k].b; }
+        if (pro.mode != FWD_PLAIN) {
+#pragma unroll
+            for (int k = 0; k < K; k++) { a[k] = pro(a[k]); b[k] = pro(b[k]); }
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) x[k] = ct_half<A>(A::from_u64(a[k], m), A::from_u64(b[k], m), w1, m, upper);
+    }
+};
+
 // Epilogue of a forward transform: v is the canonical residue of output i of the limb.
 struct FwdStore {
     NttUnit u;
@@ -352,11 +397,12 @@ struct NttInvSmall {
 template <int LOGT> struct NttFwdTile {
     static constexpr int kThreads = TilePlan<LOGT>::NT;
     static constexpr int kMinCtas = TilePlan<LOGT>::CTAS;
-    static constexpr int kStages = 2;
+    static constexpr int kStages = 3; // scatter | tile transform | canonical store (no cluster barrier between the last two)
     static constexpr bool kTrailingBarrier = false; // peers only write into this CTA's tile, and only in stage 0
     static constexpr u32 T = 1u << LOGT;
     NttArgs a;
     const char *name() const { return ntt_kernel_name(a.mode); }
+    TB_D bool barrier_after(int S) const { return S == 0 && a.solo == 0; } // solo tiles exchange nothing through shared memory
 
     template <int S> TB_D void stage(u32 bid, u32 grid, u32 rank, u32 nranks, u64 *sm, const Peers &peers) const {
         NttUnit u = resolve_unit<LOGT>(a, bid);
@@ -364,10 +410,13 @@ template <int LOGT> struct NttFwdTile {
         const int pol = md->policy;
         const FwdPrologue pro{md->p, md->ratio1, a.mode == FWD_MODDOWN ? md->p - u.dl.half_mod : 0,
                               (a.mode == FWD_MODUP && !u.reduce_src) ? (int)FWD_PLAIN : a.mode};
+        // solo tiles: a limb of two tiles launched without a cluster (run_fwd), layer 0 recomputed by both CTAs (FwdSoloLd)
+        const bool solo = a.solo != 0;
+        const u32 trank = solo ? u.row : rank;
         if constexpr (S == 0) {
-            prefetch_tiles<LOGT>(a, u, bid, rank, grid);
+            prefetch_tiles<LOGT>(a, u, bid, trank, grid);
             // scatter stage: the layers that couple the tiles, results into the peers' shared memory
-            if (nranks == 1 || u.passthrough) return;
+            if (nranks == 1 || solo || u.passthrough) return;
             cluster_arrive_started();
             auto started = [] { cluster_wait_started(); };
             auto ld = [&](u32 i) -> u64 { return u.src[i]; };
@@ -376,15 +425,27 @@ template <int LOGT> struct NttFwdTile {
             for (int k = 0; k < 8; k++) handle[k] = peers.map((u32)k < nranks ? (u32)k : 0u);
             auto st_peer = [&](u32 k, u32 pi, u64 bits) { peers.st(handle[k], pi, bits); };
             TB_WITH_POLICY(pol, TB_WITH_LOGC(u.rows_log, TB_PHASE(kThreads, t, (cluster_fwd_scatter<A, LOGC, LOGT, kThreads>(t, rank, ld, pro, st_peer, started, md));)))
-        } else {
-            const u64 off = (u64)rank << LOGT;
+        } else if constexpr (S == 1) {
             if (u.passthrough) return; // digit already in NTT form under this modulus: the inner product reads it in place
-            if (nranks == 1) {
-                auto gld = [&](u32 i) -> u64 { return pro(u.src[i]); };
-                TB_WITH_POLICY(pol, (tile_ntt_fwd<A, LOGT, true>(sm, gld, md, 1u));)
+            if (solo) {
+                TB_WITH_POLICY(pol, {
+                    const FwdSoloLd<A, LOGT> gld{u.src, pro, A::make(md), A::ld_tw(A::fwd_table(md), 1), trank != 0};
+                    // in place (cluster of two): the peer may overwrite this CTA's inputs once both have loaded theirs
+                    auto loaded = [&] { if (nranks > 1) cluster_arrive_started(); };
+                    tile_ntt_fwd<A, LOGT, true>(sm, gld, md, 2u + trank, loaded);
+                })
+            } else if (nranks == 1) {
+                TB_WITH_POLICY(pol, {
+                    const FwdTileLd<A> gld{u.src, pro, A::make(md)};
+                    tile_ntt_fwd<A, LOGT, true>(sm, gld, md, 1u);
+                })
             } else {
                 TB_WITH_POLICY(pol, (tile_ntt_fwd<A, LOGT, false>(sm, 0, md, nranks + rank));)
             }
+        } else {
+            if (u.passthrough) return;
+            if (solo && nranks > 1) cluster_wait_started();
+            const u64 off = (u64)trank << LOGT;
             // this tile's outputs are coefficients [off, off + T) of the limb's (bit-reversed) output
             if (u.dst) u.dst += off;
             if (u.ct) u.ct += off;
@@ -403,6 +464,7 @@ template <int LOGT> struct NttInvTile {
     static constexpr bool kTrailingBarrier = true; // peers read this CTA's tile in the gather stage
     NttArgs a;
     const char *name() const { return ntt_kernel_name(a.mode); }
+    TB_D bool barrier_after(int) const { return true; }
 
     template <int S> TB_D void stage(u32 bid, u32 grid, u32 rank, u32 nranks, u64 *sm, const Peers &peers) const {
         const NttUnit u = resolve_unit<LOGT>(a, bid);

@@ -17,11 +17,15 @@
 #pragma once
 #include "context.h"
 #include "modarith.cuh"
+#include <atomic>
+#include <mutex>
 
 namespace troyb {
 
-inline unsigned long long &launch_counter() {
-    static unsigned long long n = 0;
+// Process-wide launch bookkeeping. Host threads may launch concurrently (one evaluator per thread, ctypes releases the
+// GIL): the counter is atomic and the profiler's record list is guarded by a mutex.
+inline std::atomic<unsigned long long> &launch_counter() {
+    static std::atomic<unsigned long long> n{0};
     return n;
 }
 
@@ -31,13 +35,34 @@ struct ProfRecord {
     cudaEvent_t e0, e1;
 };
 struct Profiler {
-    bool enabled = false;
+    std::atomic<bool> enabled{false};
+    std::mutex mu;
     std::vector<ProfRecord> records;
+    void push(const ProfRecord &r) {
+        std::lock_guard<std::mutex> g(mu);
+        records.push_back(r);
+    }
 };
 inline Profiler &profiler() {
     static Profiler p;
     return p;
 }
+
+// cudaFuncSetAttribute applies to the CURRENT device only: remember per kernel which devices have been configured
+// (bit d of the mask = device d; one process may drive several GPUs, one context per device).
+struct DeviceOnce {
+    std::atomic<unsigned long long> mask{0};
+    template <class Fn> cudaError_t ensure(Fn configure) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        const unsigned long long bit = 1ull << (dev & 63);
+        if (mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+        e = configure(); // idempotent: two threads racing here both set the same attribute
+        if (e == cudaSuccess) mask.fetch_or(bit, std::memory_order_release);
+        return e;
+    }
+};
 
 #if defined(TROYB_HOST_EMUL)
 
@@ -103,12 +128,9 @@ template <class F> __global__ void __launch_bounds__(F::kThreads, MinCtas<F>::va
 template <class F> inline cudaError_t launch_cta(const F &f, u32 grid, size_t smem_bytes, cudaStream_t stream) {
     if (grid == 0) return cudaSuccess;
     if (smem_bytes > 48 * 1024) {
-        static bool configured = false; // per functor type
-        if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(k_cta<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            if (e != cudaSuccess) return e;
-            configured = true;
-        }
+        static DeviceOnce once; // per functor type
+        cudaError_t e = once.ensure([] { return cudaFuncSetAttribute(k_cta<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+        if (e != cudaSuccess) return e;
     }
     Profiler &prof = profiler();
     if (prof.enabled) {
@@ -121,7 +143,7 @@ template <class F> inline cudaError_t launch_cta(const F &f, u32 grid, size_t sm
         cudaEventRecord(r.e0, stream);
         k_cta<F><<<grid, F::kThreads, smem_bytes, stream>>>(f);
         cudaEventRecord(r.e1, stream);
-        prof.records.push_back(r);
+        prof.push(r);
     } else {
         k_cta<F><<<grid, F::kThreads, smem_bytes, stream>>>(f);
     }
@@ -169,7 +191,7 @@ TB_D void cluster_barrier() {
 template <class F, int S> TB_D void run_stages(const F &f, u32 rank, u32 nranks, u64 *smem, const Peers &peers) {
     if constexpr (S < F::kStages) {
         f.template stage<S>(blockIdx.x, gridDim.x, rank, nranks, smem, peers);
-        if (nranks > 1 && (S + 1 < F::kStages || F::kTrailingBarrier)) cluster_barrier();
+        if (nranks > 1 && (S + 1 < F::kStages || F::kTrailingBarrier) && f.barrier_after(S)) cluster_barrier();
         run_stages<F, S + 1>(f, rank, nranks, smem, peers);
     }
 }
@@ -186,11 +208,10 @@ template <class F> __global__ void __launch_bounds__(F::kThreads, F::kMinCtas) k
 template <class F> inline cudaError_t launch_cluster(const F &f, u32 grid, u32 nranks, size_t smem_bytes, cudaStream_t stream) {
     if (grid == 0) return cudaSuccess;
     if (grid % nranks) return cudaErrorInvalidValue;
-    static bool configured = false; // per functor type
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_cluster<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        configured = true;
+    static DeviceOnce once; // per functor type
+    {
+        cudaError_t e0 = once.ensure([] { return cudaFuncSetAttribute(k_cluster<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+        if (e0 != cudaSuccess) return e0;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -215,7 +236,7 @@ template <class F> inline cudaError_t launch_cluster(const F &f, u32 grid, u32 n
         cudaEventRecord(r.e0, stream);
         e = cudaLaunchKernelEx(&cfg, k_cluster<F>, f);
         cudaEventRecord(r.e1, stream);
-        prof.records.push_back(r);
+        prof.push(r);
     } else {
         e = cudaLaunchKernelEx(&cfg, k_cluster<F>, f);
     }

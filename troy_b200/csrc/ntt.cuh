@@ -23,6 +23,7 @@
 // butterfly element i use table entry (R << s) + (i >> (LOGT - s)).
 #pragma once
 #include "launch.cuh"
+#include <type_traits>
 
 #if defined(TROYB_HOST_EMUL)
 #include <cmath>
@@ -186,34 +187,50 @@ struct ArithU64Lazy : ArithU64Fast {
     }
 };
 
-// FP64 path for p < 2^46: residues are integers held exactly in doubles (|x| < 2^51 throughout). The product y*w is
-// formed exactly as h + l with one multiply and one FMA, the quotient comes from y * (w/p) rounded to nearest with the
-// 1.5*2^52 trick, and h - q*p + l is exact, so the result is the balanced residue up to a tiny excess:
-// |mulmod| <= (1/2 + 2^-6) p. Forward butterflies therefore need no range correction at all (growth <= 0.52 p per layer,
-// 16 layers from a start below 4p stay under 2^51); the inverse doubles the sum path each layer, so every inverse round
-// first re-centres its inputs.
+// FP64 path for p < 2^50: residues are integers held exactly in doubles (|x| < 2^51 throughout). The product y*w is formed
+// exactly as h + l with one multiply and one FMA, the quotient q is an estimate of y*w/p rounded to the nearest integer with
+// the 1.5*2^52 trick, and h - q*p + l is exact, so the result is congruent to y*w with |r| <= (1/2 + e) p, e = the error of
+// the estimate before rounding. Two ways to estimate (the template parameter):
+//   COMPACT (p < 2^46): q ~ h * (1/p). Three roundings: e <= 3 * 2^-53 * |y| w / p < 3 * 2^-53 * |y|, i.e. |r| < 0.875 p for
+//           |y| <= 2^50 and |r| < p for |y| < 2^50.4. The twiddle is ONE double per table entry (8 bytes): half the
+//           registers, half the L2 -> SM bytes and half the load-store-unit wavefronts of the {w, w/p} pairs (the late layers
+//           of a transform use one twiddle per butterfly, so twiddle bytes match the data bytes), and the same eight FP64
+//           instructions per butterfly.
+//   pairs   (p < 2^50): q ~ y * (w/p) with w/p precomputed per twiddle. Two roundings: e <= 2^-52 * |y|; needed where there is
+//           no head-room (ArithF64L).
+// Forward butterflies need no range correction (growth < 0.875 p per layer: 16 layers from a start below 4p stay under
+// 18p < 2^51 for p < 2^46); the inverse doubles the sum path each layer, so every inverse round first re-centres its inputs.
 struct TwF64 { double w, wp; };
-struct ArithF64 {
+struct TwF64c { double w; };
+template <bool COMPACT> struct ArithF64T {
     typedef double elem;
-    typedef TwF64 tw_t;
+    typedef typename std::conditional<COMPACT, TwF64c, TwF64>::type tw_t;
     static constexpr bool kReduceEachInvRound = true;
     static constexpr bool kReduceInvMidway = false;
     struct Mod {
         double p, pinv;
-        TwF64 ninv, inv1n;
+        tw_t ninv, inv1n;
     };
+    static TB_D tw_t mk_tw(double w, double wp) {
+        if constexpr (COMPACT) return TwF64c{w};
+        else return TwF64{w, wp};
+    }
     static TB_D Mod make(const ModDev *md) {
         Mod m;
         m.p = md->pd; m.pinv = md->pinv_d;
-        m.ninv = TwF64{md->ninv_d, md->ninv_dp};
-        m.inv1n = TwF64{md->inv1n_d, md->inv1n_dp};
+        m.ninv = mk_tw(md->ninv_d, md->ninv_dp);
+        m.inv1n = mk_tw(md->inv1n_d, md->inv1n_dp);
         return m;
     }
     static TB_D const void *fwd_table(const ModDev *md) { return md->fwd_d; }
     static TB_D const void *inv_table(const ModDev *md) { return md->inv_d; }
     static TB_D tw_t ld_tw(const void *tab, u32 k) {
-        ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(tab) + k);
-        return TwF64{__longlong_as_double((long long)v.x), __longlong_as_double((long long)v.y)};
+        if constexpr (COMPACT) {
+            return TwF64c{__ldg(reinterpret_cast<const double *>(tab) + k)};
+        } else {
+            ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(tab) + k);
+            return TwF64{__longlong_as_double((long long)v.x), __longlong_as_double((long long)v.y)};
+        }
     }
     static constexpr double kMagic = 6755399441055744.0; // 1.5 * 2^52
     static constexpr double kTwo52 = 4503599627370496.0;
@@ -237,7 +254,9 @@ struct ArithF64 {
     static TB_D double mulmod(double y, tw_t t, const Mod &m) {
         double h = __dmul_rn(y, t.w);
         double l = __fma_rn(y, t.w, -h);
-        double q = __dadd_rn(__fma_rn(y, t.wp, kMagic), -kMagic);
+        double q;
+        if constexpr (COMPACT) q = __dadd_rn(__fma_rn(h, m.pinv, kMagic), -kMagic);
+        else q = __dadd_rn(__fma_rn(y, t.wp, kMagic), -kMagic);
         double r = __fma_rn(-q, m.p, h);
         return __dadd_rn(r, l);
     }
@@ -260,9 +279,11 @@ struct ArithF64 {
         Y = mulmod(d, m.inv1n, m);
     }
 };
+typedef ArithF64T<true> ArithF64;
 
 // The same arithmetic for p < 2^41 (the usual 40-bit CKKS scale primes). A mulmod accepts |y| < 2^51 and returns
-// |r| <= p, and an unreduced sum path doubles per layer, so values stay below 2^50 for 9 layers after a reduction: the
+// |r| < 1.25 p, and an unreduced sum path doubles per layer, so values stay below 320 p < 2^49.4 for 9 layers after a
+// reduction (where the estimate's error is below 0.25, so the last layer's outputs are below p as canon_reduced needs): the
 // inverse transform re-centres only once, at the start of its second-to-last tile round, instead of in every round.
 struct ArithF64S : ArithF64 {
     static constexpr bool kReduceEachInvRound = false;
@@ -275,11 +296,11 @@ struct ArithF64S : ArithF64 {
 // for unreduced growth, so every butterfly re-centres the operand that is not multiplied (|x| <= p/2 after `reduce`):
 // forward outputs are |x +- t| <= 1.25 p < 2^51 (2 p after the one layer per register network that skips it), inverse inputs
 // stay below p (sum re-centred, difference multiplied), 10-11 instead of 8 FP64 instructions per butterfly - still fewer issue cycles than the 23-27 instructions of the integer paths.
-struct ArithF64L : ArithF64 {
+struct ArithF64L : ArithF64T<false> {
     static constexpr bool kReduceEachInvRound = false;
     static constexpr bool kReduceInvMidway = false;
     static TB_D elem from_u64(u64 v, const Mod &m) { // v < 2^52
-        double x = ArithF64::from_u64(v, m);
+        double x = ArithF64T<false>::from_u64(v, m);
         reduce(x, m);
         return x;
     }
@@ -301,6 +322,37 @@ struct ArithF64L : ArithF64 {
         Y = mulmod(d, w, m);
     }
 };
+
+// One output of a forward butterfly (upper = the x - w y side). Used where a CTA recomputes a layer that couples two tiles and
+// keeps only its own tile's output (kernels_ntt.cuh, solo tiles).
+template <class A> TB_D typename A::elem ct_half(typename A::elem X, typename A::elem Y, typename A::tw_t w, const typename A::Mod &m, bool upper) {
+    if constexpr (std::is_same<typename A::elem, double>::value && !std::is_same<A, ArithF64L>::value) {
+        // sign flip on the integer pipe: (-t) = t with bit 63 toggled
+        const u64 t = A::to_bits(A::mulmod(Y, w, m)) ^ ((u64)upper << 63);
+        return __dadd_rn(X, A::from_bits(t));
+    } else {
+        A::ct(X, Y, w, m);
+        return upper ? Y : X;
+    }
+}
+
+// A loader of a round's inputs may be "staged": raw(i) issues the bare global loads of input i, cook(raw[], x[]) turns the K
+// raw inputs of a group into elements. tile_round then requests every input of a group before any of them is used, and the
+// loader's mode branches run once per group instead of between the loads.
+template <class Ld, class = void> struct IsStagedLd : std::false_type {};
+template <class Ld> struct IsStagedLd<Ld, decltype((void)sizeof(typename Ld::Raw))> : std::true_type {};
+
+template <class A, int K, bool PIN, int BLO, class Ld> TB_D void load_group(const Ld &ld, u32 ib, typename A::elem (&x)[K]) {
+    if constexpr (IsStagedLd<Ld>::value) {
+        typename Ld::Raw r[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) r[k] = ld.raw(ib + (PIN ? pad_idx((u32)k << BLO) : ((u32)k << BLO)));
+        ld.cook(r, x);
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; k++) x[k] = ld(ib + (PIN ? pad_idx((u32)k << BLO) : ((u32)k << BLO)));
+    }
+}
 
 // ---- register butterfly networks --------------------------------------------------------------------------------------------
 // 2^RR coefficients held by one thread; w[(1 << u) - 1 + j] is the twiddle of block j of layer u of the network.
@@ -440,15 +492,17 @@ TB_D void tile_round(u32 vt, Ld ld, St st, const void *__restrict__ tw, u32 R, c
         // all G groups of the thread share one twiddle set; two groups in flight at a time
         u32 hi, base0;
         Q::locate(vt, 0, 0, 0, hi, base0);
-#pragma unroll 2
+        // rolled: a fully unrolled transform is ~55 KB of code per policy executed once per warp, and the instruction cache
+        // (32 KB) then stalls the warps of the other resident CTAs (ncu: stall_no_instruction)
+#pragma unroll 1
         for (int e = 0; e < SH; e++) {
             const u32 base = base0 | ((u32)e << Q::TL);
             const u32 ib = PIN ? pad_idx(base) : base, ob = POUT ? pad_idx(base) : base;
             typename A::elem x[K];
+            load_group<A, K, PIN, BLO>(ld, ib, x);
+            if (REDUCE) {
 #pragma unroll
-            for (int k = 0; k < K; k++) {
-                x[k] = ld(ib + (PIN ? pad_idx((u32)k << BLO) : ((u32)k << BLO)));
-                if (REDUCE) A::reduce(x[k], m);
+                for (int k = 0; k < K; k++) A::reduce(x[k], m);
             }
             if constexpr (INVERSE) radix_inv<A, RR, LAST>(x, cur.w[0], m);
             else radix_fwd<A, RR>(x, cur.w[0], m);
@@ -457,21 +511,8 @@ TB_D void tile_round(u32 vt, Ld ld, St st, const void *__restrict__ tw, u32 R, c
         }
     } else {
         constexpr int F = U * SH; // groups in flight
-        constexpr int D = Q::AHEAD, NR = D + 1;
-        W ring[NR];
-        ring[0] = cur;
-#pragma unroll
-        for (int d = 1; d <= D; d++) {
-            if (d < Q::TURNS) ring[d].load(vt, d, tw, R);
-        }
-#pragma unroll(D > 0 ? Q::TURNS : 1)
-        for (int turn = 0; turn < Q::TURNS; turn++) {
-            if constexpr (D > 0) {
-                if (turn + D < Q::TURNS) ring[(turn + D) % NR].load(vt, turn + D, tw, R);
-            } else {
-                if (turn > 0) ring[0].load(vt, turn, tw, R);
-            }
-            const W &wt = ring[D > 0 ? turn % NR : 0];
+        // one turn: the F groups of `turn` with the twiddles wt
+        auto do_turn = [&](int turn, const W &wt) {
             u32 ib[F], ob[F];
             typename A::elem x[F][K];
 #pragma unroll
@@ -485,10 +526,7 @@ TB_D void tile_round(u32 vt, Ld ld, St st, const void *__restrict__ tw, u32 R, c
                 }
             }
 #pragma unroll
-            for (int f = 0; f < F; f++) {
-#pragma unroll
-                for (int k = 0; k < K; k++) x[f][k] = ld(ib[f] + (PIN ? pad_idx((u32)k << BLO) : ((u32)k << BLO)));
-            }
+            for (int f = 0; f < F; f++) load_group<A, K, PIN, BLO>(ld, ib[f], x[f]);
 #pragma unroll
             for (int f = 0; f < F; f++) {
                 if (REDUCE) {
@@ -499,6 +537,24 @@ TB_D void tile_round(u32 vt, Ld ld, St st, const void *__restrict__ tw, u32 R, c
                 else radix_fwd<A, RR>(x[f], wt.w[f / SH], m);
 #pragma unroll
                 for (int k = 0; k < K; k++) st(ob[f] + (POUT ? pad_idx((u32)k << BLO) : ((u32)k << BLO)), x[f][k]);
+            }
+        };
+        if constexpr (Q::AHEAD > 0 && Q::TURNS % 2 == 0) {
+            // software pipeline of depth one over two twiddle sets, unrolled by two turns (a rolled loop keeps the code small)
+            W wa = cur, wb;
+#pragma unroll 1
+            for (int turn = 0; turn < Q::TURNS; turn += 2) {
+                wb.load(vt, turn + 1, tw, R);
+                do_turn(turn, wa);
+                if (turn + 2 < Q::TURNS) wa.load(vt, turn + 2, tw, R);
+                do_turn(turn + 1, wb);
+            }
+        } else {
+            W wa = cur;
+#pragma unroll 1
+            for (int turn = 0; turn < Q::TURNS; turn++) {
+                if (turn > 0) wa.load(vt, turn, tw, R);
+                do_turn(turn, wa);
             }
         }
     }
@@ -529,8 +585,10 @@ template <class A> struct SmSt {
 //               Otherwise the tile holds element bits left by the cluster's scatter stage.
 // The results stay in shared memory as element bits.
 // On the GPU the twiddles of round r+1 are requested before the barrier that ends round r (RoundTw).
-template <class A, int LOGT, bool GLOBAL_IN, class Gld>
-TB_D void tile_ntt_fwd(u64 *sm, Gld gld, const ModDev *md, u32 R) {
+struct NoHook { TB_D void operator()() const {} };
+//   loaded()  : called by every thread once the CTA's global inputs have all arrived (after the barrier of the first round)
+template <class A, int LOGT, bool GLOBAL_IN, class Gld, class Hook = NoHook>
+TB_D void tile_ntt_fwd(u64 *sm, Gld gld, const ModDev *md, u32 R, Hook loaded = Hook()) {
     typedef TilePlan<LOGT> P;
     constexpr int NT = P::NT;
     const typename A::Mod m = A::make(md);
@@ -539,12 +597,15 @@ TB_D void tile_ntt_fwd(u64 *sm, Gld gld, const ModDev *md, u32 R) {
     SmSt<A> ss{sm};
     constexpr int S1 = P::R0, S2 = S1 + P::R1, S3 = S2 + P::R2, S4 = S3 + P::R3;
 #if defined(TROYB_HOST_EMUL)
-    if constexpr (GLOBAL_IN) {
+    if constexpr (GLOBAL_IN && IsStagedLd<Gld>::value) {
+        TB_PHASE(NT, t, (tile_round<A, LOGT, NT, 0, P::R0, false, false, false, false, true>(t, gld, ss, tw, R, m));)
+    } else if constexpr (GLOBAL_IN) {
         auto rl = [&](u32 i) -> typename A::elem { return A::from_u64(gld(i), m); };
         TB_PHASE(NT, t, (tile_round<A, LOGT, NT, 0, P::R0, false, false, false, false, true>(t, rl, ss, tw, R, m));)
     } else {
         TB_PHASE(NT, t, (tile_round<A, LOGT, NT, 0, P::R0, false, false, false, true, true>(t, sl, ss, tw, R, m));)
     }
+    loaded();
     TB_PHASE(NT, t, (tile_round<A, LOGT, NT, S1, P::R1, false, false, false, true, true>(t, sl, ss, tw, R, m));)
     TB_PHASE(NT, t, (tile_round<A, LOGT, NT, S2, P::R2, false, false, false, true, true>(t, sl, ss, tw, R, m));)
     if constexpr (P::R3 > 0) {
@@ -557,7 +618,9 @@ TB_D void tile_ntt_fwd(u64 *sm, Gld gld, const ModDev *md, u32 R) {
     const u32 t = threadIdx.x;
     RoundTw<A, LOGT, NT, 0, P::R0> w0;
     w0.load(t, 0, tw, R);
-    if constexpr (GLOBAL_IN) {
+    if constexpr (GLOBAL_IN && IsStagedLd<Gld>::value) {
+        tile_round<A, LOGT, NT, 0, P::R0, false, false, false, false, true, true>(t, gld, ss, tw, R, m, &w0);
+    } else if constexpr (GLOBAL_IN) {
         auto rl = [&](u32 i) -> typename A::elem { return A::from_u64(gld(i), m); };
         tile_round<A, LOGT, NT, 0, P::R0, false, false, false, false, true, true>(t, rl, ss, tw, R, m, &w0);
     } else {
@@ -566,6 +629,7 @@ TB_D void tile_ntt_fwd(u64 *sm, Gld gld, const ModDev *md, u32 R) {
     RoundTw<A, LOGT, NT, S1, P::R1> w1;
     w1.load(t, 0, tw, R);
     __syncthreads();
+    loaded();
     tile_round<A, LOGT, NT, S1, P::R1, false, false, false, true, true, true>(t, sl, ss, tw, R, m, &w1);
     RoundTw<A, LOGT, NT, S2, P::R2> w2;
     w2.load(t, 0, tw, R);

@@ -36,6 +36,8 @@ _SIGNATURES = {
     "troyb_last_error": (C.c_char_p, []),
     "troyb_initialize": (C.c_int, [C.c_int]),
     "troyb_initialized": (C.c_int, []),
+    "troyb_set_device": (C.c_int, [C.c_int]),
+    "troyb_context_device": (C.c_int, [_vp]),
     "troyb_launch_count": (C.c_uint64, []),
     "troyb_profile_enable": (C.c_int, [C.c_int]),
     "troyb_profile_report": (C.c_int, [C.c_char_p, _sz]),
@@ -119,16 +121,8 @@ _library = None
 
 
 def library():
-    """The product library (CUDA). Raises ImportError when it has not been built."""
+    """The product library (CUDA): always troy_b200/libtroy_b200.so. Raises ImportError when it has not been built."""
     global _library
     if _library is None:
-        # TROYB_LIB (development knob): another CUDA build of the same sources, e.g. an A/B variant under tests/microbench
-        _library = Library(os.environ.get("TROYB_LIB", LIB_PATH))
+        _library = Library(LIB_PATH)
     return _library
-
-
-def _set_library_for_tests(lib):
-    """Test hook: tests/emul swaps in the CPU-emulated build of the same sources to debug index math without a GPU."""
-    global _library
-    prev, _library = _library, lib
-    return prev
