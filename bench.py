@@ -43,6 +43,33 @@ def measured_peaks():
     return 6650.0, "fallback"
 
 
+def bind_to_gpu_numa_node(local, world):
+    """Pin this rank's host threads to the CPUs of the NUMA node its GPU hangs off (and, on a single-node host, to this
+    rank's share of them) so that the pinned staging buffers are allocated and driven next to the GPU. Returns what was done."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local)
+        bdf = f"{getattr(bus, 'pci_domain_id', 0):04x}:{bus.pci_bus_id:02x}:{bus.pci_device_id:02x}.0"
+        node = -1
+        path = f"/sys/bus/pci/devices/{bdf}/numa_node"
+        if os.path.exists(path):
+            node = int(open(path).read().strip())
+        cpus = sorted(os.sched_getaffinity(0))
+        if node >= 0 and os.path.exists(f"/sys/devices/system/node/node{node}/cpulist"):
+            want = set()
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                want.update(range(int(lo), int(hi or lo) + 1))
+            cpus = [c for c in cpus if c in want] or cpus
+        if world > 1 and len(cpus) >= world:  # ranks of one node: disjoint shares of its CPUs
+            share = len(cpus) // world
+            cpus = cpus[local * share:(local + 1) * share]
+        os.sched_setaffinity(0, cpus)
+        return {"pci": bdf, "numa_node": node, "cpus": f"{cpus[0]}-{cpus[-1]}" if cpus else ""}
+    except Exception as e:  # affinity is an optimisation; never fail the bench for it
+        return {"error": str(e)[:120]}
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -241,6 +268,7 @@ def run_ours(args):
     # The batch is cut into chunks that go round-robin over a few streams (one EvaluatorCuda per stream): chunk c's
     # host->device copy, its multiply+relinearize and its device->host copy overlap with those of its neighbours, so the
     # PCIe link (768 MiB per step) and the SMs work at the same time. Every word of every step crosses the link.
+    affinity = bind_to_gpu_numa_node(local, world)  # before the pinned allocations, so that they land on the GPU's node
     a_host = torch.empty(B, 2, L, N, dtype=torch.int64).pin_memory()
     b_host = torch.empty(B, 2, L, N, dtype=torch.int64).pin_memory()
     out_host = torch.empty(B, 2, L, N, dtype=torch.int64).pin_memory()
@@ -277,14 +305,35 @@ def run_ours(args):
         for ln in lanes:
             cur.wait_stream(ln["stream"])
 
+    def step_copy_only():
+        # the same chunks on the same streams with the kernels left out: the ceiling the host link sets for this arm
+        for ci, c0 in enumerate(range(0, B, CH)):
+            nb = min(CH, B - c0)
+            ln = lanes[ci % n_streams]
+            with torch.cuda.stream(ln["stream"]):
+                ln["aw"][:nb, :2].copy_(a_host[c0:c0 + nb], non_blocking=True)
+                ln["bw"][:nb].copy_(b_host[c0:c0 + nb], non_blocking=True)
+                out_host[c0:c0 + nb].copy_(ln["aw"][:nb, :2], non_blocking=True)
+
     for _ in range(2):
         fork()
         step_e2e()
         join()
     e2e_steps = max(2, min(args.steps, 20))  # ~0.5 s: the PCIe arm varies by +-10 % over 5 steps on a shared host
     t_e2e = timed(step_e2e, e2e_steps, fork, join)
-    e2e = {"value": world * B * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * a_host.numel() * 8,
-           "d2h_bytes_per_step": out_host.numel() * 8, "chunk": CH, "streams": n_streams}
+    fork()
+    step_copy_only()
+    join()
+    t_copy = timed(step_copy_only, e2e_steps, fork, join)
+    h2d_b, d2h_b = 2 * a_host.numel() * 8, out_host.numel() * 8
+    e2e = {"value": world * B * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_b,
+           "d2h_bytes_per_step": d2h_b, "chunk": CH, "streams": n_streams,
+           "copy_only_ops_per_s": world * B * e2e_steps / t_copy,
+           "frac_of_copy_only": t_copy / t_e2e,
+           "h2d_gbs_per_rank": h2d_b * e2e_steps / t_e2e / 1e9, "d2h_gbs_per_rank": d2h_b * e2e_steps / t_e2e / 1e9,
+           "copy_only_h2d_gbs_per_rank": h2d_b * e2e_steps / t_copy / 1e9,
+           "limiter": "pinned host<->device copy bandwidth per rank (6 MiB cross the link per operation; no collective)",
+           "cpu_affinity": affinity}
     if rank == 0 and world == 1:
         # the results that came back over the link are the device path's results
         step()
@@ -320,6 +369,62 @@ def run_ours(args):
     t_nf = timed(ntt_f, extra_steps)
     t_ni = timed(ntt_i, extra_steps)
     limbs = ntt_polys * L
+
+    # ---- BASELINE config 2: the standalone batched NTT / INTT sweep, N = 4096 .. 65536 x {1, 8, 32} limbs of 60-bit primes,
+    # in place on at least 512 MiB of polynomials (> L2) per launch
+    ntt_sweep = None
+    if world == 1 and not args.no_sweep:
+        ntt_sweep = []
+        for n_ in (4096, 8192, 16384, 32768, 65536):
+            for l_ in (1, 8, 32):
+                qs = tb.CoeffModulus.Create(n_, [60] * (l_ + 1))
+                ps = tb.EncryptionParameters(tb.SchemeType.ckks)
+                ps.set_poly_modulus_degree(n_)
+                ps.set_coeff_modulus(qs)
+                cs = tb.SEALContextCuda(ps, expand_mod_chain=False)
+                polys = max(1, -(-(512 << 20) // (l_ * n_ * 8)))
+                sbuf = torch.randint(0, 1 << 59, (polys, l_, n_), generator=g, device=dev, dtype=torch.int64)
+
+                def sw_f():
+                    lib.call("troyb_ntt_forward", C.c_void_p(cs.h), 0, C.c_void_p(sbuf.data_ptr()), polys, C.c_void_p(stream))
+
+                def sw_i():
+                    lib.call("troyb_ntt_inverse", C.c_void_p(cs.h), 0, C.c_void_p(sbuf.data_ptr()), polys, C.c_void_p(stream))
+
+                for _ in range(2):
+                    sw_f()
+                    sw_i()
+                tf_, ti_ = timed(sw_f, 5), timed(sw_i, 5)
+                per = polys * l_ * 5
+                ntt_sweep.append({"n": n_, "limbs": l_, "bits": 60, "polys": polys,
+                                  "fwd_Mps": round(per / tf_ / 1e6, 3), "inv_Mps": round(per / ti_ / 1e6, 3),
+                                  "fwd_frac": round(per / tf_ * 16 * n_ / 1e9 / hbm_peak, 4),
+                                  "inv_frac": round(per / ti_ * 16 * n_ / 1e9 / hbm_peak, 4)})
+                del sbuf, cs
+
+    # ---- latency of ONE multiply + relinearize (batch 1) through the same API: call to completed result, default-free stream
+    one_a = tb.CiphertextCuda.from_device(ctx, a_work.data_ptr(), 1, 2, 0, True, SCALE, capacity=3)
+    one_src = tb.CiphertextCuda.from_device(ctx, a_in.data_ptr(), 1, 2, 0, True, SCALE)
+    one_b = tb.CiphertextCuda.from_device(ctx, b_in.data_ptr(), 1, 2, 0, True, SCALE)
+
+    def one_op():
+        ev.multiply(one_src, one_b, one_a)
+        ev.relinearize_inplace(one_a, rlk)
+
+    for _ in range(10):
+        one_op()
+    torch.cuda.synchronize()
+    lat = []
+    for _ in range(50):
+        t0 = time.perf_counter()
+        one_op()
+        torch.cuda.synchronize()
+        lat.append((time.perf_counter() - t0) * 1e6)
+    # the device side alone: 50 operations back to back between two events
+    t_dev1 = timed(one_op, 50) / 50 * 1e6
+    latency = {"latency_us_batch1": statistics.median(lat), "device_us_batch1": t_dev1,
+               "what": "multiply + relinearize of one ciphertext pair, N=16384 L=8: host call to synchronised result (median of 50) "
+                       "and device time per operation when issued back to back"}
 
     # ---- the HE matmul of BASELINE config 5 (MatmulHelper::matmul, app/LinearHelperCKKS.cuh:225-249) at this config's
     # shape: y[b][j] = sum_i x[b][i] * W[i][j], 16 x 8 ciphertexts times 8 x 8 plaintexts, as ONE launch, and the same
@@ -373,8 +478,7 @@ def run_ours(args):
             traffic = json.load(f).get(dom["kernel"])
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom_bytes / dom_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": dom_bytes / dom_s / 1e9 / hbm_peak, "traffic": traffic, "peak_source": peak_kind,
-                "share_of_step": dom["share"],
-                "note": "NTT butterflies are bound by the integer-multiply pipe, not HBM (DESIGN.md §roofline)"}
+                "share_of_step": dom["share"]}
 
     if rank != 0:
         if dist is not None:
@@ -452,6 +556,8 @@ def run_ours(args):
         "matmul": {"multiply_plain_accumulate_per_s": world * mm_terms * extra_steps / t_mm, "ms": t_mm / extra_steps * 1e3,
                    "shape": f"{MB_}x{MI_} ciphertexts times {MI_}x{MJ_} plaintexts, one launch",
                    "gbs": mm_bytes * extra_steps / t_mm / 1e9, "frac_of_hbm_roofline": mm_bytes * extra_steps / t_mm / 1e9 / hbm_peak},
+        "ntt_sweep": ntt_sweep,
+        "latency": latency,
         "reference_cuda_path": ref_cuda,
         "seal_cpu_baseline": seal,
         "kernels": kernels,
@@ -474,6 +580,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="ciphertext pairs per GPU per step")
     ap.add_argument("--ref-reps", type=int, default=4, help="reference arm: ops per thread per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the config-2 NTT sweep (development runs)")
     ap.add_argument("--e2e-chunk", type=int, default=16, help="end-to-end arm: ciphertext pairs per chunk")
     ap.add_argument("--e2e-streams", type=int, default=3, help="end-to-end arm: streams the chunks rotate over")
     args = ap.parse_args()

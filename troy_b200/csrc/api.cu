@@ -154,8 +154,16 @@ void ntt_plain(const Context *ctx, bool inverse, const LimbMap &map, u32 L, cons
 // One GPU runs partial over all digits and then finish. With the digits of one key-switch sharded over several GPUs
 // (troy_b200/distributed.py) every GPU runs partial on its digits, the products are summed across GPUs (the only
 // exchange of the path), and finish first reduces the sums modulo each prime.
+// Where the key inner products live. The default is the reference's t_poly_prod layout [batch][2][L+1][N]; `rows` is
+// [L+1 output moduli][batch][2][N], in which the rows a GPU owns are one contiguous block (reduce-scatter over NVLink).
+struct ProdLayout {
+    u64 batch_stride, poly_stride, limb_stride; // words
+    static ProdLayout standard(u32 Lp, u64 N) { return ProdLayout{2ull * Lp * N, (u64)Lp * N, N}; }
+    static ProdLayout rows(u32 batch, u64 N) { return ProdLayout{2ull * N, N, 2ull * batch * N}; }
+};
+
 void switch_key_partial(Context *ctx, int level, const u64 *target, u64 target_stride, const u64 *key, u32 digit0, u32 nd,
-                        u64 *prod, u32 batch, cudaStream_t s) {
+                        u64 *prod, u32 batch, cudaStream_t s, const ProdLayout *layout = nullptr) {
     if (!ctx->has_special) throw std::logic_error("keyswitching is not supported by the context");
     const u32 L = (u32)ctx->levels[level].L;
     const u64 N = ctx->N;
@@ -163,6 +171,7 @@ void switch_key_partial(Context *ctx, int level, const u64 *target, u64 target_s
     const u32 key_limbs = (u32)ctx->Ltop + 1;
     const bool ckks = ctx->scheme == SCHEME_CKKS;
     if (nd == 0 || digit0 + nd > L) throw std::invalid_argument("digit range is not valid");
+    const ProdLayout pl = layout ? *layout : ProdLayout::standard(Lp, N);
     LimbMap kmap = ctx->map_prefix(L);
     kmap.idx[L] = (uint8_t)ctx->pool_special;
     LimbMap dmap{}; // moduli of the digits in play
@@ -221,7 +230,10 @@ void switch_key_partial(Context *ctx, int level, const u64 *target, u64 target_s
                     k.accumulate = g0 > 0;
                     k.D = D.p;
                     k.key = key;
-                    k.prod = prod + (u64)b0 * 2 * Lp * N;
+                    k.prod = prod + (u64)b0 * pl.batch_stride;
+                    k.prod_batch_stride = pl.batch_stride;
+                    k.prod_poly_stride = pl.poly_stride;
+                    k.prod_limb_stride = pl.limb_stride;
                     k.pass = ckks ? tgt : nullptr;
                     k.pass_stride = target_stride;
                     ck(launch_cta(k, grid, decltype(k)::smem_bytes(), s));
@@ -250,7 +262,10 @@ void switch_key_partial(Context *ctx, int level, const u64 *target, u64 target_s
             k.total = (u64)nb * Lp * (N / 2);
             k.D = D.p;
             k.key = key;
-            k.prod = prod + (u64)b0 * 2 * Lp * N;
+            k.prod = prod + (u64)b0 * pl.batch_stride;
+            k.prod_batch_stride = pl.batch_stride;
+            k.prod_poly_stride = pl.poly_stride;
+            k.prod_limb_stride = pl.limb_stride;
             k.pass = ckks ? tgt : nullptr;
             k.pass_stride = target_stride;
             ck(launch_cta(k, grid_for(k.total, KsInnerProduct::kThreads), 0, s));
@@ -258,70 +273,107 @@ void switch_key_partial(Context *ctx, int level, const u64 *target, u64 target_s
     }
 }
 
+// The second half of a key switch in three phases, each over a range of rows (output moduli) so that GPUs that own
+// different rows can run them side by side (troy_b200/distributed.py):
+//   reduce  : rows [r0, r1) hold sums of several GPUs' canonical partial products: reduce modulo each row's prime
+//   special : INTT of the special-prime row (+ half) -> sp [batch][2][N]                       (:1299-1331)
+//   moddown : for the data limbs [j0, j1): mod-down tail fused into the last transform, added into ct   (:1333-1376)
+void switch_key_reduce_rows(Context *ctx, int level, u64 *prod, const ProdLayout &pl, u32 r0, u32 r1, u32 batch, cudaStream_t s) {
+    const u32 L = (u32)ctx->levels[level].L;
+    const u64 N = ctx->N;
+    LimbMap kmap = ctx->map_prefix(L);
+    kmap.idx[L] = (uint8_t)ctx->pool_special;
+    EltAddSub k{};
+    k.op = 4;
+    k.logN = ctx->logN;
+    k.mods = ctx->d_mods;
+    if (pl.limb_stride == N) { // standard layout: every row of every ciphertext in one pass
+        if (r0 != 0 || r1 != L + 1) throw std::invalid_argument("row ranges need the row-major product layout");
+        k.map = kmap;
+        k.n_limbs = L + 1;
+        k.total = (u64)batch * 2 * (L + 1) * N;
+        k.a = k.b = k.out = prod;
+    } else {
+        for (u32 r = r0; r < r1; r++) k.map.idx[r - r0] = kmap.idx[r];
+        k.n_limbs = r1 - r0;
+        k.row_words = pl.limb_stride;
+        k.total = (u64)(r1 - r0) * pl.limb_stride;
+        k.a = k.b = k.out = prod + (u64)r0 * pl.limb_stride;
+    }
+    ck(launch_cta(k, grid_for(k.total, EltAddSub::kThreads), 0, s));
+}
+
+void switch_key_special(Context *ctx, int level, const u64 *prod, const ProdLayout &pl, u64 *sp, u32 batch, cudaStream_t s) {
+    const u32 L = (u32)ctx->levels[level].L;
+    LimbMap kmap = ctx->map_prefix(L);
+    kmap.idx[L] = (uint8_t)ctx->pool_special;
+    NttArgs a{};
+    a.mode = INV_ADD_HALF;
+    a.map = kmap;
+    a.L = L;
+    a.K = 2;
+    a.src = prod;
+    a.src_offset = (u64)L * pl.limb_stride;
+    a.src_unit_stride = pl.batch_stride;
+    a.src_poly_stride = pl.poly_stride;
+    a.dst = sp;
+    a.drop = ctx->key_drop;
+    a.add_half = ctx->scheme != SCHEME_BGV;
+    a.scheme = ctx->scheme;
+    run_inv(ctx, a, batch * 2, s);
+}
+
 // ct_src (optional): the tail writes ct = ct_src + result for the first ct_src_polys polys and ct = result for the rest,
 // instead of ct += result (applyGalois: permuted c0 in scratch, c1 from zero; saves a copy and a memset pass over ct).
+void switch_key_moddown(Context *ctx, int level, u64 *ct, u64 ct_stride, const u64 *prod, const ProdLayout &pl, const u64 *sp,
+                        u32 j0, u32 j1, u32 batch, cudaStream_t s, const u64 *ct_src = nullptr, u64 ct_src_stride = 0,
+                        u32 ct_src_polys = 0) {
+    const u32 L = (u32)ctx->levels[level].L;
+    const bool ckks = ctx->scheme == SCHEME_CKKS;
+    if (j1 > L) j1 = L;
+    if (j0 >= j1) return;
+    LimbMap kmap = ctx->map_prefix(L);
+    kmap.idx[L] = (uint8_t)ctx->pool_special;
+    NttArgs a{};
+    a.mode = ckks ? FWD_MODDOWN : INV_COMBINE;
+    a.map = kmap;
+    a.L = L;
+    a.K = 2;
+    a.aux0 = prod;
+    a.acc_batch_stride = pl.batch_stride;
+    a.acc_poly_stride = pl.poly_stride;
+    a.acc_limb_stride = pl.limb_stride;
+    a.aux1 = sp;
+    a.ct = ct;
+    a.ct_batch_stride = ct_stride;
+    a.ct_poly_stride = (u64)L * ctx->N;
+    a.ct_src = ct_src;
+    a.ct_src_batch_stride = ct_src_stride;
+    a.ct_src_polys = ct_src_polys;
+    a.drop = ctx->key_drop;
+    a.scheme = ctx->scheme;
+    set_order(ctx, a, L);
+    if (j0 != 0 || j1 != L) { // a subset of the limbs: the launch's ranks are the owned limbs only
+        u32 n = 0;
+        uint8_t keep[kMaxLimbs];
+        for (u32 r = 0; r < L; r++)
+            if (a.order[r] >= j0 && a.order[r] < j1) keep[n++] = a.order[r];
+        for (u32 r = 0; r < n; r++) a.order[r] = keep[r];
+        a.n_rank = n;
+    }
+    if (ckks) run_fwd(ctx, a, batch * 2 * a.n_rank, s);
+    else run_inv(ctx, a, batch * 2 * a.n_rank, s);
+}
+
 void switch_key_finish(Context *ctx, int level, u64 *ct, u64 ct_stride, u64 *prod, bool reduce_first, u32 batch, cudaStream_t s,
                        const u64 *ct_src = nullptr, u64 ct_src_stride = 0, u32 ct_src_polys = 0) {
     if (!ctx->has_special) throw std::logic_error("keyswitching is not supported by the context");
     const u32 L = (u32)ctx->levels[level].L;
-    const u64 N = ctx->N;
-    const u32 Lp = L + 1;
-    const bool ckks = ctx->scheme == SCHEME_CKKS;
-    LimbMap kmap = ctx->map_prefix(L);
-    kmap.idx[L] = (uint8_t)ctx->pool_special;
-    Scratch sp((size_t)batch * 2 * N, s);
-    if (reduce_first) {
-        // sums of several GPUs' canonical partial products: reduce modulo each prime before the tail
-        EltAddSub k{};
-        k.op = 4;
-        k.logN = ctx->logN;
-        k.mods = ctx->d_mods;
-        k.map = kmap;
-        k.n_limbs = Lp;
-        k.total = (u64)batch * 2 * Lp * N;
-        k.a = prod;
-        k.b = prod;
-        k.out = prod;
-        ck(launch_cta(k, grid_for(k.total, EltAddSub::kThreads), 0, s));
-    }
-    {
-        NttArgs a{};
-        a.mode = INV_ADD_HALF;
-        a.map = kmap;
-        a.L = L;
-        a.K = 2;
-        a.src = prod;
-        a.src_offset = (u64)L * N;
-        a.src_unit_stride = 2ull * Lp * N;
-        a.src_poly_stride = (u64)Lp * N;
-        a.dst = sp.p;
-        a.drop = ctx->key_drop;
-        a.add_half = ctx->scheme != SCHEME_BGV;
-        a.scheme = ctx->scheme;
-        run_inv(ctx, a, batch * 2, s);
-    }
-    {
-        NttArgs a{};
-        a.mode = ckks ? FWD_MODDOWN : INV_COMBINE;
-        a.map = kmap;
-        a.L = L;
-        a.K = 2;
-        a.aux0 = prod;
-        a.acc_batch_stride = 2ull * Lp * N;
-        a.acc_poly_stride = (u64)Lp * N;
-        a.aux1 = sp.p;
-        a.ct = ct;
-        a.ct_batch_stride = ct_stride;
-        a.ct_poly_stride = (u64)L * N;
-        a.ct_src = ct_src;
-        a.ct_src_batch_stride = ct_src_stride;
-        a.ct_src_polys = ct_src_polys;
-        a.drop = ctx->key_drop;
-        a.scheme = ctx->scheme;
-        set_order(ctx, a, L);
-        if (ckks) run_fwd(ctx, a, batch * 2 * L, s);
-        else run_inv(ctx, a, batch * 2 * L, s);
-    }
+    const ProdLayout pl = ProdLayout::standard(L + 1, ctx->N);
+    Scratch sp((size_t)batch * 2 * ctx->N, s);
+    if (reduce_first) switch_key_reduce_rows(ctx, level, prod, pl, 0, L + 1, batch, s);
+    switch_key_special(ctx, level, prod, pl, sp.p, batch, s);
+    switch_key_moddown(ctx, level, ct, ct_stride, prod, pl, sp.p, 0, L, batch, s, ct_src, ct_src_stride, ct_src_polys);
 }
 
 void switch_key_impl(Context *ctx, int level, u64 *ct, u64 ct_stride, const u64 *target, u64 target_stride, const u64 *key,
@@ -1024,6 +1076,68 @@ int troyb_switch_key_finish(troyb_context *ctx, int level, uint64_t *d_ct, size_
     check_aligned(d_ct, "ct");
     check_aligned(d_prod, "prod");
     switch_key_finish(c, level, d_ct, ct_stride, d_prod, reduce_first != 0, (u32)batch, S(stream));
+    API_END
+}
+
+int troyb_switch_key_partial_rows(troyb_context *ctx, int level, const uint64_t *d_target, size_t target_stride,
+                                  const uint64_t *d_key, int digit_begin, int digit_end, uint64_t *d_rows, size_t batch, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const u32 L = (u32)level_limbs(c, level);
+    if (level < 0) throw std::invalid_argument("level");
+    if (!d_target || !d_key || !d_rows) throw std::invalid_argument("null argument");
+    if (digit_begin < 0 || digit_end <= digit_begin || (u32)digit_end > L) throw std::invalid_argument("digit range is not valid");
+    check_batch_stride(target_stride, (u64)L * c->N, "target");
+    check_aligned(d_target, "target");
+    check_aligned(d_key, "key");
+    check_aligned(d_rows, "rows");
+    const ProdLayout pl = ProdLayout::rows((u32)batch, c->N);
+    switch_key_partial(c, level, d_target, target_stride, d_key, (u32)digit_begin, (u32)(digit_end - digit_begin), d_rows, (u32)batch,
+                       S(stream), &pl);
+    API_END
+}
+
+int troyb_switch_key_reduce_rows(troyb_context *ctx, int level, uint64_t *d_rows, int row_begin, int row_end, size_t batch,
+                                 void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const u32 L = (u32)level_limbs(c, level);
+    if (level < 0) throw std::invalid_argument("level");
+    if (!d_rows) throw std::invalid_argument("null argument");
+    if (row_begin < 0 || row_end < row_begin || (u32)row_end > L + 1) throw std::invalid_argument("row range is not valid");
+    if (row_end > row_begin)
+        switch_key_reduce_rows(c, level, d_rows, ProdLayout::rows((u32)batch, c->N), (u32)row_begin, (u32)row_end, (u32)batch, S(stream));
+    API_END
+}
+
+int troyb_switch_key_special_row(troyb_context *ctx, int level, const uint64_t *d_rows, uint64_t *d_sp, size_t batch, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    level_limbs(c, level);
+    if (level < 0) throw std::invalid_argument("level");
+    if (!d_rows || !d_sp) throw std::invalid_argument("null argument");
+    if (!c->has_special) throw std::logic_error("keyswitching is not supported by the context");
+    switch_key_special(c, level, d_rows, ProdLayout::rows((u32)batch, c->N), d_sp, (u32)batch, S(stream));
+    API_END
+}
+
+int troyb_switch_key_moddown_rows(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_stride, const uint64_t *d_rows,
+                                  const uint64_t *d_sp, int limb_begin, int limb_end, size_t batch, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const u32 L = (u32)level_limbs(c, level);
+    if (level < 0) throw std::invalid_argument("level");
+    if (!d_ct || !d_rows || !d_sp) throw std::invalid_argument("null argument");
+    if (limb_begin < 0 || limb_end < limb_begin || (u32)limb_end > L + 1) throw std::invalid_argument("limb range is not valid");
+    check_batch_stride(ct_stride, 2ull * L * c->N, "ct");
+    check_aligned(d_ct, "ct");
+    if (!c->has_special) throw std::logic_error("keyswitching is not supported by the context");
+    switch_key_moddown(c, level, d_ct, ct_stride, d_rows, ProdLayout::rows((u32)batch, c->N), d_sp, (u32)limb_begin, (u32)limb_end,
+                       (u32)batch, S(stream));
     API_END
 }
 

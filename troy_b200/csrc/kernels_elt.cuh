@@ -31,11 +31,12 @@ struct EltAddSub {
     u64 total; // words
     const u64 *a, *b;
     u64 *out;
+    u64 row_words; // 0: limb = (word / N) % n_limbs (ciphertext layout); else limb = word / row_words (row-major buffers)
     TB_D void operator()(u32 bid, u64 *) const {
         TB_PHASE(kThreads, t, {
             u64 idx = (u64)bid * kThreads + t;
             if (idx < total) {
-                u32 limb = (u32)((idx >> logN) % n_limbs);
+                u32 limb = row_words ? (u32)(idx / row_words) : (u32)((idx >> logN) % n_limbs);
                 const ModDev &m = mods[map.idx[limb]];
                 u64 p = m.p;
                 u64 x = a[idx];
@@ -228,6 +229,7 @@ struct KsInnerProduct {
     const u64 *D;
     const u64 *key;
     u64 *prod;
+    u64 prod_batch_stride, prod_poly_stride, prod_limb_stride; // words: [batch][2][L+1][N] by default, or rows [L+1][batch][2][N]
     const u64 *pass;      // CKKS: the NTT-form target [batch][L][N]; its limb i IS digit i under modulus i (no transform)
     u64 pass_stride;
     TB_D void operator()(u32 bid, u64 *) const {
@@ -273,14 +275,14 @@ struct KsInnerProduct {
                         a0.fold(); a1.fold(); a2.fold(); a3.fold();
                     }
                 }
-                u64 *po = prod + (b * 2 * (L + 1) + i) * N + c;
+                u64 *po = prod + b * prod_batch_stride + (u64)i * prod_limb_stride + c;
                 ulonglong2 r0, r1;
                 r0.x = barrett128(a0.lo, a0.hi, m.p, m.ratio0, m.ratio1);
                 r0.y = barrett128(a1.lo, a1.hi, m.p, m.ratio0, m.ratio1);
                 r1.x = barrett128(a2.lo, a2.hi, m.p, m.ratio0, m.ratio1);
                 r1.y = barrett128(a3.lo, a3.hi, m.p, m.ratio0, m.ratio1);
                 *reinterpret_cast<ulonglong2 *>(po) = r0;
-                *reinterpret_cast<ulonglong2 *>(po + (u64)(L + 1) * N) = r1;
+                *reinterpret_cast<ulonglong2 *>(po + prod_poly_stride) = r1;
             }
         })
     }
@@ -308,6 +310,7 @@ template <int ND> struct KsInnerProductStaged {
     const u64 *D;
     const u64 *key;
     u64 *prod;
+    u64 prod_batch_stride, prod_poly_stride, prod_limb_stride; // see KsInnerProduct
     const u64 *pass;
     u64 pass_stride;
     static size_t smem_bytes() { return (size_t)ND * 2 * kCoeffs * sizeof(u64); }
@@ -336,7 +339,7 @@ template <int ND> struct KsInnerProductStaged {
             const u64 d_stride = (u64)(L + 1) * d_rows * N;
             const u64 *d = D + (((u64)(bg * bc) * (L + 1) + i) * d_rows + d_row0) * N + c;
             const u64 *ps = pass + (u64)(bg * bc) * pass_stride + (u64)i * N + c;
-            u64 *po = prod + ((u64)(bg * bc) * 2 * (L + 1) + i) * N + c;
+            u64 *po = prod + (u64)(bg * bc) * prod_batch_stride + (u64)i * prod_limb_stride + c;
             // Register-rotating pipeline over the batch elements of the CTA: row j of element b + 1 is requested as soon
             // as row j of element b has been copied out of its registers, so ND 16-byte loads per thread stay in flight
             // for a whole iteration (the kernel is bound by HBM latency x bytes in flight otherwise) with ONE set of row
@@ -349,12 +352,12 @@ template <int ND> struct KsInnerProductStaged {
             }
             xp.x = 0; xp.y = 0;
             if (bg * bc < b_end && jpass != 0xFFFFFFFFu) xp = *reinterpret_cast<const ulonglong2 *>(ps);
-            for (u32 b = bg * bc; b < b_end; b++, d += d_stride, ps += pass_stride, po += 2ull * (L + 1) * N) {
+            for (u32 b = bg * bc; b < b_end; b++, d += d_stride, ps += pass_stride, po += prod_batch_stride) {
                 const bool more = b + 1 < b_end;
                 ulonglong2 old0, old1;
                 if (accumulate) {
                     old0 = *reinterpret_cast<const ulonglong2 *>(po);
-                    old1 = *reinterpret_cast<const ulonglong2 *>(po + (u64)(L + 1) * N);
+                    old1 = *reinterpret_cast<const ulonglong2 *>(po + prod_poly_stride);
                 }
                 ColumnAcc a0, a1, a2, a3;
                 _Pragma("unroll") for (u32 j = 0; j < ND; j++) {
@@ -397,7 +400,7 @@ template <int ND> struct KsInnerProductStaged {
                     q1.x = addmod(q1.x, old1.x, p); q1.y = addmod(q1.y, old1.y, p);
                 }
                 *reinterpret_cast<ulonglong2 *>(po) = q0;
-                *reinterpret_cast<ulonglong2 *>(po + (u64)(L + 1) * N) = q1;
+                *reinterpret_cast<ulonglong2 *>(po + prod_poly_stride) = q1;
             }
         })
     }

@@ -49,6 +49,7 @@ struct NttArgs {
     u64 aux0_batch_stride;
     u64 acc_poly_stride;  // words between polys in aux0
     u64 acc_batch_stride;
+    u64 acc_limb_stride;  // words between limbs in aux0 (0 = N: [batch][2][L+1][N]; rows [L+1][batch][2][N] otherwise)
     u64 ct_poly_stride;
     u64 ct_batch_stride;
     u64 dst_poly_stride;
@@ -196,7 +197,7 @@ template <int LOGT> TB_D NttUnit resolve_unit(const NttArgs &a, u32 bid) {
         u.unit = bk * a.L + j;
         u.md = a.mods + a.map.idx[j];
         u.sp = a.aux1 + (u64)bk * N;
-        u.acc = a.aux0 + (u64)b * a.acc_batch_stride + (u64)k * a.acc_poly_stride + (u64)j * N;
+        u.acc = a.aux0 + (u64)b * a.acc_batch_stride + (u64)k * a.acc_poly_stride + (u64)j * (a.acc_limb_stride ? a.acc_limb_stride : N);
         u.ct = a.ct ? a.ct + (u64)b * a.ct_batch_stride + (u64)k * a.ct_poly_stride + (u64)j * N : nullptr;
         if (a.ct_src == nullptr) u.ct_in = u.ct;
         else u.ct_in = k < a.ct_src_polys ? a.ct_src + (u64)b * a.ct_src_batch_stride + (u64)k * a.ct_poly_stride + (u64)j * N : nullptr;

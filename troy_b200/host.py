@@ -69,11 +69,19 @@ class PlainModulus:
 
 
 class DeviceArray:
-    """Owning device buffer of uint64 words (DeviceArray<uint64_t>, src/utils/devicearray.cuh:90-200)."""
+    """Owning device buffer of uint64 words (DeviceArray<uint64_t>, src/utils/devicearray.cuh:90-200).
 
-    def __init__(self, words, stream=None):
+    Stream discipline: the buffer is allocated on ``stream`` (stream-ordered allocator) and released on the stream that used
+    it LAST (``self.stream``; ``EvaluatorCuda`` re-tags every buffer it reads or writes with its own stream), so that the free
+    is ordered behind the kernels still reading it. ``device`` is the CUDA device the buffer lives on (None: the calling
+    thread's current device)."""
+
+    def __init__(self, words, stream=None, device=None):
         self.words = int(words)
         self.stream = stream
+        self.device = device
+        if device is not None:
+            _L().call("troyb_set_device", int(device))
         p = C.c_void_p()
         _L().call("troyb_malloc", C.byref(p), self.words * 8, _vp(stream))
         self.ptr = p.value
@@ -81,6 +89,8 @@ class DeviceArray:
     def __del__(self):
         try:
             if getattr(self, "ptr", None):
+                if self.device is not None:
+                    _L().cdll.troyb_set_device(int(self.device))
                 _L().cdll.troyb_free(_vp(self.ptr), _vp(self.stream))
                 self.ptr = None
         except Exception:
@@ -89,10 +99,15 @@ class DeviceArray:
     def at(self, word_offset):
         return self.ptr + 8 * int(word_offset)
 
+    def _use_device(self):
+        if self.device is not None:
+            _L().call("troyb_set_device", int(self.device))
+
     def upload(self, arr, word_offset=0):
         a = np.ascontiguousarray(arr, dtype=np.uint64)
         if a.size + word_offset > self.words:
             raise TroyInvalidArgument("upload larger than buffer")
+        self._use_device()
         _L().call("troyb_copy_to_device", _vp(self.at(word_offset)), a.ctypes.data_as(C.c_void_p), a.size * 8,
                   _vp(self.stream))
         _L().call("troyb_stream_synchronize", _vp(self.stream))
@@ -100,6 +115,7 @@ class DeviceArray:
     def download(self, words=None, word_offset=0):
         n = self.words - word_offset if words is None else int(words)
         out = np.empty(n, dtype=np.uint64)
+        self._use_device()
         _L().call("troyb_copy_to_host", out.ctypes.data_as(C.c_void_p), _vp(self.at(word_offset)), n * 8, _vp(self.stream))
         return out
 
@@ -109,7 +125,7 @@ class ExternalArray:
     used to run the evaluator directly on torch tensors."""
 
     def __init__(self, ptr, words):
-        self.ptr, self.words, self.stream = int(ptr), int(words), None
+        self.ptr, self.words, self.stream, self.device = int(ptr), int(words), None, None
 
     def at(self, word_offset):
         return self.ptr + 8 * int(word_offset)
@@ -154,6 +170,11 @@ class SEALContextCuda:
         self.scheme = parms.scheme
         self.n = parms.poly_modulus_degree
         self.num_levels = _L().cdll.troyb_context_num_levels(_vp(self.h))
+        self.device = _L().cdll.troyb_context_device(_vp(self.h))
+
+    def alloc(self, words, stream=None):
+        """Device words on this context's device, allocated in the order of ``stream``."""
+        return DeviceArray(words, stream, self.device)
 
     def __del__(self):
         try:
@@ -210,7 +231,7 @@ class CiphertextCuda:
     """src/ciphertext_cuda.cuh:12-268: metadata + device words ``[batch][poly][limb][coeff]``."""
 
     def __init__(self, context, level=0, size=2, is_ntt_form=False, scale=1.0, correction_factor=1, batch=1,
-                 capacity=None, data=None):
+                 capacity=None, data=None, stream=None):
         self.context = context
         self.parms_id = int(level)
         self.size = int(size)
@@ -220,7 +241,7 @@ class CiphertextCuda:
         self.batch = int(batch)
         self.limbs = context.level_limbs(level)
         self.capacity = max(int(capacity or 0), self.size)
-        self.data = data if data is not None else DeviceArray(self.batch * self.capacity * self.limbs * context.n)
+        self.data = data if data is not None else context.alloc(self.batch * self.capacity * self.limbs * context.n, stream)
 
     # -- layout
     @property
@@ -262,34 +283,46 @@ class CiphertextCuda:
         return cls(context, level, size, is_ntt_form, scale, correction_factor, batch=batch, capacity=cap,
                    data=ExternalArray(ptr, words))
 
+    @property
+    def stream(self):
+        """the stream that last produced or consumed the words (see DeviceArray)"""
+        return self.data.stream
+
     def to_host(self):
+        """Copies on the stream that last touched the words and waits for it."""
         out = np.empty((self.batch, self.size, self.limbs, self.context.n), dtype=np.uint64)
+        _L().call("troyb_set_device", int(self.context.device))
         for b in range(self.batch):
             buf = np.empty(self.size * self.poly_words, dtype=np.uint64)
-            _L().call("troyb_copy_to_host", buf.ctypes.data_as(C.c_void_p), _vp(self.ptr(0, b)), buf.size * 8, _vp(None))
+            _L().call("troyb_copy_to_host", buf.ctypes.data_as(C.c_void_p), _vp(self.ptr(0, b)), buf.size * 8, _vp(self.stream))
             out[b] = buf.reshape(self.size, self.limbs, self.context.n)
         return out
 
-    def clone(self):
+    def clone(self, stream=None):
+        """A copy made in the order of ``stream`` (default: the stream that last touched this ciphertext)."""
+        s = self.stream if stream is None else stream
         c = CiphertextCuda(self.context, self.parms_id, self.size, self.is_ntt_form, self.scale, self.correction_factor,
-                           self.batch, self.capacity)
-        _L().call("troyb_copy_on_device", _vp(c.data.ptr), _vp(self.data.ptr), self.batch * self.stride * 8, _vp(None))
+                           self.batch, self.capacity, stream=s)
+        _L().call("troyb_copy_on_device", _vp(c.data.ptr), _vp(self.data.ptr), self.batch * self.stride * 8, _vp(s))
         return c
 
-    def reserve(self, capacity):
-        """src/ciphertext_cuda.cuh:68-152: grow the per-ciphertext capacity, preserving contents."""
+    def reserve(self, capacity, stream=None):
+        """src/ciphertext_cuda.cuh:68-152: grow the per-ciphertext capacity, preserving contents (in the order of ``stream``)."""
         if capacity <= self.capacity:
             return
-        new = DeviceArray(self.batch * capacity * self.poly_words)
+        s = self.stream if stream is None else stream
+        new = self.context.alloc(self.batch * capacity * self.poly_words, s)
         for b in range(self.batch):
             _L().call("troyb_copy_on_device", _vp(new.at(b * capacity * self.poly_words)), _vp(self.ptr(0, b)),
-                      self.size * self.poly_words * 8, _vp(None))
+                      self.size * self.poly_words * 8, _vp(s))
+        if isinstance(self.data, DeviceArray):
+            self.data.stream = s  # the old words are released behind the copies that read them
         self.data, self.capacity = new, capacity
 
-    def resize(self, size):
+    def resize(self, size, stream=None):
         if size < 2 and size != 0:
             raise TroyInvalidArgument("invalid size")
-        self.reserve(size)
+        self.reserve(size, stream)
         self.size = size
 
 
@@ -301,7 +334,7 @@ class PlaintextCuda:
 
     def __init__(self, context, coeff_count, parms_id=None, scale=1.0, batch=1, data=None):
         self.context, self.coeff_count, self.parms_id, self.scale, self.batch = context, int(coeff_count), parms_id, scale, batch
-        self.data = data if data is not None else DeviceArray(batch * self.coeff_count)
+        self.data = data if data is not None else context.alloc(batch * self.coeff_count)
 
     @property
     def is_ntt_form(self):
@@ -360,7 +393,7 @@ class KSwitchKeysCuda:
             a = np.ascontiguousarray(w, dtype=np.uint64)
             if a.shape != (digits, 2, n_key_limbs, context.n):
                 raise TroyInvalidArgument("kswitch_keys is not valid for encryption parameters")
-            buf = DeviceArray(a.size)
+            buf = context.alloc(a.size)
             buf.upload(a)
             k.keys[idx] = buf
         return k
@@ -415,7 +448,7 @@ class DecryptorCuda:
         self.key_words = context.level_limbs(SEALContextCuda.KEY_LEVEL) * context.n
         if w.size != self.key_words:
             raise TroyInvalidArgument("secret key is not valid for encryption parameters")
-        self.powers = DeviceArray(self.key_words)
+        self.powers = context.alloc(self.key_words, stream)
         self.powers.upload(w.reshape(-1))
         self.n_powers = 1
 
@@ -423,8 +456,9 @@ class DecryptorCuda:
         """computeSecretKeyArray (src/decryptor_cuda.cu:188-235)"""
         if max_power <= self.n_powers:
             return
-        new = DeviceArray(max_power * self.key_words)
+        new = self.context.alloc(max_power * self.key_words, self.stream)
         _L().call("troyb_secret_key_powers", _vp(self.context.h), _vp(self.powers.ptr), max_power, _vp(new.ptr), _vp(self.stream))
+        self.powers.stream = self.stream  # released behind the kernel that read it
         self.powers, self.n_powers = new, max_power
 
     def decrypt(self, ct):
@@ -437,12 +471,17 @@ class DecryptorCuda:
             raise TroyInvalidArgument("encrypted cannot be in NTT form")
         self._ensure_powers(ct.size - 1)
         words = ct.limbs * self.context.n
-        phase = DeviceArray(ct.batch * words)
+        if isinstance(ct.data, DeviceArray) and ct.data.stream is not self.stream:
+            # the ciphertext was last touched on another stream: wait for it, then it belongs to this one
+            _L().call("troyb_stream_synchronize", _vp(ct.data.stream))
+            ct.data.stream = self.stream
+        phase = self.context.alloc(ct.batch * words, self.stream)
         _L().call("troyb_decrypt_dot_product", _vp(self.context.h), ct.parms_id, _vp(ct.ptr()), ct.size, ct.stride,
                   int(ct.is_ntt_form), _vp(self.powers.ptr), _vp(phase.ptr), ct.batch, _vp(self.stream))
         if scheme == CKKS:
             return PlaintextCuda(self.context, words, ct.parms_id, ct.scale, ct.batch, data=phase)
-        out = PlaintextCuda(self.context, self.context.n, None, 1.0, ct.batch)
+        out = PlaintextCuda(self.context, self.context.n, None, 1.0, ct.batch,
+                            data=self.context.alloc(ct.batch * self.context.n, self.stream))
         if scheme == BGV:
             t = self.context.parms.plain_modulus
             try:
@@ -510,6 +549,17 @@ class EvaluatorCuda:
     def _s(self):
         return _vp(self.stream)
 
+    def _own(self, *objs):
+        """Stream hand-over: every buffer this call reads or writes joins the evaluator's stream. A buffer last touched on a
+        different stream is waited for first (an event-free, conservative hand-over: streams that stay with one evaluator
+        never synchronise), and from here on it is copied, grown and released in the order of this stream."""
+        for o in objs:
+            d = getattr(o, "data", None)
+            if isinstance(d, DeviceArray) and d.stream is not self.stream:
+                if d.stream != self.stream:
+                    _L().call("troyb_stream_synchronize", _vp(d.stream))
+                d.stream = self.stream
+
     def _check_scale(self, scale, level):
         """isScaleWithinBounds, src/evaluator_cuda.cu:32-51."""
         if self.context.scheme == CKKS:
@@ -531,6 +581,7 @@ class EvaluatorCuda:
         return ct.capacity == ct.size
 
     def negate_inplace(self, ct):
+        self._own(ct)
         if self._dense(ct):
             _L().call("troyb_negate", self._h(), ct.parms_id, _vp(ct.ptr()), _vp(ct.ptr()), ct.batch * ct.size, self._s())
             return
@@ -538,11 +589,12 @@ class EvaluatorCuda:
             _L().call("troyb_negate", self._h(), ct.parms_id, _vp(ct.ptr(0, b)), _vp(ct.ptr(0, b)), ct.size, self._s())
 
     def _addsub(self, name, a, b):
+        self._own(a, b)
         self._same_parms(a, b)
         if self.context.scheme == BGV and a.correction_factor != b.correction_factor:
             # balance the correction factors with scalar multiplications first (src/evaluator_cuda.cu:171-190)
             f, e1, e2 = _balance_correction_factors(a.correction_factor, b.correction_factor, self.context.parms.plain_modulus)
-            b = b.clone()
+            b = b.clone(self.stream)
             for ct, e in ((a, e1), (b, e2)):
                 for i in range(ct.batch):
                     _L().call("troyb_multiply_scalar", self._h(), ct.parms_id, _vp(ct.ptr(0, i)), e, _vp(ct.ptr(0, i)), ct.size,
@@ -555,7 +607,7 @@ class EvaluatorCuda:
         if a.size == b.size and self._dense(a) and self._dense(b):
             _L().call(name, self._h(), a.parms_id, _vp(a.ptr()), _vp(b.ptr()), _vp(a.ptr()), a.batch * a.size, self._s())
             return
-        a.resize(mx)
+        a.resize(mx, self.stream)
         for i in range(a.batch):
             _L().call(name, self._h(), a.parms_id, _vp(a.ptr(0, i)), _vp(b.ptr(0, i)), _vp(a.ptr(0, i)), mn, self._s())
             if a_old < b.size:
@@ -574,6 +626,7 @@ class EvaluatorCuda:
 
     # -- multiply / square (src/evaluator_cuda.cu:262-701)
     def multiply_inplace(self, a, b):
+        self._own(a, b)
         self._same_parms(a, b)
         scheme = self.context.scheme
         if scheme == CKKS and not (a.is_ntt_form and b.is_ntt_form):
@@ -586,7 +639,7 @@ class EvaluatorCuda:
             raise TroyInvalidArgument("scale out of bounds")
         a_size = a.size
         b_ptr, b_stride = b.ptr(), b.stride  # taken before a possible reallocation when b is a
-        a.reserve(out_size)
+        a.reserve(out_size, self.stream)
         if b is a:
             b_ptr, b_stride = a.ptr(), a.stride
         _L().call("troyb_multiply", self._h(), a.parms_id, _vp(a.ptr()), a_size, a.stride, _vp(b_ptr), b.size, b_stride,
@@ -600,10 +653,11 @@ class EvaluatorCuda:
     def multiply(self, a, b, destination=None):
         """multiply(encrypted1, encrypted2, destination) (src/evaluator_cuda.cuh:85-97). With a ``destination`` of the same
         batch and level and capacity for the product, the product is written there directly (the reference copies first)."""
+        self._own(a, b, destination)
         out_size = a.size + b.size - 1
         if destination is None or destination is a or destination is b or destination.batch != a.batch \
                 or destination.limbs != a.limbs or destination.capacity < out_size:
-            d = a.clone()
+            d = a.clone(self.stream)
             self.multiply_inplace(d, b)
             if destination is not None:
                 self._assign(destination, d)
@@ -647,6 +701,7 @@ class EvaluatorCuda:
 
     def relinearize_inplace(self, ct, relin_keys):
         """relinearizeInternal(ct, keys, 2); only 3 -> 2 is on the ported path (§A.9)."""
+        self._own(ct)
         if ct.size == 2:
             return
         if ct.size != 3:
@@ -660,12 +715,14 @@ class EvaluatorCuda:
 
     def switch_key_inplace(self, ct, target, keys, index):
         """switchKeyInplace(ct, target, keys, index): target is a DeviceArray/[batch][L][N] buffer."""
+        self._own(ct, target)
         self._check_keyswitch(ct, keys)
         _L().call("troyb_switch_key", self._h(), ct.parms_id, _vp(ct.ptr()), ct.stride, _vp(target.ptr), ct.poly_words,
                   _vp(keys.data(index).ptr), ct.batch, self._s())
 
     # -- Galois / rotations (src/evaluator_cuda.cu:2024-2176)
     def apply_galois_inplace(self, ct, galois_elt, galois_keys):
+        self._own(ct)
         if galois_keys.parms_id != self.context.key_parms_id():
             raise TroyInvalidArgument("galois_keys is not valid for encryption parameters")
         if not (galois_elt & 1) or galois_elt >= 2 * self.context.n:
@@ -683,6 +740,7 @@ class EvaluatorCuda:
         size-2 capacity) receives the result; ``ct`` is only read."""
         if destination is ct:
             return self.apply_galois_inplace(ct, galois_elt, galois_keys)
+        self._own(ct, destination)
         if galois_keys.parms_id != self.context.key_parms_id():
             raise TroyInvalidArgument("galois_keys is not valid for encryption parameters")
         if not (galois_elt & 1) or galois_elt >= 2 * self.context.n:
@@ -715,7 +773,8 @@ class EvaluatorCuda:
         elt = self.context.galois_elt_from_step(steps) if steps != 0 else None
         if elt is not None and galois_keys.has_key(elt):
             return self.apply_galois(ct, elt, galois_keys, destination)
-        self._assign(destination, ct.clone())
+        self._own(ct, destination)
+        self._assign(destination, ct.clone(self.stream))
         self._rotate_internal(destination, steps, galois_keys)
         return destination
 
@@ -757,6 +816,7 @@ class EvaluatorCuda:
 
     # -- rescale / mod switch (src/evaluator_cuda.cu:749-1010, 1380)
     def _scale_to_next(self, ct):
+        self._own(ct)
         scheme = self.context.scheme
         if ct.parms_id + 1 >= self.context.num_levels:
             raise TroyInvalidArgument("end of modulus switching chain reached")
@@ -766,7 +826,8 @@ class EvaluatorCuda:
             raise TroyInvalidArgument("BFV encrypted cannot be in NTT form" if scheme == BFV
                                       else "BGV encrypted cannot be in NTT form")
         q_last = self.context.level_moduli(ct.parms_id)[-1]
-        out = CiphertextCuda(self.context, ct.parms_id + 1, ct.size, ct.is_ntt_form, ct.scale, ct.correction_factor, ct.batch)
+        out = CiphertextCuda(self.context, ct.parms_id + 1, ct.size, ct.is_ntt_form, ct.scale, ct.correction_factor, ct.batch,
+                             stream=self.stream)
         _L().call("troyb_mod_switch_scale_to_next", self._h(), ct.parms_id, _vp(ct.ptr()), ct.stride, _vp(out.ptr()),
                   out.stride, ct.size, ct.batch, self._s())
         if scheme == CKKS:
@@ -777,6 +838,8 @@ class EvaluatorCuda:
         return out
 
     def _assign(self, dst, src):
+        if isinstance(dst.data, DeviceArray) and dst.data is not src.data:
+            dst.data.stream = self.stream  # the words being replaced are released behind this stream's kernels
         dst.parms_id, dst.size, dst.is_ntt_form, dst.scale = src.parms_id, src.size, src.is_ntt_form, src.scale
         dst.correction_factor, dst.batch, dst.limbs, dst.capacity, dst.data = \
             src.correction_factor, src.batch, src.limbs, src.capacity, src.data
@@ -796,7 +859,9 @@ class EvaluatorCuda:
             return self._scale_to_next(ct)
         if ct.parms_id + 1 >= self.context.num_levels:
             raise TroyInvalidArgument("end of modulus switching chain reached")
-        out = CiphertextCuda(self.context, ct.parms_id + 1, ct.size, ct.is_ntt_form, ct.scale, ct.correction_factor, ct.batch)
+        self._own(ct)
+        out = CiphertextCuda(self.context, ct.parms_id + 1, ct.size, ct.is_ntt_form, ct.scale, ct.correction_factor, ct.batch,
+                             stream=self.stream)
         n = self.context.n
         for b in range(ct.batch):
             for p in range(ct.size):
@@ -812,6 +877,7 @@ class EvaluatorCuda:
             raise TroyInvalidArgument("plain batch does not match the ciphertext batch")
 
     def _addsub_plain(self, ct, plain, subtract):
+        self._own(ct, plain)
         scheme = self.context.scheme
         if scheme == BFV and ct.is_ntt_form:
             raise TroyInvalidArgument("BFV encrypted cannot be in NTT form")
@@ -844,6 +910,7 @@ class EvaluatorCuda:
 
     def multiply_plain_inplace(self, ct, plain):
         """multiplyPlainInplace → multiplyPlainNtt / multiplyPlainNormal (src/evaluator_cuda.cu:1704-1862)."""
+        self._own(ct, plain)
         if ct.is_ntt_form != plain.is_ntt_form:
             raise TroyInvalidArgument("NTT form mismatch")
         self._check_plain_batch(ct, plain)
@@ -867,13 +934,15 @@ class EvaluatorCuda:
                     raise TroyInvalidArgument("scale out of bounds")
 
     def multiply_plain(self, ct, plain):
-        d = ct.clone()
+        self._own(ct)
+        d = ct.clone(self.stream)
         self.multiply_plain_inplace(d, plain)
         return d
 
     def multiply_plain_accumulate(self, ct, plain, destination):
         """destination += ct * plain (NTT form) in one pass: the multiplyPlain + addInplace pair of
         MatmulHelper::matmul (app/LinearHelperCKKS.cuh:225-249). The scales must agree like in addInplace."""
+        self._own(ct, plain, destination)
         if not (ct.is_ntt_form and plain.is_ntt_form and destination.is_ntt_form):
             raise TroyInvalidArgument("NTT form mismatch")
         if ct.parms_id != plain.parms_id or ct.parms_id != destination.parms_id or ct.size != destination.size \
@@ -891,8 +960,9 @@ class EvaluatorCuda:
             raise TroyInvalidArgument("plain is already in NTT form")
         if not (0 <= parms_id < self.context.num_levels):
             raise TroyInvalidArgument("parms_id is not valid for the current context")
+        self._own(plain)
         words = self.context.level_limbs(parms_id) * self.context.n
-        out = DeviceArray(plain.batch * words)
+        out = self.context.alloc(plain.batch * words, self.stream)
         _L().call("troyb_plain_lift", self._h(), parms_id, _vp(plain.data.ptr), plain.coeff_count, plain.coeff_count,
                   _vp(out.ptr), plain.batch, 1, self._s())
         plain.data, plain.coeff_count, plain.parms_id = out, words, parms_id
@@ -901,6 +971,7 @@ class EvaluatorCuda:
     def transform_to_ntt_inplace(self, ct):
         if ct.is_ntt_form:
             raise TroyInvalidArgument("encrypted is already in NTT form")
+        self._own(ct)
         if self._dense(ct):
             _L().call("troyb_ntt_forward", self._h(), ct.parms_id, _vp(ct.ptr()), ct.batch * ct.size, self._s())
         else:
@@ -911,6 +982,7 @@ class EvaluatorCuda:
     def transform_from_ntt_inplace(self, ct):
         if not ct.is_ntt_form:
             raise TroyInvalidArgument("encrypted_ntt is not in NTT form")
+        self._own(ct)
         if self._dense(ct):
             _L().call("troyb_ntt_inverse", self._h(), ct.parms_id, _vp(ct.ptr()), ct.batch * ct.size, self._s())
         else:
