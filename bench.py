@@ -321,6 +321,12 @@ def run_ours(args):
         join()
     e2e_steps = max(2, min(args.steps, 20))  # ~0.5 s: the PCIe arm varies by +-10 % over 5 steps on a shared host
     t_e2e = timed(step_e2e, e2e_steps, fork, join)
+    if rank == 0 and world == 1:
+        # the results that came back over the link are the device path's results
+        step()
+        torch.cuda.synchronize()
+        if not torch.equal(out_host[:4], a_work[:4, :2].cpu()):
+            raise SystemExit("bench: end-to-end results differ from the device-resident path")
     fork()
     step_copy_only()
     join()
@@ -334,12 +340,6 @@ def run_ours(args):
            "copy_only_h2d_gbs_per_rank": h2d_b * e2e_steps / t_copy / 1e9,
            "limiter": "pinned host<->device copy bandwidth per rank (6 MiB cross the link per operation; no collective)",
            "cpu_affinity": affinity}
-    if rank == 0 and world == 1:
-        # the results that came back over the link are the device path's results
-        step()
-        torch.cuda.synchronize()
-        if not torch.equal(out_host[:4], a_work[:4, :2].cpu()):
-            raise SystemExit("bench: end-to-end results differ from the device-resident path")
 
     # ---- the other quantities the metric names: rotate, rescale, standalone NTT
     def rot():

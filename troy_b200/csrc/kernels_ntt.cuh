@@ -59,6 +59,7 @@ struct NttArgs {
     uint8_t order[kMaxLimbs]; // launch rank -> limb index: integer-pipe and FP64-pipe limbs interleaved (see set_order)
     u32 n_rank;         // limb ranks in the launch; consecutive units cycle through them
     u32 pf_ahead;       // L2 prefetch distance in CTAs (0 = off): CTA b asks the L2 for the source tile of CTA b + pf_ahead
+    unsigned long long *dbg; // development builds (-DTROYB_DEV_TIMELINE, TROYB_TIMELINE=file): thread 0 of every CTA records globaltimer at its phase boundaries
     int solo;           // forward, limb = 2 tiles: independent CTAs that both recompute layer 0 (FwdSoloLd). Launched without a
                         // cluster when the transform is out of place; in place, as a cluster of two whose only exchange is one
                         // split barrier "my loads are done" before anybody stores (run_fwd)

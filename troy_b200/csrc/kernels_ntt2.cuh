@@ -1,0 +1,220 @@
+// NTT kernels on warp-owned blocks (ntt2.cuh): the same launch interface (NttArgs, modes, fused prologues / epilogues) as
+// kernels_ntt.cuh, the transforms re-cut so that a CTA meets ONE barrier per transform and its inputs arrive by asynchronous
+// copies. GPU only: the host emulation (tests/emul) keeps the first-generation kernels.
+#pragma once
+#include "kernels_ntt.cuh"
+#include "ntt2.cuh"
+
+namespace troyb {
+
+// 128-bit face of FwdStore: two consecutive outputs (i even).
+struct FwdStore2 {
+    FwdStore s;
+    struct Pre { ulonglong2 acc, ct; };
+    TB_D Pre pre(u32 i) const {
+        Pre r;
+        r.acc = *reinterpret_cast<const ulonglong2 *>(s.u.acc + i);
+        r.ct.x = r.ct.y = 0;
+        if (s.u.ct_in) r.ct = *reinterpret_cast<const ulonglong2 *>(s.u.ct_in + i);
+        return r;
+    }
+    // mod-down tail (FWD_MODDOWN)
+    TB_D void operator()(u32 i, u64 a, u64 b, const Pre &q) const {
+        ulonglong2 o;
+        o.x = s.finish(q.acc.x, a);
+        o.y = s.finish(q.acc.y, b);
+        if (s.u.ct) {
+            o.x = addmod(q.ct.x, o.x, s.p);
+            o.y = addmod(q.ct.y, o.y, s.p);
+            *reinterpret_cast<ulonglong2 *>(s.u.ct + i) = o;
+        } else {
+            *reinterpret_cast<ulonglong2 *>(s.u.dst + i) = o;
+        }
+    }
+};
+
+// Copies the canonical residues of the warp's block out of shared memory (tile-relative pointers in st), 128 bits per lane
+// and access. Plain stores: all 16 reads of a lane are issued before its 16 stores. Mod-down tail: the epilogue's own global
+// operands are requested 8 accesses ahead (one memory latency per batch, not per access).
+TB_D void block_copy_out(const u64 *sm, u32 base, u32 lane, const FwdStore2 &st) {
+    if (st.s.mode != FWD_MODDOWN) {
+        ulonglong2 v[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) v[k] = *reinterpret_cast<const ulonglong2 *>(sm + pad2(base + 2u * lane) + 72u * (u32)k);
+#pragma unroll
+        for (int k = 0; k < 16; k++) *reinterpret_cast<ulonglong2 *>(st.s.u.dst + base + 2u * lane + 64u * (u32)k) = v[k];
+        return;
+    }
+    constexpr int UB = 8;
+#pragma unroll 1
+    for (int k0 = 0; k0 < 16; k0 += UB) {
+        FwdStore2::Pre pre[UB];
+#pragma unroll
+        for (int k = 0; k < UB; k++) pre[k] = st.pre(base + 2u * lane + 64u * (u32)(k0 + k));
+#pragma unroll
+        for (int k = 0; k < UB; k++) {
+            const u32 i = base + 2u * lane + 64u * (u32)(k0 + k);
+            u64 a, b;
+            lds128(sm, pad2(base + 2u * lane) + 72u * (u32)(k0 + k), a, b);
+            st(i, a, b, pre[k]);
+        }
+    }
+}
+
+template <int LOGT> struct NttFwdTile2 {
+    static constexpr int kThreads = LimbPlan<LOGT, 0>::NT;
+    static constexpr int kMinCtas = LOGT == 13 ? 3 : 6;
+    static constexpr int kStages = 1;
+    static constexpr bool kTrailingBarrier = false; // peers only write into this CTA's tile, before the kernel's own barrier
+    NttArgs a;
+    const char *name() const { return ntt_kernel_name(a.mode); }
+    TB_D bool barrier_after(int) const { return false; }
+
+    template <int LOGC> TB_D void run(NttUnit &u, u32 bid, u32 grid, u32 rank, u64 *sm, const Peers &peers) const {
+        typedef LimbPlan<LOGT, LOGC> P;
+        const u32 t = threadIdx.x, warp = t >> 5, lane = t & 31u;
+        TB_MARK(a.dbg, bid, 0);
+        fwd_stage_inputs<LOGT, LOGC>(sm, t, rank, u.src);
+        const ModDev *md = u.md;
+        const int pol = md->policy;
+        prefetch_tiles<LOGT>(a, u, bid, rank, grid);
+        const FwdPrologue pro{md->p, md->ratio1, a.mode == FWD_MODDOWN ? md->p - u.dl.half_mod : 0,
+                              (a.mode == FWD_MODUP && !u.reduce_src) ? (int)FWD_PLAIN : a.mode};
+        u32 handle[1 << LOGC];
+        if constexpr (LOGC > 0) {
+#pragma unroll
+            for (int k = 0; k < (1 << LOGC); k++) handle[k] = peers.map((u32)k);
+        }
+        const u32 rt = (1u << LOGC) + rank;              // root base of this tile's own transform
+        const u32 rb = (rt << (LOGT - 10)) + warp;       // ... and of this warp's block
+        TB_MARK(a.dbg, bid, 1);
+        cp_async_wait_all();
+        __syncthreads();
+        TB_MARK(a.dbg, bid, 2);
+        TB_WITH_POLICY(pol, {
+            if constexpr (LOGC == 0) {
+                auto st_own = [&](u32, u32 w, u64 bits) { sm[w] = bits; };
+                fwd_first_stage_staged<A, LOGT, LOGC, false>(sm, t, 0u, pro, st_own, md);
+            } else {
+                auto st_peer = [&](u32 tile, u32 w, u64 bits) { peers.st(handle[tile], w, bits); };
+                fwd_first_stage_staged<A, LOGT, LOGC, true>(sm, t, rank, pro, st_peer, md);
+            }
+            TB_MARK(a.dbg, bid, 4);
+            const typename A::Mod m = A::make(md);
+            const void *tw = A::fwd_table(md);
+            BlockTw<A> pre;
+            if constexpr (!P::MID) pre.load(tw, rb); // in flight across the barrier
+            if constexpr (LOGC == 0) __syncthreads();
+            else cluster_barrier();
+            if constexpr (P::MID) {
+                round_tile<A, kThreads, false, false>(sm, t, tw, rt, m); // the three layers that couple the blocks of the tile
+                pre.load(tw, rb);
+                __syncthreads();
+            }
+            TB_MARK(a.dbg, bid, 5);
+            fwd_block_stage<A>(sm, warp << 10, lane, tw, rb, m, pre);
+            TB_MARK(a.dbg, bid, 8);
+        })
+        // this tile's outputs are coefficients [off, off + T) of the limb's (bit-reversed) output
+        const u64 off = (u64)rank << LOGT;
+        if (u.dst) u.dst += off;
+        if (u.ct) u.ct += off;
+        if (u.ct_in) u.ct_in += off;
+        if (u.acc) u.acc += off;
+        const FwdStore2 st{FwdStore{u, md->p, a.mode}};
+        block_copy_out(sm, warp << 10, lane, st);
+#if defined(TROYB_DEV_TIMELINE)
+        if (a.dbg != nullptr && threadIdx.x == 0) {
+            u32 smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            a.dbg[(size_t)bid * 16 + 9] = tb_now();
+            a.dbg[(size_t)bid * 16 + 10] = smid;
+        }
+#endif
+    }
+
+    template <int S> TB_D void stage(u32 bid, u32 grid, u32 rank, u32 nranks, u64 *sm, const Peers &peers) const {
+        NttUnit u = resolve_unit<LOGT>(a, bid);
+        if (u.passthrough) return; // digit already in NTT form under this modulus: the inner product reads it in place
+        if constexpr (LOGT == 12) {
+            run<0>(u, bid, grid, rank, sm, peers);
+        } else {
+            switch (u.rows_log) {
+            case 0: run<0>(u, bid, grid, rank, sm, peers); break;
+            case 1: run<1>(u, bid, grid, rank, sm, peers); break;
+            case 2: run<2>(u, bid, grid, rank, sm, peers); break;
+            default: run<3>(u, bid, grid, rank, sm, peers); break;
+            }
+        }
+    }
+};
+
+template <int LOGT> struct NttInvTile2 {
+    static constexpr int kThreads = LimbPlan<LOGT, 0>::NT;
+    static constexpr int kMinCtas = LOGT == 13 ? 3 : 6;
+    static constexpr int kStages = 1;
+    static constexpr bool kTrailingBarrier = true; // peers read this CTA's tile in the last stage
+    NttArgs a;
+    const char *name() const { return ntt_kernel_name(a.mode); }
+    TB_D bool barrier_after(int) const { return true; }
+
+    template <int LOGC> TB_D void run(const NttUnit &u, u32 bid, u32 grid, u32 rank, u64 *sm, const Peers &peers) const {
+        typedef LimbPlan<LOGT, LOGC> P;
+        const u32 t = threadIdx.x, warp = t >> 5, lane = t & 31u, base = warp << 10;
+        // the warp stages its own block: canonical residues, 16 copies of 16 bytes per lane
+        const u64 *in = u.src + ((u64)rank << LOGT) + base + 2u * lane;
+#pragma unroll
+        for (int k = 0; k < 16; k++) cp_async16(sm + pad2(base + 2u * lane) + 72u * (u32)k, in + 64u * (u32)k);
+        cp_async_commit();
+        const ModDev *md = u.md;
+        const u64 p = md->p;
+        const int pol = md->policy;
+        prefetch_tiles<LOGT>(a, u, bid, rank, grid);
+        u32 handle[1 << LOGC];
+        if constexpr (LOGC > 0) {
+#pragma unroll
+            for (int k = 0; k < (1 << LOGC); k++) handle[k] = peers.map((u32)k);
+        }
+        const u32 rt = (1u << LOGC) + rank;
+        const u32 rb = (rt << (LOGT - 10)) + warp;
+        auto st = [&](u32 i, u64 v) { inv_store_final(a, u, p, i, v); };
+        TB_WITH_POLICY(pol, {
+            const typename A::Mod m = A::make(md);
+            const void *tw = A::inv_table(md);
+            TwSet<A, Prefetching<A>::value ? 3 : 1> first;
+            if constexpr (Prefetching<A>::value) first.load(tw, rb, 7, lane);
+            cp_async_wait_all();
+            __syncwarp();
+            inv_block_stage<A>(sm, base, lane, tw, rb, m, first);
+            if constexpr (P::MID) {
+                __syncthreads();
+                round_tile<A, kThreads, true, A::kReduceEachInvRound>(sm, t, tw, rt, m);
+            }
+            if constexpr (LOGC == 0) {
+                __syncthreads();
+                auto ld_own = [&](u32, u32 w) -> u64 { return sm[w]; };
+                inv_last_stage<A, LOGT, LOGC>(t, 0u, ld_own, st, md);
+            } else {
+                cluster_barrier();
+                auto ld_peer = [&](u32 tile, u32 w) -> u64 { return peers.ld(handle[tile], w); };
+                inv_last_stage<A, LOGT, LOGC>(t, rank, ld_peer, st, md);
+            }
+        })
+    }
+
+    template <int S> TB_D void stage(u32 bid, u32 grid, u32 rank, u32 nranks, u64 *sm, const Peers &peers) const {
+        const NttUnit u = resolve_unit<LOGT>(a, bid);
+        if constexpr (LOGT == 12) {
+            run<0>(u, bid, grid, rank, sm, peers);
+        } else {
+            switch (u.rows_log) {
+            case 0: run<0>(u, bid, grid, rank, sm, peers); break;
+            case 1: run<1>(u, bid, grid, rank, sm, peers); break;
+            case 2: run<2>(u, bid, grid, rank, sm, peers); break;
+            default: run<3>(u, bid, grid, rank, sm, peers); break;
+            }
+        }
+    }
+};
+
+} // namespace troyb

@@ -1,5 +1,7 @@
 // Forward tile transforms: the only translation unit that instantiates the NttFwd* kernels (ntt_launch.h).
 #include "ntt_launch.h"
+#include <cstdio>
+#include <vector>
 
 namespace troyb {
 
@@ -10,6 +12,41 @@ cudaError_t launch_ntt_fwd(const Context *ctx, NttArgs a, u32 units, cudaStream_
     a.mods = ctx->d_mods;
     a.solo = 0;
     if (logN < 12) return launch_cta(NttFwdSmall{a}, units, (size_t)ctx->N * sizeof(u64), s);
+#if defined(TROYB_DEV_TIMELINE)
+    static const char *timeline = getenv("TROYB_TIMELINE");
+    if (use_ntt2() && timeline && logN >= 13) {
+        // development build: one instrumented launch, timeline dumped as text (CTA, smid, nanoseconds since the first mark)
+        const u32 c2 = 1u << (logN - 13), grid = units * c2;
+        unsigned long long *d = nullptr;
+        cudaMalloc(&d, (size_t)grid * 16 * 8);
+        cudaMemset(d, 0, (size_t)grid * 16 * 8);
+        a.dbg = d;
+        static const int extra = [] { const char *x = getenv("TROYB_SMEM_EXTRA"); return x ? atoi(x) : 0; }();
+        cudaError_t e = launch_cluster(NttFwdTile2<13>{a}, grid, c2, tile_smem2(13) + (size_t)extra, s);
+        cudaStreamSynchronize(s);
+        std::vector<unsigned long long> h((size_t)grid * 16);
+        cudaMemcpy(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost);
+        cudaFree(d);
+        if (FILE *f = fopen(timeline, "w")) {
+            unsigned long long t0 = ~0ull;
+            for (u32 b = 0; b < grid; b++) if (h[(size_t)b * 16] && h[(size_t)b * 16] < t0) t0 = h[(size_t)b * 16];
+            for (u32 b = 0; b < grid; b++) {
+                fprintf(f, "%u %llu", b, h[(size_t)b * 16 + 10]);
+                for (int k = 0; k < 10; k++) fprintf(f, " %lld", h[(size_t)b * 16 + k] ? (long long)(h[(size_t)b * 16 + k] - t0) : -1ll);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+        return e;
+    }
+#endif
+#if !defined(TROYB_HOST_EMUL)
+    if (use_ntt2()) {
+        if (logN == 12) return launch_cluster(NttFwdTile2<12>{a}, units, 1u, tile_smem2(12), s);
+        const u32 c2 = 1u << (logN - 13);
+        return launch_cluster(NttFwdTile2<13>{a}, units * c2, c2, tile_smem2(13), s);
+    }
+#endif
     const u32 c = tiles_per_limb(logN);
     if (tile_log(logN) == 12) return launch_cluster(NttFwdTile<12>{a}, units * c, c, tile_smem(12), s);
     // a limb of two tiles runs as two independent CTAs that both recompute layer 0 (kernels_ntt.cuh FwdSoloLd);
