@@ -9,6 +9,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import troy_b200 as tb  # noqa: E402
+from troy_b200 import lib as _tlib  # noqa: E402
+if os.environ.get("AB_LIB"):  # development: an A/B build of the library (TROYB_BUILD_OUT)
+    _tlib._library = _tlib.Library(os.path.join(ROOT, os.environ["AB_LIB"]))
 from troy_b200.host import DeviceArray, _L, _vp  # noqa: E402
 
 

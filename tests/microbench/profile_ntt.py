@@ -6,6 +6,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import troy_b200 as tb  # noqa: E402
+from troy_b200 import lib as _tlib  # noqa: E402
+if os.environ.get("AB_LIB"):  # development: an A/B build of the library (TROYB_BUILD_OUT)
+    _tlib._library = _tlib.Library(os.path.join(ROOT, os.environ["AB_LIB"]))
 from troy_b200.host import DeviceArray, _L, _vp  # noqa: E402
 
 n, bits, polys = int(os.environ.get("PROFILE_N", "16384")), int(os.environ.get("PROFILE_BITS", "40")), int(os.environ.get("PROFILE_POLYS", "512"))

@@ -14,6 +14,9 @@
 //   INV_COMBINE   BFV/BGV mod-down tail in coefficient form               src/evaluator_cuda.cu:1087-1161 (UtilE/F/G)
 #pragma once
 #include "ntt.cuh"
+#if !defined(TROYB_HOST_EMUL)
+#include <cuda.h>
+#endif
 
 namespace troyb {
 
@@ -23,6 +26,15 @@ enum NttMode {
 };
 
 struct NttArgs {
+#if !defined(TROYB_HOST_EMUL)
+    // Tensor maps of the second-generation kernels (ntt2.cuh): the buffer the inputs live in and the buffer plain outputs go
+    // to, each as a 2-D array [rows][16 words] with the 128-byte swizzle; a box is one staging segment / one 1024-coefficient
+    // block. Units address them by row: (pointer - base) / 16.
+    alignas(64) CUtensorMap tm_src;
+    alignas(64) CUtensorMap tm_dst;
+    const u64 *tm_src_base;
+    const u64 *tm_dst_base;
+#endif
     int mode;
     int logN;
     const ModDev *mods;

@@ -33,30 +33,22 @@ struct FwdStore2 {
     }
 };
 
-// Copies the canonical residues of the warp's block out of shared memory (tile-relative pointers in st), 128 bits per lane
-// and access. Plain stores: all 16 reads of a lane are issued before its 16 stores. Mod-down tail: the epilogue's own global
-// operands are requested 8 accesses ahead (one memory latency per batch, not per access).
+// Mod-down tail: the warp reads the canonical residues of its block back (128 bits per lane and access, coalesced on the
+// global side) and applies the epilogue; the epilogue's own global operands are requested 8 accesses ahead (one memory
+// latency per batch, not per access). Plain stores do not come here: one TMA store per block drains them.
 TB_D void block_copy_out(const u64 *sm, u32 base, u32 lane, const FwdStore2 &st) {
-    if (st.s.mode != FWD_MODDOWN) {
-        ulonglong2 v[16];
-#pragma unroll
-        for (int k = 0; k < 16; k++) v[k] = *reinterpret_cast<const ulonglong2 *>(sm + pad2(base + 2u * lane) + 72u * (u32)k);
-#pragma unroll
-        for (int k = 0; k < 16; k++) *reinterpret_cast<ulonglong2 *>(st.s.u.dst + base + 2u * lane + 64u * (u32)k) = v[k];
-        return;
-    }
     constexpr int UB = 8;
+    const u32 g = 2u * lane, a0 = base + (g ^ (((g >> 4) & 3u) << 1)), a1 = a0 ^ 8u; // pair 2 lane + 64 k: see block_b16_group
 #pragma unroll 1
     for (int k0 = 0; k0 < 16; k0 += UB) {
         FwdStore2::Pre pre[UB];
 #pragma unroll
-        for (int k = 0; k < UB; k++) pre[k] = st.pre(base + 2u * lane + 64u * (u32)(k0 + k));
+        for (int k = 0; k < UB; k++) pre[k] = st.pre(base + g + 64u * (u32)(k0 + k));
 #pragma unroll
         for (int k = 0; k < UB; k++) {
-            const u32 i = base + 2u * lane + 64u * (u32)(k0 + k);
             u64 a, b;
-            lds128(sm, pad2(base + 2u * lane) + 72u * (u32)(k0 + k), a, b);
-            st(i, a, b, pre[k]);
+            lds128(sm, ((k & 1) ? a1 : a0) + 64u * (u32)(k0 + k), a, b);
+            st(base + g + 64u * (u32)(k0 + k), a, b, pre[k]);
         }
     }
 }
@@ -74,7 +66,11 @@ template <int LOGT> struct NttFwdTile2 {
         typedef LimbPlan<LOGT, LOGC> P;
         const u32 t = threadIdx.x, warp = t >> 5, lane = t & 31u;
         TB_MARK(a.dbg, bid, 0);
-        fwd_stage_inputs<LOGT, LOGC>(sm, t, rank, u.src);
+        u64 *bar_in = sm + (1u << LOGT); // barrier words live behind the tile (tile_smem2)
+        if (t == 0) {
+            mbar_init(bar_in, 1);
+            fwd_stage_inputs<LOGT, LOGC>(sm, rank, &a.tm_src, (u32)((u.src - a.tm_src_base) >> 4), bar_in);
+        }
         const ModDev *md = u.md;
         const int pol = md->policy;
         prefetch_tiles<LOGT>(a, u, bid, rank, grid);
@@ -88,8 +84,8 @@ template <int LOGT> struct NttFwdTile2 {
         const u32 rt = (1u << LOGC) + rank;              // root base of this tile's own transform
         const u32 rb = (rt << (LOGT - 10)) + warp;       // ... and of this warp's block
         TB_MARK(a.dbg, bid, 1);
-        cp_async_wait_all();
-        __syncthreads();
+        __syncthreads();                                 // the barrier word is initialised
+        mbar_wait(bar_in, 0);
         TB_MARK(a.dbg, bid, 2);
         TB_WITH_POLICY(pol, {
             if constexpr (LOGC == 0) {
@@ -117,12 +113,22 @@ template <int LOGT> struct NttFwdTile2 {
         })
         // this tile's outputs are coefficients [off, off + T) of the limb's (bit-reversed) output
         const u64 off = (u64)rank << LOGT;
-        if (u.dst) u.dst += off;
-        if (u.ct) u.ct += off;
-        if (u.ct_in) u.ct_in += off;
-        if (u.acc) u.acc += off;
-        const FwdStore2 st{FwdStore{u, md->p, a.mode}};
-        block_copy_out(sm, warp << 10, lane, st);
+        if (a.mode != FWD_MODDOWN) {
+            // plain store: the block leaves through the tensor-map unit (the residues were written by this warp's lanes)
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_rows(&a.tm_dst, (u32)(((u.dst - a.tm_dst_base) + off) >> 4) + 64u * warp, sm + (warp << 10));
+                tma_store_commit_and_wait_read(); // the tile must outlive the unit's reads
+            }
+        } else {
+            if (u.dst) u.dst += off;
+            if (u.ct) u.ct += off;
+            if (u.ct_in) u.ct_in += off;
+            if (u.acc) u.acc += off;
+            const FwdStore2 st{FwdStore{u, md->p, a.mode}};
+            block_copy_out(sm, warp << 10, lane, st);
+        }
 #if defined(TROYB_DEV_TIMELINE)
         if (a.dbg != nullptr && threadIdx.x == 0) {
             u32 smid;
@@ -161,11 +167,13 @@ template <int LOGT> struct NttInvTile2 {
     template <int LOGC> TB_D void run(const NttUnit &u, u32 bid, u32 grid, u32 rank, u64 *sm, const Peers &peers) const {
         typedef LimbPlan<LOGT, LOGC> P;
         const u32 t = threadIdx.x, warp = t >> 5, lane = t & 31u, base = warp << 10;
-        // the warp stages its own block: canonical residues, 16 copies of 16 bytes per lane
-        const u64 *in = u.src + ((u64)rank << LOGT) + base + 2u * lane;
-#pragma unroll
-        for (int k = 0; k < 16; k++) cp_async16(sm + pad2(base + 2u * lane) + 72u * (u32)k, in + 64u * (u32)k);
-        cp_async_commit();
+        // the warp stages its own block: canonical residues, one TMA box of 64 rows
+        u64 *bar_in = sm + (1u << LOGT); // barrier words live behind the tile (tile_smem2)
+        if (lane == 0) {
+            mbar_init(&bar_in[warp], 1);
+            mbar_expect_tx(&bar_in[warp], 8192u);
+            tma_load_rows(sm + base, &a.tm_src, (u32)(((u.src - a.tm_src_base) + ((u64)rank << LOGT) + base) >> 4), &bar_in[warp]);
+        }
         const ModDev *md = u.md;
         const u64 p = md->p;
         const int pol = md->policy;
@@ -183,8 +191,8 @@ template <int LOGT> struct NttInvTile2 {
             const void *tw = A::inv_table(md);
             TwSet<A, Prefetching<A>::value ? 3 : 1> first;
             if constexpr (Prefetching<A>::value) first.load(tw, rb, 7, lane);
-            cp_async_wait_all();
-            __syncwarp();
+            __syncwarp();                                // the barrier word is initialised
+            mbar_wait(&bar_in[warp], 0);
             inv_block_stage<A>(sm, base, lane, tw, rb, m, first);
             if constexpr (P::MID) {
                 __syncthreads();

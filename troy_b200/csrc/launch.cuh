@@ -121,7 +121,7 @@ template <class F, class = void> struct MinCtas { static constexpr int value = 0
 template <class F> struct MinCtas<F, decltype((void)F::kMinCtas)> { static constexpr int value = F::kMinCtas; };
 
 template <class F> __global__ void __launch_bounds__(F::kThreads, MinCtas<F>::value) k_cta(const F f) {
-    extern __shared__ __align__(16) u64 tb_smem[];
+    extern __shared__ __align__(1024) u64 tb_smem[];
     f(blockIdx.x, tb_smem);
 }
 
@@ -196,8 +196,9 @@ template <class F, int S> TB_D void run_stages(const F &f, u32 rank, u32 nranks,
     }
 }
 
-template <class F> __global__ void __launch_bounds__(F::kThreads, F::kMinCtas) k_cluster(const F f) {
-    extern __shared__ __align__(16) u64 tb_smem[];
+// The functor travels as a __grid_constant__ parameter: kernels may take the address of its members (tensor maps).
+template <class F> __global__ void __launch_bounds__(F::kThreads, F::kMinCtas) k_cluster(const __grid_constant__ F f) {
+    extern __shared__ __align__(1024) u64 tb_smem[];
     u32 rank, nranks;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(nranks));

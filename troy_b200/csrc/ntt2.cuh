@@ -22,17 +22,19 @@
 //   inverse : the mirror image - the warp stages its block (cp.async), runs radix-8, radix-8, radix-16, ONE barrier, and
 //             the last stage gathers across blocks / tiles, applies N^-1 in the last layer and stores.
 //
-// Shared-memory layout: two pad words after every 16 (pad2). Every access pattern above is conflict free with it (lanes
-// read consecutive words inside 16-word rows; the stride-8 round splits a half warp over the two halves of the banks; the
-// last round's 64-byte groups sit 64 or 80 bytes apart, which spreads a quarter warp over all 32 banks), and all offsets
-// inside a group are compile-time constants.
+// Shared-memory layout: the tile is exactly 2^LOGT words with the 128-byte swizzle of the tensor-map unit: word i lives at
+// swz(i) = i ^ ((i >> 3) & 0xE), i.e. inside every 128-byte row the 16-byte chunk index is XOR-ed with the low three bits of
+// the row number. Every access pattern above is conflict free with it (lanes on consecutive words of one row, on rows
+// 64 bytes apart, or on whole 64-byte groups of neighbouring rows), and it is the layout cp.async.bulk.tensor reads and
+// writes, so the tile is filled by TMA loads (one per 4 .. 16 KiB segment, issued by one thread, no registers and no
+// load-store-unit wavefronts) and, where the epilogue is a plain store, drained by one TMA store per block.
 #pragma once
 #include "ntt.cuh"
+#include <cuda.h>
 
 namespace troyb {
 
-__host__ __device__ constexpr u32 pad2(u32 i) { return i + ((i >> 4) << 1); }
-__host__ __device__ constexpr u32 padded2_words(u32 n) { return n + (n >> 3); }
+__host__ __device__ constexpr u32 swz(u32 i) { return i ^ ((i >> 3) & 0xEu); }
 
 #if defined(TROYB_DEV_TIMELINE)
 TB_D unsigned long long tb_now() {
@@ -57,11 +59,36 @@ TB_D void sts128(u64 *sm, u32 w, u64 a, u64 b) {
     v.y = b;
     *reinterpret_cast<ulonglong2 *>(sm + w) = v;
 }
-TB_D void cp_async16(u64 *smem_dst, const u64 *gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((u32)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+TB_D u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+TB_D void mbar_init(u64 *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); // visible to the asynchronous proxy
 }
-TB_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-TB_D void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+TB_D void mbar_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+TB_D void mbar_wait(u64 *bar, u32 parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// box (0, row) of the tensor map -> shared memory at dst; completion counted in bytes on bar
+TB_D void tma_load_rows(void *dst, const CUtensorMap *tm, u32 row, u64 *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(0), "r"(row), "r"(smem_u32(bar)) : "memory");
+}
+TB_D void tma_store_rows(const CUtensorMap *tm, u32 row, const void *src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(tm), "r"(0), "r"(row), "r"(smem_u32(src)) : "memory");
+}
+TB_D void tma_store_commit_and_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// orders this thread's shared-memory writes before later accesses of the asynchronous proxy (TMA store)
+TB_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // NP groups that share their twiddles run the same network; tw(u, j) is the twiddle of block j of layer u of the network.
 template <class A, int RR, int NP, class TwF>
@@ -152,13 +179,13 @@ template <class A> struct Prefetching { static constexpr bool value = sizeof(typ
 template <class A, int NTHR, bool INVERSE, bool REDUCE>
 TB_D void round_tile(u64 *sm, u32 tid, const void *__restrict__ tw, u32 R, const typename A::Mod &m) {
     constexpr int NP = Prefetching<A>::value ? 2 : 1;
-    constexpr u32 KS = 1024u + 128u;
+    constexpr u32 KS = 1024u;
     constexpr int IT = 1024 / (NP * NTHR);
     TwSet<A, 3> w;
     w.load(tw, R, 0, 0);
 #pragma unroll 1
     for (int it = 0; it < IT; it++) {
-        const u32 a0 = pad2((u32)NP * tid + (u32)(NP * NTHR * it));
+        const u32 a0 = swz((u32)NP * tid + (u32)(NP * NTHR * it));
         typename A::elem x[NP][8];
 #pragma unroll
         for (int k = 0; k < 8; k++) {
@@ -192,11 +219,13 @@ TB_D void round_tile(u64 *sm, u32 tid, const void *__restrict__ tw, u32 R, const
 // B16 : layers 0..3, groups {g + 64 k} (k < 16), twiddles uniform over the warp
 // M8  : layers 4..6, groups {64 h + l + 8 k}, the 8 lanes with the same h share their twiddles
 // L8  : layers 7..9, groups of 8 consecutive coefficients
+// a0 = address of element 0 of the group, a1 = a0 ^ 8: elements g + 64 k sit in rows 4 k apart, whose parity flips the swizzle
 template <class A, bool INVERSE, bool REDUCE, class TwF>
 TB_D void block_b16_group(u64 *sm, u32 a0, const TwF &w, const typename A::Mod &m) {
+    const u32 a1 = a0 ^ 8u;
     typename A::elem x[1][16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) x[0][k] = A::from_bits(sm[a0 + 72u * (u32)k]);
+    for (int k = 0; k < 16; k++) x[0][k] = A::from_bits(sm[((k & 1) ? a1 : a0) + 64u * (u32)k]);
     if (REDUCE) {
 #pragma unroll
         for (int k = 0; k < 16; k++) A::reduce(x[0][k], m);
@@ -204,14 +233,16 @@ TB_D void block_b16_group(u64 *sm, u32 a0, const TwF &w, const typename A::Mod &
     if constexpr (INVERSE) radix_inv_tw<A, 4, 1, false>(x, w, m);
     else radix_fwd_tw<A, 4, 1>(x, w, m);
 #pragma unroll
-    for (int k = 0; k < 16; k++) sm[a0 + 72u * (u32)k] = A::to_bits(x[0][k]);
+    for (int k = 0; k < 16; k++) sm[((k & 1) ? a1 : a0) + 64u * (u32)k] = A::to_bits(x[0][k]);
 }
 
+// rb = base + 64 h (row of element 0), lh = l ^ ((h & 1) << 3): element k = 64 h + l + 8 k sits in row rb / 16 + (k >> 1) at
+// in-row word (l + 8 (k & 1)) ^ (((4 (h & 1) + (k >> 1)) << 1) = lh ^ c_k with the constant c_k = 8 (k & 1) ^ ((k >> 1) << 1)
 template <class A, bool INVERSE, bool REDUCE, class TwF>
-TB_D void block_m8_group(u64 *sm, u32 a0, const TwF &w, const typename A::Mod &m) {
+TB_D void block_m8_group(u64 *sm, u32 rb, u32 lh, const TwF &w, const typename A::Mod &m) {
     typename A::elem x[1][8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) x[0][k] = A::from_bits(sm[a0 + 8u * (u32)k + 2u * (u32)(k >> 1)]);
+    for (int k = 0; k < 8; k++) x[0][k] = A::from_bits(sm[rb + 16u * (u32)(k >> 1) + (lh ^ (u32)((8 * (k & 1)) ^ ((k >> 1) << 1)))]);
     if (REDUCE) {
 #pragma unroll
         for (int k = 0; k < 8; k++) A::reduce(x[0][k], m);
@@ -219,17 +250,18 @@ TB_D void block_m8_group(u64 *sm, u32 a0, const TwF &w, const typename A::Mod &m
     if constexpr (INVERSE) radix_inv_tw<A, 3, 1, false>(x, w, m);
     else radix_fwd_tw<A, 3, 1>(x, w, m);
 #pragma unroll
-    for (int k = 0; k < 8; k++) sm[a0 + 8u * (u32)k + 2u * (u32)(k >> 1)] = A::to_bits(x[0][k]);
+    for (int k = 0; k < 8; k++) sm[rb + 16u * (u32)(k >> 1) + (lh ^ (u32)((8 * (k & 1)) ^ ((k >> 1) << 1)))] = A::to_bits(x[0][k]);
 }
 
-// forward: leaves canonical residues; inverse: reads canonical residues
+// rb = first word of the row of group g (base + 16 (g >> 1)), c0 = 8 (g & 1) ^ (((g >> 1) & 7) << 1): the pair (2 q, 2 q + 1) of
+// the group sits at in-row word c0 ^ 2 q.   forward: leaves canonical residues; inverse: reads canonical residues
 template <class A, bool INVERSE, class TwF>
-TB_D void block_l8_group(u64 *sm, u32 a0, const TwF &w, const typename A::Mod &m) {
+TB_D void block_l8_group(u64 *sm, u32 rb, u32 c0, const TwF &w, const typename A::Mod &m) {
     typename A::elem x[1][8];
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         u64 a, b;
-        lds128(sm, a0 + 2u * (u32)q, a, b);
+        lds128(sm, rb + (c0 ^ (u32)(2 * q)), a, b);
         if constexpr (INVERSE) {
             x[0][2 * q] = A::from_u64(a, m);
             x[0][2 * q + 1] = A::from_u64(b, m);
@@ -241,21 +273,30 @@ TB_D void block_l8_group(u64 *sm, u32 a0, const TwF &w, const typename A::Mod &m
     if constexpr (INVERSE) {
         radix_inv_tw<A, 3, 1, false>(x, w, m);
 #pragma unroll
-        for (int q = 0; q < 4; q++) sts128(sm, a0 + 2u * (u32)q, A::to_bits(x[0][2 * q]), A::to_bits(x[0][2 * q + 1]));
+        for (int q = 0; q < 4; q++) sts128(sm, rb + (c0 ^ (u32)(2 * q)), A::to_bits(x[0][2 * q]), A::to_bits(x[0][2 * q + 1]));
     } else {
         radix_fwd_tw<A, 3, 1>(x, w, m);
 #pragma unroll
-        for (int q = 0; q < 4; q++) sts128(sm, a0 + 2u * (u32)q, A::canon(x[0][2 * q], m), A::canon(x[0][2 * q + 1], m));
+        for (int q = 0; q < 4; q++) sts128(sm, rb + (c0 ^ (u32)(2 * q)), A::canon(x[0][2 * q], m), A::canon(x[0][2 * q + 1], m));
     }
 }
 
-TB_D u32 m8_addr(u32 base, u32 lane, int it) { // group (h, l) of lane in turn `it`: h = lane / 8 + 4 it, l = lane % 8
-    const u32 h = (lane >> 3) + 4u * (u32)it;
-    return base + (base >> 3) + 72u * h + (lane & 7u);
-}
-TB_D u32 l8_addr(u32 base, u32 lane, int it) { // group g = lane + 32 it
+// group of lane in turn `it` of the radix-16 round: g = lane + 32 it; address of its element 0
+TB_D u32 b16_addr(u32 base, u32 lane, int it) {
     const u32 g = lane + 32u * (u32)it;
-    return base + (base >> 3) + 8u * g + 2u * (g >> 1);
+    return base + (g ^ (((g >> 4) & 3u) << 1));
+}
+// group (h, l) of lane in turn `it` of the stride-8 round: h = lane / 8 + 4 it, l = lane % 8
+TB_D void m8_addr(u32 base, u32 lane, int it, u32 &rb, u32 &lh) {
+    const u32 h = (lane >> 3) + 4u * (u32)it;
+    rb = base + 64u * h;
+    lh = (lane & 7u) ^ ((h & 1u) << 3);
+}
+// group g = lane + 32 it of the last round
+TB_D void l8_addr(u32 base, u32 lane, int it, u32 &rb, u32 &c0) {
+    const u32 g = lane + 32u * (u32)it;
+    rb = base + 16u * (g >> 1);
+    c0 = (8u * (g & 1u)) ^ (((g >> 1) & 7u) << 1);
 }
 
 // Twiddles of the block's radix-16 round (fetched by the caller BEFORE the barrier that precedes the block stage).
@@ -268,43 +309,47 @@ template <class A> struct BlockTw {
 
 template <class A> TB_D void fwd_block_stage(u64 *sm, u32 base, u32 lane, const void *__restrict__ tw, u32 Rb,
                                              const typename A::Mod &m, const BlockTw<A> &pre) {
-    const u32 pb = base + (base >> 3); // pad2(base): base is a multiple of 1024
+    u32 r0, r1;
     if constexpr (Prefetching<A>::value) {
         TwSet<A, 3> wc, wn;
-        block_b16_group<A, false, false>(sm, pb + pad2(lane), pre.b16, m);
+        block_b16_group<A, false, false>(sm, b16_addr(base, lane, 0), pre.b16, m);
         wc.load(tw, Rb, 4, lane >> 3); // first M8 group's twiddles: in flight during the second radix-16 group
-        block_b16_group<A, false, false>(sm, pb + pad2(lane) + 36u, pre.b16, m); // group lane + 32: pad2(32) = 36
+        block_b16_group<A, false, false>(sm, b16_addr(base, lane, 1), pre.b16, m);
         __syncwarp();
 #pragma unroll 1
         for (int it = 0; it < 4; it++) {
             if (it < 3) wn.load(tw, Rb, 4, (lane >> 3) + 4u * (u32)(it + 1));
             else wn.load(tw, Rb, 7, lane);
-            block_m8_group<A, false, false>(sm, m8_addr(base, lane, it), wc, m);
+            m8_addr(base, lane, it, r0, r1);
+            block_m8_group<A, false, false>(sm, r0, r1, wc, m);
             wc = wn;
         }
         __syncwarp();
 #pragma unroll 1
         for (int it = 0; it < 4; it++) {
             if (it < 3) wn.load(tw, Rb, 7, lane + 32u * (u32)(it + 1));
-            block_l8_group<A, false>(sm, l8_addr(base, lane, it), wc, m);
+            l8_addr(base, lane, it, r0, r1);
+            block_l8_group<A, false>(sm, r0, r1, wc, m);
             wc = wn;
         }
     } else {
 #pragma unroll 1
-        for (int it = 0; it < 2; it++) block_b16_group<A, false, false>(sm, pb + pad2(lane) + 36u * (u32)it, TwJit<A>{tw, Rb, 0, 0}, m);
+        for (int it = 0; it < 2; it++) block_b16_group<A, false, false>(sm, b16_addr(base, lane, it), TwJit<A>{tw, Rb, 0, 0}, m);
         __syncwarp();
 #pragma unroll 1
         for (int it = 0; it < 4; it++) {
             TwSet<A, 3> w;
             w.load(tw, Rb, 4, (lane >> 3) + 4u * (u32)it);
-            block_m8_group<A, false, false>(sm, m8_addr(base, lane, it), w, m);
+            m8_addr(base, lane, it, r0, r1);
+            block_m8_group<A, false, false>(sm, r0, r1, w, m);
         }
         __syncwarp();
 #pragma unroll 1
         for (int it = 0; it < 4; it++) {
             TwSet<A, 3> w;
             w.load(tw, Rb, 7, lane + 32u * (u32)it);
-            block_l8_group<A, false>(sm, l8_addr(base, lane, it), w, m);
+            l8_addr(base, lane, it, r0, r1);
+            block_l8_group<A, false>(sm, r0, r1, w, m);
         }
     }
     __syncwarp();
@@ -315,14 +360,15 @@ template <class A> TB_D void fwd_block_stage(u64 *sm, u32 base, u32 lane, const 
 template <class A, class First> TB_D void inv_block_stage(u64 *sm, u32 base, u32 lane, const void *__restrict__ tw, u32 Rb,
                                                           const typename A::Mod &m, const First &first) {
     constexpr bool RE = A::kReduceEachInvRound, RM = A::kReduceInvMidway;
-    const u32 pb = base + (base >> 3);
+    u32 r0, r1;
     if constexpr (Prefetching<A>::value) {
         TwSet<A, 3> wc = first, wn;
 #pragma unroll 1
         for (int it = 0; it < 4; it++) {
             if (it < 3) wn.load(tw, Rb, 7, lane + 32u * (u32)(it + 1));
             else wn.load(tw, Rb, 4, lane >> 3);
-            block_l8_group<A, true>(sm, l8_addr(base, lane, it), wc, m);
+            l8_addr(base, lane, it, r0, r1);
+            block_l8_group<A, true>(sm, r0, r1, wc, m);
             wc = wn;
         }
         __syncwarp();
@@ -331,29 +377,32 @@ template <class A, class First> TB_D void inv_block_stage(u64 *sm, u32 base, u32
         for (int it = 0; it < 4; it++) {
             if (it < 3) wn.load(tw, Rb, 4, (lane >> 3) + 4u * (u32)(it + 1));
             else wb.load(tw, Rb, 0, 0);
-            block_m8_group<A, true, RE>(sm, m8_addr(base, lane, it), wc, m);
+            m8_addr(base, lane, it, r0, r1);
+            block_m8_group<A, true, RE>(sm, r0, r1, wc, m);
             wc = wn;
         }
         __syncwarp();
 #pragma unroll 1
-        for (int it = 0; it < 2; it++) block_b16_group<A, true, RE || RM>(sm, pb + pad2(lane) + 36u * (u32)it, wb, m);
+        for (int it = 0; it < 2; it++) block_b16_group<A, true, RE || RM>(sm, b16_addr(base, lane, it), wb, m);
     } else {
 #pragma unroll 1
         for (int it = 0; it < 4; it++) {
             TwSet<A, 3> w;
             w.load(tw, Rb, 7, lane + 32u * (u32)it);
-            block_l8_group<A, true>(sm, l8_addr(base, lane, it), w, m);
+            l8_addr(base, lane, it, r0, r1);
+            block_l8_group<A, true>(sm, r0, r1, w, m);
         }
         __syncwarp();
 #pragma unroll 1
         for (int it = 0; it < 4; it++) {
             TwSet<A, 3> w;
             w.load(tw, Rb, 4, (lane >> 3) + 4u * (u32)it);
-            block_m8_group<A, true, RE>(sm, m8_addr(base, lane, it), w, m);
+            m8_addr(base, lane, it, r0, r1);
+            block_m8_group<A, true, RE>(sm, r0, r1, w, m);
         }
         __syncwarp();
 #pragma unroll 1
-        for (int it = 0; it < 2; it++) block_b16_group<A, true, RE || RM>(sm, pb + pad2(lane) + 36u * (u32)it, TwJit<A>{tw, Rb, 0, 0}, m);
+        for (int it = 0; it < 2; it++) block_b16_group<A, true, RE || RM>(sm, b16_addr(base, lane, it), TwJit<A>{tw, Rb, 0, 0}, m);
     }
 }
 
@@ -369,24 +418,20 @@ template <int LOGT, int LOGC> struct LimbPlan {
     static_assert(F1 >= 2 && F1 <= 4, "first stage radix out of range");
 };
 
-// ---- forward first stage fed by asynchronous copies ----------------------------------------------------------------------------
-// The inputs are copied straight INTO the tile: input k of group v'' (v'' counts the CTA's own groups) lives at
-// pad2(k * VC + v''), VC = groups per CTA. That is exactly where one of the outputs of the same thread position lands - output
-// k of group v'' of CTA r' goes to word pad2((k mod KT) * 2^VLOG + r' * VC + v'') of tile k / KT, the home of input
-// (k mod KT) * C + r' of group v'' there - so the only hazard is between the threads that handle the same v'' in the CTAs of
-// a cluster: a thread stores the outputs of a batch of groups only after every CTA has read that batch's inputs (a split
-// cluster barrier: arrive after the reads, wait before the stores, the butterflies in between).
-template <int LOGT, int LOGC> TB_D void fwd_stage_inputs(u64 *sm, u32 tid, u32 rank, const u64 *__restrict__ src) {
+// ---- forward first stage fed by the tensor-map unit -------------------------------------------------------------------------
+// The inputs are copied straight INTO the tile: input k of group v'' (v'' counts the CTA's own groups) lives at word
+// k * VC + v'' (VC = groups per CTA), one TMA box of VC / 16 rows per k. That is exactly where one of the outputs of the same
+// thread position lands - output k of group v'' of CTA r' goes to word (k mod KT) * 2^VLOG + r' * VC + v'' of tile k / KT, the
+// home of input (k mod KT) * C + r' of group v'' there - so the only hazard is between the threads that handle the same v''
+// in the CTAs of a cluster: a thread stores the outputs of a batch of groups only after every CTA has read that batch's
+// inputs (a split cluster barrier: arrive after the reads, wait before the stores, the butterflies in between).
+//   row0 : row (16 words) of coefficient 0 of the limb in the tensor map; called by ONE thread, after mbar_init
+template <int LOGT, int LOGC> TB_D void fwd_stage_inputs(u64 *sm, u32 rank, const CUtensorMap *tm, u32 row0, u64 *bar) {
     typedef LimbPlan<LOGT, LOGC> P;
-    constexpr int F1 = P::F1, VLOG = P::VLOG, NT = P::NT, LOGVC = LOGT - F1;
-    static_assert((1 << LOGT) / 2 == NT * 16, "16 copies per thread");
-#pragma unroll
-    for (int j = 0; j < 16; j++) {
-        const u32 pr = tid + (u32)(NT * j);                       // pair index: k * (VC / 2) + pp
-        const u32 k = pr >> (LOGVC - 1), v2 = (pr & ((1u << (LOGVC - 1)) - 1)) << 1;
-        cp_async16(sm + pad2((k << LOGVC) + v2), src + ((u64)k << VLOG) + (rank << LOGVC) + v2);
-    }
-    cp_async_commit();
+    constexpr int F1 = P::F1, K = 1 << F1, VLOG = P::VLOG, LOGVC = LOGT - F1;
+    mbar_expect_tx(bar, 8u << LOGT);
+#pragma unroll 1
+    for (u32 k = 0; k < (u32)K; k++) tma_load_rows(sm + (k << LOGVC), tm, row0 + (k << (VLOG - 4)) + (rank << (LOGVC - 4)), bar);
 }
 
 //   pro(x)                 : prologue on a staged coefficient
@@ -396,7 +441,7 @@ TB_D void fwd_first_stage_staged(const u64 *sm, u32 tid, u32 rank, Pro pro, StPe
     typedef LimbPlan<LOGT, LOGC> P;
     constexpr int F1 = P::F1, K = 1 << F1, VLOG = P::VLOG, NT = P::NT, LOGVC = LOGT - F1, VC = 1 << LOGVC, G = VC / NT;
     constexpr int B = 16 / K;                       // groups per batch: 16 inputs per thread and batch
-    constexpr u32 KS = VC + (VC >> 3);              // padded distance between the homes of inputs k and k + 1
+    constexpr u32 KS = VC;                          // distance between the homes of inputs k and k + 1
     static_assert(G == 2 * B, "two batches per tile");
     const typename A::Mod m = A::make(md);
     const void *tw = A::fwd_table(md);
@@ -406,7 +451,7 @@ TB_D void fwd_first_stage_staged(const u64 *sm, u32 tid, u32 rank, Pro pro, StPe
         typename A::elem x[B][K];
 #pragma unroll
         for (int b = 0; b < B; b++) {
-            const u32 pv = pad2(tid + (u32)((g0 + b) * NT));
+            const u32 pv = swz(tid + (u32)((g0 + b) * NT));
 #pragma unroll
             for (int k = 0; k < K; k++) x[b][k] = A::from_u64(pro(sm[pv + KS * (u32)k]), m);
         }
@@ -417,11 +462,11 @@ TB_D void fwd_first_stage_staged(const u64 *sm, u32 tid, u32 rank, Pro pro, StPe
         if (CLUSTER) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
 #pragma unroll
         for (int b = 0; b < B; b++) {
-            const u32 pv = pad2((rank << LOGVC) + tid + (u32)((g0 + b) * NT));
+            const u32 pv = swz((rank << LOGVC) + tid + (u32)((g0 + b) * NT));
 #pragma unroll
             for (int k = 0; k < K; k++) {
                 const u32 local = ((u32)k & ((1u << (LOGT - VLOG)) - 1)) << VLOG;
-                st_peer((u32)k >> (LOGT - VLOG), pad2(local) + pv, A::to_bits(x[b][k]));
+                st_peer((u32)k >> (LOGT - VLOG), local + pv, A::to_bits(x[b][k]));
             }
         }
     }
@@ -449,11 +494,11 @@ TB_D void inv_last_stage(u32 tid, u32 rank, LdPeer ld_peer, St st, const ModDev 
 #pragma unroll
         for (int b = 0; b < B; b++) {
             const u32 v = rank * (u32)((1 << LOGT) / K) + tid + (u32)((g0 + b) * NT);
-            const u32 pv = pad2(v & ((1u << VLOG) - 1));
+            const u32 pv = swz(v & ((1u << VLOG) - 1));
 #pragma unroll
             for (int k = 0; k < K; k++) {
                 const u32 local = ((u32)k & ((1u << (LOGT - VLOG)) - 1)) << VLOG;
-                raw[b][k] = ld_peer((u32)k >> (LOGT - VLOG), pad2(local) + pv);
+                raw[b][k] = ld_peer((u32)k >> (LOGT - VLOG), local + pv);
             }
         }
 #pragma unroll

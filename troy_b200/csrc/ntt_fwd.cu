@@ -5,6 +5,21 @@
 
 namespace troyb {
 
+#if !defined(TROYB_HOST_EMUL)
+// Tensor maps of a forward launch: inputs (the coefficient-form source; the rounded special limb s' for the mod-down tail) and,
+// for plain stores, outputs. False when a stride of the launch is not a whole number of 16-word rows (first-generation kernels).
+static bool fwd_maps(NttArgs &a, int logN) {
+    const u64 N = u64(1) << logN;
+    const u64 *src = a.mode == FWD_MODDOWN ? a.aux1 : a.src;
+    if (!rows_ok({N, a.src_unit_stride, a.dst_batch_stride, a.dst_poly_stride, (u64)(uintptr_t)src >> 3, (u64)(uintptr_t)a.dst >> 3})) return false;
+    a.tm_src_base = src;
+    a.tm_dst_base = a.dst;
+    if (make_rows_map(&a.tm_src, src, stage_box_rows(logN)) != cudaSuccess) return false;
+    if (a.mode != FWD_MODDOWN && make_rows_map(&a.tm_dst, a.dst, 64) != cudaSuccess) return false;
+    return true;
+}
+#endif
+
 cudaError_t launch_ntt_fwd(const Context *ctx, NttArgs a, u32 units, cudaStream_t s) {
     const int logN = ctx->logN;
     a.logN = logN;
@@ -22,6 +37,7 @@ cudaError_t launch_ntt_fwd(const Context *ctx, NttArgs a, u32 units, cudaStream_
         cudaMemset(d, 0, (size_t)grid * 16 * 8);
         a.dbg = d;
         static const int extra = [] { const char *x = getenv("TROYB_SMEM_EXTRA"); return x ? atoi(x) : 0; }();
+        if (!fwd_maps(a, logN)) return cudaErrorInvalidValue;
         cudaError_t e = launch_cluster(NttFwdTile2<13>{a}, grid, c2, tile_smem2(13) + (size_t)extra, s);
         cudaStreamSynchronize(s);
         std::vector<unsigned long long> h((size_t)grid * 16);
@@ -41,7 +57,7 @@ cudaError_t launch_ntt_fwd(const Context *ctx, NttArgs a, u32 units, cudaStream_
     }
 #endif
 #if !defined(TROYB_HOST_EMUL)
-    if (use_ntt2()) {
+    if (use_ntt2() && fwd_maps(a, logN)) {
         if (logN == 12) return launch_cluster(NttFwdTile2<12>{a}, units, 1u, tile_smem2(12), s);
         const u32 c2 = 1u << (logN - 13);
         return launch_cluster(NttFwdTile2<13>{a}, units * c2, c2, tile_smem2(13), s);

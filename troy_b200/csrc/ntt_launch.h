@@ -5,6 +5,7 @@
 #include "kernels_ntt.cuh"
 #else
 #include "kernels_ntt2.cuh"
+#include <initializer_list>
 #endif
 
 namespace troyb {
@@ -23,10 +24,47 @@ inline size_t tile_smem(int logt) { return (size_t)padded_words(1u << logt) * si
 #if defined(TROYB_HOST_EMUL)
 inline bool use_ntt2() { return false; }
 #else
-inline size_t tile_smem2(int logt) { return (size_t)padded2_words(1u << logt) * sizeof(u64); }
+inline size_t tile_smem2(int logt) { return (sizeof(u64) << logt) + 128; } // the tile + the mbarrier words
 inline bool use_ntt2() {
     static const bool on = [] { const char *e = getenv("TROYB_NTT2"); return !e || atoi(e) != 0; }();
     return on;
+}
+// Geometry of the second-generation plans on the host (mirrors LimbPlan in ntt2.cuh): tile size and rows per staging box.
+inline int tile2_log(int logN) { return logN == 12 ? 12 : 13; }
+inline u32 stage_box_rows(int logN) {
+    const int logt = tile2_log(logN), logc = logN - logt;
+    const bool mid = logc + logt - 10 > 4;
+    const int f1 = mid ? logc : logc + logt - 10;
+    return (1u << (logt - f1)) >> 4;
+}
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda).
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline TensorMapEncodeFn tensor_map_encoder() {
+    static const TensorMapEncodeFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<TensorMapEncodeFn>(p);
+    }();
+    return fn;
+}
+// The buffer at `base` as [rows][16 words] with the 128-byte swizzle; a box is `box_rows` whole rows.
+inline cudaError_t make_rows_map(CUtensorMap *tm, const u64 *base, u32 box_rows) {
+    const TensorMapEncodeFn fn = tensor_map_encoder();
+    if (!fn) return cudaErrorNotSupported;
+    const cuuint64_t dims[2] = {16, 1ull << 31};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {16, box_rows}, elem[2] = {1, 1};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<u64 *>(base), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+// Units address the maps by 16-word rows: every stride that separates units must be a multiple of 16 words.
+inline bool rows_ok(std::initializer_list<u64> strides) {
+    for (u64 v : strides) if (v & 15u) return false;
+    return true;
 }
 #endif
 
