@@ -133,6 +133,21 @@ int troyb_switch_key_partial(troyb_context *ctx, int level, const uint64_t *d_ta
 int troyb_switch_key_finish(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_stride, uint64_t *d_prod, int reduce_first,
                             size_t batch, void *stream);
 
+/* The digit-sharded key switch with the key products kept ROW-major, rows [L+1 output moduli][batch][2][N], so that the rows a
+ * GPU owns are one contiguous block: the partial products are summed with ONE reduce-scatter over NVLink, each GPU reduces and
+ * mod-downs only its own rows, and the result is all-gathered (the reference has no multi-GPU path).
+ *   partial_rows : rows = sum over digits [digit_begin, digit_end) of NTT_i(digit j) * key[j][k][i]   (:1222-1297)
+ *   reduce_rows  : rows [row_begin, row_end) hold sums of several GPUs' canonical products: reduce them modulo their primes
+ *   special_row  : sp [batch][2][N] = INTT(row L) (+ half of the special prime): the correction every data limb needs (:1299-1331)
+ *   moddown_rows : data limbs [limb_begin, limb_end) of ct [batch][2][L][N] += mod-down of their rows by the special prime (:1333-1376)
+ * A GPU that holds only the rows [r0, r1) passes d_rows offset by -r0 rows; only rows it names are touched. */
+int troyb_switch_key_partial_rows(troyb_context *ctx, int level, const uint64_t *d_target, size_t target_stride, const uint64_t *d_key,
+                                  int digit_begin, int digit_end, uint64_t *d_rows, size_t batch, void *stream);
+int troyb_switch_key_reduce_rows(troyb_context *ctx, int level, uint64_t *d_rows, int row_begin, int row_end, size_t batch, void *stream);
+int troyb_switch_key_special_row(troyb_context *ctx, int level, const uint64_t *d_rows, uint64_t *d_sp, size_t batch, void *stream);
+int troyb_switch_key_moddown_rows(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_stride, const uint64_t *d_rows,
+                                  const uint64_t *d_sp, int limb_begin, int limb_end, size_t batch, void *stream);
+
 /* EvaluatorCuda::relinearizeInternal, size 3 → 2  src/evaluator_cuda.cu:703-747: key-switch of poly 2 into polys 0,1 */
 int troyb_relinearize(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_stride, const uint64_t *d_relin_key,
                       size_t batch, void *stream);

@@ -2,8 +2,9 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py
 
-Checks, against the reference CPU library on every rank: (1) a digit-sharded relinearization (NCCL all-reduce of the
-partial key inner products) is word-for-word the reference's result; (2) independent-ciphertext sharding: every rank's
+Checks, against the reference CPU library on every rank: (1) a digit-sharded relinearization (NCCL reduce-scatter of the
+row-major partial key inner products, broadcast of the special row, all-gather of the finished limbs; and the all-reduce
+variant) is word-for-word the reference's result; (2) independent-ciphertext sharding: every rank's
 slice of a batch equals the reference."""
 import os
 import sys
@@ -33,14 +34,19 @@ def main():
         rlk = rc.relin_keys()
         L = ctx.level_limbs(0)
         mine = shard_range(L, world, rank)
-        ks = DigitShardedKeySwitch(ctx, rlk.words(0)[mine.start:mine.stop] if len(mine) else None, stream=stream)
         ntt = scheme == ref.CKKS
         sc = 2.0 ** 30 if ntt else 1.0
         batch = 4
         w = random_ct_words(rc, 0, 3, n, np.random.default_rng(11), batch=batch)
-        ct = tb.CiphertextCuda.from_host(ctx, w, 0, ntt, sc)
-        ks.relinearize_inplace(ct)
-        got = ct.to_host()
+        got = None
+        for mode in ("reduce_scatter", "all_reduce"):
+            ks = DigitShardedKeySwitch(ctx, rlk.words(0)[mine.start:mine.stop] if len(mine) else None, stream=stream, mode=mode)
+            ct = tb.CiphertextCuda.from_host(ctx, w, 0, ntt, sc)
+            ks.relinearize_inplace(ct)
+            torch.cuda.synchronize()
+            res = ct.to_host()
+            assert got is None or np.array_equal(got, res), f"rank {rank}: the two sharded variants differ (scheme {scheme})"
+            got = res
         # (2) each rank also checks only ITS ciphertexts of the batch through the unsharded path
         ev = tb.EvaluatorCuda(ctx, stream=stream)
         full = tb.RelinKeysCuda.from_host(ctx, {0: rlk.words(0)})

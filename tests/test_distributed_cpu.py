@@ -28,7 +28,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, scheme, n, bits, out):
+def _worker(rank, world, port, scheme, n, bits, mode, out):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
@@ -47,7 +47,7 @@ def _worker(rank, world, port, scheme, n, bits, out):
         key = rlk.words(0)
         L = ctx.level_limbs(0)
         mine = shard_range(L, world, rank)
-        ks = DigitShardedKeySwitch(ctx, key[mine.start:mine.stop] if len(mine) else None)
+        ks = DigitShardedKeySwitch(ctx, key[mine.start:mine.stop] if len(mine) else None, mode=mode)
         ntt = scheme == ref.CKKS
         w = random_ct_words(rc, 0, 3, n, np.random.default_rng(5), batch=2)   # same inputs in every rank
         ct = tb.CiphertextCuda.from_host(ctx, w, 0, ntt, 2.0 ** 30 if ntt else 1.0)
@@ -65,15 +65,16 @@ def _worker(rank, world, port, scheme, n, bits, out):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("mode", ["reduce_scatter", "all_reduce"])
 @pytest.mark.parametrize("scheme,n,bits", [(2, 4096, [50, 40, 40, 40, 50]), (1, 4096, [40, 36, 36, 40])])
-def test_digit_sharded_key_switch_world_size_2(ref, scheme, n, bits):
+def test_digit_sharded_key_switch_world_size_2(ref, scheme, n, bits, mode):
     import torch.multiprocessing as mp
     import __graft_entry__ as g
     g.build_emul()
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, scheme, n, bits, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, scheme, n, bits, mode, out)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:

@@ -185,7 +185,11 @@ template <int LOGT> struct NttInvTile2 {
         }
         const u32 rt = (1u << LOGC) + rank;
         const u32 rb = (rt << (LOGT - 10)) + warp;
-        auto st = [&](u32 i, u64 v) { inv_store_final(a, u, p, i, v); };
+        // the epilogue's mode is resolved once per launch, not once per stored word
+        const int mode = a.mode;
+        auto st_plain = [&](u32 i, u64 v) { u.dst[i] = v; };
+        auto st_half = [&](u32 i, u64 v) { u.dst[i] = a.add_half ? addmod(v, a.drop.half, p) : v; };
+        auto st_tail = [&](u32 i, u64 v) { inv_store_final(a, u, p, i, v); };
         TB_WITH_POLICY(pol, {
             const typename A::Mod m = A::make(md);
             const void *tw = A::inv_table(md);
@@ -201,11 +205,15 @@ template <int LOGT> struct NttInvTile2 {
             if constexpr (LOGC == 0) {
                 __syncthreads();
                 auto ld_own = [&](u32, u32 w) -> u64 { return sm[w]; };
-                inv_last_stage<A, LOGT, LOGC>(t, 0u, ld_own, st, md);
+                if (mode == INV_PLAIN) inv_last_stage<A, LOGT, LOGC>(t, 0u, ld_own, st_plain, md);
+                else if (mode == INV_ADD_HALF) inv_last_stage<A, LOGT, LOGC>(t, 0u, ld_own, st_half, md);
+                else inv_last_stage<A, LOGT, LOGC>(t, 0u, ld_own, st_tail, md);
             } else {
                 cluster_barrier();
                 auto ld_peer = [&](u32 tile, u32 w) -> u64 { return peers.ld(handle[tile], w); };
-                inv_last_stage<A, LOGT, LOGC>(t, rank, ld_peer, st, md);
+                if (mode == INV_PLAIN) inv_last_stage<A, LOGT, LOGC>(t, rank, ld_peer, st_plain, md);
+                else if (mode == INV_ADD_HALF) inv_last_stage<A, LOGT, LOGC>(t, rank, ld_peer, st_half, md);
+                else inv_last_stage<A, LOGT, LOGC>(t, rank, ld_peer, st_tail, md);
             }
         })
     }

@@ -191,7 +191,15 @@ TB_D void cluster_barrier() {
 template <class F, int S> TB_D void run_stages(const F &f, u32 rank, u32 nranks, u64 *smem, const Peers &peers) {
     if constexpr (S < F::kStages) {
         f.template stage<S>(blockIdx.x, gridDim.x, rank, nranks, smem, peers);
-        if (nranks > 1 && (S + 1 < F::kStages || F::kTrailingBarrier) && f.barrier_after(S)) cluster_barrier();
+        if (nranks > 1 && (S + 1 < F::kStages || F::kTrailingBarrier) && f.barrier_after(S)) {
+            if (S + 1 < F::kStages) {
+                cluster_barrier();
+            } else {
+                // trailing barrier: "nobody reads my shared memory any more" - execution ordering only, no memory fence
+                cluster_arrive_started();
+                cluster_wait_started();
+            }
+        }
         run_stages<F, S + 1>(f, rank, nranks, smem, peers);
     }
 }

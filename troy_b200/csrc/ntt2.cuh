@@ -372,15 +372,15 @@ template <class A, class First> TB_D void inv_block_stage(u64 *sm, u32 base, u32
             wc = wn;
         }
         __syncwarp();
-        TwSet<A, 4> wb;
 #pragma unroll 1
         for (int it = 0; it < 4; it++) {
             if (it < 3) wn.load(tw, Rb, 4, (lane >> 3) + 4u * (u32)(it + 1));
-            else wb.load(tw, Rb, 0, 0);
             m8_addr(base, lane, it, r0, r1);
             block_m8_group<A, true, RE>(sm, r0, r1, wc, m);
             wc = wn;
         }
+        TwSet<A, 4> wb; // uniform over the warp; requested before the warp synchronises
+        wb.load(tw, Rb, 0, 0);
         __syncwarp();
 #pragma unroll 1
         for (int it = 0; it < 2; it++) block_b16_group<A, true, RE || RM>(sm, b16_addr(base, lane, it), wb, m);
@@ -452,8 +452,15 @@ TB_D void fwd_first_stage_staged(const u64 *sm, u32 tid, u32 rank, Pro pro, StPe
 #pragma unroll
         for (int b = 0; b < B; b++) {
             const u32 pv = swz(tid + (u32)((g0 + b) * NT));
+            u64 raw[K];
 #pragma unroll
-            for (int k = 0; k < K; k++) x[b][k] = A::from_u64(pro(sm[pv + KS * (u32)k]), m);
+            for (int k = 0; k < K; k++) raw[k] = sm[pv + KS * (u32)k];
+            if (pro.mode != FWD_PLAIN) { // the prologue's mode branches stay out of the load sequence
+#pragma unroll
+                for (int k = 0; k < K; k++) raw[k] = pro(raw[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < K; k++) x[b][k] = A::from_u64(raw[k], m);
         }
         // every input of the batch has been issued ahead of the arrive (in order, to the same pipe), and the stores it
         // guards are a barrier round trip and a trip across the cluster away: the homes may be overwritten
@@ -483,8 +490,9 @@ TB_D void inv_last_stage(u32 tid, u32 rank, LdPeer ld_peer, St st, const ModDev 
     constexpr int F1 = P::F1, K = 1 << F1, VLOG = P::VLOG, NT = P::NT, G = ((1 << LOGT) / K) / NT;
     constexpr int B = K >= 16 ? 1 : (16 / K < G ? 16 / K : G);
     static_assert(G >= 1 && G % B == 0, "bad last stage");
-    // FP64 policies re-centre here as well (the network would otherwise start above the range its multiply accepts)
-    constexpr bool RE = A::kReduceEachInvRound || A::kReduceInvMidway;
+    // FP64 policies that re-centre in every round do it here as well; those that re-centre once, at the block's radix-16
+    // round, stay inside the 9 layers their multiply tolerates unless 4 + 3 + 3 layers follow it (N = 65536)
+    constexpr bool RE = A::kReduceEachInvRound || (A::kReduceInvMidway && P::MID && F1 >= 3);
     const typename A::Mod m = A::make(md);
     const void *tw = A::inv_table(md);
     const TwJit<A> twf{tw, 1u, 0u, 0u};

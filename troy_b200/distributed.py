@@ -6,10 +6,14 @@ Two modes, matching how the path shards:
   read-only tables and keys, so a batch is split across ranks with :func:`shard_range`, tables and keys are replicated,
   and there is NO collective on the data path (``bench.py --gpus N`` does exactly this);
 * **one key switch sharded by digit** (large N, many limbs: BASELINE.json config 5, where one key is 1.6 GiB): rank g holds
-  the key digits ``shard_range(L, world, g)``, runs the mod-up transforms and the key inner product for those digits only
-  (``troyb_switch_key_partial``), the partial products are summed across GPUs with ONE all-reduce (NCCL over NVLink /
-  NVSwitch; exact: at most 8 canonical residues below 2^60 fit 64 bits), and every rank finishes the mod-down
-  (``troyb_switch_key_finish`` with ``reduce_first``). The reference has no multi-GPU code at all.
+  the key digits ``shard_range(L, world, g)`` and runs the mod-up transforms and the key inner product for those digits only.
+  The partial products are kept ROW-major (``[L+1 output moduli][batch][2][N]``, ``troyb_switch_key_partial_rows``) and summed
+  with ONE reduce-scatter (NCCL over NVLink / NVSwitch; exact: at most 8 canonical residues below 2^60 fit 64 bits), so that
+  every rank receives, reduces and mod-downs only the rows (output moduli) it owns; the rounded special-prime row - 2 N words
+  per ciphertext, which every data limb's mod-down needs - is broadcast by its owner, and the finished limbs are all-gathered
+  into every rank's replica of the ciphertext. Everything is enqueued on one stream: no host synchronisation between the
+  kernels and the collectives. (``mode="all_reduce"`` keeps the simpler variant: one all-reduce of the whole product, every
+  rank finishing the whole mod-down.) The reference has no multi-GPU code at all.
 """
 import ctypes as C
 
@@ -32,10 +36,14 @@ class DigitShardedKeySwitch:
     ``key_words`` is this rank's slice ``[digit_begin:digit_end]`` of the key ``[digits][2][key_limbs][N]`` (host array or
     None when the slice is empty). ``group=None`` is the default group."""
 
-    def __init__(self, context, key_words, level=0, group=None, stream=None):
+    def __init__(self, context, key_words, level=0, group=None, stream=None, mode="reduce_scatter"):
         import torch.distributed as dist
         self.dist = dist
         self.context, self.level, self.group, self.stream = context, level, group, stream
+        if mode not in ("reduce_scatter", "all_reduce"):
+            raise TroyInvalidArgument("mode must be 'reduce_scatter' or 'all_reduce'")
+        self.mode = mode
+        self.bytes_sent = 0  # NVLink bytes this rank sent in the last key switch (algorithmic: ring reduce-scatter / all-gather)
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         if self.world > 8:
             raise TroyInvalidArgument("at most 8 partial products can be summed in 64 bits")
@@ -64,6 +72,8 @@ class DigitShardedKeySwitch:
         ctx = self.context
         if ct.parms_id != self.level:
             raise TroyInvalidArgument("ciphertext level does not match the sharded key")
+        if self.world > 1 and self.mode == "reduce_scatter":
+            return self._switch_key_rows(ct, target_ptr, target_stride)
         L, n = ctx.level_limbs(self.level), ctx.n
         dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
         prod = torch.zeros(ct.batch, 2, L + 1, n, dtype=torch.int64, device=dev)
@@ -80,6 +90,80 @@ class DigitShardedKeySwitch:
                  1 if self.world > 1 else 0, ct.batch, _vp(self.stream))
         if dev.type == "cuda":
             lib.call("troyb_stream_synchronize", _vp(self.stream))  # prod is released when this returns
+
+    def _on_stream(self):
+        """Context manager that makes the evaluator stream torch's current stream, so that torch's fills, copies and
+        collectives are ordered with the library's kernels without a host synchronisation."""
+        import contextlib
+        import torch
+        if self.stream is None or not torch.cuda.is_available():
+            return contextlib.nullcontext()
+        return torch.cuda.stream(torch.cuda.ExternalStream(int(self.stream)))
+
+    def _ct_view(self, ct):
+        """The ciphertext words as a torch tensor [batch][capacity][L][N] over the same memory (no copy)."""
+        import numpy as np
+        import torch
+        shape = (ct.batch, ct.capacity, ct.limbs, self.context.n)
+        if torch.cuda.is_available():
+            class _Cai:  # __cuda_array_interface__ view of memory the library owns
+                pass
+            v = _Cai()
+            v.__cuda_array_interface__ = {"shape": shape, "typestr": "<i8", "data": (int(ct.ptr()), False), "version": 2}
+            return torch.as_tensor(v, device=torch.device("cuda", torch.cuda.current_device()))
+        words = int(np.prod(shape))
+        buf = (C.c_int64 * words).from_address(int(ct.ptr()))
+        return torch.from_numpy(np.frombuffer(buf, dtype=np.int64).reshape(shape))
+
+    def _switch_key_rows(self, ct, target_ptr, target_stride):
+        """The reduce-scatter variant (see the module docstring)."""
+        import torch
+        ctx, dist, lib = self.context, self.dist, _lib.library()
+        L, n, B, W = ctx.level_limbs(self.level), ctx.n, ct.batch, self.world
+        per = -(-(L + 1) // W)                     # rows per rank (the last ranks' blocks may be short or empty)
+        r0 = min(self.rank * per, L + 1)
+        r1 = min(r0 + per, L + 1)
+        row_words = B * 2 * n
+        dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        nccl = dist.get_backend(self.group) == "nccl"
+        with self._on_stream():
+            s = _vp(self.stream)
+            rows = torch.zeros(per * W, B, 2, n, dtype=torch.int64, device=dev)
+            if self.digit_end > self.digit_begin:
+                lib.call("troyb_switch_key_partial_rows", _vp(ctx.h), self.level, _vp(target_ptr), target_stride,
+                         _vp(self._key_base()), self.digit_begin, self.digit_end, _vp(rows.data_ptr()), B, s)
+            if nccl:
+                mine = torch.empty(per, B, 2, n, dtype=torch.int64, device=dev)
+                dist.reduce_scatter_tensor(mine, rows, op=dist.ReduceOp.SUM, group=self.group)
+            else:  # gloo has no reduce-scatter: the same sums through an all-reduce (host-side tests)
+                dist.all_reduce(rows, op=dist.ReduceOp.SUM, group=self.group)
+                mine = rows[self.rank * per:(self.rank + 1) * per].contiguous()
+            # `mine` holds rows [r0, r0 + per); the library indexes rows from row 0
+            virt = mine.data_ptr() - 8 * r0 * row_words
+            if r1 > r0:
+                lib.call("troyb_switch_key_reduce_rows", _vp(ctx.h), self.level, _vp(virt), r0, r1, B, s)
+            sp = torch.empty(B, 2, n, dtype=torch.int64, device=dev)
+            owner = L // per
+            if self.rank == owner:
+                lib.call("troyb_switch_key_special_row", _vp(ctx.h), self.level, _vp(virt), _vp(sp.data_ptr()), B, s)
+            dist.broadcast(sp, src=dist.get_global_rank(self.group, owner) if self.group is not None else owner, group=self.group)
+            j1 = min(r1, L)
+            if j1 > r0:
+                lib.call("troyb_switch_key_moddown_rows", _vp(ctx.h), self.level, _vp(ct.ptr()), ct.stride, _vp(virt),
+                         _vp(sp.data_ptr()), r0, j1, B, s)
+            # every rank's replica of the ciphertext receives the limbs the others finished
+            view = self._ct_view(ct)
+            send = torch.zeros(per, B, 2, n, dtype=torch.int64, device=dev)
+            if j1 > r0:
+                send[:j1 - r0] = view[:, :2, r0:j1].permute(2, 0, 1, 3)
+            full = torch.empty(per * W, B, 2, n, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(full, send, group=self.group)
+            view[:, :2] = full[:L].permute(1, 2, 0, 3)
+            if dev.type == "cuda":
+                # the temporaries are torch tensors: the caching allocator keeps them for this stream
+                for t in (rows, mine, sp, send, full):
+                    t.record_stream(torch.cuda.current_stream())
+        self.bytes_sent = 8 * ((W - 1) * per * row_words * 2 + (B * 2 * n if self.rank == owner else 0))
 
     def relinearize_inplace(self, ct):
         """relinearizeInternal 3 -> 2 (src/evaluator_cuda.cu:703-747) with this (relinearization) key."""

@@ -73,6 +73,10 @@ _SIGNATURES = {
     "troyb_switch_key": (C.c_int, [_vp, C.c_int, _vp, _sz, _vp, _sz, _vp, _sz, _vp]),
     "troyb_switch_key_partial": (C.c_int, [_vp, C.c_int, _vp, _sz, _vp, C.c_int, C.c_int, _vp, _sz, _vp]),
     "troyb_switch_key_finish": (C.c_int, [_vp, C.c_int, _vp, _sz, _vp, C.c_int, _sz, _vp]),
+    "troyb_switch_key_partial_rows": (C.c_int, [_vp, C.c_int, _vp, _sz, _vp, C.c_int, C.c_int, _vp, _sz, _vp]),
+    "troyb_switch_key_reduce_rows": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, _sz, _vp]),
+    "troyb_switch_key_special_row": (C.c_int, [_vp, C.c_int, _vp, _vp, _sz, _vp]),
+    "troyb_switch_key_moddown_rows": (C.c_int, [_vp, C.c_int, _vp, _sz, _vp, _vp, C.c_int, C.c_int, _sz, _vp]),
     "troyb_relinearize": (C.c_int, [_vp, C.c_int, _vp, _sz, _vp, _sz, _vp]),
     "troyb_galois_permute": (C.c_int, [_vp, C.c_int, _vp, _vp, _sz, C.c_uint32, C.c_int, _vp]),
     "troyb_galois_elt_from_step": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_uint32)]),
