@@ -480,6 +480,63 @@ def run_ours(args):
                 "frac": dom_bytes / dom_s / 1e9 / hbm_peak, "traffic": traffic, "peak_source": peak_kind,
                 "share_of_step": dom["share"]}
 
+    # ---- N > 1: ONE large key switch sharded by digit over the GPUs (BASELINE config 5: CKKS N=65536, 40 digits, a 1.7 GB key):
+    # reduce-scatter of the row-major key products over NVLink, per-rank mod-down of the owned rows, all-gather. Checked
+    # against, and timed next to, the same key switch on ONE GPU (rank 0, whole key).
+    digit_sharded = None
+    if world > 1 and not args.no_sharded:
+        from troy_b200.distributed import DigitShardedKeySwitch, shard_range
+        n5, bits5, b5 = 65536, [60] + [50] * 39 + [60], 4
+        p5 = tb.EncryptionParameters(tb.SchemeType.ckks)
+        p5.set_poly_modulus_degree(n5)
+        p5.set_coeff_modulus(tb.CoeffModulus.Create(n5, bits5))
+        c5 = tb.SEALContextCuda(p5, expand_mod_chain=False)
+        l5 = c5.level_limbs(0)
+        kq5 = c5.level_moduli(-1)
+        g5 = torch.Generator(device=dev)
+        g5.manual_seed(0x5EED5)                     # the same key and ciphertexts on every rank
+        key5 = torch.empty(l5, 2, l5 + 1, n5, dtype=torch.int64, device=dev)
+        for i_, m_ in enumerate(kq5):
+            key5[:, :, i_, :] = torch.randint(0, m_, (l5, 2, n5), generator=g5, device=dev, dtype=torch.int64)
+        ct5_in = torch.empty(b5, 3, l5, n5, dtype=torch.int64, device=dev)
+        for i_, m_ in enumerate(kq5[:l5]):
+            ct5_in[:, :, i_, :] = torch.randint(0, m_, (b5, 3, n5), generator=g5, device=dev, dtype=torch.int64)
+        mine5 = shard_range(l5, world, rank)
+        ks5 = DigitShardedKeySwitch(c5, None, stream=stream, key_device_ptr=key5[mine5.start:mine5.stop].data_ptr() if len(mine5) else None)
+        ct5 = ct5_in.clone()
+        ct5_obj = tb.CiphertextCuda.from_device(c5, ct5.data_ptr(), b5, 2, 0, True, 2.0 ** 50, capacity=3)
+        tgt5 = ct5_in[:, 2].contiguous()            # the polynomial being switched, [batch][L][N]
+
+        def sharded():
+            ks5.switch_key_inplace(ct5_obj, tgt5.data_ptr(), l5 * n5)
+
+        sharded()
+        torch.cuda.synchronize()
+        first = ct5[:, :2].clone()
+        for _ in range(2):
+            sharded()
+        t_sh = timed(sharded, 5)
+        # one GPU, whole key (rank 0 measures; everybody runs it so that the GPUs stay in step)
+        ct5s = ct5_in.clone()
+
+        def single():
+            lib.call("troyb_switch_key", C.c_void_p(c5.h), 0, C.c_void_p(ct5s.data_ptr()), 3 * l5 * n5, C.c_void_p(tgt5.data_ptr()),
+                     l5 * n5, C.c_void_p(key5.data_ptr()), b5, C.c_void_p(stream))
+
+        single()
+        torch.cuda.synchronize()
+        same = bool(torch.equal(first, ct5s[:, :2]))
+        for _ in range(2):
+            single()
+        t_si = timed(single, 5)
+        ok_t = torch.tensor([1 if same else 0], device=dev)
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+        digit_sharded = {"config": f"CKKS N={n5} L={l5} (+1 special prime): one key switch of {l5} digits, digits sharded over {world} GPUs, batch {b5}",
+                         "mode": ks5.mode, "ops_per_s": b5 * 5 / t_sh, "single_gpu_ops_per_s": b5 * 5 / t_si, "vs_single_gpu": t_si / t_sh,
+                         "parity": bool(ok_t.item() == 1), "nvlink_bytes_sent_per_rank_per_call": ks5.bytes_sent,
+                         "collectives": "reduce_scatter (rows) + broadcast (special row) + all_gather (finished limbs), NCCL"}
+        del key5, ct5_in, ct5, ct5s, first
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -557,6 +614,7 @@ def run_ours(args):
                    "shape": f"{MB_}x{MI_} ciphertexts times {MI_}x{MJ_} plaintexts, one launch",
                    "gbs": mm_bytes * extra_steps / t_mm / 1e9, "frac_of_hbm_roofline": mm_bytes * extra_steps / t_mm / 1e9 / hbm_peak},
         "ntt_sweep": ntt_sweep,
+        "digit_sharded": digit_sharded,
         "latency": latency,
         "reference_cuda_path": ref_cuda,
         "seal_cpu_baseline": seal,
@@ -581,6 +639,7 @@ def main():
     ap.add_argument("--ref-reps", type=int, default=4, help="reference arm: ops per thread per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the config-2 NTT sweep (development runs)")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the digit-sharded large-N key switch")
     ap.add_argument("--e2e-chunk", type=int, default=16, help="end-to-end arm: ciphertext pairs per chunk")
     ap.add_argument("--e2e-streams", type=int, default=3, help="end-to-end arm: streams the chunks rotate over")
     args = ap.parse_args()

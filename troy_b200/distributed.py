@@ -34,9 +34,11 @@ class DigitShardedKeySwitch:
     """A key-switching key whose digits are sharded over the ranks of a process group.
 
     ``key_words`` is this rank's slice ``[digit_begin:digit_end]`` of the key ``[digits][2][key_limbs][N]`` (host array or
-    None when the slice is empty). ``group=None`` is the default group."""
+    None when the slice is empty; ``key_device_ptr`` instead when the slice is already on the device). ``group=None`` is the
+    default group. ``stream`` is the CUDA stream the kernels run on: torch must be on the same stream when the default stream
+    is used (None or 0); any other stream is made torch's current stream for the duration of a key switch."""
 
-    def __init__(self, context, key_words, level=0, group=None, stream=None, mode="reduce_scatter"):
+    def __init__(self, context, key_words, level=0, group=None, stream=None, mode="reduce_scatter", key_device_ptr=None):
         import torch.distributed as dist
         self.dist = dist
         self.context, self.level, self.group, self.stream = context, level, group, stream
@@ -53,7 +55,11 @@ class DigitShardedKeySwitch:
         key_limbs = context.level_limbs(SEALContextCuda.KEY_LEVEL)
         self.digit_words = 2 * key_limbs * context.n
         self.key = None
-        if len(r):
+        if key_device_ptr is not None:
+            # this rank's slice already lives on the device (the caller keeps it alive)
+            from .host import ExternalArray
+            self.key = ExternalArray(int(key_device_ptr), len(r) * self.digit_words)
+        elif len(r):
             import numpy as np
             a = np.ascontiguousarray(key_words, dtype=np.uint64)
             if a.shape != (len(r), 2, key_limbs, context.n):
@@ -96,8 +102,8 @@ class DigitShardedKeySwitch:
         collectives are ordered with the library's kernels without a host synchronisation."""
         import contextlib
         import torch
-        if self.stream is None or not torch.cuda.is_available():
-            return contextlib.nullcontext()
+        if not self.stream or not torch.cuda.is_available():
+            return contextlib.nullcontext()  # the default stream: torch must be on it as well
         return torch.cuda.stream(torch.cuda.ExternalStream(int(self.stream)))
 
     def _ct_view(self, ct):
