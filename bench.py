@@ -369,6 +369,26 @@ def run_ours(args):
     t_nf = timed(ntt_f, extra_steps)
     t_ni = timed(ntt_i, extra_steps)
     limbs = ntt_polys * L
+    # the same transform on this configuration's 40-bit limbs alone (7 of its 8 data limbs; FP64 butterflies) - the mixed figure
+    # above is the sum of the two kinds' times (60-bit limbs run integer butterflies: see ntt_sweep)
+    q40 = tb.CoeffModulus.Create(N, [40] * L + [60])
+    p40 = tb.EncryptionParameters(tb.SchemeType.ckks)
+    p40.set_poly_modulus_degree(N)
+    p40.set_coeff_modulus(q40)
+    c40 = tb.SEALContextCuda(p40, expand_mod_chain=False)
+
+    def ntt_f40():
+        lib.call("troyb_ntt_forward", C.c_void_p(c40.h), 0, C.c_void_p(ntt_buf.data_ptr()), ntt_polys, C.c_void_p(stream))
+
+    def ntt_i40():
+        lib.call("troyb_ntt_inverse", C.c_void_p(c40.h), 0, C.c_void_p(ntt_buf.data_ptr()), ntt_polys, C.c_void_p(stream))
+
+    ntt_buf.bitwise_and_((1 << 39) - 1)  # valid residues of every 40-bit prime
+    for _ in range(3):
+        ntt_f40()
+        ntt_i40()
+    t_nf40 = timed(ntt_f40, extra_steps)
+    t_ni40 = timed(ntt_i40, extra_steps)
 
     # ---- BASELINE config 2: the standalone batched NTT / INTT sweep, N = 4096 .. 65536 x {1, 8, 32} limbs of 60-bit primes,
     # in place on at least 512 MiB of polynomials (> L2) per launch
@@ -609,7 +629,11 @@ def run_ours(args):
                 "forward_gbs": limbs * extra_steps / t_nf * bytes_["limb_ntt"] / 1e9,
                 "forward_frac_of_hbm_roofline": limbs * extra_steps / t_nf * bytes_["limb_ntt"] / 1e9 / hbm_peak,
                 "inverse_frac_of_hbm_roofline": limbs * extra_steps / t_ni * bytes_["limb_ntt"] / 1e9 / hbm_peak,
-                "shape": f"{ntt_polys} polys x {L} limbs, N={N}"},
+                "shape": f"{ntt_polys} polys x {L} limbs, N={N}",
+                "limbs_40bit_only": {"forward_limb_ntt_per_s": world * limbs * extra_steps / t_nf40,
+                                     "inverse_limb_ntt_per_s": world * limbs * extra_steps / t_ni40,
+                                     "forward_frac_of_hbm_roofline": limbs * extra_steps / t_nf40 * bytes_["limb_ntt"] / 1e9 / hbm_peak,
+                                     "inverse_frac_of_hbm_roofline": limbs * extra_steps / t_ni40 * bytes_["limb_ntt"] / 1e9 / hbm_peak}},
         "matmul": {"multiply_plain_accumulate_per_s": world * mm_terms * extra_steps / t_mm, "ms": t_mm / extra_steps * 1e3,
                    "shape": f"{MB_}x{MI_} ciphertexts times {MI_}x{MJ_} plaintexts, one launch",
                    "gbs": mm_bytes * extra_steps / t_mm / 1e9, "frac_of_hbm_roofline": mm_bytes * extra_steps / t_mm / 1e9 / hbm_peak},

@@ -53,6 +53,22 @@ inline void check(int rc) {
     }
 }
 
+// The CUDA stream every call of the calling host thread is enqueued on (allocations, copies and kernels: one stream keeps them
+// ordered without host synchronisation). Default: the legacy default stream, like the reference (which has no stream
+// arguments at all). troyn::b200::setStream(s) / StreamGuard select another one, e.g. one stream per worker thread.
+inline void *&stream_slot() { static thread_local void *s = nullptr; return s; }
+inline void *stream() { return stream_slot(); }
+inline void setStream(void *cuda_stream) { stream_slot() = cuda_stream; }
+inline void synchronize() { check(troyb_stream_synchronize(stream())); }
+struct StreamGuard {
+    explicit StreamGuard(void *s) : prev_(stream()) { setStream(s); }
+    ~StreamGuard() { setStream(prev_); }
+    StreamGuard(const StreamGuard &) = delete;
+    StreamGuard &operator=(const StreamGuard &) = delete;
+private:
+    void *prev_;
+};
+
 // Owning device buffer of 64-bit words (util::DeviceArray<uint64_t>, src/utils/devicearray.cuh:90-200)
 class DeviceWords {
 public:
@@ -63,7 +79,7 @@ public:
     DeviceWords &operator=(const DeviceWords &o) {
         if (this == &o) return *this;
         allocate(o.n_);
-        if (n_) check(troyb_copy_on_device(p_, o.p_, n_ * 8, nullptr));
+        if (n_) check(troyb_copy_on_device(p_, o.p_, n_ * 8, b200::stream()));
         return *this;
     }
     DeviceWords &operator=(DeviceWords &&o) noexcept {
@@ -74,19 +90,19 @@ public:
     void allocate(std::size_t words) {
         if (words == n_ && p_) return;
         release();
-        if (words) { void *p = nullptr; check(troyb_malloc(&p, words * 8, nullptr)); p_ = static_cast<std::uint64_t *>(p); n_ = words; }
+        if (words) { void *p = nullptr; check(troyb_malloc(&p, words * 8, b200::stream())); p_ = static_cast<std::uint64_t *>(p); n_ = words; }
     }
     void upload(const std::uint64_t *h, std::size_t words, std::size_t at = 0) {
-        if (words) { check(troyb_copy_to_device(p_ + at, h, words * 8, nullptr)); check(troyb_stream_synchronize(nullptr)); }
+        if (words) { check(troyb_copy_to_device(p_ + at, h, words * 8, b200::stream()));  }
     }
     void download(std::uint64_t *h, std::size_t words, std::size_t at = 0) const {
-        if (words) check(troyb_copy_to_host(h, p_ + at, words * 8, nullptr));
+        if (words) check(troyb_copy_to_host(h, p_ + at, words * 8, b200::stream()));
     }
     std::uint64_t *get() const { return p_; }
     std::size_t size() const { return n_; }
 
 private:
-    void release() { if (p_) troyb_free(p_, nullptr); p_ = nullptr; n_ = 0; }
+    void release() { if (p_) troyb_free(p_, b200::stream()); p_ = nullptr; n_ = 0; }
     std::uint64_t *p_ = nullptr;
     std::size_t n_ = 0;
 };
@@ -409,7 +425,7 @@ private:
         b200::DeviceWords fresh(size * n * limbs);
         if (n == n_ && limbs == limbs_) {
             const std::size_t keep = std::min(size_, size) * n * limbs;
-            if (keep) b200::check(troyb_copy_on_device(fresh.get(), data_.get(), keep * 8, nullptr));
+            if (keep) b200::check(troyb_copy_on_device(fresh.get(), data_.get(), keep * 8, b200::stream()));
         }
         data_ = std::move(fresh);
         size_ = size; n_ = n; limbs_ = limbs;
@@ -527,7 +543,7 @@ public:
         const std::size_t need = ct.size() - 1;
         if (need > n_powers_) { // computeSecretKeyArray  src/decryptor_cuda.cu:188-235
             b200::DeviceWords p(need * key_words_);
-            b200::check(troyb_secret_key_powers(context_.handle(), powers_.get(), need, p.get(), nullptr));
+            b200::check(troyb_secret_key_powers(context_.handle(), powers_.get(), need, p.get(), b200::stream()));
             powers_ = std::move(p);
             n_powers_ = need;
         }
@@ -535,7 +551,7 @@ public:
         const std::size_t n = ct.polyModulusDegree(), words = ct.polyCoeffSize();
         b200::DeviceWords phase(words);
         b200::check(troyb_decrypt_dot_product(context_.handle(), lv, ct.data(), ct.size(), ct.size() * words, ct.isNttForm() ? 1 : 0,
-                                              powers_.get(), phase.get(), 1, nullptr));
+                                              powers_.get(), phase.get(), 1, b200::stream()));
         dst.parmsID() = parmsIDZero;
         if (s == SchemeType::ckks) { // ckksDecrypt  src/decryptor_cuda.cu:118-141
             dst.resize(words);
@@ -546,13 +562,13 @@ public:
         }
         b200::DeviceWords out(n);
         if (s == SchemeType::bfv) {
-            b200::check(troyb_decrypt_scale_and_round(context_.handle(), lv, phase.get(), out.get(), 1, nullptr));
+            b200::check(troyb_decrypt_scale_and_round(context_.handle(), lv, phase.get(), out.get(), 1, b200::stream()));
         } else {
             std::uint64_t fix = 1;
             const auto &t = context_.firstContextData()->parms().plainModulus();
             if (ct.correctionFactor() != 1 && !util::tryInvertUintMod(ct.correctionFactor(), t, fix))
                 throw std::logic_error("invalid correction factor");
-            b200::check(troyb_decrypt_mod_t(context_.handle(), lv, phase.get(), out.get(), fix, 1, nullptr));
+            b200::check(troyb_decrypt_mod_t(context_.handle(), lv, phase.get(), out.get(), fix, 1, b200::stream()));
         }
         dst.resize(n);
         out.download(dst.data(), n);
@@ -576,7 +592,7 @@ public:
 
     // ---- add / sub / negate (src/evaluator_cuda.cu:143-260)
     void negateInplace(CiphertextCuda &ct) const {
-        b200::check(troyb_negate(h(), level(ct), ct.data(), ct.data(), ct.size(), nullptr));
+        b200::check(troyb_negate(h(), level(ct), ct.data(), ct.data(), ct.size(), b200::stream()));
     }
     void negate(const CiphertextCuda &a, CiphertextCuda &dst) const { dst = a; negateInplace(dst); }
     void addInplace(CiphertextCuda &a, const CiphertextCuda &b) const { addSub(a, b, false); }
@@ -611,7 +627,7 @@ public:
         a.resize(out); // keeps the first a_size polynomials
         const std::uint64_t *pb = square ? a.data() : b.data();
         b200::check(troyb_multiply(h(), lv, a.data(), a_size, stride, pb, b_size, square ? stride : b_size * b.polyCoeffSize(), a.data(),
-                                   stride, 1, nullptr));
+                                   stride, 1, b200::stream()));
         if (s == SchemeType::ckks) a.scale() = new_scale;
         if (s == SchemeType::bgv) {
             const std::uint64_t t = context_.firstContextData()->parms().plainModulus().value();
@@ -631,7 +647,7 @@ public:
         if (ct.size() != 3) throw std::logic_error("relinearization of size > 3 is outside the ported path");
         checkKeySwitch(ct, rlk);
         if (!rlk.hasKey(2)) throw std::invalid_argument("not enough relinearization keys");
-        b200::check(troyb_relinearize(h(), level(ct), ct.data(), 3 * ct.polyCoeffSize(), rlk.key(RelinKeysCuda::getIndex(2)), 1, nullptr));
+        b200::check(troyb_relinearize(h(), level(ct), ct.data(), 3 * ct.polyCoeffSize(), rlk.key(RelinKeysCuda::getIndex(2)), 1, b200::stream()));
         ct.resize(2);
     }
     void relinearize(const CiphertextCuda &ct, const RelinKeysCuda &rlk, CiphertextCuda &dst) const { dst = ct; relinearizeInplace(dst, rlk); }
@@ -644,7 +660,7 @@ public:
         if (ct.size() > 2) throw std::invalid_argument("encrypted size must be 2");
         if (!gk.hasKey(elt)) throw std::invalid_argument("Galois key not present");
         checkKeySwitch(ct, gk);
-        b200::check(troyb_apply_galois(h(), level(ct), ct.data(), 2 * ct.polyCoeffSize(), elt, gk.key(GaloisKeysCuda::getIndex(elt)), 1, nullptr));
+        b200::check(troyb_apply_galois(h(), level(ct), ct.data(), 2 * ct.polyCoeffSize(), elt, gk.key(GaloisKeysCuda::getIndex(elt)), 1, b200::stream()));
     }
     void applyGalois(const CiphertextCuda &ct, std::uint32_t elt, const GaloisKeysCuda &gk, CiphertextCuda &dst) const { dst = ct; applyGaloisInplace(dst, elt, gk); }
     void rotateRowsInplace(CiphertextCuda &ct, int steps, const GaloisKeysCuda &gk) const {
@@ -687,7 +703,7 @@ public:
         const std::size_t n = ct.polyModulusDegree(), L = ct.coeffModulusSize();
         b200::DeviceWords out(ct.size() * (L - 1) * n);
         for (std::size_t p = 0; p < ct.size(); p++)
-            b200::check(troyb_copy_on_device(out.get() + p * (L - 1) * n, ct.data(p), (L - 1) * n * 8, nullptr));
+            b200::check(troyb_copy_on_device(out.get() + p * (L - 1) * n, ct.data(p), (L - 1) * n * 8, b200::stream()));
         CiphertextCuda r = metaOf(ct);
         r.adopt(std::move(out), ct.size(), n, L - 1);
         r.parmsID() = context_.parmsIDOf(lv + 1);
@@ -703,12 +719,12 @@ public:
     // ---- NTT transforms (src/evaluator_cuda.cu:1950-2022)
     void transformToNttInplace(CiphertextCuda &ct) const {
         if (ct.isNttForm()) throw std::invalid_argument("encrypted is already in NTT form");
-        b200::check(troyb_ntt_forward(h(), level(ct), ct.data(), ct.size(), nullptr));
+        b200::check(troyb_ntt_forward(h(), level(ct), ct.data(), ct.size(), b200::stream()));
         ct.isNttForm() = true;
     }
     void transformFromNttInplace(CiphertextCuda &ct) const {
         if (!ct.isNttForm()) throw std::invalid_argument("encrypted_ntt is not in NTT form");
-        b200::check(troyb_ntt_inverse(h(), level(ct), ct.data(), ct.size(), nullptr));
+        b200::check(troyb_ntt_inverse(h(), level(ct), ct.data(), ct.size(), b200::stream()));
         ct.isNttForm() = false;
     }
     // ---- ciphertext (x) plaintext (src/evaluator_cuda.cu:1555-1935). Plaintexts keep their host representation in this
@@ -726,12 +742,12 @@ public:
         if (ct.isNttForm()) {
             // multiplyPlainNtt  src/evaluator_cuda.cu:1818-1862
             if (ct.parmsID() != plain.parmsID()) throw std::invalid_argument("encrypted_ntt and plain_ntt parameter mismatch");
-            b200::check(troyb_multiply_plain_ntt(h(), lv, ct.data(), ct.size(), stride, d.get(), 0, ct.data(), stride, 1, 0, nullptr));
+            b200::check(troyb_multiply_plain_ntt(h(), lv, ct.data(), ct.size(), stride, d.get(), 0, ct.data(), stride, 1, 0, b200::stream()));
             ct.scale() *= plain.scale();
             if (!scaleWithinBounds(ct.scale(), ct.parmsID())) throw std::invalid_argument("scale out of bounds");
         } else {
             // multiplyPlainNormal  src/evaluator_cuda.cu:1757-1816
-            b200::check(troyb_multiply_plain_normal(h(), lv, ct.data(), ct.size(), stride, d.get(), plain.coeffCount(), 1, nullptr));
+            b200::check(troyb_multiply_plain_normal(h(), lv, ct.data(), ct.size(), stride, d.get(), plain.coeffCount(), 1, b200::stream()));
             if (scheme() == SchemeType::ckks) {
                 ct.scale() *= plain.scale();
                 if (!scaleWithinBounds(ct.scale(), ct.parmsID())) throw std::invalid_argument("scale out of bounds");
@@ -747,7 +763,7 @@ public:
         const std::size_t n = cd->parms().polyModulusDegree(), L = cd->parms().coeffModulus().size(), count = plain.coeffCount();
         b200::DeviceWords in(count), out(L * n);
         in.upload(plain.data(), count);
-        b200::check(troyb_plain_lift(h(), context_.levelOf(parms_id), in.get(), count, count, out.get(), 1, 1, nullptr));
+        b200::check(troyb_plain_lift(h(), context_.levelOf(parms_id), in.get(), count, count, out.get(), 1, 1, b200::stream()));
         plain.resize(L * n);
         out.download(plain.data(), L * n);
         plain.parmsID() = parms_id;
@@ -791,10 +807,10 @@ private:
         if (s == SchemeType::ckks) {
             // kAddPolyCoeffmod / kSubPolyCoeffmod on poly 0  src/evaluator_cuda.cu:1607-1612,1680-1685
             if (plain.coeffCount() != ct.polyCoeffSize()) throw std::invalid_argument("plain is not valid for encryption parameters");
-            b200::check((sub ? troyb_sub : troyb_add)(h(), lv, ct.data(), d.get(), ct.data(), 1, nullptr));
+            b200::check((sub ? troyb_sub : troyb_add)(h(), lv, ct.data(), d.get(), ct.data(), 1, b200::stream()));
         } else {
             b200::check(troyb_add_plain(h(), lv, ct.data(), ct.size() * ct.polyCoeffSize(), d.get(), plain.coeffCount(), 0,
-                                        ct.correctionFactor(), sub ? 1 : 0, 1, nullptr));
+                                        ct.correctionFactor(), sub ? 1 : 0, 1, b200::stream()));
         }
     }
     void checkKeySwitch(const CiphertextCuda &ct, const KSwitchKeysCuda &keys) const {
@@ -814,8 +830,8 @@ private:
             std::uint64_t f, e1, e2;
             balanceCorrectionFactors(a.correctionFactor(), b.correctionFactor(), t, f, e1, e2);
             CiphertextCuda b2 = b;
-            b200::check(troyb_multiply_scalar(h(), level(a), a.data(), e1, a.data(), a.size(), nullptr));
-            b200::check(troyb_multiply_scalar(h(), level(b2), b2.data(), e2, b2.data(), b2.size(), nullptr));
+            b200::check(troyb_multiply_scalar(h(), level(a), a.data(), e1, a.data(), a.size(), b200::stream()));
+            b200::check(troyb_multiply_scalar(h(), level(b2), b2.data(), e2, b2.data(), b2.size(), b200::stream()));
             a.correctionFactor() = f;
             b2.correctionFactor() = f;
             addSub(a, b2, sub);
@@ -826,10 +842,10 @@ private:
         const int lv = level(a);
         const std::size_t a_old = a.size(), mn = std::min(a.size(), b.size()), mx = std::max(a.size(), b.size());
         a.resize(mx);
-        b200::check((sub ? troyb_sub : troyb_add)(h(), lv, a.data(), b.data(), a.data(), mn, nullptr));
+        b200::check((sub ? troyb_sub : troyb_add)(h(), lv, a.data(), b.data(), a.data(), mn, b200::stream()));
         if (a_old < b.size()) {
-            if (!sub) b200::check(troyb_copy_on_device(a.data(a_old), b.data(a_old), (b.size() - a_old) * a.polyCoeffSize() * 8, nullptr));
-            else b200::check(troyb_negate(h(), lv, b.data(a_old), a.data(a_old), b.size() - a_old, nullptr));
+            if (!sub) b200::check(troyb_copy_on_device(a.data(a_old), b.data(a_old), (b.size() - a_old) * a.polyCoeffSize() * 8, b200::stream()));
+            else b200::check(troyb_negate(h(), lv, b.data(a_old), a.data(a_old), b.size() - a_old, b200::stream()));
         }
     }
     // balanceCorrectionFactors (src/evaluator_cuda.cu:53-114): the pair (e1, e2) with e1 f1 = e2 f2 (mod t) of least
@@ -882,7 +898,7 @@ private:
         if (s != SchemeType::ckks && ct.isNttForm()) throw std::invalid_argument(s == SchemeType::bfv ? "BFV encrypted cannot be in NTT form" : "BGV encrypted cannot be in NTT form");
         const std::size_t n = ct.polyModulusDegree(), L = ct.coeffModulusSize();
         b200::DeviceWords out(ct.size() * (L - 1) * n);
-        b200::check(troyb_mod_switch_scale_to_next(h(), lv, ct.data(), ct.size() * L * n, out.get(), ct.size() * (L - 1) * n, ct.size(), 1, nullptr));
+        b200::check(troyb_mod_switch_scale_to_next(h(), lv, ct.data(), ct.size() * L * n, out.get(), ct.size() * (L - 1) * n, ct.size(), 1, b200::stream()));
         const auto &q = context_.getContextData(ct.parmsID())->parms().coeffModulus();
         const std::uint64_t q_last = q.back().value();
         CiphertextCuda r = metaOf(ct);

@@ -17,6 +17,9 @@ def bench_step(batch):
         ("EltTensor", 256 * batch): "ct_tensor_product", ("NttInvTile<13>", 16 * batch): "ntt_inv",
         ("NttFwdTile<13>", 144 * batch): "ntt_fwd_modup", ("NttInvTile<13>", 4 * batch): "ntt_inv_add_half",
         ("NttFwdTile<13>", 32 * batch): "ntt_fwd_moddown",
+        # second-generation transforms (round 2)
+        ("NttInvTile2<13>", 16 * batch): "ntt_inv", ("NttFwdTile2<13>", 144 * batch): "ntt_fwd_modup",
+        ("NttInvTile2<13>", 4 * batch): "ntt_inv_add_half", ("NttFwdTile2<13>", 32 * batch): "ntt_fwd_moddown",
     }
 
 
