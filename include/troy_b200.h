@@ -214,6 +214,47 @@ int troyb_add_plain(troyb_context *ctx, int level, uint64_t *d_c0, size_t ct_str
                     size_t plain_coeff_count, size_t plain_stride, uint64_t correction_factor, int subtract, size_t batch,
                     void *stream);
 
+/* ---- encryption: the step right before the path --------------------------------------------------
+ * The reference's CPU encryptor draws from ONE sequential byte stream per call (Blake2xbPRNG, src/randomgen.cpp:184-194:
+ * 4096-byte buffers, buffer c = BLAKE2Xb(key = 64-byte seed, input = c)). These entry points reproduce that stream and the
+ * samplers' consumption of it on the device, so that for the same seed the ciphertext words equal the CPU path's
+ * (the reference's CUDA encryptor, src/utils/rlwe_cuda.cu:193-333, draws from cuRAND and matches neither).
+ * The ternary sampler follows libstdc++'s std::uniform_int_distribution (GCC >= 11), which is what the reference CPU library
+ * executes when built with this image's toolchain. Seeds: 8 words (64 bytes) per generator, device memory. */
+
+/* UniformRandomGenerator::generate  src/randomgen.cpp:164-180: the first `bytes` (a multiple of 4096) of the stream of each of
+ * `batch` generators; seeds seed_stride words apart, outputs out_stride words apart. */
+int troyb_prng_fill(const uint64_t *d_seeds, size_t seed_stride, uint64_t *d_out, size_t out_stride, size_t bytes, size_t batch,
+                    void *stream);
+
+/* util::samplePolyTernary / samplePolyCbd / samplePolyUniform  src/utils/rlwe.cpp:21-41, 71-105, 123-158 over the base of
+ * `level` (-1: key level): d_out [batch][L][N]. The draws are taken from the expanded stream d_stream (stream_bytes per
+ * generator, stream_stride words apart) starting at byte start_bytes (uniform: 0); positions past stream_bytes are computed
+ * from d_seeds on demand (d_seeds may be NULL when the expanded part is known to suffice). d_end_bytes (optional, [batch]):
+ * the generator's position after the ternary sampler (it moves by 4 bytes per draw, rejected draws included). */
+int troyb_sample_poly_ternary(troyb_context *ctx, int level, const uint64_t *d_stream, size_t stream_stride, size_t stream_bytes,
+                              const uint64_t *d_seeds, size_t seed_stride, uint64_t start_bytes, uint64_t *d_out, size_t out_stride,
+                              uint64_t *d_end_bytes, size_t batch, void *stream);
+int troyb_sample_poly_cbd(troyb_context *ctx, int level, const uint64_t *d_stream, size_t stream_stride, size_t stream_bytes,
+                          const uint64_t *d_seeds, size_t seed_stride, uint64_t start_bytes, uint64_t *d_out, size_t out_stride,
+                          size_t batch, void *stream);
+int troyb_sample_poly_uniform(troyb_context *ctx, int level, const uint64_t *d_stream, size_t stream_stride, size_t stream_bytes,
+                              const uint64_t *d_seeds, size_t seed_stride, uint64_t *d_out, size_t out_stride, size_t batch,
+                              void *stream);
+
+/* util::encryptZeroAsymmetric  src/utils/rlwe.cpp:160-243 as Encryptor::encryptZeroInternal calls it (src/encryptor.cpp:88-164):
+ * encryption of zero under the public key at `level` (-1: key level), d_ct [batch][2][L][N]; when the chain has a level above
+ * `level` the encryption is done there and divided by that level's last prime (the special prime for level 0).
+ * d_public_key: [2][key limbs][N], NTT form at the key level. d_seeds: [batch][8], one generator per ciphertext
+ * (parms.randomGenerator()->create()). CKKS results are in NTT form, BFV / BGV in coefficient form. */
+int troyb_encrypt_zero_asymmetric(troyb_context *ctx, int level, const uint64_t *d_public_key, const uint64_t *d_seeds,
+                                  uint64_t *d_ct, size_t ct_stride, size_t batch, void *stream);
+
+/* util::encryptZeroSymmetric  src/utils/rlwe.cpp:245-356 (save_seed = false): (c0, c1) = (-(a s + e), a) at `level` (-1: key
+ * level — KeyGenerator's public key). d_secret_key: [key limbs][N], NTT form at the key level. */
+int troyb_encrypt_zero_symmetric(troyb_context *ctx, int level, const uint64_t *d_secret_key, const uint64_t *d_seeds, uint64_t *d_ct,
+                                 size_t ct_stride, size_t batch, void *stream);
+
 /* ---- decryption: the step right after the path ------------------------------------------------- */
 
 /* DecryptorCuda::computeSecretKeyArray  src/decryptor_cuda.cu:188-235: d_out[i] = s^(i+1), i < max_power, each

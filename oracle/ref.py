@@ -77,6 +77,12 @@ def lib():
             "ref_decrypt_batch": (C.c_int, [vp, vp, u64p]),
             "ref_encrypt_ckks": (vp, [vp, dp, C.c_int, C.c_double]),
             "ref_decrypt_ckks": (C.c_int, [vp, vp, dp]),
+            "ref_prng_bytes": (C.c_int, [u64p, C.c_uint64, C.POINTER(C.c_uint8)]),
+            "ref_sample_poly": (C.c_int, [vp, C.c_int, C.c_int, u64p, C.c_uint64, u64p, u64p]),
+            "ref_sample_poly_replay": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.c_uint64, C.c_uint64, u64p, u64p]),
+            "ref_public_key_words": (C.c_int64, [vp, u64p]),
+            "ref_encrypt_zero": (vp, [vp, C.c_int, C.c_int]),
+            "ref_encrypt_plain": (vp, [vp, vp, C.c_int]),
             "ref_time_ops": (C.c_double, [vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int]),
             "ref_time_ntt": (C.c_double, [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int]),
         }
@@ -326,6 +332,49 @@ class RefContext:
             raise RefError(_err())
         return a
 
+    def public_key_words(self):
+        """[2][key_limbs][N] NTT-form words of the public key (after keygen())."""
+        kl = len(self.level_moduli(-1))
+        out = np.zeros((2, kl, self.n), dtype=np.uint64)
+        if lib().ref_public_key_words(self.h, _p(out)) != out.size:
+            raise RefError(_err())
+        return out
+
+    def sample_poly(self, level, which, seed, skip_bytes=0):
+        """util::samplePolyTernary (0) / samplePolyCbd (1) / samplePolyUniform (2) from a fresh Blake2xbPRNG(seed) after
+        skip_bytes of its stream: ([L][N] words, stream position afterwards)."""
+        L = len(self.level_moduli(level))
+        out = np.zeros((L, self.n), dtype=np.uint64)
+        sd = np.ascontiguousarray(seed, dtype=np.uint64)
+        pos = np.zeros(1, dtype=np.uint64)
+        if lib().ref_sample_poly(self.h, level, which, _p(sd), skip_bytes, _p(out), _p(pos)) != 0:
+            raise RefError(_err())
+        return out, int(pos[0])
+
+    def sample_poly_replay(self, level, which, stream, skip_bytes=0):
+        """The same samplers drawing from the given byte stream (uint8 array; zeros past its end)."""
+        L = len(self.level_moduli(level))
+        out = np.zeros((L, self.n), dtype=np.uint64)
+        st = np.ascontiguousarray(stream, dtype=np.uint8)
+        pos = np.zeros(1, dtype=np.uint64)
+        if lib().ref_sample_poly_replay(self.h, level, which, st.ctypes.data_as(C.POINTER(C.c_uint8)), st.size, skip_bytes,
+                                        _p(out), _p(pos)) != 0:
+            raise RefError(_err())
+        return out, int(pos[0])
+
+    def encrypt_zero(self, level=0, asymmetric=True):
+        """Encryptor::encryptZero / encryptZeroSymmetric at a level (-1: key level), generator seeded as the context was."""
+        h = lib().ref_encrypt_zero(self.h, level, int(asymmetric))
+        if not h:
+            raise RefError(_err())
+        return RefCiphertext(self, h)
+
+    def encrypt_plain(self, pt, asymmetric=True):
+        h = lib().ref_encrypt_plain(self.h, pt.h, int(asymmetric))
+        if not h:
+            raise RefError(_err())
+        return RefCiphertext(self, h)
+
     def encrypt_batch(self, values):
         v = np.ascontiguousarray(values, dtype=np.uint64)
         h = lib().ref_encrypt_batch(self.h, _p(v), len(v))
@@ -371,3 +420,12 @@ def ntt_prime(n, prime, data, inverse=False, reps=1):
 
 def time_ntt(n, prime, inverse, reps, threads):
     return lib().ref_time_ntt(n, prime, int(inverse), reps, threads)
+
+
+def prng_bytes(seed, nbytes):
+    """The first nbytes of Blake2xbPRNG(seed)'s stream (src/randomgen.cpp:164-194)."""
+    sd = np.ascontiguousarray(seed, dtype=np.uint64)
+    out = np.zeros(nbytes, dtype=np.uint8)
+    if lib().ref_prng_bytes(_p(sd), nbytes, out.ctypes.data_as(C.POINTER(C.c_uint8))) != 0:
+        raise RefError(_err())
+    return out

@@ -16,6 +16,7 @@
 #include "utils/ntt.h"
 #include "utils/galois.h"
 #include "utils/polyarithsmallmod.h"
+#include "utils/rlwe.h"
 
 #include <cstring>
 #include <memory>
@@ -616,6 +617,120 @@ double ref_time_ntt(uint64_t n, uint64_t prime, int inverse, int reps, int threa
     auto t1 = std::chrono::steady_clock::now();
     return std::chrono::duration<double>(t1 - t0).count();
     REF_CATCH(-1.0)
+}
+
+} // extern "C"
+
+// ---- generator, samplers, encrypt-zero (src/randomgen.cpp, src/utils/rlwe.cpp, src/encryptor.cpp) ---------------------------
+namespace {
+// A Blake2xbPRNG that knows how many bytes have been drawn from it (the stream position the device samplers must reproduce).
+struct CountingBlake2xb : Blake2xbPRNG {
+    using Blake2xbPRNG::Blake2xbPRNG;
+    uint64_t refills = 0;
+    void refill_buffer() override { refills++; Blake2xbPRNG::refill_buffer(); }
+    uint64_t position() const { return refills ? (refills - 1) * buffer_size_ + buffer_current_ : 0; }
+};
+// A generator that replays a given byte stream (zeros past its end): lets the tests put rejected draws where they want them.
+struct ReplayPRNG : UniformRandomGenerator {
+    const uint8_t *bytes;
+    uint64_t len, refills = 0;
+    ReplayPRNG(const uint8_t *b, uint64_t n) : UniformRandomGenerator(PRNGSeed{}), bytes(b), len(n) {}
+    PRNGType type() const noexcept override { return PRNGType::unknown; }
+    void refill_buffer() override {
+        const uint64_t at = refills++ * buffer_size_;
+        for (uint64_t i = 0; i < buffer_size_; i++) buffer_[i] = std::byte(at + i < len ? bytes[at + i] : 0);
+    }
+    uint64_t position() const { return refills ? (refills - 1) * buffer_size_ + buffer_current_ : 0; }
+};
+PRNGSeed seed_of(const uint64_t *seed8) {
+    PRNGSeed seed;
+    for (size_t i = 0; i < seed.size(); i++) seed[i] = seed8[i];
+    return seed;
+}
+} // namespace
+extern "C" {
+
+// UniformRandomGenerator::generate on a fresh Blake2xbPRNG(seed)
+int ref_prng_bytes(const uint64_t *seed8, uint64_t nbytes, uint8_t *out) {
+    REF_TRY
+    Blake2xbPRNG g(seed_of(seed8));
+    g.generate(nbytes, reinterpret_cast<std::byte *>(out));
+    return 0;
+    REF_CATCH(-1)
+}
+
+// which: 0 samplePolyTernary, 1 samplePolyCbd, 2 samplePolyUniform over the base of `level`, from a fresh Blake2xbPRNG(seed)
+// after discarding skip_bytes; *pos_out = stream position afterwards.
+int ref_sample_poly(void *h, int level, int which, const uint64_t *seed8, uint64_t skip_bytes, uint64_t *out, uint64_t *pos_out) {
+    REF_TRY
+    auto d = level_data(static_cast<RefCtx *>(h), level);
+    auto g = std::make_shared<CountingBlake2xb>(seed_of(seed8));
+    std::vector<std::byte> skip(skip_bytes);
+    if (skip_bytes) g->generate(skip_bytes, skip.data());
+    switch (which) {
+    case 0: util::samplePolyTernary(g, d->parms(), out); break;
+    case 1: util::samplePolyCbd(g, d->parms(), out); break;
+    case 2: util::samplePolyUniform(g, d->parms(), out); break;
+    default: g_last_error = "bad sampler"; return -1;
+    }
+    if (pos_out) *pos_out = g->position();
+    return 0;
+    REF_CATCH(-1)
+}
+
+// The same samplers drawing from a caller-supplied byte stream.
+int ref_sample_poly_replay(void *h, int level, int which, const uint8_t *stream, uint64_t stream_bytes, uint64_t skip_bytes,
+                           uint64_t *out, uint64_t *pos_out) {
+    REF_TRY
+    auto d = level_data(static_cast<RefCtx *>(h), level);
+    auto g = std::make_shared<ReplayPRNG>(stream, stream_bytes);
+    std::vector<std::byte> skip(skip_bytes);
+    if (skip_bytes) g->generate(skip_bytes, skip.data());
+    switch (which) {
+    case 0: util::samplePolyTernary(g, d->parms(), out); break;
+    case 1: util::samplePolyCbd(g, d->parms(), out); break;
+    case 2: util::samplePolyUniform(g, d->parms(), out); break;
+    default: g_last_error = "bad sampler"; return -1;
+    }
+    if (pos_out) *pos_out = g->position();
+    return 0;
+    REF_CATCH(-1)
+}
+
+// Public key as KeyGenerator made it: [2][key limbs][N], NTT form. Returns the word count.
+int64_t ref_public_key_words(void *h, uint64_t *out) {
+    REF_TRY
+    auto c = static_cast<RefCtx *>(h);
+    const Ciphertext &k = c->pk.data();
+    size_t words = k.size() * k.coeffModulusSize() * k.polyModulusDegree();
+    if (out) std::memcpy(out, k.data(), words * sizeof(uint64_t));
+    return (int64_t)words;
+    REF_CATCH(-1)
+}
+
+// Encryptor::encryptZero / encryptZeroSymmetric at `level` (-1: key level) with the context's (seeded) generator factory.
+void *ref_encrypt_zero(void *h, int level, int asymmetric) {
+    REF_TRY
+    auto c = static_cast<RefCtx *>(h);
+    auto d = level_data(c, level);
+    Encryptor enc(*c->context, c->pk, c->keygen->secretKey());
+    auto ct = std::make_unique<Ciphertext>();
+    if (asymmetric) enc.encryptZero(d->parmsID(), *ct);
+    else enc.encryptZeroSymmetric(d->parmsID(), *ct);
+    return ct.release();
+    REF_CATCH(nullptr)
+}
+
+// Encryptor::encrypt / encryptSymmetric of a plaintext handle
+void *ref_encrypt_plain(void *h, void *pth, int asymmetric) {
+    REF_TRY
+    auto c = static_cast<RefCtx *>(h);
+    Encryptor enc(*c->context, c->pk, c->keygen->secretKey());
+    auto ct = std::make_unique<Ciphertext>();
+    if (asymmetric) enc.encrypt(*static_cast<Plaintext *>(pth), *ct);
+    else enc.encryptSymmetric(*static_cast<Plaintext *>(pth), *ct);
+    return ct.release();
+    REF_CATCH(nullptr)
 }
 
 } // extern "C"

@@ -250,3 +250,118 @@ def run_decrypt_flow(ref, tb, scheme, n, bits, rng, batch=2):
         got = dec.decrypt(tb.CiphertextCuda.from_host(ctx, rct.words(), 0, False, 1.0)).to_host()[0]
         want = rc.decrypt_plain(rct).words()
         assert np.array_equal(got[: want.size], want) and not got[want.size:].any(), "decrypt of a real encryption"
+
+
+def _expand_stream(tb, seeds, nbytes):
+    """UniformRandomGenerator::generate on the device: [batch] streams of nbytes (a multiple of 4096)."""
+    from troy_b200.host import DeviceArray, _L, _vp
+    sd = np.ascontiguousarray(seeds, dtype=np.uint64).reshape(-1, 8)
+    d_seeds, out = DeviceArray(sd.size), DeviceArray(sd.shape[0] * nbytes // 8)
+    d_seeds.upload(sd.reshape(-1))
+    _L().call("troyb_prng_fill", _vp(d_seeds.ptr), 8, _vp(out.ptr), nbytes // 8, nbytes, sd.shape[0], _vp(None))
+    return d_seeds, out
+
+
+def run_prng_flow(ref, tb, rng):
+    """Blake2xbPRNG (src/randomgen.cpp:164-194): the expanded stream of several generators, byte for byte."""
+    seeds = rng.integers(0, 2 ** 63, (3, 8), dtype=np.uint64)
+    for nbytes in (4096, 5 * 4096, 66 * 4096):
+        _, out = _expand_stream(tb, seeds, nbytes)
+        got = out.download().view(np.uint8).reshape(3, nbytes)
+        for b in range(3):
+            assert np.array_equal(got[b], ref.prng_bytes(seeds[b], nbytes)), f"stream of generator {b}, {nbytes} bytes"
+
+
+def run_sampler_flow(ref, tb, scheme, n, bits, rng):
+    """samplePolyTernary / samplePolyCbd / samplePolyUniform (src/utils/rlwe.cpp:21-158) at the key level and two data
+    levels: from the real generator (also with the expanded part cut short, so that the rest is computed on demand), and
+    from crafted streams in which 1 %, 30 % and 90 % of the draws are rejected (zeros for the ternary sampler, words above
+    the largest multiple of the prime for the uniform one); words and the generator's end position against the reference."""
+    import ctypes as C
+    from troy_b200.host import DeviceArray, _L, _vp
+    rc, ctx = make_pair(ref, tb, scheme, n, bits)
+    seed = rng.integers(0, 2 ** 63, 8, dtype=np.uint64)
+    for level in [-1, 0, 1][: 1 + ctx.num_levels]:
+        L = ctx.level_limbs(level)
+        o, end = DeviceArray(L * n), DeviceArray(1)
+
+        def call(which, st, nbytes, expanded, d_seed, start):
+            h, lv, sp, ss = _vp(ctx.h), level, _vp(st.ptr), nbytes // 8
+            if which == 0:
+                _L().call("troyb_sample_poly_ternary", h, lv, sp, ss, expanded, d_seed, 8, C.c_uint64(start), _vp(o.ptr), L * n,
+                          _vp(end.ptr), 1, _vp(None))
+            elif which == 1:
+                _L().call("troyb_sample_poly_cbd", h, lv, sp, ss, expanded, d_seed, 8, C.c_uint64(start), _vp(o.ptr), L * n, 1,
+                          _vp(None))
+            else:
+                _L().call("troyb_sample_poly_uniform", h, lv, sp, ss, expanded, d_seed, 8, _vp(o.ptr), L * n, 1, _vp(None))
+            return o.download().reshape(L, n)
+
+        nbytes = ((L * n * 8 + 8192 + 4095) // 4096) * 4096
+        d_seed, st = _expand_stream(tb, seed, nbytes)
+        for which, start in ((0, 0), (0, 4 * n + 8), (1, 64), (1, 4 * n), (2, 0)):
+            want, pos = rc.sample_poly(level, which, seed, start)
+            assert np.array_equal(call(which, st, nbytes, nbytes, _vp(d_seed.ptr), start), want), f"sampler {which} level {level}"
+            if which == 0:
+                assert int(end.download()[0]) == pos
+                # only the first 64 bytes expanded: every later draw is computed from the seed on demand
+                assert np.array_equal(call(which, st, nbytes, 64, _vp(d_seed.ptr), start), want), f"on-demand sampler level {level}"
+        nbytes = ((L * n * 16 + 4095) // 4096) * 4096
+        st = DeviceArray(nbytes // 8)
+        for frac in (0.01, 0.3, 0.9):
+            words = rng.integers(0, 2 ** 63, nbytes // 8, dtype=np.uint64) * 2 + rng.integers(0, 2, nbytes // 8, dtype=np.uint64)
+            w32 = words.view(np.uint32).copy()
+            r32 = rng.random(w32.size) < frac
+            r32[w32.size // 2:] = False  # the stream must not run dry
+            w32[r32] = 0
+            st.upload(w32.view(np.uint64))
+            want, pos = rc.sample_poly_replay(level, 0, w32.view(np.uint8), 8)
+            assert np.array_equal(call(0, st, nbytes, nbytes, _vp(None), 8), want), f"ternary, {frac} rejected, level {level}"
+            assert int(end.download()[0]) == pos
+            wu = words.copy()
+            rej = rng.random(wu.size) < frac
+            rej[L * n + L * n // 2:] = False
+            wu[rej] = np.uint64(2 ** 64 - 1) - rng.integers(0, 3, int(rej.sum()), dtype=np.uint64)
+            st.upload(wu)
+            want, pos = rc.sample_poly_replay(level, 2, wu.view(np.uint8))
+            assert pos > L * n * 8
+            assert np.array_equal(call(2, st, nbytes, nbytes, _vp(None), 0), want), f"uniform, {frac} rejected, level {level}"
+
+
+def run_encrypt_flow(ref, tb, scheme, n, bits, rng, batch=2):
+    """Encryptor::encryptZero / encryptZeroSymmetric at every level (SURVEY.md §8f row 3), then encrypt / encryptSymmetric of a
+    plaintext followed by decryption on the device: for the seed the reference context was built with, every ciphertext
+    word equals the reference CPU encryptor's (src/utils/rlwe.cpp:160-356, src/encryptor.cpp:88-253)."""
+    rc, ctx = make_pair(ref, tb, scheme, n, bits)
+    rc.keygen()
+    enc = tb.EncryptorCuda(ctx, rc.public_key_words(), rc.secret_key_words())
+    seeds = np.array([SEED] * batch, dtype=np.uint64)
+    levels = ([-1] if ctx.using_keyswitching() else []) + list(range(ctx.num_levels))
+    for level in levels:
+        for asym in (True, False):
+            want = rc.encrypt_zero(level, asym)
+            got = (enc.encrypt_zero if asym else enc.encrypt_zero_symmetric)(level, batch=batch, seeds=seeds)
+            for i in range(batch):
+                assert_same(got, want, f"encrypt_zero [scheme {scheme}, N {n}, level {level}, asymmetric {asym}]", i)
+    ckks = scheme == ref.CKKS
+    dec = tb.DecryptorCuda(ctx, rc.secret_key_words())
+    for asym in (True, False):
+        if ckks:
+            level = min(1, ctx.num_levels - 1)
+            mods = rc.level_moduli(level)
+            pw = np.stack([np.stack([rng.integers(0, m, n, dtype=np.uint64) for m in mods]) for _ in range(batch)])
+            pt = tb.PlaintextCuda.from_host(ctx, pw, level, 2.0 ** 30)
+            rpts = [rc.plaintext(pw[i], level, 2.0 ** 30) for i in range(batch)]
+        else:
+            pw = rng.integers(0, rc.plain_modulus, (batch, n), dtype=np.uint64)
+            pt = tb.PlaintextCuda.from_host(ctx, pw)
+            rpts = [rc.plaintext(pw[i]) for i in range(batch)]
+        got = (enc.encrypt if asym else enc.encrypt_symmetric)(pt, seeds=seeds)
+        for i in range(batch):
+            assert_same(got, rc.encrypt_plain(rpts[i], asym), f"encrypt [scheme {scheme}, N {n}, asymmetric {asym}]", i)
+        if not ckks:  # and back: the device decryptor returns the plaintext
+            assert np.array_equal(dec.decrypt(got).to_host(), pw), "decrypt(encrypt(plain))"
+    # different seeds give different ciphertexts; the default draws fresh seeds
+    two = enc.encrypt_zero(0, batch=2, seeds=rng.integers(0, 2 ** 63, (2, 8), dtype=np.uint64)).to_host()
+    assert not np.array_equal(two[0], two[1])
+    assert not np.array_equal(enc.encrypt_zero(0).to_host(), enc.encrypt_zero(0).to_host())

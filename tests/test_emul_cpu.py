@@ -76,3 +76,23 @@ def test_fp64_butterflies_for_50_bit_primes_emulated(ref, emul_lib, scheme, n, b
     """46..50-bit primes run the FP64 butterflies with per-butterfly re-centring (ArithF64L): no head-room to spare, so this
     is checked on parameter sets made only of such primes, at every transform size class."""
     run_evaluator_flow(ref, emul_lib, scheme, n, bits, np.random.default_rng(600 + scheme + n), batch=2)
+
+
+def test_prng_stream_emulated(ref, emul_lib):
+    from common import run_prng_flow
+    run_prng_flow(ref, emul_lib, np.random.default_rng(700))
+
+
+@pytest.mark.parametrize("scheme,n,bits", [(2, 1024, [60, 40, 40, 60]), (1, 256, [40, 30, 30, 40]), (3, 4096, [60, 50, 60])])
+def test_samplers_emulated(ref, emul_lib, scheme, n, bits):
+    """The device samplers against the reference's, including heavy rejection."""
+    from common import run_sampler_flow
+    run_sampler_flow(ref, emul_lib, scheme, n, bits, np.random.default_rng(710 + scheme))
+
+
+@pytest.mark.parametrize("scheme,n,bits", [(2, 1024, [60, 40, 40, 60]), (1, 256, [40, 30, 30, 40]), (3, 4096, [60, 40, 60]),
+                                           (2, 256, [40]), (1, 16384, [60, 40, 60])])
+def test_encrypt_emulated(ref, emul_lib, scheme, n, bits):
+    """Encryption on the device: same seed, same words as the reference CPU encryptor."""
+    from common import run_encrypt_flow
+    run_encrypt_flow(ref, emul_lib, scheme, n, bits, np.random.default_rng(720 + scheme + n))

@@ -3,8 +3,8 @@ metadata are compared with the reference troy:: CPU library (oracle/_ref) on ide
 import numpy as np
 import pytest
 
-from common import (assert_same, make_pair, random_ct_words, run_decrypt_flow, run_evaluator_flow, run_matmul_flow,
-                    run_plain_flow)
+from common import (assert_same, make_pair, random_ct_words, run_decrypt_flow, run_encrypt_flow, run_evaluator_flow,
+                    run_matmul_flow, run_plain_flow, run_prng_flow, run_sampler_flow)
 
 pytestmark = pytest.mark.gpu
 
@@ -126,6 +126,26 @@ def test_config5_full_size_key_switch(ref, cuda_lib):
 def test_decrypt(ref, cuda_lib, scheme, n, bits):
     """CKKS / BFV / BGV decryption on the device against the reference CPU decryptor."""
     run_decrypt_flow(ref, cuda_lib, scheme, n, bits, np.random.default_rng(5000 + n + scheme))
+
+
+def test_prng_stream(ref, cuda_lib):
+    """Blake2xbPRNG's byte stream expanded on the device."""
+    run_prng_flow(ref, cuda_lib, np.random.default_rng(6000))
+
+
+@pytest.mark.parametrize("scheme,n,bits", [(2, 16384, [60, 40, 40, 60]), (1, 8192, [60, 40, 40, 60]), (3, 32768, [60, 50, 60]),
+                                           (2, 65536, [60, 50, 60]), (1, 256, [40, 30, 30, 40])])
+def test_samplers(ref, cuda_lib, scheme, n, bits):
+    """samplePolyTernary / samplePolyCbd / samplePolyUniform on the device, real and crafted streams (up to 90 % of the draws
+    rejected), words and end positions against the reference's samplers."""
+    run_sampler_flow(ref, cuda_lib, scheme, n, bits, np.random.default_rng(6100 + n + scheme))
+
+
+@pytest.mark.parametrize("scheme,n,bits", FLOWS)
+def test_encrypt(ref, cuda_lib, scheme, n, bits):
+    """Encryption on the device with the CPU generator's semantics: same seed, same ciphertext words as the reference CPU
+    encryptor, asymmetric and symmetric, at every level; then decryption on the device gives the plaintext back."""
+    run_encrypt_flow(ref, cuda_lib, scheme, n, bits, np.random.default_rng(6200 + n + scheme))
 
 
 def test_matmul(ref, cuda_lib):

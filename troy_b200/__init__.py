@@ -7,7 +7,7 @@ CUDA library is missing the import of :mod:`troy_b200.lib` fails loudly.
 """
 from .host import (  # noqa: F401
     BFV, BGV, CKKS,
-    CiphertextCuda, CoeffModulus, DecryptorCuda, EncryptionParameters, EvaluatorCuda, GaloisKeysCuda, KSwitchKeysCuda, KernelProvider,
+    CiphertextCuda, CoeffModulus, DecryptorCuda, EncryptionParameters, EncryptorCuda, EvaluatorCuda, GaloisKeysCuda, KSwitchKeysCuda, KernelProvider,
     PlainModulus, PlaintextCuda, RelinKeysCuda, SEALContextCuda, SchemeType,
 )
 from .lib import TroyError, library  # noqa: F401

@@ -4,6 +4,7 @@
 #include "context.h"
 #include "kernels_elt.cuh"
 #include "kernels_ntt.cuh"
+#include "kernels_rlwe.cuh"
 #include "ntt_launch.h"
 #include "hostmath.h"
 
@@ -383,6 +384,62 @@ void switch_key_impl(Context *ctx, int level, u64 *ct, u64 ct_stride, const u64 
     Scratch prod((size_t)batch * 2 * (L + 1) * ctx->N, s);
     switch_key_partial(ctx, level, target, target_stride, key, 0, L, prod.p, batch, s);
     switch_key_finish(ctx, level, ct, ct_stride, prod.p, false, batch, s, ct_src, ct_src_stride, ct_src_polys);
+}
+
+// Division by the last prime of a base with rounding (the level's last prime, or the special prime at the key level):
+// divideAndRoundqLastNttInplace (CKKS, NTT form)  src/utils/rns_cuda.cu:348-363; divideAndRoundqLastInplace (BFV) and
+// modTAndDivideqLastInplace (BGV) in coefficient form. in: [size][L][N], out: [size][L-1][N].
+void drop_last(Context *c, const DropDev &drop, const LimbMap &map, u32 L, bool ntt_form, const u64 *d_in, u64 in_stride, u64 *d_out,
+               u64 out_stride, u32 size, u32 batch, cudaStream_t s) {
+    const u64 N = c->N;
+    if (ntt_form) {
+        Scratch sp((size_t)batch * size * N, s);
+        NttArgs a{};
+        a.mode = INV_ADD_HALF;
+        a.map = map;
+        a.L = L;
+        a.K = size;
+        a.src = d_in;
+        a.src_offset = (u64)(L - 1) * N;
+        a.src_unit_stride = in_stride;
+        a.src_poly_stride = (u64)L * N;
+        a.dst = sp.p;
+        a.drop = drop;
+        a.add_half = 1;
+        a.scheme = c->scheme;
+        run_inv(c, a, batch * size, s);
+        NttArgs f{};
+        f.mode = FWD_MODDOWN;
+        f.map = c->map_prefix(L - 1);
+        f.L = L - 1;
+        f.K = size;
+        f.aux0 = d_in;
+        f.acc_batch_stride = in_stride;
+        f.acc_poly_stride = (u64)L * N;
+        f.aux1 = sp.p;
+        f.ct = nullptr;
+        f.dst = d_out;
+        f.dst_batch_stride = out_stride;
+        f.dst_poly_stride = (u64)(L - 1) * N;
+        f.drop = drop;
+        f.scheme = c->scheme;
+        set_order(c, f, L - 1);
+        run_fwd(c, f, batch * size * (L - 1), s);
+    } else {
+        EltDropLast k{};
+        k.logN = c->logN;
+        k.scheme = c->scheme;
+        k.mods = c->d_mods;
+        k.drop = drop;
+        k.L = L;
+        k.size = size;
+        k.total = (u64)batch * size * (L - 1) * N;
+        k.in_batch_stride = in_stride;
+        k.out_batch_stride = out_stride;
+        k.in = d_in;
+        k.out = d_out;
+        ck(launch_cta(k, grid_for(k.total, EltDropLast::kThreads), 0, s));
+    }
 }
 
 void check_batch_stride(size_t stride, size_t min_words, const char *what) {
@@ -1249,62 +1306,285 @@ int troyb_mod_switch_scale_to_next(troyb_context *ctx, int level, const uint64_t
     Context *c = C(ctx);
     const u32 L = (u32)level_limbs(c, level);
     const u64 N = c->N;
-    cudaStream_t s = S(stream);
     if (level < 0 || level + 1 >= (int)c->levels.size()) throw std::invalid_argument("end of modulus switching chain reached");
     if (d_in == d_out) throw std::invalid_argument("in-place call must go through a temporary (as the reference does)");
     check_batch_stride(in_stride, size * L * N, "in");
     check_batch_stride(out_stride, size * (L - 1) * N, "out");
     check_aligned(d_in, "in");
     check_aligned(d_out, "out");
-    const LevelData &lv = c->levels[level];
-    if (c->scheme == SCHEME_CKKS) {
-        // divideAndRoundqLastNttInplace  src/utils/rns_cuda.cu:348-363
-        Scratch sp((size_t)batch * size * N, s);
-        NttArgs a{};
-        a.mode = INV_ADD_HALF;
-        a.map = c->map_prefix(L);
-        a.L = L;
-        a.K = (u32)size;
-        a.src = d_in;
-        a.src_offset = (u64)(L - 1) * N;
-        a.src_unit_stride = in_stride;
-        a.src_poly_stride = (u64)L * N;
-        a.dst = sp.p;
-        a.drop = lv.drop;
-        a.add_half = 1;
-        a.scheme = c->scheme;
-        run_inv(c, a, (u32)(batch * size), s);
-        NttArgs f{};
-        f.mode = FWD_MODDOWN;
-        f.map = c->map_prefix(L - 1);
-        f.L = L - 1;
-        f.K = (u32)size;
-        f.aux0 = d_in;
-        f.acc_batch_stride = in_stride;
-        f.acc_poly_stride = (u64)L * N;
-        f.aux1 = sp.p;
-        f.ct = nullptr;
-        f.dst = d_out;
-        f.dst_batch_stride = out_stride;
-        f.dst_poly_stride = (u64)(L - 1) * N;
-        f.drop = lv.drop;
-        f.scheme = c->scheme;
-        set_order(c, f, L - 1);
-        run_fwd(c, f, (u32)(batch * size * (L - 1)), s);
+    drop_last(c, c->levels[level].drop, c->map_prefix(L), L, c->scheme == SCHEME_CKKS, d_in, in_stride, d_out, out_stride, (u32)size,
+              (u32)batch, S(stream));
+    API_END
+}
+
+// ---- encrypt-zero with the host generator's semantics (kernels_rlwe.cuh) ------------------------------
+namespace {
+
+struct LevelBase {
+    u32 L;
+    LimbMap map;
+};
+LevelBase level_base(const Context *c, int level) {
+    LevelBase b;
+    b.L = (u32)level_limbs(c, level);
+    b.map = level == -1 && c->has_special ? c->map_prefix_special(c->Ltop) : c->map_prefix((int)b.L);
+    return b;
+}
+
+// Expands `bytes` (rounded up to whole 4096-byte buffers) of `batch` generators; returns the words per generator.
+u64 prng_expand(const u64 *d_seeds, u64 seed_stride, u64 *d_out, u64 out_stride, u64 bytes, u32 batch, cudaStream_t s) {
+    PrngExpand k{};
+    k.seeds = d_seeds;
+    k.seed_stride = seed_stride;
+    k.out = d_out;
+    k.out_stride = out_stride;
+    k.buffers = (u32)((bytes + Blake2::kBufferBytes - 1) / Blake2::kBufferBytes);
+    k.ctas_per_stream = (k.buffers + 3) / 4;
+    ck(launch_cta(k, batch * k.ctas_per_stream, 4 * 8 * sizeof(u64), s));
+    return (u64)k.buffers * (Blake2::kBufferBytes / 8);
+}
+u64 buffers_words(u64 bytes) { return (bytes + Blake2::kBufferBytes - 1) / Blake2::kBufferBytes * (Blake2::kBufferBytes / 8); }
+
+PrngView make_view(const u64 *d_stream, u64 bytes, const u64 *d_seeds) {
+    PrngView v;
+    v.buf = d_stream;
+    v.bytes = bytes & ~63ull;
+    v.seed = d_seeds;
+    return v;
+}
+
+// samplePolyTernary (n_tern = 1) followed by n_cbd x samplePolyCbd from one stream; out [batch][n_tern + n_cbd][L][N].
+// d_end (optional, [batch]): stream position in bytes after the last draw.
+void sample_small(Context *c, const LevelBase &lb, const PrngView &view, u64 view_stride, u64 seed_stride, u64 start_bytes,
+                  u32 n_tern, u32 n_cbd, u64 *d_out, u64 out_stride, u64 *d_end, u32 batch, cudaStream_t s) {
+    const u32 N = (u32)c->N, nseg = (N + kSampleSeg - 1) / kSampleSeg;
+    if (N % kSampleSeg) throw std::invalid_argument("poly_modulus_degree must be a multiple of 256 for the device samplers");
+    if (start_bytes & 3) throw std::invalid_argument("stream position must be a multiple of 4");
+    Scratch seg(n_tern ? (size_t)batch * (nseg + 2) : 0, s);
+    if (n_tern) {
+        SampleTernaryScan k{};
+        k.view = view;
+        k.view_stride = view_stride;
+        k.seed_stride = seed_stride;
+        k.start_bytes = start_bytes;
+        k.N = N;
+        k.nseg = nseg;
+        k.seg = seg.p;
+        ck(launch_cta(k, batch, 0, s));
+    }
+    SampleExpand e{};
+    e.view = view;
+    e.view_stride = view_stride;
+    e.seed_stride = seed_stride;
+    e.start_bytes = start_bytes;
+    e.cbd_bytes = start_bytes;
+    e.N = N;
+    e.nseg = nseg;
+    e.n_tern = n_tern;
+    e.n_cbd = n_cbd;
+    e.n_limbs = lb.L;
+    e.seg = n_tern ? seg.p : nullptr;
+    e.mods = c->d_mods;
+    e.map = lb.map;
+    e.out = d_out;
+    e.out_stride = out_stride;
+    ck(launch_cta(e, batch * nseg, 0, s));
+    if (d_end) {
+        if (n_tern) {
+            // end of the ternary draws (+ the rejection-free noise draws)
+            ck(cudaMemcpy2DAsync(d_end, sizeof(u64), seg.p + nseg + 1, (nseg + 2) * sizeof(u64), sizeof(u64), batch,
+                                 cudaMemcpyDeviceToDevice, s));
+            if (n_cbd) throw std::logic_error("end position is reported for single samplers only");
+        } else {
+            std::vector<u64> end(batch, start_bytes + 6ull * n_cbd * N);
+            ck(cudaMemcpyAsync(d_end, end.data(), batch * sizeof(u64), cudaMemcpyHostToDevice, s));
+            ck(cudaStreamSynchronize(s)); // `end` is a host temporary
+        }
+    }
+}
+
+// samplePolyUniform over the level's base from the start of each stream; out [batch][L][N] (out_stride words apart).
+void sample_uniform(Context *c, const LevelBase &lb, const PrngView &view, u64 view_stride, u64 seed_stride, u64 *d_out,
+                    u64 out_stride, u32 batch, cudaStream_t s) {
+    const u64 N = c->N;
+    if (view.bytes < (u64)lb.L * N * 8) throw std::invalid_argument("stream shorter than the polynomial");
+    SampleUniformFill f{};
+    f.view = view;
+    f.view_stride = view_stride;
+    f.logN = c->logN;
+    f.n_limbs = lb.L;
+    f.mods = c->d_mods;
+    f.map = lb.map;
+    f.out = d_out;
+    f.out_stride = out_stride;
+    f.total = (u64)batch * lb.L * N;
+    ck(launch_cta(f, grid_for(f.total, SampleUniformFill::kThreads), 0, s));
+    Scratch repl((size_t)batch * N, s);
+    SampleUniformResolve r{};
+    r.view = view;
+    r.view_stride = view_stride;
+    r.seed_stride = seed_stride;
+    r.N = (u32)N;
+    r.n_limbs = lb.L;
+    r.mods = c->d_mods;
+    r.map = lb.map;
+    r.out = d_out;
+    r.out_stride = out_stride;
+    r.repl = repl.p;
+    ck(launch_cta(r, batch, SampleUniformResolve::kSmemWords * sizeof(u64), s));
+}
+
+void enc_combine(Context *c, const LevelBase &lb, int op, u32 polys, u32 batch, const u64 *x, u64 x_batch, u64 x_poly, const u64 *y,
+                 u64 y_batch, u64 y_poly, const u64 *z, u64 z_batch, u64 z_poly, u64 *out, u64 out_batch, u64 out_poly, u64 f,
+                 cudaStream_t s) {
+    EncCombine k{};
+    k.op = op;
+    k.logN = c->logN;
+    k.n_limbs = lb.L;
+    k.polys = polys;
+    k.total = (u64)batch * polys * lb.L * c->N;
+    k.mods = c->d_mods;
+    k.map = lb.map;
+    k.f = f;
+    k.x = x; k.x_batch = x_batch; k.x_poly = x_poly;
+    k.y = y; k.y_batch = y_batch; k.y_poly = y_poly;
+    k.z = z; k.z_batch = z_batch; k.z_poly = z_poly;
+    k.out = out; k.out_batch = out_batch; k.out_poly = out_poly;
+    ck(launch_cta(k, grid_for(k.total, EncCombine::kThreads), 0, s));
+}
+
+} // namespace
+
+int troyb_prng_fill(const uint64_t *d_seeds, size_t seed_stride, uint64_t *d_out, size_t out_stride, size_t bytes, size_t batch,
+                    void *stream) {
+    API_BEGIN
+    need_init();
+    if (bytes % Blake2::kBufferBytes) throw std::invalid_argument("bytes must be a multiple of 4096 (the generator's buffer)");
+    if (out_stride * 8 < bytes) throw std::invalid_argument("out_stride shorter than the stream");
+    if (batch && bytes) prng_expand(d_seeds, seed_stride, d_out, out_stride, bytes, (u32)batch, S(stream));
+    API_END
+}
+
+int troyb_sample_poly_ternary(troyb_context *ctx, int level, const uint64_t *d_stream, size_t stream_stride, size_t stream_bytes,
+                              const uint64_t *d_seeds, size_t seed_stride, uint64_t start_bytes, uint64_t *d_out, size_t out_stride,
+                              uint64_t *d_end_bytes, size_t batch, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const LevelBase lb = level_base(c, level);
+    check_batch_stride(out_stride, (size_t)lb.L * c->N, "out");
+    sample_small(c, lb, make_view(d_stream, stream_bytes, d_seeds), stream_stride, seed_stride, start_bytes, 1, 0, d_out, out_stride,
+                 d_end_bytes, (u32)batch, S(stream));
+    API_END
+}
+
+int troyb_sample_poly_cbd(troyb_context *ctx, int level, const uint64_t *d_stream, size_t stream_stride, size_t stream_bytes,
+                          const uint64_t *d_seeds, size_t seed_stride, uint64_t start_bytes, uint64_t *d_out, size_t out_stride,
+                          size_t batch, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const LevelBase lb = level_base(c, level);
+    check_batch_stride(out_stride, (size_t)lb.L * c->N, "out");
+    if (start_bytes & 1) throw std::invalid_argument("stream position must be even");
+    sample_small(c, lb, make_view(d_stream, stream_bytes, d_seeds), stream_stride, seed_stride, start_bytes & ~3ull, 0, 1, d_out,
+                 out_stride, nullptr, (u32)batch, S(stream));
+    API_END
+}
+
+int troyb_sample_poly_uniform(troyb_context *ctx, int level, const uint64_t *d_stream, size_t stream_stride, size_t stream_bytes,
+                              const uint64_t *d_seeds, size_t seed_stride, uint64_t *d_out, size_t out_stride, size_t batch,
+                              void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const LevelBase lb = level_base(c, level);
+    check_batch_stride(out_stride, (size_t)lb.L * c->N, "out");
+    sample_uniform(c, lb, make_view(d_stream, stream_bytes, d_seeds), stream_stride, seed_stride, d_out, out_stride, (u32)batch,
+                   S(stream));
+    API_END
+}
+
+int troyb_encrypt_zero_asymmetric(troyb_context *ctx, int level, const uint64_t *d_public_key, const uint64_t *d_seeds,
+                                  uint64_t *d_ct, size_t ct_stride, size_t batch, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    cudaStream_t s = S(stream);
+    const u64 N = c->N;
+    const bool ntt_form = c->scheme == SCHEME_CKKS;
+    const LevelBase out_lb = level_base(c, level);
+    // Encryptor::encryptZeroInternal  src/encryptor.cpp:119-156: encrypt one level up the chain (the key level for the first
+    // data level) and divide by the extra prime, when the chain has such a level
+    const bool switch_down = level == 0 ? c->has_special : level > 0;
+    const int enc_level = switch_down ? level - 1 : level;
+    const LevelBase lb = level_base(c, enc_level);
+    const u64 pk_poly = (u64)level_limbs(c, -1) * N; // the key's polynomials keep the key level's stride
+    check_batch_stride(ct_stride, 2 * (size_t)out_lb.L * N, "ct");
+    check_aligned(d_ct, "ct");
+    const u32 B = (u32)batch;
+    if (!B) return TROYB_OK;
+    // the generator's stream: N ternary draws (4 bytes each, + the rare rejected ones), then 2 x N noise draws of 6 bytes
+    const u64 stream_bytes = 16 * N + 1024, sw = buffers_words(stream_bytes);
+    Scratch st((size_t)B * sw, s);
+    prng_expand(d_seeds, 8, st.p, sw, stream_bytes, B, s);
+    const u64 poly = (u64)lb.L * N;
+    Scratch smp((size_t)B * 3 * poly, s); // u, e_0, e_1
+    sample_small(c, lb, make_view(st.p, sw * 8, d_seeds), sw, 8, 0, 1, 2, smp.p, 3 * poly, nullptr, B, s);
+    Scratch wide(switch_down ? (size_t)B * 2 * poly : 0, s);
+    u64 *enc = switch_down ? wide.p : d_ct;
+    const u64 enc_stride = switch_down ? 2 * poly : ct_stride;
+    if (ntt_form) {
+        ntt_plain(c, false, lb.map, lb.L, smp.p, 3 * poly, smp.p, 3 * poly, 3 * lb.L, B, true, s);
+        enc_combine(c, lb, 1, 2, B, smp.p, 3 * poly, 0, d_public_key, 0, pk_poly, smp.p + poly, 3 * poly, poly, enc, enc_stride, poly,
+                    1, s);
     } else {
-        EltDropLast k{};
-        k.logN = c->logN;
-        k.scheme = c->scheme;
-        k.mods = c->d_mods;
-        k.drop = lv.drop;
-        k.L = L;
-        k.size = (u32)size;
-        k.total = (u64)batch * size * (L - 1) * N;
-        k.in_batch_stride = in_stride;
-        k.out_batch_stride = out_stride;
-        k.in = d_in;
-        k.out = d_out;
-        ck(launch_cta(k, grid_for(k.total, EltDropLast::kThreads), 0, s));
+        ntt_plain(c, false, lb.map, lb.L, smp.p, 3 * poly, smp.p, 3 * poly, lb.L, B, true, s);
+        enc_combine(c, lb, 0, 2, B, smp.p, 3 * poly, 0, d_public_key, 0, pk_poly, nullptr, 0, 0, enc, enc_stride, poly, 1, s);
+        ntt_plain(c, true, lb.map, lb.L, enc, enc_stride, enc, enc_stride, 2 * lb.L, B, true, s);
+        enc_combine(c, lb, 2, 2, B, nullptr, 0, 0, nullptr, 0, 0, smp.p + poly, 3 * poly, poly, enc, enc_stride, poly,
+                    c->scheme == SCHEME_BGV ? c->plain : 1, s);
+    }
+    if (switch_down)
+        drop_last(c, enc_level == -1 ? c->key_drop : c->levels[enc_level].drop, lb.map, lb.L, ntt_form, enc, enc_stride, d_ct, ct_stride,
+                  2, B, s);
+    API_END
+}
+
+int troyb_encrypt_zero_symmetric(troyb_context *ctx, int level, const uint64_t *d_secret_key, const uint64_t *d_seeds, uint64_t *d_ct,
+                                 size_t ct_stride, size_t batch, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    cudaStream_t s = S(stream);
+    const u64 N = c->N;
+    const bool ntt_form = c->scheme == SCHEME_CKKS;
+    const LevelBase lb = level_base(c, level);
+    const u64 poly = (u64)lb.L * N;
+    check_batch_stride(ct_stride, 2 * (size_t)poly, "ct");
+    check_aligned(d_ct, "ct");
+    const u32 B = (u32)batch;
+    if (!B) return TROYB_OK;
+    // bootstrap generator: 64 bytes = the seed of the generator that expands c1, then N noise draws of 6 bytes
+    const u64 boot_bytes = 64 + 6 * N, bw = buffers_words(boot_bytes);
+    Scratch boot((size_t)B * bw, s);
+    prng_expand(d_seeds, 8, boot.p, bw, boot_bytes, B, s);
+    // ciphertext generator: L * N words + the redraws (a word is rejected with probability < q / 2^64 <= 1/8)
+    const u64 uni_bytes = poly * 8 + poly + 4096, uw = buffers_words(uni_bytes);
+    Scratch uni((size_t)B * uw, s);
+    prng_expand(boot.p, bw, uni.p, uw, uni_bytes, B, s);
+    u64 *c1 = d_ct + poly;
+    sample_uniform(c, lb, make_view(uni.p, uw * 8, boot.p), uw, bw, c1, ct_stride, B, s);
+    Scratch noise((size_t)B * poly, s);
+    sample_small(c, lb, make_view(boot.p, bw * 8, d_seeds), bw, 8, 64, 0, 1, noise.p, poly, nullptr, B, s);
+    const u64 f = c->scheme == SCHEME_BGV ? c->plain : 1;
+    if (ntt_form) {
+        ntt_plain(c, false, lb.map, lb.L, noise.p, poly, noise.p, poly, lb.L, B, true, s);
+        enc_combine(c, lb, 4, 1, B, c1, ct_stride, 0, d_secret_key, 0, 0, noise.p, poly, 0, d_ct, ct_stride, 0, f, s);
+    } else {
+        enc_combine(c, lb, 0, 1, B, c1, ct_stride, 0, d_secret_key, 0, 0, nullptr, 0, 0, d_ct, ct_stride, 0, 1, s);
+        ntt_plain(c, true, lb.map, lb.L, d_ct, ct_stride, d_ct, ct_stride, 2 * lb.L, B, true, s);
+        enc_combine(c, lb, 3, 1, B, nullptr, 0, 0, nullptr, 0, 0, noise.p, poly, 0, d_ct, ct_stride, 0, f, s);
     }
     API_END
 }

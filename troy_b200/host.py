@@ -6,11 +6,13 @@ the CUDA library behind the C ABI. Differences that are deliberate and documente
 * a ``ParmsID`` is the chain index (``int``; ``-1`` is the key level) instead of a Blake2 hash of the parameters;
 * every ciphertext object may carry a leading ``batch`` dimension (``[batch][poly][limb][coeff]``); ``batch == 1`` is
   exactly the reference object, larger batches are how one GPU is kept busy with independent ciphertexts;
-* key generation / encryption / encoding stay on the host in the reference (``KeyGeneratorCuda`` wraps the host
-  ``KeyGenerator``, src/keygenerator_cuda.cuh:36-60), so keys and ciphertexts enter through ``from_host`` uploads.
+* key generation and encoding stay on the host in the reference (``KeyGeneratorCuda`` wraps the host ``KeyGenerator``,
+  src/keygenerator_cuda.cuh:36-60), so keys enter through ``from_host`` uploads; ``EncryptorCuda`` encrypts on the device
+  with the words the reference's CPU encryptor gives for the same seed.
 """
 import ctypes as C
 import math
+import os
 
 import numpy as np
 
@@ -494,6 +496,91 @@ class DecryptorCuda:
         _L().call("troyb_decrypt_scale_and_round", _vp(self.context.h), ct.parms_id, _vp(phase.ptr), _vp(out.data.ptr), ct.batch,
                   _vp(self.stream))
         return out
+
+
+class EncryptorCuda:
+    """src/encryptor_cuda.cuh / src/encryptor.cpp: encryption on the device with the CPU path's generator semantics.
+
+    ``public_key_words``: ``[2][key_limbs][N]``, ``secret_key_words``: ``[key_limbs][N]`` (NTT form at the key level, as
+    ``KeyGenerator`` stores them); either may be None. Every ciphertext draws from its own Blake2xb generator, as
+    ``parms.randomGenerator()->create()`` gives the reference (src/utils/rlwe.cpp:183, 284): ``seeds`` is ``[batch][8]`` words
+    (64 bytes each); None takes them from ``os.urandom`` like the reference's default factory (src/randomgen.cpp:20-36). For a
+    given seed the words equal those of the reference's CPU encryptor."""
+
+    def __init__(self, context, public_key_words=None, secret_key_words=None, stream=None):
+        self.context, self.stream = context, stream
+        kl = context.level_limbs(SEALContextCuda.KEY_LEVEL)
+        self.pk = self.sk = None
+        if public_key_words is not None:
+            w = np.ascontiguousarray(public_key_words, dtype=np.uint64)
+            if w.size != 2 * kl * context.n:
+                raise TroyInvalidArgument("public key is not valid for encryption parameters")
+            self.pk = context.alloc(w.size, stream)
+            self.pk.upload(w.reshape(-1))
+        if secret_key_words is not None:
+            w = np.ascontiguousarray(secret_key_words, dtype=np.uint64)
+            if w.size != kl * context.n:
+                raise TroyInvalidArgument("secret key is not valid for encryption parameters")
+            self.sk = context.alloc(w.size, stream)
+            self.sk.upload(w.reshape(-1))
+
+    def _seeds(self, seeds, batch):
+        if seeds is None:
+            w = np.frombuffer(os.urandom(64 * batch), dtype=np.uint64)
+        else:
+            w = np.ascontiguousarray(seeds, dtype=np.uint64).reshape(-1)
+        if w.size != 8 * batch:
+            raise TroyInvalidArgument("one 64-byte seed per ciphertext")
+        d = self.context.alloc(w.size, self.stream)
+        d.upload(w)
+        return d
+
+    def _encrypt_zero(self, level, asymmetric, batch, seeds):
+        """Encryptor::encryptZeroInternal  src/encryptor.cpp:88-164"""
+        ctx = self.context
+        key = self.pk if asymmetric else self.sk
+        if key is None:
+            raise TroyLogicError("public key is not set" if asymmetric else "secret key is not set")
+        if level != SEALContextCuda.KEY_LEVEL and not 0 <= level < ctx.num_levels:
+            raise TroyInvalidArgument("parms_id is not valid for encryption parameters")
+        d_seeds = self._seeds(seeds, batch)
+        ct = CiphertextCuda(ctx, level, 2, ctx.scheme == CKKS, 1.0, 1, batch=batch, stream=self.stream)
+        name = "troyb_encrypt_zero_asymmetric" if asymmetric else "troyb_encrypt_zero_symmetric"
+        _L().call(name, _vp(ctx.h), level, _vp(key.ptr), _vp(d_seeds.ptr), _vp(ct.data.ptr), ct.stride, batch, _vp(self.stream))
+        return ct
+
+    def encrypt_zero(self, parms_id=0, batch=1, seeds=None):
+        return self._encrypt_zero(parms_id, True, batch, seeds)
+
+    def encrypt_zero_symmetric(self, parms_id=0, batch=1, seeds=None):
+        return self._encrypt_zero(parms_id, False, batch, seeds)
+
+    def _encrypt(self, plain, asymmetric, seeds):
+        """Encryptor::encryptInternal  src/encryptor.cpp:166-253: encryption of zero, then the plaintext goes into c0."""
+        ctx, scheme = self.context, self.context.scheme
+        batch = plain.batch
+        if scheme == CKKS:
+            if not plain.is_ntt_form:
+                raise TroyInvalidArgument("plain must be in NTT form")
+            ct = self._encrypt_zero(plain.parms_id, asymmetric, batch, seeds)
+            for b in range(batch):  # addPolyCoeffmod on c0
+                _L().call("troyb_add", _vp(ctx.h), ct.parms_id, _vp(ct.ptr(0, b)), _vp(plain.data.at(b * plain.coeff_count)),
+                          _vp(ct.ptr(0, b)), 1, _vp(self.stream))
+            ct.scale = plain.scale
+            return ct
+        if plain.is_ntt_form:
+            raise TroyInvalidArgument("plain cannot be in NTT form")
+        ct = self._encrypt_zero(0, asymmetric, batch, seeds)
+        # BFV: multiplyAddPlainWithScalingVariant; BGV: addPlainWithoutScalingVariant (correction factor 1)
+        _L().call("troyb_add_plain", _vp(ctx.h), 0, _vp(ct.ptr()), ct.stride, _vp(plain.data.ptr), plain.coeff_count,
+                  plain.stride, C.c_uint64(1), 0, batch, _vp(self.stream))
+        return ct
+
+    def encrypt(self, plain, seeds=None):
+        return self._encrypt(plain, True, seeds)
+
+    def encrypt_symmetric(self, plain, seeds=None):
+        return self._encrypt(plain, False, seeds)
 
 
 def _balance_correction_factors(f1, f2, t):

@@ -77,6 +77,12 @@ _SIGNATURES = {
     "troyb_switch_key_reduce_rows": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, _sz, _vp]),
     "troyb_switch_key_special_row": (C.c_int, [_vp, C.c_int, _vp, _vp, _sz, _vp]),
     "troyb_switch_key_moddown_rows": (C.c_int, [_vp, C.c_int, _vp, _sz, _vp, _vp, C.c_int, C.c_int, _sz, _vp]),
+    "troyb_prng_fill": (C.c_int, [_vp, _sz, _vp, _sz, _sz, _sz, _vp]),
+    "troyb_sample_poly_ternary": (C.c_int, [_vp, C.c_int, _vp, _sz, _sz, _vp, _sz, C.c_uint64, _vp, _sz, _vp, _sz, _vp]),
+    "troyb_sample_poly_cbd": (C.c_int, [_vp, C.c_int, _vp, _sz, _sz, _vp, _sz, C.c_uint64, _vp, _sz, _sz, _vp]),
+    "troyb_sample_poly_uniform": (C.c_int, [_vp, C.c_int, _vp, _sz, _sz, _vp, _sz, _vp, _sz, _sz, _vp]),
+    "troyb_encrypt_zero_asymmetric": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _sz, _sz, _vp]),
+    "troyb_encrypt_zero_symmetric": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _sz, _sz, _vp]),
     "troyb_relinearize": (C.c_int, [_vp, C.c_int, _vp, _sz, _vp, _sz, _vp]),
     "troyb_galois_permute": (C.c_int, [_vp, C.c_int, _vp, _vp, _sz, C.c_uint32, C.c_int, _vp]),
     "troyb_galois_elt_from_step": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_uint32)]),
