@@ -255,6 +255,19 @@ int troyb_encrypt_zero_asymmetric(troyb_context *ctx, int level, const uint64_t 
 int troyb_encrypt_zero_symmetric(troyb_context *ctx, int level, const uint64_t *d_secret_key, const uint64_t *d_seeds, uint64_t *d_ct,
                                  size_t ct_stride, size_t batch, void *stream);
 
+/* Seeded ciphertexts, the reference CUDA path's transport form of a fresh symmetric encryption (half the bytes): c1 is not
+ * stored but re-expanded from a 64-bit seed by the reference's cuRAND sampler (coefficient g: XORWOW curand_init(seed + g, 0, 0),
+ * limb j: its j-th curand_uniform_double * q_j, truncated; src/utils/rlwe_cuda.cu:25-28, 152-163).
+ *   expand_seeded_poly : what CiphertextCuda::load(stream, context) does for seed != 0  src/ciphertext_cuda.cu:158-175: d_poly
+ *                        [batch][L][N] from d_ct_seeds [batch], in the sampled (NTT) domain; for BFV the loader then inverts it.
+ *   encrypt_zero_symmetric_seeded : encryptZeroSymmetric of the CUDA path  src/utils/rlwe_cuda.cu:261-333: as
+ *                        troyb_encrypt_zero_symmetric, but c1 is the expansion of a seed taken from the ciphertext generator
+ *                        (written to d_ct_seeds [batch]); the noise still comes from the host generator's stream. */
+int troyb_expand_seeded_poly(troyb_context *ctx, int level, const uint64_t *d_ct_seeds, uint64_t *d_poly, size_t poly_stride,
+                             size_t batch, void *stream);
+int troyb_encrypt_zero_symmetric_seeded(troyb_context *ctx, int level, const uint64_t *d_secret_key, const uint64_t *d_seeds,
+                                        uint64_t *d_ct, size_t ct_stride, uint64_t *d_ct_seeds, size_t batch, void *stream);
+
 /* ---- decryption: the step right after the path ------------------------------------------------- */
 
 /* DecryptorCuda::computeSecretKeyArray  src/decryptor_cuda.cu:188-235: d_out[i] = s^(i+1), i < max_power, each

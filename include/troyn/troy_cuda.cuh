@@ -344,9 +344,14 @@ public:
     const double &scale() const { return scale_; }
     std::uint64_t &correctionFactor() { return correction_; }
     const std::uint64_t &correctionFactor() const { return correction_; }
-    std::uint64_t *data() { return data_.get(); }
+    // CiphertextCuda::seed  src/ciphertext_cuda.cuh:189: nonzero for a fresh symmetric encryption whose c1 is the cuRAND
+    // expansion of the seed (save then stores c0 only). Any mutable access to the words clears it, which covers the
+    // `seed() = 0` of every evaluator method of the reference.
+    std::uint64_t seed() const { return seed_; }
+    std::uint64_t &seed() { return seed_; }
+    std::uint64_t *data() { seed_ = 0; return data_.get(); }
     const std::uint64_t *data() const { return data_.get(); }
-    std::uint64_t *data(std::size_t poly) { return data_.get() + poly * polyCoeffSize(); }
+    std::uint64_t *data(std::size_t poly) { seed_ = 0; return data_.get() + poly * polyCoeffSize(); }
     const std::uint64_t *data(std::size_t poly) const { return data_.get() + poly * polyCoeffSize(); }
 
     // resize / reserve keep the first min(old, new) polynomials (src/ciphertext_cuda.cuh:68-152)
@@ -361,39 +366,60 @@ public:
     void release() { *this = CiphertextCuda(); }
 
     // Wire format of the reference (src/ciphertext_cuda.cu:16-194): parms_id, is_ntt_form, size, N, limbs, scale,
-    // correction_factor, seed, terms, data_size, data. Seeded ciphertexts (the transport form of fresh symmetric
-    // encryptions, expanded with the reference's cuRAND sampler) are never produced here and are rejected on load.
+    // correction_factor, seed, terms, data_size, data. A seeded ciphertext (a fresh symmetric encryption) stores c0 only; its
+    // c1 is re-expanded from the seed on load(stream, context) with the reference's cuRAND sampler semantics.
     void save(std::ostream &stream) const {
-        std::vector<std::uint64_t> w(size_ * n_ * limbs_);
+        if (seed_ != 0 && size_ > 2) throw std::invalid_argument("Seed exists but size is not 2.");
+        std::vector<std::uint64_t> w((seed_ != 0 ? 1 : size_) * n_ * limbs_);
         data_.download(w.data(), w.size());
         saveHeader(stream, false);
         const std::size_t count = w.size();
         stream.write(reinterpret_cast<const char *>(&count), sizeof(count));
         stream.write(reinterpret_cast<const char *>(w.data()), count * 8);
     }
-    void load(std::istream &stream) {
-        if (loadHeader(stream)) throw std::invalid_argument("Trying to load a termed ciphertext, but indices is not specified");
-        std::size_t count = 0;
-        stream.read(reinterpret_cast<char *>(&count), sizeof(count));
-        std::vector<std::uint64_t> w(count);
-        stream.read(reinterpret_cast<char *>(w.data()), count * 8);
-        if (count < size_ * n_ * limbs_) throw std::invalid_argument("ciphertext data is too short");
-        data_ = b200::DeviceWords(size_ * n_ * limbs_);
-        data_.upload(w.data(), size_ * n_ * limbs_);
-    }
-    void load(std::istream &stream, const SEALContextCuda &) { load(stream); }
+    void load(std::istream &stream) { loadImpl(stream, nullptr); }
+    void load(std::istream &stream, const SEALContextCuda &context) { loadImpl(stream, &context); }
     // saveTerms / loadTerms (:45-77, :101-140): only the listed coefficients of poly 0 travel (coefficient form), poly 1.. whole
     inline void saveTerms(std::ostream &stream, EvaluatorCuda &evaluator, const std::vector<std::size_t> &term_ids) const;
     inline void loadTerms(std::istream &stream, EvaluatorCuda &evaluator, const std::vector<std::size_t> &term_ids);
 
     // used by the evaluator when an operation changes the limb count
     void adopt(b200::DeviceWords &&data, std::size_t size, std::size_t n, std::size_t limbs) {
-        data_ = std::move(data); size_ = size; n_ = n; limbs_ = limbs;
+        data_ = std::move(data); size_ = size; n_ = n; limbs_ = limbs; seed_ = 0;
     }
 
 private:
+    void loadImpl(std::istream &stream, const SEALContextCuda *context) {
+        std::uint64_t seed = 0;
+        if (loadHeader(stream, &seed)) throw std::invalid_argument("Trying to load a termed ciphertext, but indices is not specified");
+        if (seed != 0 && !context) throw std::invalid_argument("seed is not zero.");
+        if (seed != 0 && size_ > 2) throw std::invalid_argument("Seed exists but size is not 2.");
+        std::size_t count = 0;
+        stream.read(reinterpret_cast<char *>(&count), sizeof(count));
+        std::vector<std::uint64_t> w(count);
+        stream.read(reinterpret_cast<char *>(w.data()), count * 8);
+        const std::size_t stored = (seed != 0 ? 1 : size_) * n_ * limbs_;
+        if (count < stored) throw std::invalid_argument("ciphertext data is too short");
+        data_ = b200::DeviceWords(size_ * n_ * limbs_);
+        data_.upload(w.data(), stored);
+        if (seed != 0) { // src/ciphertext_cuda.cu:158-190: c1 from the seed, inverted for the coefficient-form schemes (the
+                         // reference's loader inverts for BFV only, which leaves its BGV seeded ciphertexts undecryptable)
+            const bool key_level = parms_id_ == context->keyParmsID() && context->using_keyswitching();
+            const int level = key_level ? -1 : context->levelOf(parms_id_);
+            b200::DeviceWords d_seed(1);
+            d_seed.upload(&seed, 1);
+            std::uint64_t *c1 = data_.get() + n_ * limbs_;
+            b200::check(troyb_expand_seeded_poly(context->handle(), level, d_seed.get(), c1, n_ * limbs_, 1, b200::stream()));
+            if (context->keyContextData()->parms().scheme() != SchemeType::ckks) {
+                if (key_level) b200::check(troyb_ntt_inverse_key(context->handle(), c1, 1, b200::stream()));
+                else b200::check(troyb_ntt_inverse(context->handle(), level, c1, 1, b200::stream()));
+            }
+            b200::synchronize(); // `seed` and `w` are host temporaries of this call
+        }
+        seed_ = 0; // as the reference's loaders leave it
+    }
     void saveHeader(std::ostream &stream, bool terms) const {
-        const std::uint64_t seed = 0;
+        const std::uint64_t seed = seed_;
         stream.write(reinterpret_cast<const char *>(&parms_id_), sizeof(ParmsID));
         stream.write(reinterpret_cast<const char *>(&is_ntt_), sizeof(bool));
         stream.write(reinterpret_cast<const char *>(&size_), sizeof(std::size_t));
@@ -404,7 +430,7 @@ private:
         stream.write(reinterpret_cast<const char *>(&seed), sizeof(std::uint64_t));
         stream.write(reinterpret_cast<const char *>(&terms), sizeof(bool));
     }
-    bool loadHeader(std::istream &stream) { // returns the `terms` flag
+    bool loadHeader(std::istream &stream, std::uint64_t *seed_out = nullptr) { // returns the `terms` flag
         std::uint64_t seed = 0;
         bool terms = false;
         stream.read(reinterpret_cast<char *>(&parms_id_), sizeof(ParmsID));
@@ -416,7 +442,8 @@ private:
         stream.read(reinterpret_cast<char *>(&correction_), sizeof(std::uint64_t));
         stream.read(reinterpret_cast<char *>(&seed), sizeof(std::uint64_t));
         stream.read(reinterpret_cast<char *>(&terms), sizeof(bool));
-        if (seed != 0) throw std::invalid_argument("seed is not zero.");
+        if (seed_out) *seed_out = seed;
+        else if (seed != 0) throw std::invalid_argument("seed is not zero.");
         return terms;
     }
     void resizeInternal(std::size_t size, std::size_t n, std::size_t limbs) {
@@ -435,6 +462,7 @@ private:
     bool is_ntt_ = false;
     double scale_ = 1.0;
     std::uint64_t correction_ = 1;
+    std::uint64_t seed_ = 0;
     b200::DeviceWords data_;
 };
 
@@ -505,23 +533,112 @@ private:
     KeyGenerator gen_;
 };
 
-// Encryption / decryption are host work outside the hot path: host class + copy.
+// EncryptorCuda (src/encryptor_cuda.cuh / .cu): encryption runs on the device and follows the reference's CPU encryptor word
+// for word (src/encryptor.cpp:88-253, src/utils/rlwe.cpp:160-356): every call takes a generator from the parameters' factory
+// (parms.randomGenerator()->create(), so a factory with a fixed seed reproduces the CPU path's ciphertexts) and hands its
+// 64-byte seed to troyb_encrypt_zero_*; the plaintext is then added into c0 on the device. Only the Blake2xb generator (the
+// default) is reproduced. (The reference's own CUDA encryptor draws from cuRAND and matches no host generator.)
 class EncryptorCuda {
 public:
-    EncryptorCuda(const SEALContextCuda &context, const PublicKey &pk) : enc_(context.host(), pk) {}
-    EncryptorCuda(const SEALContextCuda &context, const SecretKey &sk) : enc_(context.host(), sk) {}
-    EncryptorCuda(const SEALContextCuda &context, const PublicKey &pk, const SecretKey &sk) : enc_(context.host(), pk, sk) {}
-    void encrypt(const Plaintext &plain, CiphertextCuda &dst) const { Ciphertext c; enc_.encrypt(plain, c); dst = CiphertextCuda(c); }
-    void encryptSymmetric(const Plaintext &plain, CiphertextCuda &dst) const { Ciphertext c; enc_.encryptSymmetric(plain, c); dst = CiphertextCuda(c); }
+    EncryptorCuda(const SEALContextCuda &context, const PublicKey &pk) : context_(context) { setPublicKey(pk); }
+    EncryptorCuda(const SEALContextCuda &context, const SecretKey &sk) : context_(context) { setSecretKey(sk); }
+    EncryptorCuda(const SEALContextCuda &context, const PublicKey &pk, const SecretKey &sk) : context_(context) {
+        setPublicKey(pk);
+        setSecretKey(sk);
+    }
+    EncryptorCuda(const EncryptorCuda &) = delete;
+    EncryptorCuda(EncryptorCuda &&) = delete;
+    void setPublicKey(const PublicKey &pk) {
+        if (!isMetadataValidFor(pk, context_.host()) || !isBufferValid(pk)) throw std::invalid_argument("public key is not valid for encryption parameters");
+        const Ciphertext &k = pk.data();
+        pk_.allocate(k.size() * k.coeffModulusSize() * k.polyModulusDegree());
+        pk_.upload(k.data(), pk_.size());
+    }
+    void setSecretKey(const SecretKey &sk) {
+        if (!isMetadataValidFor(sk, context_.host()) || !isBufferValid(sk)) throw std::invalid_argument("secret key is not valid for encryption parameters");
+        sk_.allocate(sk.data().coeffCount());
+        sk_.upload(sk.data().data(), sk_.size());
+    }
+    void encrypt(const Plaintext &plain, CiphertextCuda &dst) const { encryptInternal(plain, true, dst); }
+    void encryptSymmetric(const Plaintext &plain, CiphertextCuda &dst) const { encryptInternal(plain, false, dst); }
     CiphertextCuda encrypt(const Plaintext &plain) const { CiphertextCuda d; encrypt(plain, d); return d; }
     CiphertextCuda encryptSymmetric(const Plaintext &plain) const { CiphertextCuda d; encryptSymmetric(plain, d); return d; }
-    void setPublicKey(const PublicKey &pk) { enc_.setPublicKey(pk); }
-    void setSecretKey(const SecretKey &sk) { enc_.setSecretKey(sk); }
-    void encryptZero(CiphertextCuda &dst) const { Ciphertext c; enc_.encryptZero(c); dst = CiphertextCuda(c); }
-    void encryptZero(ParmsID id, CiphertextCuda &dst) const { Ciphertext c; enc_.encryptZero(id, c); dst = CiphertextCuda(c); }
+    void encryptZero(CiphertextCuda &dst) const { encryptZeroInternal(context_.firstParmsID(), true, dst); }
+    void encryptZero(ParmsID id, CiphertextCuda &dst) const { encryptZeroInternal(id, true, dst); }
+    CiphertextCuda encryptZero() const { CiphertextCuda d; encryptZero(d); return d; }
+    CiphertextCuda encryptZero(ParmsID id) const { CiphertextCuda d; encryptZero(id, d); return d; }
+    void encryptZeroSymmetric(CiphertextCuda &dst) const { encryptZeroInternal(context_.firstParmsID(), false, dst); }
+    void encryptZeroSymmetric(ParmsID id, CiphertextCuda &dst) const { encryptZeroInternal(id, false, dst); }
+    CiphertextCuda encryptZeroSymmetric() const { CiphertextCuda d; encryptZeroSymmetric(d); return d; }
+    CiphertextCuda encryptZeroSymmetric(ParmsID id) const { CiphertextCuda d; encryptZeroSymmetric(id, d); return d; }
+    // Symmetric encryptions in the reference's CUDA path are SEEDED (c1 = cuRAND expansion of destination.seed(), so that save
+    // writes c0 + seed; src/utils/rlwe_cuda.cu:290-305) - the default here too. false: c1 is drawn from the Blake2xb ciphertext
+    // generator as the CPU path does (src/utils/rlwe.cpp:290-296), word for word.
+    void setSeededSymmetric(bool on) { seeded_symmetric_ = on; }
 
 private:
-    Encryptor enc_;
+    // Encryptor::encryptZeroInternal  src/encryptor.cpp:88-164
+    void encryptZeroInternal(const ParmsID &id, bool asymmetric, CiphertextCuda &dst) const {
+        auto cd = context_.getContextData(id);
+        if (!cd) throw std::invalid_argument("parms_id is not valid for encryption parameters");
+        const b200::DeviceWords &key = asymmetric ? pk_ : sk_;
+        if (!key.size()) throw std::logic_error(asymmetric ? "public key is not set" : "secret key is not set");
+        const auto &parms = cd->parms();
+        auto prng = parms.randomGenerator()->create();
+        if (prng->info().type() != PRNGType::blake2xb) throw std::logic_error("only the Blake2xb generator is reproduced on the device");
+        const PRNGSeed seed = prng->seed();
+        b200::DeviceWords d_seed(seed.size());
+        d_seed.upload(seed.data(), seed.size());
+        const int level = id == context_.keyParmsID() && context_.using_keyswitching() ? -1 : context_.levelOf(id);
+        const std::size_t n = parms.polyModulusDegree(), limbs = parms.coeffModulus().size();
+        b200::DeviceWords out(2 * n * limbs);
+        if (asymmetric) b200::check(troyb_encrypt_zero_asymmetric(context_.handle(), level, key.get(), d_seed.get(), out.get(), out.size(), 1, b200::stream()));
+        else if (!seeded_symmetric_) b200::check(troyb_encrypt_zero_symmetric(context_.handle(), level, key.get(), d_seed.get(), out.get(), out.size(), 1, b200::stream()));
+        std::uint64_t ct_seed = 0;
+        if (!asymmetric && seeded_symmetric_) {
+            b200::DeviceWords d_ct_seed(1);
+            b200::check(troyb_encrypt_zero_symmetric_seeded(context_.handle(), level, key.get(), d_seed.get(), out.get(), out.size(), d_ct_seed.get(), 1, b200::stream()));
+            d_ct_seed.download(&ct_seed, 1);
+            b200::synchronize();
+        }
+        dst.adopt(std::move(out), 2, n, limbs);
+        dst.parmsID() = id;
+        dst.isNttForm() = parms.scheme() == SchemeType::ckks;
+        dst.scale() = 1.0;
+        dst.correctionFactor() = 1;
+        dst.seed() = ct_seed;
+    }
+    // Encryptor::encryptInternal  src/encryptor.cpp:166-253
+    void encryptInternal(const Plaintext &plain, bool asymmetric, CiphertextCuda &dst) const {
+        if (!isValidFor(plain, context_.host())) throw std::invalid_argument("plain is not valid for encryption parameters");
+        const SchemeType scheme = context_.keyContextData()->parms().scheme();
+        if (scheme == SchemeType::ckks) {
+            if (!plain.isNttForm()) throw std::invalid_argument("plain must be in NTT form");
+            if (!context_.getContextData(plain.parmsID())) throw std::invalid_argument("plain is not valid for encryption parameters");
+            encryptZeroInternal(plain.parmsID(), asymmetric, dst);
+            const std::uint64_t ct_seed = dst.seed(); // adding into c0 leaves c1, and with it the seed, valid
+            b200::DeviceWords p(dst.polyCoeffSize());
+            p.upload(plain.data(), p.size());
+            std::uint64_t *c0 = dst.data();
+            b200::check(troyb_add(context_.handle(), context_.levelOf(plain.parmsID()), c0, p.get(), c0, 1, b200::stream()));
+            dst.scale() = plain.scale();
+            dst.seed() = ct_seed;
+            return;
+        }
+        if (plain.isNttForm()) throw std::invalid_argument("plain cannot be in NTT form");
+        encryptZeroInternal(context_.firstParmsID(), asymmetric, dst);
+        // BFV: multiplyAddPlainWithScalingVariant; BGV: addPlainWithoutScalingVariant (the fresh correction factor is 1)
+        const std::size_t count = plain.coeffCount();
+        if (!count) return;
+        const std::uint64_t ct_seed = dst.seed();
+        b200::DeviceWords p(count);
+        p.upload(plain.data(), count);
+        b200::check(troyb_add_plain(context_.handle(), 0, dst.data(), 2 * dst.polyCoeffSize(), p.get(), count, 0, 1, 0, 1, b200::stream()));
+        dst.seed() = ct_seed;
+    }
+    const SEALContextCuda &context_;
+    b200::DeviceWords pk_, sk_;
+    bool seeded_symmetric_ = true;
 };
 
 // DecryptorCuda (src/decryptor_cuda.cuh / .cu): the secret key powers live on the device; decrypt() is the dot product
@@ -924,6 +1041,7 @@ inline void CiphertextCuda::saveTerms(std::ostream &stream, EvaluatorCuda &evalu
     copy.data_.download(w.data(), w.size());
     // the header records the form of the ORIGINAL ciphertext (src/ciphertext_cuda.cu:46-47)
     saveHeader(stream, true);
+    if (seed_ != 0) throw std::invalid_argument("Seed is not zero."); // after the header, as the reference (:64-66)
     for (std::size_t id : term_ids)
         for (std::size_t j = 0; j < limbs_; j++) stream.write(reinterpret_cast<const char *>(&w[j * n_ + id]), 8);
     const std::size_t offset = n_ * limbs_, count = w.size() - offset;

@@ -149,6 +149,32 @@ static int serialize(const char *in_path, const char *dir) {
     append(out, c2);
     std::ofstream o(d + "/ours_result.bin", std::ios::binary);
     o.write(reinterpret_cast<const char *>(out.data()), out.size() * 8);
+    // Seeded ciphertexts (the transport form of fresh symmetric encryptions): the reference encrypts zero symmetrically, saves
+    // (c0 + seed), reloads with the context (c1 re-expanded by its cuRAND sampler) and writes the words; then it loads
+    // <dir>/ours_seeded_ct.bin (a seeded ciphertext written by troy_b200) the same way, decrypts it and writes the plaintext.
+    {
+        Encryptor enc(context, pk, keygen.secretKey());
+        Ciphertext z;
+        enc.encryptZeroSymmetric(z);
+        { std::ofstream f(d + "/seeded_ct.bin", std::ios::binary); z.save(f); }
+        Ciphertext z2;
+        { std::ifstream f(d + "/seeded_ct.bin", std::ios::binary); z2.load(f, context); }
+        std::vector<uint64_t> w;
+        append(w, z2);
+        std::ofstream o1(d + "/seeded_expanded.bin", std::ios::binary);
+        o1.write(reinterpret_cast<const char *>(w.data()), w.size() * 8);
+        std::ifstream f(d + "/ours_seeded_ct.bin", std::ios::binary);
+        if (f.good()) {
+            Ciphertext mine;
+            mine.load(f, context);
+            Decryptor dec(context, keygen.secretKey());
+            Plaintext p;
+            dec.decrypt(mine, p);
+            troy::Plaintext hp = p.cpu();
+            std::ofstream o2(d + "/ours_seeded_plain.bin", std::ios::binary);
+            o2.write(reinterpret_cast<const char *>(hp.data()), hp.coeffCount() * 8);
+        }
+    }
     std::printf("serialize ok\n");
     return 0;
 }

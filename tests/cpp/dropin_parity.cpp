@@ -8,6 +8,7 @@
 
 #include <cstring>
 #include <random>
+#include <sstream>
 
 namespace {
 
@@ -168,5 +169,81 @@ template <SchemeType S> void integerSchemeFlow() {
 
 TEST(DropInParity, BFVMultiplyRelinRotateModSwitch) { integerSchemeFlow<SchemeType::bfv>(); }
 TEST(DropInParity, BGVMultiplyRelinRotateModSwitch) { integerSchemeFlow<SchemeType::bgv>(); }
+
+// Encryption on the device through the drop-in EncryptorCuda: with the parameters' generator factory seeded, every word
+// equals the reference CPU Encryptor's (asymmetric and symmetric, encrypt-zero at each level and encrypt of a plaintext).
+template <SchemeType scheme> void encryptFlow() {
+    troyn::KernelProvider::initialize();
+    const size_t n = 4096;
+    troyn::EncryptionParameters parms(scheme);
+    parms.setPolyModulusDegree(n);
+    parms.setCoeffModulus(CoeffModulus::Create(n, {60, 40, 40, 60}));
+    if (scheme != SchemeType::ckks) parms.setPlainModulus(PlainModulus::Batching(n, 20));
+    parms.setRandomGenerator(seeded());
+    troyn::SEALContext context(parms, true, SecurityLevel::none);
+    troyn::KeyGenerator keygen(context);
+    troyn::PublicKey pk;
+    keygen.createPublicKey(pk);
+    Encryptor cpu(context.host(), pk, keygen.secretKey());
+    troyn::Encryptor gpu(context, pk, keygen.secretKey());
+    gpu.setSeededSymmetric(false); // the CPU path's symmetric encryption (c1 from the Blake2xb ciphertext generator)
+    for (auto cd = context.firstContextData(); cd; cd = cd->nextContextData()) {
+        Ciphertext want;
+        troyn::Ciphertext got;
+        cpu.encryptZero(cd->parmsID(), want);
+        gpu.encryptZero(cd->parmsID(), got);
+        expectSame(got, want, context, "encryptZero");
+        cpu.encryptZeroSymmetric(cd->parmsID(), want);
+        gpu.encryptZeroSymmetric(cd->parmsID(), got);
+        expectSame(got, want, context, "encryptZeroSymmetric");
+    }
+    Plaintext plain;
+    if (scheme == SchemeType::ckks) {
+        CKKSEncoder encoder(context.host());
+        std::vector<std::complex<double>> v(n / 2);
+        for (size_t i = 0; i < n / 2; i++) v[i] = {double(i % 31), double(i % 7)};
+        encoder.encode(v, context.firstParmsID(), std::pow(2.0, 40), plain);
+    } else {
+        BatchEncoder encoder(context.host());
+        std::vector<uint64_t> v(n);
+        for (size_t i = 0; i < n; i++) v[i] = (7 * i + 3) % 1000;
+        encoder.encode(v, plain);
+    }
+    Ciphertext want;
+    troyn::Ciphertext got;
+    cpu.encrypt(plain, want);
+    gpu.encrypt(plain, got);
+    expectSame(got, want, context, "encrypt");
+    cpu.encryptSymmetric(plain, want);
+    gpu.encryptSymmetric(plain, got);
+    expectSame(got, want, context, "encryptSymmetric");
+    // the CUDA path's seeded form: save writes c0 + seed (half the words), load(stream, context) re-expands c1
+    gpu.setSeededSymmetric(true);
+    troyn::Ciphertext seeded;
+    gpu.encryptSymmetric(plain, seeded);
+    ASSERT_NE(seeded.seed(), 0u);
+    std::stringstream ss, full;
+    seeded.save(ss);
+    got.save(full);
+    ASSERT_LT(ss.str().size(), full.str().size() / 2 + 128);
+    troyn::Ciphertext reloaded;
+    ASSERT_THROW({ std::stringstream again(ss.str()); reloaded.load(again); }, std::invalid_argument);
+    reloaded.load(ss, context);
+    {
+        Ciphertext a = seeded.cpu(), b = reloaded.cpu();
+        ASSERT_EQ(0, std::memcmp(a.data(), b.data(), 2 * a.polyModulusDegree() * a.coeffModulusSize() * 8)) << "seeded round trip";
+    }
+    got = reloaded;
+    // and the device decryptor gives the plaintext back
+    troyn::Decryptor dec(context, keygen.secretKey());
+    Plaintext back;
+    dec.decrypt(got, back);
+    if (scheme != SchemeType::ckks) {
+        for (size_t i = 0; i < plain.coeffCount(); i++) ASSERT_EQ(i < back.coeffCount() ? back.data()[i] : 0, plain.data()[i]) << "coefficient " << i;
+    }
+}
+TEST(DropInParity, CKKSEncryptOnDevice) { encryptFlow<SchemeType::ckks>(); }
+TEST(DropInParity, BFVEncryptOnDevice) { encryptFlow<SchemeType::bfv>(); }
+TEST(DropInParity, BGVEncryptOnDevice) { encryptFlow<SchemeType::bgv>(); }
 
 } // namespace

@@ -91,7 +91,7 @@ def test_samplers_emulated(ref, emul_lib, scheme, n, bits):
 
 
 @pytest.mark.parametrize("scheme,n,bits", [(2, 1024, [60, 40, 40, 60]), (1, 256, [40, 30, 30, 40]), (3, 4096, [60, 40, 60]),
-                                           (2, 256, [40]), (1, 16384, [60, 40, 60])])
+                                           (2, 256, [40]), (1, 16384, [60, 40, 60]), (2, 64, [40, 30, 30, 40]), (3, 32, [40, 30, 40])])
 def test_encrypt_emulated(ref, emul_lib, scheme, n, bits):
     """Encryption on the device: same seed, same words as the reference CPU encryptor."""
     from common import run_encrypt_flow

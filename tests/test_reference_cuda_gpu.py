@@ -90,6 +90,22 @@ def test_wire_format_against_the_reference_cuda_classes(ref, cuda_lib, tmp_path,
         ser.save_ciphertext(a, f)
     with open(tmp_path / "ours_rlk.bin", "wb") as f:
         ser.save_kswitch_keys(d_rlk, f)
+    # a seeded ciphertext of ours (fresh symmetric encryption: c0 + 64-bit seed) for the reference to load and decrypt
+    enc = tb.EncryptorCuda(ctx, None, rc.secret_key_words())
+    dec = tb.DecryptorCuda(ctx, rc.secret_key_words())
+    if ckks:
+        pw = np.stack([rng.integers(0, m, n, dtype=np.uint64) for m in rc.level_moduli(0)])
+        pt = tb.PlaintextCuda.from_host(ctx, pw, 0, sc)
+    else:
+        pt = tb.PlaintextCuda.from_host(ctx, rng.integers(0, rc.plain_modulus, n, dtype=np.uint64))
+    mine = enc.encrypt_symmetric(pt, save_seed=True)
+    assert mine.seeds is not None and int(mine.seeds[0]) != 0
+    with open(tmp_path / "ours_seeded_ct.bin", "wb") as f:
+        ser.save_ciphertext(mine, f)
+    assert os.path.getsize(tmp_path / "ours_seeded_ct.bin") < os.path.getsize(tmp_path / "ours_ct.bin") // 2 + 128
+    my_plain = dec.decrypt(mine).to_host()[0]
+    back = ser.load_ciphertext(ctx, io.BytesIO(open(tmp_path / "ours_seeded_ct.bin", "rb").read()))
+    assert np.array_equal(back.to_host(), mine.to_host()), "seeded save / load round trip"
     r = subprocess.run([TOOL, "serialize", fin, str(tmp_path)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
     assert open(tmp_path / "ct.bin", "rb").read() == open(tmp_path / "ours_ct.bin", "rb").read(), "ciphertext bytes differ"
@@ -101,3 +117,10 @@ def test_wire_format_against_the_reference_cuda_classes(ref, cuda_lib, tmp_path,
     ev.relinearize_inplace(a, loaded)
     raw = np.fromfile(tmp_path / "ours_result.bin", dtype=np.uint64)
     assert np.array_equal(raw[1:], a.to_host()[0].reshape(-1)), "the reference computed something else from our bytes"
+    # the reference's seeded ciphertext: our loader's expansion of c1 equals the reference loader's, word for word
+    theirs = ser.load_ciphertext(ctx, io.BytesIO(open(tmp_path / "seeded_ct.bin", "rb").read()))
+    want = np.fromfile(tmp_path / "seeded_expanded.bin", dtype=np.uint64)
+    assert np.array_equal(theirs.to_host()[0].reshape(-1), want[1:]), "c1 expanded from the reference's seed differs"
+    # and the reference, loading OUR seeded ciphertext, decrypts what our decryptor decrypts
+    got = np.fromfile(tmp_path / "ours_seeded_plain.bin", dtype=np.uint64)
+    assert np.array_equal(got, my_plain[: got.size]) and not my_plain[got.size:].any(), "the reference decrypted something else"

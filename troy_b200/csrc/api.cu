@@ -1339,8 +1339,8 @@ u64 prng_expand(const u64 *d_seeds, u64 seed_stride, u64 *d_out, u64 out_stride,
     k.out = d_out;
     k.out_stride = out_stride;
     k.buffers = (u32)((bytes + Blake2::kBufferBytes - 1) / Blake2::kBufferBytes);
-    k.ctas_per_stream = (k.buffers + 3) / 4;
-    ck(launch_cta(k, batch * k.ctas_per_stream, 4 * 8 * sizeof(u64), s));
+    k.ctas_per_stream = (k.buffers + PrngExpand::kBuffersPerCta - 1) / PrngExpand::kBuffersPerCta;
+    ck(launch_cta(k, batch * k.ctas_per_stream, PrngExpand::kBuffersPerCta * 8 * sizeof(u64), s));
     return (u64)k.buffers * (Blake2::kBufferBytes / 8);
 }
 u64 buffers_words(u64 bytes) { return (bytes + Blake2::kBufferBytes - 1) / Blake2::kBufferBytes * (Blake2::kBufferBytes / 8); }
@@ -1358,7 +1358,6 @@ PrngView make_view(const u64 *d_stream, u64 bytes, const u64 *d_seeds) {
 void sample_small(Context *c, const LevelBase &lb, const PrngView &view, u64 view_stride, u64 seed_stride, u64 start_bytes,
                   u32 n_tern, u32 n_cbd, u64 *d_out, u64 out_stride, u64 *d_end, u32 batch, cudaStream_t s) {
     const u32 N = (u32)c->N, nseg = (N + kSampleSeg - 1) / kSampleSeg;
-    if (N % kSampleSeg) throw std::invalid_argument("poly_modulus_degree must be a multiple of 256 for the device samplers");
     if (start_bytes & 3) throw std::invalid_argument("stream position must be a multiple of 4");
     Scratch seg(n_tern ? (size_t)batch * (nseg + 2) : 0, s);
     if (n_tern) {
@@ -1432,6 +1431,25 @@ void sample_uniform(Context *c, const LevelBase &lb, const PrngView &view, u64 v
     r.out_stride = out_stride;
     r.repl = repl.p;
     ck(launch_cta(r, batch, SampleUniformResolve::kSmemWords * sizeof(u64), s));
+}
+
+// c1 of a seeded ciphertext from its 64-bit seed (NTT domain for every scheme; see SeededUniformExpand)
+void seeded_expand(Context *c, const LevelBase &lb, const u64 *d_ct_seeds, u64 *d_poly, u64 poly_stride, u32 batch, cudaStream_t s) {
+#if defined(TROYB_HOST_EMUL)
+    (void)c; (void)lb; (void)d_ct_seeds; (void)d_poly; (void)poly_stride; (void)batch; (void)s;
+    throw std::logic_error("seeded ciphertexts need the cuRAND device generator (not available in the host emulation)");
+#else
+    SeededUniformExpand k{};
+    k.seeds = d_ct_seeds;
+    k.N = (u32)c->N;
+    k.n_limbs = lb.L;
+    k.mods = c->d_mods;
+    k.map = lb.map;
+    k.out = d_poly;
+    k.out_stride = poly_stride;
+    k.total = (u64)batch * c->N;
+    ck(launch_cta(k, grid_for(k.total, SeededUniformExpand::kThreads), 0, s));
+#endif
 }
 
 void enc_combine(Context *c, const LevelBase &lb, int op, u32 polys, u32 batch, const u64 *x, u64 x_batch, u64 x_poly, const u64 *y,
@@ -1551,30 +1569,49 @@ int troyb_encrypt_zero_asymmetric(troyb_context *ctx, int level, const uint64_t 
     API_END
 }
 
-int troyb_encrypt_zero_symmetric(troyb_context *ctx, int level, const uint64_t *d_secret_key, const uint64_t *d_seeds, uint64_t *d_ct,
-                                 size_t ct_stride, size_t batch, void *stream) {
-    API_BEGIN
-    need_init();
-    Context *c = C(ctx);
-    cudaStream_t s = S(stream);
+namespace {
+// encryptZeroSymmetric. d_ct_seeds == null: c1 is drawn from the ciphertext generator by samplePolyUniform (the CPU path,
+// src/utils/rlwe.cpp:245-356); else c1 is the cuRAND expansion of a 64-bit seed taken from that generator, which is written to
+// d_ct_seeds [batch] (the CUDA path's seeded form, src/utils/rlwe_cuda.cu:261-333).
+void encrypt_zero_symmetric(Context *c, int level, const u64 *d_secret_key, const u64 *d_seeds, u64 *d_ct, u64 ct_stride,
+                            u64 *d_ct_seeds, u32 B, cudaStream_t s) {
     const u64 N = c->N;
     const bool ntt_form = c->scheme == SCHEME_CKKS;
     const LevelBase lb = level_base(c, level);
     const u64 poly = (u64)lb.L * N;
     check_batch_stride(ct_stride, 2 * (size_t)poly, "ct");
     check_aligned(d_ct, "ct");
-    const u32 B = (u32)batch;
-    if (!B) return TROYB_OK;
+    if (!B) return;
     // bootstrap generator: 64 bytes = the seed of the generator that expands c1, then N noise draws of 6 bytes
     const u64 boot_bytes = 64 + 6 * N, bw = buffers_words(boot_bytes);
     Scratch boot((size_t)B * bw, s);
     prng_expand(d_seeds, 8, boot.p, bw, boot_bytes, B, s);
-    // ciphertext generator: L * N words + the redraws (a word is rejected with probability < q / 2^64 <= 1/8)
-    const u64 uni_bytes = poly * 8 + poly + 4096, uw = buffers_words(uni_bytes);
-    Scratch uni((size_t)B * uw, s);
-    prng_expand(boot.p, bw, uni.p, uw, uni_bytes, B, s);
     u64 *c1 = d_ct + poly;
-    sample_uniform(c, lb, make_view(uni.p, uw * 8, boot.p), uw, bw, c1, ct_stride, B, s);
+    if (d_ct_seeds) {
+        const u64 uw = buffers_words(Blake2::kBufferBytes);
+        Scratch uni((size_t)B * uw, s);
+        prng_expand(boot.p, bw, uni.p, uw, Blake2::kBufferBytes, B, s);
+        SeedFromStream k{};
+        k.view = make_view(uni.p, uw * 8, boot.p);
+        k.view_stride = uw;
+        k.seed_stride = bw;
+        k.batch = B;
+        k.out = d_ct_seeds;
+        ck(launch_cta(k, grid_for(B, SeedFromStream::kThreads), 0, s));
+        seeded_expand(c, lb, d_ct_seeds, c1, ct_stride, B, s);
+    } else {
+        // ciphertext generator: L * N words + the redraws. A word is rejected with probability (2^64 mod q + 1) / 2^64 (tiny for
+        // the usual primes just below a power of two): expand twice the expected number + a buffer; the rest is computed on demand
+        double redraws = 0;
+        for (u32 l = 0; l < lb.L; l++) {
+            const u64 q = c->pool[lb.map.idx[l]];
+            redraws += (double)N * ((double)((~0ull) % q + 2) / 18446744073709551616.0);
+        }
+        const u64 uni_bytes = poly * 8 + 16 * (u64)redraws + 4096, uw = buffers_words(uni_bytes);
+        Scratch uni((size_t)B * uw, s);
+        prng_expand(boot.p, bw, uni.p, uw, uni_bytes, B, s);
+        sample_uniform(c, lb, make_view(uni.p, uw * 8, boot.p), uw, bw, c1, ct_stride, B, s);
+    }
     Scratch noise((size_t)B * poly, s);
     sample_small(c, lb, make_view(boot.p, bw * 8, d_seeds), bw, 8, 64, 0, 1, noise.p, poly, nullptr, B, s);
     const u64 f = c->scheme == SCHEME_BGV ? c->plain : 1;
@@ -1586,6 +1623,34 @@ int troyb_encrypt_zero_symmetric(troyb_context *ctx, int level, const uint64_t *
         ntt_plain(c, true, lb.map, lb.L, d_ct, ct_stride, d_ct, ct_stride, 2 * lb.L, B, true, s);
         enc_combine(c, lb, 3, 1, B, nullptr, 0, 0, nullptr, 0, 0, noise.p, poly, 0, d_ct, ct_stride, 0, f, s);
     }
+}
+} // namespace
+
+int troyb_encrypt_zero_symmetric(troyb_context *ctx, int level, const uint64_t *d_secret_key, const uint64_t *d_seeds, uint64_t *d_ct,
+                                 size_t ct_stride, size_t batch, void *stream) {
+    API_BEGIN
+    need_init();
+    encrypt_zero_symmetric(C(ctx), level, d_secret_key, d_seeds, d_ct, ct_stride, nullptr, (u32)batch, S(stream));
+    API_END
+}
+
+int troyb_encrypt_zero_symmetric_seeded(troyb_context *ctx, int level, const uint64_t *d_secret_key, const uint64_t *d_seeds,
+                                        uint64_t *d_ct, size_t ct_stride, uint64_t *d_ct_seeds, size_t batch, void *stream) {
+    API_BEGIN
+    need_init();
+    if (!d_ct_seeds) throw std::invalid_argument("ct_seeds is null");
+    encrypt_zero_symmetric(C(ctx), level, d_secret_key, d_seeds, d_ct, ct_stride, d_ct_seeds, (u32)batch, S(stream));
+    API_END
+}
+
+int troyb_expand_seeded_poly(troyb_context *ctx, int level, const uint64_t *d_ct_seeds, uint64_t *d_poly, size_t poly_stride,
+                             size_t batch, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const LevelBase lb = level_base(c, level);
+    check_batch_stride(poly_stride, (size_t)lb.L * c->N, "poly");
+    seeded_expand(c, lb, d_ct_seeds, d_poly, poly_stride, (u32)batch, S(stream));
     API_END
 }
 

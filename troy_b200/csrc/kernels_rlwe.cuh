@@ -13,6 +13,9 @@
 // src/utils/blake2b.c / blake2xb.c implement.
 #pragma once
 #include "launch.cuh"
+#if !defined(TROYB_HOST_EMUL)
+#include <curand_kernel.h>
+#endif
 
 namespace troyb {
 
@@ -143,7 +146,8 @@ TB_HD int popc8(u32 x) {
 // Blake2xbPRNG::refill_buffer  src/randomgen.cpp:184-194, for `buffers` consecutive buffers (from counter 0) of `batch`
 // generators. Seeds: 8 words each, seed_stride words apart (they may be the first 64 bytes of another expanded stream).
 struct PrngExpand {
-    static constexpr int kThreads = 256; // four 4096-byte buffers per CTA, one 64-byte block per thread
+    static constexpr int kThreads = 256;
+    static constexpr u32 kBuffersPerCta = 16; // root hashes by 16 threads, then 4 rounds of one 64-byte block per thread
     const char *name() const { return "prng_blake2xb_expand"; }
     const u64 *seeds;
     u64 seed_stride;
@@ -152,9 +156,9 @@ struct PrngExpand {
     u32 buffers;    // per generator
     u32 ctas_per_stream;
     TB_D void operator()(u32 bid, u64 *smem) const {
-        const u32 b = bid / ctas_per_stream, c0 = (bid % ctas_per_stream) * 4;
+        const u32 b = bid / ctas_per_stream, c0 = (bid % ctas_per_stream) * kBuffersPerCta;
         TB_PHASE(kThreads, t, {
-            if (t < 4 && c0 + t < buffers) {
+            if (t < kBuffersPerCta && c0 + t < buffers) {
                 u64 sd[8], rt[8];
                 for (int i = 0; i < 8; i++) sd[i] = seeds[b * seed_stride + i];
                 Blake2::root(sd, c0 + t, rt);
@@ -162,13 +166,15 @@ struct PrngExpand {
             }
         })
         TB_PHASE(kThreads, t, {
-            const u32 c = c0 + (t >> 6);
-            if (c < buffers) {
-                u64 rt[8], o[8];
-                for (int i = 0; i < 8; i++) rt[i] = smem[(t >> 6) * 8 + i];
-                Blake2::block(rt, t & 63, o);
-                u64 *dst = out + b * out_stride + (u64)c * 512 + (t & 63) * 8;
-                for (int i = 0; i < 8; i++) dst[i] = o[i];
+            for (u32 r = 0; r < kBuffersPerCta / 4; r++) {
+                const u32 k = r * 4 + (t >> 6), c = c0 + k;
+                if (c < buffers) {
+                    u64 rt[8], o[8];
+                    for (int i = 0; i < 8; i++) rt[i] = smem[k * 8 + i];
+                    Blake2::block(rt, t & 63, o);
+                    u64 *dst = out + b * out_stride + (u64)c * 512 + (t & 63) * 8;
+                    for (int i = 0; i < 8; i++) dst[i] = o[i];
+                }
             }
         })
     }
@@ -205,7 +211,8 @@ struct SampleTernaryScan {
         TB_PHASE(kThreads, t, {
             for (u32 s = t; s < nseg; s += kThreads) {
                 u32 z = 0;
-                for (u32 k = 0; k < kSampleSeg; k++) z += v.word32(k0 + (u64)s * kSampleSeg + k) == 0 ? 1u : 0u;
+                const u32 len = N - s * kSampleSeg < kSampleSeg ? N - s * kSampleSeg : kSampleSeg;
+                for (u32 k = 0; k < len; k++) z += v.word32(k0 + (u64)s * kSampleSeg + k) == 0 ? 1u : 0u;
                 sg[s] = z;
             }
         })
@@ -252,7 +259,7 @@ struct SampleExpand {
         const u64 k0 = start_bytes >> 2;
         TB_PHASE(kThreads, t, {
             const u32 i = s * kSampleSeg + t;
-            if (n_tern) {
+            if (i < N && n_tern) {
                 const u64 zeros = sg[nseg];
                 if (zeros == 0) {
                     const u32 w = v.word32(k0 + i);
@@ -260,7 +267,7 @@ struct SampleExpand {
                 } else if (t == 0) {
                     // a rejection somewhere in this polynomial (probability N * 2^-32): walk the segment in stream order
                     u64 z = sg[s];
-                    for (u32 k = 0; k < kSampleSeg; k++) {
+                    for (u32 k = 0; k < kSampleSeg && s * kSampleSeg + k < N; k++) {
                         const u64 pos = (u64)s * kSampleSeg + k;
                         const u32 w = v.word32(k0 + pos);
                         if (w == 0) z++;
@@ -276,7 +283,7 @@ struct SampleExpand {
                 }
             }
             const u64 base = n_tern ? sg[nseg + 1] : cbd_bytes;
-            for (u32 j = 0; j < n_cbd; j++) {
+            for (u32 j = 0; i < N && j < n_cbd; j++) {
                 const u64 x = v.bytes6(base + 6ull * ((u64)j * N + i));
                 const int noise = popc8((u32)x) + popc8((u32)(x >> 8)) + popc8((u32)(x >> 16) & 0x1F) - popc8((u32)(x >> 24)) -
                                   popc8((u32)(x >> 32)) - popc8((u32)(x >> 40) & 0x1F);
@@ -408,6 +415,63 @@ struct SampleUniformResolve {
     }
 };
 
+// ---- seeded ciphertexts (the reference's transport form of fresh symmetric encryptions) --------------------------------------
+// CiphertextCuda::load(stream, context)  src/ciphertext_cuda.cu:158-175 and encryptZeroSymmetric  src/utils/rlwe_cuda.cu:290-305:
+// c1 is not transmitted; it is the expansion of a 64-bit seed by the reference's cuRAND sampler, coefficient index g owning the
+// XORWOW generator curand_init(seed + g, 0, 0) and limb j taking its j-th curand_uniform_double draw times q_j, truncated
+// (gInitCurandStates / gSamplePolyUniform, src/utils/rlwe_cuda.cu:25-28, 152-163). cuRAND's device generator is NVIDIA's header
+// library; the arithmetic around it is restated. The result is in the "sampled" domain (NTT form; the caller inverts it for BFV
+// as the reference's loader does).
+struct SeededUniformExpand {
+    static constexpr int kThreads = 256;
+    const char *name() const { return "seeded_c1_expand"; }
+    const u64 *seeds; // [batch]
+    u32 N, n_limbs;
+    const ModDev *mods;
+    LimbMap map;
+    u64 *out;
+    u64 out_stride;
+    u64 total; // batch * N
+    TB_D void operator()(u32 bid, u64 *) const {
+#if !defined(TROYB_HOST_EMUL)
+        const u64 idx = (u64)bid * kThreads + threadIdx.x;
+        if (idx < total) {
+            const u64 b = idx / N, g = idx % N;
+            curandState st;
+            curand_init(seeds[b] + g, 0, 0, &st);
+            for (u32 j = 0; j < n_limbs; j++)
+                out[b * out_stride + (u64)j * N + g] = (u64)(curand_uniform_double(&st) * (double)mods[map.idx[j]].p);
+        }
+#else
+        (void)bid;
+#endif
+    }
+};
+
+// The 64-bit seed the reference's symmetric encryptor takes from the ciphertext generator (the first two 32-bit draws with a
+// nonzero combination, src/utils/rlwe_cuda.cu:292-297); one thread per generator.
+struct SeedFromStream {
+    static constexpr int kThreads = 32;
+    const char *name() const { return "seed_from_stream"; }
+    PrngView view;
+    u64 view_stride, seed_stride;
+    u32 batch;
+    u64 *out; // [batch]
+    TB_D void operator()(u32 bid, u64 *) const {
+        TB_PHASE(kThreads, t, {
+            const u32 b = bid * kThreads + t;
+            if (b < batch) {
+                PrngView v = view;
+                v.buf += b * view_stride;
+                if (v.seed) v.seed += b * seed_stride;
+                u64 seed = 0;
+                for (u64 k = 0; seed == 0; k += 2) seed = ((u64)v.word32(k) << 32) + v.word32(k + 1);
+                out[b] = seed;
+            }
+        })
+    }
+};
+
 // ---- encrypt-zero arithmetic ------------------------------------------------------------------------------------------------
 // The coefficient-wise steps of encryptZeroAsymmetric / encryptZeroSymmetric (src/utils/rlwe.cpp:199-242, 305-342): each is
 // dyadicProductCoeffmod / multiplyPolyScalarCoeffmod / addPolyCoeffmod / negatePolyCoeffmod in one pass.
@@ -433,9 +497,9 @@ struct EncCombine {
         TB_PHASE(kThreads, t, {
             const u64 idx = (u64)bid * kThreads + t;
             if (idx < total) {
-                const u64 per = (u64)n_limbs << logN;
-                const u64 unit = idx / per, r = idx % per;
-                const u64 b = unit / polys, j = unit % polys;
+                const u32 ul = (u32)(idx >> logN), unit = ul / n_limbs;
+                const u64 r = ((u64)(ul - unit * n_limbs) << logN) | (idx & ((u64(1) << logN) - 1));
+                const u64 b = unit / polys, j = unit - (u32)b * polys;
                 const ModDev &m = mods[map.idx[(u32)(r >> logN)]];
                 const u64 p = m.p;
                 u64 *po = out + b * out_batch + j * out_poly + r;

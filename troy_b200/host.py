@@ -244,6 +244,10 @@ class CiphertextCuda:
         self.limbs = context.level_limbs(level)
         self.capacity = max(int(capacity or 0), self.size)
         self.data = data if data is not None else context.alloc(self.batch * self.capacity * self.limbs * context.n, stream)
+        # CiphertextCuda::seed  src/ciphertext_cuda.cuh:189: [batch] 64-bit seeds of a FRESH symmetric encryption whose c1 is the
+        # cuRAND expansion of the seed (serialize.save_ciphertext then stores c0 only); None otherwise. Every evaluator call
+        # that takes the ciphertext clears it (the reference's `seed() = 0`).
+        self.seeds = None
 
     # -- layout
     @property
@@ -535,8 +539,10 @@ class EncryptorCuda:
         d.upload(w)
         return d
 
-    def _encrypt_zero(self, level, asymmetric, batch, seeds):
-        """Encryptor::encryptZeroInternal  src/encryptor.cpp:88-164"""
+    def _encrypt_zero(self, level, asymmetric, batch, seeds, save_seed=False):
+        """Encryptor::encryptZeroInternal  src/encryptor.cpp:88-164. ``save_seed`` (symmetric only): the seeded form of the
+        reference's CUDA encryptor (src/utils/rlwe_cuda.cu:261-333) - c1 is the cuRAND expansion of a 64-bit seed kept in
+        ``ct.seeds``, so that the ciphertext travels as c0 + seed."""
         ctx = self.context
         key = self.pk if asymmetric else self.sk
         if key is None:
@@ -545,6 +551,12 @@ class EncryptorCuda:
             raise TroyInvalidArgument("parms_id is not valid for encryption parameters")
         d_seeds = self._seeds(seeds, batch)
         ct = CiphertextCuda(ctx, level, 2, ctx.scheme == CKKS, 1.0, 1, batch=batch, stream=self.stream)
+        if save_seed and not asymmetric:
+            d_ct_seeds = ctx.alloc(batch, self.stream)
+            _L().call("troyb_encrypt_zero_symmetric_seeded", _vp(ctx.h), level, _vp(key.ptr), _vp(d_seeds.ptr), _vp(ct.data.ptr),
+                      ct.stride, _vp(d_ct_seeds.ptr), batch, _vp(self.stream))
+            ct.seeds = d_ct_seeds.download()
+            return ct
         name = "troyb_encrypt_zero_asymmetric" if asymmetric else "troyb_encrypt_zero_symmetric"
         _L().call(name, _vp(ctx.h), level, _vp(key.ptr), _vp(d_seeds.ptr), _vp(ct.data.ptr), ct.stride, batch, _vp(self.stream))
         return ct
@@ -552,17 +564,17 @@ class EncryptorCuda:
     def encrypt_zero(self, parms_id=0, batch=1, seeds=None):
         return self._encrypt_zero(parms_id, True, batch, seeds)
 
-    def encrypt_zero_symmetric(self, parms_id=0, batch=1, seeds=None):
-        return self._encrypt_zero(parms_id, False, batch, seeds)
+    def encrypt_zero_symmetric(self, parms_id=0, batch=1, seeds=None, save_seed=False):
+        return self._encrypt_zero(parms_id, False, batch, seeds, save_seed)
 
-    def _encrypt(self, plain, asymmetric, seeds):
+    def _encrypt(self, plain, asymmetric, seeds, save_seed=False):
         """Encryptor::encryptInternal  src/encryptor.cpp:166-253: encryption of zero, then the plaintext goes into c0."""
         ctx, scheme = self.context, self.context.scheme
         batch = plain.batch
         if scheme == CKKS:
             if not plain.is_ntt_form:
                 raise TroyInvalidArgument("plain must be in NTT form")
-            ct = self._encrypt_zero(plain.parms_id, asymmetric, batch, seeds)
+            ct = self._encrypt_zero(plain.parms_id, asymmetric, batch, seeds, save_seed)
             for b in range(batch):  # addPolyCoeffmod on c0
                 _L().call("troyb_add", _vp(ctx.h), ct.parms_id, _vp(ct.ptr(0, b)), _vp(plain.data.at(b * plain.coeff_count)),
                           _vp(ct.ptr(0, b)), 1, _vp(self.stream))
@@ -570,7 +582,7 @@ class EncryptorCuda:
             return ct
         if plain.is_ntt_form:
             raise TroyInvalidArgument("plain cannot be in NTT form")
-        ct = self._encrypt_zero(0, asymmetric, batch, seeds)
+        ct = self._encrypt_zero(0, asymmetric, batch, seeds, save_seed)
         # BFV: multiplyAddPlainWithScalingVariant; BGV: addPlainWithoutScalingVariant (correction factor 1)
         _L().call("troyb_add_plain", _vp(ctx.h), 0, _vp(ct.ptr()), ct.stride, _vp(plain.data.ptr), plain.coeff_count,
                   plain.stride, C.c_uint64(1), 0, batch, _vp(self.stream))
@@ -579,8 +591,8 @@ class EncryptorCuda:
     def encrypt(self, plain, seeds=None):
         return self._encrypt(plain, True, seeds)
 
-    def encrypt_symmetric(self, plain, seeds=None):
-        return self._encrypt(plain, False, seeds)
+    def encrypt_symmetric(self, plain, seeds=None, save_seed=False):
+        return self._encrypt(plain, False, seeds, save_seed)
 
 
 def _balance_correction_factors(f1, f2, t):
@@ -641,6 +653,8 @@ class EvaluatorCuda:
         different stream is waited for first (an event-free, conservative hand-over: streams that stay with one evaluator
         never synchronise), and from here on it is copied, grown and released in the order of this stream."""
         for o in objs:
+            if isinstance(o, CiphertextCuda):
+                o.seeds = None
             d = getattr(o, "data", None)
             if isinstance(d, DeviceArray) and d.stream is not self.stream:
                 if d.stream != self.stream:

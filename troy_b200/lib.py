@@ -83,6 +83,8 @@ _SIGNATURES = {
     "troyb_sample_poly_uniform": (C.c_int, [_vp, C.c_int, _vp, _sz, _sz, _vp, _sz, _vp, _sz, _sz, _vp]),
     "troyb_encrypt_zero_asymmetric": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _sz, _sz, _vp]),
     "troyb_encrypt_zero_symmetric": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _sz, _sz, _vp]),
+    "troyb_encrypt_zero_symmetric_seeded": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
+    "troyb_expand_seeded_poly": (C.c_int, [_vp, C.c_int, _vp, _vp, _sz, _sz, _vp]),
     "troyb_relinearize": (C.c_int, [_vp, C.c_int, _vp, _sz, _vp, _sz, _vp]),
     "troyb_galois_permute": (C.c_int, [_vp, C.c_int, _vp, _vp, _sz, C.c_uint32, C.c_int, _vp]),
     "troyb_galois_elt_from_step": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_uint32)]),

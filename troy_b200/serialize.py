@@ -8,9 +8,9 @@ Formats (all little-endian raw members, no compression; `savet` = raw bytes of t
   KSwitchKeysCuda::save   src/kswitchkeys_cuda.cuh:330-339 parms_id[32] n[8] { m[8] { CiphertextCuda::save x m } } x n
 A parms_id is the BLAKE2b-256 hash of {scheme, N, coeff moduli of the level, plain modulus} as 64-bit words
 (EncryptionParameters::computeParmsID, src/encryptionparams.cpp:118-156); this package names levels by index, so the hash
-is computed on save and looked up on load. Seeded (seed != 0) and termed ciphertexts are the reference's compressed
-transport forms of FRESH encryptions (they need its cuRAND sampler) and are rejected on load, like CiphertextCuda::load(stream)
-without a context does for seeds.
+is computed on save and looked up on load. A seeded ciphertext (seed != 0: a fresh symmetric encryption) travels as c0 + seed;
+its c1 is re-expanded on load with the reference's cuRAND sampler semantics (CiphertextCuda::load(stream, context),
+src/ciphertext_cuda.cu:141-192; troyb_expand_seeded_poly). Termed ciphertexts are rejected here as CiphertextCuda::load does.
 """
 import hashlib
 import struct
@@ -45,9 +45,10 @@ def _read(stream, fmt):
     return struct.unpack(fmt, raw)
 
 
-def _save_ct_words(stream, pid, is_ntt, size, n, limbs, scale, correction_factor, words):
+def _save_ct_words(stream, pid, is_ntt, size, n, limbs, scale, correction_factor, words, seed=0):
     stream.write(pid)
-    stream.write(struct.pack("<?QQQdQQ?Q", bool(is_ntt), size, n, limbs, float(scale), int(correction_factor), 0, False, words.size))
+    stream.write(struct.pack("<?QQQdQQ?Q", bool(is_ntt), size, n, limbs, float(scale), int(correction_factor), int(seed), False,
+                             words.size))
     stream.write(np.ascontiguousarray(words, dtype=np.uint64).tobytes())
 
 
@@ -56,28 +57,49 @@ def _load_ct_words(stream):
     is_ntt, size, n, limbs, scale, cf, seed, terms, data_size = _read(stream, "<?QQQdQQ?Q")
     if terms:
         raise TroyInvalidArgument("Trying to load a termed ciphertext, but indices is not specified")
-    if seed != 0:
-        raise TroyInvalidArgument("seed is not zero.")
+    if seed != 0 and size > 2:
+        raise TroyInvalidArgument("Seed exists but size is not 2.")
+    stored = (1 if seed != 0 else size) * n * limbs
     words = np.frombuffer(stream.read(8 * data_size), dtype=np.uint64)
-    if words.size != data_size or data_size < size * n * limbs:
+    if words.size != data_size or data_size < stored:
         raise TroyInvalidArgument("unexpected end of stream")
-    return pid, is_ntt, size, n, limbs, scale, cf, words[: size * n * limbs]
+    return pid, is_ntt, size, n, limbs, scale, cf, words[:stored], seed
 
 
 def save_ciphertext(ct, stream, batch_index=0):
     """CiphertextCuda::save of one ciphertext of a batch."""
     words = ct.to_host()[batch_index]
+    seed = 0 if ct.seeds is None else int(ct.seeds[batch_index])
+    if seed != 0 and ct.size > 2:
+        raise TroyInvalidArgument("Seed exists but size is not 2.")
+    if seed != 0:
+        words = words[:1]  # c0 only; c1 is the expansion of the seed
     _save_ct_words(stream, parms_id(ct.context, ct.parms_id), ct.is_ntt_form, ct.size, ct.context.n, ct.limbs, ct.scale,
-                   ct.correction_factor, words.reshape(-1))
+                   ct.correction_factor, words.reshape(-1), seed)
 
 
 def load_ciphertext(context, stream):
-    """CiphertextCuda::load."""
-    pid, is_ntt, size, n, limbs, scale, cf, words = _load_ct_words(stream)
+    """CiphertextCuda::load(stream, context)  src/ciphertext_cuda.cu:141-192."""
+    import ctypes as C
+    from .host import _L, _vp
+    pid, is_ntt, size, n, limbs, scale, cf, words, seed = _load_ct_words(stream)
     level = _level_of(context, pid)
     if n != context.n or limbs != context.level_limbs(level):
         raise TroyInvalidArgument("encrypted is not valid for encryption parameters")
-    return CiphertextCuda.from_host(context, words.reshape(size, limbs, n), level, is_ntt, scale, cf)
+    if seed == 0:
+        return CiphertextCuda.from_host(context, words.reshape(size, limbs, n), level, is_ntt, scale, cf)
+    ct = CiphertextCuda(context, level, 2, is_ntt, scale, cf)
+    ct.data.upload(words)
+    d_seed = context.alloc(1)
+    d_seed.upload(np.array([seed], dtype=np.uint64))
+    _L().call("troyb_expand_seeded_poly", _vp(context.h), level, _vp(d_seed.ptr), _vp(ct.ptr(1)), ct.poly_words, 1, _vp(None))
+    if context.scheme != CKKS:  # coefficient-form schemes (the reference's loader inverts for BFV only, src/ciphertext_cuda.cu:187-189,
+        # which leaves its own BGV seeded ciphertexts undecryptable; that slip is not reproduced)
+        name = "troyb_ntt_inverse_key" if level == SEALContextCuda.KEY_LEVEL else "troyb_ntt_inverse"
+        args = (_vp(context.h),) + (() if level == SEALContextCuda.KEY_LEVEL else (level,))
+        _L().call(name, *args, _vp(ct.ptr(1)), 1, _vp(None))
+    _L().call("troyb_stream_synchronize", _vp(None))
+    return ct
 
 
 def save_plaintext(pt, stream, batch_index=0):
@@ -134,7 +156,7 @@ def load_kswitch_keys(context, stream, cls=KSwitchKeysCuda):
             continue
         rows = []
         for _ in range(digits):
-            dpid, is_ntt, size, n, limbs, _, _, words = _load_ct_words(stream)
+            dpid, is_ntt, size, n, limbs, _, _, words, _ = _load_ct_words(stream)
             if dpid != pid or size != 2 or not is_ntt:
                 raise TroyInvalidArgument("kswitch_keys is not valid for encryption parameters")
             rows.append(words.reshape(2, limbs, n))
