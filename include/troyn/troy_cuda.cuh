@@ -5,9 +5,9 @@
 // the same namespaces, same method names, argument meaning and exception types) and links libtroy_b200.so plus the
 // reference's own host (CPU) classes, which this header reuses exactly where the reference's CUDA classes do:
 //   * KeyGeneratorCuda wraps the host KeyGenerator          (reference: src/keygenerator_cuda.cuh:36-60)
-//   * encoders, encryption, decryption and plaintexts are host work that is out of the hot path:
-//     they delegate to the host classes and move words over the C ABI's copy calls.
-// Everything arithmetic on ciphertexts (Evaluator) runs in the CUDA library; nothing here computes on the CPU.
+//   * encoders and plaintexts are host work that is out of the hot path: they delegate to the
+//     host classes and move words over the C ABI's copy calls.
+// Everything arithmetic on ciphertexts (Evaluator, Encryptor, Decryptor) runs in the CUDA library; nothing here computes on the CPU.
 //
 // Needs the reference's host headers on the include path (-I<troy>/src). Header-only; C++17; no CUDA headers needed.
 //
@@ -217,11 +217,17 @@ class PublicKeyCuda : public PublicKey {
 public:
     PublicKeyCuda() = default;
     PublicKeyCuda(const PublicKey &k) : PublicKey(k) {}
+    // PublicKeyCuda::save / load: the key's ciphertext in CiphertextCuda's format (src/publickey_cuda.cuh, src/ciphertext_cuda.cu:16-43)
+    inline void save(std::ostream &stream) const;
+    inline void load(std::istream &stream);
 };
 class SecretKeyCuda : public SecretKey {
 public:
     SecretKeyCuda() = default;
     SecretKeyCuda(const SecretKey &k) : SecretKey(k) {}
+    // SecretKeyCuda::save / load  src/secretkey_cuda.cuh:292-297: the key's plaintext in PlaintextCuda's format
+    void save(std::ostream &stream) const { PlaintextCuda(data()).save(stream); }
+    void load(std::istream &stream) { PlaintextCuda p; p.load(stream); data() = p; }
 };
 // Encoders are host work in this build: the host classes, constructed from the device context.
 class CKKSEncoderCuda : public CKKSEncoder {
@@ -479,7 +485,9 @@ public:
             const auto &digits = h.data()[idx];
             if (digits.empty()) continue;
             const Ciphertext &first = digits[0].data();
-            const std::size_t per = first.size() * first.polyModulusDegree() * first.coeffModulusSize();
+            n_ = first.polyModulusDegree();
+            limbs_ = first.coeffModulusSize();
+            const std::size_t per = first.size() * n_ * limbs_;
             keys_[idx].allocate(per * digits.size());
             for (std::size_t j = 0; j < digits.size(); j++) keys_[idx].upload(digits[j].data().data(), per, j * per);
         }
@@ -491,9 +499,78 @@ public:
         return keys_[index].get();
     }
     bool hasIndex(std::size_t index) const { return index < keys_.size() && keys_[index].size() != 0; }
+    // KSwitchKeysCuda::save / load  src/kswitchkeys_cuda.cuh:330-353: parms_id, n, then per index m and m key digits, each one
+    // a size-2 NTT-form ciphertext at the key level in CiphertextCuda's format
+    void save(std::ostream &stream) const {
+        stream.write(reinterpret_cast<const char *>(&parms_id_), sizeof(ParmsID));
+        const std::size_t n = keys_.size(), per = 2 * n_ * limbs_;
+        stream.write(reinterpret_cast<const char *>(&n), sizeof(n));
+        std::vector<std::uint64_t> w(per);
+        for (const auto &k : keys_) {
+            const std::size_t m = per ? k.size() / per : 0;
+            stream.write(reinterpret_cast<const char *>(&m), sizeof(m));
+            for (std::size_t j = 0; j < m; j++) {
+                k.download(w.data(), per, j * per);
+                b200::synchronize();
+                const bool ntt = true, terms = false;
+                const std::size_t size = 2;
+                const double scale = 1.0;
+                const std::uint64_t one = 1, zero = 0;
+                stream.write(reinterpret_cast<const char *>(&parms_id_), sizeof(ParmsID));
+                stream.write(reinterpret_cast<const char *>(&ntt), sizeof(bool));
+                stream.write(reinterpret_cast<const char *>(&size), sizeof(size));
+                stream.write(reinterpret_cast<const char *>(&n_), sizeof(n_));
+                stream.write(reinterpret_cast<const char *>(&limbs_), sizeof(limbs_));
+                stream.write(reinterpret_cast<const char *>(&scale), sizeof(scale));
+                stream.write(reinterpret_cast<const char *>(&one), sizeof(one));
+                stream.write(reinterpret_cast<const char *>(&zero), sizeof(zero));
+                stream.write(reinterpret_cast<const char *>(&terms), sizeof(bool));
+                stream.write(reinterpret_cast<const char *>(&per), sizeof(per));
+                stream.write(reinterpret_cast<const char *>(w.data()), per * 8);
+            }
+        }
+    }
+    void load(std::istream &stream) {
+        stream.read(reinterpret_cast<char *>(&parms_id_), sizeof(ParmsID));
+        std::size_t n = 0;
+        stream.read(reinterpret_cast<char *>(&n), sizeof(n));
+        keys_.clear();
+        keys_.resize(n);
+        for (std::size_t i = 0; i < n; i++) {
+            std::size_t m = 0;
+            stream.read(reinterpret_cast<char *>(&m), sizeof(m));
+            std::vector<std::uint64_t> all;
+            for (std::size_t j = 0; j < m; j++) {
+                ParmsID id;
+                bool ntt = false, terms = false;
+                std::size_t size = 0, count = 0;
+                double scale = 1.0;
+                std::uint64_t cf = 1, seed = 0;
+                stream.read(reinterpret_cast<char *>(&id), sizeof(ParmsID));
+                stream.read(reinterpret_cast<char *>(&ntt), sizeof(bool));
+                stream.read(reinterpret_cast<char *>(&size), sizeof(size));
+                stream.read(reinterpret_cast<char *>(&n_), sizeof(n_));
+                stream.read(reinterpret_cast<char *>(&limbs_), sizeof(limbs_));
+                stream.read(reinterpret_cast<char *>(&scale), sizeof(scale));
+                stream.read(reinterpret_cast<char *>(&cf), sizeof(cf));
+                stream.read(reinterpret_cast<char *>(&seed), sizeof(seed));
+                stream.read(reinterpret_cast<char *>(&terms), sizeof(bool));
+                stream.read(reinterpret_cast<char *>(&count), sizeof(count));
+                if (!stream || terms || seed != 0 || size != 2 || count != 2 * n_ * limbs_) throw std::invalid_argument("kswitch_keys data is invalid");
+                all.resize(all.size() + count);
+                stream.read(reinterpret_cast<char *>(all.data() + all.size() - count), count * 8);
+            }
+            if (!all.empty()) {
+                keys_[i].allocate(all.size());
+                keys_[i].upload(all.data(), all.size());
+                b200::synchronize(); // `all` is a host temporary
+            }
+        }
+    }
 
 protected:
     ParmsID parms_id_ = parmsIDZero;
+    std::size_t n_ = 0, limbs_ = 0;
     std::vector<b200::DeviceWords> keys_;
 };
 
@@ -1033,6 +1110,9 @@ private:
 
     SEALContextCuda context_;
 };
+
+inline void PublicKeyCuda::save(std::ostream &stream) const { CiphertextCuda(data()).save(stream); }
+inline void PublicKeyCuda::load(std::istream &stream) { CiphertextCuda c; c.load(stream); data() = c.cpu(); }
 
 inline void CiphertextCuda::saveTerms(std::ostream &stream, EvaluatorCuda &evaluator, const std::vector<std::size_t> &term_ids) const {
     CiphertextCuda copy = *this;
