@@ -468,6 +468,30 @@ def run_ours(args):
     mm_terms = MB_ * MI_ * MJ_
     mm_bytes = (MB_ * MI_ * 2 + MI_ * MJ_ + MB_ * MJ_ * 2) * L * N * 8  # every operand word once
 
+    # ---- encryption on the device: encrypt-zero of B ciphertexts at the first level, public-key and
+    # secret-key, one Blake2xb generator per ciphertext (synthetic key words and seeds; parity is the tests' business)
+    enc_pk = uniform((2,), kq)
+    enc_sk = uniform((), kq)
+    enc_seeds = torch.randint(0, 2 ** 62, (B, 8), device=dev, dtype=torch.int64)
+    enc_out = torch.empty(B, 2, L, N, dtype=torch.int64, device=dev)
+
+    def enc_asym():
+        lib.call("troyb_encrypt_zero_asymmetric", C.c_void_p(ctx.h), 0, C.c_void_p(enc_pk.data_ptr()), C.c_void_p(enc_seeds.data_ptr()),
+                 C.c_void_p(enc_out.data_ptr()), 2 * L * N, B, C.c_void_p(stream))
+
+    def enc_sym():
+        lib.call("troyb_encrypt_zero_symmetric", C.c_void_p(ctx.h), 0, C.c_void_p(enc_sk.data_ptr()), C.c_void_p(enc_seeds.data_ptr()),
+                 C.c_void_p(enc_out.data_ptr()), 2 * L * N, B, C.c_void_p(stream))
+
+    for _ in range(3):
+        enc_asym()
+        enc_sym()
+    t_enc_a = timed(enc_asym, extra_steps)
+    t_enc_s = timed(enc_sym, extra_steps)
+    encrypt = {"encrypt_zero_per_s": world * B * extra_steps / t_enc_a, "encrypt_zero_symmetric_per_s": world * B * extra_steps / t_enc_s,
+               "what": f"Encryptor::encryptZero / encryptZeroSymmetric at the first level on the device, batch {B}, words identical to the "
+                       "reference CPU encryptor's for the same seeds (reference CPU, one thread: 72 / 134 per s, profiles/r2_encrypt_bench.jsonl)"}
+
     # ---- per-kernel device time of one step (CUDA events around every launch) for the roofline of the dominant kernel
     lib.call("troyb_profile_enable", 1)
     step()
@@ -638,6 +662,7 @@ def run_ours(args):
                    "shape": f"{MB_}x{MI_} ciphertexts times {MI_}x{MJ_} plaintexts, one launch",
                    "gbs": mm_bytes * extra_steps / t_mm / 1e9, "frac_of_hbm_roofline": mm_bytes * extra_steps / t_mm / 1e9 / hbm_peak},
         "ntt_sweep": ntt_sweep,
+        "encrypt": encrypt,
         "digit_sharded": digit_sharded,
         "latency": latency,
         "reference_cuda_path": ref_cuda,
