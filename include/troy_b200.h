@@ -124,8 +124,9 @@ int troyb_switch_key(troyb_context *ctx, int level, uint64_t *d_ct, size_t ct_st
  *   partial : prod [batch][2][L+1][N] = sum over digits j in [digit_begin, digit_end) of NTT_i(digit j) * key[j][k][i]
  *             (canonical residues)                                          src/evaluator_cuda.cu:1222-1297
  *   finish  : mod-down of prod by the special prime, ADDED into ct [2][L][N]   src/evaluator_cuda.cu:1299-1376
- *             reduce_first != 0: prod holds the SUM of several GPUs' partial products (each < 2^60, at most 8 of them)
- *             and is first reduced modulo each prime (in place).
+ *             reduce_first != 0: prod holds the SUM of several GPUs' partial products (each < 2^60, at most 8 of them),
+ *             which is reduced modulo each prime on the way (CKKS: the special-prime rows in place, the data rows inside the
+ *             mod-down tail; BFV / BGV: all rows in place).
  * troyb_switch_key == partial over all digits followed by finish. d_key is the whole key; a GPU that holds only its
  * digits passes a pointer offset by -digit_begin digits (only its digits are read). */
 int troyb_switch_key_partial(troyb_context *ctx, int level, const uint64_t *d_target, size_t target_stride, const uint64_t *d_key,

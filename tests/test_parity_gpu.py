@@ -314,3 +314,23 @@ def test_bgv_add_sub_with_different_correction_factors(ref, cuda_lib):
     assert_same(sq, rsq, "BGV add with correction-factor balancing")
     ev.sub_inplace(s2, a); rc.eval(ref.OP_SUB, rs2, ra)
     assert_same(s2, rs2, "BGV sub with correction-factor balancing")
+
+
+@pytest.mark.parametrize("scheme,n,bits", [(2, 16384, [60, 40, 40, 40, 40, 40, 40, 40, 60]), (1, 8192, [60, 40, 40, 60]),
+                                           (3, 32768, [60, 50, 50, 50, 60]), (2, 65536, [60, 50, 50, 50, 60]), (2, 4096, [60, 40, 40, 60])])
+def test_fused_key_switch(ref, cuda_lib, monkeypatch, scheme, n, bits):
+    """TROYB_KS_FUSED=1: mod-up transform, key product and accumulation in ONE kernel (the transformed digits are multiplied by the
+    key in the tile and reduce-added into the accumulators at the L2; D is never allocated, ks_inner_product is not launched).
+    Same flows, same words as the reference; the launch list of a key switch has no inner-product kernel."""
+    import ctypes as C
+    import json
+    from troy_b200.host import _L
+    monkeypatch.setenv("TROYB_KS_FUSED", "1")
+    run_evaluator_flow(ref, cuda_lib, scheme, n, bits, np.random.default_rng(7000 + n + scheme), batch=3)
+    _L().call("troyb_profile_enable", 1)
+    run_evaluator_flow(ref, cuda_lib, scheme, n, bits, np.random.default_rng(7100 + n + scheme))
+    buf = C.create_string_buffer(1 << 16)
+    _L().call("troyb_profile_report", buf, len(buf))
+    _L().call("troyb_profile_enable", 0)
+    names = {json.loads(x)["kernel"] for x in buf.value.decode().splitlines() if x.strip()}
+    assert "ntt_fwd_modup" in names and "ks_inner_product" not in names

@@ -163,7 +163,9 @@ struct ProdLayout {
     static ProdLayout rows(u32 batch, u64 N) { return ProdLayout{2ull * N, N, 2ull * batch * N}; }
 };
 
-void switch_key_partial(Context *ctx, int level, const u64 *target, u64 target_stride, const u64 *key, u32 digit0, u32 nd,
+// Returns true when prod holds UNREDUCED sums of canonical residues (the fused path): the caller reduces them modulo each
+// prime before use (switch_key_finish(reduce_first)).
+bool switch_key_partial(Context *ctx, int level, const u64 *target, u64 target_stride, const u64 *key, u32 digit0, u32 nd,
                         u64 *prod, u32 batch, cudaStream_t s, const ProdLayout *layout = nullptr) {
     if (!ctx->has_special) throw std::logic_error("keyswitching is not supported by the context");
     const u32 L = (u32)ctx->levels[level].L;
@@ -189,9 +191,53 @@ void switch_key_partial(Context *ctx, int level, const u64 *target, u64 target_s
     const u32 chunk = (batch + n_chunks - 1) / n_chunks; // equal chunks
 
     Scratch t_target(ckks ? (size_t)batch * nd * N : 0, s);
+    if (ckks) ntt_plain(ctx, true, dmap, nd, target + (u64)digit0 * N, target_stride, t_target.p, (u64)nd * N, nd, batch, true, s);
+
+#if !defined(TROYB_HOST_EMUL)
+    // Fused mod-up + key inner product (TROYB_KS_FUSED=1, off by default: measured 10 % slower on B200): every
+    // transform multiplies its output by the key's two components and reduce-adds the products into prod at the L2 (bulk
+    // reduce-adds), so D is never allocated and the inner-product kernel is not launched. Needs the standard product layout,
+    // the second-generation transforms, and sums of nd + 2 canonical residues that fit 64 bits. The switch is read per call.
+    const char *fe = getenv("TROYB_KS_FUSED");
+    const bool fused_env = fe && atoi(fe) != 0;
+    if (fused_env && layout == nullptr && use_ntt2() && ctx->logN >= 12) {
+        // every accumulator takes nd + 1 products - canonical, or below 2 p on the FP64 limbs - and the mod-down tail adds one prime
+        bool fits = true;
+        for (u32 i = 0; i < Lp; i++) {
+            const ModDev &md = ctx->h_mods[kmap.idx[i]];
+            const u32 lazy = (md.policy == POLICY_F64 || md.policy == POLICY_F64_SMALL) ? 2 : 1;
+            fits = fits && (unsigned __int128)md.p * (lazy * (nd + 1) + 1) < ((unsigned __int128)1 << 64);
+        }
+        if (fits) {
+            ck(cudaMemsetAsync(prod, 0, (size_t)batch * pl.batch_stride * sizeof(u64), s));
+            NttArgs a{};
+            a.mode = FWD_MODUP;
+            a.map = kmap;
+            a.L = nd;
+            a.digit0 = digit0;
+            a.src = ckks ? t_target.p : target + (u64)digit0 * N;
+            a.src_unit_stride = ckks ? (u64)nd * N : target_stride;
+            a.aux0 = ckks ? target : nullptr;
+            a.aux0_batch_stride = target_stride;
+            a.dst = nullptr;
+            a.scheme = ctx->scheme;
+            a.fused = 1;
+            a.key = key + (u64)digit0 * 2 * key_limbs * N;
+            a.key_digit_stride = 2ull * key_limbs * N;
+            a.key_comp_stride = (u64)key_limbs * N;
+            a.key_special_limb = key_limbs - 1;
+            a.prod = prod;
+            a.prod_batch_stride = pl.batch_stride;
+            a.prod_poly_stride = pl.poly_stride;
+            a.prod_limb_stride = pl.limb_stride;
+            set_order(ctx, a, Lp);
+            run_fwd(ctx, a, batch * Lp * nd, s);
+            return true;
+        }
+    }
+#endif
     Scratch D((size_t)chunk * per_ct_words, s);
 
-    if (ckks) ntt_plain(ctx, true, dmap, nd, target + (u64)digit0 * N, target_stride, t_target.p, (u64)nd * N, nd, batch, true, s);
     for (u32 b0 = 0; b0 < batch; b0 += chunk) {
         const u32 nb = std::min(chunk, batch - b0);
         const u64 *tgt = target + (u64)b0 * target_stride;
@@ -272,6 +318,7 @@ void switch_key_partial(Context *ctx, int level, const u64 *target, u64 target_s
             ck(launch_cta(k, grid_for(k.total, KsInnerProduct::kThreads), 0, s));
         }
     }
+    return false;
 }
 
 // The second half of a key switch in three phases, each over a range of rows (output moduli) so that GPUs that own
@@ -372,7 +419,22 @@ void switch_key_finish(Context *ctx, int level, u64 *ct, u64 ct_stride, u64 *pro
     const u32 L = (u32)ctx->levels[level].L;
     const ProdLayout pl = ProdLayout::standard(L + 1, ctx->N);
     Scratch sp((size_t)batch * 2 * ctx->N, s);
-    if (reduce_first) switch_key_reduce_rows(ctx, level, prod, pl, 0, L + 1, batch, s);
+    if (reduce_first) {
+        if (ctx->scheme == SCHEME_CKKS) {
+            // the mod-down tail takes unreduced accumulators as they are (FwdStore::finish); only the special-prime rows, which
+            // feed an inverse transform, are reduced here
+            EltReduceRow k{};
+            k.logN = ctx->logN;
+            k.mod = ctx->h_mods[ctx->pool_special];
+            k.base = prod;
+            k.unit_stride = pl.poly_stride;
+            k.offset = (u64)L * pl.limb_stride;
+            k.total = (u64)batch * 2 * ctx->N / 2;
+            ck(launch_cta(k, grid_for(k.total, EltReduceRow::kThreads), 0, s));
+        } else {
+            switch_key_reduce_rows(ctx, level, prod, pl, 0, L + 1, batch, s);
+        }
+    }
     switch_key_special(ctx, level, prod, pl, sp.p, batch, s);
     switch_key_moddown(ctx, level, ct, ct_stride, prod, pl, sp.p, 0, L, batch, s, ct_src, ct_src_stride, ct_src_polys);
 }
@@ -382,8 +444,8 @@ void switch_key_impl(Context *ctx, int level, u64 *ct, u64 ct_stride, const u64 
     if (!ctx->has_special) throw std::logic_error("keyswitching is not supported by the context");
     const u32 L = (u32)ctx->levels[level].L;
     Scratch prod((size_t)batch * 2 * (L + 1) * ctx->N, s);
-    switch_key_partial(ctx, level, target, target_stride, key, 0, L, prod.p, batch, s);
-    switch_key_finish(ctx, level, ct, ct_stride, prod.p, false, batch, s, ct_src, ct_src_stride, ct_src_polys);
+    const bool unreduced = switch_key_partial(ctx, level, target, target_stride, key, 0, L, prod.p, batch, s);
+    switch_key_finish(ctx, level, ct, ct_stride, prod.p, unreduced, batch, s, ct_src, ct_src_stride, ct_src_polys);
 }
 
 // Division by the last prime of a base with rounding (the level's last prime, or the special prime at the key level):
@@ -1116,8 +1178,9 @@ int troyb_switch_key_partial(troyb_context *ctx, int level, const uint64_t *d_ta
     check_aligned(d_target, "target");
     check_aligned(d_key, "key");
     check_aligned(d_prod, "prod");
-    switch_key_partial(c, level, d_target, target_stride, d_key, (u32)digit_begin, (u32)(digit_end - digit_begin), d_prod, (u32)batch,
-                       S(stream));
+    if (switch_key_partial(c, level, d_target, target_stride, d_key, (u32)digit_begin, (u32)(digit_end - digit_begin), d_prod, (u32)batch,
+                           S(stream))) // the contract of this entry point is canonical residues
+        switch_key_reduce_rows(c, level, d_prod, ProdLayout::standard(L + 1, c->N), 0, L + 1, (u32)batch, S(stream));
     API_END
 }
 

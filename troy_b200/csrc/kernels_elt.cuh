@@ -52,6 +52,31 @@ struct EltAddSub {
     }
 };
 
+// One row (N words, `offset` into units `unit_stride` words apart) of every unit reduced modulo one prime in place: the
+// special-prime rows of unreduced key products (sums of canonical residues) before their inverse transform.
+struct EltReduceRow {
+    static constexpr int kThreads = kEltThreads;
+    const char *name() const { return "reduce_special_rows"; }
+    int logN;
+    ModDev mod;
+    u64 *base;
+    u64 unit_stride, offset;
+    u64 total; // units * N / 2 (two adjacent words per thread)
+    TB_D void operator()(u32 bid, u64 *) const {
+        TB_PHASE(kThreads, t, {
+            const u64 idx = (u64)bid * kThreads + t;
+            if (idx < total) {
+                const u64 w = idx * 2, unit = w >> logN, c = w & ((u64(1) << logN) - 1);
+                ulonglong2 *ptr = reinterpret_cast<ulonglong2 *>(base + unit * unit_stride + offset + c);
+                ulonglong2 v = *ptr;
+                v.x = barrett64(v.x, mod.p, mod.ratio1);
+                v.y = barrett64(v.y, mod.p, mod.ratio1);
+                *ptr = v;
+            }
+        })
+    }
+};
+
 // ---- ciphertext tensor product ----------------------------------------------------------------------------
 // gDyadicConvolutionCoeffmod / kDyadicSquareCoeffmod  src/kernelutils.cu:89-199 ; ckksMultiply src/evaluator_cuda.cu:384-433
 // out[i] = sum_{j+k=i} a[j]*b[k] mod q, one pass, 128-bit accumulation + one Barrett-128 per output word.

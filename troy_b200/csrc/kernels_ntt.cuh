@@ -72,6 +72,15 @@ struct NttArgs {
     u32 n_rank;         // limb ranks in the launch; consecutive units cycle through them
     u32 pf_ahead;       // L2 prefetch distance in CTAs (0 = off): CTA b asks the L2 for the source tile of CTA b + pf_ahead
     unsigned long long *dbg; // development builds (-DTROYB_DEV_TIMELINE, TROYB_TIMELINE=file): thread 0 of every CTA records globaltimer at its phase boundaries
+    // --- fused mod-up + key inner product (second-generation kernels only): instead of storing the transformed digit, the CTA
+    // multiplies it by the key's two components and reduce-adds the products into the accumulators (TMA reduce, u64 sums of
+    // canonical residues; the caller zeroes the accumulators first and reduces them modulo each prime afterwards)
+    int fused;
+    const u64 *key;       // key + digit0 digits: [digit][2][key_limbs][N]
+    u64 key_digit_stride, key_comp_stride;
+    u32 key_special_limb; // key limb of the special prime (launch limb L_full)
+    u64 *prod;            // accumulators [batch][2][L_full + 1][N] (strides below)
+    u64 prod_batch_stride, prod_poly_stride, prod_limb_stride;
     int solo;           // forward, limb = 2 tiles: independent CTAs that both recompute layer 0 (FwdSoloLd). Launched without a
                         // cluster when the transform is out of place; in place, as a cluster of two whose only exchange is one
                         // split barrier "my loads are done" before anybody stores (run_fwd)
@@ -151,6 +160,9 @@ struct NttUnit {
     u64 *ct;          // ciphertext row (written)
     const u64 *ct_in; // the row added to the result (ct itself, a row of NttArgs::ct_src, or null for zero)
     DropLimb dl;
+    const u64 *key0;  // fused MODUP: row of key component 0 for (digit, output modulus); component 1 is key_comp_stride further
+    u64 *prod0;       // fused MODUP: accumulator row of component 0 for (batch element, output modulus)
+    const u64 *pass;  // fused MODUP, pass-through unit: the NTT-form limb that stands in for the transform's output
     bool passthrough; // MODUP with i == j in CKKS: copy the NTT-form limb
     bool reduce_src;  // MODUP: the digit must be reduced mod q_i before the transform
     u32 row;          // four-step row
@@ -191,6 +203,12 @@ template <int LOGT> TB_D NttUnit resolve_unit(const NttArgs &a, u32 bid) {
         u.src = a.src + (u64)b * a.src_unit_stride + (u64)j * N;
         u.dst = a.dst + (u64)u.unit * N;
         if (a.aux0 != nullptr && i == j + a.digit0) u.passthrough = true; // the inner product reads the NTT-form limb in place
+        if (a.fused) {
+            const u32 key_limb = (i + 1 == a.n_rank) ? a.key_special_limb : i;
+            u.key0 = a.key + (u64)j * a.key_digit_stride + (u64)key_limb * N;
+            u.prod0 = a.prod + (u64)b * a.prod_batch_stride + (u64)i * a.prod_limb_stride;
+            u.pass = u.passthrough ? a.aux0 + (u64)b * a.aux0_batch_stride + (u64)i * N : nullptr;
+        }
         // a digit whose own modulus is below 4 q_i is already a valid lazy input of the forward transform (every
         // butterfly policy accepts [0, 4p)): its Barrett reduction mod q_i is skipped (results are canonical either way)
         u.reduce_src = (a.mods[a.map.idx[j + a.digit0]].p >> 2) >= u.md->p;
@@ -321,7 +339,9 @@ struct FwdStore {
         }
         return r;
     }
-    TB_D u64 finish(u64 acc, u64 v) const { return shoup(submod(acc, v, p), u.dl.inv_last, u.dl.inv_last_shoup, p); }
+    // (acc - v) * q_last^-1: the Shoup multiply takes any 64-bit operand, so acc may be an unreduced sum of canonical residues
+    // (fused key products, sums over GPUs) as long as acc + p fits 64 bits
+    TB_D u64 finish(u64 acc, u64 v) const { return shoup(acc + p - v, u.dl.inv_last, u.dl.inv_last_shoup, p); }
     TB_D void operator()(u32 i, u64 v, const Pre &q) const {
         if (mode == FWD_MODDOWN) {
             u64 r = finish(q.acc, v);

@@ -53,6 +53,83 @@ TB_D void block_copy_out(const u64 *sm, u32 base, u32 lane, const FwdStore2 &st)
     }
 }
 
+// Fused mod-up + key inner product (NttArgs::fused): the warp multiplies its finished block (canonical residues x of digit j
+// under output modulus i, still in the tile) by the key's two components and ADDS the products to the accumulators of (batch
+// element, output modulus i) with bulk reduce-adds (cp.reduce.async.bulk ... .add.u64: 64-bit integer adds performed at the
+// L2; the sums of the digits of one key switch stay below 2^64 and are reduced by the consumers). The block is handled in two
+// halves of 512 coefficients: row by row (64 coefficients) the lanes read x from the tile's swizzle, form y0 = x k0 and
+// y1 = x k1, put y0 back into the row in LINEAR order and keep y1 in registers; one 4 KiB reduce-add sends the half's y0, and
+// once the unit has read it the same half takes y1 and a second reduce-add. A pass-through unit (CKKS, digit i under modulus
+// i) takes x from the NTT-form target instead of the tile. Key operands are requested four rows ahead.
+// F64: the limb's prime is below 2^46 and the products are formed on the FP64 pipe.
+struct FusedKey {
+    const u64 *key0, *key1; // rows of the two key components, at the tile's first coefficient
+    u64 *prod0, *prod1;     // accumulator rows of the two components, at the tile's first coefficient
+    const u64 *pass;        // pass-through source row at the tile's first coefficient, or null
+    const ModDev *md;
+};
+template <bool F64> TB_D void block_key_product(u64 *sm, u32 base, u32 lane, const FusedKey &f) {
+    const u32 g = 2u * lane, a0 = base + (g ^ (((g >> 4) & 3u) << 1)), a1 = a0 ^ 8u; // as block_copy_out
+    const ModDev *md = f.md;
+    const u64 p = md->p, mu = md->bar_mu;
+    const u32 sh = md->bar_shift;
+    typedef ArithF64T<true> AF;
+    const AF::Mod m = AF::make(md);
+    const double lift = AF::kTwo52 + m.p; // r + p as the low bits of r + p + 2^52: a residue in (0, 2p), one instruction
+    auto mul = [&](u64 x, u64 k) -> u64 {
+        if constexpr (F64) {
+            const double r = AF::mulmod(AF::from_u64(x, m), AF::mk_tw(AF::from_u64(k, m), 0.0), m); // |r| < p
+            return (u64)__double_as_longlong(__dadd_rn(r, lift)) & 0x000FFFFFFFFFFFFFull;
+        } else {
+            return reduce_sum(x * k, mulhi64(x, k), p, mu, sh); // canonical
+        }
+    };
+#pragma unroll 1
+    for (u32 h = 0; h < 2; h++) {
+        ulonglong2 y1[8];
+#pragma unroll
+        for (int q4 = 0; q4 < 8; q4 += 4) {
+            ulonglong2 ka[4], kb[4], xs[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const u32 i = base + g + 64u * (8u * h + (u32)(q4 + k));
+                ka[k] = __ldg(reinterpret_cast<const ulonglong2 *>(f.key0 + i));
+                kb[k] = __ldg(reinterpret_cast<const ulonglong2 *>(f.key1 + i));
+                if (f.pass) xs[k] = *reinterpret_cast<const ulonglong2 *>(f.pass + i);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const u32 kk = 8u * h + (u32)(q4 + k), addr = ((kk & 1) ? a1 : a0) + 64u * kk;
+                u64 xa, xb;
+                if (f.pass) { xa = xs[k].x; xb = xs[k].y; }
+                else lds128(sm, addr, xa, xb);
+                ulonglong2 y0;
+                y0.x = mul(xa, ka[k].x); y0.y = mul(xb, ka[k].y);
+                y1[q4 + k].x = mul(xa, kb[k].x); y1[q4 + k].y = mul(xb, kb[k].y);
+                __syncwarp(); // every lane has read its part of row kk
+                *reinterpret_cast<ulonglong2 *>(sm + base + 64u * kk + g) = y0;
+            }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            bulk_reduce_add_u64(f.prod0 + base + 512u * h, sm + base + 512u * h, 4096u);
+            bulk_commit();
+            bulk_wait_read<0>(); // the half is free again once the unit has read it
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; k++) *reinterpret_cast<ulonglong2 *>(sm + base + 64u * (8u * h + (u32)k) + g) = y1[k];
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            bulk_reduce_add_u64(f.prod1 + base + 512u * h, sm + base + 512u * h, 4096u);
+            bulk_commit();
+        }
+    }
+    if (lane == 0) bulk_wait_read<0>(); // the tile must outlive the unit's reads
+}
+
 template <int LOGT> struct NttFwdTile2 {
     static constexpr int kThreads = LimbPlan<LOGT, 0>::NT;
     static constexpr int kMinCtas = LOGT == 13 ? 3 : 6;
@@ -113,7 +190,9 @@ template <int LOGT> struct NttFwdTile2 {
         })
         // this tile's outputs are coefficients [off, off + T) of the limb's (bit-reversed) output
         const u64 off = (u64)rank << LOGT;
-        if (a.mode != FWD_MODDOWN) {
+        if (a.mode == FWD_MODUP && a.fused) {
+            fused_tail(u, sm, off, warp, lane, pol);
+        } else if (a.mode != FWD_MODDOWN) {
             // plain store: the block leaves through the tensor-map unit (the residues were written by this warp's lanes)
             fence_proxy_async();
             __syncwarp();
@@ -139,9 +218,22 @@ template <int LOGT> struct NttFwdTile2 {
 #endif
     }
 
+    // Fused mod-up: key products of this warp's block into the accumulators (block_key_product).
+    TB_D void fused_tail(const NttUnit &u, u64 *sm, u64 off, u32 warp, u32 lane, int pol) const {
+        const FusedKey f{u.key0 + off, u.key0 + a.key_comp_stride + off, u.prod0 + off, u.prod0 + a.prod_poly_stride + off,
+                         u.pass ? u.pass + off : nullptr, u.md};
+        if (pol == POLICY_F64 || pol == POLICY_F64_SMALL) block_key_product<true>(sm, warp << 10, lane, f);
+        else block_key_product<false>(sm, warp << 10, lane, f);
+    }
+
     template <int S> TB_D void stage(u32 bid, u32 grid, u32 rank, u32 nranks, u64 *sm, const Peers &peers) const {
         NttUnit u = resolve_unit<LOGT>(a, bid);
-        if (u.passthrough) return; // digit already in NTT form under this modulus: the inner product reads it in place
+        if (u.passthrough) {
+            // digit already in NTT form under this modulus: unfused, the inner product reads it in place; fused, its key
+            // products are formed here from the NTT-form limb (no transform, no barriers: every CTA of the cluster takes this path)
+            if (a.fused) fused_tail(u, sm, (u64)rank << LOGT, threadIdx.x >> 5, threadIdx.x & 31u, u.md->policy);
+            return;
+        }
         if constexpr (LOGT == 12) {
             run<0>(u, bid, grid, rank, sm, peers);
         } else {

@@ -87,6 +87,17 @@ TB_D void tma_store_rows(const CUtensorMap *tm, u32 row, const void *src) {
 TB_D void tma_store_commit_and_wait_read() {
     asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+// The same box as tma_store_rows, ADDED (64-bit integer add, performed at the L2) into global memory instead of stored.
+TB_D void tma_reduce_add_rows(const CUtensorMap *tm, u32 row, const void *src) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(tm), "r"(0), "r"(row), "r"(smem_u32(src)) : "memory");
+}
+// `bytes` (a multiple of 16) of consecutive 64-bit words at src (shared memory, linear) added into dst (global memory)
+TB_D void bulk_reduce_add_u64(u64 *dst, const void *src, u32 bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u64 [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+TB_D void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int PENDING> TB_D void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory"); }
 // orders this thread's shared-memory writes before later accesses of the asynchronous proxy (TMA store)
 TB_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -13,9 +13,12 @@ static bool fwd_maps(NttArgs &a, int logN) {
     const u64 *src = a.mode == FWD_MODDOWN ? a.aux1 : a.src;
     if (!rows_ok({N, a.src_unit_stride, a.dst_batch_stride, a.dst_poly_stride, (u64)(uintptr_t)src >> 3, (u64)(uintptr_t)a.dst >> 3})) return false;
     a.tm_src_base = src;
-    a.tm_dst_base = a.dst;
+    a.tm_dst_base = a.fused ? a.prod : a.dst; // fused mod-up: no stores through the map (bulk reduce-adds into prod instead)
+    if (a.fused && !rows_ok({a.prod_batch_stride, a.prod_poly_stride, a.prod_limb_stride, a.key_digit_stride, a.key_comp_stride,
+                             (u64)(uintptr_t)a.prod >> 3, (u64)(uintptr_t)a.key >> 3, a.aux0_batch_stride, (u64)(uintptr_t)a.aux0 >> 3}))
+        return false;
     if (make_rows_map(&a.tm_src, src, stage_box_rows(logN)) != cudaSuccess) return false;
-    if (a.mode != FWD_MODDOWN && make_rows_map(&a.tm_dst, a.dst, 64) != cudaSuccess) return false;
+    if (a.mode != FWD_MODDOWN && make_rows_map(&a.tm_dst, a.tm_dst_base, 64) != cudaSuccess) return false;
     return true;
 }
 #endif
@@ -62,6 +65,7 @@ cudaError_t launch_ntt_fwd(const Context *ctx, NttArgs a, u32 units, cudaStream_
         const u32 c2 = 1u << (logN - 13);
         return launch_cluster(NttFwdTile2<13>{a}, units * c2, c2, tile_smem2(13), s);
     }
+    if (a.fused) return cudaErrorNotSupported; // the caller checks fused_modup_possible() first
 #endif
     const u32 c = tiles_per_limb(logN);
     if (tile_log(logN) == 12) return launch_cluster(NttFwdTile<12>{a}, units * c, c, tile_smem(12), s);
