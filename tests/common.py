@@ -299,7 +299,7 @@ def run_sampler_flow(ref, tb, scheme, n, bits, rng):
 
         nbytes = ((L * n * 8 + 8192 + 4095) // 4096) * 4096
         d_seed, st = _expand_stream(tb, seed, nbytes)
-        for which, start in ((0, 0), (0, 4 * n + 8), (1, 64), (1, 4 * n), (2, 0)):
+        for which, start in ((0, 0), (0, 4 * n + 8), (1, 64), (1, 4 * n), (1, 4 * n + 6), (2, 0)):
             want, pos = rc.sample_poly(level, which, seed, start)
             assert np.array_equal(call(which, st, nbytes, nbytes, _vp(d_seed.ptr), start), want), f"sampler {which} level {level}"
             if which == 0:

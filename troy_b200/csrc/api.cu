@@ -1421,7 +1421,8 @@ PrngView make_view(const u64 *d_stream, u64 bytes, const u64 *d_seeds) {
 void sample_small(Context *c, const LevelBase &lb, const PrngView &view, u64 view_stride, u64 seed_stride, u64 start_bytes,
                   u32 n_tern, u32 n_cbd, u64 *d_out, u64 out_stride, u64 *d_end, u32 batch, cudaStream_t s) {
     const u32 N = (u32)c->N, nseg = (N + kSampleSeg - 1) / kSampleSeg;
-    if (start_bytes & 3) throw std::invalid_argument("stream position must be a multiple of 4");
+    if (n_tern && (start_bytes & 3)) throw std::invalid_argument("stream position must be a multiple of 4");
+    if (start_bytes & 1) throw std::invalid_argument("stream position must be even");
     Scratch seg(n_tern ? (size_t)batch * (nseg + 2) : 0, s);
     if (n_tern) {
         SampleTernaryScan k{};
@@ -1438,8 +1439,8 @@ void sample_small(Context *c, const LevelBase &lb, const PrngView &view, u64 vie
     e.view = view;
     e.view_stride = view_stride;
     e.seed_stride = seed_stride;
-    e.start_bytes = start_bytes;
-    e.cbd_bytes = start_bytes;
+    e.start_bytes = start_bytes & ~3ull; // ternary draws (multiple of 4 when n_tern)
+    e.cbd_bytes = start_bytes;           // noise draws when there is no ternary polynomial before them
     e.N = N;
     e.nseg = nseg;
     e.n_tern = n_tern;
@@ -1567,8 +1568,7 @@ int troyb_sample_poly_cbd(troyb_context *ctx, int level, const uint64_t *d_strea
     Context *c = C(ctx);
     const LevelBase lb = level_base(c, level);
     check_batch_stride(out_stride, (size_t)lb.L * c->N, "out");
-    if (start_bytes & 1) throw std::invalid_argument("stream position must be even");
-    sample_small(c, lb, make_view(d_stream, stream_bytes, d_seeds), stream_stride, seed_stride, start_bytes & ~3ull, 0, 1, d_out,
+    sample_small(c, lb, make_view(d_stream, stream_bytes, d_seeds), stream_stride, seed_stride, start_bytes, 0, 1, d_out,
                  out_stride, nullptr, (u32)batch, S(stream));
     API_END
 }
