@@ -47,3 +47,34 @@ def test_host_helpers():
     assert RelinKeysCuda.get_index(2) == 0
     with pytest.raises(ValueError):
         RelinKeysCuda.get_index(1)
+
+
+def test_pytroy_module_imports_and_names_follow_the_reference_binder():
+    """binder/pytroy*.so (when built): importable without a GPU, and the classes / methods a script written for the reference's
+    pytroy module uses on the path are there under the same names (binder/binder.cu)."""
+    import glob
+    import sys
+    if not glob.glob(os.path.join(ROOT, "binder", "pytroy*.so")):
+        pytest.skip("binder/pytroy*.so not built")
+    sys.path.insert(0, os.path.join(ROOT, "binder"))
+    import pytroy
+    for cls, methods in {
+        "EncryptionParameters": ["set_poly_modulus_degree", "set_coeff_modulus", "set_plain_modulus"],
+        "CoeffModulus": ["create"], "PlainModulus": ["batching"], "SEALContext": ["first_parms_id", "key_parms_id"],
+        "KeyGenerator": ["secret_key", "create_public_key", "create_relin_keys", "create_galois_keys"],
+        "Encryptor": ["encrypt", "encrypt_symmetric", "encrypt_zero"], "Decryptor": ["decrypt"],
+        "CKKSEncoder": ["encode", "decode", "slot_count"], "BatchEncoder": ["encode", "decode"],
+        "Ciphertext": ["save", "load", "save_terms", "load_terms", "scale", "parms_id", "size"], "Plaintext": ["save", "load"],
+        "RelinKeys": ["save", "load"], "GaloisKeys": ["save", "load"], "PublicKey": ["save", "load"], "SecretKey": ["save", "load"],
+        "Evaluator": ["multiply_inplace", "relinearize_inplace", "rescale_to_next_inplace", "rotate_vector_inplace", "rotate_rows_inplace",
+                      "mod_switch_to_next_inplace", "add_inplace", "sub_inplace", "negate_inplace", "square_inplace", "multiply_plain_inplace",
+                      "add_plain_inplace", "transform_to_ntt_inplace", "transform_from_ntt_inplace", "apply_galois_inplace",
+                      "complex_conjugate_inplace", "rotate_columns_inplace"],
+    }.items():
+        c = getattr(pytroy, cls)
+        for m in methods:
+            assert hasattr(c, m), f"pytroy.{cls}.{m}"
+    parms = pytroy.EncryptionParameters(pytroy.SchemeType.ckks)
+    parms.set_poly_modulus_degree(8192)
+    parms.set_coeff_modulus(pytroy.CoeffModulus.create(8192, [40, 40, 40]))
+    assert parms.poly_modulus_degree() == 8192 and len(parms.coeff_modulus()) == 3
