@@ -690,7 +690,7 @@ def main():
     ap.add_argument("--no-sweep", action="store_true", help="skip the config-2 NTT sweep (development runs)")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the digit-sharded large-N key switch")
     ap.add_argument("--e2e-chunk", type=int, default=16, help="end-to-end arm: ciphertext pairs per chunk")
-    ap.add_argument("--e2e-streams", type=int, default=3, help="end-to-end arm: streams the chunks rotate over")
+    ap.add_argument("--e2e-streams", type=int, default=4, help="end-to-end arm: streams the chunks rotate over")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
