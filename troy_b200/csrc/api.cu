@@ -1524,7 +1524,7 @@ void enc_combine(Context *c, const LevelBase &lb, int op, u32 polys, u32 batch, 
     k.logN = c->logN;
     k.n_limbs = lb.L;
     k.polys = polys;
-    k.total = (u64)batch * polys * lb.L * c->N;
+    k.total = (u64)batch * polys * lb.L * c->N / 2;
     k.mods = c->d_mods;
     k.map = lb.map;
     k.f = f;
@@ -1603,6 +1603,7 @@ int troyb_encrypt_zero_asymmetric(troyb_context *ctx, int level, const uint64_t 
     const u64 pk_poly = (u64)level_limbs(c, -1) * N; // the key's polynomials keep the key level's stride
     check_batch_stride(ct_stride, 2 * (size_t)out_lb.L * N, "ct");
     check_aligned(d_ct, "ct");
+    check_aligned(d_public_key, "public key");
     const u32 B = (u32)batch;
     if (!B) return TROYB_OK;
     // the generator's stream: N ternary draws (4 bytes each, + the rare rejected ones), then 2 x N noise draws of 6 bytes
@@ -1644,6 +1645,7 @@ void encrypt_zero_symmetric(Context *c, int level, const u64 *d_secret_key, cons
     const u64 poly = (u64)lb.L * N;
     check_batch_stride(ct_stride, 2 * (size_t)poly, "ct");
     check_aligned(d_ct, "ct");
+    check_aligned(d_secret_key, "secret key");
     if (!B) return;
     // bootstrap generator: 64 bytes = the seed of the generator that expands c1, then N noise draws of 6 bytes
     const u64 boot_bytes = 64 + 6 * N, bw = buffers_words(boot_bytes);

@@ -486,34 +486,44 @@ struct EncCombine {
     const char *name() const { return "encrypt_zero_combine"; }
     int op, logN;
     u32 n_limbs, polys;
-    u64 total; // batch * polys * n_limbs * N
+    u64 total; // batch * polys * n_limbs * N / 2 (two adjacent coefficients per thread, 128-bit accesses)
     const ModDev *mods;
     LimbMap map;
     u64 f;     // plain modulus (BGV) or 1
     const u64 *x, *y, *z;
     u64 *out;
     u64 x_batch, x_poly, y_batch, y_poly, z_batch, z_poly, out_batch, out_poly;
+    static TB_D ulonglong2 ld2(const u64 *p) { return *reinterpret_cast<const ulonglong2 *>(p); }
     TB_D void operator()(u32 bid, u64 *) const {
         TB_PHASE(kThreads, t, {
-            const u64 idx = (u64)bid * kThreads + t;
-            if (idx < total) {
+            const u64 idx = ((u64)bid * kThreads + t) * 2;
+            if (idx < total * 2) {
                 const u32 ul = (u32)(idx >> logN), unit = ul / n_limbs;
                 const u64 r = ((u64)(ul - unit * n_limbs) << logN) | (idx & ((u64(1) << logN) - 1));
                 const u64 b = unit / polys, j = unit - (u32)b * polys;
                 const ModDev &m = mods[map.idx[(u32)(r >> logN)]];
                 const u64 p = m.p;
                 u64 *po = out + b * out_batch + j * out_poly + r;
-                u64 acc = 0;
-                if (op == 0 || op == 1 || op == 4)
-                    acc = mulmod_barrett(x[b * x_batch + j * x_poly + r], y[b * y_batch + j * y_poly + r], p, m.ratio0, m.ratio1);
-                else acc = *po;
-                if (op != 0) {
-                    u64 e = z[b * z_batch + j * z_poly + r];
-                    if (f != 1) e = mulmod_barrett(e, barrett64(f, p, m.ratio1), p, m.ratio0, m.ratio1);
-                    acc = addmod(acc, e, p);
+                ulonglong2 acc;
+                if (op == 0 || op == 1 || op == 4) {
+                    const ulonglong2 xv = ld2(x + b * x_batch + j * x_poly + r), yv = ld2(y + b * y_batch + j * y_poly + r);
+                    acc.x = mulmod_barrett(xv.x, yv.x, p, m.ratio0, m.ratio1);
+                    acc.y = mulmod_barrett(xv.y, yv.y, p, m.ratio0, m.ratio1);
+                } else {
+                    acc = ld2(po);
                 }
-                if (op == 3 || op == 4) acc = negmod(acc, p);
-                *po = acc;
+                if (op != 0) {
+                    ulonglong2 e = ld2(z + b * z_batch + j * z_poly + r);
+                    if (f != 1) {
+                        const u64 fm = barrett64(f, p, m.ratio1);
+                        e.x = mulmod_barrett(e.x, fm, p, m.ratio0, m.ratio1);
+                        e.y = mulmod_barrett(e.y, fm, p, m.ratio0, m.ratio1);
+                    }
+                    acc.x = addmod(acc.x, e.x, p);
+                    acc.y = addmod(acc.y, e.y, p);
+                }
+                if (op == 3 || op == 4) { acc.x = negmod(acc.x, p); acc.y = negmod(acc.y, p); }
+                *reinterpret_cast<ulonglong2 *>(po) = acc;
             }
         })
     }
