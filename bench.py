@@ -490,7 +490,7 @@ def run_ours(args):
     t_enc_s = timed(enc_sym, extra_steps)
     encrypt = {"encrypt_zero_per_s": world * B * extra_steps / t_enc_a, "encrypt_zero_symmetric_per_s": world * B * extra_steps / t_enc_s,
                "what": f"Encryptor::encryptZero / encryptZeroSymmetric at the first level on the device, batch {B}, words identical to the "
-                       "reference CPU encryptor's for the same seeds (reference CPU, one thread: 72 / 134 per s, profiles/r2_encrypt_bench.jsonl)"}
+                       "reference CPU encryptor's for the same seeds (reference CPU, one thread: 69 / 129 per s, profiles/r2_encrypt_bench.jsonl)"}
 
     # ---- per-kernel device time of one step (CUDA events around every launch) for the roofline of the dominant kernel
     lib.call("troyb_profile_enable", 1)
