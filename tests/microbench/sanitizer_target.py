@@ -23,4 +23,9 @@ run_matmul_flow(ref, tb, 4096, [60, 40, 60], rng, B=3, I=3, J=3)
 for scheme, n, bits in [(2, 16384, [60, 40, 60]), (1, 4096, [60, 40, 40, 60]), (3, 256, [40, 30, 30, 40])]:
     run_encrypt_flow(ref, tb, scheme, n, bits, rng)
 run_sampler_flow(ref, tb, 2, 1024, [60, 40, 40, 60], rng)
+# the fused mod-up + key inner product (bulk reduce-adds from the tile), opt-in
+os.environ["TROYB_KS_FUSED"] = "1"
+for scheme, n, bits in [(2, 16384, [60, 40, 60]), (1, 8192, [60, 40, 40, 60]), (3, 32768, [50, 40, 60])]:
+    run_evaluator_flow(ref, tb, scheme, n, bits, rng, batch=2)
+os.environ["TROYB_KS_FUSED"] = "0"
 print("sanitizer target done")
