@@ -29,6 +29,12 @@ METRIC, UNIT = "ckks_n16384_mult_relin_ops_per_s", "ops/s"
 WORKLOAD = "CKKS N=16384 L=8 {60,40x7,60} scale 2^40: multiply+relinearize on a batch of synthetic ciphertext pairs"
 
 
+def bench_config(world, batch=256):
+    """The `config` object of BOTH arms (the reference arm times a bounded sample of this workload; cpu_baseline.sample says which)."""
+    return {"workload": WORKLOAD, "batch_per_gpu": batch, "parallelism": f"{world} independent ciphertext shards, no collective",
+            "l2": f"inputs {batch * 5 * L * N * 8 >> 20} MiB per step > 126 MiB L2 (no explicit flush)"}
+
+
 def algo_bytes():
     """SURVEY.md §8(d) per-unit algorithmic HBM bytes."""
     return dict(limb_ntt=16 * N, multiply=56 * L * N, keyswitch=8 * N * (2 * L * L + 7 * L),
@@ -147,7 +153,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_step": reps * cores, "l2": "n/a (host)"},
+        "config": bench_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -641,8 +647,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": t_main / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "parallelism": f"{world} independent ciphertext shards, no collective",
-                   "l2": f"inputs {B * 5 * L * N * 8 >> 20} MiB per step > 126 MiB L2 (no explicit flush)"},
+        "config": bench_config(world, B),
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "mult_relin_frac_of_hbm_roofline": value / world * (bytes_["multiply"] + bytes_["keyswitch"]) / 1e9 / hbm_peak,
         "rotate": {"value": world * B * extra_steps / t_rot, "unit": "ops/s",
