@@ -96,3 +96,30 @@ def test_encrypt_emulated(ref, emul_lib, scheme, n, bits):
     """Encryption on the device: same seed, same words as the reference CPU encryptor."""
     from common import run_encrypt_flow
     run_encrypt_flow(ref, emul_lib, scheme, n, bits, np.random.default_rng(720 + scheme + n))
+
+
+def test_encryptor_error_behaviour_emulated(ref, emul_lib):
+    """Encryptor's argument checks (src/encryptor.cpp:88-253): missing keys, levels outside the chain, plaintext form."""
+    from common import make_pair
+    from troy_b200.lib import TroyInvalidArgument, TroyLogicError
+    tb = emul_lib
+    rc, ctx = make_pair(ref, tb, ref.CKKS, 256, [40, 30, 30, 40])
+    rc.keygen()
+    only_pk = tb.EncryptorCuda(ctx, rc.public_key_words(), None)
+    with pytest.raises(TroyLogicError):
+        only_pk.encrypt_zero_symmetric(0)
+    only_sk = tb.EncryptorCuda(ctx, None, rc.secret_key_words())
+    with pytest.raises(TroyLogicError):
+        only_sk.encrypt_zero(0)
+    with pytest.raises(TroyInvalidArgument):
+        only_pk.encrypt_zero(ctx.num_levels)          # parms_id is not valid for encryption parameters
+    with pytest.raises(TroyInvalidArgument):
+        only_pk.encrypt_zero(0, batch=2, seeds=np.zeros(8, dtype=np.uint64))  # one seed per ciphertext
+    with pytest.raises(TroyInvalidArgument):
+        tb.EncryptorCuda(ctx, np.zeros(5, dtype=np.uint64), None)             # key of the wrong size
+    coeff = tb.PlaintextCuda.from_host(ctx, np.arange(16, dtype=np.uint64))   # coefficient form: CKKS wants NTT form
+    with pytest.raises(TroyInvalidArgument):
+        only_pk.encrypt(coeff)
+    # every level of the chain, asymmetric: the limb count follows the level
+    for level in range(ctx.num_levels):
+        assert only_pk.encrypt_zero(level).limbs == ctx.level_limbs(level)
