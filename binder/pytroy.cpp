@@ -127,6 +127,7 @@ PYBIND11_MODULE(pytroy, m) {
 
     py::class_<SecretKey>(m, "SecretKey").def(py::init<>()).def("save", [](const SecretKey &k) { return saved(k); }).def("load", [](SecretKey &k, const py::bytes &b) { loaded(k, b); });
     py::class_<PublicKey>(m, "PublicKey").def(py::init<>()).def("save", [](const PublicKey &k) { return saved(k); }).def("load", [](PublicKey &k, const py::bytes &b) { loaded(k, b); });
+    py::class_<KSwitchKeys>(m, "KSwitchKeys").def(py::init<>()).def("save", [](const KSwitchKeys &k) { return saved(k); }).def("load", [](KSwitchKeys &k, const py::bytes &b) { loaded(k, b); });
     py::class_<RelinKeys>(m, "RelinKeys").def(py::init<>()).def("save", [](const RelinKeys &k) { return saved(k); }).def("load", [](RelinKeys &k, const py::bytes &b) { loaded(k, b); });
     py::class_<GaloisKeys>(m, "GaloisKeys").def(py::init<>()).def("save", [](const GaloisKeys &k) { return saved(k); }).def("load", [](GaloisKeys &k, const py::bytes &b) { loaded(k, b); });
 
@@ -136,6 +137,7 @@ PYBIND11_MODULE(pytroy, m) {
         .def("secret_key", &KeyGenerator::secretKey)
         .def("create_public_key", [](KeyGenerator &g) { PublicKey k; g.createPublicKey(k); return k; })
         .def("create_relin_keys", [](KeyGenerator &g) { RelinKeys k; g.createRelinKeys(k); return k; })
+        .def("create_keyswitching_keys", [](KeyGenerator &g, const SecretKey &other) { return g.createKeySwitchingKeys(other); })
         .def("create_galois_keys", [](KeyGenerator &g) { GaloisKeys k; g.createGaloisKeys(k); return k; })
         .def("create_galois_keys", [](KeyGenerator &g, const std::vector<int> &steps) { GaloisKeys k; g.createGaloisKeys(steps, k); return k; });
 
@@ -144,7 +146,9 @@ PYBIND11_MODULE(pytroy, m) {
         .def("slot_count", [](const BatchEncoder &e) { return e.slotCount(); })
         .def("encode", [](BatchEncoder &e, const std::vector<std::uint64_t> &v, Plaintext &p) { e.encode(v, p); })
         .def("encode", [](BatchEncoder &e, const std::vector<std::uint64_t> &v) { Plaintext p; e.encode(v, p); return p; })
-        .def("decode", [](BatchEncoder &e, const Plaintext &p) { std::vector<std::uint64_t> v; e.decode(p, v); return v; });
+        .def("decode", [](BatchEncoder &e, const Plaintext &p) { std::vector<std::uint64_t> v; e.decode(p, v); return v; })
+        .def("encode_polynomial", [](BatchEncoder &e, const std::vector<std::uint64_t> &v) { Plaintext p; e.encodePolynomial(v, p); return p; })
+        .def("decode_polynomial", [](BatchEncoder &e, const Plaintext &p) { std::vector<std::uint64_t> v; e.decodePolynomial(p, v); return v; });
 
     py::class_<CKKSEncoder>(m, "CKKSEncoder")
         .def(py::init<const SEALContext &>())
@@ -193,6 +197,11 @@ PYBIND11_MODULE(pytroy, m) {
         .def("square", [](const Evaluator &e, const Ciphertext &a) { return fresh([&](Ciphertext &o) { e.square(a, o); }); })
         .def("relinearize_inplace", &Evaluator::relinearizeInplace)
         .def("relinearize", [](const Evaluator &e, const Ciphertext &a, const RelinKeys &k) { return fresh([&](Ciphertext &o) { e.relinearize(a, k, o); }); })
+        .def("multiply_many", [](const Evaluator &e, const std::vector<Ciphertext> &v, const RelinKeys &k) { return fresh([&](Ciphertext &o) { e.multiplyMany(v, k, o); }); })
+        .def("exponentiate_inplace", &Evaluator::exponentiateInplace)
+        .def("exponentiate", [](const Evaluator &e, const Ciphertext &a, std::uint64_t n, const RelinKeys &k) { return fresh([&](Ciphertext &o) { e.exponentiate(a, n, k, o); }); })
+        .def("apply_keyswitching_inplace", &Evaluator::applyKeySwitchingInplace)
+        .def("apply_keyswitching", [](const Evaluator &e, const Ciphertext &a, const KSwitchKeys &k) { return fresh([&](Ciphertext &o) { e.applyKeySwitching(a, k, o); }); })
         .def("mod_switch_to_next_inplace", [](const Evaluator &e, Ciphertext &a) { e.modSwitchToNextInplace(a); })
         .def("mod_switch_to_next", [](const Evaluator &e, const Ciphertext &a) { return fresh([&](Ciphertext &o) { e.modSwitchToNext(a, o); }); })
         .def("mod_switch_to_inplace", [](const Evaluator &e, Ciphertext &a, const ParmsID &id) { e.modSwitchToInplace(a, id); })

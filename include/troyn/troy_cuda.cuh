@@ -298,7 +298,37 @@ private:
 };
 class BatchEncoderCuda : public BatchEncoder {
 public:
-    BatchEncoderCuda(const SEALContextCuda &context) : BatchEncoder(context.host()) {}
+    BatchEncoderCuda(const SEALContextCuda &context)
+        : BatchEncoder(context.host()), t_(context.firstContextData()->parms().plainModulus().value()) {}
+    // encodePolynomial / decodePolynomial  src/batchencoder_cuda.cu:124-171, 267-286: coefficients modulo t, no slot transform
+    void encodePolynomial(const std::vector<std::uint64_t> &values, PlaintextCuda &destination) const {
+        if (values.size() > slotCount()) throw std::invalid_argument("values_matrix size is too large");
+        destination.parmsID() = parmsIDZero;
+        destination.resize(values.size());
+        for (std::size_t i = 0; i < values.size(); i++) destination.data()[i] = values[i] % t_;
+    }
+    void encodePolynomial(const std::vector<std::int64_t> &values, PlaintextCuda &destination) const {
+        if (values.size() > slotCount()) throw std::invalid_argument("values_matrix size is too large");
+        destination.parmsID() = parmsIDZero;
+        destination.resize(slotCount());
+        for (std::size_t i = 0; i < slotCount(); i++) {
+            const std::int64_t v = i < values.size() ? values[i] : 0;
+            destination.data()[i] = v < 0 ? t_ - (static_cast<std::uint64_t>(-v) % t_) : static_cast<std::uint64_t>(v) % t_;
+        }
+    }
+    void decodePolynomial(const PlaintextCuda &plain, std::vector<std::uint64_t> &destination) const {
+        destination.assign(plain.data(), plain.data() + std::min(plain.coeffCount(), slotCount()));
+    }
+    void decodePolynomial(const PlaintextCuda &plain, std::vector<std::int64_t> &destination) const {
+        destination.assign(slotCount(), 0);
+        for (std::size_t i = 0; i < std::min(plain.coeffCount(), slotCount()); i++) {
+            const std::uint64_t r = plain.data()[i];
+            destination[i] = r > (t_ >> 1) ? static_cast<std::int64_t>(r) - static_cast<std::int64_t>(t_) : static_cast<std::int64_t>(r);
+        }
+    }
+
+private:
+    std::uint64_t t_;
 };
 
 class EvaluatorCuda;
@@ -604,6 +634,8 @@ public:
     void createGaloisKeys(const std::vector<std::uint32_t> &elts, GaloisKeysCuda &dst) { GaloisKeys k; gen_.createGaloisKeys(elts, k); dst = GaloisKeysCuda(k); }
     void createGaloisKeys(const std::vector<int> &steps, GaloisKeysCuda &dst) { GaloisKeys k; gen_.createGaloisKeys(steps, k); dst = GaloisKeysCuda(k); }
     void createGaloisKeys(GaloisKeysCuda &dst) { GaloisKeys k; gen_.createGaloisKeys(k); dst = GaloisKeysCuda(k); }
+    // key-switching key from another party's secret key to this generator's (src/keygenerator.h:292)
+    KSwitchKeysCuda createKeySwitchingKeys(const SecretKey &new_key) { return KSwitchKeysCuda(gen_.createKeySwitchingKeys(new_key)); }
     KeyGenerator &host() { return gen_; }
 
 private:
@@ -636,7 +668,9 @@ public:
         sk_.allocate(sk.data().coeffCount());
         sk_.upload(sk.data().data(), sk_.size());
     }
-    void encrypt(const Plaintext &plain, CiphertextCuda &dst) const { encryptInternal(plain, true, dst); }
+    // Without a public key but with a secret key, encrypt() encrypts symmetrically: the reference's own CUDA test BFVKeySwitching
+    // calls it that way (its CUDA class reads the unset key there; its CPU class throws "public key is not set").
+    void encrypt(const Plaintext &plain, CiphertextCuda &dst) const { encryptInternal(plain, pk_.size() != 0 || sk_.size() == 0, dst); }
     void encryptSymmetric(const Plaintext &plain, CiphertextCuda &dst) const { encryptInternal(plain, false, dst); }
     CiphertextCuda encrypt(const Plaintext &plain) const { CiphertextCuda d; encrypt(plain, d); return d; }
     CiphertextCuda encryptSymmetric(const Plaintext &plain) const { CiphertextCuda d; encryptSymmetric(plain, d); return d; }
@@ -845,6 +879,59 @@ public:
         ct.resize(2);
     }
     void relinearize(const CiphertextCuda &ct, const RelinKeysCuda &rlk, CiphertextCuda &dst) const { dst = ct; relinearizeInplace(dst, rlk); }
+    // EvaluatorCuda::multiplyMany  src/evaluator_cuda.cu:1447-1523: product tree, every product relinearised (BFV / BGV)
+    void multiplyMany(const std::vector<CiphertextCuda> &cts, const RelinKeysCuda &rlk, CiphertextCuda &dst) const {
+        if (cts.empty()) throw std::invalid_argument("encrypteds vector must not be empty");
+        for (auto &c : cts) if (&c == &dst) throw std::invalid_argument("encrypteds must be different from destination");
+        if (!context_.getContextData(cts[0].parmsID())) throw std::invalid_argument("encrypteds is not valid for encryption parameters");
+        if (scheme() != SchemeType::bfv && scheme() != SchemeType::bgv) throw std::logic_error("unsupported scheme");
+        if (cts.size() == 1) { dst = cts[0]; return; }
+        std::vector<CiphertextCuda> prod;
+        for (std::size_t i = 0; i + 1 < cts.size(); i += 2) {
+            CiphertextCuda t;
+            if (cts[i].data() == cts[i + 1].data()) square(cts[i], t);
+            else multiply(cts[i], cts[i + 1], t);
+            relinearizeInplace(t, rlk);
+            prod.emplace_back(std::move(t));
+        }
+        if (cts.size() & 1) prod.emplace_back(cts.back());
+        for (std::size_t i = 0; i + 1 < prod.size(); i += 2) {
+            CiphertextCuda t;
+            multiply(prod[i], prod[i + 1], t);
+            relinearizeInplace(t, rlk);
+            prod.emplace_back(std::move(t));
+        }
+        dst = prod.back();
+    }
+    // EvaluatorCuda::exponentiateInplace  src/evaluator_cuda.cu:1525-1553
+    void exponentiateInplace(CiphertextCuda &ct, std::uint64_t exponent, const RelinKeysCuda &rlk) const {
+        if (!context_.getContextData(ct.parmsID())) throw std::invalid_argument("encrypted is not valid for encryption parameters");
+        if (!context_.getContextData(rlk.parmsID())) throw std::invalid_argument("relin_keys is not valid for encryption parameters");
+        if (exponent == 0) throw std::invalid_argument("exponent cannot be 0");
+        if (exponent == 1) return;
+        // copies of one ciphertext: the product tree multiplies distinct buffers where the reference squares aliased ones - the same words
+        std::vector<CiphertextCuda> copies(static_cast<std::size_t>(exponent), ct);
+        multiplyMany(copies, rlk, ct);
+    }
+    void exponentiate(const CiphertextCuda &ct, std::uint64_t exponent, const RelinKeysCuda &rlk, CiphertextCuda &dst) const {
+        dst = ct;
+        exponentiateInplace(dst, exponent, rlk);
+    }
+    // EvaluatorCuda::applyKeySwitchingInplace  src/evaluator_cuda.cu:1365-1378: c1 becomes the target of a key switch with the
+    // single key of `keys`, and starts again from zero
+    void applyKeySwitchingInplace(CiphertextCuda &ct, const KSwitchKeysCuda &keys) const {
+        if (keys.size() != 1 || !keys.hasIndex(0)) throw std::invalid_argument("kswitch_keys.data().size() != 1");
+        if (ct.size() != 2) throw std::invalid_argument("encrypted.size() != 2");
+        const std::size_t words = ct.polyCoeffSize();
+        b200::DeviceWords target(words);
+        b200::check(troyb_copy_on_device(target.get(), ct.data(1), words * 8, b200::stream()));
+        b200::check(troyb_memset_zero(ct.data(1), words * 8, b200::stream()));
+        b200::check(troyb_switch_key(h(), level(ct), ct.data(), 2 * words, target.get(), words, keys.key(0), 1, b200::stream()));
+    }
+    void applyKeySwitching(const CiphertextCuda &ct, const KSwitchKeysCuda &keys, CiphertextCuda &dst) const {
+        dst = ct;
+        applyKeySwitchingInplace(dst, keys);
+    }
 
     // ---- Galois / rotations (src/evaluator_cuda.cu:2024-2176)
     void applyGaloisInplace(CiphertextCuda &ct, std::uint32_t elt, const GaloisKeysCuda &gk) const {

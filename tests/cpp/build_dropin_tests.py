@@ -34,6 +34,10 @@ REFERENCE_TESTS = [
     "CKKSEncryptAddPlainDecrypt", "CKKSEncryptSubPlainDecrypt", "BFVEncryptAddPlainDecrypt", "BFVEncryptSubPlainDecrypt",
     "BFVEncryptMultiplyPlainDecrypt", "BGVEncryptAddPlainDecrypt", "BGVEncryptSubPlainDecrypt", "BGVEncryptMultiplyPlainDecrypt",
     "CKKSEncryptMultiplyByNumberDecrypt", "TransformPlainToNTT", "BFVEncryptMultiplyPlainNTTDecrypt", "BGVEncryptMultiplyPlainNTTDecrypt",
+    # compositions over the path: product trees, powers, sums, key switching to another secret key, multi-level switches, wire format
+    "BFVEncryptMultiplyManyDecrypt", "BGVEncryptMultiplyManyDecrypt", "BFVEncryptExponentiateDecrypt", "BGVEncryptExponentiateDecrypt",
+    "BFVEncryptAddManyDecrypt", "BGVEncryptAddManyDecrypt", "BFVKeySwitching", "BFVEncryptModSwitchToDecrypt", "BGVEncryptModSwitchToDecrypt",
+    "CKKSEncryptNaiveMultiplyDecrypt", "CKKSEncryptMultiplyRelinRescaleModSwitchAddDecrypt", "SerializeTest",
 ]
 
 

@@ -29,8 +29,10 @@ def test_word_for_word_parity_through_the_cpp_layer():
 
 
 def test_reference_cuda_tests_pass_against_the_drop_in():
+    """51 of the 52 tests of the reference's test/evaluator_cuda.cu, unchanged (the LWE assembly test is outside the path)."""
     out = _run("EvaluatorCudaTest.*")
     assert "[  FAILED  ]" not in out
+    assert "51 tests" in out
 
 
 def test_reference_app_header_matmul_runs_on_the_drop_in():

@@ -111,3 +111,15 @@ def test_integer_schemes(pytroy, scheme):
     half = n // 2
     want = np.concatenate([np.roll(want[:half], -1), np.roll(want[half:], -1)])
     assert np.array_equal(got, want)
+    # product tree and powers (multiply_many / exponentiate), and a key switch to another party's secret key
+    small = rng.integers(0, 7, n)
+    cs = encryptor.encrypt(encoder.encode([int(v) for v in small]))
+    cube = ev.exponentiate(cs, 3, rlk)
+    assert np.array_equal(np.array(encoder.decode(decryptor.decrypt(cube)), dtype=np.int64), small ** 3 % t)
+    tree = ev.multiply_many([cs, ca, cs], rlk)
+    assert np.array_equal(np.array(encoder.decode(decryptor.decrypt(tree)), dtype=np.int64), small * a * small % t)
+    other = pytroy.KeyGenerator(ctx)
+    ksk = keygen.create_keyswitching_keys(other.secret_key())
+    theirs = pytroy.Encryptor(ctx, other.secret_key()).encrypt_symmetric(encoder.encode([int(v) for v in a]))
+    mine = ev.apply_keyswitching(theirs, ksk)
+    assert np.array_equal(np.array(encoder.decode(decryptor.decrypt(mine)), dtype=np.int64), a % t)
