@@ -77,12 +77,22 @@ def main():
         app = open(os.path.join(REF, "app", "LinearHelperCKKS.cuh")).read()
         with open(os.path.join(tmp, "LinearHelperCKKS.cuh"), "w") as f:
             f.write("\n".join(l for l in app.splitlines() if "troy_cuda.cuh" not in l) + "\n")
+        # the reference's encryptor and CKKS-encoder CUDA test files, whole: only the line that includes the reference's own CUDA API
+        # is redirected to the drop-in header (scratch copies under /tmp at build time, nothing enters the repository)
+        whole = []
+        for name in ("encryptor_cuda.cu", "ckks_cuda.cu"):
+            text_w = open(os.path.join(REF, "test", name)).read().replace('#include "../src/troy_cuda.cuh"', '#include "troy_cuda.cuh"')
+            dst = os.path.join(tmp, "reference_" + name.replace(".cu", ".cpp"))
+            with open(dst, "w") as f:
+                f.write(text_w)
+            whole.append(dst)
         inc = ["-I" + tmp, "-I" + os.path.join(ROOT, "include", "troyn"), "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(REF, "src"),
                "-I" + os.path.join(gt, "include"), "-I" + gt]
         objs = []
         jobs = [(gen, "ref_tests.o"), (os.path.join(ROOT, "tests", "cpp", "dropin_parity.cpp"), "parity.o"),
                 (os.path.join(ROOT, "tests", "cpp", "dropin_linear.cpp"), "linear.o"),
                 (os.path.join(gt, "src", "gtest-all.cc"), "gtest-all.o"), (os.path.join(gt, "src", "gtest_main.cc"), "gtest_main.o")]
+        jobs += [(w, os.path.basename(w) + ".o") for w in whole]
         procs = []
         for s, o in jobs:
             o = os.path.join(tmp, o)
@@ -95,7 +105,7 @@ def main():
         print("+", " ".join(cmd), flush=True)
         if subprocess.call(cmd):
             return 1
-    print(f"built {OUT}: {len(found)} reference CUDA tests + DropInParity + DropInLinear")
+    print(f"built {OUT}: {len(found)} reference evaluator tests + the reference's encryptor_cuda.cu and ckks_cuda.cu + DropInParity + DropInLinear")
     return 0
 
 

@@ -35,6 +35,14 @@ def test_reference_cuda_tests_pass_against_the_drop_in():
     assert "51 tests" in out
 
 
+def test_reference_encryptor_and_encoder_test_files_pass_against_the_drop_in():
+    """The reference's test/encryptor_cuda.cu (6 tests: encryption and decryption now run on the device) and test/ckks_cuda.cu
+    (2 tests), whole files, unchanged but for the include of the CUDA API."""
+    out = _run("EncryptorCudaTest.*:CKKSEncoderCudaTest.*")
+    assert "[  FAILED  ]" not in out
+    assert "8 tests" in out
+
+
 def test_reference_app_header_matmul_runs_on_the_drop_in():
     """app/LinearHelperCKKS.cuh (MatmulHelper) compiled unchanged against the drop-in header: encode, encrypt, matmul,
     serialise by terms, decrypt on the device; the decoded product equals x @ W."""
