@@ -105,6 +105,16 @@ def main():
         print("+", " ".join(cmd), flush=True)
         if subprocess.call(cmd):
             return 1
+        # the reference's own timing program against the drop-in (the other build, against the reference's CUDA library, is
+        # oracle/_ref/timetest_reference)
+        tt = os.path.join(tmp, "reference_timetest.cpp")
+        with open(tt, "w") as f:
+            f.write(open(os.path.join(REF, "test", "timetest.cu")).read().replace('#include "../src/troy_cuda.cuh"', '#include "troy_cuda.cuh"'))
+        cmd = ["g++", "-std=c++17", "-O2", "-w", *inc, tt, "-o", os.path.join(OUT_DIR, "timetest_dropin"), "-L" + os.path.join(ROOT, "troy_b200"),
+               "-ltroy_b200", "-L" + os.path.join(ROOT, "oracle", "_ref"), "-ltroyref", "-Wl,-rpath,$ORIGIN/../../../troy_b200",
+               "-Wl,-rpath,$ORIGIN/../../../oracle/_ref", "-lpthread"]
+        if subprocess.call(cmd):
+            print("note: the reference's timetest.cu did not build against the drop-in")
     print(f"built {OUT}: {len(found)} reference evaluator tests + the reference's encryptor_cuda.cu and ckks_cuda.cu + DropInParity + DropInLinear")
     return 0
 
