@@ -105,6 +105,13 @@ int troyb_negate(troyb_context *ctx, int level, const uint64_t *d_a, uint64_t *d
 int troyb_multiply_scalar(troyb_context *ctx, int level, const uint64_t *d_a, uint64_t scalar, uint64_t *d_out, size_t n_polys,
                           void *stream);
 
+/* kMultiplyInvPolyDegreeCoeffmod  src/kernelutils.cu:578-592 (EvaluatorCuda::divideByPolyModulusDegreeInplace, src/evaluator_cuda.cu:2262):
+ * out = a * N^-1 mod q_l on every limb. */
+int troyb_multiply_inv_degree(troyb_context *ctx, int level, const uint64_t *d_a, uint64_t *d_out, size_t n_polys, void *stream);
+/* kNegacyclicShiftPolyCoeffmod  src/kernelutils.cu:537-576 (EvaluatorCuda::negacyclicShift / extractLWE / assembleLWE / packLWECiphertexts,
+ * src/evaluator_cuda.cu:2185-2365): out = in * X^shift modulo X^N + 1 on n_polys coefficient-form polys, shift in [0, 2N); out of place. */
+int troyb_negacyclic_shift(troyb_context *ctx, int level, const uint64_t *d_in, uint64_t *d_out, size_t n_polys, uint64_t shift, void *stream);
+
 /* EvaluatorCuda::multiplyInplace → ckksMultiply / bgvMultiply / bfvMultiply  src/evaluator_cuda.cu:262-523
  * (squareInplace :525-701 is the same call with d_b = d_a). Inputs a: a_size polys, b: b_size polys; output
  * a_size+b_size-1 polys. d_out may alias d_a (in-place, as the reference does after resize).

@@ -502,6 +502,39 @@ private:
     b200::DeviceWords data_;
 };
 
+// LWECiphertextCuda (src/ciphertext_cuda.cuh:270-330): one coefficient of an RLWE ciphertext as an LWE sample - c1 (a whole
+// polynomial, [limbs][N], coefficient form) and c0 (one word per limb).
+class LWECiphertextCuda {
+public:
+    ParmsID &parmsID() noexcept { return parms_id_; }
+    const ParmsID &parmsID() const noexcept { return parms_id_; }
+    bool isNttForm() const noexcept { return false; }
+    double &scale() noexcept { return scale_; }
+    double scale() const noexcept { return scale_; }
+    std::uint64_t correctionFactor() const noexcept { return correction_; }
+    std::uint64_t &correctionFactor() noexcept { return correction_; }
+    std::size_t polyModulusDegree() const noexcept { return n_; }
+    std::size_t coeffModulusSize() const noexcept { return limbs_; }
+    std::uint64_t *c1() { return c1_.get(); }
+    const std::uint64_t *c1() const { return c1_.get(); }
+    std::uint64_t *c0() { return c0_.get(); }
+    const std::uint64_t *c0() const { return c0_.get(); }
+    static LWECiphertextCuda fromMembers(ParmsID parms_id, std::size_t n, std::size_t limbs, double scale, std::uint64_t correction,
+                                         b200::DeviceWords &&c1, b200::DeviceWords &&c0) {
+        LWECiphertextCuda ct;
+        ct.parms_id_ = parms_id; ct.n_ = n; ct.limbs_ = limbs; ct.scale_ = scale; ct.correction_ = correction;
+        ct.c1_ = std::move(c1); ct.c0_ = std::move(c0);
+        return ct;
+    }
+
+private:
+    ParmsID parms_id_ = parmsIDZero;
+    std::size_t n_ = 0, limbs_ = 0;
+    double scale_ = 1.0;
+    std::uint64_t correction_ = 1;
+    b200::DeviceWords c1_, c0_;
+};
+
 // keys()[index] = one key-switching key as device words [digit][2][key limbs][N]   (src/kswitchkeys_cuda.cuh:43-56,366)
 class KSwitchKeysCuda {
 public:
@@ -634,6 +667,8 @@ public:
     void createGaloisKeys(const std::vector<std::uint32_t> &elts, GaloisKeysCuda &dst) { GaloisKeys k; gen_.createGaloisKeys(elts, k); dst = GaloisKeysCuda(k); }
     void createGaloisKeys(const std::vector<int> &steps, GaloisKeysCuda &dst) { GaloisKeys k; gen_.createGaloisKeys(steps, k); dst = GaloisKeysCuda(k); }
     void createGaloisKeys(GaloisKeysCuda &dst) { GaloisKeys k; gen_.createGaloisKeys(k); dst = GaloisKeysCuda(k); }
+    // keys for the automorphisms X -> X^(2^k + 1) of the LWE packing (src/keygenerator.cpp:350-358)
+    GaloisKeysCuda createAutomorphismKeys() { return GaloisKeysCuda(gen_.createAutomorphismKeys()); }
     // key-switching key from another party's secret key to this generator's (src/keygenerator.h:292)
     KSwitchKeysCuda createKeySwitchingKeys(const SecretKey &new_key) { return KSwitchKeysCuda(gen_.createKeySwitchingKeys(new_key)); }
     KeyGenerator &host() { return gen_; }
@@ -798,12 +833,10 @@ public:
                 throw std::logic_error("invalid correction factor");
             b200::check(troyb_decrypt_mod_t(context_.handle(), lv, phase.get(), out.get(), fix, 1, b200::stream()));
         }
+        // full size, like the reference's CUDA decryptor (src/decryptor_cuda.cu:119-131; its CPU decryptor trims to the significant
+        // coefficients, the CUDA one has that step commented out, and decodePolynomial callers index up to the slot count)
         dst.resize(n);
         out.download(dst.data(), n);
-        // the CPU decryptor trims the plaintext to its significant coefficients (src/decryptor.cpp bfvDecrypt / bgvDecrypt)
-        std::size_t count = n;
-        while (count > 1 && dst.data()[count - 1] == 0) count--;
-        dst.resize(count);
     }
     int invariantNoiseBudget(const CiphertextCuda &ct) { return dec_.invariantNoiseBudget(ct.cpu()); }
 
@@ -931,6 +964,98 @@ public:
     void applyKeySwitching(const CiphertextCuda &ct, const KSwitchKeysCuda &keys, CiphertextCuda &dst) const {
         dst = ct;
         applyKeySwitchingInplace(dst, keys);
+    }
+
+    // ---- LWE extraction / packing (src/evaluator_cuda.cu:2178-2365): compositions over the negacyclic shift, applyGalois and add
+    void negacyclicShift(const CiphertextCuda &ct, std::size_t shift, CiphertextCuda &dst) const {
+        CiphertextCuda out = ct; // metadata and size
+        b200::check(troyb_negacyclic_shift(h(), level(ct), ct.data(), out.data(), ct.size(), shift, b200::stream()));
+        dst = std::move(out);
+    }
+    void negacyclicShiftInplace(CiphertextCuda &ct, std::size_t shift) const { CiphertextCuda x = ct; negacyclicShift(x, shift, ct); }
+    LWECiphertextCuda extractLWE(const CiphertextCuda &ct, std::size_t term) const {
+        if (ct.size() != 2) throw std::invalid_argument("Encrypted size must be 2 to be extracted.");
+        if (ct.isNttForm()) {
+            CiphertextCuda t;
+            transformFromNtt(ct, t);
+            return extractLWE(t, term);
+        }
+        const std::size_t n = ct.polyModulusDegree(), limbs = ct.coeffModulusSize();
+        b200::DeviceWords c1(n * limbs), c0(limbs);
+        b200::check(troyb_negacyclic_shift(h(), level(ct), ct.data(1), c1.get(), 1, term == 0 ? 0 : 2 * n - term, b200::stream()));
+        for (std::size_t l = 0; l < limbs; l++) // extractLWECopyC0: coefficient `term` of every limb of c0
+            b200::check(troyb_copy_on_device(c0.get() + l, ct.data(0) + l * n + term, 8, b200::stream()));
+        return LWECiphertextCuda::fromMembers(ct.parmsID(), n, limbs, ct.scale(), ct.correctionFactor(), std::move(c1), std::move(c0));
+    }
+    CiphertextCuda assembleLWE(const LWECiphertextCuda &lwe, std::size_t term) const {
+        const std::size_t n = lwe.polyModulusDegree(), limbs = lwe.coeffModulusSize(), poly = n * limbs;
+        const int lv = context_.levelOf(lwe.parmsID());
+        b200::DeviceWords data(2 * poly);
+        b200::check(troyb_memset_zero(data.get(), poly * 8, b200::stream()));
+        b200::check(troyb_negacyclic_shift(h(), lv, lwe.c1(), data.get() + poly, 1, term, b200::stream()));
+        for (std::size_t l = 0; l < limbs; l++) // assembleLWECopyC0
+            b200::check(troyb_copy_on_device(data.get() + l * n + term, lwe.c0() + l, 8, b200::stream()));
+        CiphertextCuda out;
+        out.adopt(std::move(data), 2, n, limbs);
+        out.parmsID() = lwe.parmsID();
+        out.isNttForm() = false;
+        out.scale() = lwe.scale();
+        out.correctionFactor() = lwe.correctionFactor();
+        return out;
+    }
+    void fieldTraceInplace(CiphertextCuda &ct, const GaloisKeysCuda &automorphism_keys, std::size_t logn) const {
+        std::size_t degree = ct.polyModulusDegree();
+        CiphertextCuda t;
+        while (degree > (std::size_t(1) << logn)) {
+            applyGalois(ct, (std::uint32_t)(degree + 1), automorphism_keys, t);
+            addInplace(ct, t);
+            degree >>= 1;
+        }
+    }
+    void divideByPolyModulusDegreeInplace(CiphertextCuda &ct, std::uint64_t mul = 1) const {
+        const int lv = level(ct);
+        std::uint64_t *d = ct.data();
+        b200::check(troyb_multiply_inv_degree(h(), lv, d, d, ct.size(), b200::stream()));
+        if (mul > 1) b200::check(troyb_multiply_scalar(h(), lv, d, mul, d, ct.size(), b200::stream()));
+    }
+    CiphertextCuda packLWECiphertexts(const std::vector<LWECiphertextCuda> &lwes, GaloisKeysCuda &automorphism_keys) const {
+        if (lwes.empty()) throw std::invalid_argument("LWE ciphertexts must not be empty.");
+        for (auto &x : lwes) if (x.parmsID() != lwes[0].parmsID()) throw std::invalid_argument("LWE ciphertexts must have same parmsID.");
+        const std::size_t n = lwes[0].polyModulusDegree();
+        const bool ckks = scheme() == SchemeType::ckks;
+        std::size_t l = 0;
+        while ((std::size_t(1) << l) < lwes.size()) l++;
+        std::vector<CiphertextCuda> rlwes(std::size_t(1) << l);
+        CiphertextCuda zero = assembleLWE(lwes[0], 0);
+        b200::check(troyb_memset_zero(zero.data(), 2 * zero.polyCoeffSize() * 8, b200::stream()));
+        for (std::size_t i = 0; i < rlwes.size(); i++) {
+            std::size_t index = 0;
+            for (std::size_t b = 0; b < l; b++) index |= ((i >> b) & 1) << (l - 1 - b); // reverseBits(i, l)
+            if (index < lwes.size()) {
+                rlwes[i] = assembleLWE(lwes[index], 0);
+                divideByPolyModulusDegreeInplace(rlwes[i]);
+            } else {
+                rlwes[i] = zero;
+            }
+        }
+        CiphertextCuda temp = zero;
+        for (std::size_t layer = 0; layer < l; layer++) {
+            const std::size_t gap = std::size_t(1) << layer, shift = n >> (layer + 1);
+            for (std::size_t offset = 0; offset < rlwes.size(); offset += 2 * gap) {
+                CiphertextCuda &even = rlwes[offset], &odd = rlwes[offset + gap];
+                negacyclicShift(odd, shift, temp);
+                sub(even, temp, odd);
+                addInplace(even, temp);
+                if (ckks) transformToNttInplace(odd);
+                applyGaloisInplace(odd, (std::uint32_t)((std::size_t(1) << (layer + 1)) + 1), automorphism_keys);
+                if (ckks) transformFromNttInplace(odd);
+                addInplace(even, odd);
+            }
+        }
+        CiphertextCuda ret = std::move(rlwes[0]);
+        fieldTraceInplace(ret, automorphism_keys, l);
+        if (ckks) transformToNttInplace(ret);
+        return ret;
     }
 
     // ---- Galois / rotations (src/evaluator_cuda.cu:2024-2176)
@@ -1246,6 +1371,7 @@ using EncryptionParameters = troy::EncryptionParametersCuda;
 using SEALContext = troy::SEALContextCuda;
 using Plaintext = troy::PlaintextCuda;
 using Ciphertext = troy::CiphertextCuda;
+using LWECiphertext = troy::LWECiphertextCuda;
 using Encryptor = troy::EncryptorCuda;
 using Decryptor = troy::DecryptorCuda;
 using Evaluator = troy::EvaluatorCuda;

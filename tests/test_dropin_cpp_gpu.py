@@ -29,10 +29,11 @@ def test_word_for_word_parity_through_the_cpp_layer():
 
 
 def test_reference_cuda_tests_pass_against_the_drop_in():
-    """51 of the 52 tests of the reference's test/evaluator_cuda.cu, unchanged (the LWE assembly test is outside the path)."""
+    """All 52 tests of the reference's test/evaluator_cuda.cu, unchanged (the last one, BFVAssembleLWETest, covers LWE extraction,
+    assembly, the field trace and packLWECiphertexts)."""
     out = _run("EvaluatorCudaTest.*")
     assert "[  FAILED  ]" not in out
-    assert "51 tests" in out
+    assert "52 tests" in out
 
 
 def test_reference_encryptor_and_encoder_test_files_pass_against_the_drop_in():

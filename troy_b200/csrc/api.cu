@@ -798,6 +798,30 @@ int troyb_multiply_scalar(troyb_context *ctx, int level, const uint64_t *a, uint
     return addsub(ctx, level, 3, a, a, out, n, st, scalar);
 }
 
+int troyb_multiply_inv_degree(troyb_context *ctx, int level, const uint64_t *a, uint64_t *out, size_t n, void *st) {
+    return addsub(ctx, level, 5, a, nullptr, out, n, st);
+}
+int troyb_negacyclic_shift(troyb_context *ctx, int level, const uint64_t *d_in, uint64_t *d_out, size_t n_polys, uint64_t shift, void *stream) {
+    API_BEGIN
+    need_init();
+    Context *c = C(ctx);
+    const u32 L = (u32)level_limbs(c, level);
+    if (level < 0) throw std::invalid_argument("level is not valid for encryption parameters");
+    if (shift >= 2 * c->N) throw std::invalid_argument("shift must be below 2 N");
+    if (d_in == d_out) throw std::invalid_argument("negacyclic shift is out of place");
+    EltNegacyclicShift k{};
+    k.logN = c->logN;
+    k.mods = c->d_mods;
+    k.map = c->map_prefix(L);
+    k.n_limbs = L;
+    k.shift = shift;
+    k.total = (u64)n_polys * L * c->N;
+    k.in = d_in;
+    k.out = d_out;
+    ck(launch_cta(k, grid_for(k.total, EltNegacyclicShift::kThreads), 0, S(stream)));
+    API_END
+}
+
 int troyb_multiply(troyb_context *ctx, int level, const uint64_t *d_a, size_t a_size, size_t a_stride, const uint64_t *d_b,
                    size_t b_size, size_t b_stride, uint64_t *d_out, size_t out_stride, size_t batch, void *stream) {
     API_BEGIN

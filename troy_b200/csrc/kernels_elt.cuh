@@ -22,7 +22,7 @@ TB_D void mac128(u64 &lo, u64 &hi, u64 a, u64 b) {
 struct EltAddSub {
     static constexpr int kThreads = kEltThreads;
     const char *name() const { return "elt_add_sub_negate_scale"; }
-    int op; // 0 add, 1 sub, 2 negate, 3 multiply by `scalar`, 4 reduce modulo the prime
+    int op; // 0 add, 1 sub, 2 negate, 3 multiply by `scalar`, 4 reduce modulo the prime, 5 multiply by N^-1 (kMultiplyInvPolyDegreeCoeffmod)
     u64 scalar;
     int logN;
     const ModDev *mods;
@@ -45,6 +45,7 @@ struct EltAddSub {
                 else if (op == 1) r = submod(x, b[idx], p);
                 else if (op == 2) r = negmod(x, p);
                 else if (op == 4) r = barrett64(x, p, m.ratio1);
+                else if (op == 5) r = shoup(x, m.ninv, m.ninv_shoup, p);
                 else r = mulmod_barrett(x, barrett64(scalar, p, m.ratio1), p, m.ratio0, m.ratio1);
                 out[idx] = r;
             }
@@ -72,6 +73,34 @@ struct EltReduceRow {
                 v.x = barrett64(v.x, mod.p, mod.ratio1);
                 v.y = barrett64(v.y, mod.p, mod.ratio1);
                 *ptr = v;
+            }
+        })
+    }
+};
+
+// kNegacyclicShiftPolyCoeffmod  src/kernelutils.cu:537-576: multiplication by X^shift modulo X^N + 1, shift in [0, 2N):
+// out[(g + shift) mod N] = in[g], negated when g + shift passes N an odd number of times. Written as a gather.
+struct EltNegacyclicShift {
+    static constexpr int kThreads = kEltThreads;
+    const char *name() const { return "negacyclic_shift"; }
+    int logN;
+    const ModDev *mods;
+    LimbMap map;
+    u32 n_limbs;
+    u64 shift;
+    u64 total; // polys * n_limbs * N
+    const u64 *in;
+    u64 *out;
+    TB_D void operator()(u32 bid, u64 *) const {
+        TB_PHASE(kThreads, t, {
+            const u64 idx = (u64)bid * kThreads + t;
+            if (idx < total) {
+                const u64 N = u64(1) << logN, i = idx & (N - 1), base = idx - i;
+                const u64 g = (i - shift) & (N - 1);          // source coefficient
+                const bool flip = ((g + shift) >> logN) & 1;  // crossed X^N = -1 an odd number of times
+                const u64 p = mods[map.idx[(u32)((idx >> logN) % n_limbs)]].p;
+                const u64 v = in[base + g];
+                out[idx] = flip ? negmod(v, p) : v;
             }
         })
     }

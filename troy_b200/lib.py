@@ -69,6 +69,8 @@ _SIGNATURES = {
     "troyb_sub": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _sz, _vp]),
     "troyb_negate": (C.c_int, [_vp, C.c_int, _vp, _vp, _sz, _vp]),
     "troyb_multiply_scalar": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64, _vp, _sz, _vp]),
+    "troyb_multiply_inv_degree": (C.c_int, [_vp, C.c_int, _vp, _vp, _sz, _vp]),
+    "troyb_negacyclic_shift": (C.c_int, [_vp, C.c_int, _vp, _vp, _sz, C.c_uint64, _vp]),
     "troyb_multiply": (C.c_int, [_vp, C.c_int, _vp, _sz, _sz, _vp, _sz, _sz, _vp, _sz, _sz, _vp]),
     "troyb_switch_key": (C.c_int, [_vp, C.c_int, _vp, _sz, _vp, _sz, _vp, _sz, _vp]),
     "troyb_switch_key_partial": (C.c_int, [_vp, C.c_int, _vp, _sz, _vp, C.c_int, C.c_int, _vp, _sz, _vp]),
