@@ -1,7 +1,7 @@
 // pytroy — the reference's Python module (binder/binder.cu: PYBIND11_MODULE(pytroy, m)) for the classes of the RNS polynomial
 // path, bound over the drop-in header include/troyn/troy_cuda.cuh (and so over libtroy_b200.so). Python-visible names and
 // argument order follow the reference's module, so that scripts written for it (e.g. its binder/test.py) run unchanged;
-// the LWE / Conv2d application helpers of the reference (app/LinearHelper.cuh) are outside the path and not bound.
+// the Conv2d / BFV-matmul application helpers of the reference (app/LinearHelper.cuh) are outside the path and not bound.
 // Serialisation goes through Python `bytes` in the reference's wire format.
 #include <pybind11/complex.h>
 #include <pybind11/numpy.h>
@@ -139,7 +139,14 @@ PYBIND11_MODULE(pytroy, m) {
         .def("create_relin_keys", [](KeyGenerator &g) { RelinKeys k; g.createRelinKeys(k); return k; })
         .def("create_keyswitching_keys", [](KeyGenerator &g, const SecretKey &other) { return g.createKeySwitchingKeys(other); })
         .def("create_galois_keys", [](KeyGenerator &g) { GaloisKeys k; g.createGaloisKeys(k); return k; })
-        .def("create_galois_keys", [](KeyGenerator &g, const std::vector<int> &steps) { GaloisKeys k; g.createGaloisKeys(steps, k); return k; });
+        .def("create_galois_keys", [](KeyGenerator &g, const std::vector<int> &steps) { GaloisKeys k; g.createGaloisKeys(steps, k); return k; })
+        .def("create_automorphism_keys", [](KeyGenerator &g) { return g.createAutomorphismKeys(); });
+
+    // binder/binder.cu:298-302
+    py::class_<LWECiphertext>(m, "LWECiphertext")
+        .def("copy", [](const LWECiphertext &c) { return LWECiphertext(c); })
+        .def("poly_modulus_degree", &LWECiphertext::polyModulusDegree)
+        .def("coeff_modulus_size", &LWECiphertext::coeffModulusSize);
 
     py::class_<BatchEncoder>(m, "BatchEncoder")
         .def(py::init<const SEALContext &>())
@@ -228,5 +235,13 @@ PYBIND11_MODULE(pytroy, m) {
         .def("rotate_vector_inplace", &Evaluator::rotateVectorInplace)
         .def("rotate_vector", [](const Evaluator &e, const Ciphertext &a, int steps, const GaloisKeys &k) { return fresh([&](Ciphertext &o) { e.rotateVector(a, steps, k, o); }); })
         .def("complex_conjugate_inplace", &Evaluator::complexConjugateInplace)
-        .def("complex_conjugate", [](const Evaluator &e, const Ciphertext &a, const GaloisKeys &k) { return fresh([&](Ciphertext &o) { e.complexConjugate(a, k, o); }); });
+        .def("complex_conjugate", [](const Evaluator &e, const Ciphertext &a, const GaloisKeys &k) { return fresh([&](Ciphertext &o) { e.complexConjugate(a, k, o); }); })
+        // LWE extraction / packing (binder/binder.cu:712-722)
+        .def("extract_lwe", &Evaluator::extractLWE)
+        .def("assemble_lwe", &Evaluator::assembleLWE)
+        .def("field_trace_inplace", &Evaluator::fieldTraceInplace)
+        .def("divide_by_poly_modulus_degree_inplace", &Evaluator::divideByPolyModulusDegreeInplace, py::arg("ciphertext"), py::arg("mul") = 1)
+        .def("pack_lwe_ciphertexts", &Evaluator::packLWECiphertexts)
+        .def("negacyclic_shift", [](const Evaluator &e, const Ciphertext &a, std::size_t shift) { return fresh([&](Ciphertext &o) { e.negacyclicShift(a, shift, o); }); })
+        .def("negacyclic_shift_inplace", &Evaluator::negacyclicShiftInplace);
 }

@@ -43,6 +43,8 @@ def lib():
             "ref_ntt_tables": (C.c_int, [vp, C.c_int, C.c_int, u64p, u64p, u64p]),
             "ref_ntt": (C.c_int, [vp, C.c_int, C.c_int, u64p, C.c_int]),
             "ref_ntt_prime": (C.c_int, [C.c_uint64, C.c_uint64, u64p, C.c_int, C.c_int]),
+            "ref_negacyclic_shift": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, u64p, u64p]),
+            "ref_multiply_inv_degree": (C.c_int, [C.c_uint64, C.c_uint64, u64p, u64p]),
             "ref_rns_info": (C.c_int, [vp, C.c_int, u64p, u64p]),
             "ref_rns_op": (C.c_int, [vp, C.c_int, C.c_int, u64p, u64p]),
             "ref_galois_elt_from_step": (C.c_uint32, [vp, C.c_int]),
@@ -416,6 +418,24 @@ def ntt_prime(n, prime, data, inverse=False, reps=1):
     if lib().ref_ntt_prime(n, prime, _p(d), int(inverse), reps) != 0:
         raise RefError(_err())
     return d
+
+
+def negacyclic_shift(n, prime, shift, data):
+    """data * X^shift modulo X^n + 1 and ``prime`` (src/utils/polyarithsmallmod.cpp:128-152)"""
+    d = np.ascontiguousarray(data, dtype=np.uint64)
+    out = np.empty_like(d)
+    if lib().ref_negacyclic_shift(n, prime, shift, _p(d), _p(out)) != 0:
+        raise RefError(_err())
+    return out
+
+
+def multiply_inv_degree(n, prime, data):
+    """data * n^-1 modulo ``prime`` (EvaluatorCuda::divideByPolyModulusDegreeInplace per limb)"""
+    d = np.ascontiguousarray(data, dtype=np.uint64)
+    out = np.empty_like(d)
+    if lib().ref_multiply_inv_degree(n, prime, _p(d), _p(out)) != 0:
+        raise RefError(_err())
+    return out
 
 
 def time_ntt(n, prime, inverse, reps, threads):

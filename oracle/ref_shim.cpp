@@ -173,6 +173,25 @@ int ref_ntt_prime(uint64_t n, uint64_t prime, uint64_t *data, int inverse, int r
     REF_CATCH(-1)
 }
 
+// Multiplication by X^shift modulo X^n + 1 under one prime (src/utils/polyarithsmallmod.cpp:128-152), shift in [0, 2n),
+// and multiplication by n^-1 (what EvaluatorCuda::divideByPolyModulusDegreeInplace does per limb, src/evaluator_cuda.cu:2262):
+// the CPU statements of the two kernels behind the LWE extraction / packing methods.
+int ref_negacyclic_shift(uint64_t n, uint64_t prime, uint64_t shift, const uint64_t *in, uint64_t *out) {
+    REF_TRY
+    util::negacyclicShiftPolyCoeffmod(ConstHostPointer<uint64_t>(in), (size_t)n, (size_t)shift, Modulus(prime), HostPointer<uint64_t>(out));
+    return 0;
+    REF_CATCH(-1)
+}
+int ref_multiply_inv_degree(uint64_t n, uint64_t prime, const uint64_t *in, uint64_t *out) {
+    REF_TRY
+    Modulus q(prime);
+    uint64_t inv = 0;
+    if (!util::tryInvertUintMod(n, q, inv)) throw std::invalid_argument("n is not invertible");
+    util::multiplyPolyScalarCoeffmod(ConstHostPointer<uint64_t>(in), (size_t)n, inv, q, HostPointer<uint64_t>(out));
+    return 0;
+    REF_CATCH(-1)
+}
+
 // ---- RNSTool pieces (src/utils/rns.cpp) ----------------------------------------------------
 // info: [|q|, |B|, |Bsk|, |Bsk∪m̃|, m_sk, gamma, m_tilde, t]; bsk_out: Bsk primes
 int ref_rns_info(void *h, int level, uint64_t *info, uint64_t *bsk_out) {

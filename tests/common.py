@@ -1,6 +1,7 @@
 """Shared helpers for the parity tests: build the reference context and the troy_b200 context on identical parameters,
 seeded keys and synthetic ciphertexts (uniform residues), and compare every output word."""
 import numpy as np
+import pytest
 
 SEED = (1, 2, 3, 4, 5, 6, 7, 8)
 
@@ -365,3 +366,37 @@ def run_encrypt_flow(ref, tb, scheme, n, bits, rng, batch=2):
     two = enc.encrypt_zero(0, batch=2, seeds=rng.integers(0, 2 ** 63, (2, 8), dtype=np.uint64)).to_host()
     assert not np.array_equal(two[0], two[1])
     assert not np.array_equal(enc.encrypt_zero(0).to_host(), enc.encrypt_zero(0).to_host())
+
+
+def run_lwe_kernels_flow(ref, tb, scheme, n, bits):
+    """The two kernels behind extractLWE / assembleLWE / packLWECiphertexts (kNegacyclicShiftPolyCoeffmod,
+    kMultiplyInvPolyDegreeCoeffmod, src/kernelutils.cu:537-592) against the reference's CPU statements, every word, at
+    shifts on both sides of N (including 0, N and 2N - 1) and on a lower level; X^a * X^b = X^(a+b) as the size-free property."""
+    from troy_b200.lib import TroyInvalidArgument
+    rc, ctx = make_pair(ref, tb, scheme, n, bits)
+    ev = tb.EvaluatorCuda(ctx)
+    rng = np.random.default_rng(900 + n)
+    for level in (0, 1):
+        mods = rc.level_moduli(level)
+        w = random_ct_words(rc, level, 2, n, rng, batch=2)
+        w[0, 0, 0, :7] = 0  # zero coefficients stay zero on the negated side (the reference tests poly[i] != 0)
+        ct = tb.CiphertextCuda.from_host(ctx, w, level, False)
+        for shift in (0, 1, n // 2 + 3, n - 1, n, n + 5, 2 * n - 1):
+            got = ev.negacyclic_shift(ct, shift).to_host()
+            for b in range(2):
+                for k in range(2):
+                    for l, q in enumerate(mods):
+                        want = ref.negacyclic_shift(n, int(q), shift, w[b, k, l])
+                        assert np.array_equal(got[b, k, l], want), (level, shift, b, k, l)
+        a, bb = 3, n - 2
+        twice = ev.negacyclic_shift(ev.negacyclic_shift(ct, a), bb).to_host()
+        assert np.array_equal(twice, ev.negacyclic_shift(ct, a + bb).to_host())
+        with pytest.raises(TroyInvalidArgument):
+            ev.negacyclic_shift(ct, 2 * n)
+        d = ct.clone()
+        ev.divide_by_poly_modulus_degree_inplace(d)
+        got = d.to_host()
+        for b in range(2):
+            for k in range(2):
+                for l, q in enumerate(mods):
+                    assert np.array_equal(got[b, k, l], ref.multiply_inv_degree(n, int(q), w[b, k, l])), (level, b, k, l)

@@ -61,7 +61,8 @@ def test_pytroy_module_imports_and_names_follow_the_reference_binder():
     for cls, methods in {
         "EncryptionParameters": ["set_poly_modulus_degree", "set_coeff_modulus", "set_plain_modulus"],
         "CoeffModulus": ["create"], "PlainModulus": ["batching"], "SEALContext": ["first_parms_id", "key_parms_id"],
-        "KeyGenerator": ["secret_key", "create_public_key", "create_relin_keys", "create_galois_keys"],
+        "KeyGenerator": ["secret_key", "create_public_key", "create_relin_keys", "create_galois_keys", "create_automorphism_keys"],
+        "LWECiphertext": ["copy"],
         "Encryptor": ["encrypt", "encrypt_symmetric", "encrypt_zero"], "Decryptor": ["decrypt"],
         "CKKSEncoder": ["encode", "decode", "slot_count"], "BatchEncoder": ["encode", "decode"],
         "Ciphertext": ["save", "load", "save_terms", "load_terms", "scale", "parms_id", "size"], "Plaintext": ["save", "load"],
@@ -69,7 +70,8 @@ def test_pytroy_module_imports_and_names_follow_the_reference_binder():
         "Evaluator": ["multiply_inplace", "relinearize_inplace", "rescale_to_next_inplace", "rotate_vector_inplace", "rotate_rows_inplace",
                       "mod_switch_to_next_inplace", "add_inplace", "sub_inplace", "negate_inplace", "square_inplace", "multiply_plain_inplace",
                       "add_plain_inplace", "transform_to_ntt_inplace", "transform_from_ntt_inplace", "apply_galois_inplace",
-                      "complex_conjugate_inplace", "rotate_columns_inplace"],
+                      "complex_conjugate_inplace", "rotate_columns_inplace", "extract_lwe", "assemble_lwe", "field_trace_inplace",
+                      "divide_by_poly_modulus_degree_inplace", "pack_lwe_ciphertexts", "negacyclic_shift", "negacyclic_shift_inplace"],
     }.items():
         c = getattr(pytroy, cls)
         for m in methods:

@@ -123,3 +123,9 @@ def test_encryptor_error_behaviour_emulated(ref, emul_lib):
     # every level of the chain, asymmetric: the limb count follows the level
     for level in range(ctx.num_levels):
         assert only_pk.encrypt_zero(level).limbs == ctx.level_limbs(level)
+
+
+@pytest.mark.parametrize("scheme,n,bits", [(1, 256, [40, 30, 30, 40]), (2, 64, [40, 30, 30, 40])])
+def test_negacyclic_shift_and_divide_by_degree_emulated(ref, emul_lib, scheme, n, bits):
+    from common import run_lwe_kernels_flow
+    run_lwe_kernels_flow(ref, emul_lib, scheme, n, bits)

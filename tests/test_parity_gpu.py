@@ -334,3 +334,11 @@ def test_fused_key_switch(ref, cuda_lib, monkeypatch, scheme, n, bits):
     _L().call("troyb_profile_enable", 0)
     names = {json.loads(x)["kernel"] for x in buf.value.decode().splitlines() if x.strip()}
     assert "ntt_fwd_modup" in names and "ks_inner_product" not in names
+
+
+@pytest.mark.parametrize("scheme,n,bits", [(1, 8192, [60, 40, 40, 60]), (2, 16384, [60, 40, 40, 40, 60]), (3, 64, [40, 30, 30, 40])])
+def test_negacyclic_shift_and_divide_by_degree(ref, cuda_lib, scheme, n, bits):
+    """troyb_negacyclic_shift / troyb_multiply_inv_degree (the kernels behind extractLWE / assembleLWE / packLWECiphertexts)
+    word for word against the reference's CPU statements."""
+    from common import run_lwe_kernels_flow
+    run_lwe_kernels_flow(ref, cuda_lib, scheme, n, bits)

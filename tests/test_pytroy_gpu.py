@@ -123,3 +123,54 @@ def test_integer_schemes(pytroy, scheme):
     theirs = pytroy.Encryptor(ctx, other.secret_key()).encrypt_symmetric(encoder.encode([int(v) for v in a]))
     mine = ev.apply_keyswitching(theirs, ksk)
     assert np.array_equal(np.array(encoder.decode(decryptor.decrypt(mine)), dtype=np.int64), a % t)
+
+
+@pytest.mark.parametrize("scheme,n", [("bfv", 4096), ("bgv", 2048)])
+def test_lwe_extract_assemble_pack(pytroy, scheme, n):
+    """extract_lwe / assemble_lwe / field_trace_inplace / pack_lwe_ciphertexts (binder/binder.cu:712-722) at a working size: the
+    flow of the reference's BFVAssembleLWETest (test/evaluator_cuda.cu:6340-6440), which runs at N = 32."""
+    parms = pytroy.EncryptionParameters(getattr(pytroy.SchemeType, scheme))
+    parms.set_poly_modulus_degree(n)
+    parms.set_coeff_modulus(pytroy.CoeffModulus.create(n, [50, 40, 50]))
+    parms.set_plain_modulus(pytroy.PlainModulus.batching(n, 20))
+    t = parms.plain_modulus().value()
+    ctx = pytroy.SEALContext(parms, True, pytroy.SecurityLevel.none)
+    encoder = pytroy.BatchEncoder(ctx)
+    keygen = pytroy.KeyGenerator(ctx)
+    encryptor = pytroy.Encryptor(ctx, keygen.create_public_key(), keygen.secret_key())
+    decryptor = pytroy.Decryptor(ctx, keygen.secret_key())
+    ev = pytroy.Evaluator(ctx)
+    auto_keys = keygen.create_automorphism_keys()
+    rng = np.random.default_rng(n)
+    coeffs = [int(v) for v in rng.integers(0, t, n)]
+    ct = encryptor.encrypt(encoder.encode_polynomial(coeffs))
+
+    def dec(c):
+        return encoder.decode_polynomial(decryptor.decrypt(c))
+    # X^a * X^b = X^(a+b), and the shift is the negacyclic one
+    s = ev.negacyclic_shift(ct, 5)
+    got = dec(s)
+    assert got[5:] == coeffs[:n - 5] and got[:5] == [(t - v) % t for v in coeffs[n - 5:]]
+    ev.negacyclic_shift_inplace(s, 2 * n - 5)
+    assert dec(s) == coeffs
+    # one coefficient out as an LWE sample and back in at another position
+    term = n // 2 + 7
+    lwe = ev.extract_lwe(ct, term)
+    assert lwe.poly_modulus_degree() == n and lwe.coeff_modulus_size() == 2
+    assert dec(ev.assemble_lwe(lwe, 0))[0] == coeffs[term]
+    assert dec(ev.assemble_lwe(lwe.copy(), 9))[9] == coeffs[term]
+    # field trace down to the constant coefficient: N * c_0
+    tr = ct.copy()
+    ev.field_trace_inplace(tr, auto_keys, 0)
+    got = dec(tr)
+    assert got[0] == coeffs[0] * n % t and not any(got[1:])
+    # 18 LWE samples packed into one ciphertext: coefficient i * N / 32 carries sample i
+    count = 18
+    cts = [encryptor.encrypt(encoder.encode_polynomial([int(v) for v in rng.integers(0, t, n)])) for _ in range(count)]
+    want = [dec(c)[0] for c in cts]
+    packed = ev.pack_lwe_ciphertexts([ev.extract_lwe(c, 0) for c in cts], auto_keys)
+    got = dec(packed)
+    step = n // 32
+    for i in range(count):
+        assert got[i * step] == want[i], i
+    assert not any(got[i] for i in range(n) if i % step)

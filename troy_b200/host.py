@@ -1091,10 +1091,32 @@ class EvaluatorCuda:
                 _L().call("troyb_ntt_inverse", self._h(), ct.parms_id, _vp(ct.ptr(0, b)), ct.size, self._s())
         ct.is_ntt_form = False
 
+    def negacyclic_shift(self, ct, shift):
+        """src/evaluator_cuda.cu:2185-2205: ct * X^shift modulo X^N + 1 (coefficient form), a new ciphertext; shift in [0, 2N)."""
+        if ct.is_ntt_form:
+            raise TroyInvalidArgument("encrypted is in NTT form")
+        self._own(ct)
+        out = CiphertextCuda(self.context, ct.parms_id, ct.size, False, ct.scale, ct.correction_factor, ct.batch, ct.size,
+                             stream=self.stream)
+        for b in range(ct.batch):
+            _L().call("troyb_negacyclic_shift", self._h(), ct.parms_id, _vp(ct.ptr(0, b)), _vp(out.ptr(0, b)), ct.size,
+                      C.c_uint64(int(shift)), self._s())
+        return out
+
+    def divide_by_poly_modulus_degree_inplace(self, ct, mul=1):
+        """src/evaluator_cuda.cu:2262-2275: every word times N^-1 (then times ``mul``) modulo its limb's prime."""
+        self._own(ct)
+        for b in range(ct.batch):
+            _L().call("troyb_multiply_inv_degree", self._h(), ct.parms_id, _vp(ct.ptr(0, b)), _vp(ct.ptr(0, b)), ct.size, self._s())
+            if mul > 1:
+                _L().call("troyb_multiply_scalar", self._h(), ct.parms_id, _vp(ct.ptr(0, b)), C.c_uint64(int(mul)), _vp(ct.ptr(0, b)),
+                          ct.size, self._s())
+
     def synchronize(self):
         _L().call("troyb_stream_synchronize", self._s())
 
     # camelCase aliases matching the reference's spelling
+    negacyclicShift, divideByPolyModulusDegreeInplace = negacyclic_shift, divide_by_poly_modulus_degree_inplace
     negateInplace, addInplace, subInplace = negate_inplace, add_inplace, sub_inplace
     multiplyInplace, squareInplace, relinearizeInplace = multiply_inplace, square_inplace, relinearize_inplace
     applyGaloisInplace, rotateRowsInplace, rotateColumnsInplace = apply_galois_inplace, rotate_rows_inplace, rotate_columns_inplace
