@@ -400,3 +400,37 @@ def run_lwe_kernels_flow(ref, tb, scheme, n, bits):
             for k in range(2):
                 for l, q in enumerate(mods):
                     assert np.array_equal(got[b, k, l], ref.multiply_inv_degree(n, int(q), w[b, k, l])), (level, b, k, l)
+
+
+def run_extreme_keyswitch_flow(ref, tb, scheme, n, bits, rng):
+    """Relinearisation with every key word and every ciphertext word at its extreme (p - 1 everywhere; then p - 1 against random
+    and alternating 0 / p - 1): the inner product's accumulators (ColumnAcc and the 40-bit SmallAcc with its FP64 quotient
+    estimate) are sized for exactly these sums. Compared word for word with the reference, like every other flow."""
+    rc, ctx = make_pair(ref, tb, scheme, n, bits)
+    rc.keygen()
+    rlk = rc.relin_keys()
+    kq = np.array(rc.level_moduli(-1), dtype=np.uint64)
+    mods = np.array(rc.level_moduli(0), dtype=np.uint64)
+    shape = rlk.words(0).shape  # [digit][2][key limbs][N]
+    ev = tb.EvaluatorCuda(ctx)
+    ntt = scheme == ref.CKKS
+    sc = 2.0 ** 40 if ntt else 1.0
+    top = np.broadcast_to((kq - np.uint64(1))[None, None, :, None], shape)
+    ct_top = np.broadcast_to((mods - np.uint64(1))[None, :, None], (3, len(mods), n))
+    alt = (np.arange(n) & 1).astype(np.uint64)
+    cases = [("all p - 1", top, ct_top),
+             ("keys p - 1, random ciphertext", top, random_ct_words(rc, 0, 3, n, rng)),
+             ("random keys, ciphertext p - 1", None, ct_top),
+             ("alternating", top * alt[None, None, None, :], ct_top * (np.uint64(1) - alt)[None, None, :] + ct_top * alt[None, None, :])]
+    for what, kw, cw in cases:
+        if kw is None:
+            kw = np.stack([np.stack([np.stack([rng.integers(0, int(m), n, dtype=np.uint64) for m in kq]) for _ in range(2)])
+                           for _ in range(shape[0])])
+        kw = np.ascontiguousarray(kw, dtype=np.uint64)
+        cw = np.ascontiguousarray(cw, dtype=np.uint64)
+        rlk.set_words(0, kw)
+        d_rlk = tb.RelinKeysCuda.from_host(ctx, {0: kw})
+        a, ra = tb.CiphertextCuda.from_host(ctx, cw, 0, ntt, sc), rc.ciphertext(cw, 0, ntt, sc)
+        ev.relinearize_inplace(a, d_rlk)
+        rc.eval(ref.OP_RELIN, ra, keys=rlk)
+        assert_same(a, ra, f"relinearize, {what} [scheme {scheme}, N {n}]")

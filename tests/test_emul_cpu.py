@@ -129,3 +129,9 @@ def test_encryptor_error_behaviour_emulated(ref, emul_lib):
 def test_negacyclic_shift_and_divide_by_degree_emulated(ref, emul_lib, scheme, n, bits):
     from common import run_lwe_kernels_flow
     run_lwe_kernels_flow(ref, emul_lib, scheme, n, bits)
+
+
+@pytest.mark.parametrize("scheme,n,bits", [(2, 1024, [40] * 8 + [60]), (1, 512, [60] + [40] * 7 + [60]), (2, 2048, [30, 40, 36, 50]), (3, 512, [40] * 9)])
+def test_keyswitch_with_extreme_operands_emulated(ref, emul_lib, scheme, n, bits):
+    from common import run_extreme_keyswitch_flow
+    run_extreme_keyswitch_flow(ref, emul_lib, scheme, n, bits, np.random.default_rng(7))

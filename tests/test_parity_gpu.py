@@ -342,3 +342,10 @@ def test_negacyclic_shift_and_divide_by_degree(ref, cuda_lib, scheme, n, bits):
     word for word against the reference's CPU statements."""
     from common import run_lwe_kernels_flow
     run_lwe_kernels_flow(ref, cuda_lib, scheme, n, bits)
+
+
+@pytest.mark.parametrize("scheme,n,bits", [(2, 16384, [60] + [40] * 7 + [60]), (1, 8192, [40] * 8 + [60]), (3, 4096, [40] * 9), (2, 4096, [30, 40, 36, 50])])
+def test_keyswitch_with_extreme_operands(ref, cuda_lib, scheme, n, bits):
+    """All key and ciphertext words at p - 1 (and mixed extremes): the bounds of the inner product's accumulators."""
+    from common import run_extreme_keyswitch_flow
+    run_extreme_keyswitch_flow(ref, cuda_lib, scheme, n, bits, np.random.default_rng(7))

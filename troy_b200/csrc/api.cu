@@ -260,9 +260,14 @@ bool switch_key_partial(Context *ctx, int level, const u64 *target, u64 target_s
             // key slices staged in shared memory, digits in groups of at most 8, partial sums added up in prod
             const u64 units = (u64)nb * Lp * (N / kStagedCoeffs);
             const u32 bc = (u32)std::min<u64>(16, std::max<u64>(1, units / ((u64)ctx->sm_count * 3 * 8)));
-            const u32 grid = (u32)(N / kStagedCoeffs) * Lp * ((nb + bc - 1) / bc);
+            // rows (output moduli) whose prime has at most 40 bits take the short-accumulator form (SmallAcc), the others the
+            // general one: two launches over disjoint row lists
+            static const bool use_small = [] { const char *e = getenv("TROYB_IP_SMALL"); return !(e && e[0] == '0'); }();
+            std::vector<uint8_t> rows_small, rows_big;
+            for (u32 i = 0; i < Lp; i++)
+                ((use_small && (ctx->h_mods[kmap.idx[i]].p >> 40) == 0) ? rows_small : rows_big).push_back((uint8_t)i);
             for (u32 g0 = 0; g0 < nd; g0 += kStagedMaxDigits) {
-                auto launch = [&](auto k) {
+                auto launch = [&](auto k, const std::vector<uint8_t> &rows) {
                     k.logN = ctx->logN;
                     k.mods = ctx->d_mods;
                     k.map = kmap;
@@ -283,17 +288,35 @@ bool switch_key_partial(Context *ctx, int level, const u64 *target, u64 target_s
                     k.prod_limb_stride = pl.limb_stride;
                     k.pass = ckks ? tgt : nullptr;
                     k.pass_stride = target_stride;
+                    k.n_rows = (u32)rows.size();
+                    std::copy(rows.begin(), rows.end(), k.rows);
+                    const u32 grid = (u32)(N / kStagedCoeffs) * k.n_rows * ((nb + bc - 1) / bc);
                     ck(launch_cta(k, grid, decltype(k)::smem_bytes(), s));
                 };
-                switch (std::min(kStagedMaxDigits, nd - g0)) {
-                case 1: launch(KsInnerProductStaged<1>{}); break;
-                case 2: launch(KsInnerProductStaged<2>{}); break;
-                case 3: launch(KsInnerProductStaged<3>{}); break;
-                case 4: launch(KsInnerProductStaged<4>{}); break;
-                case 5: launch(KsInnerProductStaged<5>{}); break;
-                case 6: launch(KsInnerProductStaged<6>{}); break;
-                case 7: launch(KsInnerProductStaged<7>{}); break;
-                default: launch(KsInnerProductStaged<8>{}); break;
+                const u32 ndg = std::min(kStagedMaxDigits, nd - g0);
+                if (!rows_big.empty()) {
+                    switch (ndg) {
+                    case 1: launch(KsInnerProductStaged<1>{}, rows_big); break;
+                    case 2: launch(KsInnerProductStaged<2>{}, rows_big); break;
+                    case 3: launch(KsInnerProductStaged<3>{}, rows_big); break;
+                    case 4: launch(KsInnerProductStaged<4>{}, rows_big); break;
+                    case 5: launch(KsInnerProductStaged<5>{}, rows_big); break;
+                    case 6: launch(KsInnerProductStaged<6>{}, rows_big); break;
+                    case 7: launch(KsInnerProductStaged<7>{}, rows_big); break;
+                    default: launch(KsInnerProductStaged<8>{}, rows_big); break;
+                    }
+                }
+                if (!rows_small.empty()) {
+                    switch (ndg) {
+                    case 1: launch(KsInnerProductStaged<1, true>{}, rows_small); break;
+                    case 2: launch(KsInnerProductStaged<2, true>{}, rows_small); break;
+                    case 3: launch(KsInnerProductStaged<3, true>{}, rows_small); break;
+                    case 4: launch(KsInnerProductStaged<4, true>{}, rows_small); break;
+                    case 5: launch(KsInnerProductStaged<5, true>{}, rows_small); break;
+                    case 6: launch(KsInnerProductStaged<6, true>{}, rows_small); break;
+                    case 7: launch(KsInnerProductStaged<7, true>{}, rows_small); break;
+                    default: launch(KsInnerProductStaged<8, true>{}, rows_small); break;
+                    }
                 }
             }
         } else {

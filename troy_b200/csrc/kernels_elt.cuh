@@ -269,6 +269,55 @@ struct XLimbs {
     }
 };
 
+// The same sum for primes of at most 40 bits (x, k < 2^40), at most nine terms: x is cut into 20-bit halves xa, xb and k into its
+// 32-bit low word k0 and the 8-bit rest k1, so that
+//   ca = sum xa*k0 (< 9 * 2^52), ca1 = sum xa*k1 (< 9 * 2^28, ONE 32-bit register), cb, cb1 likewise for xb,
+//   value = Sa + Sb 2^20,  Sa = ca + ca1 2^32 < 2^64,  Sb = cb + cb1 2^32 < 2^64:
+// two wide and two 32-bit multiply-adds per term, six registers of state (the general form: five wide ones and ten), no fold.
+// The remainder is taken with a quotient estimated in FP64: value < 2^85 and p > 2^39 give q < 2^46, the estimate
+// trunc((Sa + Sb 2^20)~ * (1/p)~) carries a relative error below 2^-51, i.e. less than 2^-5 in absolute terms, so it is q - 1, q or
+// q + 1 and value - estimate * p, computed modulo 2^64, lies in [-p, 2p): two corrections give the canonical residue.
+struct SmallAcc {
+    static constexpr u32 kMaxTerms = 9;
+    u64 ca, cb;
+    u32 ca1, cb1;
+    TB_D void mac_first(u32 xa, u32 xb, u64 k) {
+        const u32 k0 = (u32)k, k1 = (u32)(k >> 32);
+        ca = ColumnAcc::mulw(xa, k0);
+        cb = ColumnAcc::mulw(xb, k0);
+        ca1 = xa * k1;
+        cb1 = xb * k1;
+    }
+    TB_D void mac(u32 xa, u32 xb, u64 k) {
+        const u32 k0 = (u32)k, k1 = (u32)(k >> 32);
+        ColumnAcc::madw(ca, xa, k0);
+        ColumnAcc::madw(cb, xb, k0);
+        ca1 += xa * k1;
+        cb1 += xb * k1;
+    }
+    TB_D u64 reduce(u64 p, double pinv) const {
+        const u64 sa = ca + ((u64)ca1 << 32), sb = cb + ((u64)cb1 << 32);
+#if defined(TROYB_HOST_EMUL)
+        const double v = __builtin_fma((double)sb, 1048576.0, (double)sa);
+        const u64 q = (u64)(v * pinv);
+#else
+        const double v = __fma_rn(__ull2double_rn(sb), 1048576.0, __ull2double_rn(sa));
+        const u64 q = __double2ull_rz(__dmul_rn(v, pinv));
+#endif
+        u64 r = sa + (sb << 20) - q * p;
+        if ((long long)r < 0) r += p;
+        return r - (r >= p ? p : 0);
+    }
+};
+// the 20-bit halves of a residue below 2^40
+struct XHalves {
+    u32 xa, xb;
+    TB_D explicit XHalves(u64 x) {
+        xa = (u32)x & 0xFFFFFu;
+        xb = (u32)(x >> 20);
+    }
+};
+
 struct KsInnerProduct {
     static constexpr int kThreads = kEltThreads;
     const char *name() const { return "ks_inner_product"; }
@@ -348,12 +397,16 @@ struct KsInnerProduct {
 // batch elements (ND is a template parameter so that the digit loops unroll without guards). The key's L2 -> SM traffic (twice the size of D when every ciphertext fetches it again) drops by bc,
 // and for keys larger than the L2 (N = 65536, 40 limbs) so does its HBM traffic.
 //   accumulate : add the previous contents of prod (launches over successive digit groups of one key switch)
-template <int ND> struct KsInnerProductStaged {
+//   SMALL      : every row of the launch has a prime of at most 40 bits (SmallAcc); the rows of a launch are listed in `rows`
+template <int ND, bool SMALL = false> struct KsInnerProductStaged {
     static constexpr int kThreads = kEltThreads;
-    static constexpr int kMinCtas = 2; // up to 128 registers: two batch elements' rows plus twenty 64-bit columns
+    static constexpr int kMinCtas = 2; // up to 128 registers: a batch element's rows in flight plus the accumulators. The 40-bit form at three CTAs
+                                       // (80 registers) spills and measures slower than the general form (0.806 against 0.767 ms), at two it takes 0.624 ms
     static constexpr u32 kCoeffs = 2 * kEltThreads; // per CTA
-    static_assert(ND >= 1 && ND <= (int)ColumnAcc::kFoldEvery, "one fold per launch");
+    static_assert(ND >= 1 && ND <= (int)ColumnAcc::kFoldEvery && ND + 1 <= (int)SmallAcc::kMaxTerms, "one fold per launch");
     const char *name() const { return "ks_inner_product"; }
+    u32 n_rows;           // output moduli of this launch ...
+    uint8_t rows[kMaxLimbs + 1]; // ... and which (i == L: the special prime)
     int logN;
     const ModDev *mods;
     LimbMap map;
@@ -368,11 +421,11 @@ template <int ND> struct KsInnerProductStaged {
     const u64 *pass;
     u64 pass_stride;
     static size_t smem_bytes() { return (size_t)ND * 2 * kCoeffs * sizeof(u64); }
-    // grid = (N / kCoeffs) * (L + 1) * ceil(batch / bc), coefficient block fastest
+    // grid = (N / kCoeffs) * n_rows * ceil(batch / bc), coefficient block fastest
     TB_D void operator()(u32 bid, u64 *sm) const {
         const u64 N = u64(1) << logN;
         const u32 blocks = (u32)(N / kCoeffs);
-        const u32 cb = bid % blocks, i = (bid / blocks) % (L + 1), bg = bid / blocks / (L + 1);
+        const u32 cb = bid % blocks, i = rows[(bid / blocks) % n_rows], bg = bid / blocks / n_rows;
         const u32 key_limb = (i == L) ? special_key_limb : i;
         const u64 key_digit_stride = 2ull * key_limbs * N, key_comp_stride = (u64)key_limbs * N;
         const u64 *kp = key + (u64)key_limb * N + (u64)cb * kCoeffs + (u64)digit0 * key_digit_stride;
@@ -386,6 +439,8 @@ template <int ND> struct KsInnerProductStaged {
             const ModDev &m = mods[map.idx[i]];
             const u64 p = m.p, mu = m.bar_mu;
             const u32 sh = m.bar_shift;
+            const double pinv = m.pinv_d; // SMALL
+            (void)mu; (void)sh; (void)pinv;
             const u64 c = (u64)cb * kCoeffs + 2 * t;
             // digit i of output modulus i < L is the NTT-form target itself (pass): its row of D is never written or read
             const u32 jpass = (pass != nullptr && i < L && i >= digit0 && i - digit0 < ND) ? i - digit0 : 0xFFFFFFFFu;
@@ -413,42 +468,79 @@ template <int ND> struct KsInnerProductStaged {
                     old0 = *reinterpret_cast<const ulonglong2 *>(po);
                     old1 = *reinterpret_cast<const ulonglong2 *>(po + prod_poly_stride);
                 }
-                ColumnAcc a0, a1, a2, a3;
-                _Pragma("unroll") for (u32 j = 0; j < ND; j++) {
-                    const ulonglong2 cur = x[j];
-                    if (more && j != jpass) x[j] = *reinterpret_cast<const ulonglong2 *>(d + d_stride + (u64)j * N);
-                    const ulonglong2 k0 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * j) * kCoeffs + 2 * t);
-                    const ulonglong2 k1 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * j + 1) * kCoeffs + 2 * t);
-                    const XLimbs xa(cur.x), xb(cur.y);
-                    if (j == 0) {
-                        a0.mac_first(xa.xl, xa.xh, xa.x0, xa.x1, k0.x);
-                        a1.mac_first(xb.xl, xb.xh, xb.x0, xb.x1, k0.y);
-                        a2.mac_first(xa.xl, xa.xh, xa.x0, xa.x1, k1.x);
-                        a3.mac_first(xb.xl, xb.xh, xb.x0, xb.x1, k1.y);
-                    } else {
+                ulonglong2 q0, q1;
+                if constexpr (SMALL) {
+                    SmallAcc a0, a1, a2, a3;
+                    _Pragma("unroll") for (u32 j = 0; j < ND; j++) {
+                        const ulonglong2 cur = x[j];
+                        if (more && j != jpass) x[j] = *reinterpret_cast<const ulonglong2 *>(d + d_stride + (u64)j * N);
+                        const ulonglong2 k0 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * j) * kCoeffs + 2 * t);
+                        const ulonglong2 k1 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * j + 1) * kCoeffs + 2 * t);
+                        const XHalves xa(cur.x), xb(cur.y);
+                        if (j == 0) {
+                            a0.mac_first(xa.xa, xa.xb, k0.x);
+                            a1.mac_first(xb.xa, xb.xb, k0.y);
+                            a2.mac_first(xa.xa, xa.xb, k1.x);
+                            a3.mac_first(xb.xa, xb.xb, k1.y);
+                        } else {
+                            a0.mac(xa.xa, xa.xb, k0.x);
+                            a1.mac(xb.xa, xb.xb, k0.y);
+                            a2.mac(xa.xa, xa.xb, k1.x);
+                            a3.mac(xb.xa, xb.xb, k1.y);
+                        }
+                    }
+                    if (jpass != 0xFFFFFFFFu) { // CTA-uniform
+                        const ulonglong2 cur = xp;
+                        if (more) xp = *reinterpret_cast<const ulonglong2 *>(ps + pass_stride);
+                        const ulonglong2 k0 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * jpass) * kCoeffs + 2 * t);
+                        const ulonglong2 k1 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * jpass + 1) * kCoeffs + 2 * t);
+                        const XHalves xa(cur.x), xb(cur.y);
+                        a0.mac(xa.xa, xa.xb, k0.x);
+                        a1.mac(xb.xa, xb.xb, k0.y);
+                        a2.mac(xa.xa, xa.xb, k1.x);
+                        a3.mac(xb.xa, xb.xb, k1.y);
+                    }
+                    q0.x = a0.reduce(p, pinv);
+                    q0.y = a1.reduce(p, pinv);
+                    q1.x = a2.reduce(p, pinv);
+                    q1.y = a3.reduce(p, pinv);
+                } else {
+                    ColumnAcc a0, a1, a2, a3;
+                    _Pragma("unroll") for (u32 j = 0; j < ND; j++) {
+                        const ulonglong2 cur = x[j];
+                        if (more && j != jpass) x[j] = *reinterpret_cast<const ulonglong2 *>(d + d_stride + (u64)j * N);
+                        const ulonglong2 k0 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * j) * kCoeffs + 2 * t);
+                        const ulonglong2 k1 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * j + 1) * kCoeffs + 2 * t);
+                        const XLimbs xa(cur.x), xb(cur.y);
+                        if (j == 0) {
+                            a0.mac_first(xa.xl, xa.xh, xa.x0, xa.x1, k0.x);
+                            a1.mac_first(xb.xl, xb.xh, xb.x0, xb.x1, k0.y);
+                            a2.mac_first(xa.xl, xa.xh, xa.x0, xa.x1, k1.x);
+                            a3.mac_first(xb.xl, xb.xh, xb.x0, xb.x1, k1.y);
+                        } else {
+                            a0.mac(xa.xl, xa.xh, xa.x0, xa.x1, k0.x);
+                            a1.mac(xb.xl, xb.xh, xb.x0, xb.x1, k0.y);
+                            a2.mac(xa.xl, xa.xh, xa.x0, xa.x1, k1.x);
+                            a3.mac(xb.xl, xb.xh, xb.x0, xb.x1, k1.y);
+                        }
+                    }
+                    if (jpass != 0xFFFFFFFFu) { // CTA-uniform
+                        const ulonglong2 cur = xp;
+                        if (more) xp = *reinterpret_cast<const ulonglong2 *>(ps + pass_stride);
+                        const ulonglong2 k0 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * jpass) * kCoeffs + 2 * t);
+                        const ulonglong2 k1 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * jpass + 1) * kCoeffs + 2 * t);
+                        const XLimbs xa(cur.x), xb(cur.y);
                         a0.mac(xa.xl, xa.xh, xa.x0, xa.x1, k0.x);
                         a1.mac(xb.xl, xb.xh, xb.x0, xb.x1, k0.y);
                         a2.mac(xa.xl, xa.xh, xa.x0, xa.x1, k1.x);
                         a3.mac(xb.xl, xb.xh, xb.x0, xb.x1, k1.y);
                     }
+                    a0.fold(); a1.fold(); a2.fold(); a3.fold();
+                    q0.x = reduce_sum(a0.lo, a0.hi, p, mu, sh);
+                    q0.y = reduce_sum(a1.lo, a1.hi, p, mu, sh);
+                    q1.x = reduce_sum(a2.lo, a2.hi, p, mu, sh);
+                    q1.y = reduce_sum(a3.lo, a3.hi, p, mu, sh);
                 }
-                if (jpass != 0xFFFFFFFFu) { // CTA-uniform
-                    const ulonglong2 cur = xp;
-                    if (more) xp = *reinterpret_cast<const ulonglong2 *>(ps + pass_stride);
-                    const ulonglong2 k0 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * jpass) * kCoeffs + 2 * t);
-                    const ulonglong2 k1 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * jpass + 1) * kCoeffs + 2 * t);
-                    const XLimbs xa(cur.x), xb(cur.y);
-                    a0.mac(xa.xl, xa.xh, xa.x0, xa.x1, k0.x);
-                    a1.mac(xb.xl, xb.xh, xb.x0, xb.x1, k0.y);
-                    a2.mac(xa.xl, xa.xh, xa.x0, xa.x1, k1.x);
-                    a3.mac(xb.xl, xb.xh, xb.x0, xb.x1, k1.y);
-                }
-                a0.fold(); a1.fold(); a2.fold(); a3.fold();
-                ulonglong2 q0, q1;
-                q0.x = reduce_sum(a0.lo, a0.hi, p, mu, sh);
-                q0.y = reduce_sum(a1.lo, a1.hi, p, mu, sh);
-                q1.x = reduce_sum(a2.lo, a2.hi, p, mu, sh);
-                q1.y = reduce_sum(a3.lo, a3.hi, p, mu, sh);
                 if (accumulate) {
                     q0.x = addmod(q0.x, old0.x, p); q0.y = addmod(q0.y, old0.y, p);
                     q1.x = addmod(q1.x, old1.x, p); q1.y = addmod(q1.y, old1.y, p);
