@@ -258,6 +258,8 @@ bool switch_key_partial(Context *ctx, int level, const u64 *target, u64 target_s
         }
         if (N >= kStagedCoeffs) {
             // key slices staged in shared memory, digits in groups of at most 8, partial sums added up in prod
+            // batch elements per CTA (each CTA stages its key slice once), from the size of the whole product; sized per launch instead,
+            // the two-row launch of the 60-bit primes gets four elements per CTA and the pair measures 0.634 instead of 0.624 ms
             const u64 units = (u64)nb * Lp * (N / kStagedCoeffs);
             const u32 bc = (u32)std::min<u64>(16, std::max<u64>(1, units / ((u64)ctx->sm_count * 3 * 8)));
             // rows (output moduli) whose prime has at most 40 bits take the short-accumulator form (SmallAcc), the others the

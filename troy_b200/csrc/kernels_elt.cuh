@@ -106,6 +106,75 @@ struct EltNegacyclicShift {
     }
 };
 
+// c = a * b and c += a * b as ONE 32 x 32 -> 64 multiply(-add) with a 64-bit addend. Written as PTX on the GPU so that the accumulators
+// stay 64-bit register pairs (the compiler otherwise splits them into halves and adds the zero initial value separately).
+TB_D void madw_u32(u64 &c, u32 a, u32 b) {
+#if defined(TROYB_HOST_EMUL)
+    c += (u64)a * b;
+#else
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c) : "r"(a), "r"(b));
+#endif
+}
+TB_D u64 mulw_u32(u32 a, u32 b) {
+#if defined(TROYB_HOST_EMUL)
+    return (u64)a * b;
+#else
+    u64 c;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(c) : "r"(a), "r"(b));
+    return c;
+#endif
+}
+
+// A sum of at most nine products x * k of residues modulo a prime of at most 40 bits (x, k < 2^40; the general form of such sums is
+// ColumnAcc below): x is cut into 20-bit halves xa, xb and k into its
+// 32-bit low word k0 and the 8-bit rest k1, so that
+//   ca = sum xa*k0 (< 9 * 2^52), ca1 = sum xa*k1 (< 9 * 2^28, ONE 32-bit register), cb, cb1 likewise for xb,
+//   value = Sa + Sb 2^20,  Sa = ca + ca1 2^32 < 2^64,  Sb = cb + cb1 2^32 < 2^64:
+// two wide and two 32-bit multiply-adds per term, six registers of state (the general form: five wide ones and ten), no fold.
+// The remainder is taken with a quotient estimated in FP64: value < 2^85 and p > 2^39 give q < 2^46, the estimate
+// trunc((Sa + Sb 2^20)~ * (1/p)~) carries a relative error below 2^-51, i.e. less than 2^-5 in absolute terms, so it is q - 1, q or
+// q + 1 and value - estimate * p, computed modulo 2^64, lies in [-p, 2p): two corrections give the canonical residue.
+struct SmallAcc {
+    static constexpr u32 kMaxTerms = 9;
+    u64 ca, cb;
+    u32 ca1, cb1;
+    TB_D void mac_first(u32 xa, u32 xb, u64 k) {
+        const u32 k0 = (u32)k, k1 = (u32)(k >> 32);
+        ca = mulw_u32(xa, k0);
+        cb = mulw_u32(xb, k0);
+        ca1 = xa * k1;
+        cb1 = xb * k1;
+    }
+    TB_D void mac(u32 xa, u32 xb, u64 k) {
+        const u32 k0 = (u32)k, k1 = (u32)(k >> 32);
+        madw_u32(ca, xa, k0);
+        madw_u32(cb, xb, k0);
+        ca1 += xa * k1;
+        cb1 += xb * k1;
+    }
+    TB_D u64 reduce(u64 p, double pinv) const {
+        const u64 sa = ca + ((u64)ca1 << 32), sb = cb + ((u64)cb1 << 32);
+#if defined(TROYB_HOST_EMUL)
+        const double v = __builtin_fma((double)sb, 1048576.0, (double)sa);
+        const u64 q = (u64)(v * pinv);
+#else
+        const double v = __fma_rn(__ull2double_rn(sb), 1048576.0, __ull2double_rn(sa));
+        const u64 q = __double2ull_rz(__dmul_rn(v, pinv));
+#endif
+        u64 r = sa + (sb << 20) - q * p;
+        if ((long long)r < 0) r += p;
+        return r - (r >= p ? p : 0);
+    }
+};
+// the 20-bit halves of a residue below 2^40
+struct XHalves {
+    u32 xa, xb;
+    TB_D explicit XHalves(u64 x) {
+        xa = (u32)x & 0xFFFFFu;
+        xb = (u32)(x >> 20);
+    }
+};
+
 // ---- ciphertext tensor product ----------------------------------------------------------------------------
 // gDyadicConvolutionCoeffmod / kDyadicSquareCoeffmod  src/kernelutils.cu:89-199 ; ckksMultiply src/evaluator_cuda.cu:384-433
 // out[i] = sum_{j+k=i} a[j]*b[k] mod q, one pass, 128-bit accumulation + one Barrett-128 per output word.
@@ -142,7 +211,31 @@ struct EltTensor {
                 const u64 *pa = a + bt * a_batch_stride + rem;
                 const u64 *pb = b + bt * b_batch_stride + rem;
                 u64 *po = out + bt * out_batch_stride + rem;
-                if (a_size == 2 && b_size == 2) {
+                if (a_size == 2 && b_size == 2 && (p >> 40) == 0) {
+                    // primes of at most 40 bits (CTA-uniform: a CTA stays inside one limb for N >= 512, and the result does not depend
+                    // on the form taken): 20-bit halves of a, short accumulators, FP64 quotient estimate (SmallAcc)
+                    const ulonglong2 a0 = ld2(pa), a1 = ld2(pa + per_batch), b0 = ld2(pb), b1 = ld2(pb + per_batch);
+                    const double pinv = m.pinv_d;
+                    const XHalves a0x(a0.x), a0y(a0.y), a1x(a1.x), a1y(a1.y);
+                    SmallAcc s;
+                    s.mac_first(a0x.xa, a0x.xb, b0.x);
+                    const u64 c0x = s.reduce(p, pinv);
+                    s.mac_first(a0y.xa, a0y.xb, b0.y);
+                    const u64 c0y = s.reduce(p, pinv);
+                    s.mac_first(a0x.xa, a0x.xb, b1.x);
+                    s.mac(a1x.xa, a1x.xb, b0.x);
+                    const u64 c1x = s.reduce(p, pinv);
+                    s.mac_first(a0y.xa, a0y.xb, b1.y);
+                    s.mac(a1y.xa, a1y.xb, b0.y);
+                    const u64 c1y = s.reduce(p, pinv);
+                    s.mac_first(a1x.xa, a1x.xb, b1.x);
+                    const u64 c2x = s.reduce(p, pinv);
+                    s.mac_first(a1y.xa, a1y.xb, b1.y);
+                    const u64 c2y = s.reduce(p, pinv);
+                    st2(po, c0x, c0y);
+                    st2(po + per_batch, c1x, c1y);
+                    st2(po + 2 * per_batch, c2x, c2y);
+                } else if (a_size == 2 && b_size == 2) {
                     const ulonglong2 a0 = ld2(pa), a1 = ld2(pa + per_batch), b0 = ld2(pb), b1 = ld2(pb + per_batch);
                     // residues below p < 2^61: sums of at most two products are below 2^(n+63) (reduce_sum)
                     u64 lo, hi;
@@ -200,24 +293,8 @@ struct ColumnAcc {
     u64 c0l, c0h, c1a, c1b, c2;
     u64 lo, hi; // folded 128-bit sum
     TB_D void init() { c0l = c0h = c1a = c1b = c2 = 0; lo = hi = 0; }
-    // c += a * b as ONE multiply-add with a 64-bit addend. Written as PTX on the GPU so that the accumulators stay
-    // 64-bit register pairs (the compiler otherwise splits them into halves and adds the zero initial value separately).
-    static TB_D void madw(u64 &c, u32 a, u32 b) {
-#if defined(TROYB_HOST_EMUL)
-        c += (u64)a * b;
-#else
-        asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c) : "r"(a), "r"(b));
-#endif
-    }
-    static TB_D u64 mulw(u32 a, u32 b) {
-#if defined(TROYB_HOST_EMUL)
-        return (u64)a * b;
-#else
-        u64 c;
-        asm("mul.wide.u32 %0, %1, %2;" : "=l"(c) : "r"(a), "r"(b));
-        return c;
-#endif
-    }
+    static TB_D void madw(u64 &c, u32 a, u32 b) { madw_u32(c, a, b); }
+    static TB_D u64 mulw(u32 a, u32 b) { return mulw_u32(a, b); }
     // first term: plain products, no addend
     TB_D void mac_first(u32 xl, u32 xh, u32 x0, u32 x1, u64 k) {
         const u32 k0 = (u32)k, k1 = (u32)(k >> 32);
@@ -266,55 +343,6 @@ struct XLimbs {
         xl = __byte_perm(x0, 0, 0x4410); // one PRMT each
         xh = __byte_perm(x0, 0, 0x4432);
 #endif
-    }
-};
-
-// The same sum for primes of at most 40 bits (x, k < 2^40), at most nine terms: x is cut into 20-bit halves xa, xb and k into its
-// 32-bit low word k0 and the 8-bit rest k1, so that
-//   ca = sum xa*k0 (< 9 * 2^52), ca1 = sum xa*k1 (< 9 * 2^28, ONE 32-bit register), cb, cb1 likewise for xb,
-//   value = Sa + Sb 2^20,  Sa = ca + ca1 2^32 < 2^64,  Sb = cb + cb1 2^32 < 2^64:
-// two wide and two 32-bit multiply-adds per term, six registers of state (the general form: five wide ones and ten), no fold.
-// The remainder is taken with a quotient estimated in FP64: value < 2^85 and p > 2^39 give q < 2^46, the estimate
-// trunc((Sa + Sb 2^20)~ * (1/p)~) carries a relative error below 2^-51, i.e. less than 2^-5 in absolute terms, so it is q - 1, q or
-// q + 1 and value - estimate * p, computed modulo 2^64, lies in [-p, 2p): two corrections give the canonical residue.
-struct SmallAcc {
-    static constexpr u32 kMaxTerms = 9;
-    u64 ca, cb;
-    u32 ca1, cb1;
-    TB_D void mac_first(u32 xa, u32 xb, u64 k) {
-        const u32 k0 = (u32)k, k1 = (u32)(k >> 32);
-        ca = ColumnAcc::mulw(xa, k0);
-        cb = ColumnAcc::mulw(xb, k0);
-        ca1 = xa * k1;
-        cb1 = xb * k1;
-    }
-    TB_D void mac(u32 xa, u32 xb, u64 k) {
-        const u32 k0 = (u32)k, k1 = (u32)(k >> 32);
-        ColumnAcc::madw(ca, xa, k0);
-        ColumnAcc::madw(cb, xb, k0);
-        ca1 += xa * k1;
-        cb1 += xb * k1;
-    }
-    TB_D u64 reduce(u64 p, double pinv) const {
-        const u64 sa = ca + ((u64)ca1 << 32), sb = cb + ((u64)cb1 << 32);
-#if defined(TROYB_HOST_EMUL)
-        const double v = __builtin_fma((double)sb, 1048576.0, (double)sa);
-        const u64 q = (u64)(v * pinv);
-#else
-        const double v = __fma_rn(__ull2double_rn(sb), 1048576.0, __ull2double_rn(sa));
-        const u64 q = __double2ull_rz(__dmul_rn(v, pinv));
-#endif
-        u64 r = sa + (sb << 20) - q * p;
-        if ((long long)r < 0) r += p;
-        return r - (r >= p ? p : 0);
-    }
-};
-// the 20-bit halves of a residue below 2^40
-struct XHalves {
-    u32 xa, xb;
-    TB_D explicit XHalves(u64 x) {
-        xa = (u32)x & 0xFFFFFu;
-        xb = (u32)(x >> 20);
     }
 };
 
