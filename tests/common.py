@@ -200,7 +200,7 @@ def run_plain_flow(ref, tb, scheme, n, bits, rng, batch=2, level=0):
     check("multiply_plain (NTT form)")
 
 
-def run_matmul_flow(ref, tb, n, bits, rng, B=3, I=3, J=3, level=0):
+def run_matmul_flow(ref, tb, n, bits, rng, B=3, I=3, J=3, level=0, extreme=False):
     """MatmulHelper::matmul (app/LinearHelperCKKS.cuh:225-249) on random NTT-form operands: the one-launch product against
     the reference's own loop of multiplyPlain + addInplace, every word."""
     rc, ctx = make_pair(ref, tb, ref.CKKS, n, bits)
@@ -209,6 +209,10 @@ def run_matmul_flow(ref, tb, n, bits, rng, B=3, I=3, J=3, level=0):
     mods = rc.level_moduli(level)
     x = random_ct_words(rc, level, 2, n, rng, B * I)
     w = np.stack([np.stack([rng.integers(0, m, n, dtype=np.uint64) for m in mods]) for _ in range(I * J)])
+    if extreme:  # every operand word at p - 1: the accumulators' bounds
+        top = np.array(mods, dtype=np.uint64) - np.uint64(1)
+        x = np.ascontiguousarray(np.broadcast_to(top[None, None, :, None], x.shape))
+        w = np.ascontiguousarray(np.broadcast_to(top[None, :, None], w.shape))
     helper = tb.MatmulHelper(B, 1, 1, n // 2)
     helper.grid = (I, J)  # operands are synthetic: only the grid shape matters here
     a = tb.Cipher2d(B, I, tb.CiphertextCuda.from_host(ctx, x, level, True, sc))

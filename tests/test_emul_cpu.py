@@ -40,6 +40,8 @@ def test_matmul_emulated(ref, emul_lib):
     """The one-launch HE matmul against the reference's multiplyPlain + addInplace loop; odd grids hit the edge tiles."""
     run_matmul_flow(ref, emul_lib, 256, [40, 30, 30, 40], np.random.default_rng(41), B=3, I=3, J=3)
     run_matmul_flow(ref, emul_lib, 4096, [60, 40, 60], np.random.default_rng(42), B=2, I=40, J=1, level=1)
+    run_matmul_flow(ref, emul_lib, 1024, [40, 40, 36, 60], np.random.default_rng(43), B=3, I=21, J=2)
+    run_matmul_flow(ref, emul_lib, 512, [60, 40, 40, 60], np.random.default_rng(44), B=2, I=19, J=3, extreme=True)
 
 
 def test_matmul_block_layout():

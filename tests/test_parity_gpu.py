@@ -153,6 +153,9 @@ def test_matmul(ref, cuda_lib):
     run_matmul_flow(ref, cuda_lib, 16384, [60, 40, 40, 40, 60], np.random.default_rng(51), B=3, I=5, J=3)
     run_matmul_flow(ref, cuda_lib, 65536, [60, 50, 60], np.random.default_rng(52), B=2, I=2, J=4, level=1)
     run_matmul_flow(ref, cuda_lib, 4096, [60, 40, 60], np.random.default_rng(53), B=1, I=70, J=1)
+    # long sums on 40-bit limbs (short accumulators renewed every eight terms), random and with every word at p - 1
+    run_matmul_flow(ref, cuda_lib, 8192, [40, 40, 36, 60], np.random.default_rng(54), B=3, I=21, J=2)
+    run_matmul_flow(ref, cuda_lib, 4096, [60, 40, 40, 60], np.random.default_rng(55), B=2, I=19, J=3, extreme=True)
 
 
 # ---- committed golden fixtures (generated from the reference by tests/golden/make_golden.py) ----------------------

@@ -7,7 +7,7 @@ pick() { python - "$1" <<'PY'
 import json,sys
 d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 k=[(x["kernel"],x["launches"],round(x["ms"],4)) for x in d.get("kernels",[])]
-print(sys.argv[1], round(d["value"],1), round(d["ms_per_step"],4), k)
+print(sys.argv[1], round(d["value"],1), round(d["ms_per_step"],4), k, d.get("matmul",{}).get("ms"), d.get("rescale",{}).get("value"))
 PY
 }
 timeout 300 python bench.py --no-cpu-baseline --no-sweep > $OUT/base.json 2> $OUT/base.err; pick $OUT/base.json

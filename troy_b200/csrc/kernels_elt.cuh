@@ -145,6 +145,12 @@ struct SmallAcc {
         ca1 = xa * k1;
         cb1 = xb * k1;
     }
+    TB_D void zero() { ca = cb = 0; ca1 = cb1 = 0; }
+    // long sums: after eight terms the sum is replaced by its residue (which counts as one term)
+    TB_D void renew(u64 p, double pinv) {
+        ca = reduce(p, pinv);
+        cb = 0; ca1 = cb1 = 0;
+    }
     TB_D void mac(u32 xa, u32 xb, u64 k) {
         const u32 k0 = (u32)k, k1 = (u32)(k >> 32);
         madw_u32(ca, xa, k0);
@@ -611,8 +617,18 @@ struct EltMulPlain {
                 const u32 sh = m.bar_shift;
                 const ulonglong2 x = EltTensor::ld2(ct + b * ct_stride + rem);
                 const ulonglong2 w = EltTensor::ld2(plain + b * plain_stride + in_poly);
-                u64 r0 = reduce_sum(x.x * w.x, mulhi64(x.x, w.x), p, mu, sh);
-                u64 r1 = reduce_sum(x.y * w.y, mulhi64(x.y, w.y), p, mu, sh);
+                u64 r0, r1;
+                if ((p >> 40) == 0) { // SmallAcc: see the tensor product
+                    const XHalves xx(x.x), xy(x.y);
+                    SmallAcc s;
+                    s.mac_first(xx.xa, xx.xb, w.x);
+                    r0 = s.reduce(p, m.pinv_d);
+                    s.mac_first(xy.xa, xy.xb, w.y);
+                    r1 = s.reduce(p, m.pinv_d);
+                } else {
+                    r0 = reduce_sum(x.x * w.x, mulhi64(x.x, w.x), p, mu, sh);
+                    r1 = reduce_sum(x.y * w.y, mulhi64(x.y, w.y), p, mu, sh);
+                }
                 u64 *po = out + b * out_stride + rem;
                 if (accumulate) {
                     const ulonglong2 o = EltTensor::ld2(po);
@@ -634,7 +650,7 @@ struct EltMulPlain {
 // products and modular additions yields.
 struct EltMatmulPlain {
     static constexpr int kThreads = kEltThreads;
-    static constexpr int kMinCtas = 3;
+    static constexpr int kMinCtas = 2;
     const char *name() const { return "ct_matmul_plain"; }
     int logN;
     const ModDev *mods;
@@ -663,6 +679,33 @@ struct EltMatmulPlain {
                 const u64 wplain = (u64)n_limbs << logN;
                 const u64 *pa0 = a + (u64)b0 * I * a_ct_stride + off, *pa1 = a + (u64)b1 * I * a_ct_stride + off;
                 const u64 *pw0 = w + (u64)j0 * wplain + woff, *pw1 = w + (u64)j1 * wplain + woff;
+                if ((p >> 40) == 0) {
+                    // primes of at most 40 bits: short accumulators (SmallAcc), renewed every eight terms
+                    const double pinv = m.pinv_d;
+                    SmallAcc acc[2][2][2]; // [b][j][coefficient]
+                    _Pragma("unroll") for (int q = 0; q < 8; q++) (&acc[0][0][0])[q].zero();
+                    _Pragma("unroll 2") for (u32 i = 0; i < I; i++) {
+                        const ulonglong2 x0 = EltTensor::ld2(pa0 + (u64)i * a_ct_stride), x1 = EltTensor::ld2(pa1 + (u64)i * a_ct_stride);
+                        const ulonglong2 w0 = EltTensor::ld2(pw0 + (u64)i * J * wplain), w1 = EltTensor::ld2(pw1 + (u64)i * J * wplain);
+                        const XHalves x0x(x0.x), x0y(x0.y), x1x(x1.x), x1y(x1.y);
+                        acc[0][0][0].mac(x0x.xa, x0x.xb, w0.x); acc[0][0][1].mac(x0y.xa, x0y.xb, w0.y);
+                        acc[0][1][0].mac(x0x.xa, x0x.xb, w1.x); acc[0][1][1].mac(x0y.xa, x0y.xb, w1.y);
+                        acc[1][0][0].mac(x1x.xa, x1x.xb, w0.x); acc[1][0][1].mac(x1y.xa, x1y.xb, w0.y);
+                        acc[1][1][0].mac(x1x.xa, x1x.xb, w1.x); acc[1][1][1].mac(x1y.xa, x1y.xb, w1.y);
+                        if ((i & 7) == 7) {
+                            _Pragma("unroll") for (int q = 0; q < 8; q++) (&acc[0][0][0])[q].renew(p, pinv);
+                        }
+                    }
+                    _Pragma("unroll") for (int bb = 0; bb < 2; bb++) {
+                        _Pragma("unroll") for (int jj = 0; jj < 2; jj++) {
+                            const u32 b = bb ? b0 + 1 : b0, j = jj ? j0 + 1 : j0;
+                            if (b < B && j < J) {
+                                EltTensor::st2(out + ((u64)b * J + j) * out_ct_stride + off, acc[bb][jj][0].reduce(p, pinv),
+                                               acc[bb][jj][1].reduce(p, pinv));
+                            }
+                        }
+                    }
+                } else {
                 u64 lo[2][2][2], hi[2][2][2]; // [b][j][coefficient]
                 _Pragma("unroll") for (int q = 0; q < 8; q++) { (&lo[0][0][0])[q] = 0; (&hi[0][0][0])[q] = 0; }
                 _Pragma("unroll 2") for (u32 i = 0; i < I; i++) {
@@ -689,6 +732,7 @@ struct EltMatmulPlain {
                         }
                     }
                 }
+                } // general form
             }
         })
     }
