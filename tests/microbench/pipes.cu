@@ -29,6 +29,22 @@ template <int KIND> __global__ void __launch_bounds__(1024) k(uint64_t *out, lon
             if (KIND == 7) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(1.0000001), "d"(1e-12));
             if (KIND == 8) asm volatile("add.u64 %0, %0, %1;" : "+l"(w[i]) : "l"((uint64_t)b << 31 | c));
             if (KIND == 9) asm volatile("{.reg .pred p; setp.ge.u64 p, %0, %1; @p sub.u64 %0, %0, %1;}" : "+l"(w[i]) : "l"((uint64_t)b << 31 | c));
+            // rounding a double to an integer-valued double (FRND): which pipe, and does it overlap with DFMA?
+            if (KIND == 10) asm volatile("cvt.rni.f64.f64 %0, %0;" : "+d"(d[i]));
+            // the FP64 butterfly's quotient step two ways, 8 FP64-class instructions per chain step:
+            //   11: seven DFMA + one FRND (q = rint(h * pinv));  12: eight DFMA (q = fma(h, pinv, MAGIC) - MAGIC)
+            if (KIND == 11) {
+                asm volatile("fma.rn.f64 %0, %0, %1, %2;\n\tfma.rn.f64 %0, %0, %1, %2;\n\tfma.rn.f64 %0, %0, %1, %2;\n\tcvt.rni.f64.f64 %0, %0;\n\t"
+                             "fma.rn.f64 %0, %0, %1, %2;\n\tfma.rn.f64 %0, %0, %1, %2;\n\tfma.rn.f64 %0, %0, %1, %2;\n\tfma.rn.f64 %0, %0, %1, %2;"
+                             : "+d"(d[i]) : "d"(1.0000001), "d"(1e-12));
+            }
+            if (KIND == 12) {
+                asm volatile("fma.rn.f64 %0, %0, %1, %2;\n\tfma.rn.f64 %0, %0, %1, %2;\n\tfma.rn.f64 %0, %0, %1, %2;\n\tfma.rn.f64 %0, %0, %1, %2;\n\t"
+                             "fma.rn.f64 %0, %0, %1, %2;\n\tfma.rn.f64 %0, %0, %1, %2;\n\tfma.rn.f64 %0, %0, %1, %2;\n\tfma.rn.f64 %0, %0, %1, %2;"
+                             : "+d"(d[i]) : "d"(1.0000001), "d"(1e-12));
+            }
+            // the conversions of SmallAcc::reduce
+            if (KIND == 13) asm volatile("{.reg .f64 t; cvt.rn.f64.u64 t, %0; cvt.rzi.u64.f64 %0, t;}" : "+l"(w[i]));
         }
     }
     long long t1 = clock64();
@@ -72,5 +88,9 @@ int main() {
     run<7>("dfma", sms, out, cyc);
     run<8>("add.u64", sms, out, cyc);
     run<9>("cond_sub.u64", sms, out, cyc);
+    run<10>("cvt.rni.f64.f64", sms, out, cyc);
+    run<11>("7 dfma + 1 cvt.rni per step (count: steps)", sms, out, cyc);
+    run<12>("8 dfma per step (count: steps)", sms, out, cyc);
+    run<13>("cvt.f64.u64 + cvt.u64.f64 (count: pairs)", sms, out, cyc);
     return 0;
 }

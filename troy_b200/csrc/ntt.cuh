@@ -239,8 +239,20 @@ template <bool COMPACT> struct ArithF64T {
     }
     static TB_D elem from_bits(u64 v) { return __longlong_as_double((long long)v); }
     static TB_D u64 to_bits(elem x) { return (u64)__double_as_longlong(x); }
+    // rint(a * b), the quotient estimate. Two forms: the 1.5 * 2^52 trick (one FMA and one add, both on the FP64 pipe), or a
+    // multiply and FRND.F64 (TROYB_F64_FRND: the rounding leaves the FP64 pipe; the product is rounded once more before the
+    // rounding to an integer, 2^-12 at most for quotients below 2^41, inside the error bounds stated above).
+    static TB_D double rint_mul(double a, double b) {
+#if defined(TROYB_F64_FRND) && !defined(TROYB_HOST_EMUL)
+        double r;
+        asm("cvt.rni.f64.f64 %0, %1;" : "=d"(r) : "d"(__dmul_rn(a, b)));
+        return r;
+#else
+        return __dadd_rn(__fma_rn(a, b, kMagic), -kMagic);
+#endif
+    }
     static TB_D void reduce(elem &x, const Mod &m) {
-        double q = __dadd_rn(__fma_rn(x, m.pinv, kMagic), -kMagic);
+        double q = rint_mul(x, m.pinv);
         x = __fma_rn(-q, m.p, x);
     }
     static TB_D u64 canon_reduced(elem x, const Mod &m) { // |x| < p (a mulmod result)
@@ -255,8 +267,8 @@ template <bool COMPACT> struct ArithF64T {
         double h = __dmul_rn(y, t.w);
         double l = __fma_rn(y, t.w, -h);
         double q;
-        if constexpr (COMPACT) q = __dadd_rn(__fma_rn(h, m.pinv, kMagic), -kMagic);
-        else q = __dadd_rn(__fma_rn(y, t.wp, kMagic), -kMagic);
+        if constexpr (COMPACT) q = rint_mul(h, m.pinv);
+        else q = rint_mul(y, t.wp);
         double r = __fma_rn(-q, m.p, h);
         return __dadd_rn(r, l);
     }
