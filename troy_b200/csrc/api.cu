@@ -258,16 +258,14 @@ bool switch_key_partial(Context *ctx, int level, const u64 *target, u64 target_s
         }
         if (N >= kStagedCoeffs) {
             // key slices staged in shared memory, digits in groups of at most 8, partial sums added up in prod
-            // batch elements per CTA (each CTA stages its key slice once), from the size of the whole product; sized per launch instead,
-            // the two-row launch of the 60-bit primes gets four elements per CTA and the pair measures 0.634 instead of 0.624 ms
+            // batch elements per CTA (each CTA stages its key slice once): about eight waves of CTAs
             const u64 units = (u64)nb * Lp * (N / kStagedCoeffs);
             const u32 bc = (u32)std::min<u64>(16, std::max<u64>(1, units / ((u64)ctx->sm_count * 3 * 8)));
-            // rows (output moduli) whose prime has at most 40 bits take the short-accumulator form (SmallAcc), the others the
-            // general one: two launches over disjoint row lists
+            // every row (output modulus) in one launch; CTAs of rows whose prime has at most 40 bits take the short-accumulator form
+            // (SmallAcc) unless TROYB_IP_SMALL=0
             static const bool use_small = [] { const char *e = getenv("TROYB_IP_SMALL"); return !(e && e[0] == '0'); }();
-            std::vector<uint8_t> rows_small, rows_big;
-            for (u32 i = 0; i < Lp; i++)
-                ((use_small && (ctx->h_mods[kmap.idx[i]].p >> 40) == 0) ? rows_small : rows_big).push_back((uint8_t)i);
+            std::vector<uint8_t> rows_all;
+            for (u32 i = 0; i < Lp; i++) rows_all.push_back((uint8_t)i);
             for (u32 g0 = 0; g0 < nd; g0 += kStagedMaxDigits) {
                 auto launch = [&](auto k, const std::vector<uint8_t> &rows) {
                     k.logN = ctx->logN;
@@ -296,28 +294,27 @@ bool switch_key_partial(Context *ctx, int level, const u64 *target, u64 target_s
                     ck(launch_cta(k, grid, decltype(k)::smem_bytes(), s));
                 };
                 const u32 ndg = std::min(kStagedMaxDigits, nd - g0);
-                if (!rows_big.empty()) {
+                if (!use_small) {
                     switch (ndg) {
-                    case 1: launch(KsInnerProductStaged<1>{}, rows_big); break;
-                    case 2: launch(KsInnerProductStaged<2>{}, rows_big); break;
-                    case 3: launch(KsInnerProductStaged<3>{}, rows_big); break;
-                    case 4: launch(KsInnerProductStaged<4>{}, rows_big); break;
-                    case 5: launch(KsInnerProductStaged<5>{}, rows_big); break;
-                    case 6: launch(KsInnerProductStaged<6>{}, rows_big); break;
-                    case 7: launch(KsInnerProductStaged<7>{}, rows_big); break;
-                    default: launch(KsInnerProductStaged<8>{}, rows_big); break;
+                    case 1: launch(KsInnerProductStaged<1>{}, rows_all); break;
+                    case 2: launch(KsInnerProductStaged<2>{}, rows_all); break;
+                    case 3: launch(KsInnerProductStaged<3>{}, rows_all); break;
+                    case 4: launch(KsInnerProductStaged<4>{}, rows_all); break;
+                    case 5: launch(KsInnerProductStaged<5>{}, rows_all); break;
+                    case 6: launch(KsInnerProductStaged<6>{}, rows_all); break;
+                    case 7: launch(KsInnerProductStaged<7>{}, rows_all); break;
+                    default: launch(KsInnerProductStaged<8>{}, rows_all); break;
                     }
-                }
-                if (!rows_small.empty()) {
+                } else {
                     switch (ndg) {
-                    case 1: launch(KsInnerProductStaged<1, true>{}, rows_small); break;
-                    case 2: launch(KsInnerProductStaged<2, true>{}, rows_small); break;
-                    case 3: launch(KsInnerProductStaged<3, true>{}, rows_small); break;
-                    case 4: launch(KsInnerProductStaged<4, true>{}, rows_small); break;
-                    case 5: launch(KsInnerProductStaged<5, true>{}, rows_small); break;
-                    case 6: launch(KsInnerProductStaged<6, true>{}, rows_small); break;
-                    case 7: launch(KsInnerProductStaged<7, true>{}, rows_small); break;
-                    default: launch(KsInnerProductStaged<8, true>{}, rows_small); break;
+                    case 1: launch(KsInnerProductStaged<1, true>{}, rows_all); break;
+                    case 2: launch(KsInnerProductStaged<2, true>{}, rows_all); break;
+                    case 3: launch(KsInnerProductStaged<3, true>{}, rows_all); break;
+                    case 4: launch(KsInnerProductStaged<4, true>{}, rows_all); break;
+                    case 5: launch(KsInnerProductStaged<5, true>{}, rows_all); break;
+                    case 6: launch(KsInnerProductStaged<6, true>{}, rows_all); break;
+                    case 7: launch(KsInnerProductStaged<7, true>{}, rows_all); break;
+                    default: launch(KsInnerProductStaged<8, true>{}, rows_all); break;
                     }
                 }
             }

@@ -431,7 +431,9 @@ struct KsInnerProduct {
 // batch elements (ND is a template parameter so that the digit loops unroll without guards). The key's L2 -> SM traffic (twice the size of D when every ciphertext fetches it again) drops by bc,
 // and for keys larger than the L2 (N = 65536, 40 limbs) so does its HBM traffic.
 //   accumulate : add the previous contents of prod (launches over successive digit groups of one key switch)
-//   SMALL      : every row of the launch has a prime of at most 40 bits (SmallAcc); the rows of a launch are listed in `rows`
+//   SMALL      : CTAs whose row has a prime of at most 40 bits take the short-accumulator form (SmallAcc), the others the general one, in
+//                ONE launch: the ALU-bound CTAs of the 60-bit rows then share the SMs with the DRAM-bound ones of the 40-bit rows (0.593 ms;
+//                as two launches by row kind 0.624 ms). false: general form everywhere (TROYB_IP_SMALL=0). The rows of a launch are listed in `rows`
 template <int ND, bool SMALL = false> struct KsInnerProductStaged {
     static constexpr int kThreads = kEltThreads;
     static constexpr int kMinCtas = 2; // up to 128 registers: a batch element's rows in flight plus the accumulators. The 40-bit form at three CTAs
@@ -503,7 +505,7 @@ template <int ND, bool SMALL = false> struct KsInnerProductStaged {
                     old1 = *reinterpret_cast<const ulonglong2 *>(po + prod_poly_stride);
                 }
                 ulonglong2 q0, q1;
-                if constexpr (SMALL) {
+                if (SMALL && (p >> 40) == 0) { // CTA-uniform
                     SmallAcc a0, a1, a2, a3;
                     _Pragma("unroll") for (u32 j = 0; j < ND; j++) {
                         const ulonglong2 cur = x[j];
