@@ -260,7 +260,8 @@ bool switch_key_partial(Context *ctx, int level, const u64 *target, u64 target_s
             // key slices staged in shared memory, digits in groups of at most 8, partial sums added up in prod
             // batch elements per CTA (each CTA stages its key slice once): about eight waves of CTAs
             const u64 units = (u64)nb * Lp * (N / kStagedCoeffs);
-            const u32 bc = (u32)std::min<u64>(16, std::max<u64>(1, units / ((u64)ctx->sm_count * 3 * 8)));
+            static const u32 bc_max = [] { const char *e = getenv("TROYB_IP_BC"); return e ? (u32)std::max(1, atoi(e)) : 32u; }(); // cap; 4 / 8 / 16 / 32 / 64 measure 0.672 / 0.627 / 0.594 / 0.588 / 0.588 ms at the bench batch
+            const u32 bc = (u32)std::min<u64>(bc_max, std::max<u64>(1, units / ((u64)ctx->sm_count * 3 * 8)));
             // every row (output modulus) in one launch; CTAs of rows whose prime has at most 40 bits take the short-accumulator form
             // (SmallAcc) unless TROYB_IP_SMALL=0
             static const bool use_small = [] { const char *e = getenv("TROYB_IP_SMALL"); return !(e && e[0] == '0'); }();
