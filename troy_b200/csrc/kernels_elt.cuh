@@ -352,6 +352,25 @@ struct XLimbs {
     }
 };
 
+// One face for the two accumulator forms, so that a kernel writes its sum once: Form::X splits an operand, Form::Acc adds the
+// products up, finish() returns the canonical residue.
+struct GeneralForm {
+    typedef XLimbs X;
+    struct Acc : ColumnAcc {
+        TB_D void first(const X &x, u64 k) { mac_first(x.xl, x.xh, x.x0, x.x1, k); }
+        TB_D void add(const X &x, u64 k) { mac(x.xl, x.xh, x.x0, x.x1, k); }
+        TB_D u64 finish(u64 p, u64 mu, u32 sh, double) { fold(); return reduce_sum(lo, hi, p, mu, sh); }
+    };
+};
+struct SmallForm {
+    typedef XHalves X;
+    struct Acc : SmallAcc {
+        TB_D void first(const X &x, u64 k) { mac_first(x.xa, x.xb, k); }
+        TB_D void add(const X &x, u64 k) { mac(x.xa, x.xb, k); }
+        TB_D u64 finish(u64 p, u64, u32, double pinv) { return reduce(p, pinv); }
+    };
+};
+
 struct KsInnerProduct {
     static constexpr int kThreads = kEltThreads;
     const char *name() const { return "ks_inner_product"; }
@@ -505,24 +524,20 @@ template <int ND, bool SMALL = false> struct KsInnerProductStaged {
                     old1 = *reinterpret_cast<const ulonglong2 *>(po + prod_poly_stride);
                 }
                 ulonglong2 q0, q1;
-                if (SMALL && (p >> 40) == 0) { // CTA-uniform
-                    SmallAcc a0, a1, a2, a3;
+                auto sum = [&](auto form) {
+                    typedef decltype(form) Form;
+                    typedef typename Form::X X;
+                    typename Form::Acc a0, a1, a2, a3;
                     _Pragma("unroll") for (u32 j = 0; j < ND; j++) {
                         const ulonglong2 cur = x[j];
                         if (more && j != jpass) x[j] = *reinterpret_cast<const ulonglong2 *>(d + d_stride + (u64)j * N);
                         const ulonglong2 k0 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * j) * kCoeffs + 2 * t);
                         const ulonglong2 k1 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * j + 1) * kCoeffs + 2 * t);
-                        const XHalves xa(cur.x), xb(cur.y);
+                        const X xa(cur.x), xb(cur.y);
                         if (j == 0) {
-                            a0.mac_first(xa.xa, xa.xb, k0.x);
-                            a1.mac_first(xb.xa, xb.xb, k0.y);
-                            a2.mac_first(xa.xa, xa.xb, k1.x);
-                            a3.mac_first(xb.xa, xb.xb, k1.y);
+                            a0.first(xa, k0.x); a1.first(xb, k0.y); a2.first(xa, k1.x); a3.first(xb, k1.y);
                         } else {
-                            a0.mac(xa.xa, xa.xb, k0.x);
-                            a1.mac(xb.xa, xb.xb, k0.y);
-                            a2.mac(xa.xa, xa.xb, k1.x);
-                            a3.mac(xb.xa, xb.xb, k1.y);
+                            a0.add(xa, k0.x); a1.add(xb, k0.y); a2.add(xa, k1.x); a3.add(xb, k1.y);
                         }
                     }
                     if (jpass != 0xFFFFFFFFu) { // CTA-uniform
@@ -530,53 +545,16 @@ template <int ND, bool SMALL = false> struct KsInnerProductStaged {
                         if (more) xp = *reinterpret_cast<const ulonglong2 *>(ps + pass_stride);
                         const ulonglong2 k0 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * jpass) * kCoeffs + 2 * t);
                         const ulonglong2 k1 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * jpass + 1) * kCoeffs + 2 * t);
-                        const XHalves xa(cur.x), xb(cur.y);
-                        a0.mac(xa.xa, xa.xb, k0.x);
-                        a1.mac(xb.xa, xb.xb, k0.y);
-                        a2.mac(xa.xa, xa.xb, k1.x);
-                        a3.mac(xb.xa, xb.xb, k1.y);
+                        const X xa(cur.x), xb(cur.y);
+                        a0.add(xa, k0.x); a1.add(xb, k0.y); a2.add(xa, k1.x); a3.add(xb, k1.y);
                     }
-                    q0.x = a0.reduce(p, pinv);
-                    q0.y = a1.reduce(p, pinv);
-                    q1.x = a2.reduce(p, pinv);
-                    q1.y = a3.reduce(p, pinv);
-                } else {
-                    ColumnAcc a0, a1, a2, a3;
-                    _Pragma("unroll") for (u32 j = 0; j < ND; j++) {
-                        const ulonglong2 cur = x[j];
-                        if (more && j != jpass) x[j] = *reinterpret_cast<const ulonglong2 *>(d + d_stride + (u64)j * N);
-                        const ulonglong2 k0 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * j) * kCoeffs + 2 * t);
-                        const ulonglong2 k1 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * j + 1) * kCoeffs + 2 * t);
-                        const XLimbs xa(cur.x), xb(cur.y);
-                        if (j == 0) {
-                            a0.mac_first(xa.xl, xa.xh, xa.x0, xa.x1, k0.x);
-                            a1.mac_first(xb.xl, xb.xh, xb.x0, xb.x1, k0.y);
-                            a2.mac_first(xa.xl, xa.xh, xa.x0, xa.x1, k1.x);
-                            a3.mac_first(xb.xl, xb.xh, xb.x0, xb.x1, k1.y);
-                        } else {
-                            a0.mac(xa.xl, xa.xh, xa.x0, xa.x1, k0.x);
-                            a1.mac(xb.xl, xb.xh, xb.x0, xb.x1, k0.y);
-                            a2.mac(xa.xl, xa.xh, xa.x0, xa.x1, k1.x);
-                            a3.mac(xb.xl, xb.xh, xb.x0, xb.x1, k1.y);
-                        }
-                    }
-                    if (jpass != 0xFFFFFFFFu) { // CTA-uniform
-                        const ulonglong2 cur = xp;
-                        if (more) xp = *reinterpret_cast<const ulonglong2 *>(ps + pass_stride);
-                        const ulonglong2 k0 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * jpass) * kCoeffs + 2 * t);
-                        const ulonglong2 k1 = *reinterpret_cast<const ulonglong2 *>(sm + (u64)(2 * jpass + 1) * kCoeffs + 2 * t);
-                        const XLimbs xa(cur.x), xb(cur.y);
-                        a0.mac(xa.xl, xa.xh, xa.x0, xa.x1, k0.x);
-                        a1.mac(xb.xl, xb.xh, xb.x0, xb.x1, k0.y);
-                        a2.mac(xa.xl, xa.xh, xa.x0, xa.x1, k1.x);
-                        a3.mac(xb.xl, xb.xh, xb.x0, xb.x1, k1.y);
-                    }
-                    a0.fold(); a1.fold(); a2.fold(); a3.fold();
-                    q0.x = reduce_sum(a0.lo, a0.hi, p, mu, sh);
-                    q0.y = reduce_sum(a1.lo, a1.hi, p, mu, sh);
-                    q1.x = reduce_sum(a2.lo, a2.hi, p, mu, sh);
-                    q1.y = reduce_sum(a3.lo, a3.hi, p, mu, sh);
-                }
+                    q0.x = a0.finish(p, mu, sh, pinv);
+                    q0.y = a1.finish(p, mu, sh, pinv);
+                    q1.x = a2.finish(p, mu, sh, pinv);
+                    q1.y = a3.finish(p, mu, sh, pinv);
+                };
+                if (SMALL && (p >> 40) == 0) sum(SmallForm{}); // CTA-uniform
+                else sum(GeneralForm{});
                 if (accumulate) {
                     q0.x = addmod(q0.x, old0.x, p); q0.y = addmod(q0.y, old0.y, p);
                     q1.x = addmod(q1.x, old1.x, p); q1.y = addmod(q1.y, old1.y, p);
